@@ -1,0 +1,112 @@
+/*
+ * reveal_b200.h -- C-ABI of libreveal_b200.so: the B200-native index build and
+ * MUM sweeps behind the `reveallib` extension surface of jasperlinthorst/reveal.
+ *
+ * Every entry point is what the reference's extension glue would bind in place
+ * of its CPU code for this path (paths relative to the reference tree):
+ *
+ *   rv_build / rv_build_device   <- construct():  reveallib/interface.c:160-291
+ *                                   (revcomp :148-158,168-172; divsufsort :213-222;
+ *                                    inverse SA :235-238; compute_lcp :97-114,253;
+ *                                    build_SO :116-134,265-271)
+ *   rv_get_*                     <- array getters of the index type, interface.c:539-655
+ *   rv_mums_pair                 <- getmums  reveallib/reveal.c:55-116  (flavour 0)
+ *                                   getmums_rem         reveal.c:119-180 (flavour 1)
+ *   rv_mums_multi                <- getmultimums        reveal.c:436-580 + ismultimum :227-259
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a
+ * negative rv_status; rv_last_error() holds the message of the last failure on
+ * the calling thread; outputs are caller-allocated host buffers unless the name
+ * says "device".  Index entries are int32 on the device (n < 2^30); with
+ * idx_bits == 64 the getters widen to int64 / uint32 like the reference's
+ * reveallib64 build (reveallib/reveal.h:7-13) -- the numbers are the same.
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef REVEAL_B200_H
+#define REVEAL_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct rv_index rv_index; /* opaque: device-resident T, SA, SAi, LCP, SO + workspace */
+
+enum rv_status {
+    RV_OK = 0,
+    RV_ERR_ARG = -1,         /* bad argument */
+    RV_ERR_CUDA = -2,        /* CUDA runtime error (message in rv_last_error) */
+    RV_ERR_NOMEM = -3,       /* out of host or device memory */
+    RV_ERR_UNSUPPORTED = -4, /* e.g. n >= 2^30 */
+    RV_ERR_STATE = -5        /* call order (e.g. sweep before build) */
+};
+
+/* per-phase device time of the last build, CUDA events on the build stream (ms) */
+typedef struct rv_times {
+    float h2d_ms, pack_ms, sa_ms, lcp_ms, so_ms, total_ms;
+    int32_t sa_rounds;        /* prefix-doubling rounds */
+    int32_t launches;         /* kernels this library launched for the build */
+    int64_t sa_sorted_items;  /* sum over radix sorts of their item counts */
+} rv_times;
+
+const char *rv_last_error(void);
+const char *rv_version(void);
+int rv_device_count(int *count);
+int rv_set_device(int device);
+
+/* Handles.  A handle owns a grow-only device workspace that is reused by every
+ * build on it, so steady-state builds never call cudaMalloc.
+ * stream: a cudaStream_t passed as void* (NULL = a private non-blocking stream). */
+int rv_index_create(rv_index **out, void *stream);
+void rv_index_free(rv_index *idx);
+
+/* construct(): T = concatenated text of n bytes ('$' after every sequence,
+ * interface.c:71-85), nsep[k] = position of the last '$' of sample k
+ * (nsamples-1 entries, interface.c:36-43), rc = 1 reverse-complements
+ * T[nsep[0]..n) first (interface.c:168-172).  rv_build copies T from host
+ * memory; rv_build_device takes T already resident in HBM (left untouched
+ * unless rc, in which case the handle works on its own copy). */
+int rv_build(rv_index *idx, const uint8_t *T, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
+int rv_build_device(rv_index *idx, const uint8_t *dT, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
+int rv_get_times(const rv_index *idx, rv_times *out);
+int64_t rv_index_n(const rv_index *idx);
+
+/* Getters: copy an array to host memory. idx_bits 32 -> int32 entries (LCP int32),
+ * 64 -> int64 entries (LCP uint32), like reveallib / reveallib64. */
+int rv_get_sa(rv_index *idx, void *out, int32_t idx_bits);
+int rv_get_sai(rv_index *idx, void *out, int32_t idx_bits);
+int rv_get_lcp(rv_index *idx, void *out, int32_t idx_bits);
+int rv_get_so(rv_index *idx, uint16_t *out);          /* RV_ERR_STATE when nsamples <= 2 (SO is NULL in the reference) */
+int rv_get_text(rv_index *idx, uint8_t *out);         /* T as indexed (after rc) */
+/* device pointers of the resident arrays (int32 / uint16 / uint8), for callers that stay on the GPU */
+int rv_device_arrays(rv_index *idx, const uint8_t **dT, const int32_t **dSA, const int32_t **dSAi, const int32_t **dLCP, const uint16_t **dSO);
+
+/* Pair sweep over the root index.  Rows (l, a, b) as int64 triples in ascending
+ * SA rank, exactly the reference's list order.  Two-step: *_count runs the
+ * sweep and leaves the result on the device, *_fetch copies up to cap rows. */
+int rv_mums_pair_count(rv_index *idx, int32_t minl, int32_t flavour, int64_t *count);
+int rv_mums_pair_fetch(rv_index *idx, int64_t *rows, int64_t cap);
+
+/* Multi-genome sweep.  CSR result: hdr rows (l, n_members, first_member) and
+ * member rows (sample, position), list order = the reference's pop order,
+ * members in SA-rank order. */
+int rv_mums_multi_count(rv_index *idx, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
+int rv_mums_multi_fetch(rv_index *idx, int64_t *hdr, int64_t hdr_cap, int64_t *members, int64_t mem_cap);
+
+/* Sweeps over caller-supplied device arrays of a SUB-index that shares the
+ * main text (the children of reveal.c:582-664 split; RevealIndex.main): the
+ * same kernels, used by the recursion.  dSO may be NULL iff main_nsamples == 2. */
+int rv_sweep_pair_device(rv_index *ws, const uint8_t *dT, const int32_t *dSA, const int32_t *dLCP, int64_t n, int64_t nT,
+                         int64_t nsep0, int32_t rc, int32_t flavour, int32_t minl, int64_t *count);
+int rv_sweep_multi_device(rv_index *ws, const uint8_t *dT, const int32_t *dSA, const int32_t *dLCP, const uint16_t *dSO, int64_t n,
+                          int64_t nsep0, int32_t main_nsamples, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,70 @@
+// rv_internal.h -- host-side plumbing shared by the translation units of
+// libreveal_b200.so (workspace arena, error propagation, phase entry points).
+#pragma once
+#include "rv_platform.cuh"
+#include "../../include/reveal_b200.h"
+#include <stdio.h>
+#include <string.h>
+
+namespace rv {
+
+// ---- error propagation: every entry point returns 0 or a negative code -------
+// (codes: enum rv_status in include/reveal_b200.h)
+
+void set_error(const char *fmt, ...);
+
+#define RV_CUDA(call)                                                                            \
+    do {                                                                                         \
+        cudaError_t rv_e_ = (call);                                                              \
+        if (rv_e_ != cudaSuccess) {                                                              \
+            rv::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(rv_e_)); \
+            return RV_ERR_CUDA;                                                              \
+        }                                                                                        \
+    } while (0)
+#define RV_TRY(call)                 \
+    do {                             \
+        int rv_r_ = (call);          \
+        if (rv_r_ != 0) return rv_r_; \
+    } while (0)
+#define RV_KCHECK() RV_CUDA(cudaGetLastError())
+
+// ---- grow-only device workspace (bump allocator, 256-byte aligned) ------------
+// One slab per index handle: repeated builds of the same size never touch
+// cudaMalloc again, and everything a build needs is contiguous in HBM.
+struct Arena {
+    unsigned char *base = nullptr;
+    size_t cap = 0, off = 0;
+    int reserve(size_t bytes);
+    void reset() { off = 0; }
+    void release();
+    template <class T> T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        if (off + bytes > cap) return nullptr;
+        T *p = (T *)(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct PhaseTimes {  // device milliseconds (CUDA events on the build stream)
+    float pack = 0, sa = 0, lcp = 0, so = 0, total = 0;
+    int sa_rounds = 0;
+    long long sa_sorted_items = 0;  // sum over radix-sort calls of the item count
+    int launches = 0;
+};
+
+struct Stream {
+    cudaStream_t s = 0;
+    int launches = 0;  // kernels launched by this library on the stream since the last reset
+};
+
+// ---- phase entry points (each in its own .cu) ---------------------------------
+size_t sa_workspace_bytes(i64 n);
+// Builds SA and ISA (=final ranks) of the byte string dT[0..n) into dSA/dISA (int32).
+int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, PhaseTimes *pt);
+
+int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
+int so_build(Stream &st, i64 n, const i64 *dNsep, int nsamples, unsigned short *dSO);
+int revcomp_suffix(Stream &st, unsigned char *dT, i64 start, i64 n);
+
+}  // namespace rv

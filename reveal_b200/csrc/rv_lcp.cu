@@ -1,0 +1,120 @@
+// rv_lcp.cu -- barrier-aware LCP array, sample-id array and reverse complement.
+//
+// lcp_build replaces compute_lcp (reveallib/interface.c:97-114): Kasai et al.
+// with the reference's barrier rule -- the extension loop stops when the two
+// characters differ OR the character is '$' or 'N' (interface.c:107) -- so
+//   LCP[r] = min( lcp(T[SA[r-1]..], T[SA[r]..]), distance from SA[r] to the next '$'/'N' ),  LCP[0] = 0.
+// The value is order-free, so text positions are cut into chunks that run
+// Kasai's carry (h-1 is a lower bound for the next position) independently.
+// so_build replaces build_SO (interface.c:116-134); revcomp_suffix replaces
+// revcomp + comp_tab (interface.c:136-158) as used by construct (interface.c:168-172).
+#include "rv_internal.h"
+
+namespace rv {
+
+__global__ void __launch_bounds__(128) lcp_kasai_kernel(const unsigned char *__restrict__ T, i64 n, const int *__restrict__ SA,
+                                                       const int *__restrict__ ISA, int *__restrict__ LCP, int chunk) {
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 i0 = c * chunk;
+    if (i0 >= n) return;
+    i64 i1 = i0 + chunk < n ? i0 + chunk : n;
+    i64 h = 0;
+    for (i64 i = i0; i < i1; i++) {
+        int r = ISA[i];
+        if (r == 0) {
+            LCP[0] = 0;
+            h = 0;
+            continue;
+        }
+        i64 j = SA[r - 1];
+        while (i + h < n && j + h < n) {
+            unsigned char a = T[i + h];
+            if (a != T[j + h] || a == '$' || a == 'N') break;
+            h++;
+        }
+        LCP[r] = (int)h;
+        if (h > 0) h--;
+    }
+}
+
+int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP) {
+    if (n <= 0) return RV_OK;
+    // chunk length: enough threads to fill the machine, long enough to amortise the restart of h
+    i64 chunk = n / (148 * 2048);
+    if (chunk < 32) chunk = 32;
+    if (chunk > 256) chunk = 256;
+    i64 threads = (n + chunk - 1) / chunk;
+    RV_LAUNCH(lcp_kasai_kernel, (unsigned)((threads + 127) / 128), 128, 0, st.s, dT, n, dSA, dISA, dLCP, (int)chunk);
+    st.launches++;
+    RV_KCHECK();
+    return RV_OK;
+}
+
+// SO[p] = number of sample separators strictly before p  (nsep[k] = position of the last '$' of sample k)
+__global__ void __launch_bounds__(256) so_fill_kernel(i64 n, const i64 *__restrict__ nsep, int nsamples, unsigned short *__restrict__ SO) {
+    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int lo = 0, hi = nsamples - 1;  // count of k in [0,nsamples-1) with nsep[k] < p
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (nsep[mid] < p) lo = mid + 1; else hi = mid;
+    }
+    SO[p] = (unsigned short)lo;
+}
+
+int so_build(Stream &st, i64 n, const i64 *dNsep, int nsamples, unsigned short *dSO) {
+    if (n <= 0) return RV_OK;
+    RV_LAUNCH(so_fill_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, n, dNsep, nsamples, dSO);
+    st.launches++;
+    RV_KCHECK();
+    return RV_OK;
+}
+
+// IUPAC-aware complement of interface.c:136-145 as a rule (identity below '@'):
+// A<->T C<->G B<->V D<->H K<->M R<->Y in both cases, U->A, u->a, '`'->'@'.
+__device__ __forceinline__ unsigned char comp_char(unsigned char c) {
+    unsigned char up = c & 0xDFu, low = c & 0x20u;
+    bool alpha = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
+    if (c == 96) return 64;
+    if (!alpha) return c;
+    unsigned char r = up;
+    switch (up) {
+        case 'A': r = 'T'; break;
+        case 'T': r = 'A'; break;
+        case 'U': r = 'A'; break;
+        case 'C': r = 'G'; break;
+        case 'G': r = 'C'; break;
+        case 'B': r = 'V'; break;
+        case 'V': r = 'B'; break;
+        case 'D': r = 'H'; break;
+        case 'H': r = 'D'; break;
+        case 'K': r = 'M'; break;
+        case 'M': r = 'K'; break;
+        case 'R': r = 'Y'; break;
+        case 'Y': r = 'R'; break;
+        default: break;
+    }
+    return (unsigned char)(r | low);
+}
+
+__global__ void __launch_bounds__(256) revcomp_kernel(unsigned char *T, i64 start, i64 len) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 half = (len + 1) / 2;
+    if (i >= half) return;
+    i64 a = start + i, b = start + len - 1 - i;
+    unsigned char ca = comp_char(T[a]), cb = comp_char(T[b]);
+    T[a] = cb;
+    T[b] = ca;  // a == b in the middle of an odd length: both hold comp(T[a])
+}
+
+int revcomp_suffix(Stream &st, unsigned char *dT, i64 start, i64 n) {
+    i64 len = n - start;
+    if (len <= 0) return RV_OK;
+    i64 half = (len + 1) / 2;
+    RV_LAUNCH(revcomp_kernel, (unsigned)((half + 255) / 256), 256, 0, st.s, dT, start, len);
+    st.launches++;
+    RV_KCHECK();
+    return RV_OK;
+}
+
+}  // namespace rv

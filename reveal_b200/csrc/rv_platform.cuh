@@ -1,0 +1,108 @@
+// rv_platform.cuh -- one place where the kernels meet the toolchain.
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a (real CUDA).
+// Test-only build: g++ -DRV_EMU with tests/emu/cuda_emu.h, a fiber-based
+// emulation of blocks/warps used in the GPU-less container to check kernel
+// logic against the oracle (never shipped, never loaded by the product path).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef RV_EMU
+#include "cuda_emu.h"
+#define RV_LAUNCH(kern, grid, block, smem, stream, ...)                                    \
+    do {                                                                                   \
+        auto rv_k_ = kern;                                                                 \
+        emu::launch(#kern, dim3(grid), dim3(block), (size_t)(smem), [&]() { rv_k_(__VA_ARGS__); }); \
+    } while (0)
+#define RV_DYN_SMEM(T, name) T *name = (T *)emu::S().dyn_smem
+#define RV_SPIN() rv_emu_spin()
+#else
+#include <cuda_runtime.h>
+#define RV_LAUNCH(kern, grid, block, smem, stream, ...)                \
+    do {                                                               \
+        auto rv_k_ = kern;                                             \
+        rv_k_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+    } while (0)
+#define RV_DYN_SMEM(T, name)                                    \
+    extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+    T *name = (T *)name##_raw_
+#define RV_SPIN() ((void)0)
+#endif
+
+namespace rv {
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+typedef long long i64;
+
+static const unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
+
+// volatile single-word global accesses for inter-block protocols
+__device__ __forceinline__ u32 ld_volatile(const u32 *p) { return *(const volatile u32 *)p; }
+__device__ __forceinline__ void st_volatile(u32 *p, u32 v) { *(volatile u32 *)p = v; }
+
+// ---- warp / block scan helpers (warp-shuffle based) ---------------------------
+template <class T> __device__ __forceinline__ T warp_incl_sum(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T t = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ u32 warp_incl_max(u32 v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= (unsigned)d) v = v > t ? v : t;
+    }
+    return v;
+}
+
+// Block-wide scans for blocks of NT threads (NT multiple of 32, <= 1024).
+// `scratch` must hold 33 words and must not be reused by another scan without
+// a __syncthreads in between.  Returns the inclusive scan value of the calling
+// thread; *total receives the block aggregate.  Contains two __syncthreads.
+template <int NT, class T> __device__ __forceinline__ T block_incl_sum(T v, T *scratch, T *total) {
+    const int W = NT / 32;
+    T inc = warp_incl_sum(v);
+    unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T t = lane_id() < (unsigned)W ? scratch[lane_id()] : (T)0;
+        T ti = warp_incl_sum(t);
+        if (lane_id() < (unsigned)W) scratch[lane_id()] = ti - t;  // exclusive warp offsets
+        if (lane_id() == 31) scratch[32] = ti;
+    }
+    __syncthreads();
+    T r = inc + scratch[w];
+    *total = scratch[32];
+    return r;
+}
+template <int NT> __device__ __forceinline__ u32 block_incl_max(u32 v, u32 *scratch, u32 *total) {
+    const int W = NT / 32;
+    u32 inc = warp_incl_max(v);
+    unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        u32 t = lane_id() < (unsigned)W ? scratch[lane_id()] : 0u;
+        u32 ti = warp_incl_max(t);
+        u32 ex = __shfl_up_sync(FULL, ti, 1);
+        if (lane_id() == 0) ex = 0u;
+        if (lane_id() < (unsigned)W) scratch[lane_id()] = ex;  // max over the preceding warps
+        if (lane_id() == 31) scratch[32] = ti;
+    }
+    __syncthreads();
+    u32 pre = scratch[w];
+    u32 r = inc > pre ? inc : pre;
+    *total = scratch[32];
+    return r;
+}
+
+}  // namespace rv

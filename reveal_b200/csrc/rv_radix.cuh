@@ -1,0 +1,235 @@
+// rv_radix.cuh -- hand-written LSD radix sort of (key, 32-bit value) pairs for
+// sm_100a: one histogram kernel for all digit positions, then one single-pass
+// ("onesweep"-style) kernel per digit: tiles are claimed in order through an
+// atomic ticket, ranked with warp match/ballot, staged in shared memory in
+// bucket order and scattered to HBM in contiguous per-bucket runs; the
+// cross-tile bucket offsets come from a decoupled look-back over per-tile
+// (flag|count) words, so every pass reads and writes each pair exactly once.
+//
+// Replaces, together with rv_sa.cu, the reference's divsufsort() call
+// (reveallib/interface.c:213-222 -> divsufsort/divsufsort.c:333).
+#pragma once
+#include "rv_internal.h"
+
+namespace rv {
+
+static const int RS_THREADS = 256;
+static const int RS_WARPS = RS_THREADS / 32;
+static const int RS_IPT = 16;
+static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
+static const int RS_BINS = 256;
+static const int RS_MAXPASS = 8;
+
+static const u32 RS_FLAG_AGG = 1u << 30;   // tile aggregate available
+static const u32 RS_FLAG_INCL = 2u << 30;  // inclusive prefix available
+static const u32 RS_FLAG_MASK = 3u << 30;
+static const u32 RS_VAL_MASK = ~RS_FLAG_MASK;  // => item counts must stay below 2^30
+
+struct RadixPlan {
+    int npass;
+    int shift[RS_MAXPASS];
+    u32 mask[RS_MAXPASS];
+};
+
+// Digits over the bit ranges [lo0,hi0) and [lo1,hi1) of the key (second range
+// optional), each range split into the fewest <=8-bit digits of even width.
+inline RadixPlan make_plan(int lo0, int hi0, int lo1 = 0, int hi1 = 0) {
+    RadixPlan p;
+    p.npass = 0;
+    int lo[2] = {lo0, lo1}, hi[2] = {hi0, hi1};
+    for (int r = 0; r < 2; r++) {
+        int bits = hi[r] - lo[r];
+        if (bits <= 0) continue;
+        int np = (bits + 7) / 8;
+        int at = lo[r];
+        for (int k = 0; k < np; k++) {
+            int w = (bits - (at - lo[r]) + (np - k) - 1) / (np - k);
+            p.shift[p.npass] = at;
+            p.mask[p.npass] = (1u << w) - 1u;
+            p.npass++;
+            at += w;
+        }
+    }
+    return p;
+}
+
+inline size_t radix_scratch_bytes(i64 n) {
+    i64 tiles = (n + RS_TILE - 1) / RS_TILE;
+    // [hist npass*256][base npass*256][ticket 8][status npass*tiles*256]
+    return (size_t)(2 * RS_MAXPASS * RS_BINS + 8 + 32) * 4 + (size_t)RS_MAXPASS * tiles * RS_BINS * 4 + 512;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT *__restrict__ keys, i64 n, RadixPlan plan, u32 *__restrict__ ghist) {
+    __shared__ u32 sh[RS_MAXPASS * RS_BINS];
+    for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    i64 stride = (i64)gridDim.x * RS_THREADS;
+    for (i64 i = (i64)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+        KeyT k = keys[i];
+        for (int p = 0; p < plan.npass; p++) {
+            u32 d = (u32)(k >> plan.shift[p]) & plan.mask[p];
+            atomicAdd(&sh[p * RS_BINS + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) {
+        u32 c = sh[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// one block per pass: exclusive scan of the 256 bucket counts
+__global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict__ ghist, u32 *__restrict__ gbase) {
+    __shared__ u32 scratch[33];
+    u32 c = ghist[blockIdx.x * RS_BINS + threadIdx.x];
+    u32 total;
+    u32 inc = block_incl_sum<RS_BINS>(c, scratch, &total);
+    gbase[blockIdx.x * RS_BINS + threadIdx.x] = inc - c;
+}
+
+template <typename KeyT, bool HAS_VAL>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin, u32 *__restrict__ vout,
+               i64 n, int shift, u32 mask, const u32 *__restrict__ gbase, u32 *status, u32 *ticket) {
+    __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> per-warp exclusive offsets
+    __shared__ u32 s_start[RS_BINS];             // first tile-local slot of each bucket
+    __shared__ u32 s_off[RS_BINS];               // global slot of a bucket's first item minus s_start (mod 2^32)
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_tile;
+    RV_DYN_SMEM(unsigned char, smem);
+    KeyT *s_keys = (KeyT *)smem;
+    u32 *s_vals = (u32 *)(smem + (size_t)RS_TILE * sizeof(KeyT));
+
+    const unsigned tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const i64 base = (i64)tile * RS_TILE;
+    const int cnt = (int)((n - base) < (i64)RS_TILE ? (n - base) : (i64)RS_TILE);
+
+    // ---- load (warp-striped: a warp owns 32*IPT consecutive pairs) and rank ----
+    KeyT key[RS_IPT];
+    unsigned short rnk[RS_IPT];
+    const int wbase = (int)w * 32 * RS_IPT;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; k++) {
+        int idx = wbase + k * 32 + (int)l;
+        key[k] = idx < cnt ? kin[base + idx] : (KeyT)0;
+    }
+    u32 *wh = s_whist + w * RS_BINS;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; k++) {
+        int idx = wbase + k * 32 + (int)l;
+        bool valid = idx < cnt;
+        u32 d = (u32)(key[k] >> shift) & mask;
+        unsigned peers = __match_any_sync(FULL, valid ? d : 0xffffu);
+        int leader = __ffs((int)peers) - 1;
+        u32 old = 0;
+        if (valid && (int)l == leader) {
+            old = wh[d];
+            wh[d] = old + (u32)__popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rnk[k] = (unsigned short)(old + (u32)__popc(peers & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-bucket: warp offsets, tile count, tile-local start, look-back ----
+    {
+        const u32 d = tid;  // RS_THREADS == RS_BINS
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            u32 t = s_whist[ww * RS_BINS + d];
+            s_whist[ww * RS_BINS + d] = run;
+            run += t;
+        }
+        u32 total;
+        u32 inc = block_incl_sum<RS_THREADS>(run, s_scan, &total);
+        u32 start = inc - run;
+        s_start[d] = start;
+        u32 excl = 0;
+        u32 *my = status + (size_t)tile * RS_BINS + d;
+        if (tile > 0) {
+            st_volatile(my, RS_FLAG_AGG | run);
+            for (i64 t = (i64)tile - 1;; t--) {
+                const u32 *q = status + (size_t)t * RS_BINS + d;
+                u32 v;
+                while (((v = ld_volatile(q)) & RS_FLAG_MASK) == 0u) { RV_SPIN(); }
+                excl += v & RS_VAL_MASK;
+                if ((v & RS_FLAG_MASK) == RS_FLAG_INCL) break;
+            }
+        }
+        st_volatile(my, RS_FLAG_INCL | (excl + run));
+        s_off[d] = gbase[d] + excl - start;
+    }
+    __syncthreads();
+
+    // ---- stage the tile in bucket order, then scatter contiguous runs ----------
+#pragma unroll
+    for (int k = 0; k < RS_IPT; k++) {
+        int idx = wbase + k * 32 + (int)l;
+        if (idx < cnt) {
+            u32 d = (u32)(key[k] >> shift) & mask;
+            u32 p = s_start[d] + wh[d] + rnk[k];
+            s_keys[p] = key[k];
+            if (HAS_VAL) s_vals[p] = vin[base + idx];
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < cnt; p += RS_THREADS) {
+        KeyT kk = s_keys[p];
+        u32 d = (u32)(kk >> shift) & mask;
+        u32 dst = s_off[d] + (u32)p;
+        kout[dst] = kk;
+        if (HAS_VAL) vout[dst] = s_vals[p];
+    }
+}
+
+// Sorts n pairs by the digits of `plan` (least significant first), ping-ponging
+// between (k0,v0) and (k1,v1).  On return *result_in_0 tells where the sorted
+// pairs are.  `scratch` needs radix_scratch_bytes(n).  Stable.
+template <typename KeyT>
+int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, const RadixPlan &plan, void *scratch, bool *result_in_0) {
+    *result_in_0 = true;
+    if (n <= 1 || plan.npass == 0) return RV_OK;
+    if (n >= (i64)1 << 30) {
+        set_error("radix_sort_pairs: n=%lld exceeds the 2^30 look-back word limit", (long long)n);
+        return RV_ERR_UNSUPPORTED;
+    }
+    const i64 tiles = (n + RS_TILE - 1) / RS_TILE;
+    u32 *ghist = (u32 *)scratch;
+    u32 *gbase = ghist + RS_MAXPASS * RS_BINS;
+    u32 *ticket = gbase + RS_MAXPASS * RS_BINS;
+    u32 *status = ticket + 32;
+    size_t zero_bytes = (size_t)(2 * RS_MAXPASS * RS_BINS + 32) * 4 + (size_t)plan.npass * tiles * RS_BINS * 4;
+    RV_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, st.s));
+    int hist_blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+    RV_LAUNCH((rs_hist_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st.s, k0, n, plan, ghist);
+    RV_LAUNCH(rs_scan_kernel, plan.npass, RS_BINS, 0, st.s, ghist, gbase);
+    st.launches += 2;
+    const size_t smem = (size_t)RS_TILE * (sizeof(KeyT) + 4);
+    static bool attr_done = false;
+    if (!attr_done) {
+        auto kfn = rs_pass_kernel<KeyT, true>;
+        (void)kfn;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    bool in0 = true;
+    for (int p = 0; p < plan.npass; p++) {
+        RV_LAUNCH((rs_pass_kernel<KeyT, true>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0,
+                  in0 ? v0 : v1, in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], gbase + p * RS_BINS,
+                  status + (size_t)p * tiles * RS_BINS, ticket + p);
+        st.launches++;
+        in0 = !in0;
+    }
+    RV_KCHECK();
+    *result_in_0 = in0;
+    return RV_OK;
+}
+
+}  // namespace rv

@@ -1,0 +1,35 @@
+"""Kernel LOGIC check without a GPU: the product's .cu sources compiled for the
+host with the fiber emulation of tests/emu (same C-ABI), compared bit-exactly
+with the golden vectors and the oracle.  The real parity gate is the gpu-marked
+suite; this tier exists so that indexing/scan/look-back bugs are caught here."""
+import numpy as np
+import pytest
+
+import oracle.port as P
+from conftest import golden_names, load_golden
+from util import check_against_golden, check_against_oracle, random_related
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_emu_matches_golden(emu_lib, name):
+    check_against_golden(emu_lib, load_golden(name))
+
+
+@pytest.mark.parametrize("nsamples,length,sigma,minl", [(2, 1500, 2, 4), (3, 3000, 4, 6), (2, 9000, 4, 8), (5, 2500, 3, 5)])
+def test_emu_matches_oracle_random(emu_lib, nsamples, length, sigma, minl):
+    rng = np.random.default_rng(nsamples * 1000 + length)
+    T, nsep, _ = P.assemble(random_related(rng, nsamples, length, sigma))
+    check_against_oracle(emu_lib, T, nsep, nsamples, minl=minl)
+
+
+def test_emu_single_sample_and_tiny(emu_lib):
+    for text in (b"A", b"AC", b"ACA", b"GATTACA"):
+        T, nsep, _ = P.assemble([[text]])
+        check_against_oracle(emu_lib, T, nsep, 1, minl=0)
+
+
+def test_emu_rc(emu_lib):
+    rng = np.random.default_rng(7)
+    s = random_related(rng, 2, 2000, 4)
+    T, nsep, _ = P.assemble(s)
+    check_against_oracle(emu_lib, T, nsep, 2, rc=1, minl=6)

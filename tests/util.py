@@ -1,0 +1,132 @@
+"""Shared helpers of the parity tests: run one build + sweeps through the C-ABI
+(any library exporting it) and through the oracle, and compare bit-exactly."""
+import ctypes
+
+import numpy as np
+
+from reveal_b200 import _native
+
+
+class NativeIndex:
+    """Thin test-side wrapper over the C-ABI handle."""
+
+    def __init__(self, L, T, nsep, nsamples, rc=0, device_ptr=None):
+        self.L = L
+        self.h = ctypes.c_void_p()
+        _native.check(L, L.rv_index_create(ctypes.byref(self.h), None))
+        self.T = np.ascontiguousarray(T, dtype=np.uint8)
+        self.n = len(self.T)
+        self.nsamples = int(nsamples)
+        ns = np.asarray(nsep, dtype=np.int64)
+        _native.check(L, L.rv_build(self.h, self.T.ctypes.data, self.n, ns.ctypes.data if len(ns) else None, self.nsamples, int(rc)))
+
+    def close(self):
+        if self.h is not None:
+            self.L.rv_index_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def arr(self, which, bits=32):
+        L = self.L
+        if which == "SO":
+            a = np.empty(self.n, np.uint16)
+            _native.check(L, L.rv_get_so(self.h, a.ctypes.data))
+            return a
+        if which == "T":
+            a = np.empty(self.n, np.uint8)
+            _native.check(L, L.rv_get_text(self.h, a.ctypes.data))
+            return a
+        if which == "LCP":
+            a = np.empty(self.n, np.uint32 if bits == 64 else np.int32)
+            _native.check(L, L.rv_get_lcp(self.h, a.ctypes.data, bits))
+            return a
+        a = np.empty(self.n, np.int64 if bits == 64 else np.int32)
+        _native.check(L, (L.rv_get_sa if which == "SA" else L.rv_get_sai)(self.h, a.ctypes.data, bits))
+        return a
+
+    def mums(self, minl, flavour=0):
+        L = self.L
+        c = ctypes.c_int64()
+        _native.check(L, L.rv_mums_pair_count(self.h, int(minl), int(flavour), ctypes.byref(c)))
+        rows = np.empty((c.value, 3), np.int64)
+        _native.check(L, L.rv_mums_pair_fetch(self.h, rows.ctypes.data, c.value))
+        return rows
+
+    def multimums(self, minl, minn=2):
+        L = self.L
+        nr, nm = ctypes.c_int64(), ctypes.c_int64()
+        _native.check(L, L.rv_mums_multi_count(self.h, int(minl), int(minn), ctypes.byref(nr), ctypes.byref(nm)))
+        hdr = np.empty((nr.value, 3), np.int64)
+        mem = np.empty((nm.value, 2), np.int64)
+        _native.check(L, L.rv_mums_multi_fetch(self.h, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+        return hdr, mem
+
+    def times(self):
+        t = _native.Times()
+        _native.check(self.L, self.L.rv_get_times(self.h, ctypes.byref(t)))
+        return t.as_dict()
+
+
+def assert_same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    if a.size and not np.array_equal(a, b):
+        bad = np.flatnonzero((a != b).reshape(len(a), -1).any(axis=1))
+        raise AssertionError("%s: %d rows differ, first at %d: %s vs %s" % (what, len(bad), bad[0], a[bad[0]], b[bad[0]]))
+
+
+def check_against_golden(L, g):
+    """Build with library L on the golden's input and compare every array / MUM list bit-exactly."""
+    ns = int(g["nsamples"])
+    with NativeIndex(L, g["T_in"], g["nsep"], ns, rc=int(g["rc"])) as idx:
+        assert_same(idx.arr("SA"), g["SA"], "SA")
+        assert_same(idx.arr("SAi"), g["SAi"], "SAi")
+        assert_same(idx.arr("LCP"), g["LCP"], "LCP")
+        assert_same(idx.arr("T"), g["T_indexed"], "T")
+        assert_same(idx.arr("SA", 64), g["SA"].astype(np.int64), "SA64")
+        assert_same(idx.arr("LCP", 64), g["LCP"].astype(np.uint32), "LCP64")
+        assert_same(idx.mums(int(g["minl"])), g["mums"], "getmums")
+        if ns > 2:
+            assert_same(idx.arr("SO"), g["SO"], "SO")
+            hdr, mem = idx.multimums(int(g["minl"]), int(g["minn"]))
+            assert_same(hdr, g["mm_hdr"], "getmultimums hdr")
+            assert_same(mem, g["mm_mem"], "getmultimums members")
+
+
+def check_against_oracle(L, T, nsep, nsamples, rc=0, minl=5, minn=2, arrays=True):
+    """Build with library L and with the oracle port on the same input; compare bit-exactly."""
+    import oracle.port as P
+    o = P.Index(T, nsep, nsamples, rc)
+    with NativeIndex(L, T, nsep, nsamples, rc=rc) as idx:
+        if arrays:
+            assert_same(idx.arr("SA"), o.SA, "SA")
+            assert_same(idx.arr("SAi"), o.SAi, "SAi")
+            assert_same(idx.arr("LCP"), o.LCP, "LCP")
+            if nsamples > 2:
+                assert_same(idx.arr("SO"), o.SO, "SO")
+        if nsamples >= 2:
+            for fl in (0, 1):
+                assert_same(idx.mums(minl, fl), o.getmums(minl, rem=bool(fl)), "getmums flavour %d" % fl)
+        hdr, mem = idx.multimums(minl, minn)
+        oh, om = o.getmultimums(minl, minn)
+        assert_same(hdr, oh, "getmultimums hdr")
+        assert_same(mem, om, "getmultimums members")
+        return idx.times(), len(oh)
+
+
+def random_related(rng, nsamples, length, sigma=4, snp=0.02, alphabet=b"ACGT"):
+    """nsamples noisy copies of one random sequence over the first `sigma` letters."""
+    al = np.frombuffer(alphabet, np.uint8)
+    base = rng.integers(0, sigma, size=length)
+    out = []
+    for _ in range(nsamples):
+        g = base.copy()
+        m = rng.random(length) < snp
+        g[m] = rng.integers(0, sigma, size=int(m.sum()))
+        out.append([al[g].tobytes()])
+    return out
