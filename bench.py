@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bases/sec of the rem anchor phase (index build + MUM sweep).
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+construct() = suffix array + inverse + barrier-aware LCP (+ sample array), then
+the SA/LCP sweep that emits the (multi-)MUMs at the reference's `rem` defaults
+(-m 20 -n 2).  Default workload = BASELINE.json configs[1]: 2 synthetic 5 Mbp
+genomes (1 % SNP, 0.1 % indel).  "bases" = characters of the concatenated text
+(genome bases + one sentinel per sequence) that the step anchors.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): every rank builds its own independent index
+(the rem recursion / --chunksize jobs shard as independent index builds, SURVEY
+8e), MUM records are gathered to rank 0 with NCCL, nothing else crosses GPUs.
+
+`--impl reference` times the reference's own CPU implementation of the same step
+(its unmodified extension compiled into oracle/_ref: divsufsort + compute_lcp +
+getmums/getmultimums through its Python API) on the host, single-threaded like
+the reference is.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (genomes, length, description)
+    "c2": (2, 5_000_000, "2 synthetic 5 Mbp genomes (1% SNP, 0.1% indel), rem -m 20 -n 2 (BASELINE configs[1])"),
+    "c3": (5, 5_000_000, "5 synthetic 5 Mbp genomes, simultaneous rem anchor (BASELINE configs[2])"),
+    "c4": (2, 100_000_000, "2 synthetic 100 Mbp genomes (BASELINE configs[3], root build + sweep)"),
+    "tiny": (2, 200_000, "2 synthetic 200 kbp genomes (plumbing)"),
+}
+MINL, MINN = 20, 2
+METRIC = "aligned bases/sec (rem anchor phase: index build + MUM sweep)"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        threading.Thread.__init__(self, daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(name, seed):
+    from reveal_b200 import synth
+    g, length, desc = WORKLOADS[name]
+    T, nsep, ns = synth.workload(g, length, seed=seed)
+    return T, nsep, ns, desc
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU path (unmodified extension in oracle/_ref), rank 0 only."""
+    if rank != 0:
+        return
+    import oracle.ref as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference tree absent at build time)"}))
+        return
+    T, nsep, ns, desc = make_workload(args.workload, seed=1)
+    n = len(T)
+    bounds = [0] + [int(x) + 1 for x in nsep] + [n]
+    seqs = [T[bounds[k]:bounds[k + 1] - 1].tobytes().decode("ascii") for k in range(ns)]
+    m = R.module(32)
+
+    def step():
+        idx = m.index()
+        for k, s in enumerate(seqs):
+            idx.addsample("g%d" % k)
+            idx.addsequence(s)
+        t0 = time.perf_counter()
+        idx.construct()
+        mums = idx.getmums(MINL) if ns == 2 else idx.getmultimums(minlength=MINL, minn=MINN)
+        dt = time.perf_counter() - t0
+        return dt, len(mums)
+
+    for _ in range(args.warmup):
+        step()
+    times = []
+    for _ in range(args.steps):
+        dt, nm = step()
+        times.append(dt)
+    tot = sum(times)
+    value = n * args.steps / tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "bases_per_step": n, "mums_per_step": nm, "minl": MINL, "minn": MINN},
+            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": 1, "kind": "reference",
+                             "sample": "the full workload per step (construct + getmums%s through the reference extension's Python API)" % ("" if ns == 2 else "/getmultimums")},
+            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+class DevArray:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, True), "version": 2}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from reveal_b200 import _native
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _native.lib()
+    _native.check(L, L.rv_set_device(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T, nsep, ns, desc = make_workload(args.workload, seed=1 + rank)
+    n = len(T)
+    nsep = np.ascontiguousarray(nsep, dtype=np.int64)
+    hT = torch.from_numpy(T).pin_memory()
+    dT = hT.to(dev)
+    stream = torch.cuda.Stream(device=dev)
+    h = ctypes.c_void_p()
+    _native.check(L, L.rv_index_create(ctypes.byref(h), ctypes.c_void_p(stream.cuda_stream)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    cnt = ctypes.c_int64()
+    nmem = ctypes.c_int64()
+    host_rows = torch.empty((1 << 22, 3), dtype=torch.int64).pin_memory()
+
+    def sweep():
+        if ns == 2:
+            _native.check(L, L.rv_mums_pair_count(h, MINL, 1, ctypes.byref(cnt)))
+        else:
+            _native.check(L, L.rv_mums_multi_count(h, MINL, MINN, ctypes.byref(cnt), ctypes.byref(nmem)))
+        return cnt.value
+
+    def gather_results():
+        """N > 1: MUM records of every rank to rank 0 over NCCL (the only collective on the path)."""
+        if world == 1:
+            return
+        p, k = ctypes.c_void_p(), ctypes.c_int64()
+        _native.check(L, L.rv_result_device(h, ctypes.byref(p), ctypes.byref(k), None, None))
+        mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([k.value], dtype=torch.int64, device=dev))
+        mx = int(max(int(c.item()) for c in counts))
+        pad = torch.zeros((mx, 3), dtype=torch.int64, device=dev)
+        pad[: k.value] = mine
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+
+    def step_resident():
+        _native.check(L, L.rv_build_device(h, ctypes.c_void_p(dT.data_ptr()), n, nsep.ctypes.data, ns, 0))
+        k = sweep()
+        gather_results()
+        return k
+
+    def step_e2e():
+        _native.check(L, L.rv_build(h, ctypes.c_void_p(hT.data_ptr()), n, nsep.ctypes.data, ns, 0))
+        k = sweep()
+        if ns == 2:
+            _native.check(L, L.rv_mums_pair_fetch(h, ctypes.c_void_p(host_rows.data_ptr()), min(k, host_rows.shape[0])))
+            d2h = k * 24
+        else:
+            hdr = np.empty((k, 3), np.int64)
+            mem = np.empty((nmem.value, 2), np.int64)
+            _native.check(L, L.rv_mums_multi_fetch(h, hdr.ctypes.data, k, mem.ctypes.data, nmem.value))
+            d2h = k * 24 + nmem.value * 16
+        return k, d2h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # ---- timed: device-resident input -----------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _native.check(L, L.rv_profile(h, 1))
+    prof0 = _native.KernelProfile()
+    _native.check(L, L.rv_get_profile(h, ctypes.byref(prof0)))
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict L2 between timed iterations (inputs are smaller than L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nm = step_resident()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    prof = _native.KernelProfile()
+    _native.check(L, L.rv_get_profile(h, ctypes.byref(prof)))
+    times = _native.Times()
+    _native.check(L, L.rv_get_times(h, ctypes.byref(times)))
+    _native.check(L, L.rv_profile(h, 0))
+    # ---- timed: end to end from pinned host memory through the C-ABI -----------------------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        k, d2h = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.summary() if sampler else None
+
+    tmax = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    ntot = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ntot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
+    total_bases = float(ntot[0])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = total_bases * args.steps / (dev_ms_max * 1e-3)
+        e2e_value = total_bases * args.steps / (e2e_ms_max * 1e-3)
+        launches = int(prof.launches_total - prof0.launches_total)
+        pass_gbs = (prof.pass_bytes / 1e9) / (prof.pass_ms * 1e-3) if prof.pass_ms > 0 else None
+        line = {"metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": desc, "bases_per_step_per_gpu": n, "mums_per_step": nm, "minl": MINL, "minn": MINN,
+                           "l2": "flushed between timed steps (256 MiB write)", "sharding": "independent index build per rank; NCCL gather of MUM records" if world > 1 else "single GPU"},
+                "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n + 8 * len(nsep)), "d2h_bytes_per_step": int(d2h + 32),
+                        "ms_per_step": e2e_ms_max / args.steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "rs_pass_kernel (radix-sort digit pass of the SA builder)",
+                             "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": (pass_gbs / peak) if pass_gbs else None,
+                             "peak_source": peak_src, "traffic": None,
+                             "launches": int(prof.pass_launches), "avg_launch_ms": (prof.pass_ms / prof.pass_launches) if prof.pass_launches else None,
+                             "share_of_step": (prof.pass_ms / dev_ms) if dev_ms else None,
+                             "path": {"algorithmic_bytes_per_base": 35 if ns == 2 else 39,
+                                      "achieved": (35 if ns == 2 else 39) * n * args.steps / (dev_ms * 1e-3) / 1e9, "unit": "GB/s"}},
+                "phases_ms_last_step": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in times.as_dict().items()},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(T, nsep, ns)
+        print(json.dumps(line))
+    L.rv_index_free(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(T, nsep, ns):
+    """The reference's CPU code on this host, one core (it is single-threaded on this path)."""
+    import oracle.ref as R
+    n = len(T)
+    if R.available():
+        SA, SAi, LCP, (t_sa, t_isa, t_lcp) = R.raw_build(T)
+        import oracle.port as P
+        t0 = time.perf_counter()
+        if ns == 2:
+            k = len(P.getmums(T, SA, LCP, int(nsep[0]), MINL, rem=True))
+        else:
+            SO = P.build_so(nsep, ns, n)
+            k = len(P.getmulti(T, SA, LCP, SO, int(nsep[0]), ns, MINL, MINN)[0])
+        t_sw = time.perf_counter() - t0
+        tot = t_sa + t_isa + t_lcp + t_sw
+        return {"value": n / tot, "unit": "bases/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
+                "sample": "the full workload once: reference divsufsort %.2fs + ISA %.2fs + compute_lcp %.2fs (oracle/_ref objects) + sweep %.2fs (oracle port)" % (t_sa, t_isa, t_lcp, t_sw),
+                "mums": int(k)}
+    import oracle.port as P
+    t0 = time.perf_counter()
+    o = P.Index(T, nsep, ns)
+    k = len(o.getmums(MINL, rem=True)) if ns == 2 else len(o.getmultimums(MINL, MINN)[0])
+    tot = time.perf_counter() - t0
+    return {"value": n / tot, "unit": "bases/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+            "sample": "the full workload once through the oracle port (SA-IS + Kasai + sweep)", "mums": int(k)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,19 @@ void rv_index_free(rv_index *idx);
 int rv_build(rv_index *idx, const uint8_t *T, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
 int rv_build_device(rv_index *idx, const uint8_t *dT, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
 int rv_get_times(const rv_index *idx, rv_times *out);
+
+/* Optional profile of the dominant kernel (the radix-sort pass): when enabled the
+ * library brackets every run of pass launches with CUDA events on the build
+ * stream and accumulates duration, launch count and algorithmic bytes
+ * (items x 12 B x read+write) until the next rv_profile(idx, 1) resets them. */
+typedef struct rv_kernel_profile {
+    double pass_ms;
+    int64_t pass_launches;
+    int64_t pass_bytes;
+    int64_t launches_total; /* every kernel this handle launched since creation */
+} rv_kernel_profile;
+int rv_profile(rv_index *idx, int32_t enable);
+int rv_get_profile(const rv_index *idx, rv_kernel_profile *out);
 int64_t rv_index_n(const rv_index *idx);
 
 /* Getters: copy an array to host memory. idx_bits 32 -> int32 entries (LCP int32),
@@ -94,6 +107,10 @@ int rv_mums_pair_fetch(rv_index *idx, int64_t *rows, int64_t cap);
  * members in SA-rank order. */
 int rv_mums_multi_count(rv_index *idx, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
 int rv_mums_multi_fetch(rv_index *idx, int64_t *hdr, int64_t hdr_cap, int64_t *members, int64_t mem_cap);
+
+/* Device pointers of the last sweep result (rows / hdr as int64 triples, members
+ * as int64 pairs; NULL when empty), for callers that gather over NCCL. */
+int rv_result_device(rv_index *idx, const int64_t **d_rows, int64_t *nrows, const int64_t **d_members, int64_t *nmembers);
 
 /* Sweeps over caller-supplied device arrays of a SUB-index that shares the
  * main text (the children of reveal.c:582-664 split; RevealIndex.main): the

@@ -23,6 +23,14 @@ class Times(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class KernelProfile(ctypes.Structure):
+    _fields_ = [("pass_ms", ctypes.c_double), ("pass_launches", ctypes.c_int64), ("pass_bytes", ctypes.c_int64),
+                ("launches_total", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 # every symbol include/reveal_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "rv_last_error": (ctypes.c_char_p, []),
@@ -35,6 +43,8 @@ SIGNATURES = {
     "rv_build_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_int32]),
     "rv_get_times": (ctypes.c_int, [c_vp, ctypes.POINTER(Times)]),
     "rv_index_n": (ctypes.c_int64, [c_vp]),
+    "rv_profile": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "rv_get_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(KernelProfile)]),
     "rv_get_sa": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32]),
     "rv_get_sai": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32]),
     "rv_get_lcp": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32]),
@@ -45,6 +55,7 @@ SIGNATURES = {
     "rv_mums_pair_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_mums_multi_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
     "rv_mums_multi_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
+    "rv_result_device": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i64p, ctypes.POINTER(c_vp), c_i64p]),
     "rv_sweep_pair_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_sweep_multi_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

@@ -129,6 +129,8 @@ void rv_index_free(rv_index *h) {
     h->res.release();
     for (int i = 0; i < 6; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->st.pe0) cudaEventDestroy(h->st.pe0);
+    if (h->st.pe1) cudaEventDestroy(h->st.pe1);
     if (h->own_stream) cudaStreamDestroy(h->st.s);
     delete h;
 }
@@ -167,6 +169,7 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
         return RV_ERR_NOMEM;
     }
     Stream &st = h->st;
+    st.launches_total += st.launches;
     st.launches = 0;
     PhaseTimes pt;
     RV_CUDA(cudaEventRecord(h->ev[0], st.s));
@@ -215,6 +218,27 @@ int rv_get_times(const rv_index *h, rv_times *out) {
     return RV_OK;
 }
 int64_t rv_index_n(const rv_index *h) { return h ? h->n : 0; }
+
+int rv_profile(rv_index *h, int32_t enable) {
+    if (!h) return RV_ERR_ARG;
+    if (enable && !h->st.pe0) {
+        RV_CUDA(cudaEventCreate(&h->st.pe0));
+        RV_CUDA(cudaEventCreate(&h->st.pe1));
+    }
+    h->st.prof = enable != 0;
+    h->st.pass_ms = 0;
+    h->st.pass_launches = 0;
+    h->st.pass_bytes = 0;
+    return RV_OK;
+}
+int rv_get_profile(const rv_index *h, rv_kernel_profile *out) {
+    if (!h || !out) return RV_ERR_ARG;
+    out->pass_ms = h->st.pass_ms;
+    out->pass_launches = h->st.pass_launches;
+    out->pass_bytes = h->st.pass_bytes;
+    out->launches_total = h->st.launches_total + h->st.launches;
+    return RV_OK;
+}
 
 static int need_built(const rv_index *h) {
     if (!h) { set_error("null index handle"); return RV_ERR_ARG; }
@@ -366,6 +390,15 @@ int rv_mums_multi_fetch(rv_index *h, int64_t *hdr, int64_t hdr_cap, int64_t *mem
         RV_CUDA(cudaMemcpyAsync(members, h->d_members, (size_t)m * 16, cudaMemcpyDeviceToHost, h->st.s));
     }
     RV_CUDA(cudaStreamSynchronize(h->st.s));
+    return RV_OK;
+}
+
+int rv_result_device(rv_index *h, const int64_t **d_rows, int64_t *nrows, const int64_t **d_members, int64_t *nmembers) {
+    if (!h || h->last_kind == 0) { set_error("no sweep result"); return RV_ERR_STATE; }
+    if (d_rows) *d_rows = h->last_rec ? h->d_rows : nullptr;
+    if (nrows) *nrows = h->last_rec;
+    if (d_members) *d_members = (h->last_kind == 2 && h->last_mem) ? h->d_members : nullptr;
+    if (nmembers) *nmembers = h->last_kind == 2 ? h->last_mem : 0;
     return RV_OK;
 }
 

@@ -55,7 +55,14 @@ struct PhaseTimes {  // device milliseconds (CUDA events on the build stream)
 
 struct Stream {
     cudaStream_t s = 0;
-    int launches = 0;  // kernels launched by this library on the stream since the last reset
+    int launches = 0;           // kernels launched by this library on the stream since the last reset
+    long long launches_total = 0;
+    // optional per-kernel profile of the dominant kernel (radix pass), CUDA events on this stream
+    bool prof = false;
+    cudaEvent_t pe0 = 0, pe1 = 0;
+    double pass_ms = 0;         // summed duration of rs_pass_kernel launches
+    long long pass_launches = 0;
+    long long pass_bytes = 0;   // algorithmic bytes: items * (key + value) * (read + write)
 };
 
 // ---- phase entry points (each in its own .cu) ---------------------------------

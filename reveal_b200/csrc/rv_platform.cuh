@@ -34,7 +34,7 @@ namespace rv {
 
 typedef unsigned int u32;
 typedef unsigned long long u64;
-typedef long long i64;
+typedef int64_t i64;
 
 static const unsigned FULL = 0xffffffffu;
 

@@ -1,0 +1,144 @@
+"""Parity tests proper: the sm_100a CUDA path, called through the C-ABI of
+libreveal_b200.so on a real GPU, against (1) the golden vectors minted from the
+unmodified reference, (2) the CPU oracle on the same seeded inputs, and (3) at
+BASELINE sizes through size-independent properties.  Everything is integer/byte
+work: the bar is bit-exact equality."""
+import numpy as np
+import pytest
+
+import oracle.port as P
+from conftest import golden_names, load_golden
+from reveal_b200 import synth
+from util import NativeIndex, assert_same, check_against_golden, check_against_oracle, random_related
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_golden(cuda_lib, name):
+    check_against_golden(cuda_lib, load_golden(name))
+
+
+@pytest.mark.parametrize("nsamples,length,sigma,minl", [
+    (2, 1500, 2, 4), (3, 3000, 4, 6), (2, 9000, 4, 8), (5, 2500, 3, 5),
+    (2, 300000, 4, 12), (4, 200000, 4, 12), (7, 50000, 4, 10), (2, 40000, 2, 16),
+])
+def test_cuda_matches_oracle_random(cuda_lib, nsamples, length, sigma, minl):
+    rng = np.random.default_rng(nsamples * 1000 + length)
+    T, nsep, _ = P.assemble(random_related(rng, nsamples, length, sigma))
+    check_against_oracle(cuda_lib, T, nsep, nsamples, minl=minl)
+
+
+def test_cuda_tiny_and_single_sample(cuda_lib):
+    for text in (b"A", b"AC", b"ACA", b"GATTACA", b"A" * 5000, b"AC" * 3000):
+        T, nsep, _ = P.assemble([[text]])
+        check_against_oracle(cuda_lib, T, nsep, 1, minl=0)
+
+
+def test_cuda_ragged_many_contigs(cuda_lib):
+    """Many '$' (graph inputs put one per segment), empty-ish and 1-bp contigs."""
+    rng = np.random.default_rng(11)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    base = al[rng.integers(0, 4, size=60000)].tobytes()
+    cuts = np.sort(rng.integers(0, len(base), size=400))
+    s0 = [base[a:b] for a, b in zip([0] + cuts.tolist(), cuts.tolist() + [len(base)]) if b > a]
+    mut = bytearray(base)
+    for p in rng.integers(0, len(base), size=600):
+        mut[p] = al[rng.integers(0, 4)]
+    cuts = np.sort(rng.integers(0, len(base), size=300))
+    s1 = [bytes(mut[a:b]) for a, b in zip([0] + cuts.tolist(), cuts.tolist() + [len(base)]) if b > a] + [b"A", b"C"]
+    T, nsep, _ = P.assemble([s0, s1])
+    check_against_oracle(cuda_lib, T, nsep, 2, minl=10)
+
+
+def test_cuda_rc_and_alphabets(cuda_lib):
+    rng = np.random.default_rng(7)
+    T, nsep, _ = P.assemble(random_related(rng, 2, 50000, 4))
+    check_against_oracle(cuda_lib, T, nsep, 2, rc=1, minl=10)
+    # IUPAC + N + lowercase (the reference keeps case with --noupper)
+    T, nsep, _ = P.assemble(random_related(rng, 3, 30000, 16, alphabet=b"ACGTNRYKMSWBDHVn"))
+    check_against_oracle(cuda_lib, T, nsep, 3, minl=4)
+    T, nsep, _ = P.assemble(random_related(rng, 2, 30000, 8, alphabet=b"ACGTacgt"))
+    check_against_oracle(cuda_lib, T, nsep, 2, minl=6)
+
+
+@pytest.mark.parametrize("ngenomes,length", [(2, 500000), (3, 300000)])
+def test_cuda_matches_oracle_synthetic_genomes(cuda_lib, ngenomes, length):
+    """The bench recipe (1% SNP, 0.1% indel) at a size the oracle does in a second."""
+    T, nsep, ns = synth.workload(ngenomes, length, seed=3)
+    check_against_oracle(cuda_lib, T, nsep, ns, minl=20)
+
+
+def _properties(T, nsep, ns, idx, minl):
+    n = len(T)
+    SA, SAi, LCP = idx.arr("SA"), idx.arr("SAi"), idx.arr("LCP")
+    # permutation + inverse
+    assert np.array_equal(SAi[SA], np.arange(n, dtype=np.int32))
+    # sortedness on a sample of adjacent pairs, and LCP against a direct byte comparison
+    rng = np.random.default_rng(0)
+    Tb = T.tobytes()
+    for r in rng.integers(1, n, size=4000).tolist():
+        a, b = int(SA[r - 1]), int(SA[r])
+        h = 0
+        while a + h < n and b + h < n and Tb[a + h] == Tb[b + h]:
+            h += 1
+        assert a + h == n or (b + h < n and Tb[a + h] < Tb[b + h]), "SA order violated at rank %d" % r
+        stop = h
+        for k in range(h):  # barrier rule of compute_lcp (interface.c:107)
+            if Tb[b + k] in (36, 78):
+                stop = k
+                break
+        assert int(LCP[r]) == stop, "LCP mismatch at rank %d" % r
+    # every reported MUM is an exact match, left- and right-maximal, one position per sample
+    mums = idx.mums(minl)
+    assert len(mums) > 0
+    for l, a, b in mums[:: max(1, len(mums) // 3000)].tolist():
+        assert Tb[a:a + l] == Tb[b:b + l]
+        assert a <= nsep[0] < b
+        assert a == 0 or Tb[a - 1] != Tb[b - 1] or Tb[a - 1] in (36, 78)
+        assert Tb[a + l] != Tb[b + l] or Tb[a + l] in (36, 78)
+    return mums
+
+
+def test_cuda_full_size_c2(cuda_lib):
+    """BASELINE configs[1]: 2 synthetic 5 Mbp genomes -- properties, then bit-exact vs the oracle."""
+    T, nsep, ns = synth.workload(2, 5_000_000, seed=1)
+    with NativeIndex(cuda_lib, T, nsep, ns) as idx:
+        mums = _properties(T, nsep, ns, idx, 20)
+        o = P.Index(T, nsep, ns)
+        assert_same(idx.arr("SA"), o.SA, "SA")
+        assert_same(idx.arr("LCP"), o.LCP, "LCP")
+        assert_same(mums, o.getmums(20), "getmums")
+        # idempotence: a second build on the same handle (workspace reuse) gives the same answer
+    with NativeIndex(cuda_lib, T, nsep, ns) as idx2:
+        assert_same(idx2.mums(20), mums, "getmums (rebuild)")
+
+
+def test_cuda_full_size_c3_multi(cuda_lib):
+    """BASELINE configs[2]: 5 synthetic 5 Mbp genomes, multi-MUM sweep vs the oracle."""
+    T, nsep, ns = synth.workload(5, 5_000_000, seed=1)
+    o = P.Index(T, nsep, ns)
+    with NativeIndex(cuda_lib, T, nsep, ns) as idx:
+        assert_same(idx.arr("SA"), o.SA, "SA")
+        assert_same(idx.arr("LCP"), o.LCP, "LCP")
+        assert_same(idx.arr("SO"), o.SO, "SO")
+        hdr, mem = idx.multimums(20, 2)
+        oh, om = o.getmultimums(20, 2)
+        assert_same(hdr, oh, "getmultimums hdr")
+        assert_same(mem, om, "getmultimums members")
+
+
+def test_reveallib_surface_on_gpu():
+    """The drop-in class end to end (reference test01 input, test_reveal.py:36-41)."""
+    from reveal_b200 import reveallib, reveallib64
+    for mod in (reveallib, reveallib64):
+        idx = mod.index()
+        idx.addsample("1")
+        assert idx.addsequence("ACTTGCTAGCTAGTCAG") == (0, 17)
+        idx.addsample("2")
+        assert idx.addsequence("ACTAGCTAGCTAGTGAG") == (18, 35)
+        idx.construct()
+        g = load_golden("test01_pair")
+        assert idx.SA == g["SA"].tolist() and idx.LCP == g["LCP"].tolist() and idx.SAi == g["SAi"].tolist()
+        assert idx.getmums(1) == [(l, (a, b), 0) for l, a, b in g["mums"].tolist()]
+        assert idx.nsep == [17] and idx.n == 36 and idx.nsamples == 2
