@@ -154,11 +154,12 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     h->nsamples = nsamples;
     h->rc = rc ? 1 : 0;
     h->nsep.assign(nsep, nsep + (nsamples - 1));
-    const bool own_text = !T_on_device || rc;
-    size_t need = pad256((size_t)n + 16) + 3 * pad256((size_t)n * 4) + pad256((size_t)n * 2) + pad256((size_t)nsamples * 8) + sa_workspace_bytes(n) + 4096;
+    // The handle always works on its own copy of T: 256-byte aligned and zero padded past n, which the
+    // word-wise suffix comparisons rely on (and rc rewrites the text in place, interface.c:168-172).
+    size_t need = pad256((size_t)n + 64) + 3 * pad256((size_t)n * 4) + pad256((size_t)n * 2) + pad256((size_t)nsamples * 8) + sa_workspace_bytes(n) + 4096;
     RV_TRY(h->arena.reserve(need));
     h->arena.reset();
-    unsigned char *textbuf = h->arena.take<unsigned char>((size_t)n + 16);
+    unsigned char *textbuf = h->arena.take<unsigned char>((size_t)n + 64);
     h->dSA = h->arena.take<int>(n);
     h->dISA = h->arena.take<int>(n);
     h->dLCP = h->arena.take<int>(n);
@@ -173,12 +174,9 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     st.launches = 0;
     PhaseTimes pt;
     RV_CUDA(cudaEventRecord(h->ev[0], st.s));
-    if (own_text) {
-        RV_CUDA(cudaMemcpyAsync(textbuf, T, (size_t)n, T_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st.s));
-        h->dT = textbuf;
-    } else {
-        h->dT = (unsigned char *)T;
-    }
+    RV_CUDA(cudaMemcpyAsync(textbuf, T, (size_t)n, T_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st.s));
+    RV_CUDA(cudaMemsetAsync(textbuf + n, 0, 64, st.s));
+    h->dT = textbuf;
     if (nsamples > 1) RV_CUDA(cudaMemcpyAsync(h->dNsep, h->nsep.data(), (size_t)(nsamples - 1) * 8, cudaMemcpyHostToDevice, st.s));
     RV_CUDA(cudaEventRecord(h->ev[1], st.s));
     if (rc) RV_TRY(revcomp_suffix(st, h->dT, h->nsep[0], n));

@@ -68,16 +68,21 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ 
     keys[e] = ((u64)grp[e] << 32) | (u64)k2;
 }
 
-__device__ __forceinline__ void ap_flags(const u64 *__restrict__ keys, i64 A, i64 e, bool &head, bool &active) {
+// head: first entry of its equal-key run.  active: the run still needs doubling rounds, i.e. it has more
+// than G members (G = 1 in the doubling rounds: any tie) or the comparison kernel deferred it.
+__device__ __forceinline__ void ap_flags(const u64 *__restrict__ keys, i64 A, i64 e, int G, const unsigned char *__restrict__ deferred,
+                                         bool &head, bool &active) {
     u64 k = keys[e];
-    bool eq_prev = e > 0 && keys[e - 1] == k;
-    bool eq_next = e + 1 < A && keys[e + 1] == k;
-    head = !eq_prev;
-    active = eq_prev || eq_next;
+    int L = 0, R = 0;
+    while (L < G && e - L - 1 >= 0 && keys[e - L - 1] == k) L++;
+    while (R < G && e + R + 1 < A && keys[e + R + 1] == k) R++;
+    head = L == 0;
+    active = (L + R + 1 > G) || (deferred && L + R > 0 && deferred[e - L]);
 }
 
 // per tile: (largest slot+1 of a group head, number of entries that stay active)
-__global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, i64 A,
+__global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, i64 A, int G,
+                                                               const unsigned char *__restrict__ deferred,
                                                                u32 *__restrict__ tile_max, u32 *__restrict__ tile_cnt) {
     __shared__ u32 s1[33], s2[33];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
@@ -87,8 +92,8 @@ __global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const u64 *__rest
         i64 e = base + k;
         if (e < A) {
             bool head, active;
-            ap_flags(keys, A, e, head, active);
-            if (head) mx = (pos ? pos[e] : (u32)e) + 1u;
+            ap_flags(keys, A, e, G, deferred, head, active);
+            if (head && (active || G == 1)) mx = (pos ? pos[e] : (u32)e) + 1u;
             cnt += active ? 1u : 0u;
         }
     }
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(1024) sa_tilescan_kernel(u32 *__restrict__ til
 //   SA[slot] = suffix, rank[suffix] = slot of its group head, and append the
 //   entries of groups that still have >= 2 members to the next active list.
 __global__ void __launch_bounds__(AP_THREADS)
-sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const u32 *__restrict__ pos, i64 A,
-                const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt, int *__restrict__ SA, int *__restrict__ rank,
+sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const u32 *__restrict__ pos, i64 A, int G,
+                const unsigned char *__restrict__ deferred, const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt, int *__restrict__ SA, int *__restrict__ rank,
                 u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2) {
     __shared__ u32 s1[33], s2[33];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
@@ -147,8 +152,8 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
         act[k] = false;
         if (e < A) {
             bool head, active;
-            ap_flags(keys, A, e, head, active);
-            if (head) hp[k] = (pos ? pos[e] : (u32)e) + 1u;
+            ap_flags(keys, A, e, G, deferred, head, active);
+            if (head && (active || G == 1)) hp[k] = (pos ? pos[e] : (u32)e) + 1u;
             act[k] = active;
             cnt += active ? 1u : 0u;
         }
@@ -169,7 +174,7 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
 #pragma unroll
     for (int k = 0; k < AP_IPT; k++) {
         i64 e = base + k;
-        if (e < A) {
+        if (e < A && (act[k] || G == 1)) {  // G > 1: the other entries were finished by sa_finish_small_kernel
             u32 g = (hp[k] > pre_max ? hp[k] : pre_max) - 1u;  // slot of the group head
             u32 slot = pos ? pos[e] : (u32)e;
             u32 s = sa[e];
@@ -185,6 +190,89 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
     }
 }
 
+// ---- small groups: finish by direct suffix comparison ---------------------------------
+// After the k-mer sort nearly every group of similar genomes is a handful of homologous
+// positions whose suffixes agree for ~1/divergence characters.  One thread orders such a
+// group (<= SA_SMALL_G members) by comparing the suffixes themselves, four text bytes per
+// step through funnel-shifted aligned words, instead of log(LCP) doubling rounds over the
+// whole array.  Comparisons longer than SA_CMP_CAP bytes defer the group to the doubling
+// rounds, which bound the work for long repeats / identical sequences.
+static const int SA_SMALL_G = 16;
+static const int SA_CMP_CAP = 4096;
+
+// order of suffixes a and b (a != b) that agree on their first `skip` characters.
+// returns -1 (a < b), +1 (a > b), 0 (undecided within SA_CMP_CAP bytes).  T is 4-byte
+// aligned and readable (zero padded) up to n + 8.
+__device__ __forceinline__ int suffix_cmp(const unsigned char *__restrict__ T, i64 n, u32 a, u32 b, int skip) {
+    const u32 *__restrict__ W = (const u32 *)T;
+    i64 p = (i64)a + skip, q = (i64)b + skip;
+    i64 lenmin = (n - p) < (n - q) ? (n - p) : (n - q);  // >= 0
+    i64 ia = p >> 2, ib = q >> 2;
+    const unsigned sha = (unsigned)(p & 3) * 8u, shb = (unsigned)(q & 3) * 8u;
+    u32 lo_a = W[ia], lo_b = W[ib];
+    for (i64 h = 0; h < lenmin; h += 4) {
+        u32 hi_a = W[++ia], hi_b = W[++ib];
+        u32 wa = __funnelshift_r(lo_a, hi_a, sha), wb = __funnelshift_r(lo_b, hi_b, shb);
+        lo_a = hi_a;
+        lo_b = hi_b;
+        u32 x = wa ^ wb;
+        if (x) {
+            int byte = (__ffs((int)x) - 1) >> 3;  // first differing byte in text order (little-endian words)
+            if (h + byte >= lenmin) break;        // the difference lies past the end of the shorter suffix
+            u32 ca = (wa >> (8 * byte)) & 0xffu, cb = (wb >> (8 * byte)) & 0xffu;
+            return ca < cb ? -1 : 1;
+        }
+        if (h >= SA_CMP_CAP) return 0;
+    }
+    return p > q ? -1 : 1;  // one suffix is a proper prefix of the other: the shorter one sorts first
+}
+
+__global__ void __launch_bounds__(256)
+sa_finish_small_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T, int skip,
+                       int *__restrict__ SA, int *__restrict__ rank, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u64 key = keys[j];
+    if (j > 0 && keys[j - 1] == key) return;  // not the head of its group
+    int g = 1;
+    while (g <= SA_SMALL_G && j + g < n && keys[j + g] == key) g++;
+    if (g == 1) {
+        u32 s = sa[j];
+        SA[j] = (int)s;
+        rank[s] = (int)j;
+        return;
+    }
+    if (g > SA_SMALL_G) {
+        *flag_large = 1u;
+        return;
+    }
+    u32 ids[SA_SMALL_G];
+    ids[0] = sa[j];
+    bool undecided = false;
+    for (int t = 1; t < g; t++) {  // insertion sort; every comparison starts after the shared k-mer
+        u32 x = sa[j + t];
+        int at = t;
+        while (at > 0) {
+            int c = suffix_cmp(T, n, x, ids[at - 1], skip);
+            if (c == 0) undecided = true;
+            if (c >= 0) break;
+            ids[at] = ids[at - 1];
+            at--;
+        }
+        ids[at] = x;
+        if (undecided) break;
+    }
+    if (undecided) {
+        deferred[j] = 1;
+        *flag_large = 1u;
+        return;
+    }
+    for (int t = 0; t < g; t++) {
+        SA[j + t] = (int)ids[t];
+        rank[ids[t]] = (int)(j + t);
+    }
+}
+
 static inline int bits_for(u64 v) {  // number of bits needed to hold v
     int b = 0;
     while (v) { b++; v >>= 1; }
@@ -195,7 +283,7 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, PhaseTimes *pt) {
@@ -211,8 +299,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     const i64 tiles_n = (n + AP_TILE - 1) / AP_TILE;
     u32 *tile_max = ws.take<u32>(tiles_n), *tile_cnt = ws.take<u32>(tiles_n);
     void *rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
-    u32 *small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count
-    if (!k0 || !k1 || !v0 || !v1 || !posA || !posB || !grpA || !grpB || !tile_max || !tile_cnt || !rscratch || !small) {
+    u32 *small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "large groups exist"
+    unsigned char *deferred = ws.take<unsigned char>(n);
+    if (!deferred || !k0 || !k1 || !v0 || !v1 || !posA || !posB || !grpA || !grpB || !tile_max || !tile_cnt || !rscratch || !small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;
     }
@@ -247,7 +336,21 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     u64 *keys_alt = in0 ? k1 : k0;
     u32 *sa_alt = in0 ? v1 : v0;
 
-    // 3. first split: every suffix is "active", slot = index
+    // 3. finish singletons and small groups by direct comparison
+    RV_CUDA(cudaMemsetAsync(deferred, 0, (size_t)n, st.s));
+    RV_LAUNCH(sa_finish_small_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, keys, sa, n, dT, k, dSA, dISA, deferred, small + 257);
+    st.launches++;
+    {
+        u32 large = 0;
+        RV_CUDA(cudaMemcpyAsync(&large, small + 257, 4, cudaMemcpyDeviceToHost, st.s));
+        RV_CUDA(cudaStreamSynchronize(st.s));
+        if (!large) {
+            RV_KCHECK();
+            return RV_OK;
+        }
+    }
+
+    // 4. prefix doubling for what is left (groups of more than SA_SMALL_G suffixes, deferred groups)
     u32 *pos = nullptr, *grp = nullptr;   // current active list is (sa, pos, grp)
     u32 *pos_next = posA, *grp_next = grpA;
     i64 A = n;
@@ -255,16 +358,18 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     i64 h = k;
     for (int round = 0;; round++) {
         const i64 tiles = (A + AP_TILE - 1) / AP_TILE;
-        RV_LAUNCH(sa_reduce_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, tile_max, tile_cnt);
+        const int G = round == 0 ? SA_SMALL_G : 1;
+        const unsigned char *dfr = round == 0 ? deferred : nullptr;
+        RV_LAUNCH(sa_reduce_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, G, dfr, tile_max, tile_cnt);
         RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, tile_max, tile_cnt, tiles, small + 256);
         // the compacted entries go to the buffers not holding the current list
-        RV_LAUNCH(sa_apply_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, tile_max, tile_cnt, dSA, dISA, sa_alt, pos_next,
+        RV_LAUNCH(sa_apply_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, G, dfr, tile_max, tile_cnt, dSA, dISA, sa_alt, pos_next,
                   grp_next);
         st.launches += 3;
         u32 nactive = 0;
         RV_CUDA(cudaMemcpyAsync(&nactive, small + 256, 4, cudaMemcpyDeviceToHost, st.s));
         RV_CUDA(cudaStreamSynchronize(st.s));
-        if (pt) pt->sa_rounds = round;
+        if (pt) pt->sa_rounds = round + 1;
         if (nactive == 0) break;
         if (h >= n) {
             set_error("sa_build: internal error, %u suffixes still tied at h=%lld >= n", nactive, (long long)h);

@@ -33,3 +33,24 @@ def test_emu_rc(emu_lib):
     s = random_related(rng, 2, 2000, 4)
     T, nsep, _ = P.assemble(s)
     check_against_oracle(emu_lib, T, nsep, 2, rc=1, minl=6)
+
+
+def test_emu_long_identical_stretch_defers_to_doubling(emu_lib):
+    """Matches longer than the comparison cap (SA_CMP_CAP) must fall back to the doubling rounds."""
+    rng = np.random.default_rng(3)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    s = al[rng.integers(0, 4, size=7000)].tobytes()
+    t = bytearray(s)
+    t[6500] = ord("A") if t[6500] != ord("A") else ord("C")
+    T, nsep, _ = P.assemble([[s], [bytes(t)], [s[100:6900]]])
+    check_against_oracle(emu_lib, T, nsep, 3, minl=10)
+
+
+def test_emu_large_groups_and_small_groups_mixed(emu_lib):
+    rng = np.random.default_rng(4)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    rep = al[rng.integers(0, 4, size=60)].tobytes()
+    s0 = al[rng.integers(0, 4, size=1500)].tobytes() + rep * 25 + al[rng.integers(0, 4, size=1500)].tobytes()
+    s1 = s0[:700] + b"G" + s0[701:2000] + rep * 3 + s0[2000:]
+    T, nsep, _ = P.assemble([[s0], [s1]])
+    check_against_oracle(emu_lib, T, nsep, 2, minl=8)
