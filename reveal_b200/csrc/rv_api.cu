@@ -181,9 +181,10 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     RV_CUDA(cudaEventRecord(h->ev[1], st.s));
     if (rc) RV_TRY(revcomp_suffix(st, h->dT, h->nsep[0], n));
     RV_CUDA(cudaEventRecord(h->ev[2], st.s));
-    RV_TRY(sa_build(st, h->arena, h->dT, n, h->dSA, h->dISA, &pt));
+    bool lcp_done = false;
+    RV_TRY(sa_build(st, h->arena, h->dT, n, h->dSA, h->dISA, h->dLCP, &lcp_done, &pt));
     RV_CUDA(cudaEventRecord(h->ev[3], st.s));
-    RV_TRY(lcp_build(st, h->dT, n, h->dSA, h->dISA, h->dLCP));
+    if (!lcp_done) RV_TRY(lcp_build(st, h->dT, n, h->dSA, h->dISA, h->dLCP));
     RV_CUDA(cudaEventRecord(h->ev[4], st.s));
     if (nsamples > 2) RV_TRY(so_build(st, n, h->dNsep, nsamples, h->dSO));
     RV_CUDA(cudaEventRecord(h->ev[5], st.s));

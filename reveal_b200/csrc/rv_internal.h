@@ -67,8 +67,10 @@ struct Stream {
 
 // ---- phase entry points (each in its own .cu) ---------------------------------
 size_t sa_workspace_bytes(i64 n);
-// Builds SA and ISA (=final ranks) of the byte string dT[0..n) into dSA/dISA (int32).
-int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, PhaseTimes *pt);
+// Builds SA and ISA (=final ranks) of the byte string dT[0..n) into dSA/dISA (int32).  dT must be 8-byte
+// aligned and readable (zero padded) up to n+16.  When the comparison stage could place every suffix the
+// barrier-aware LCP array is complete as well (*lcp_done); otherwise the caller runs lcp_build.
+int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt);
 
 int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
 int so_build(Stream &st, i64 n, const i64 *dNsep, int nsamples, unsigned short *dSO);

@@ -1,30 +1,43 @@
-// rv_sa.cu -- GPU suffix-array builder (prefix doubling over radix-sorted keys).
+// rv_sa.cu -- GPU suffix-array builder: k-mer radix sort, direct comparison inside small
+// groups, prefix doubling for the rest.
 //
 // Replaces the reference's  divsufsort(T, SA, n)  (reveallib/interface.c:213-222,
-// divsufsort/divsufsort.c:333)  and the inverse fill  SAi[SA[i]] = i
-// (reveallib/interface.c:235-238).  The suffix array of a byte string is unique
-// (plain unsigned-byte lexicographic order, a suffix that is a proper prefix of
-// another sorts first), so any correct builder is bit-identical to divsufsort.
+// divsufsort/divsufsort.c:333), the inverse fill  SAi[SA[i]] = i  (interface.c:235-238)
+// and -- for every suffix the comparison stage places -- compute_lcp (interface.c:97-114).
+// The suffix array of a byte string is unique (plain unsigned-byte lexicographic order, a
+// suffix that is a proper prefix of another sorts first), so any correct builder is
+// bit-identical to divsufsort.
 //
-// Algorithm (Manber-Myers / Larsson-Sadakane doubling, GPU form):
-//   1. 256-bin histogram of T -> dense symbol codes 1..sigma (0 = past the end),
-//      b = bits per code, k = 64/b symbols fit one 64-bit key;
-//   2. key[i] = first k symbols of suffix i; radix sort (key, i);
-//   3. equal-key runs are "groups"; rank[i] = SA slot of the first member of
-//      i's group; groups of one suffix are final and leave the active list;
-//   4. round h = k, 2k, 4k...: for every active suffix i the sort key is
-//      (rank[i] : rank[i+h]+1 or 0 past the end); radix sort the active list,
-//      which permutes suffixes only inside their groups; split groups where the
-//      second half differs; write SA slots + ranks; compact the active list.
-//   When the active list is empty every rank is the suffix's final SA slot,
-//   i.e. the rank array IS the inverse suffix array.
+// Stages
+//   1. 256-bin histogram of T -> dense symbol codes 1..sigma (0 = past the end of the text).
+//   2. key[i] = first k symbols of suffix i as a base-(sigma+1) number (order preserving); k is
+//      the shortest prefix that separates ~4n random k-mers, in a 32-bit key when that fits
+//      (DNA + '$': 12 symbols) else a 64-bit key; hand-written onesweep radix sort of (key, i).
+//   3. Equal-key runs are "groups".  Similar genomes give groups of a few homologous positions
+//      whose suffixes agree for ~1/divergence characters.  Groups of <= SA_SMALL_G suffixes are
+//      ordered by ALL-PAIRS direct comparison: one thread per member walks its earlier group
+//      mates 8 text bytes per step (funnel-shifted aligned words), the warp keeps iterating
+//      until every lane's queue is empty, so lanes only idle at the tail.  Every pair yields
+//      who is smaller (-> a per-member count = its place in the group) and their common
+//      prefix; the largest common prefix with a smaller mate is the member's LCP entry, with
+//      the reference's '$'/'N' barrier applied.  A comparison longer than SA_CMP_CAP bytes
+//      defers its group to stage 4.
+//   4. Groups of more than SA_SMALL_G suffixes and deferred groups: prefix doubling
+//      (Manber-Myers / Larsson-Sadakane) over the still-tied suffixes only, sort key
+//      (rank[i] : rank[i+h]+1), h = k, 2k, 4k, ...; bounded work for long repeats.
+//   When stage 4 is not needed (no repeats beyond SA_SMALL_G copies) the LCP array is complete
+//   after stage 3; otherwise the caller runs the Kasai kernel of rv_lcp.cu.
 #include "rv_radix.cuh"
+#include <stdlib.h>
 
 namespace rv {
 
 static const int AP_THREADS = 256;
 static const int AP_IPT = 8;
 static const int AP_TILE = AP_THREADS * AP_IPT;  // 2048 active entries per tile
+
+static const int SA_SMALL_G = 16;     // largest group finished by direct comparison
+static const int SA_CMP_CAP = 4096;   // bytes after which a comparison is deferred to doubling
 
 struct CodeTable {
     unsigned short code[256];  // 0 is reserved for "past the end of the text"
@@ -40,24 +53,206 @@ __global__ void __launch_bounds__(256) sa_bytehist_kernel(const unsigned char *_
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-// key[i] = codes of T[i..i+k) packed most-significant-first, b bits each; val[i] = i
-__global__ void __launch_bounds__(256) sa_keygen_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, int b, int k,
-                                                       u64 *__restrict__ keys, u32 *__restrict__ vals) {
+// key[i] = sum_t code(T[i+t]) * base^(k-1-t)  (code 0 past the end); val[i] = i.
+// Each thread rolls the key over KG_PER consecutive positions.
+static const int KG_PER = 8;
+template <typename KeyT>
+__global__ void __launch_bounds__(256) sa_keygen_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 base, int k, KeyT top,
+                                                       KeyT *__restrict__ keys, u32 *__restrict__ vals) {
     __shared__ unsigned short s_code[256];
     s_code[threadIdx.x] = tab.code[threadIdx.x];
     __syncthreads();
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u64 key = 0;
+    i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * KG_PER;
+    if (i0 >= n) return;
+    KeyT key = 0;
     for (int t = 0; t < k; t++) {
-        i64 p = i + t;
-        u64 c = p < n ? (u64)s_code[T[p]] : 0ull;
-        key = (key << b) | c;
+        i64 p = i0 + t;
+        key = key * (KeyT)base + (KeyT)(p < n ? s_code[T[p]] : 0);
     }
-    keys[i] = key;
-    vals[i] = (u32)i;
+    for (int j = 0; j < KG_PER && i0 + j < n; j++) {
+        keys[i0 + j] = key;
+        vals[i0 + j] = (u32)(i0 + j);
+        i64 p = i0 + j;
+        KeyT first = (KeyT)s_code[T[p]];                       // symbol leaving the window
+        KeyT next = (KeyT)(p + k < n ? s_code[T[p + k]] : 0);  // symbol entering it
+        key = (key - first * top) * (KeyT)base + next;          // top = base^(k-1)
+    }
 }
 
+// ---- group geometry ---------------------------------------------------------------------
+// L / R: equal keys to the left / right of entry e, each capped at G.
+template <typename KeyT>
+__device__ __forceinline__ void run_lengths(const KeyT *__restrict__ keys, i64 A, i64 e, int G, int &L, int &R) {
+    KeyT k = keys[e];
+    L = 0;
+    R = 0;
+    while (L < G && e - L - 1 >= 0 && keys[e - L - 1] == k) L++;
+    while (R < G && e + R + 1 < A && keys[e + R + 1] == k) R++;
+}
+
+// ---- stage 3: all-pairs comparison inside small groups -------------------------------------
+__device__ __forceinline__ u64 ld_unaligned64(const u64 *__restrict__ W, i64 word, unsigned sh, u64 &lo) {
+    u64 hi = W[word + 1];
+    u64 w = (lo >> sh) | ((hi << 1) << (63u - sh));
+    lo = hi;
+    return w;
+}
+// index of the first zero byte of v, or 8
+__device__ __forceinline__ int first_zero_byte(u64 v) {
+    u64 z = (v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull;
+    return z ? ((__ffsll((long long)z) - 1) >> 3) : 8;
+}
+// index of the first '$' or 'N' byte of w (text order = little-endian byte order), or 8
+__device__ __forceinline__ int first_barrier_byte(u64 w) {
+    int a = first_zero_byte(w ^ 0x2424242424242424ull);
+    int b = first_zero_byte(w ^ 0x4E4E4E4E4E4E4E4Eull);
+    return a < b ? a : b;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T, int skip,
+                u32 *__restrict__ cnt, int *__restrict__ lcpv, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
+    const u64 *__restrict__ W = (const u64 *)T;
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    int L = 0, R = 0;
+    bool small = false;
+    u32 x = 0;
+    if (e < n) {
+        run_lengths(keys, n, e, SA_SMALL_G, L, R);
+        small = L + R + 1 <= SA_SMALL_G;
+        if (!small && L == 0) *flag_large = 1u;
+        x = sa[e];
+    }
+    int remaining = small ? L : 0;  // mates e-1 .. e-L still to compare with
+    // barrier inside the shared k-mer: identical for every member of the group
+    int cap0 = 0x7fffffff;
+    if (remaining > 0 || (small && R > 0)) {
+        for (int t = 0; t < skip; t++) {
+            unsigned char c = T[(i64)x + t];  // the k-mer is inside the text for every member of a group >= 2
+            if (c == '$' || c == 'N') { cap0 = t; break; }
+        }
+    }
+    u32 my_cnt = 0;
+    int my_lcp = 0;
+    bool give_up = false;
+    // state of the comparison in flight
+    bool active = false;
+    i64 ey = 0, wa = 0, wb = 0, h = 0, lenmin = 0, p = 0, q = 0;
+    unsigned sha = 0, shb = 0;
+    u64 lo_a = 0, lo_b = 0;
+    int bar = 0x7fffffff;  // first barrier offset (from the suffix start) seen in the matched part
+    for (;;) {
+        if (!active && remaining > 0 && !give_up) {
+            ey = e - remaining;
+            remaining--;
+            u32 y = sa[ey];
+            p = (i64)x + skip;
+            q = (i64)y + skip;
+            lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
+            wa = p >> 3;
+            wb = q >> 3;
+            sha = (unsigned)(p & 7) * 8u;
+            shb = (unsigned)(q & 7) * 8u;
+            lo_a = W[wa];
+            lo_b = W[wb];
+            h = 0;
+            bar = cap0;
+            active = true;
+        }
+        if (!__any_sync(FULL, active)) break;
+        if (active) {
+            u64 a = ld_unaligned64(W, wa, sha, lo_a);
+            u64 b = ld_unaligned64(W, wb, shb, lo_b);
+            wa++;
+            wb++;
+            u64 d = a ^ b;
+            int nd = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;  // equal leading bytes of this word
+            if (bar == 0x7fffffff) {
+                int fb = first_barrier_byte(a);
+                if (fb < nd) bar = skip + (int)h + fb;
+            }
+            bool done = false, x_less = false;
+            i64 match = 0;
+            if (h + nd >= lenmin) {  // ran off the shorter suffix without a difference inside it
+                done = true;
+                match = lenmin;
+                x_less = p > q;      // the shorter suffix (larger start) sorts first
+            } else if (nd < 8) {
+                done = true;
+                match = h + nd;
+                x_less = ((a >> (8 * nd)) & 0xffull) < ((b >> (8 * nd)) & 0xffull);
+            } else {
+                h += 8;
+                if (h >= SA_CMP_CAP) {
+                    give_up = true;
+                    active = false;
+                }
+            }
+            if (done) {
+                i64 lcp = (i64)skip + match;
+                if ((i64)bar < lcp) lcp = bar;
+                if (x_less) {  // y is the larger one: it gains a smaller mate
+                    atomicAdd(&cnt[ey], 1u);
+                    atomicMax(&lcpv[ey], (int)lcp);
+                } else {
+                    my_cnt++;
+                    my_lcp = my_lcp > (int)lcp ? my_lcp : (int)lcp;
+                }
+                active = false;
+            }
+        }
+    }
+    if (give_up) {
+        deferred[e - L] = 1;
+        *flag_large = 1u;
+    }
+    if (small && my_cnt) {
+        atomicAdd(&cnt[e], my_cnt);
+        atomicMax(&lcpv[e], my_lcp);
+    }
+}
+
+// place every member of a finished group: slot = group start + number of smaller mates
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ cnt, const int *__restrict__ lcpv,
+                const unsigned char *__restrict__ deferred, int *__restrict__ SA, int *__restrict__ rank, int *__restrict__ LCP) {
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int L, R;
+    run_lengths(keys, n, e, SA_SMALL_G, L, R);
+    if (L + R + 1 > SA_SMALL_G || (L + R > 0 && deferred[e - L])) return;  // stage 4
+    u32 r = cnt[e];
+    i64 slot = e - L + (i64)r;
+    u32 s = sa[e];
+    SA[slot] = (int)s;
+    rank[s] = (int)slot;
+    if (r > 0) LCP[slot] = lcpv[e];  // the smallest member's entry crosses the group boundary: sa_headlcp_kernel
+}
+
+// LCP entry of the first slot of every group: neighbours differ inside the k-mer, compare from scratch
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ T, const int *__restrict__ SA, int *__restrict__ LCP) {
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j == 0) {
+        LCP[0] = 0;
+        return;
+    }
+    if (keys[j] == keys[j - 1]) return;
+    i64 a = SA[j], b = SA[j - 1];
+    int h = 0;
+    while (a + h < n && b + h < n) {
+        unsigned char c = T[a + h];
+        if (c != T[b + h] || c == '$' || c == 'N') break;
+        h++;
+    }
+    LCP[j] = h;
+}
+
+// ---- stage 4: prefix doubling ---------------------------------------------------------------
 // key[e] = rank[sa[e]] : (rank[sa[e]+h]+1, or 0 when the suffix ends first)
 __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ grp, const int *__restrict__ rank,
                                                        i64 A, i64 n, i64 h, u64 *__restrict__ keys) {
@@ -69,19 +264,19 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ 
 }
 
 // head: first entry of its equal-key run.  active: the run still needs doubling rounds, i.e. it has more
-// than G members (G = 1 in the doubling rounds: any tie) or the comparison kernel deferred it.
-__device__ __forceinline__ void ap_flags(const u64 *__restrict__ keys, i64 A, i64 e, int G, const unsigned char *__restrict__ deferred,
+// than G members (G = 1 in the doubling rounds: any tie) or the comparison stage deferred it.
+template <typename KeyT>
+__device__ __forceinline__ void ap_flags(const KeyT *__restrict__ keys, i64 A, i64 e, int G, const unsigned char *__restrict__ deferred,
                                          bool &head, bool &active) {
-    u64 k = keys[e];
-    int L = 0, R = 0;
-    while (L < G && e - L - 1 >= 0 && keys[e - L - 1] == k) L++;
-    while (R < G && e + R + 1 < A && keys[e + R + 1] == k) R++;
+    int L, R;
+    run_lengths(keys, A, e, G, L, R);
     head = L == 0;
     active = (L + R + 1 > G) || (deferred && L + R > 0 && deferred[e - L]);
 }
 
 // per tile: (largest slot+1 of a group head, number of entries that stay active)
-__global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, i64 A, int G,
+template <typename KeyT>
+__global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, i64 A, int G,
                                                                const unsigned char *__restrict__ deferred,
                                                                u32 *__restrict__ tile_max, u32 *__restrict__ tile_cnt) {
     __shared__ u32 s1[33], s2[33];
@@ -109,6 +304,7 @@ __global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const u64 *__rest
 // single block: exclusive max-scan / sum-scan over the tile aggregates; total -> *out_total
 __global__ void __launch_bounds__(1024) sa_tilescan_kernel(u32 *__restrict__ tile_max, u32 *__restrict__ tile_cnt, i64 tiles, u32 *__restrict__ out_total) {
     __shared__ u32 s1[33], s2[33];
+    __shared__ u32 s_im[1024];
     u32 carry_max = 0, carry_sum = 0;
     for (i64 b0 = 0; b0 < tiles; b0 += 1024) {
         i64 t = b0 + threadIdx.x;
@@ -119,7 +315,6 @@ __global__ void __launch_bounds__(1024) sa_tilescan_kernel(u32 *__restrict__ til
         u32 ic = block_incl_sum<1024>(c, s2, &tc);
         if (t < tiles) tile_cnt[t] = carry_sum + ic - c;
         // exclusive max needs the inclusive max of the previous thread: stage through shared memory
-        __shared__ u32 s_im[1024];
         s_im[threadIdx.x] = im;
         __syncthreads();
         if (t < tiles) {
@@ -136,11 +331,13 @@ __global__ void __launch_bounds__(1024) sa_tilescan_kernel(u32 *__restrict__ til
 // per tile: finish the two scans with the tile carries and apply the round:
 //   SA[slot] = suffix, rank[suffix] = slot of its group head, and append the
 //   entries of groups that still have >= 2 members to the next active list.
+template <typename KeyT>
 __global__ void __launch_bounds__(AP_THREADS)
-sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const u32 *__restrict__ pos, i64 A, int G,
-                const unsigned char *__restrict__ deferred, const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt, int *__restrict__ SA, int *__restrict__ rank,
-                u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2) {
+sa_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, const u32 *__restrict__ pos, i64 A, int G,
+                const unsigned char *__restrict__ deferred, const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt,
+                int *__restrict__ SA, int *__restrict__ rank, u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2) {
     __shared__ u32 s1[33], s2[33];
+    __shared__ u32 s_im[AP_THREADS];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
     u32 hp[AP_IPT];
     bool act[AP_IPT];
@@ -164,7 +361,6 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
     u32 imax = block_incl_max<AP_THREADS>(mx, s1, &tm);
     u32 isum = block_incl_sum<AP_THREADS>(cnt, s2, &tc);
     // exclusive max over the threads before this one
-    __shared__ u32 s_im[AP_THREADS];
     s_im[threadIdx.x] = imax;
     __syncthreads();
     u32 pre_max = threadIdx.x > 0 ? s_im[threadIdx.x - 1] : 0u;
@@ -174,7 +370,7 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
 #pragma unroll
     for (int k = 0; k < AP_IPT; k++) {
         i64 e = base + k;
-        if (e < A && (act[k] || G == 1)) {  // G > 1: the other entries were finished by sa_finish_small_kernel
+        if (e < A && (act[k] || G == 1)) {  // G > 1: the other entries were placed by the comparison stage
             u32 g = (hp[k] > pre_max ? hp[k] : pre_max) - 1u;  // slot of the group head
             u32 slot = pos ? pos[e] : (u32)e;
             u32 s = sa[e];
@@ -190,89 +386,6 @@ sa_apply_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, const 
     }
 }
 
-// ---- small groups: finish by direct suffix comparison ---------------------------------
-// After the k-mer sort nearly every group of similar genomes is a handful of homologous
-// positions whose suffixes agree for ~1/divergence characters.  One thread orders such a
-// group (<= SA_SMALL_G members) by comparing the suffixes themselves, four text bytes per
-// step through funnel-shifted aligned words, instead of log(LCP) doubling rounds over the
-// whole array.  Comparisons longer than SA_CMP_CAP bytes defer the group to the doubling
-// rounds, which bound the work for long repeats / identical sequences.
-static const int SA_SMALL_G = 16;
-static const int SA_CMP_CAP = 4096;
-
-// order of suffixes a and b (a != b) that agree on their first `skip` characters.
-// returns -1 (a < b), +1 (a > b), 0 (undecided within SA_CMP_CAP bytes).  T is 4-byte
-// aligned and readable (zero padded) up to n + 8.
-__device__ __forceinline__ int suffix_cmp(const unsigned char *__restrict__ T, i64 n, u32 a, u32 b, int skip) {
-    const u32 *__restrict__ W = (const u32 *)T;
-    i64 p = (i64)a + skip, q = (i64)b + skip;
-    i64 lenmin = (n - p) < (n - q) ? (n - p) : (n - q);  // >= 0
-    i64 ia = p >> 2, ib = q >> 2;
-    const unsigned sha = (unsigned)(p & 3) * 8u, shb = (unsigned)(q & 3) * 8u;
-    u32 lo_a = W[ia], lo_b = W[ib];
-    for (i64 h = 0; h < lenmin; h += 4) {
-        u32 hi_a = W[++ia], hi_b = W[++ib];
-        u32 wa = __funnelshift_r(lo_a, hi_a, sha), wb = __funnelshift_r(lo_b, hi_b, shb);
-        lo_a = hi_a;
-        lo_b = hi_b;
-        u32 x = wa ^ wb;
-        if (x) {
-            int byte = (__ffs((int)x) - 1) >> 3;  // first differing byte in text order (little-endian words)
-            if (h + byte >= lenmin) break;        // the difference lies past the end of the shorter suffix
-            u32 ca = (wa >> (8 * byte)) & 0xffu, cb = (wb >> (8 * byte)) & 0xffu;
-            return ca < cb ? -1 : 1;
-        }
-        if (h >= SA_CMP_CAP) return 0;
-    }
-    return p > q ? -1 : 1;  // one suffix is a proper prefix of the other: the shorter one sorts first
-}
-
-__global__ void __launch_bounds__(256)
-sa_finish_small_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T, int skip,
-                       int *__restrict__ SA, int *__restrict__ rank, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
-    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    u64 key = keys[j];
-    if (j > 0 && keys[j - 1] == key) return;  // not the head of its group
-    int g = 1;
-    while (g <= SA_SMALL_G && j + g < n && keys[j + g] == key) g++;
-    if (g == 1) {
-        u32 s = sa[j];
-        SA[j] = (int)s;
-        rank[s] = (int)j;
-        return;
-    }
-    if (g > SA_SMALL_G) {
-        *flag_large = 1u;
-        return;
-    }
-    u32 ids[SA_SMALL_G];
-    ids[0] = sa[j];
-    bool undecided = false;
-    for (int t = 1; t < g; t++) {  // insertion sort; every comparison starts after the shared k-mer
-        u32 x = sa[j + t];
-        int at = t;
-        while (at > 0) {
-            int c = suffix_cmp(T, n, x, ids[at - 1], skip);
-            if (c == 0) undecided = true;
-            if (c >= 0) break;
-            ids[at] = ids[at - 1];
-            at--;
-        }
-        ids[at] = x;
-        if (undecided) break;
-    }
-    if (undecided) {
-        deferred[j] = 1;
-        *flag_large = 1u;
-        return;
-    }
-    for (int t = 0; t < g; t++) {
-        SA[j + t] = (int)ids[t];
-        rank[ids[t]] = (int)(j + t);
-    }
-}
-
 static inline int bits_for(u64 v) {  // number of bits needed to hold v
     int b = 0;
     while (v) { b++; v >>= 1; }
@@ -282,92 +395,83 @@ static inline int bits_for(u64 v) {  // number of bits needed to hold v
 size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
-    // keys x2 (u64), vals x2, pos x2, grp x2 (u32), tile aggregates, radix scratch, small stuff
+    // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
     return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
-int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, PhaseTimes *pt) {
-    if (n <= 0) return RV_OK;
-    if (n >= ((i64)1 << 30)) {
-        set_error("sa_build: n=%lld not supported yet (limit 2^30-1)", (long long)n);
-        return RV_ERR_UNSUPPORTED;
-    }
-    u64 *k0 = ws.take<u64>(n), *k1 = ws.take<u64>(n);
-    u32 *v0 = ws.take<u32>(n), *v1 = ws.take<u32>(n);
-    u32 *posA = ws.take<u32>(n), *posB = ws.take<u32>(n);
-    u32 *grpA = ws.take<u32>(n), *grpB = ws.take<u32>(n);
-    const i64 tiles_n = (n + AP_TILE - 1) / AP_TILE;
-    u32 *tile_max = ws.take<u32>(tiles_n), *tile_cnt = ws.take<u32>(tiles_n);
-    void *rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
-    u32 *small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "large groups exist"
-    unsigned char *deferred = ws.take<unsigned char>(n);
-    if (!deferred || !k0 || !k1 || !v0 || !v1 || !posA || !posB || !grpA || !grpB || !tile_max || !tile_cnt || !rscratch || !small) {
-        set_error("sa_build: workspace too small");
-        return RV_ERR_NOMEM;
-    }
+struct SaBuffers {
+    u64 *k0, *k1;
+    u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
+    unsigned char *deferred;
+    void *rscratch;
+};
 
-    // 1. alphabet
-    u32 hist[256];
-    RV_CUDA(cudaMemsetAsync(small, 0, 512 * 4, st.s));
-    {
-        i64 blocks = (n + 256 * 64 - 1) / (256 * 64);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        RV_LAUNCH(sa_bytehist_kernel, (unsigned)blocks, 256, 0, st.s, dT, n, small);
-        st.launches++;
-    }
-    RV_CUDA(cudaMemcpyAsync(hist, small, 256 * 4, cudaMemcpyDeviceToHost, st.s));
-    RV_CUDA(cudaStreamSynchronize(st.s));
-    CodeTable tab;
-    memset(&tab, 0, sizeof tab);
-    int sigma = 0;
-    for (int c = 0; c < 256; c++)
-        if (hist[c]) tab.code[c] = (unsigned short)(++sigma);
-    const int b = bits_for((u64)sigma);  // codes 0..sigma
-    const int k = 64 / b;
-
-    // 2. initial keys + sort
-    RV_LAUNCH(sa_keygen_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, dT, n, tab, b, k, k0, v0);
+// stages 2-3 for one key width; on return *keys_out / *sa_out hold the sorted keys and suffixes
+template <typename KeyT>
+static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, u32 base, int k,
+                            int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, bool *large, PhaseTimes *pt) {
+    KeyT *k0 = (KeyT *)B.k0, *k1 = (KeyT *)B.k1;
+    KeyT top = 1;
+    for (int t = 1; t < k; t++) top *= (KeyT)base;
+    i64 kg_threads = (n + KG_PER - 1) / KG_PER;
+    RV_LAUNCH((sa_keygen_kernel<KeyT>), (unsigned)((kg_threads + 255) / 256), 256, 0, st.s, dT, n, tab, base, k, top, k0, B.v0);
     st.launches++;
     bool in0;
-    RV_TRY(radix_sort_pairs<u64>(st, k0, k1, v0, v1, n, make_plan(0, b * k), rscratch, &in0));
+    RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0));
     if (pt) pt->sa_sorted_items += n;
-    u64 *keys = in0 ? k0 : k1;
-    u32 *sa = in0 ? v0 : v1;
-    u64 *keys_alt = in0 ? k1 : k0;
-    u32 *sa_alt = in0 ? v1 : v0;
-
-    // 3. finish singletons and small groups by direct comparison
-    RV_CUDA(cudaMemsetAsync(deferred, 0, (size_t)n, st.s));
-    RV_LAUNCH(sa_finish_small_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, keys, sa, n, dT, k, dSA, dISA, deferred, small + 257);
-    st.launches++;
-    {
-        u32 large = 0;
-        RV_CUDA(cudaMemcpyAsync(&large, small + 257, 4, cudaMemcpyDeviceToHost, st.s));
-        RV_CUDA(cudaStreamSynchronize(st.s));
-        if (!large) {
-            RV_KCHECK();
-            return RV_OK;
-        }
+    KeyT *keys = in0 ? k0 : k1;
+    u32 *sa = in0 ? B.v0 : B.v1;
+    // comparison stage: cnt = grpA, lcpv = grpB (both free until stage 4)
+    u32 *cnt = B.grpA;
+    int *lcpv = (int *)B.grpB;
+    RV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * 4, st.s));
+    RV_CUDA(cudaMemsetAsync(lcpv, 0, (size_t)n * 4, st.s));
+    RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    RV_LAUNCH((sa_pairs_kernel<KeyT>), blocks, 256, 0, st.s, keys, sa, n, dT, k, cnt, lcpv, B.deferred, B.small + 257);
+    RV_LAUNCH((sa_place_kernel<KeyT>), blocks, 256, 0, st.s, keys, sa, n, cnt, lcpv, B.deferred, dSA, dISA, dLCP);
+    st.launches += 2;
+    u32 lg = 0;
+    RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    *large = lg != 0;
+    if (!*large) {
+        RV_LAUNCH((sa_headlcp_kernel<KeyT>), blocks, 256, 0, st.s, keys, n, dT, dSA, dLCP);
+        st.launches++;
     }
+    RV_KCHECK();
+    *keys_out = keys;
+    *sa_out = sa;
+    *sa_free = in0 ? B.v1 : B.v0;
+    return RV_OK;
+}
 
-    // 4. prefix doubling for what is left (groups of more than SA_SMALL_G suffixes, deferred groups)
-    u32 *pos = nullptr, *grp = nullptr;   // current active list is (sa, pos, grp)
-    u32 *pos_next = posA, *grp_next = grpA;
+// doubling rounds; round 0 works on the initial keys (KeyT), later rounds on (rank : rank) u64 keys
+template <typename KeyT>
+static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *keys0, u32 *sa, u32 *sa_alt, int *dSA, int *dISA, PhaseTimes *pt) {
+    u32 *pos = nullptr, *grp = nullptr;  // current active list is (sa, pos, grp)
+    u32 *pos_next = B.posA, *grp_next = B.grpA;
+    u64 *keys = B.k0, *keys_alt = B.k1;  // free once round 0 has consumed keys0 (which may alias one of them)
     i64 A = n;
     const int nbits = bits_for((u64)n);  // ranks < n, second key <= n
     i64 h = k;
     for (int round = 0;; round++) {
         const i64 tiles = (A + AP_TILE - 1) / AP_TILE;
-        const int G = round == 0 ? SA_SMALL_G : 1;
-        const unsigned char *dfr = round == 0 ? deferred : nullptr;
-        RV_LAUNCH(sa_reduce_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, G, dfr, tile_max, tile_cnt);
-        RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, tile_max, tile_cnt, tiles, small + 256);
-        // the compacted entries go to the buffers not holding the current list
-        RV_LAUNCH(sa_apply_kernel, (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, G, dfr, tile_max, tile_cnt, dSA, dISA, sa_alt, pos_next,
-                  grp_next);
+        if (round == 0) {
+            RV_LAUNCH((sa_reduce_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, pos, A, SA_SMALL_G, B.deferred, B.tile_max, B.tile_cnt);
+            RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
+            RV_LAUNCH((sa_apply_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, sa, pos, A, SA_SMALL_G, B.deferred, B.tile_max,
+                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next);
+        } else {
+            RV_LAUNCH((sa_reduce_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
+                      B.tile_cnt);
+            RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
+            RV_LAUNCH((sa_apply_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
+                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next);
+        }
         st.launches += 3;
         u32 nactive = 0;
-        RV_CUDA(cudaMemcpyAsync(&nactive, small + 256, 4, cudaMemcpyDeviceToHost, st.s));
+        RV_CUDA(cudaMemcpyAsync(&nactive, B.small + 256, 4, cudaMemcpyDeviceToHost, st.s));
         RV_CUDA(cudaStreamSynchronize(st.s));
         if (pt) pt->sa_rounds = round + 1;
         if (nactive == 0) break;
@@ -380,13 +484,12 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         { u32 *t = sa; sa = sa_alt; sa_alt = t; }
         pos = pos_next;
         grp = grp_next;
-        pos_next = (pos == posA) ? posB : posA;
-        grp_next = (grp == grpA) ? grpB : grpA;
-        // keys for this round go to `keys` (free now), sorted ping-pong with keys_alt / (sa, sa_alt)
+        pos_next = (pos == B.posA) ? B.posB : B.posA;
+        grp_next = (grp == B.grpA) ? B.grpB : B.grpA;
         RV_LAUNCH(sa_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dISA, A, n, h, keys);
         st.launches++;
         bool r0;
-        RV_TRY(radix_sort_pairs<u64>(st, keys, keys_alt, sa, sa_alt, A, make_plan(0, nbits, 32, 32 + nbits), rscratch, &r0));
+        RV_TRY(radix_sort_pairs<u64>(st, keys, keys_alt, sa, sa_alt, A, make_plan(0, nbits, 32, 32 + nbits), B.rscratch, &r0));
         if (pt) pt->sa_sorted_items += A;
         if (!r0) {
             { u64 *t = keys; keys = keys_alt; keys_alt = t; }
@@ -395,6 +498,101 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         h *= 2;
     }
     RV_KCHECK();
+    return RV_OK;
+}
+
+int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt) {
+    *lcp_done = false;
+    if (n <= 0) return RV_OK;
+    if (n >= ((i64)1 << 30)) {
+        set_error("sa_build: n=%lld not supported yet (limit 2^30-1)", (long long)n);
+        return RV_ERR_UNSUPPORTED;
+    }
+    SaBuffers B;
+    B.k0 = ws.take<u64>(n);
+    B.k1 = ws.take<u64>(n);
+    B.v0 = ws.take<u32>(n);
+    B.v1 = ws.take<u32>(n);
+    B.posA = ws.take<u32>(n);
+    B.posB = ws.take<u32>(n);
+    B.grpA = ws.take<u32>(n);
+    B.grpB = ws.take<u32>(n);
+    const i64 tiles_n = (n + AP_TILE - 1) / AP_TILE;
+    B.tile_max = ws.take<u32>(tiles_n);
+    B.tile_cnt = ws.take<u32>(tiles_n);
+    B.rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
+    B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
+    B.deferred = ws.take<unsigned char>(n);
+    if (!B.deferred || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+        !B.rscratch || !B.small) {
+        set_error("sa_build: workspace too small");
+        return RV_ERR_NOMEM;
+    }
+
+    // 1. alphabet
+    u32 hist[256];
+    RV_CUDA(cudaMemsetAsync(B.small, 0, 512 * 4, st.s));
+    {
+        i64 blocks = (n + 256 * 64 - 1) / (256 * 64);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        RV_LAUNCH(sa_bytehist_kernel, (unsigned)blocks, 256, 0, st.s, dT, n, B.small);
+        st.launches++;
+    }
+    RV_CUDA(cudaMemcpyAsync(hist, B.small, 256 * 4, cudaMemcpyDeviceToHost, st.s));
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    CodeTable tab;
+    memset(&tab, 0, sizeof tab);
+    int sigma = 0, sigma_eff = 0;
+    for (int c = 0; c < 256; c++)
+        if (hist[c]) {
+            tab.code[c] = (unsigned short)(++sigma);
+            if ((u64)hist[c] * 32 >= (u64)n) sigma_eff++;  // symbols that carry the entropy (ACGT, not '$'/N/IUPAC)
+        }
+    if (sigma_eff < 2) sigma_eff = 2;
+    const u32 base = (u32)sigma + 1;  // digits 0..sigma
+    // shortest k with sigma_eff^k >= 4n: random k-mers are then mostly unique
+    int k_need = 1;
+    {
+        double want = 4.0 * (double)n, have = sigma_eff;
+        while (have < want && k_need < 64) { have *= sigma_eff; k_need++; }
+    }
+    auto capacity = [&](int bits) {  // largest k with base^k <= 2^bits
+        int kk = 0;
+        double v = 1.0, lim = bits == 32 ? 4294967296.0 : 18446744073709551616.0;
+        while (v * base <= lim && kk < 64) { v *= base; kk++; }
+        return kk;
+    };
+    const int k32 = capacity(32), k64 = capacity(64);
+    // a 32-bit key is taken when it is at most 1 symbol short of k_need (4x fewer distinct k-mers): the
+    // comparison stage absorbs the slightly larger groups and the sort moves 8 instead of 12 bytes per pair
+    bool use32 = k32 >= 1 && k32 + 1 >= k_need;
+    if (const char *force = getenv("RV_SA_KEY_BITS")) {  // test hook: exercise both key widths on small inputs
+        if (force[0] == '6') use32 = false;
+        if (force[0] == '3') use32 = true;
+    }
+    int k = use32 ? k32 : (k_need < k64 ? k_need : k64);
+    if (k < 1) k = 1;
+    u64 maxkey = 1;
+    for (int t = 0; t < k; t++) maxkey *= base;  // base^k fits by construction (k64 may give exactly 2^64 -> wraps to 0)
+    const int key_bits = use32 ? bits_for(maxkey - 1) : (maxkey == 0 ? 64 : bits_for(maxkey - 1));
+
+    bool large = false;
+    u32 *sa = nullptr, *sa_free = nullptr;
+    if (use32) {
+        u32 *keys = nullptr;
+        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
+        if (large) {
+            // round 0 reads the u32 keys that live in the first half of k0 or k1; later rounds reuse both
+            // buffers as u64 keys, so move the u32 keys out of the way (posB is free until round 2)
+            RV_CUDA(cudaMemcpyAsync(B.posB, keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, st.s));
+            RV_TRY(doubling<u32>(st, B, n, k, B.posB, sa, sa_free, dSA, dISA, pt));
+        }
+    } else {
+        u64 *keys = nullptr;
+        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
+        if (large) RV_TRY(doubling<u64>(st, B, n, k, keys, sa, sa_free, dSA, dISA, pt));
+    }
+    *lcp_done = !large;
     return RV_OK;
 }
 

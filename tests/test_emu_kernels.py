@@ -54,3 +54,13 @@ def test_emu_large_groups_and_small_groups_mixed(emu_lib):
     s1 = s0[:700] + b"G" + s0[701:2000] + rep * 3 + s0[2000:]
     T, nsep, _ = P.assemble([[s0], [s1]])
     check_against_oracle(emu_lib, T, nsep, 2, minl=8)
+
+
+@pytest.mark.parametrize("bits", ["32", "64"])
+def test_emu_both_key_widths(emu_lib, monkeypatch, bits):
+    monkeypatch.setenv("RV_SA_KEY_BITS", bits)
+    rng = np.random.default_rng(21)
+    T, nsep, _ = P.assemble(random_related(rng, 3, 2500, 4))
+    check_against_oracle(emu_lib, T, nsep, 3, minl=6)
+    check_against_golden(emu_lib, load_golden("tandem"))
+    check_against_golden(emu_lib, load_golden("all_A"))

@@ -142,3 +142,32 @@ def test_reveallib_surface_on_gpu():
         assert idx.SA == g["SA"].tolist() and idx.LCP == g["LCP"].tolist() and idx.SAi == g["SAi"].tolist()
         assert idx.getmums(1) == [(l, (a, b), 0) for l, a, b in g["mums"].tolist()]
         assert idx.nsep == [17] and idx.n == 36 and idx.nsamples == 2
+
+
+@pytest.mark.parametrize("bits", ["32", "64"])
+def test_cuda_both_key_widths(cuda_lib, monkeypatch, bits):
+    """RV_SA_KEY_BITS forces the 32- / 64-bit k-mer key path of the SA builder."""
+    monkeypatch.setenv("RV_SA_KEY_BITS", bits)
+    rng = np.random.default_rng(21)
+    T, nsep, _ = P.assemble(random_related(rng, 3, 120000, 4))
+    check_against_oracle(cuda_lib, T, nsep, 3, minl=10)
+    for name in ("tandem", "all_A", "iupac_mix", "with_N_d2"):
+        check_against_golden(cuda_lib, load_golden(name))
+    T, nsep, ns = synth.workload(2, 400000, seed=5)
+    check_against_oracle(cuda_lib, T, nsep, ns, minl=20)
+
+
+def test_cuda_long_identical_and_repeats(cuda_lib):
+    """Comparisons longer than the cap and groups larger than SA_SMALL_G go through the doubling rounds + Kasai."""
+    rng = np.random.default_rng(3)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    s = al[rng.integers(0, 4, size=70000)].tobytes()
+    t = bytearray(s)
+    t[65000] = ord("A") if t[65000] != ord("A") else ord("C")
+    T, nsep, _ = P.assemble([[s], [bytes(t)], [s[100:69000]]])
+    check_against_oracle(cuda_lib, T, nsep, 3, minl=10)
+    rep = al[rng.integers(0, 4, size=60)].tobytes()
+    s0 = al[rng.integers(0, 4, size=15000)].tobytes() + rep * 40 + al[rng.integers(0, 4, size=15000)].tobytes()
+    s1 = s0[:7000] + b"G" + s0[7001:20000] + rep * 3 + s0[20000:]
+    T, nsep, _ = P.assemble([[s0], [s1]])
+    check_against_oracle(cuda_lib, T, nsep, 2, minl=8)
