@@ -91,125 +91,155 @@ __device__ __forceinline__ void run_lengths(const KeyT *__restrict__ keys, i64 A
 }
 
 // ---- stage 3: all-pairs comparison inside small groups -------------------------------------
-__device__ __forceinline__ u64 ld_unaligned64(const u64 *__restrict__ W, i64 word, unsigned sh, u64 &lo) {
-    u64 hi = W[word + 1];
-    u64 w = (lo >> sh) | ((hi << 1) << (63u - sh));
-    lo = hi;
-    return w;
-}
-// index of the first zero byte of v, or 8
-__device__ __forceinline__ int first_zero_byte(u64 v) {
-    u64 z = (v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull;
-    return z ? ((__ffsll((long long)z) - 1) >> 3) : 8;
-}
-// index of the first '$' or 'N' byte of w (text order = little-endian byte order), or 8
-__device__ __forceinline__ int first_barrier_byte(u64 w) {
-    int a = first_zero_byte(w ^ 0x2424242424242424ull);
-    int b = first_zero_byte(w ^ 0x4E4E4E4E4E4E4E4Eull);
-    return a < b ? a : b;
+// bit i of bar[] is set iff T[i] is '$' or 'N' (the reference's LCP barrier, interface.c:107)
+__global__ void __launch_bounds__(256) sa_barrier_bits_kernel(const unsigned char *__restrict__ T, i64 n, u32 *__restrict__ bar, i64 words) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned char c = i < n ? T[i] : 0;
+    unsigned m = __ballot_sync(FULL, c == '$' || c == 'N');
+    if ((threadIdx.x & 31u) == 0 && (i >> 5) < words) bar[i >> 5] = m;
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(256)
-sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T, int skip,
-                u32 *__restrict__ cnt, int *__restrict__ lcpv, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
-    const u64 *__restrict__ W = (const u64 *)T;
-    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    int L = 0, R = 0;
-    bool small = false;
-    u32 x = 0;
-    if (e < n) {
-        run_lengths(keys, n, e, SA_SMALL_G, L, R);
-        small = L + R + 1 <= SA_SMALL_G;
-        if (!small && L == 0) *flag_large = 1u;
-        x = sa[e];
-    }
-    int remaining = small ? L : 0;  // mates e-1 .. e-L still to compare with
-    // barrier inside the shared k-mer: identical for every member of the group
-    int cap0 = 0x7fffffff;
-    if (remaining > 0 || (small && R > 0)) {
-        for (int t = 0; t < skip; t++) {
-            unsigned char c = T[(i64)x + t];  // the k-mer is inside the text for every member of a group >= 2
-            if (c == '$' || c == 'N') { cap0 = t; break; }
-        }
-    }
-    u32 my_cnt = 0;
-    int my_lcp = 0;
-    bool give_up = false;
-    // state of the comparison in flight
-    bool active = false;
-    i64 ey = 0, wa = 0, wb = 0, h = 0, lenmin = 0, p = 0, q = 0;
-    unsigned sha = 0, shb = 0;
-    u64 lo_a = 0, lo_b = 0;
-    int bar = 0x7fffffff;  // first barrier offset (from the suffix start) seen in the matched part
+// offset of the first barrier character in T[x .. x+len), or len
+__device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar, i64 x, i64 len) {
+    i64 w = x >> 5;
+    unsigned sh = (unsigned)(x & 31);
+    u32 bits = bar[w] >> sh;
+    i64 base = 0, have = 32 - sh;  // bits of `bits` that are valid
     for (;;) {
-        if (!active && remaining > 0 && !give_up) {
-            ey = e - remaining;
-            remaining--;
-            u32 y = sa[ey];
-            p = (i64)x + skip;
-            q = (i64)y + skip;
-            lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
-            wa = p >> 3;
-            wb = q >> 3;
-            sha = (unsigned)(p & 7) * 8u;
-            shb = (unsigned)(q & 7) * 8u;
-            lo_a = W[wa];
-            lo_b = W[wb];
-            h = 0;
-            bar = cap0;
-            active = true;
+        if (bits) {
+            i64 at = base + (__ffs((int)bits) - 1);
+            return at < len ? at : len;
         }
+        base += have;
+        if (base >= len) return len;
+        bits = bar[++w];
+        have = 32;
+    }
+}
+
+static const int PR_THREADS = 256;
+static const int PR_WARPS = PR_THREADS / 32;
+static const int PR_SPL = 4;                    // slots per lane
+static const int PR_CHUNK = 32 * PR_SPL;        // 128 consecutive slots per warp
+static const int PR_QCAP = PR_CHUNK * (SA_SMALL_G - 1);
+
+// One warp owns PR_CHUNK consecutive SA slots.  Every pair (member, earlier mate) of a small group
+// becomes a work item in the warp's shared-memory queue; lanes pull the next item whenever they are
+// idle, so all 32 lanes stay busy until the queue runs dry.  A comparison step covers 16 text bytes:
+// five aligned 32-bit words per suffix funnel-shifted to the suffix start, XOR, first set bit.
+template <typename KeyT>
+__global__ void __launch_bounds__(PR_THREADS)
+sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T,
+                const u32 *__restrict__ bar, int skip, u32 *__restrict__ cnt, int *__restrict__ lcpv,
+                unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
+    __shared__ unsigned short s_queue[PR_WARPS][PR_QCAP];
+    const u32 *__restrict__ W = (const u32 *)T;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const i64 chunk0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
+    unsigned short *queue = s_queue[w];
+
+    // ---- enqueue: slot t of the chunk contributes the pairs (t, t-d), d = 1..L ----
+    u32 qn = 0;
+#pragma unroll
+    for (int i = 0; i < PR_SPL; i++) {
+        const int t = i * 32 + (int)lane;
+        const i64 e = chunk0 + t;
+        int c = 0;
+        if (e < n) {
+            int L, R;
+            run_lengths(keys, n, e, SA_SMALL_G, L, R);
+            if (L + R + 1 <= SA_SMALL_G) c = L;
+            else if (L == 0) *flag_large = 1u;
+        }
+        u32 inc = warp_incl_sum((u32)c);
+        u32 at = qn + inc - (u32)c;
+        for (int d = 1; d <= c; d++) queue[at + d - 1] = (unsigned short)((t << 4) | d);
+        qn += __shfl_sync(FULL, inc, 31);
+    }
+    __syncwarp();
+
+    // ---- flattened comparison loop ----
+    u32 next = 0;
+    bool active = false;
+    i64 ex = 0, ey = 0, p = 0, q = 0, lenmin = 0, h = 0;
+    u32 x = 0, y = 0;
+    i64 ia = 0, ib = 0;
+    unsigned sha = 0, shb = 0;
+    u32 lo_a = 0, lo_b = 0;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!active) {
+            u32 idx = next + (u32)__popc(idle & lanemask_lt());
+            if (idx < qn) {
+                unsigned it = queue[idx];
+                ex = chunk0 + (it >> 4);
+                ey = ex - (i64)(it & 15u);
+                x = sa[ex];
+                y = sa[ey];
+                p = (i64)x + skip;
+                q = (i64)y + skip;
+                lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
+                ia = p >> 2;
+                ib = q >> 2;
+                sha = (unsigned)(p & 3) * 8u;
+                shb = (unsigned)(q & 3) * 8u;
+                lo_a = W[ia];
+                lo_b = W[ib];
+                h = 0;
+                active = true;
+            }
+        }
+        next += (u32)__popc(idle);
         if (!__any_sync(FULL, active)) break;
         if (active) {
-            u64 a = ld_unaligned64(W, wa, sha, lo_a);
-            u64 b = ld_unaligned64(W, wb, shb, lo_b);
-            wa++;
-            wb++;
-            u64 d = a ^ b;
-            int nd = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;  // equal leading bytes of this word
-            if (bar == 0x7fffffff) {
-                int fb = first_barrier_byte(a);
-                if (fb < nd) bar = skip + (int)h + fb;
-            }
+            u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
+            u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
+            u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
+            u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+            u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+            u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
             bool done = false, x_less = false;
             i64 match = 0;
-            if (h + nd >= lenmin) {  // ran off the shorter suffix without a difference inside it
+            if (d0 | d1 | d2 | d3) {
+                int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
+                u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+                int byte = (__ffs((int)dd) - 1) >> 3;
+                i64 at = h + wsel * 4 + byte;  // first differing byte, counted from p / q
                 done = true;
-                match = lenmin;
-                x_less = p > q;      // the shorter suffix (larger start) sorts first
-            } else if (nd < 8) {
-                done = true;
-                match = h + nd;
-                x_less = ((a >> (8 * nd)) & 0xffull) < ((b >> (8 * nd)) & 0xffull);
+                if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
+                    match = lenmin;
+                    x_less = p > q;  // the shorter suffix (larger start) sorts first
+                } else {
+                    match = at;
+                    x_less = T[p + at] < T[q + at];
+                }
             } else {
-                h += 8;
-                if (h >= SA_CMP_CAP) {
-                    give_up = true;
+                h += 16;
+                ia += 4;
+                ib += 4;
+                lo_a = a4;
+                lo_b = b4;
+                if (h >= lenmin) {
+                    done = true;
+                    match = lenmin;
+                    x_less = p > q;
+                } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                    int L, R;
+                    run_lengths(keys, n, ex, SA_SMALL_G, L, R);
+                    deferred[ex - L] = 1;
+                    *flag_large = 1u;
                     active = false;
                 }
             }
             if (done) {
-                i64 lcp = (i64)skip + match;
-                if ((i64)bar < lcp) lcp = bar;
-                if (x_less) {  // y is the larger one: it gains a smaller mate
-                    atomicAdd(&cnt[ey], 1u);
-                    atomicMax(&lcpv[ey], (int)lcp);
-                } else {
-                    my_cnt++;
-                    my_lcp = my_lcp > (int)lcp ? my_lcp : (int)lcp;
-                }
+                // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
+                i64 lcp = first_barrier(bar, (i64)x, (i64)skip + match);
+                i64 big = x_less ? ey : ex;  // slot (before placing) of the larger suffix: it gains a smaller mate
+                atomicAdd(&cnt[big], 1u);
+                atomicMax(&lcpv[big], (int)lcp);
                 active = false;
             }
         }
-    }
-    if (give_up) {
-        deferred[e - L] = 1;
-        *flag_large = 1u;
-    }
-    if (small && my_cnt) {
-        atomicAdd(&cnt[e], my_cnt);
-        atomicMax(&lcpv[e], my_lcp);
     }
 }
 
@@ -396,13 +426,14 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + a / 8 + 1024 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
     u64 *k0, *k1;
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
     unsigned char *deferred;
+    u32 *bar;  // barrier bitmask, (n+31)/32 + 2 words
     void *rscratch;
 };
 
@@ -428,9 +459,13 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     RV_CUDA(cudaMemsetAsync(lcpv, 0, (size_t)n * 4, st.s));
     RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    RV_LAUNCH((sa_pairs_kernel<KeyT>), blocks, 256, 0, st.s, keys, sa, n, dT, k, cnt, lcpv, B.deferred, B.small + 257);
+    const i64 bar_words = (n + 31) / 32 + 2;
+    RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((bar_words * 32 + 255) / 256), 256, 0, st.s, dT, n, B.bar, bar_words);
+    const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
+    RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, k, cnt,
+              lcpv, B.deferred, B.small + 257);
     RV_LAUNCH((sa_place_kernel<KeyT>), blocks, 256, 0, st.s, keys, sa, n, cnt, lcpv, B.deferred, dSA, dISA, dLCP);
-    st.launches += 2;
+    st.launches += 3;
     u32 lg = 0;
     RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
     RV_CUDA(cudaStreamSynchronize(st.s));
@@ -523,7 +558,8 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
     B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
     B.deferred = ws.take<unsigned char>(n);
-    if (!B.deferred || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    B.bar = ws.take<u32>((n + 31) / 32 + 2);
+    if (!B.deferred || !B.bar || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;

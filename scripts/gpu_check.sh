@@ -29,8 +29,10 @@ launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/launches_run.log 2>&1; echo "ncu launches exit $?" ;;
 ncu)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rs_pass_kernel -s 12 -c 3 -f -o gpurun_out/prof_rs_pass \
-      python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_run.log 2>&1; echo "ncu full exit $?" ;;
+  # NCU_KERNEL (regex, default rs_pass_kernel), NCU_SKIP (launches of that kernel to skip), NCU_WORKLOAD
+  k="${NCU_KERNEL:-rs_pass_kernel}"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_$k \
+      python bench.py --workload ${NCU_WORKLOAD:-c2} --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_run.log 2>&1; echo "ncu full exit $?" ;;
 sanitize)
   timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or tiny or ragged" > gpurun_out/memcheck.log 2>&1; echo "memcheck exit $?"
   tail -5 gpurun_out/memcheck.log
