@@ -91,20 +91,38 @@ __device__ __forceinline__ void run_lengths(const KeyT *__restrict__ keys, i64 A
 }
 
 // ---- stage 3: all-pairs comparison inside small groups -------------------------------------
-// bit i of bar[] is set iff T[i] is '$' or 'N' (the reference's LCP barrier, interface.c:107)
-__global__ void __launch_bounds__(256) sa_barrier_bits_kernel(const unsigned char *__restrict__ T, i64 n, u32 *__restrict__ bar, i64 words) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+// Two-level barrier bitmap: bit i of bar0[] is set iff T[i] is '$' or 'N' (the reference's LCP
+// barrier, interface.c:107); bit w of bar1[] is set iff word w of bar0 is non-zero.
+__global__ void __launch_bounds__(1024) sa_barrier_bits_kernel(const unsigned char *__restrict__ T, i64 n, u32 *__restrict__ bar0, u32 *__restrict__ bar1) {
+    __shared__ u32 s_nz[32];
+    i64 i = (i64)blockIdx.x * 1024 + threadIdx.x;
     unsigned char c = i < n ? T[i] : 0;
     unsigned m = __ballot_sync(FULL, c == '$' || c == 'N');
-    if ((threadIdx.x & 31u) == 0 && (i >> 5) < words) bar[i >> 5] = m;
+    if ((threadIdx.x & 31u) == 0) {
+        bar0[i >> 5] = m;
+        s_nz[threadIdx.x >> 5] = m ? 1u : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned nz = __ballot_sync(FULL, s_nz[threadIdx.x] != 0u);
+        if (threadIdx.x == 0) bar1[blockIdx.x] = nz;
+    }
 }
 
 // offset of the first barrier character in T[x .. x+len), or len
-__device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar, i64 x, i64 len) {
+__device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, i64 x, i64 len) {
+    if (len <= 0) return 0;
     i64 w = x >> 5;
+    const i64 wl = (x + len - 1) >> 5;
+    if ((w >> 5) == (wl >> 5)) {  // all level-0 words under one level-1 word: usually "nothing here"
+        u32 m1 = bar1[w >> 5] >> (unsigned)(w & 31);
+        unsigned span = (unsigned)(wl - w);  // words w .. w+span
+        if (span < 31u) m1 &= (2u << span) - 1u;
+        if (m1 == 0u) return len;
+    }
     unsigned sh = (unsigned)(x & 31);
-    u32 bits = bar[w] >> sh;
-    i64 base = 0, have = 32 - sh;  // bits of `bits` that are valid
+    u32 bits = bar0[w] >> sh;
+    i64 base = 0, have = 32 - sh;
     for (;;) {
         if (bits) {
             i64 at = base + (__ffs((int)bits) - 1);
@@ -112,159 +130,204 @@ __device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar, i64 x,
         }
         base += have;
         if (base >= len) return len;
-        bits = bar[++w];
+        bits = bar0[++w];
         have = 32;
     }
 }
 
-static const int PR_THREADS = 256;
+static const int PR_THREADS = 128;
 static const int PR_WARPS = PR_THREADS / 32;
-static const int PR_SPL = 4;                    // slots per lane
-static const int PR_CHUNK = 32 * PR_SPL;        // 128 consecutive slots per warp
-static const int PR_QCAP = PR_CHUNK * (SA_SMALL_G - 1);
+static const int PR_CHUNK = 512;                       // nominal SA slots per warp
+static const int PR_MAXT = PR_CHUNK + SA_SMALL_G;      // a chunk is stretched to whole groups
+static const int PR_QCAP = 1024;                       // ring of work items per warp
+static const int PR_ROUND_ITEMS = 32 * (SA_SMALL_G - 1);
 
-// One warp owns PR_CHUNK consecutive SA slots.  Every pair (member, earlier mate) of a small group
-// becomes a work item in the warp's shared-memory queue; lanes pull the next item whenever they are
-// idle, so all 32 lanes stay busy until the queue runs dry.  A comparison step covers 16 text bytes:
-// five aligned 32-bit words per suffix funnel-shifted to the suffix start, XOR, first set bit.
+// One warp owns a run of whole groups (about PR_CHUNK consecutive SA slots).  Every pair (member,
+// earlier mate) of a small group becomes a work item in the warp's shared-memory ring; lanes pull the
+// next item whenever they are idle, so all 32 lanes stay busy until the ring runs dry.  A comparison
+// step covers 16 text bytes: five aligned 32-bit words per suffix funnel-shifted to the suffix start,
+// XOR, first set bit.  The larger suffix of a pair gains one smaller mate (-> its place inside the
+// group) and the pair's common prefix (-> its LCP entry = the largest over its smaller mates); both
+// live in shared memory because a group never leaves its warp.  The warp then places its groups.
 template <typename KeyT>
 __global__ void __launch_bounds__(PR_THREADS)
 sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T,
-                const u32 *__restrict__ bar, int skip, u32 *__restrict__ cnt, int *__restrict__ lcpv,
-                unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
-    __shared__ unsigned short s_queue[PR_WARPS][PR_QCAP];
+                const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
+                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
+    __shared__ u32 s_queue[PR_WARPS][PR_QCAP];
+    __shared__ u32 s_cnt[PR_WARPS][PR_MAXT];
+    __shared__ int s_lcp[PR_WARPS][PR_MAXT];
+    __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group, 0xFF: not a small group
+    __shared__ unsigned char s_def[PR_WARPS][PR_MAXT];  // at the head slot: group deferred to the doubling rounds
     const u32 *__restrict__ W = (const u32 *)T;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const i64 chunk0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
-    unsigned short *queue = s_queue[w];
+    u32 *queue = s_queue[w];
+    u32 *cnt = s_cnt[w];
+    int *lcpv = s_lcp[w];
+    unsigned char *sL = s_L[w], *sdef = s_def[w];
 
-    // ---- enqueue: slot t of the chunk contributes the pairs (t, t-d), d = 1..L ----
-    u32 qn = 0;
-#pragma unroll
-    for (int i = 0; i < PR_SPL; i++) {
-        const int t = i * 32 + (int)lane;
-        const i64 e = chunk0 + t;
-        int c = 0;
-        if (e < n) {
+    // ---- the warp's run of whole groups: [s, end) ----
+    const i64 c0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
+    i64 s = c0, end = c0 + PR_CHUNK < n ? c0 + PR_CHUNK : n;
+    if (lane == 0 && c0 < n) {
+        if (c0 > 0) {
             int L, R;
-            run_lengths(keys, n, e, SA_SMALL_G, L, R);
-            if (L + R + 1 <= SA_SMALL_G) c = L;
-            else if (L == 0) *flag_large = 1u;
+            run_lengths(keys, n, c0, SA_SMALL_G, L, R);
+            if (L > 0 && L + R + 1 <= SA_SMALL_G) s = c0 + R + 1;  // that group belongs to the previous warp
         }
-        u32 inc = warp_incl_sum((u32)c);
-        u32 at = qn + inc - (u32)c;
-        for (int d = 1; d <= c; d++) queue[at + d - 1] = (unsigned short)((t << 4) | d);
-        qn += __shfl_sync(FULL, inc, 31);
+        if (end < n) {
+            int L, R;
+            run_lengths(keys, n, end, SA_SMALL_G, L, R);
+            if (L > 0 && L + R + 1 <= SA_SMALL_G) end = end + R + 1;  // finish the group that straddles the nominal end
+        }
     }
-    __syncwarp();
+    s = __shfl_sync(FULL, s, 0);
+    end = __shfl_sync(FULL, end, 0);
+    const int nt = c0 < n && end > s ? (int)(end - s) : 0;  // local slots t = 0 .. nt-1
+    const int rounds = (nt + 31) / 32;
 
-    // ---- flattened comparison loop ----
-    u32 next = 0;
-    bool active = false;
-    i64 ex = 0, ey = 0, p = 0, q = 0, lenmin = 0, h = 0;
-    u32 x = 0, y = 0;
-    i64 ia = 0, ib = 0;
-    unsigned sha = 0, shb = 0;
-    u32 lo_a = 0, lo_b = 0;
-    for (;;) {
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (!active) {
-            u32 idx = next + (u32)__popc(idle & lanemask_lt());
-            if (idx < qn) {
-                unsigned it = queue[idx];
-                ex = chunk0 + (it >> 4);
-                ey = ex - (i64)(it & 15u);
-                x = sa[ex];
-                y = sa[ey];
-                p = (i64)x + skip;
-                q = (i64)y + skip;
-                lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
-                ia = p >> 2;
-                ib = q >> 2;
-                sha = (unsigned)(p & 3) * 8u;
-                shb = (unsigned)(q & 3) * 8u;
-                lo_a = W[ia];
-                lo_b = W[ib];
-                h = 0;
-                active = true;
+    u32 qn = 0, next = 0;  // ring: items [next, qn)
+    int round = 0;
+    while (round < rounds) {
+        // ---- enqueue rounds of 32 slots while the ring has room for a worst-case round ----
+        while (round < rounds && (qn - next) + PR_ROUND_ITEMS <= PR_QCAP) {
+            const int t = round * 32 + (int)lane;
+            int c = 0;
+            if (t < nt) {
+                int L, R;
+                run_lengths(keys, n, s + t, SA_SMALL_G, L, R);
+                const bool small = L + R + 1 <= SA_SMALL_G;
+                sL[t] = small ? (unsigned char)L : (unsigned char)0xFF;
+                cnt[t] = 0;
+                lcpv[t] = 0;
+                sdef[t] = 0;
+                if (small) c = L;
+                else if (L == 0) *flag_large = 1u;
             }
+            u32 inc = warp_incl_sum((u32)c);
+            u32 at = qn + inc - (u32)c;
+            for (int d = 1; d <= c; d++) queue[(at + d - 1) & (PR_QCAP - 1)] = ((u32)t << 4) | (u32)d;
+            qn += __shfl_sync(FULL, inc, 31);
+            round++;
         }
-        next += (u32)__popc(idle);
-        if (!__any_sync(FULL, active)) break;
-        if (active) {
-            u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
-            u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
-            u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
-            u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
-            u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
-            u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
-            bool done = false, x_less = false;
-            i64 match = 0;
-            if (d0 | d1 | d2 | d3) {
-                int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
-                u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-                int byte = (__ffs((int)dd) - 1) >> 3;
-                i64 at = h + wsel * 4 + byte;  // first differing byte, counted from p / q
-                done = true;
-                if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
-                    match = lenmin;
-                    x_less = p > q;  // the shorter suffix (larger start) sorts first
-                } else {
-                    match = at;
-                    x_less = T[p + at] < T[q + at];
+        __syncwarp();
+
+        // ---- drain: flattened comparison loop ----
+        bool active = false;
+        int tx = 0, ty = 0;
+        u32 x = 0, y = 0;
+        i64 p = 0, q = 0, lenmin = 0, h = 0, ia = 0, ib = 0;
+        unsigned sha = 0, shb = 0;
+        u32 lo_a = 0, lo_b = 0;
+        for (;;) {
+            unsigned idle = __ballot_sync(FULL, !active);
+            if (!active) {
+                u32 idx = next + (u32)__popc(idle & lanemask_lt());
+                if ((int)(qn - idx) > 0) {
+                    u32 it = queue[idx & (PR_QCAP - 1)];
+                    tx = (int)(it >> 4);
+                    ty = tx - (int)(it & 15u);
+                    x = sa[s + tx];
+                    y = sa[s + ty];
+                    p = (i64)x + skip;
+                    q = (i64)y + skip;
+                    lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
+                    ia = p >> 2;
+                    ib = q >> 2;
+                    sha = (unsigned)(p & 3) * 8u;
+                    shb = (unsigned)(q & 3) * 8u;
+                    lo_a = W[ia];
+                    lo_b = W[ib];
+                    h = 0;
+                    active = true;
                 }
-            } else {
-                h += 16;
-                ia += 4;
-                ib += 4;
-                lo_a = a4;
-                lo_b = b4;
-                if (h >= lenmin) {
+            }
+            {
+                u32 taken = (u32)__popc(idle), avail = qn - next;
+                next += taken < avail ? taken : avail;
+            }
+            if (!__any_sync(FULL, active)) break;
+            if (active) {
+                u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
+                u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
+                u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
+                u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
+                u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
+                u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
+                u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
+                bool done = false, x_less = false;
+                i64 match = 0;
+                if (d0 | d1 | d2 | d3) {
+                    int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
+                    u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+                    u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
+                    u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
+                    int bsh = (__ffs((int)dd) - 1) & ~7;     // bit offset of the first differing byte
+                    i64 at = h + wsel * 4 + (bsh >> 3);      // counted from p / q
                     done = true;
-                    match = lenmin;
-                    x_less = p > q;
-                } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
-                    int L, R;
-                    run_lengths(keys, n, ex, SA_SMALL_G, L, R);
-                    deferred[ex - L] = 1;
-                    *flag_large = 1u;
+                    if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
+                        match = lenmin;
+                        x_less = p > q;  // the shorter suffix (larger start) sorts first
+                    } else {
+                        match = at;
+                        x_less = ((va >> bsh) & 0xffu) < ((vb >> bsh) & 0xffu);
+                    }
+                } else {
+                    h += 16;
+                    ia += 4;
+                    ib += 4;
+                    lo_a = a4;
+                    lo_b = b4;
+                    if (h >= lenmin) {
+                        done = true;
+                        match = lenmin;
+                        x_less = p > q;
+                    } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                        sdef[tx - (int)sL[tx]] = 1;
+                        active = false;
+                    }
+                }
+                if (done) {
+                    // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
+                    i64 lcp = first_barrier(bar0, bar1, (i64)x, (i64)skip + match);
+                    int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
+                    atomicAdd(&cnt[big], 1u);
+                    atomicMax(&lcpv[big], (int)lcp);
                     active = false;
                 }
             }
-            if (done) {
-                // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
-                i64 lcp = first_barrier(bar, (i64)x, (i64)skip + match);
-                i64 big = x_less ? ey : ex;  // slot (before placing) of the larger suffix: it gains a smaller mate
-                atomicAdd(&cnt[big], 1u);
-                atomicMax(&lcpv[big], (int)lcp);
-                active = false;
-            }
         }
+        __syncwarp();
+    }
+
+    // ---- place the warp's groups: slot = group start + number of smaller mates ----
+    for (int t = (int)lane; t < nt; t += 32) {
+        unsigned L = sL[t];
+        if (L == 0xFFu) continue;  // member of a group with more than SA_SMALL_G suffixes: stage 4
+        const int t0 = t - (int)L;
+        if (sdef[t0]) {
+            if (L == 0) {
+                deferred[s + t] = 1;
+                *flag_large = 1u;
+            }
+            continue;
+        }
+        u32 r = cnt[t];
+        i64 slot = s + t0 + (i64)r;
+        u32 suf = sa[s + t];
+        SA[slot] = (int)suf;
+        rank[suf] = (int)slot;
+        if (r > 0) LCP[slot] = lcpv[t];  // the smallest member's entry crosses the group boundary: sa_headlcp_kernel
     }
 }
 
-// place every member of a finished group: slot = group start + number of smaller mates
+// LCP entry of the first slot of every group: its left neighbour differs inside the k-mer, so one
+// (two for long keys) 16-byte comparison step from the suffix starts settles it.
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ cnt, const int *__restrict__ lcpv,
-                const unsigned char *__restrict__ deferred, int *__restrict__ SA, int *__restrict__ rank, int *__restrict__ LCP) {
-    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    int L, R;
-    run_lengths(keys, n, e, SA_SMALL_G, L, R);
-    if (L + R + 1 > SA_SMALL_G || (L + R > 0 && deferred[e - L])) return;  // stage 4
-    u32 r = cnt[e];
-    i64 slot = e - L + (i64)r;
-    u32 s = sa[e];
-    SA[slot] = (int)s;
-    rank[s] = (int)slot;
-    if (r > 0) LCP[slot] = lcpv[e];  // the smallest member's entry crosses the group boundary: sa_headlcp_kernel
-}
-
-// LCP entry of the first slot of every group: neighbours differ inside the k-mer, compare from scratch
-template <typename KeyT>
-__global__ void __launch_bounds__(256)
-sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ T, const int *__restrict__ SA, int *__restrict__ LCP) {
+sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
+                  const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
+    const u32 *__restrict__ W = (const u32 *)T;
     i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     if (j == 0) {
@@ -272,14 +335,33 @@ sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__r
         return;
     }
     if (keys[j] == keys[j - 1]) return;
-    i64 a = SA[j], b = SA[j - 1];
-    int h = 0;
-    while (a + h < n && b + h < n) {
-        unsigned char c = T[a + h];
-        if (c != T[b + h] || c == '$' || c == 'N') break;
-        h++;
+    const i64 p = SA[j], q = SA[j - 1];
+    const i64 lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
+    i64 ia = p >> 2, ib = q >> 2;
+    const unsigned sha = (unsigned)(p & 3) * 8u, shb = (unsigned)(q & 3) * 8u;
+    u32 lo_a = W[ia], lo_b = W[ib];
+    i64 h = 0, match = lenmin;
+    while (h < lenmin) {
+        u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
+        u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
+        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
+        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+        if (d0 | d1 | d2 | d3) {
+            int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
+            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+            i64 at = h + wsel * 4 + ((__ffs((int)dd) - 1) >> 3);
+            match = at < lenmin ? at : lenmin;
+            break;
+        }
+        h += 16;
+        ia += 4;
+        ib += 4;
+        lo_a = a4;
+        lo_b = b4;
     }
-    LCP[j] = h;
+    LCP[j] = (int)first_barrier(bar0, bar1, p, match);
 }
 
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
@@ -426,14 +508,14 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + a / 8 + 1024 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + a / 8 + a / 256 + 4096 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
     u64 *k0, *k1;
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
     unsigned char *deferred;
-    u32 *bar;  // barrier bitmask, (n+31)/32 + 2 words
+    u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
     void *rscratch;
 };
 
@@ -452,26 +534,20 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     if (pt) pt->sa_sorted_items += n;
     KeyT *keys = in0 ? k0 : k1;
     u32 *sa = in0 ? B.v0 : B.v1;
-    // comparison stage: cnt = grpA, lcpv = grpB (both free until stage 4)
-    u32 *cnt = B.grpA;
-    int *lcpv = (int *)B.grpB;
-    RV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * 4, st.s));
-    RV_CUDA(cudaMemsetAsync(lcpv, 0, (size_t)n * 4, st.s));
+    // comparison stage
     RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    const i64 bar_words = (n + 31) / 32 + 2;
-    RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((bar_words * 32 + 255) / 256), 256, 0, st.s, dT, n, B.bar, bar_words);
+    RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((n + 1023) / 1024 + 1), 1024, 0, st.s, dT, n, B.bar, B.bar1);
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
-    RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, k, cnt,
-              lcpv, B.deferred, B.small + 257);
-    RV_LAUNCH((sa_place_kernel<KeyT>), blocks, 256, 0, st.s, keys, sa, n, cnt, lcpv, B.deferred, dSA, dISA, dLCP);
-    st.launches += 3;
+    RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, B.bar1, k,
+              dSA, dISA, dLCP, B.deferred, B.small + 257);
+    st.launches += 2;
     u32 lg = 0;
     RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
     RV_CUDA(cudaStreamSynchronize(st.s));
     *large = lg != 0;
     if (!*large) {
-        RV_LAUNCH((sa_headlcp_kernel<KeyT>), blocks, 256, 0, st.s, keys, n, dT, dSA, dLCP);
+        RV_LAUNCH((sa_headlcp_kernel<KeyT>), blocks, 256, 0, st.s, keys, n, dT, B.bar, B.bar1, dSA, dLCP);
         st.launches++;
     }
     RV_KCHECK();
@@ -558,8 +634,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
     B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
     B.deferred = ws.take<unsigned char>(n);
-    B.bar = ws.take<u32>((n + 31) / 32 + 2);
-    if (!B.deferred || !B.bar || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    B.bar = ws.take<u32>(n / 32 + 98);
+    B.bar1 = ws.take<u32>(n / 1024 + 8);
+    if (!B.deferred || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;

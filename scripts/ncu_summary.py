@@ -25,18 +25,34 @@ for r in rows[2:]:
             i = hdr.index(w)
             print("%-90s %s %s" % (w, r[i][:100], units[i]))
 if len(sys.argv) > 2:
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(src.splitlines()))
-    # find header row
-    for hi, r in enumerate(rows):
-        if "Source" in r and any("Sampl" in c for c in r):
-            break
-    h = rows[hi]
-    si = h.index("Source")
-    ci = [i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)" or "Samples" in c][0]
-    body = [r for r in rows[hi + 1:] if len(r) > ci and r[ci].replace(".", "").isdigit()]
-    tot = sum(float(r[ci]) for r in body) or 1
-    body.sort(key=lambda r: -float(r[ci]))
-    print("hottest source lines (%s):" % h[ci])
-    for r in body[:int(sys.argv[2])]:
-        print("%6.1f%%  %s" % (100 * float(r[ci]) / tot, r[si].strip()[:140]))
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    cur_file, h = "", None
+    lines = {}   # (file, line, text) -> [samples, instructions]
+    tot = 0.0
+    for r in csv.reader(src.splitlines()):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+            continue
+        if r[0] == "Function Name":
+            continue
+        if r[0] == "Line No":
+            h = r
+            ci = h.index("# Samples")
+            ii = h.index("Instructions Executed")
+            continue
+        if h is None or len(r) <= ci:
+            continue
+        if r[0] != "":      # a CUDA source line row (aggregated over its SASS)
+            try:
+                v = float(r[ci]); ins = float(r[ii])
+            except ValueError:
+                continue
+            key = (cur_file, r[0], r[1].strip())
+            e = lines.setdefault(key, [0.0, 0.0])
+            e[0] += v; e[1] += ins
+            tot += v
+    print("hottest source lines (# warp-stall samples; warp instructions executed):")
+    for (f, ln, text), (v, ins) in sorted(lines.items(), key=lambda x: -x[1][0])[:int(sys.argv[2])]:
+        print("%5.1f%%  %10.0f inst  %s:%s  %s" % (100 * v / (tot or 1), ins, f, ln, text[:110]))
