@@ -114,11 +114,19 @@ __device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar0, const
     if (len <= 0) return 0;
     i64 w = x >> 5;
     const i64 wl = (x + len - 1) >> 5;
-    if ((w >> 5) == (wl >> 5)) {  // all level-0 words under one level-1 word: usually "nothing here"
-        u32 m1 = bar1[w >> 5] >> (unsigned)(w & 31);
-        unsigned span = (unsigned)(wl - w);  // words w .. w+span
-        if (span < 31u) m1 &= (2u << span) - 1u;
-        if (m1 == 0u) return len;
+    if (wl - w < 32) {  // at most two level-1 words cover the range: usually "nothing here"
+        const i64 v = w >> 5, vl = wl >> 5;
+        u32 m = bar1[v] >> (unsigned)(w & 31);          // words w .. end of level-1 word v
+        if (v == vl) {
+            unsigned span = (unsigned)(wl - w);
+            if (span < 31u) m &= (2u << span) - 1u;
+        } else {
+            unsigned last = (unsigned)(wl & 31);         // words 0 .. last of level-1 word vl
+            u32 m2 = bar1[vl];
+            if (last < 31u) m2 &= (2u << last) - 1u;
+            m |= m2;
+        }
+        if (m == 0u) return len;
     }
     unsigned sh = (unsigned)(x & 31);
     u32 bits = bar0[w] >> sh;
@@ -137,38 +145,45 @@ __device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar0, const
 
 static const int PR_THREADS = 128;
 static const int PR_WARPS = PR_THREADS / 32;
-static const int PR_CHUNK = 512;                       // nominal SA slots per warp
-static const int PR_MAXT = PR_CHUNK + SA_SMALL_G;      // a chunk is stretched to whole groups
-static const int PR_QCAP = 1024;                       // ring of work items per warp
-static const int PR_ROUND_ITEMS = 32 * (SA_SMALL_G - 1);
+static const int PR_CHUNK = 256;                       // nominal SA slots per warp
+static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched to whole groups (<= SA_SMALL_G more), padded to rounds
+static const int PR_ROUNDS = PR_MAXT / 32;
+static const int PR_QCAP = 512;                        // ring of work items per warp (>= one worst-case round of 32*15)
 
 // One warp owns a run of whole groups (about PR_CHUNK consecutive SA slots).  Every pair (member,
 // earlier mate) of a small group becomes a work item in the warp's shared-memory ring; lanes pull the
-// next item whenever they are idle, so all 32 lanes stay busy until the ring runs dry.  A comparison
-// step covers 16 text bytes: five aligned 32-bit words per suffix funnel-shifted to the suffix start,
-// XOR, first set bit.  The larger suffix of a pair gains one smaller mate (-> its place inside the
-// group) and the pair's common prefix (-> its LCP entry = the largest over its smaller mates); both
-// live in shared memory because a group never leaves its warp.  The warp then places its groups.
+// next item whenever they are idle and the ring is refilled as it runs low, so the lanes stay busy
+// until the chunk is done.  A comparison step covers 16 text bytes: five aligned 32-bit words per
+// suffix funnel-shifted to the suffix start, XOR, first set bit.  The larger suffix of a pair gains one
+// smaller mate (-> its place inside the group) and the pair's common prefix (-> its LCP entry = the
+// largest over its smaller mates); both live in shared memory because a group never leaves its warp.
+// The warp then places its groups: SA, inverse SA and LCP.
 template <typename KeyT>
-__global__ void __launch_bounds__(PR_THREADS)
+__global__ void __launch_bounds__(PR_THREADS, 10)
 sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T,
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
                 int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
-    __shared__ u32 s_queue[PR_WARPS][PR_QCAP];
-    __shared__ u32 s_cnt[PR_WARPS][PR_MAXT];
+    __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
     __shared__ int s_lcp[PR_WARPS][PR_MAXT];
-    __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group, 0xFF: not a small group
-    __shared__ unsigned char s_def[PR_WARPS][PR_MAXT];  // at the head slot: group deferred to the doubling rounds
+    __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
+    __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group; 0xFF: not a small group
+    __shared__ unsigned short s_queue[PR_WARPS][PR_QCAP];
+    __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];     // bit t: slot t starts a group
+    __shared__ u32 s_def[PR_WARPS][PR_ROUNDS];          // bit t0: the group starting at t0 is deferred to stage 4
     const u32 *__restrict__ W = (const u32 *)T;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    u32 *queue = s_queue[w];
-    u32 *cnt = s_cnt[w];
+    u32 *ssa = s_sa[w];
     int *lcpv = s_lcp[w];
-    unsigned char *sL = s_L[w], *sdef = s_def[w];
+    u32 *cnt = s_cnt[w];
+    unsigned char *sL = s_L[w];
+    unsigned short *queue = s_queue[w];
+    u32 *head = s_head[w] + 1;  // head[-1] and head[PR_ROUNDS] exist (zero) for the 64-bit windows
+    u32 *sdef = s_def[w];
 
     // ---- the warp's run of whole groups: [s, end) ----
     const i64 c0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
     i64 s = c0, end = c0 + PR_CHUNK < n ? c0 + PR_CHUNK : n;
+    int end_closed = 1;  // the last group of the run really ends at `end`
     if (lane == 0 && c0 < n) {
         if (c0 > 0) {
             int L, R;
@@ -178,143 +193,181 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         if (end < n) {
             int L, R;
             run_lengths(keys, n, end, SA_SMALL_G, L, R);
-            if (L > 0 && L + R + 1 <= SA_SMALL_G) end = end + R + 1;  // finish the group that straddles the nominal end
+            if (L > 0) {
+                if (L + R + 1 <= SA_SMALL_G) end = end + R + 1;     // finish the group that straddles the nominal end
+                else end_closed = 0;                                  // a large group runs through the end
+            }
         }
     }
     s = __shfl_sync(FULL, s, 0);
     end = __shfl_sync(FULL, end, 0);
+    end_closed = __shfl_sync(FULL, end_closed, 0);
     const int nt = c0 < n && end > s ? (int)(end - s) : 0;  // local slots t = 0 .. nt-1
+    if (nt == 0) return;  // warp-uniform
     const int rounds = (nt + 31) / 32;
 
+    // ---- stage suffixes, group heads and per-slot state ----
+    if (lane < 2) s_head[w][lane ? PR_ROUNDS + 1 : 0] = 0u;
+    for (int r = 0; r < rounds; r++) {
+        const int t = r * 32 + (int)lane;
+        const i64 e = s + t;
+        const bool valid = t < nt;
+        KeyT k = valid ? keys[e] : (KeyT)0;
+        KeyT kp = __shfl_up_sync(FULL, k, 1);
+        if (lane == 0) kp = (valid && e > 0) ? keys[e - 1] : (KeyT)0;
+        bool is_head = valid && (e == 0 || k != kp);
+        unsigned hm = __ballot_sync(FULL, is_head);
+        if (lane == 0) {
+            head[r] = hm;
+            sdef[r] = 0u;
+        }
+        ssa[t] = valid ? sa[e] : 0u;
+        lcpv[t] = 0;
+        if ((lane & 3u) == 0) cnt[t >> 2] = 0u;
+    }
+    for (int r = rounds; r < PR_ROUNDS; r++)
+        if (lane == 0) head[r] = 0u;
+    __syncwarp();
+
+    // ---- unified loop: refill the ring when it runs low, pull items, compare ----
     u32 qn = 0, next = 0;  // ring: items [next, qn)
     int round = 0;
-    while (round < rounds) {
-        // ---- enqueue rounds of 32 slots while the ring has room for a worst-case round ----
-        while (round < rounds && (qn - next) + PR_ROUND_ITEMS <= PR_QCAP) {
+    bool active = false;
+    int tx = 0, ty = 0;
+    u32 x = 0;
+    i64 p = 0, q = 0, lenmin = 0, h = 0, ia = 0, ib = 0;
+    unsigned sha = 0, shb = 0;
+    u32 lo_a = 0, lo_b = 0;
+    for (;;) {
+        // refill (warp-uniform condition)
+        while (round < rounds && (qn - next) < 64u) {
             const int t = round * 32 + (int)lane;
             int c = 0;
             if (t < nt) {
-                int L, R;
-                run_lengths(keys, n, s + t, SA_SMALL_G, L, R);
-                const bool small = L + R + 1 <= SA_SMALL_G;
+                const unsigned b = (unsigned)t & 31u;
+                // previous head at or before t: window = head[round-1] : head[round]
+                u64 v = ((u64)head[round] << 32) | (u64)head[round - 1];
+                u64 below = v & ((2ull << (32u + b)) - 1ull);
+                int L = below ? (int)(32u + b) - (63 - __clzll((long long)below)) : 0xFF;
+                // next head after t: window = head[round] : head[round+1]
+                u64 v2 = (((u64)head[round + 1] << 32) | (u64)head[round]) >> (b + 1u);
+                int R;
+                if (v2) R = __ffsll((long long)v2) - 1;
+                else R = 0xFF;
+                if (R != 0xFF && t + R + 1 > nt) R = 0xFF;          // (cannot happen: no head bits beyond nt)
+                if (R == 0xFF && t + 33 >= nt) R = end_closed ? nt - 1 - t : 0xFF;  // the run ends the group
+                const bool small = L != 0xFF && R != 0xFF && L + R + 1 <= SA_SMALL_G;
                 sL[t] = small ? (unsigned char)L : (unsigned char)0xFF;
-                cnt[t] = 0;
-                lcpv[t] = 0;
-                sdef[t] = 0;
                 if (small) c = L;
                 else if (L == 0) *flag_large = 1u;
             }
             u32 inc = warp_incl_sum((u32)c);
+            u32 total = __shfl_sync(FULL, inc, 31);
+            if ((qn - next) + total > (u32)PR_QCAP) break;  // no room yet: drain first (sL rewritten later, same values)
             u32 at = qn + inc - (u32)c;
-            for (int d = 1; d <= c; d++) queue[(at + d - 1) & (PR_QCAP - 1)] = ((u32)t << 4) | (u32)d;
-            qn += __shfl_sync(FULL, inc, 31);
+            for (int d = 1; d <= c; d++) queue[(at + d - 1) & (PR_QCAP - 1)] = (unsigned short)(((u32)t << 4) | (u32)d);
+            qn += total;
             round++;
+            __syncwarp();
         }
-        __syncwarp();
-
-        // ---- drain: flattened comparison loop ----
-        bool active = false;
-        int tx = 0, ty = 0;
-        u32 x = 0, y = 0;
-        i64 p = 0, q = 0, lenmin = 0, h = 0, ia = 0, ib = 0;
-        unsigned sha = 0, shb = 0;
-        u32 lo_a = 0, lo_b = 0;
-        for (;;) {
-            unsigned idle = __ballot_sync(FULL, !active);
-            if (!active) {
-                u32 idx = next + (u32)__popc(idle & lanemask_lt());
-                if ((int)(qn - idx) > 0) {
-                    u32 it = queue[idx & (PR_QCAP - 1)];
-                    tx = (int)(it >> 4);
-                    ty = tx - (int)(it & 15u);
-                    x = sa[s + tx];
-                    y = sa[s + ty];
-                    p = (i64)x + skip;
-                    q = (i64)y + skip;
-                    lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
-                    ia = p >> 2;
-                    ib = q >> 2;
-                    sha = (unsigned)(p & 3) * 8u;
-                    shb = (unsigned)(q & 3) * 8u;
-                    lo_a = W[ia];
-                    lo_b = W[ib];
-                    h = 0;
-                    active = true;
-                }
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!active) {
+            u32 idx = next + (u32)__popc(idle & lanemask_lt());
+            if ((int)(qn - idx) > 0) {
+                u32 it = queue[idx & (PR_QCAP - 1)];
+                tx = (int)(it >> 4);
+                ty = tx - (int)(it & 15u);
+                x = ssa[tx];
+                u32 y = ssa[ty];
+                p = (i64)x + skip;
+                q = (i64)y + skip;
+                lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
+                ia = p >> 2;
+                ib = q >> 2;
+                sha = (unsigned)(p & 3) * 8u;
+                shb = (unsigned)(q & 3) * 8u;
+                lo_a = W[ia];
+                lo_b = W[ib];
+                h = 0;
+                active = true;
             }
-            {
-                u32 taken = (u32)__popc(idle), avail = qn - next;
-                next += taken < avail ? taken : avail;
-            }
-            if (!__any_sync(FULL, active)) break;
-            if (active) {
-                u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
-                u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
-                u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
-                u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
-                u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
-                u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
-                u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
-                bool done = false, x_less = false;
-                i64 match = 0;
-                if (d0 | d1 | d2 | d3) {
-                    int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
-                    u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-                    u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
-                    u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
-                    int bsh = (__ffs((int)dd) - 1) & ~7;     // bit offset of the first differing byte
-                    i64 at = h + wsel * 4 + (bsh >> 3);      // counted from p / q
-                    done = true;
-                    if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
-                        match = lenmin;
-                        x_less = p > q;  // the shorter suffix (larger start) sorts first
-                    } else {
-                        match = at;
-                        x_less = ((va >> bsh) & 0xffu) < ((vb >> bsh) & 0xffu);
-                    }
+        }
+        {
+            u32 taken = (u32)__popc(idle), avail = qn - next;
+            next += taken < avail ? taken : avail;
+        }
+        if (!__any_sync(FULL, active)) {
+            if (round >= rounds) break;
+            continue;  // ring empty but slots left: refill
+        }
+        if (active) {
+            u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
+            u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
+            u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
+            u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
+            u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
+            u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
+            u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
+            bool done = false, x_less = false;
+            i64 match = 0;
+            if (d0 | d1 | d2 | d3) {
+                int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
+                u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+                u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
+                u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
+                int bsh = (__ffs((int)dd) - 1) & ~7;     // bit offset of the first differing byte
+                i64 at = h + wsel * 4 + (bsh >> 3);      // counted from p / q
+                done = true;
+                if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
+                    match = lenmin;
+                    x_less = p > q;  // the shorter suffix (larger start) sorts first
                 } else {
-                    h += 16;
-                    ia += 4;
-                    ib += 4;
-                    lo_a = a4;
-                    lo_b = b4;
-                    if (h >= lenmin) {
-                        done = true;
-                        match = lenmin;
-                        x_less = p > q;
-                    } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
-                        sdef[tx - (int)sL[tx]] = 1;
-                        active = false;
-                    }
+                    match = at;
+                    x_less = ((va >> bsh) & 0xffu) < ((vb >> bsh) & 0xffu);
                 }
-                if (done) {
-                    // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
-                    i64 lcp = first_barrier(bar0, bar1, (i64)x, (i64)skip + match);
-                    int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
-                    atomicAdd(&cnt[big], 1u);
-                    atomicMax(&lcpv[big], (int)lcp);
+            } else {
+                h += 16;
+                ia += 4;
+                ib += 4;
+                lo_a = a4;
+                lo_b = b4;
+                if (h >= lenmin) {
+                    done = true;
+                    match = lenmin;
+                    x_less = p > q;
+                } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                    int t0 = tx - (int)sL[tx];
+                    atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
                     active = false;
                 }
             }
+            if (done) {
+                // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
+                i64 lcp = first_barrier(bar0, bar1, (i64)x, (i64)skip + match);
+                int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
+                atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
+                atomicMax(&lcpv[big], (int)lcp);
+                active = false;
+            }
         }
-        __syncwarp();
     }
+    __syncwarp();
 
     // ---- place the warp's groups: slot = group start + number of smaller mates ----
     for (int t = (int)lane; t < nt; t += 32) {
         unsigned L = sL[t];
         if (L == 0xFFu) continue;  // member of a group with more than SA_SMALL_G suffixes: stage 4
         const int t0 = t - (int)L;
-        if (sdef[t0]) {
+        if ((sdef[t0 >> 5] >> (t0 & 31)) & 1u) {
             if (L == 0) {
                 deferred[s + t] = 1;
                 *flag_large = 1u;
             }
             continue;
         }
-        u32 r = cnt[t];
+        u32 r = (cnt[t >> 2] >> (8 * (t & 3))) & 0xffu;
         i64 slot = s + t0 + (i64)r;
-        u32 suf = sa[s + t];
+        u32 suf = ssa[t];
         SA[slot] = (int)suf;
         rank[suf] = (int)slot;
         if (r > 0) LCP[slot] = lcpv[t];  // the smallest member's entry crosses the group boundary: sa_headlcp_kernel
