@@ -53,6 +53,12 @@ inline RadixPlan make_plan(int lo0, int hi0, int lo1 = 0, int hi1 = 0) {
     return p;
 }
 
+inline int mask_bits(u32 m) {
+    int b = 0;
+    while (m) { b++; m >>= 1; }
+    return b;
+}
+
 inline size_t radix_scratch_bytes(i64 n) {
     i64 tiles = (n + RS_TILE - 1) / RS_TILE;
     // [hist npass*256][base npass*256][ticket 8][status npass*tiles*256]
@@ -89,10 +95,10 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict_
 }
 
 template <typename KeyT, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin, u32 *__restrict__ vout,
-               i64 n, int shift, u32 mask, const u32 *__restrict__ gbase, u32 *status, u32 *ticket) {
-    __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> per-warp exclusive offsets
+               i64 n, int shift, u32 mask, int dbits, const u32 *__restrict__ gbase, u32 *status, u32 *ticket) {
+    __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> running per-warp offsets inside the bucket
     __shared__ u32 s_start[RS_BINS];             // first tile-local slot of each bucket
     __shared__ u32 s_off[RS_BINS];               // global slot of a bucket's first item minus s_start (mod 2^32)
     __shared__ u32 s_scan[33];
@@ -109,77 +115,84 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
     const i64 base = (i64)tile * RS_TILE;
     const int cnt = (int)((n - base) < (i64)RS_TILE ? (n - base) : (i64)RS_TILE);
 
-    // ---- load (warp-striped: a warp owns 32*IPT consecutive pairs) and rank ----
+    // ---- load (warp-striped: a warp owns 32*IPT consecutive pairs) + early per-warp bucket counts ----
     KeyT key[RS_IPT];
-    unsigned short rnk[RS_IPT];
     const int wbase = (int)w * 32 * RS_IPT;
+    u32 *wh = s_whist + w * RS_BINS;
 #pragma unroll
     for (int k = 0; k < RS_IPT; k++) {
         int idx = wbase + k * 32 + (int)l;
         key[k] = idx < cnt ? kin[base + idx] : (KeyT)0;
     }
-    u32 *wh = s_whist + w * RS_BINS;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; k++) {
+        int idx = wbase + k * 32 + (int)l;
+        if (idx < cnt) atomicAdd(&wh[(u32)(key[k] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+
+    // ---- per bucket: exclusive warp offsets, tile count (published at once), tile-local start ----
+    u32 run = 0;
+    u32 *my = status + (size_t)tile * RS_BINS + tid;  // RS_THREADS == RS_BINS: thread d owns bucket d
+    {
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            u32 t = s_whist[ww * RS_BINS + tid];
+            s_whist[ww * RS_BINS + tid] = run;
+            run += t;
+        }
+        // successors can add this tile's count while it is still ranking
+        st_volatile(my, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | run);
+        u32 total;
+        u32 inc = block_incl_sum<RS_THREADS>(run, s_scan, &total);
+        s_start[tid] = inc - run;
+    }
+    __syncthreads();
+
+    // ---- rank with ballots (peers = lanes of the warp holding the same digit) and stage in bucket order ----
 #pragma unroll
     for (int k = 0; k < RS_IPT; k++) {
         int idx = wbase + k * 32 + (int)l;
         bool valid = idx < cnt;
         u32 d = (u32)(key[k] >> shift) & mask;
-        unsigned peers = __match_any_sync(FULL, valid ? d : 0xffffu);
-        int leader = __ffs((int)peers) - 1;
+        unsigned peers = __ballot_sync(FULL, valid);
+        for (int b = 0; b < dbits; b++) {
+            unsigned bal = __ballot_sync(FULL, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
         u32 old = 0;
+        const int leader = __ffs((int)peers) - 1;  // invalid lanes: garbage, unused
         if (valid && (int)l == leader) {
             old = wh[d];
             wh[d] = old + (u32)__popc(peers);
         }
-        old = __shfl_sync(FULL, old, leader);
-        rnk[k] = (unsigned short)(old + (u32)__popc(peers & lanemask_lt()));
+        old = __shfl_sync(FULL, old, leader & 31);
+        if (valid) {
+            u32 p = s_start[d] + old + (u32)__popc(peers & lanemask_lt());
+            s_keys[p] = key[k];
+            if (HAS_VAL) s_vals[p] = vin[base + idx];
+        }
         __syncwarp();
     }
-    __syncthreads();
 
-    // ---- per-bucket: warp offsets, tile count, tile-local start, look-back ----
+    // ---- decoupled look-back for the bucket's global offset ----
     {
-        const u32 d = tid;  // RS_THREADS == RS_BINS
-        u32 run = 0;
-#pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) {
-            u32 t = s_whist[ww * RS_BINS + d];
-            s_whist[ww * RS_BINS + d] = run;
-            run += t;
-        }
-        u32 total;
-        u32 inc = block_incl_sum<RS_THREADS>(run, s_scan, &total);
-        u32 start = inc - run;
-        s_start[d] = start;
         u32 excl = 0;
-        u32 *my = status + (size_t)tile * RS_BINS + d;
         if (tile > 0) {
-            st_volatile(my, RS_FLAG_AGG | run);
             for (i64 t = (i64)tile - 1;; t--) {
-                const u32 *q = status + (size_t)t * RS_BINS + d;
+                const u32 *q = status + (size_t)t * RS_BINS + tid;
                 u32 v;
                 while (((v = ld_volatile(q)) & RS_FLAG_MASK) == 0u) { RV_SPIN(); }
                 excl += v & RS_VAL_MASK;
                 if ((v & RS_FLAG_MASK) == RS_FLAG_INCL) break;
             }
+            st_volatile(my, RS_FLAG_INCL | (excl + run));
         }
-        st_volatile(my, RS_FLAG_INCL | (excl + run));
-        s_off[d] = gbase[d] + excl - start;
+        s_off[tid] = gbase[tid] + excl - s_start[tid];
     }
     __syncthreads();
 
-    // ---- stage the tile in bucket order, then scatter contiguous runs ----------
-#pragma unroll
-    for (int k = 0; k < RS_IPT; k++) {
-        int idx = wbase + k * 32 + (int)l;
-        if (idx < cnt) {
-            u32 d = (u32)(key[k] >> shift) & mask;
-            u32 p = s_start[d] + wh[d] + rnk[k];
-            s_keys[p] = key[k];
-            if (HAS_VAL) s_vals[p] = vin[base + idx];
-        }
-    }
-    __syncthreads();
+    // ---- scatter contiguous per-bucket runs ----
     for (int p = tid; p < cnt; p += RS_THREADS) {
         KeyT kk = s_keys[p];
         u32 d = (u32)(kk >> shift) & mask;
@@ -223,7 +236,7 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     if (st.prof) RV_CUDA(cudaEventRecord(st.pe0, st.s));
     for (int p = 0; p < plan.npass; p++) {
         RV_LAUNCH((rs_pass_kernel<KeyT, true>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0,
-                  in0 ? v0 : v1, in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], gbase + p * RS_BINS,
+                  in0 ? v0 : v1, in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS,
                   status + (size_t)p * tiles * RS_BINS, ticket + p);
         st.launches++;
         in0 = !in0;
