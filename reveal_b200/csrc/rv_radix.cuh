@@ -150,6 +150,7 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
     __syncthreads();
 
     // ---- rank with ballots (peers = lanes of the warp holding the same digit) and stage in bucket order ----
+    unsigned short slot[RS_IPT];  // tile-local destination of every pair (the values follow in one batch of loads)
 #pragma unroll
     for (int k = 0; k < RS_IPT; k++) {
         int idx = wbase + k * 32 + (int)l;
@@ -170,9 +171,22 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
         if (valid) {
             u32 p = s_start[d] + old + (u32)__popc(peers & lanemask_lt());
             s_keys[p] = key[k];
-            if (HAS_VAL) s_vals[p] = vin[base + idx];
+            slot[k] = (unsigned short)p;
         }
         __syncwarp();
+    }
+    if (HAS_VAL) {
+        u32 val[RS_IPT];
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) {
+            int idx = wbase + k * 32 + (int)l;
+            val[k] = idx < cnt ? vin[base + idx] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) {
+            int idx = wbase + k * 32 + (int)l;
+            if (idx < cnt) s_vals[slot[k]] = val[k];
+        }
     }
 
     // ---- decoupled look-back for the bucket's global offset ----

@@ -110,36 +110,36 @@ __global__ void __launch_bounds__(1024) sa_barrier_bits_kernel(const unsigned ch
 }
 
 // offset of the first barrier character in T[x .. x+len), or len
-__device__ __forceinline__ i64 first_barrier(const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, i64 x, i64 len) {
-    if (len <= 0) return 0;
-    i64 w = x >> 5;
-    const i64 wl = (x + len - 1) >> 5;
-    if (wl - w < 32) {  // at most two level-1 words cover the range: usually "nothing here"
-        const i64 v = w >> 5, vl = wl >> 5;
-        u32 m = bar1[v] >> (unsigned)(w & 31);          // words w .. end of level-1 word v
+__device__ __forceinline__ u32 first_barrier(const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, u32 x, u32 len) {
+    if (len == 0u) return 0u;
+    u32 w = x >> 5;
+    const u32 wl = (x + len - 1u) >> 5;
+    if (wl - w < 32u) {  // at most two level-1 words cover the range: usually "nothing here"
+        const u32 v = w >> 5, vl = wl >> 5;
+        u32 m = bar1[v] >> (w & 31u);                   // words w .. end of level-1 word v
         if (v == vl) {
-            unsigned span = (unsigned)(wl - w);
+            u32 span = wl - w;
             if (span < 31u) m &= (2u << span) - 1u;
         } else {
-            unsigned last = (unsigned)(wl & 31);         // words 0 .. last of level-1 word vl
+            u32 last = wl & 31u;                         // words 0 .. last of level-1 word vl
             u32 m2 = bar1[vl];
             if (last < 31u) m2 &= (2u << last) - 1u;
             m |= m2;
         }
         if (m == 0u) return len;
     }
-    unsigned sh = (unsigned)(x & 31);
+    u32 sh = x & 31u;
     u32 bits = bar0[w] >> sh;
-    i64 base = 0, have = 32 - sh;
+    u32 base = 0, have = 32u - sh;
     for (;;) {
         if (bits) {
-            i64 at = base + (__ffs((int)bits) - 1);
+            u32 at = base + (u32)(__ffs((int)bits) - 1);
             return at < len ? at : len;
         }
         base += have;
         if (base >= len) return len;
         bits = bar0[++w];
-        have = 32;
+        have = 32u;
     }
 }
 
@@ -235,9 +235,11 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     bool active = false;
     int tx = 0, ty = 0;
     u32 x = 0;
-    i64 p = 0, q = 0, lenmin = 0, h = 0, ia = 0, ib = 0;
+    u32 p = 0, q = 0, lenmin = 0, h = 0;  // n < 2^30: text offsets fit 32 bits
+    const u32 *pa = W, *pb = W;
     unsigned sha = 0, shb = 0;
     u32 lo_a = 0, lo_b = 0;
+    const u32 n32 = (u32)n;
     for (;;) {
         // refill (warp-uniform condition)
         while (round < rounds && (qn - next) < 64u) {
@@ -279,15 +281,15 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                 ty = tx - (int)(it & 15u);
                 x = ssa[tx];
                 u32 y = ssa[ty];
-                p = (i64)x + skip;
-                q = (i64)y + skip;
-                lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
-                ia = p >> 2;
-                ib = q >> 2;
-                sha = (unsigned)(p & 3) * 8u;
-                shb = (unsigned)(q & 3) * 8u;
-                lo_a = W[ia];
-                lo_b = W[ib];
+                p = x + (u32)skip;
+                q = y + (u32)skip;
+                lenmin = n32 - (p > q ? p : q);
+                pa = W + (p >> 2);
+                pb = W + (q >> 2);
+                sha = (p & 3u) * 8u;
+                shb = (q & 3u) * 8u;
+                lo_a = *pa;
+                lo_b = *pb;
                 h = 0;
                 active = true;
             }
@@ -301,22 +303,22 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             continue;  // ring empty but slots left: refill
         }
         if (active) {
-            u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
-            u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
+            u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+            u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
             u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
             u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
             u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
             u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
             u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
             bool done = false, x_less = false;
-            i64 match = 0;
+            u32 match = 0;
             if (d0 | d1 | d2 | d3) {
-                int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
+                u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
                 u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
                 u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
                 u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
-                int bsh = (__ffs((int)dd) - 1) & ~7;     // bit offset of the first differing byte
-                i64 at = h + wsel * 4 + (bsh >> 3);      // counted from p / q
+                u32 bsh = (u32)(__ffs((int)dd) - 1) & ~7u;  // bit offset of the first differing byte
+                u32 at = h + wsel * 4u + (bsh >> 3);        // counted from p / q
                 done = true;
                 if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
                     match = lenmin;
@@ -326,16 +328,16 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                     x_less = ((va >> bsh) & 0xffu) < ((vb >> bsh) & 0xffu);
                 }
             } else {
-                h += 16;
-                ia += 4;
-                ib += 4;
+                h += 16u;
+                pa += 4;
+                pb += 4;
                 lo_a = a4;
                 lo_b = b4;
                 if (h >= lenmin) {
                     done = true;
                     match = lenmin;
                     x_less = p > q;
-                } else if (h >= SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                } else if (h >= (u32)SA_CMP_CAP) {  // too long: let the doubling rounds order this group
                     int t0 = tx - (int)sL[tx];
                     atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
                     active = false;
@@ -343,7 +345,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             }
             if (done) {
                 // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
-                i64 lcp = first_barrier(bar0, bar1, (i64)x, (i64)skip + match);
+                u32 lcp = first_barrier(bar0, bar1, x, (u32)skip + match);
                 int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
                 atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
                 atomicMax(&lcpv[big], (int)lcp);
@@ -414,7 +416,7 @@ sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__r
         lo_a = a4;
         lo_b = b4;
     }
-    LCP[j] = (int)first_barrier(bar0, bar1, p, match);
+    LCP[j] = (int)first_barrier(bar0, bar1, (u32)p, (u32)match);
 }
 
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
