@@ -419,6 +419,57 @@ sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__r
     LCP[j] = (int)first_barrier(bar0, bar1, (u32)p, (u32)match);
 }
 
+// Stage-4 variant of the above: `need` marks the slots whose LCP entry the comparison stage did not
+// produce (group heads, members of groups that went through the doubling rounds).
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+sa_need_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ deferred, unsigned char *__restrict__ need) {
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int L, R;
+    run_lengths(keys, n, j, SA_SMALL_G, L, R);
+    need[j] = (L == 0 || L + R + 1 > SA_SMALL_G || deferred[j - L]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+sa_lcp_need_kernel(const unsigned char *__restrict__ need, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
+                   const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
+    const u32 *__restrict__ W = (const u32 *)T;
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !need[j]) return;
+    if (j == 0) {
+        LCP[0] = 0;
+        return;
+    }
+    const u32 p = (u32)SA[j], q = (u32)SA[j - 1];
+    const u32 lenmin = (u32)n - (p > q ? p : q);
+    const u32 *pa = W + (p >> 2), *pb = W + (q >> 2);
+    const unsigned sha = (p & 3u) * 8u, shb = (q & 3u) * 8u;
+    u32 lo_a = *pa, lo_b = *pb;
+    u32 h = 0, match = lenmin;
+    while (h < lenmin) {
+        u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+        u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
+        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
+        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+        if (d0 | d1 | d2 | d3) {
+            u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
+            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+            u32 at = h + wsel * 4u + ((u32)(__ffs((int)dd) - 1) >> 3);
+            match = at < lenmin ? at : lenmin;
+            break;
+        }
+        h += 16u;
+        pa += 4;
+        pb += 4;
+        lo_a = a4;
+        lo_b = b4;
+    }
+    LCP[j] = (int)first_barrier(bar0, bar1, p, match);
+}
+
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
 // key[e] = rank[sa[e]] : (rank[sa[e]+h]+1, or 0 when the suffix ends first)
 __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ grp, const int *__restrict__ rank,
@@ -563,13 +614,13 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + a / 8 + a / 256 + 4096 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + 4096 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
     u64 *k0, *k1;
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
-    unsigned char *deferred;
+    unsigned char *deferred, *need;
     u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
     void *rscratch;
 };
@@ -614,7 +665,8 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
 
 // doubling rounds; round 0 works on the initial keys (KeyT), later rounds on (rank : rank) u64 keys
 template <typename KeyT>
-static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *keys0, u32 *sa, u32 *sa_alt, int *dSA, int *dISA, PhaseTimes *pt) {
+static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *keys0, u32 *sa, u32 *sa_alt, int *dSA, int *dISA, i64 *first_active,
+                    PhaseTimes *pt) {
     u32 *pos = nullptr, *grp = nullptr;  // current active list is (sa, pos, grp)
     u32 *pos_next = B.posA, *grp_next = B.grpA;
     u64 *keys = B.k0, *keys_alt = B.k1;  // free once round 0 has consumed keys0 (which may alias one of them)
@@ -640,6 +692,7 @@ static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *ke
         RV_CUDA(cudaMemcpyAsync(&nactive, B.small + 256, 4, cudaMemcpyDeviceToHost, st.s));
         RV_CUDA(cudaStreamSynchronize(st.s));
         if (pt) pt->sa_rounds = round + 1;
+        if (round == 0) *first_active = nactive;
         if (nactive == 0) break;
         if (h >= n) {
             set_error("sa_build: internal error, %u suffixes still tied at h=%lld >= n", nactive, (long long)h);
@@ -689,9 +742,10 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
     B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
     B.deferred = ws.take<unsigned char>(n);
+    B.need = ws.take<unsigned char>(n);
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
-    if (!B.deferred || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    if (!B.deferred || !B.need || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;
@@ -746,19 +800,35 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
 
     bool large = false;
     u32 *sa = nullptr, *sa_free = nullptr;
+    i64 first_active = 0;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     if (use32) {
         u32 *keys = nullptr;
         RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
         if (large) {
+            RV_LAUNCH((sa_need_kernel<u32>), blocks, 256, 0, st.s, keys, n, B.deferred, B.need);
+            st.launches++;
             // round 0 reads the u32 keys that live in the first half of k0 or k1; later rounds reuse both
             // buffers as u64 keys, so move the u32 keys out of the way (posB is free until round 2)
             RV_CUDA(cudaMemcpyAsync(B.posB, keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, st.s));
-            RV_TRY(doubling<u32>(st, B, n, k, B.posB, sa, sa_free, dSA, dISA, pt));
+            RV_TRY(doubling<u32>(st, B, n, k, B.posB, sa, sa_free, dSA, dISA, &first_active, pt));
         }
     } else {
         u64 *keys = nullptr;
         RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
-        if (large) RV_TRY(doubling<u64>(st, B, n, k, keys, sa, sa_free, dSA, dISA, pt));
+        if (large) {
+            RV_LAUNCH((sa_need_kernel<u64>), blocks, 256, 0, st.s, keys, n, B.deferred, B.need);
+            st.launches++;
+            RV_TRY(doubling<u64>(st, B, n, k, keys, sa, sa_free, dSA, dISA, &first_active, pt));
+        }
+    }
+    if (large && first_active <= n / 16) {
+        // few suffixes needed the doubling rounds: finish their LCP entries (and every group head's) by direct
+        // comparison; with many (long repeats) Kasai's amortised walk in rv_lcp.cu is the better tool
+        RV_LAUNCH(sa_lcp_need_kernel, blocks, 256, 0, st.s, B.need, n, dT, B.bar, B.bar1, dSA, dLCP);
+        st.launches++;
+        RV_KCHECK();
+        large = false;
     }
     *lcp_done = !large;
     return RV_OK;
