@@ -120,6 +120,26 @@ int rv_sweep_pair_device(rv_index *ws, const uint8_t *dT, const int32_t *dSA, co
 int rv_sweep_multi_device(rv_index *ws, const uint8_t *dT, const int32_t *dSA, const int32_t *dLCP, const uint16_t *dSO, int64_t n,
                           int64_t nsep0, int32_t main_nsamples, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
 
+/* ---- recursion: sub-indexes (the children of reveal.c:582-664 split, RevealIndex.main) ----------
+ * A sub-index is a device-resident (SA, LCP) pair of n entries that shares the main index's text,
+ * inverse SA and sample array, exactly like the reference's child indexes (reveal.c:1136-1207).
+ * rv_sub_root wraps the root arrays; rv_sub_split performs one step of the reference's aligner
+ * after its two Python callbacks: label scatter (reveal.c:1005-1117), split (:582-664), lower-casing
+ * of the matched bases in T (:1230-1234) and bubble_sort of the leading child (:666-727).
+ * Intervals are (begin, end) pairs of text positions, end exclusive; children[0..2] receive the
+ * leading, trailing and parallel child (NULL when empty).  The sweeps over a sub-index are
+ * getmums_rem (reveal.c:119-180) / getmultimums (:436-580) as the aligner calls them (:802-829);
+ * results are fetched with rv_mums_pair_fetch / rv_mums_multi_fetch on the main handle. */
+typedef struct rv_sub rv_sub;
+int rv_sub_root(rv_index *idx, rv_sub **out);
+int64_t rv_sub_n(const rv_sub *sub);
+void rv_sub_free(rv_sub *sub);
+int rv_sub_get(rv_sub *sub, int32_t which /* 0 SA, 1 LCP */, int32_t *out);
+int rv_sub_mums_pair(rv_sub *sub, int32_t minl, int64_t *count);
+int rv_sub_mums_multi(rv_sub *sub, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
+int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

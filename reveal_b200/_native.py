@@ -56,6 +56,14 @@ SIGNATURES = {
     "rv_mums_multi_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
     "rv_mums_multi_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_result_device": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i64p, ctypes.POINTER(c_vp), c_i64p]),
+    "rv_sub_root": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "rv_sub_n": (ctypes.c_int64, [c_vp]),
+    "rv_sub_free": (None, [c_vp]),
+    "rv_sub_get": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp]),
+    "rv_sub_mums_pair": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p]),
+    "rv_sub_mums_multi": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
+    "rv_sub_split": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32,
+                                    ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.POINTER(c_vp)]),
     "rv_sweep_pair_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_sweep_multi_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libreveal_b200.so")
 OBJ = os.path.join(_HERE, "csrc", "build")
-UNITS = ["rv_api", "rv_sa", "rv_lcp", "rv_sweep"]
+UNITS = ["rv_api", "rv_sa", "rv_lcp", "rv_sweep", "rv_split"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -62,7 +62,10 @@ struct rv_index {
     i64 *d_rows = nullptr, *d_members = nullptr;
     rv_times times;
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
+    void *pool = nullptr;  // DevPool of rv_split.cu (children of the recursion)
 };
+
+extern "C" void rv_pool_destroy(void *pool);
 
 static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
@@ -124,6 +127,7 @@ int rv_index_create(rv_index **out, void *stream) {
 void rv_index_free(rv_index *h) {
     if (!h) return;
     cudaStreamSynchronize(h->st.s);
+    rv_pool_destroy(h->pool);
     h->arena.release();
     h->sw.release();
     h->res.release();
@@ -330,6 +334,37 @@ static int run_multi(rv_index *h, const SweepArgs &a, int64_t *nrec, int64_t *nm
     *nmem = m;
     return RV_OK;
 }
+
+extern "C++" {
+namespace rv {
+struct MainView {
+    Stream *st;
+    unsigned char *T;
+    int *SA, *ISA, *LCP;
+    unsigned short *SO;
+    i64 n, nsep0;
+    int nsamples, rc;
+    void **pool_slot;
+};
+int main_view(rv_index *h, MainView *out) {
+    RV_TRY(need_built(h));
+    out->st = &h->st;
+    out->T = h->dT;
+    out->SA = h->dSA;
+    out->ISA = h->dISA;
+    out->LCP = h->dLCP;
+    out->SO = h->dSO;
+    out->n = h->n;
+    out->nsep0 = h->nsamples > 1 ? h->nsep[0] : -1;
+    out->nsamples = h->nsamples;
+    out->rc = h->rc;
+    out->pool_slot = &h->pool;
+    return RV_OK;
+}
+int sub_sweep_pair(rv_index *h, const SweepArgs &a, int64_t *count) { return run_pair(h, a, count); }
+int sub_sweep_multi(rv_index *h, const SweepArgs &a, int64_t *nrec, int64_t *nmem) { return run_multi(h, a, nrec, nmem); }
+}  // namespace rv
+}  // extern "C++"
 
 static SweepArgs root_args(const rv_index *h) {
     SweepArgs a;

@@ -44,6 +44,8 @@ class index(object):
         self._rc = 0
         self._depth = 0
         self._built = False
+        self._Tdirty = False       # device text differs from the host copy (align lower-cases matched bases)
+        self._nmums = 0
         self._h = None
         self.samples = []
         self.nodes = set()
@@ -217,7 +219,12 @@ class index(object):
 
     @property
     def T(self):
-        return self._text().tobytes().decode("latin-1")
+        T = self._text()
+        if self._built and self._Tdirty:  # matched regions are lower-cased in place during align (reveal.c:1230-1234)
+            self._call(self._lib().rv_get_text(self._handle(), T.ctypes.data))
+            self._chunks = [T.tobytes()]
+            self._Tdirty = False
+        return T.tobytes().decode("latin-1")
 
 
 def _version():

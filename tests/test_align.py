@@ -1,0 +1,80 @@
+"""Recursion parity: reveal_b200's align() against the reference's unmodified
+C aligner (oracle/_ref), both driven by the same deterministic callbacks.  Compared: every call the
+mumpicker receives (depth, n, nsamples, nodes, the MUM list incl. order), every chosen MUM, and the
+final text with its lower-cased matched regions.  CPU tier = emulated kernels on small inputs; the
+gpu-marked cases run the CUDA library."""
+import numpy as np
+import pytest
+
+import oracle.ref as R
+from align_callbacks import make_callbacks
+from util import random_related
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref (compiled reference) not present")
+
+
+def run_reference(samples, minl, minn, maxsteps=None):
+    log = []
+    idx = R.index_from_samples(samples)
+    mp, ga = make_callbacks(log, minlen=minl, maxsteps=maxsteps)
+    idx.align(mp, ga, threads=0, minl=minl, minn=minn)
+    return log, idx.T[:idx.n]
+
+
+def run_ours(reveallib, samples, minl, minn, maxsteps=None):
+    log = []
+    idx = reveallib.index()
+    for k, seqs in enumerate(samples):
+        idx.addsample("s%d" % k)
+        for s in seqs:
+            idx.addsequence(s if isinstance(s, str) else bytes(s).decode("ascii"))
+    idx.construct()
+    mp, ga = make_callbacks(log, minlen=minl, maxsteps=maxsteps)
+    idx.align(mp, ga, threads=0, minl=minl, minn=minn)
+    return log, idx.T
+
+
+def compare(a, b):
+    la, ta = a
+    lb, tb = b
+    assert len(la) == len(lb), "number of callback events differs: %d vs %d" % (len(la), len(lb))
+    for k, (x, y) in enumerate(zip(la, lb)):
+        assert x == y, "event %d differs:\n ref  %s\n ours %s" % (k, str(x)[:600], str(y)[:600])
+    assert ta == tb
+    return len([e for e in la if e[0] == "align"])
+
+
+CASES = [
+    ("pair_small", 2, 1500, 4, 8, 2),
+    ("pair_binary", 2, 800, 2, 10, 2),
+    ("triple", 3, 1200, 4, 8, 2),
+    ("five", 5, 700, 4, 7, 2),
+    ("triple_minn3", 3, 1000, 4, 8, 3),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,ns,length,sigma,minl,minn", CASES)
+def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma, minl, minn):
+    rng = np.random.default_rng(len(name) * 100 + length)
+    samples = random_related(rng, ns, length, sigma, snp=0.03)
+    steps = compare(run_reference(samples, minl, minn), run_ours(emu_reveallib, samples, minl, minn))
+    assert steps > 3
+
+
+@needs_ref
+def test_align_reference_test01_pair(emu_reveallib):
+    """The reference's own in-memory pair (reveal/tests/test_reveal.py:36-41), minlength=1."""
+    samples = [["ACTTGCTAGCTAGTCAG"], ["ACTAGCTAGCTAGTGAG"]]
+    compare(run_reference(samples, 1, 2), run_ours(emu_reveallib, samples, 1, 2))
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("ns,length,minl,minn,maxsteps", [(2, 60000, 12, 2, None), (3, 40000, 12, 2, None), (5, 20000, 10, 2, None), (2, 400000, 20, 2, 400)])
+def test_align_matches_reference_cuda(ns, length, minl, minn, maxsteps):
+    from reveal_b200 import reveallib, synth
+    gs = synth.genomes(ns, length, seed=9, snp=0.01, indel=0.001)
+    samples = [[g.tobytes()] for g in gs]
+    steps = compare(run_reference(samples, minl, minn, maxsteps), run_ours(reveallib, samples, minl, minn, maxsteps))
+    assert steps > 10
