@@ -496,7 +496,7 @@ int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64
 
     // ---- upload the small tables in one buffer ----
     size_t words = (size_t)2 * m1 + 2 * m2 + bbeg.size() + 8;
-    size_t bytes = words * 8 + (size_t)m1 + 64;
+    size_t bytes = (words * 8 + (size_t)m1 + 64 + 15) / 16 * 16;  // d_counts lives in the (aligned) last 32 bytes
     void *dtab = nullptr;
     RV_TRY(pool->take(bytes, &dtab));
     std::vector<unsigned char> host(bytes, 0);
