@@ -143,7 +143,7 @@ class DevArray:
     """Exposes a raw device pointer to torch through __cuda_array_interface__."""
 
     def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -182,16 +182,12 @@ def run_ours(args, rank, world, local_rank):
         """N > 1: MUM records of every rank to rank 0 over NCCL (the only collective on the path)."""
         if world == 1:
             return
+        from reveal_b200 import shard
         p, k = ctypes.c_void_p(), ctypes.c_int64()
         _native.check(L, L.rv_result_device(h, ctypes.byref(p), ctypes.byref(k), None, None))
-        mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([k.value], dtype=torch.int64, device=dev))
-        mx = int(max(int(c.item()) for c in counts))
-        pad = torch.zeros((mx, 3), dtype=torch.int64, device=dev)
-        pad[: k.value] = mine
-        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
+        with torch.cuda.stream(stream):  # same stream as the sweep kernels that produced the rows
+            mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
+            shard.gather_rows(mine, dst=0)
 
     def step_resident():
         _native.check(L, L.rv_build_device(h, ctypes.c_void_p(dT.data_ptr()), n, nsep.ctypes.data, ns, 0))

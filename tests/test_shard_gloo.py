@@ -1,0 +1,55 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the unit partitioning and the variable-length
+gather that bench.py / the recursion sharding use over NCCL on the GPUs."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from reveal_b200 import shard
+
+
+def test_partition_is_balanced_and_deterministic():
+    sizes = [100, 7, 93, 12, 50, 49, 1, 1, 30]
+    parts = shard.partition(sizes, 4)
+    assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) <= 100 and max(loads) - min(loads) <= 30
+    assert parts == shard.partition(sizes, 4)
+    assert shard.partition([], 3) == [[], [], []]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # each rank "builds" its own units and holds a different number of MUM rows (rank 1: none)
+    units = shard.partition([40, 10, 30, 20], world)[rank]
+    k = 0 if rank == 1 else 5
+    rows = torch.arange(k * 3, dtype=torch.int64).reshape(k, 3) + 1000 * rank
+    got = shard.gather_rows(rows, dst=0)
+    if rank == 0:
+        q.put((units, [g.tolist() for g in got]))
+    else:
+        assert got is None
+        q.put((units, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gathered = [r for r in res if r[1] is not None][0][1]
+    assert gathered[0] == (torch.arange(15).reshape(5, 3)).tolist()
+    assert gathered[1] == []
+    all_units = sorted(u for r in res for u in r[0])
+    assert all_units == [0, 1, 2, 3]
