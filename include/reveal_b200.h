@@ -72,14 +72,19 @@ int rv_build(rv_index *idx, const uint8_t *T, int64_t n, const int64_t *nsep, in
 int rv_build_device(rv_index *idx, const uint8_t *dT, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
 int rv_get_times(const rv_index *idx, rv_times *out);
 
-/* Optional profile of the dominant kernel (the radix-sort pass): when enabled the
- * library brackets every run of pass launches with CUDA events on the build
- * stream and accumulates duration, launch count and algorithmic bytes
- * (items x 12 B x read+write) until the next rv_profile(idx, 1) resets them. */
+/* Optional per-kernel profile: when enabled the library brackets the launches of its heavy kernels
+ * with CUDA events on the build stream and accumulates, per slot, duration, launch count and
+ * ALGORITHMIC bytes (stated per slot below and in DESIGN.md) until the next rv_profile(idx, 1). */
+enum rv_prof_slot {
+    RV_PROF_RADIX_PASS = 0, /* rs_pass_kernel: items x (key + 4 B suffix) x (read + write) */
+    RV_PROF_PAIRS = 1,      /* sa_pairs_kernel: n x (key + 4 B suffix read; SA + SAi + LCP = 12 B written) */
+    RV_PROF_SWEEP = 2,      /* pair / multi sweep kernels (count + write): n x 9 B (11 B with SO) per pass */
+    RV_PROF_LCP = 3         /* lcp_kasai_kernel (fallback): n x 13 B */
+};
 typedef struct rv_kernel_profile {
-    double pass_ms;
-    int64_t pass_launches;
-    int64_t pass_bytes;
+    double ms[4];
+    int64_t launches[4];
+    int64_t bytes[4];
     int64_t launches_total; /* every kernel this handle launched since creation */
 } rv_kernel_profile;
 int rv_profile(rv_index *idx, int32_t enable);

@@ -24,11 +24,12 @@ class Times(ctypes.Structure):
 
 
 class KernelProfile(ctypes.Structure):
-    _fields_ = [("pass_ms", ctypes.c_double), ("pass_launches", ctypes.c_int64), ("pass_bytes", ctypes.c_int64),
+    SLOTS = ("rs_pass_kernel", "sa_pairs_kernel", "sweep kernels", "lcp_kasai_kernel")
+    _fields_ = [("ms", ctypes.c_double * 4), ("launches", ctypes.c_int64 * 4), ("bytes", ctypes.c_int64 * 4),
                 ("launches_total", ctypes.c_int64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {name: {"ms": self.ms[k], "launches": self.launches[k], "bytes": self.bytes[k]} for k, name in enumerate(self.SLOTS)}
 
 
 # every symbol include/reveal_b200.h declares: name -> (restype, argtypes)

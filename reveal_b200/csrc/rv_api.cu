@@ -229,16 +229,20 @@ int rv_profile(rv_index *h, int32_t enable) {
         RV_CUDA(cudaEventCreate(&h->st.pe1));
     }
     h->st.prof = enable != 0;
-    h->st.pass_ms = 0;
-    h->st.pass_launches = 0;
-    h->st.pass_bytes = 0;
+    for (int k = 0; k < 4; k++) {
+        h->st.prof_ms[k] = 0;
+        h->st.prof_launches[k] = 0;
+        h->st.prof_bytes[k] = 0;
+    }
     return RV_OK;
 }
 int rv_get_profile(const rv_index *h, rv_kernel_profile *out) {
     if (!h || !out) return RV_ERR_ARG;
-    out->pass_ms = h->st.pass_ms;
-    out->pass_launches = h->st.pass_launches;
-    out->pass_bytes = h->st.pass_bytes;
+    for (int k = 0; k < 4; k++) {
+        out->ms[k] = h->st.prof_ms[k];
+        out->launches[k] = h->st.prof_launches[k];
+        out->bytes[k] = h->st.prof_bytes[k];
+    }
     out->launches_total = h->st.launches_total + h->st.launches;
     return RV_OK;
 }

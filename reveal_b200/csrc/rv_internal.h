@@ -60,10 +60,27 @@ struct Stream {
     // optional per-kernel profile of the dominant kernel (radix pass), CUDA events on this stream
     bool prof = false;
     cudaEvent_t pe0 = 0, pe1 = 0;
-    double pass_ms = 0;         // summed duration of rs_pass_kernel launches
-    long long pass_launches = 0;
-    long long pass_bytes = 0;   // algorithmic bytes: items * (key + value) * (read + write)
+    double prof_ms[4] = {0, 0, 0, 0};          // per slot (enum rv_prof_slot): summed kernel time
+    long long prof_launches[4] = {0, 0, 0, 0};
+    long long prof_bytes[4] = {0, 0, 0, 0};    // algorithmic bytes moved by those launches
 };
+
+// bracket a run of launches of one kernel with events (profile mode only; the end syncs the stream)
+inline int prof_begin(Stream &st) {
+    if (st.prof) RV_CUDA(cudaEventRecord(st.pe0, st.s));
+    return RV_OK;
+}
+inline int prof_end(Stream &st, int slot, long long launches, long long bytes) {
+    if (!st.prof) return RV_OK;
+    float ms = 0;
+    RV_CUDA(cudaEventRecord(st.pe1, st.s));
+    RV_CUDA(cudaEventSynchronize(st.pe1));
+    RV_CUDA(cudaEventElapsedTime(&ms, st.pe0, st.pe1));
+    st.prof_ms[slot] += ms;
+    st.prof_launches[slot] += launches;
+    st.prof_bytes[slot] += bytes;
+    return RV_OK;
+}
 
 // ---- phase entry points (each in its own .cu) ---------------------------------
 size_t sa_workspace_bytes(i64 n);

@@ -44,7 +44,9 @@ int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const 
     if (chunk < 32) chunk = 32;
     if (chunk > 256) chunk = 256;
     i64 threads = (n + chunk - 1) / chunk;
+    RV_TRY(prof_begin(st));
     RV_LAUNCH(lcp_kasai_kernel, (unsigned)((threads + 127) / 128), 128, 0, st.s, dT, n, dSA, dISA, dLCP, (int)chunk);
+    RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
     st.launches++;
     RV_KCHECK();
     return RV_OK;

@@ -247,7 +247,7 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
         attr_done = true;
     }
     bool in0 = true;
-    if (st.prof) RV_CUDA(cudaEventRecord(st.pe0, st.s));
+    RV_TRY(prof_begin(st));
     for (int p = 0; p < plan.npass; p++) {
         RV_LAUNCH((rs_pass_kernel<KeyT, true>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0,
                   in0 ? v0 : v1, in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS,
@@ -256,15 +256,7 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
         in0 = !in0;
     }
     RV_KCHECK();
-    if (st.prof) {
-        float ms = 0;
-        RV_CUDA(cudaEventRecord(st.pe1, st.s));
-        RV_CUDA(cudaEventSynchronize(st.pe1));
-        RV_CUDA(cudaEventElapsedTime(&ms, st.pe0, st.pe1));
-        st.pass_ms += ms;
-        st.pass_launches += plan.npass;
-        st.pass_bytes += (long long)plan.npass * n * (long long)(sizeof(KeyT) + 4) * 2;
-    }
+    RV_TRY(prof_end(st, RV_PROF_RADIX_PASS, plan.npass, (long long)plan.npass * n * (long long)(sizeof(KeyT) + 4) * 2));
     *result_in_0 = in0;
     return RV_OK;
 }

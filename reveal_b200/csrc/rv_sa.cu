@@ -645,8 +645,10 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const unsigned blocks = (unsigned)((n + 255) / 256);
     RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((n + 1023) / 1024 + 1), 1024, 0, st.s, dT, n, B.bar, B.bar1);
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
+    RV_TRY(prof_begin(st));
     RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, B.bar1, k,
               dSA, dISA, dLCP, B.deferred, B.small + 257);
+    RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 2;
     u32 lg = 0;
     RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
