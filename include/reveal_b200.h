@@ -142,6 +142,14 @@ void rv_sub_free(rv_sub *sub);
 int rv_sub_get(rv_sub *sub, int32_t which /* 0 SA, 1 LCP */, int32_t *out);
 int rv_sub_mums_pair(rv_sub *sub, int32_t minl, int64_t *count);
 int rv_sub_mums_multi(rv_sub *sub, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
+/* rv_sub_step = rv_sub_split that may ALSO run the children's MUM sweep (sweep[c] != 0 for the children that
+ * carry no precomputed skipmums) in the same launch: parents of at most 16384 suffixes are handled by one
+ * thread block end to end (one launch, one synchronisation per recursion step).  A following
+ * rv_sub_mums_pair / _multi on such a child answers from the stored result; rv_sub_fetch copies it. */
+int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
+                int32_t minn, rv_sub **children);
+int rv_sub_fetch(rv_sub *sub, int64_t *rows, int64_t cap_rows, int64_t *members, int64_t cap_members);
 int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                  const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);
 

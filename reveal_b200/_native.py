@@ -65,6 +65,9 @@ SIGNATURES = {
     "rv_sub_mums_multi": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
     "rv_sub_split": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32,
                                     ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.POINTER(c_vp)]),
+    "rv_sub_step": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32,
+                                   ctypes.c_int64, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_vp)]),
+    "rv_sub_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_sweep_pair_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_sweep_multi_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

@@ -22,6 +22,7 @@
 // thread replays the reference's loop body on exactly those entries, in order.
 #include "rv_internal.h"
 #include "rv_sweep.h"
+#include "rv_sweep_dev.cuh"
 #include <vector>
 #include <map>
 
@@ -230,27 +231,27 @@ __device__ __forceinline__ void bubble_body(int *SA, int *LCP, int *SAi, i64 n, 
     }
 }
 
-__global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int nbegins) {
-    __shared__ int s_cand[BB_CAP];
-    __shared__ int s_cnt;
+// bubble_sort of one child by one thread block (any block size that is a power of two <= 1024)
+__device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n, const i64 *begins, int nbegins, int *s_cand, int *s_cnt) {
+    const int NT = (int)blockDim.x;
     for (int b = 0; b < nbegins; b++) {
         const i64 begin = begins[b];
-        if (threadIdx.x == 0) s_cnt = 0;
+        if (threadIdx.x == 0) *s_cnt = 0;
         __syncthreads();
         // candidates: LCP values only decrease during the pass, so a slot whose original values do not
         // reach across `begin` can never take either branch
-        for (i64 i = threadIdx.x; i < n; i += BB_THREADS) {
+        for (i64 i = threadIdx.x; i < n; i += NT) {
             i64 s = SA[i];
             if (s < begin) {
                 bool c = s + LCP[i] > begin || (i < n - 1 && s + LCP[i + 1] > begin);
                 if (c) {
-                    int at = atomicAdd(&s_cnt, 1);
+                    int at = atomicAdd(s_cnt, 1);
                     if (at < BB_CAP) s_cand[at] = (int)i;
                 }
             }
         }
         __syncthreads();
-        const int cnt = s_cnt;
+        const int cnt = *s_cnt;
         if (cnt > BB_CAP) {  // rare: too many candidates for shared memory, replay the whole loop
             if (threadIdx.x == 0)
                 for (i64 i = 0; i < n; i++) bubble_body(SA, LCP, SAi, n, i, begin);
@@ -258,11 +259,11 @@ __global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, i
             // bitonic sort of the candidate slots (ascending), padded with INT_MAX
             int m = 1;
             while (m < cnt) m <<= 1;
-            for (int i = cnt + threadIdx.x; i < m; i += BB_THREADS) s_cand[i] = 0x7fffffff;
+            for (int i = cnt + threadIdx.x; i < m; i += NT) s_cand[i] = 0x7fffffff;
             __syncthreads();
             for (int k = 2; k <= m; k <<= 1) {
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = threadIdx.x; i < m; i += BB_THREADS) {
+                    for (int i = threadIdx.x; i < m; i += NT) {
                         int ixj = i ^ j;
                         if (ixj > i) {
                             int a = s_cand[i], c = s_cand[ixj];
@@ -280,6 +281,201 @@ __global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, i
                 for (int c = 0; c < cnt; c++) bubble_body(SA, LCP, SAi, n, (i64)s_cand[c], begin);
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int nbegins) {
+    __shared__ int s_cand[BB_CAP];
+    __shared__ int s_cnt;
+    bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, &s_cnt);
+}
+
+// ---- one whole recursion step of a SMALL sub-index in a single launch ---------------------------
+// Deep in the recursion almost every sub-index has a few hundred to a few thousand suffixes; ten launches
+// and three host synchronisations per step would be pure latency.  One 1024-thread block does the step:
+// labels in shared memory, block-wide split scan, T lower-casing, bubble_sort of the leading child, and
+// then already the MUM sweep of every child that will need one (it has no precomputed skipmums), written
+// in list order into a host-mapped buffer.  The host sees one launch and one synchronisation per step.
+static const int SM_THREADS = 1024;
+static const int SM_MAXN = 16384;   // parent entries handled by the single-block path
+static const int SM_MAXIV = 40;     // intervals that fit the kernel argument
+static const int SM_MAXMUM = 16;
+
+struct SmallStepArgs {
+    unsigned char *T;
+    int *SAi;
+    const unsigned short *SO;
+    i64 nT, nsep0;
+    int main_nsamples, rc, minl, minn;
+    const int *pSA, *pLCP;
+    int n;
+    int m1;
+    i64 total1;
+    i64 ibeg[SM_MAXIV], pre[SM_MAXIV];
+    unsigned char lab[SM_MAXIV];
+    int m2;
+    i64 mum_l;
+    i64 mbeg[SM_MAXMUM];
+    int nb;
+    i64 bbeg[SM_MAXMUM];
+    int *cSA[3], *cLCP[3];
+    int cn[3], do_sweep[3];
+    i64 *out;       // host-mapped: [0..15] header, then rows / members
+    i64 out_words;
+};
+
+// ordered emission of one child's sweep by the whole block; returns through hdr[3*c..]: nrec, nmem, overflow
+__device__ __forceinline__ void small_sweep(const SmallStepArgs &a, int c, u32 *s_scan_a, u32 *s_scan_b, i64 *s_cursor) {
+    SweepArgs p;
+    p.T = a.T;
+    p.SA = a.cSA[c];
+    p.LCP = a.cLCP[c];
+    p.SO = a.SO;
+    p.n = a.cn[c];
+    p.nT = a.nT;
+    p.nsep0 = a.nsep0;
+    p.rc = a.rc;
+    p.flavour = 1;
+    p.minl = a.minl;
+    p.minn = a.minn;
+    p.main_nsamples = a.main_nsamples;
+    const bool multi = a.main_nsamples > 2;
+    const int n = a.cn[c];
+    const int chunk = (n + SM_THREADS - 1) / SM_THREADS;
+    const int lo = (int)threadIdx.x * chunk;
+    const int hi = lo + chunk < n ? lo + chunk : n;
+    u32 nr = 0, nm = 0;
+    for (int i = lo; i < hi; i++) {
+        if (multi) {
+            multi_visit(p, (i64)i, [&](i64, i64, i64 size) { nr++; nm += (u32)size; });
+        } else {
+            i64 l, x, y;
+            nr += pair_test(p, (i64)i, l, x, y) ? 1u : 0u;
+        }
+    }
+    u32 tr, tm;
+    u32 ir = block_incl_sum<SM_THREADS, u32>(nr, s_scan_a, &tr);
+    u32 im = block_incl_sum<SM_THREADS, u32>(nm, s_scan_b, &tm);
+    const i64 cur = *s_cursor;
+    const i64 need = (i64)tr * 3 + (i64)tm * 2;
+    const bool fits = cur + need <= a.out_words;
+    if (fits) {
+        i64 *rows = a.out + cur;
+        i64 *mem = rows + (i64)tr * 3;
+        u32 at_r = ir - nr, at_m = im - nm;
+        for (int i = lo; i < hi && nr; i++) {
+            if (multi) {
+                multi_visit(p, (i64)i, [&](i64 l, i64 lb, i64 size) {
+                    rows[3 * (i64)at_r + 0] = l;
+                    rows[3 * (i64)at_r + 1] = size;
+                    rows[3 * (i64)at_r + 2] = (i64)at_m;
+                    for (i64 x = 0; x < size; x++) {
+                        i64 pos = p.SA[lb + x];
+                        mem[2 * (i64)at_m + 0] = sample_of(p, pos);
+                        mem[2 * (i64)at_m + 1] = pos;
+                        at_m++;
+                    }
+                    at_r++;
+                });
+            } else {
+                i64 l = 0, x = 0, y = 0;
+                if (pair_test(p, (i64)i, l, x, y)) {
+                    rows[3 * (i64)at_r + 0] = l;
+                    rows[3 * (i64)at_r + 1] = x;
+                    rows[3 * (i64)at_r + 2] = y;
+                    at_r++;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.out[4 * c + 0] = tr;
+        a.out[4 * c + 1] = tm;
+        a.out[4 * c + 2] = fits ? cur : -1;  // word offset of the rows, -1: did not fit (host re-sweeps)
+        if (fits) *s_cursor = cur + need;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SM_THREADS) small_step_kernel(SmallStepArgs a) {
+    __shared__ unsigned char sD[SM_MAXN];
+    __shared__ int s_cand[BB_CAP];
+    __shared__ int s_cnt;
+    __shared__ SplitState s_warp[32];
+    __shared__ u32 s_scan_a[33], s_scan_b[33];
+    __shared__ i64 s_cursor;
+    const int tid = (int)threadIdx.x;
+    const int n = a.n;
+    // ---- labels (reveal.c:1005-1117) ----
+    for (int i = tid; i < n; i += SM_THREADS) sD[i] = 0;
+    if (tid == 0) s_cursor = 16;
+    __syncthreads();
+    for (i64 g = tid; g < a.total1; g += SM_THREADS) {
+        int k = 0;
+        while (k + 1 < a.m1 && a.pre[k + 1] <= g) k++;
+        int r = a.SAi[a.ibeg[k] + (g - a.pre[k])];
+        if ((unsigned)r < (unsigned)n) sD[r] = a.lab[k];
+    }
+    __syncthreads();
+    const i64 mtotal = (i64)a.m2 * a.mum_l;
+    for (i64 g = tid; g < mtotal; g += SM_THREADS) {
+        int r = a.SAi[a.mbeg[g / a.mum_l] + g % a.mum_l];
+        if ((unsigned)r < (unsigned)n) sD[r] = 3;
+    }
+    __syncthreads();
+    // ---- split (reveal.c:582-664) ----
+    {
+        const int chunk = (n + SM_THREADS - 1) / SM_THREADS;
+        const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        SplitState st = split_identity();
+        for (int i = lo; i < hi; i++) {
+            int dummy;
+            int v = (i == 0 || !(sD[i - 1] >= 1 && sD[i - 1] <= 4)) ? INF_LCP : a.pLCP[i];
+            split_step(st, v, class_of(sD[i]), dummy);
+        }
+        SplitState run = block_excl_scan_state(st, s_warp, nullptr);
+        for (int i = lo; i < hi; i++) {
+            int cls = class_of(sD[i]);
+            int out_m;
+            u32 rank = cls >= 0 ? run.cnt[cls] : 0u;
+            int v = (i == 0 || !(sD[i - 1] >= 1 && sD[i - 1] <= 4)) ? INF_LCP : a.pLCP[i];
+            split_step(run, v, cls, out_m);
+            if (cls >= 0 && (int)rank < a.cn[cls]) {
+                int s = a.pSA[i];
+                a.cSA[cls][rank] = s;
+                a.cLCP[cls][rank] = rank == 0 ? 0 : out_m;
+                a.SAi[s] = (int)rank;
+            }
+        }
+        // class sizes for the host-side consistency check
+        if (tid == SM_THREADS - 1) {
+            SplitState fin = run;  // state after the last slot of the last thread = whole range
+            a.out[12] = fin.cnt[0];
+            a.out[13] = fin.cnt[1];
+            a.out[14] = fin.cnt[2];
+        }
+    }
+    __syncthreads();
+    // ---- mark the matched bases (reveal.c:1230-1234) ----
+    for (i64 g = tid; g < mtotal; g += SM_THREADS) {
+        i64 j = a.mbeg[g / a.mum_l] + g % a.mum_l;
+        unsigned char c = a.T[j];
+        if (c >= 'A' && c <= 'Z') a.T[j] = (unsigned char)(c + 32);
+    }
+    __syncthreads();
+    // ---- bubble_sort of the leading child (reveal.c:1250-1252) ----
+    if (a.cn[0] > 0 && a.nb > 0) bubble_block(a.cSA[0], a.cLCP[0], a.SAi, (i64)a.cn[0], a.bbeg, a.nb, s_cand, &s_cnt);
+    __syncthreads();
+    // ---- the children's MUM sweeps (reveal.c:802-829 of their own steps) ----
+    for (int c = 0; c < 3; c++) {
+        if (a.cn[c] > 0 && a.do_sweep[c]) {
+            small_sweep(a, c, s_scan_a, s_scan_b, &s_cursor);
+        } else if (tid == 0) {
+            a.out[4 * c + 0] = 0;
+            a.out[4 * c + 1] = 0;
+            a.out[4 * c + 2] = -2;  // not swept
+        }
     }
 }
 
@@ -334,11 +530,22 @@ struct DevPool {
     }
 };
 
+// per main index: buffer pool + the host-mapped result buffer of the single-block step
+struct RecCtx {
+    DevPool pool;
+    i64 *h_out = nullptr, *d_out = nullptr;
+    i64 out_words = 0;
+};
+
 struct rv_sub {
     rv_index *main;
     int *SA = nullptr, *LCP = nullptr;
     i64 n = 0;
     bool owns = false;  // false: the root view over the main index's arrays
+    // MUM sweep already done by the step that created this child (small_step_kernel)
+    bool cached = false;
+    int cminl = 0, cminn = 0;
+    std::vector<i64> rows, members;
 };
 
 // accessors into rv_index implemented in rv_api.cu
@@ -357,19 +564,21 @@ int sub_sweep_pair(rv_index *h, const SweepArgs &a, int64_t *count);
 int sub_sweep_multi(rv_index *h, const SweepArgs &a, int64_t *nrec, int64_t *nmem);
 }  // namespace rv
 
-static DevPool *pool_of(MainView &v) {
-    if (!*v.pool_slot) *v.pool_slot = new DevPool();
-    return (DevPool *)*v.pool_slot;
+static RecCtx *ctx_of(MainView &v) {
+    if (!*v.pool_slot) *v.pool_slot = new RecCtx();
+    return (RecCtx *)*v.pool_slot;
 }
+static DevPool *pool_of(MainView &v) { return &ctx_of(v)->pool; }
 
 extern "C" {
 
 void rv_pool_destroy(void *pool) {  // called by rv_index_free
     if (!pool) return;
-    DevPool *p = (DevPool *)pool;
-    p->trim();
-    for (auto &kv : p->size_) cudaFree(kv.first);
-    delete p;
+    RecCtx *c = (RecCtx *)pool;
+    c->pool.trim();
+    for (auto &kv : c->pool.size_) cudaFree(kv.first);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    delete c;
 }
 
 int rv_sub_root(rv_index *h, rv_sub **out) {
@@ -428,7 +637,12 @@ static SweepArgs sub_args(const rv_sub *s, const MainView &v) {
 }
 
 int rv_sub_mums_pair(rv_sub *s, int32_t minl, int64_t *count) {
-    if (!s) return RV_ERR_ARG;
+    if (!s || !count) return RV_ERR_ARG;
+    if (s->cached && s->cminl == minl) {
+        *count = (int64_t)(s->rows.size() / 3);
+        return RV_OK;
+    }
+    s->cached = false;
     MainView v;
     RV_TRY(main_view(s->main, &v));
     SweepArgs a = sub_args(s, v);
@@ -437,7 +651,13 @@ int rv_sub_mums_pair(rv_sub *s, int32_t minl, int64_t *count) {
 }
 
 int rv_sub_mums_multi(rv_sub *s, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem) {
-    if (!s) return RV_ERR_ARG;
+    if (!s || !nrec || !nmem) return RV_ERR_ARG;
+    if (s->cached && s->cminl == minl && s->cminn == minn) {
+        *nrec = (int64_t)(s->rows.size() / 3);
+        *nmem = (int64_t)(s->members.size() / 2);
+        return RV_OK;
+    }
+    s->cached = false;
     MainView v;
     RV_TRY(main_view(s->main, &v));
     SweepArgs a = sub_args(s, v);
@@ -450,8 +670,8 @@ int rv_sub_mums_multi(rv_sub *s, int32_t minl, int32_t minn, int64_t *nrec, int6
 // mum_sp[0..mum_n) are the start positions of the chosen MUM, mum_l its length; matching[] the (begin,end)
 // pairs graphalign returned, in its iteration order (bubble_sort replays them in that order).
 // children[0..2] = leading, trailing, parallel (NULL when that class is empty).
-int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
-                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children) {
+static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                         const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children) {
     if (!parent || !children) return RV_ERR_ARG;
     children[0] = children[1] = children[2] = nullptr;
     MainView v;
@@ -584,6 +804,154 @@ int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64
         }
     for (int c = 0; c < 3; c++) children[c] = kids[c];
     return RV_OK;
+}
+
+// the single-launch path for small parents; *handled = 0 when the step does not qualify
+static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                      const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep,
+                      int32_t minl, int32_t minn, rv_sub **children, int *handled) {
+    *handled = 0;
+    MainView v;
+    RV_TRY(main_view(parent->main, &v));
+    const i64 n = parent->n;
+    if (n <= 0 || n > SM_MAXN || mum_n > SM_MAXMUM || nmatch > SM_MAXMUM || mum_l <= 0) return RV_OK;
+    SmallStepArgs a;
+    memset(&a, 0, sizeof a);
+    i64 total = 0, cls_n[3] = {0, 0, 0};
+    const int64_t *src[3] = {lead, trail, par};
+    const int32_t cnts[3] = {nlead, ntrail, npar};
+    const unsigned char labels[3] = {1, 2, 4};
+    int m1 = 0;
+    for (int c = 0; c < 3; c++)
+        for (int k = 0; k < cnts[c]; k++) {
+            i64 b = src[c][2 * k], e = src[c][2 * k + 1];
+            if (e <= b) continue;
+            if (b < 0 || e > v.n) { set_error("rv_sub_step: interval out of range"); return RV_ERR_ARG; }
+            if (m1 >= SM_MAXIV) return RV_OK;  // too many intervals for the argument block: general path
+            a.ibeg[m1] = b;
+            a.pre[m1] = total;
+            a.lab[m1] = labels[c];
+            m1++;
+            total += e - b;
+            cls_n[c] += e - b;
+        }
+    for (int k = 0; k < mum_n; k++) {
+        if (mum_sp[k] < 0 || mum_sp[k] + mum_l > v.n) { set_error("rv_sub_step: mum out of range"); return RV_ERR_ARG; }
+        a.mbeg[k] = mum_sp[k];
+    }
+    for (int k = 0; k < nmatch; k++) a.bbeg[k] = matching[2 * k];
+    RecCtx *ctx = ctx_of(v);
+    if (!ctx->h_out) {
+        const size_t bytes = (size_t)8 << 20;
+        void *hp = nullptr, *dp = nullptr;
+        RV_CUDA(cudaHostAlloc(&hp, bytes, cudaHostAllocMapped));
+        RV_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        ctx->h_out = (i64 *)hp;
+        ctx->d_out = (i64 *)dp;
+        ctx->out_words = (i64)(bytes / 8);
+    }
+    DevPool *pool = &ctx->pool;
+    rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < 3; c++)
+        if (cls_n[c] > 0) {
+            rv_sub *k = new rv_sub();
+            k->main = parent->main;
+            k->n = cls_n[c];
+            k->owns = true;
+            void *p1 = nullptr, *p2 = nullptr;
+            int r1 = pool->take((size_t)(cls_n[c] + 2) * 4, &p1);
+            int r2 = r1 == RV_OK ? pool->take((size_t)(cls_n[c] + 2) * 4, &p2) : r1;
+            if (r1 != RV_OK || r2 != RV_OK) { delete k; return RV_ERR_NOMEM; }
+            k->SA = (int *)p1;
+            k->LCP = (int *)p2;
+            kids[c] = k;
+        }
+    a.T = v.T;
+    a.SAi = v.ISA;
+    a.SO = v.SO;
+    a.nT = v.n;
+    a.nsep0 = v.nsep0;
+    a.main_nsamples = v.nsamples;
+    a.rc = v.rc;
+    a.minl = minl;
+    a.minn = minn;
+    a.pSA = parent->SA;
+    a.pLCP = parent->LCP;
+    a.n = (int)n;
+    a.m1 = m1;
+    a.total1 = total;
+    a.m2 = mum_n;
+    a.mum_l = mum_l;
+    a.nb = nmatch;
+    for (int c = 0; c < 3; c++) {
+        a.cSA[c] = kids[c] ? kids[c]->SA : nullptr;
+        a.cLCP[c] = kids[c] ? kids[c]->LCP : nullptr;
+        a.cn[c] = (int)cls_n[c];
+        a.do_sweep[c] = (sweep && sweep[c]) ? 1 : 0;
+    }
+    a.out = ctx->d_out;
+    a.out_words = ctx->out_words;
+    Stream &st = *v.st;
+    RV_LAUNCH(small_step_kernel, 1, SM_THREADS, 0, st.s, a);
+    st.launches++;
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    RV_KCHECK();
+    const i64 *o = ctx->h_out;
+    for (int c = 0; c < 3; c++)
+        if (o[12 + c] != cls_n[c]) {
+            set_error("rv_sub_step: class %d has %lld suffixes in the parent but the intervals cover %lld positions", c, (long long)o[12 + c],
+                      (long long)cls_n[c]);
+            for (int q = 0; q < 3; q++) rv_sub_free(kids[q]);
+            return RV_ERR_ARG;
+        }
+    for (int c = 0; c < 3; c++) {
+        rv_sub *k = kids[c];
+        if (!k) continue;
+        const i64 nr = o[4 * c + 0], nm = o[4 * c + 1], off = o[4 * c + 2];
+        if (off >= 0) {  // swept and it fitted
+            k->rows.assign(o + off, o + off + nr * 3);
+            k->members.assign(o + off + nr * 3, o + off + nr * 3 + nm * 2);
+            k->cached = true;
+            k->cminl = minl;
+            k->cminn = minn;
+        }
+        children[c] = k;
+    }
+    *handled = 1;
+    return RV_OK;
+}
+
+int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
+                int32_t minn, rv_sub **children) {
+    if (!parent || !children) return RV_ERR_ARG;
+    children[0] = children[1] = children[2] = nullptr;
+    int handled = 0;
+    RV_TRY(step_small(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, sweep, minl, minn, children, &handled));
+    if (handled) return RV_OK;
+    return split_general(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, children);
+}
+
+int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children) {
+    return rv_sub_step(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, nullptr, 0, 2, children);
+}
+
+// rows / hdr (int64 triples) and members (int64 pairs) of the sub-index's last sweep
+int rv_sub_fetch(rv_sub *s, int64_t *rows, int64_t cap_rows, int64_t *members, int64_t cap_members) {
+    if (!s) return RV_ERR_ARG;
+    if (s->cached) {
+        i64 r = (i64)(s->rows.size() / 3), m = (i64)(s->members.size() / 2);
+        if (r > cap_rows) r = cap_rows;
+        if (m > cap_members) m = cap_members;
+        if (r > 0 && rows) memcpy(rows, s->rows.data(), (size_t)r * 24);
+        if (m > 0 && members) memcpy(members, s->members.data(), (size_t)m * 16);
+        return RV_OK;
+    }
+    MainView v;
+    RV_TRY(main_view(s->main, &v));
+    if (v.nsamples > 2) return rv_mums_multi_fetch(s->main, rows, cap_rows, members, cap_members);
+    return rv_mums_pair_fetch(s->main, rows, cap_rows);
 }
 
 }  // extern "C"

@@ -83,21 +83,21 @@ def _count_samples(main, intervals):
 
 
 def _extract(main, sub, minl, minn):
-    """Step 1: MUMs of a sub-index in the shape the reference passes to mumpicker."""
+    """Step 1: MUMs of a sub-index in the shape the reference passes to mumpicker.  When the step that
+    created the sub-index already swept it (single-launch path) the calls below answer from that result."""
     L = main._lib()
-    h = main._handle()
     if main._nsamples > 2:
         nr, nm = ctypes.c_int64(), ctypes.c_int64()
         main._call(L.rv_sub_mums_multi(sub, int(minl), int(minn), ctypes.byref(nr), ctypes.byref(nm)))
         hdr = np.empty((nr.value, 3), dtype=np.int64)
         mem = np.empty((nm.value, 2), dtype=np.int64)
-        main._call(L.rv_mums_multi_fetch(h, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+        main._call(L.rv_sub_fetch(sub, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
         members = [tuple(x) for x in mem.tolist()]
         return [(l, n, tuple(members[first:first + n])) for l, n, first in hdr.tolist()]
     c = ctypes.c_int64()
     main._call(L.rv_sub_mums_pair(sub, int(minl), ctypes.byref(c)))
     rows = np.empty((c.value, 3), dtype=np.int64)
-    main._call(L.rv_mums_pair_fetch(h, rows.ctypes.data, c.value))
+    main._call(L.rv_sub_fetch(sub, rows.ctypes.data, c.value, None, 0))
     return [(l, 2, ((0, a), (1, b))) for l, a, b in rows.tolist()]  # reveal.c:167-169
 
 
@@ -144,8 +144,12 @@ def align(main, mumpicker, graphalign, threads=0, wpen=0, wscore=0, minl=0, minn
                 par = _intervals(rest)
                 match = _intervals(matching)
                 kids = (ctypes.c_void_p * 3)()
-                main._call(L.rv_sub_split(view._sub, lead.ctypes.data, len(lead), trail.ctypes.data, len(trail), par.ctypes.data, len(par),
-                                          mum_sp.ctypes.data, int(mum_n), int(mum_l), match.ctypes.data, len(match), kids))
+                # children without precomputed skipmums will be swept first thing in their own step: let the
+                # device do it in the same launch when the parent is small
+                sweep = np.asarray([len(skipleft) == 0, len(skipright) == 0, 1], dtype=np.int32)
+                main._call(L.rv_sub_step(view._sub, lead.ctypes.data, len(lead), trail.ctypes.data, len(trail), par.ctypes.data, len(par),
+                                         mum_sp.ctypes.data, int(mum_n), int(mum_l), match.ctypes.data, len(match), sweep.ctypes.data,
+                                         int(minl), int(minn), kids))
                 main._Tdirty = True  # matched bases were lower-cased on the device
                 depth = idx.depth + 1
                 nmums += 1

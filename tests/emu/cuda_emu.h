@@ -310,6 +310,9 @@ cudaError_t cudaFree(void *p);
 cudaError_t emu_check_guards();
 static inline cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+enum { cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return 0; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { if (n) memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
