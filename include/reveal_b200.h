@@ -149,6 +149,8 @@ int rv_sub_mums_multi(rv_sub *sub, int32_t minl, int32_t minn, int64_t *nrec, in
 int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
                 int32_t minn, rv_sub **children);
+/* steps2[0]/seconds2[0]: recursion steps taken by the single-launch path and their host wall time; [1]: general path */
+int rv_rec_stats(rv_index *idx, int64_t *steps2, double *seconds2);
 int rv_sub_fetch(rv_sub *sub, int64_t *rows, int64_t cap_rows, int64_t *members, int64_t cap_members);
 int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                  const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);

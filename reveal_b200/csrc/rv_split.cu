@@ -23,6 +23,7 @@
 #include "rv_internal.h"
 #include "rv_sweep.h"
 #include "rv_sweep_dev.cuh"
+#include <stdlib.h>
 #include <vector>
 #include <map>
 
@@ -290,6 +291,60 @@ __global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, i
     bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, &s_cnt);
 }
 
+// Large children: the candidate scan runs grid-wide, the sort + replay in one block.
+__global__ void __launch_bounds__(256) bubble_detect_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, i64 n, const i64 *__restrict__ begins,
+                                                           int b, int *__restrict__ cand, int *__restrict__ cand_cnt) {
+    const i64 begin = begins[b];
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        i64 s = SA[i];
+        if (s < begin) {
+            bool c = s + LCP[i] > begin || (i < n - 1 && s + LCP[i + 1] > begin);
+            if (c) {
+                int at = atomicAdd(cand_cnt, 1);
+                if (at < BB_CAP) cand[at] = (int)i;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BB_THREADS) bubble_apply_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int b,
+                                                                  const int *__restrict__ cand, int *cand_cnt) {
+    __shared__ int s_cand[BB_CAP];
+    const i64 begin = begins[b];
+    const int cnt = *cand_cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) *cand_cnt = 0;  // ready for the next matched interval
+    if (cnt > BB_CAP) {  // rare: too many candidates, replay the whole loop
+        if (threadIdx.x == 0)
+            for (i64 i = 0; i < n; i++) bubble_body(SA, LCP, SAi, n, i, begin);
+        return;
+    }
+    if (cnt == 0) return;
+    int m = 1;
+    while (m < cnt) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += BB_THREADS) s_cand[i] = i < cnt ? cand[i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += BB_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    int a = s_cand[i], c = s_cand[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > c) == up) {
+                        s_cand[i] = c;
+                        s_cand[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0)
+        for (int c = 0; c < cnt; c++) bubble_body(SA, LCP, SAi, n, (i64)s_cand[c], begin);
+}
+
 // ---- one whole recursion step of a SMALL sub-index in a single launch ---------------------------
 // Deep in the recursion almost every sub-index has a few hundred to a few thousand suffixes; ten launches
 // and three host synchronisations per step would be pure latency.  One 1024-thread block does the step:
@@ -535,7 +590,12 @@ struct RecCtx {
     DevPool pool;
     i64 *h_out = nullptr, *d_out = nullptr;
     i64 out_words = 0;
+    // step statistics: [0] single-launch path, [1] general path
+    long long steps[2] = {0, 0};
+    double host_s[2] = {0, 0};
 };
+#include <chrono>
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct rv_sub {
     rv_index *main;
@@ -787,15 +847,32 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
         st.launches++;
     }
     // ---- bubble_sort(i_leading, matching_intervals)  (reveal.c:1250-1252) ----
+    void *dcand = nullptr;
     if (kids[0] && !bbeg.empty()) {
-        RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, (int)bbeg.size());
-        st.launches++;
+        i64 block_maxn = 8192;
+        if (const char *e = getenv("RV_BUBBLE_BLOCK_MAXN")) block_maxn = atoll(e);  // test hook
+        if (kids[0]->n <= block_maxn) {
+            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, (int)bbeg.size());
+            st.launches++;
+        } else {
+            RV_TRY(pool->take((size_t)(BB_CAP + 16) * 4, &dcand));
+            int *cand = (int *)dcand, *cand_cnt = cand + BB_CAP;
+            RV_CUDA(cudaMemsetAsync(cand_cnt, 0, 4, st.s));
+            i64 blocks = (kids[0]->n + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            for (int b = 0; b < (int)bbeg.size(); b++) {
+                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, kids[0]->SA, kids[0]->LCP, kids[0]->n, d_bbeg, b, cand, cand_cnt);
+                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, b, cand, cand_cnt);
+                st.launches += 2;
+            }
+        }
     }
     RV_CUDA(cudaStreamSynchronize(st.s));
     RV_KCHECK();
     pool->give(dtab);
     pool->give(dD);
     pool->give(dtiles);
+    pool->give(dcand);
     for (int c = 0; c < 3; c++)
         if ((i64)hc[c] != cls_n[c]) {
             set_error("rv_sub_split: class %d has %u suffixes in the parent but the intervals cover %lld positions", c, hc[c], (long long)cls_n[c]);
@@ -814,7 +891,12 @@ static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const 
     MainView v;
     RV_TRY(main_view(parent->main, &v));
     const i64 n = parent->n;
-    if (n <= 0 || n > SM_MAXN || mum_n > SM_MAXMUM || nmatch > SM_MAXMUM || mum_l <= 0) return RV_OK;
+    i64 small_maxn = SM_MAXN;
+    if (const char *e = getenv("RV_SMALL_MAXN")) {  // test hook: 0 forces the general path
+        i64 x = atoll(e);
+        if (x < small_maxn) small_maxn = x;
+    }
+    if (n <= 0 || n > small_maxn || mum_n > SM_MAXMUM || nmatch > SM_MAXMUM || mum_l <= 0) return RV_OK;
     SmallStepArgs a;
     memset(&a, 0, sizeof a);
     i64 total = 0, cls_n[3] = {0, 0, 0};
@@ -927,14 +1009,37 @@ int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_
     if (!parent || !children) return RV_ERR_ARG;
     children[0] = children[1] = children[2] = nullptr;
     int handled = 0;
+    MainView v;
+    RV_TRY(main_view(parent->main, &v));
+    RecCtx *ctx = ctx_of(v);
+    double t0 = now_s();
     RV_TRY(step_small(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, sweep, minl, minn, children, &handled));
-    if (handled) return RV_OK;
-    return split_general(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, children);
+    if (handled) {
+        ctx->steps[0]++;
+        ctx->host_s[0] += now_s() - t0;
+        return RV_OK;
+    }
+    int r = split_general(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, children);
+    ctx->steps[1]++;
+    ctx->host_s[1] += now_s() - t0;
+    return r;
 }
 
 int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                  const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children) {
     return rv_sub_step(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, nullptr, 0, 2, children);
+}
+
+// recursion statistics of a main index: steps and host seconds of the single-launch / general step paths
+int rv_rec_stats(rv_index *h, int64_t *steps2, double *seconds2) {
+    MainView v;
+    RV_TRY(main_view(h, &v));
+    RecCtx *ctx = ctx_of(v);
+    for (int k = 0; k < 2; k++) {
+        if (steps2) steps2[k] = ctx->steps[k];
+        if (seconds2) seconds2[k] = ctx->host_s[k];
+    }
+    return RV_OK;
 }
 
 // rows / hdr (int64 triples) and members (int64 pairs) of the sub-index's last sweep

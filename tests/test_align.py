@@ -63,6 +63,19 @@ def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma
 
 
 @needs_ref
+@pytest.mark.parametrize("small_maxn,bubble_maxn", [("0", "100000"), ("0", "0"), ("600", "0")])
+def test_align_general_step_paths_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn):
+    """RV_SMALL_MAXN / RV_BUBBLE_BLOCK_MAXN force the multi-kernel step and the grid-wide bubble detection."""
+    monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
+    monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
+    rng = np.random.default_rng(77)
+    samples = random_related(rng, 3, 1100, 4, snp=0.03)
+    assert compare(run_reference(samples, 8, 2), run_ours(emu_reveallib, samples, 8, 2)) > 3
+    samples = random_related(rng, 2, 1500, 4, snp=0.03)
+    assert compare(run_reference(samples, 8, 2), run_ours(emu_reveallib, samples, 8, 2)) > 3
+
+
+@needs_ref
 def test_align_reference_test01_pair(emu_reveallib):
     """The reference's own in-memory pair (reveal/tests/test_reveal.py:36-41), minlength=1."""
     samples = [["ACTTGCTAGCTAGTCAG"], ["ACTAGCTAGCTAGTGAG"]]
