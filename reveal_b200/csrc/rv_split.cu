@@ -540,9 +540,13 @@ using namespace rv;
 
 // ---- device buffer pool: children come and go thousands of times per alignment ------------------
 struct DevPool {
+    // size-class free lists over blocks carved from a few big slabs: a recursion step never calls cudaMalloc
+    // (which synchronises the device and costs ~1 ms) except when a new slab is needed
     std::multimap<size_t, void *> free_;
     std::map<void *, size_t> size_;
-    size_t held = 0;
+    std::vector<void *> slabs_;
+    unsigned char *cur_ = nullptr;
+    size_t cur_left_ = 0;
     static size_t round_up(size_t b) {
         size_t c = 1024;
         while (c < b) c <<= 1;
@@ -556,32 +560,41 @@ struct DevPool {
             free_.erase(it);
             return RV_OK;
         }
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, c);
-        if (e != cudaSuccess) {  // give cached blocks back and retry once
-            trim();
-            e = cudaMalloc(&p, c);
+        if (c > cur_left_) {
+            size_t slab = (size_t)64 << 20;
+            if (slab < 2 * c) slab = 2 * c;
+            void *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, slab);
+            if (e != cudaSuccess && slab > c) {
+                slab = c;
+                e = cudaMalloc(&p, slab);
+            }
+            if (e != cudaSuccess) {
+                set_error("cudaMalloc(%zu) failed: %s", slab, cudaGetErrorString(e));
+                return RV_ERR_NOMEM;
+            }
+            // the unused tail of the previous slab is abandoned (at most one block of the largest class seen)
+            slabs_.push_back(p);
+            cur_ = (unsigned char *)p;
+            cur_left_ = slab;
         }
-        if (e != cudaSuccess) {
-            set_error("cudaMalloc(%zu) failed: %s", c, cudaGetErrorString(e));
-            return RV_ERR_NOMEM;
-        }
-        size_[p] = c;
-        held += c;
-        *out = p;
+        *out = cur_;
+        size_[cur_] = c;
+        cur_ += c;
+        cur_left_ -= c;
         return RV_OK;
     }
     void give(void *p) {
         if (!p) return;
         free_.insert({size_[p], p});
     }
-    void trim() {
-        for (auto &kv : free_) {
-            cudaFree(kv.second);
-            held -= size_[kv.second];
-            size_.erase(kv.second);
-        }
+    void destroy() {
+        for (void *p : slabs_) cudaFree(p);
+        slabs_.clear();
         free_.clear();
+        size_.clear();
+        cur_ = nullptr;
+        cur_left_ = 0;
     }
 };
 
@@ -635,8 +648,7 @@ extern "C" {
 void rv_pool_destroy(void *pool) {  // called by rv_index_free
     if (!pool) return;
     RecCtx *c = (RecCtx *)pool;
-    c->pool.trim();
-    for (auto &kv : c->pool.size_) cudaFree(kv.first);
+    c->pool.destroy();
     if (c->h_out) cudaFreeHost(c->h_out);
     delete c;
 }
