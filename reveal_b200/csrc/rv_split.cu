@@ -232,6 +232,75 @@ __device__ __forceinline__ void bubble_body(int *SA, int *LCP, int *SAi, i64 n, 
     }
 }
 
+// Replays the loop body for the sorted candidate slots cand[0..cnt), candidates one after the other (their
+// effects depend on each other) but each one block-parallel: the insertion of reveal.c:688-700 is a backward
+// search for the first LCP below the truncated length followed by a shift of the whole span by one slot, and
+// for a suffix that starts right before `begin` that span is a large part of the child.
+__device__ __forceinline__ void bubble_replay_block(int *SA, int *LCP, int *SAi, i64 n, i64 begin, const int *s_cand, int cnt, int *s_tmp /*[8]*/) {
+    const int NT = (int)blockDim.x;
+    const int tid = (int)threadIdx.x;
+    for (int c = 0; c < cnt; c++) {
+        const i64 i = s_cand[c];
+        if (tid == 0) {
+            int mode = 0;
+            const int sa = SA[i], lcp = LCP[i];
+            if ((sa < begin) && ((i64)sa + lcp > begin)) {
+                mode = 1;
+            } else if (i < n - 1 && (sa < begin) && ((i64)sa + LCP[i + 1] > begin)) {
+                if (LCP[i + 1] > lcp) LCP[i + 1] = (int)(begin - sa);
+            }
+            s_tmp[0] = mode;
+            s_tmp[1] = sa;
+            s_tmp[2] = lcp;
+            s_tmp[3] = -1;  // stop slot found by the search
+        }
+        __syncthreads();
+        if (s_tmp[0] == 1) {
+            const int tmpSA = s_tmp[1], tmpLCP = s_tmp[2];
+            const i64 thr = begin - tmpSA;
+            // ---- search: x = first slot going down from i with LCP[x] < thr, else 0 ----
+            i64 hi = i;
+            i64 xstop = 0;
+            while (hi >= 1) {
+                i64 x = hi - tid;
+                if (x >= 1 && (i64)LCP[x] < thr) atomicMax(&s_tmp[3], (int)x);
+                __syncthreads();
+                int found = s_tmp[3];
+                __syncthreads();
+                if (found >= 0) {
+                    xstop = found;
+                    break;
+                }
+                hi -= NT;
+            }
+            // ---- shift [xstop, i-1] up by one slot, top window first ----
+            for (i64 top = i; top > xstop; top -= NT) {
+                i64 x = top - tid;  // destination slot
+                int vs = 0, vl = 0;
+                const bool mine = x > xstop;
+                if (mine) {
+                    vs = SA[x - 1];
+                    vl = LCP[x - 1];
+                }
+                __syncthreads();
+                if (mine) {
+                    SA[x] = vs;
+                    LCP[x] = vl;
+                    SAi[vs] = (int)x;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                SAi[tmpSA] = (int)xstop;
+                SA[xstop] = tmpSA;
+                LCP[xstop + 1] = (int)thr;
+                if (i < n - 1 && tmpLCP < LCP[i + 1]) LCP[i + 1] = tmpLCP;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // bubble_sort of one child by one thread block (any block size that is a power of two <= 1024)
 __device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n, const i64 *begins, int nbegins, int *s_cand, int *s_cnt) {
     const int NT = (int)blockDim.x;
@@ -278,8 +347,7 @@ __device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n,
                     __syncthreads();
                 }
             }
-            if (threadIdx.x == 0)
-                for (int c = 0; c < cnt; c++) bubble_body(SA, LCP, SAi, n, (i64)s_cand[c], begin);
+            bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_cnt + 1);
         }
         __syncthreads();
     }
@@ -287,8 +355,8 @@ __device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n,
 
 __global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int nbegins) {
     __shared__ int s_cand[BB_CAP];
-    __shared__ int s_cnt;
-    bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, &s_cnt);
+    __shared__ int s_cnt[12];  // [0] candidate count, [1..] scratch of the replay
+    bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, s_cnt);
 }
 
 // Large children: the candidate scan runs grid-wide, the sort + replay in one block.
@@ -341,8 +409,8 @@ __global__ void __launch_bounds__(BB_THREADS) bubble_apply_kernel(int *SA, int *
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0)
-        for (int c = 0; c < cnt; c++) bubble_body(SA, LCP, SAi, n, (i64)s_cand[c], begin);
+    __shared__ int s_tmp[8];
+    bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_tmp);
 }
 
 // ---- one whole recursion step of a SMALL sub-index in a single launch ---------------------------
@@ -456,7 +524,7 @@ __device__ __forceinline__ void small_sweep(const SmallStepArgs &a, int c, u32 *
 __global__ void __launch_bounds__(SM_THREADS) small_step_kernel(SmallStepArgs a) {
     __shared__ unsigned char sD[SM_MAXN];
     __shared__ int s_cand[BB_CAP];
-    __shared__ int s_cnt;
+    __shared__ int s_cnt[12];
     __shared__ SplitState s_warp[32];
     __shared__ u32 s_scan_a[33], s_scan_b[33];
     __shared__ i64 s_cursor;
@@ -520,7 +588,7 @@ __global__ void __launch_bounds__(SM_THREADS) small_step_kernel(SmallStepArgs a)
     }
     __syncthreads();
     // ---- bubble_sort of the leading child (reveal.c:1250-1252) ----
-    if (a.cn[0] > 0 && a.nb > 0) bubble_block(a.cSA[0], a.cLCP[0], a.SAi, (i64)a.cn[0], a.bbeg, a.nb, s_cand, &s_cnt);
+    if (a.cn[0] > 0 && a.nb > 0) bubble_block(a.cSA[0], a.cLCP[0], a.SAi, (i64)a.cn[0], a.bbeg, a.nb, s_cand, s_cnt);
     __syncthreads();
     // ---- the children's MUM sweeps (reveal.c:802-829 of their own steps) ----
     for (int c = 0; c < 3; c++) {
