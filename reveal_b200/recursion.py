@@ -63,23 +63,48 @@ class SubIndex(object):
             self._sub = None
 
 
+_I64 = ctypes.c_int64
+
+
 def _intervals(obj):
-    """Python iterable of (begin, end) -> contiguous int64 [k,2] array, in iteration order."""
-    rows = [(int(b), int(e)) for b, e in obj]
-    a = np.asarray(rows, dtype=np.int64).reshape(-1, 2)
-    return np.ascontiguousarray(a)
+    """Python iterable of (begin, end) -> (ctypes int64 array [b0,e0,b1,e1,...], count, covered length, begins).
+    Plain lists + ctypes: a recursion step handles a handful of intervals, numpy would cost more than it saves."""
+    flat, begins, total = [], [], 0
+    for b, e in obj:
+        b = int(b)
+        e = int(e)
+        flat.append(b)
+        flat.append(e)
+        begins.append(b)
+        total += e - b
+    return (_I64 * (len(flat) or 1))(*flat), len(begins), total, begins
 
 
-def _count_samples(main, intervals):
+def _count_samples(main, begins):
     """Number of distinct samples among the interval starts (reveal.c:1026-1041)."""
-    if len(intervals) == 0:
+    if not begins:
         return 0
-    begins = intervals[:, 0]
     if main._nsamples > 2:
-        nsep = np.asarray(main._nsep, dtype=np.int64)
-        return len(np.unique(np.searchsorted(nsep, begins, side="left")))  # SO[begin] = #nsep < begin
+        nsep = main._nsep
+        seen = set()
+        for b in begins:  # SO[begin] = number of separators before begin
+            lo, hi = 0, len(nsep)
+            while lo < hi:
+                mid = (lo + hi) >> 1
+                if nsep[mid] < b:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            seen.add(lo)
+        return len(seen)
     nsep0 = main._nsep[0]
-    return int((begins < nsep0).any()) + int((begins > nsep0).any())
+    left = right = 0
+    for b in begins:
+        if b < nsep0:
+            left = 1
+        elif b > nsep0:
+            right = 1
+    return left + right
 
 
 def _extract(main, sub, minl, minn):
@@ -87,22 +112,33 @@ def _extract(main, sub, minl, minn):
     created the sub-index already swept it (single-launch path) the calls below answer from that result."""
     L = main._lib()
     if main._nsamples > 2:
-        nr, nm = ctypes.c_int64(), ctypes.c_int64()
-        main._call(L.rv_sub_mums_multi(sub, int(minl), int(minn), ctypes.byref(nr), ctypes.byref(nm)))
-        hdr = np.empty((nr.value, 3), dtype=np.int64)
-        mem = np.empty((nm.value, 2), dtype=np.int64)
-        main._call(L.rv_sub_fetch(sub, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
-        members = [tuple(x) for x in mem.tolist()]
-        return [(l, n, tuple(members[first:first + n])) for l, n, first in hdr.tolist()]
-    c = ctypes.c_int64()
-    main._call(L.rv_sub_mums_pair(sub, int(minl), ctypes.byref(c)))
-    rows = np.empty((c.value, 3), dtype=np.int64)
-    main._call(L.rv_sub_fetch(sub, rows.ctypes.data, c.value, None, 0))
-    return [(l, 2, ((0, a), (1, b))) for l, a, b in rows.tolist()]  # reveal.c:167-169
+        nr, nm = _I64(), _I64()
+        main._call(L.rv_sub_mums_multi(sub, minl, minn, ctypes.byref(nr), ctypes.byref(nm)))
+        r, m = nr.value, nm.value
+        if r == 0:
+            return []
+        hdr = (_I64 * (3 * r))()
+        mem = (_I64 * (2 * m))()
+        main._call(L.rv_sub_fetch(sub, hdr, r, mem, m))
+        mem = mem[:]
+        hdr = hdr[:]
+        members = list(zip(mem[0::2], mem[1::2]))
+        return [(hdr[k], hdr[k + 1], tuple(members[hdr[k + 2]:hdr[k + 2] + hdr[k + 1]])) for k in range(0, 3 * r, 3)]
+    c = _I64()
+    main._call(L.rv_sub_mums_pair(sub, minl, ctypes.byref(c)))
+    r = c.value
+    if r == 0:
+        return []
+    rows = (_I64 * (3 * r))()
+    main._call(L.rv_sub_fetch(sub, rows, r, None, 0))
+    rows = rows[:]
+    return [(rows[k], 2, ((0, rows[k + 1]), (1, rows[k + 2]))) for k in range(0, 3 * r, 3)]  # reveal.c:167-169
 
 
 def align(main, mumpicker, graphalign, threads=0, wpen=0, wscore=0, minl=0, minn=0):
     from .reveallib import error
+    minl = int(minl)
+    minn = int(minn)
     L = main._lib()
     main._depth = 0
     main.main = main
@@ -130,7 +166,7 @@ def align(main, mumpicker, graphalign, threads=0, wpen=0, wscore=0, minl=0, minn
                     continue  # no more MUMs in this sub-index
                 mumobject, skipleft, skipright = pick
                 mum_l, mum_n, spd = mumobject
-                mum_sp = np.asarray([int(spd[i][1]) for i in range(mum_n)], dtype=np.int64)
+                mum_sp = (_I64 * max(1, mum_n))(*[int(spd[i][1]) for i in range(mum_n)])
                 result = graphalign(idx, mumobject)
                 if result is None:
                     continue
@@ -139,30 +175,29 @@ def align(main, mumpicker, graphalign, threads=0, wpen=0, wscore=0, minl=0, minn
                 if len(result) != 7:
                     continue  # the reference silently drops an unparsable result (reveal.c:987-999)
                 leading, trailing, matching, rest, merged, newleft, newright = result
-                lead = _intervals(leading)
-                trail = _intervals(trailing)
-                par = _intervals(rest)
-                match = _intervals(matching)
+                lead, nlead, leadn, lead_b = _intervals(leading)
+                trail, ntrail, trailn, trail_b = _intervals(trailing)
+                par, npar, parn, par_b = _intervals(rest)
+                match, nmatch, _, _ = _intervals(matching)
                 kids = (ctypes.c_void_p * 3)()
                 # children without precomputed skipmums will be swept first thing in their own step: let the
                 # device do it in the same launch when the parent is small
-                sweep = np.asarray([len(skipleft) == 0, len(skipright) == 0, 1], dtype=np.int32)
-                main._call(L.rv_sub_step(view._sub, lead.ctypes.data, len(lead), trail.ctypes.data, len(trail), par.ctypes.data, len(par),
-                                         mum_sp.ctypes.data, int(mum_n), int(mum_l), match.ctypes.data, len(match), sweep.ctypes.data,
-                                         int(minl), int(minn), kids))
+                sweep = (ctypes.c_int32 * 3)(len(skipleft) == 0, len(skipright) == 0, 1)
+                main._call(L.rv_sub_step(view._sub, lead, nlead, trail, ntrail, par, npar, mum_sp, int(mum_n), int(mum_l), match, nmatch,
+                                         sweep, minl, minn, kids))
                 main._Tdirty = True  # matched bases were lower-cased on the device
                 depth = idx.depth + 1
                 nmums += 1
                 i_lead = i_trail = i_par = None
                 if kids[0]:
-                    i_lead = SubIndex(main, ctypes.c_void_p(kids[0]), int((lead[:, 1] - lead[:, 0]).sum()), depth, _count_samples(main, lead),
-                                      leading, idx.leftnode, newright, skipleft)
+                    i_lead = SubIndex(main, ctypes.c_void_p(kids[0]), leadn, depth, _count_samples(main, lead_b), leading, idx.leftnode,
+                                      newright, skipleft)
                 if kids[1]:
-                    i_trail = SubIndex(main, ctypes.c_void_p(kids[1]), int((trail[:, 1] - trail[:, 0]).sum()), depth, _count_samples(main, trail),
-                                       trailing, newleft, idx.rightnode, skipright)
+                    i_trail = SubIndex(main, ctypes.c_void_p(kids[1]), trailn, depth, _count_samples(main, trail_b), trailing, newleft,
+                                       idx.rightnode, skipright)
                 if kids[2]:
-                    i_par = SubIndex(main, ctypes.c_void_p(kids[2]), int((par[:, 1] - par[:, 0]).sum()), depth, _count_samples(main, par),
-                                     rest, idx.leftnode, idx.rightnode, [])
+                    i_par = SubIndex(main, ctypes.c_void_p(kids[2]), parn, depth, _count_samples(main, par_b), rest, idx.leftnode,
+                                     idx.rightnode, [])
                 for child in (i_par, i_lead, i_trail):  # push order of reveal.c:1296-1324
                     if child is not None:
                         queue.append((child, child))
