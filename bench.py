@@ -45,6 +45,19 @@ METRIC = "aligned bases/sec (rem anchor phase: index build + MUM sweep)"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic(kernel, workload):
+    """dram bytes per launch of `kernel` from the newest committed ncu capture of this workload (profiles/*/traffic.json)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+            if d.get("workload") == workload and kernel in d:
+                return int(d[kernel]["dram_read_bytes"]) + int(d[kernel]["dram_write_bytes"]), os.path.relpath(path, ROOT)
+        except Exception:
+            pass
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
                                 "algorithmic_bytes_per_launch": prof.bytes[k] / prof.launches[k]})
         kernels.sort(key=lambda d: -d["share_of_step"])
         top = kernels[0] if kernels else {}
+        traffic, traffic_src = measured_traffic(top.get("kernel"), args.workload)
         bpb = 35 if ns == 2 else 39
         line = {"metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -285,7 +299,8 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches": launches,
                 # the dominant kernel = largest measured share of the step; algorithmic bytes per slot: include/reveal_b200.h, DESIGN.md
                 "roofline": {"bound": "hbm", "kernel": top.get("kernel"), "achieved": top.get("achieved"), "peak": peak, "unit": "GB/s",
-                             "frac": top.get("frac"), "peak_source": peak_src, "traffic": None, "launches": top.get("launches"),
+                             "frac": top.get("frac"), "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_bytes_per_launch": top.get("algorithmic_bytes_per_launch"), "launches": top.get("launches"),
                              "avg_launch_ms": top.get("avg_launch_ms"), "share_of_step": top.get("share_of_step"),
                              "kernels": kernels,
                              "path": {"algorithmic_bytes_per_base": bpb, "achieved": bpb * n * args.steps / (dev_ms * 1e-3) / 1e9,
