@@ -114,7 +114,7 @@ def run_reference(args, rank, world):
         return
     import oracle.ref as R
     if not R.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference tree absent at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (reference tree absent at build time)"})
         return
     T, nsep, ns, desc = make_workload(args.workload, seed=1)
     n = len(T)
@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "bases/s", "cores": 1, "kind": "reference",
                              "sample": "the full workload per step (construct + getmums%s through the reference extension's Python API)" % ("" if ns == 2 else "/getmultimums")},
             "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -309,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(T, nsep, ns)
-        print(json.dumps(line))
+        emit(line)
     L.rv_index_free(h)
     if world > 1:
         dist.destroy_process_group()
@@ -342,7 +342,21 @@ def cpu_baseline(T, nsep, ns):
             "sample": "the full workload once through the oracle port (SA-IS + Kasai + sweep)", "mums": int(k)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL banner ...) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
