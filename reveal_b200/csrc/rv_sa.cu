@@ -143,6 +143,37 @@ __device__ __forceinline__ u32 first_barrier(const u32 *__restrict__ bar0, const
     }
 }
 
+// barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison, 16 bytes per step
+__device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u32 p, u32 q, const u32 *__restrict__ bar0,
+                                          const u32 *__restrict__ bar1) {
+    const u32 lenmin = n32 - (p > q ? p : q);
+    const u32 *pa = W + (p >> 2), *pb = W + (q >> 2);
+    const unsigned sha = (p & 3u) * 8u, shb = (q & 3u) * 8u;
+    u32 lo_a = *pa, lo_b = *pb;
+    u32 h = 0, match = lenmin;
+    while (h < lenmin) {
+        u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+        u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
+        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
+        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+        if (d0 | d1 | d2 | d3) {
+            u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
+            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+            u32 at = h + wsel * 4u + ((u32)(__ffs((int)dd) - 1) >> 3);
+            match = at < lenmin ? at : lenmin;
+            break;
+        }
+        h += 16u;
+        pa += 4;
+        pb += 4;
+        lo_a = a4;
+        lo_b = b4;
+    }
+    return (int)first_barrier(bar0, bar1, p, match);
+}
+
 static const int PR_THREADS = 128;
 static const int PR_WARPS = PR_THREADS / 32;
 static const int PR_CHUNK = 256;                       // nominal SA slots per warp
@@ -162,8 +193,9 @@ template <typename KeyT>
 __global__ void __launch_bounds__(PR_THREADS, 10)
 sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T,
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
-                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large) {
+                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start) {
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
+    __shared__ u32 s_fin[PR_WARPS][PR_MAXT];            // suffix at every local slot after placement (0xFFFFFFFF: not placed here)
     __shared__ int s_lcp[PR_WARPS][PR_MAXT];
     __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
     __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group; 0xFF: not a small group
@@ -203,6 +235,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     end = __shfl_sync(FULL, end, 0);
     end_closed = __shfl_sync(FULL, end_closed, 0);
     const int nt = c0 < n && end > s ? (int)(end - s) : 0;  // local slots t = 0 .. nt-1
+    if (lane == 0) chunk_start[(i64)blockIdx.x * PR_WARPS + w] = nt ? (int)s : -1;  // its LCP entry: sa_chunkhead_kernel
     if (nt == 0) return;  // warp-uniform
     const int rounds = (nt + 31) / 32;
 
@@ -356,6 +389,9 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     __syncwarp();
 
     // ---- place the warp's groups: slot = group start + number of smaller mates ----
+    u32 *fin = s_fin[w];
+    for (int t = (int)lane; t < nt; t += 32) fin[t] = 0xFFFFFFFFu;
+    __syncwarp();
     for (int t = (int)lane; t < nt; t += 32) {
         unsigned L = sL[t];
         if (L == 0xFFu) continue;  // member of a group with more than SA_SMALL_G suffixes: stage 4
@@ -372,54 +408,32 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         u32 suf = ssa[t];
         SA[slot] = (int)suf;
         rank[suf] = (int)slot;
-        if (r > 0) LCP[slot] = lcpv[t];  // the smallest member's entry crosses the group boundary: sa_headlcp_kernel
+        fin[t0 + (int)r] = suf;
+        if (r > 0) LCP[slot] = lcpv[t];
+    }
+    __syncwarp();
+    // ---- the first slot of every group: its left neighbour differs inside the k-mer, one short direct comparison.
+    //      (The first slot of the chunk has its neighbour in another warp: sa_chunkhead_kernel.) ----
+    for (int f = (int)lane; f < nt; f += 32) {
+        if (f == 0 || !((head[f >> 5] >> (f & 31)) & 1u)) continue;
+        u32 a = fin[f], b = fin[f - 1];
+        if (a == 0xFFFFFFFFu || b == 0xFFFFFFFFu) continue;  // stage 4 will finish these (sa_lcp_need_kernel)
+        LCP[s + f] = direct_lcp(W, n32, a, b, bar0, bar1);
     }
 }
 
-// LCP entry of the first slot of every group: its left neighbour differs inside the k-mer, so one
-// (two for long keys) 16-byte comparison step from the suffix starts settles it.
-template <typename KeyT>
+// LCP entry of the first slot of every warp chunk of sa_pairs_kernel
 __global__ void __launch_bounds__(256)
-sa_headlcp_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
-                  const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
-    const u32 *__restrict__ W = (const u32 *)T;
-    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    if (j == 0) {
-        LCP[0] = 0;
-        return;
-    }
-    if (keys[j] == keys[j - 1]) return;
-    const i64 p = SA[j], q = SA[j - 1];
-    const i64 lenmin = (n - p) < (n - q) ? (n - p) : (n - q);
-    i64 ia = p >> 2, ib = q >> 2;
-    const unsigned sha = (unsigned)(p & 3) * 8u, shb = (unsigned)(q & 3) * 8u;
-    u32 lo_a = W[ia], lo_b = W[ib];
-    i64 h = 0, match = lenmin;
-    while (h < lenmin) {
-        u32 a1 = W[ia + 1], a2 = W[ia + 2], a3 = W[ia + 3], a4 = W[ia + 4];
-        u32 b1 = W[ib + 1], b2 = W[ib + 2], b3 = W[ib + 3], b4 = W[ib + 4];
-        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
-        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
-        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
-        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
-        if (d0 | d1 | d2 | d3) {
-            int wsel = d0 ? 0 : (d1 ? 1 : (d2 ? 2 : 3));
-            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-            i64 at = h + wsel * 4 + ((__ffs((int)dd) - 1) >> 3);
-            match = at < lenmin ? at : lenmin;
-            break;
-        }
-        h += 16;
-        ia += 4;
-        ib += 4;
-        lo_a = a4;
-        lo_b = b4;
-    }
-    LCP[j] = (int)first_barrier(bar0, bar1, (u32)p, (u32)match);
+sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
+                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    int j = chunk_start[c];
+    if (j < 0) return;
+    LCP[j] = j == 0 ? 0 : direct_lcp((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
 }
 
-// Stage-4 variant of the above: `need` marks the slots whose LCP entry the comparison stage did not
+// Stage 4: `need` marks the slots whose LCP entry the comparison stage did not
 // produce (group heads, members of groups that went through the doubling rounds).
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
@@ -434,40 +448,9 @@ sa_need_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__rest
 __global__ void __launch_bounds__(256)
 sa_lcp_need_kernel(const unsigned char *__restrict__ need, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
-    const u32 *__restrict__ W = (const u32 *)T;
     i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || !need[j]) return;
-    if (j == 0) {
-        LCP[0] = 0;
-        return;
-    }
-    const u32 p = (u32)SA[j], q = (u32)SA[j - 1];
-    const u32 lenmin = (u32)n - (p > q ? p : q);
-    const u32 *pa = W + (p >> 2), *pb = W + (q >> 2);
-    const unsigned sha = (p & 3u) * 8u, shb = (q & 3u) * 8u;
-    u32 lo_a = *pa, lo_b = *pb;
-    u32 h = 0, match = lenmin;
-    while (h < lenmin) {
-        u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
-        u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
-        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
-        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
-        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
-        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
-        if (d0 | d1 | d2 | d3) {
-            u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
-            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-            u32 at = h + wsel * 4u + ((u32)(__ffs((int)dd) - 1) >> 3);
-            match = at < lenmin ? at : lenmin;
-            break;
-        }
-        h += 16u;
-        pa += 4;
-        pb += 4;
-        lo_a = a4;
-        lo_b = b4;
-    }
-    LCP[j] = (int)first_barrier(bar0, bar1, p, match);
+    LCP[j] = j == 0 ? 0 : direct_lcp((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
 }
 
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
@@ -614,13 +597,14 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + 4096 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + a / 64 + 8192 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
     u64 *k0, *k1;
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
     unsigned char *deferred, *need;
+    int *chunk_start;  // first slot of every warp chunk of sa_pairs_kernel
     u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
     void *rscratch;
 };
@@ -647,7 +631,7 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
     RV_TRY(prof_begin(st));
     RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, B.bar1, k,
-              dSA, dISA, dLCP, B.deferred, B.small + 257);
+              dSA, dISA, dLCP, B.deferred, B.small + 257, B.chunk_start);
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 2;
     u32 lg = 0;
@@ -655,7 +639,8 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     RV_CUDA(cudaStreamSynchronize(st.s));
     *large = lg != 0;
     if (!*large) {
-        RV_LAUNCH((sa_headlcp_kernel<KeyT>), blocks, 256, 0, st.s, keys, n, dT, B.bar, B.bar1, dSA, dLCP);
+        const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
+        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP);
         st.launches++;
     }
     RV_KCHECK();
@@ -745,9 +730,10 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
     B.deferred = ws.take<unsigned char>(n);
     B.need = ws.take<unsigned char>(n);
+    B.chunk_start = ws.take<int>(n / PR_CHUNK + 2 * PR_WARPS + 8);
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
-    if (!B.deferred || !B.need || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    if (!B.deferred || !B.need || !B.chunk_start || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;

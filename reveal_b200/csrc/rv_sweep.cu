@@ -24,48 +24,61 @@ static const int SW_THREADS = 256;
 static const int SW_CHUNKS = 4;
 static const int SW_TILE = SW_THREADS * SW_CHUNKS;
 
-__global__ void __launch_bounds__(SW_THREADS) pair_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec) {
+// count pass: per-tile number of hits + one hit bit per slot (a ballot word per 32 slots), so that the write
+// pass only touches the (sparse) hits
+__global__ void __launch_bounds__(SW_THREADS) pair_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u32 *__restrict__ hitbits) {
     __shared__ u64 scratch[33];
     u64 mine = 0;
     for (int c = 0; c < SW_CHUNKS; c++) {
         i64 i = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
         i64 l, a, b;
-        mine += pair_test(p, i, l, a, b) ? 1u : 0u;
+        bool hit = pair_test(p, i, l, a, b);
+        unsigned m = __ballot_sync(FULL, hit);
+        if ((threadIdx.x & 31u) == 0) hitbits[i >> 5] = m;
+        mine += hit ? 1u : 0u;
     }
     u64 total;
     block_incl_sum<SW_THREADS, u64>(mine, scratch, &total);
     if (threadIdx.x == 0) tile_rec[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SW_THREADS) pair_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, i64 *__restrict__ out, i64 cap) {
-    __shared__ u64 scratch[33];
-    u64 carry = tile_rec[blockIdx.x];
-    for (int c = 0; c < SW_CHUNKS; c++) {
-        i64 i = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
+// write pass: one warp per tile of SW_TILE slots (= 32 ballot words, one per lane)
+__global__ void __launch_bounds__(SW_THREADS) pair_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u32 *__restrict__ hitbits,
+                                                                i64 tiles, i64 *__restrict__ out, i64 cap) {
+    const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
+    if (tile >= tiles) return;  // warp-uniform
+    const unsigned lane = threadIdx.x & 31u;
+    const i64 word = tile * (SW_TILE / 32) + lane;
+    u32 bits = word * 32 < p.n ? hitbits[word] : 0u;
+    u32 c = (u32)__popc(bits);
+    u32 inc = warp_incl_sum(c);
+    u64 at = tile_rec[tile] + (u64)(inc - c);
+    while (bits) {
+        int bpos = __ffs((int)bits) - 1;
+        bits &= bits - 1u;
+        i64 i = word * 32 + bpos;
         i64 l = 0, a = 0, b = 0;
-        bool hit = pair_test(p, i, l, a, b);
-        u64 total;
-        u64 inc = block_incl_sum<SW_THREADS, u64>(hit ? 1u : 0u, scratch, &total);
-        if (hit) {
-            u64 at = carry + inc - 1;
-            if ((i64)at < cap) {
-                out[3 * at + 0] = l;
-                out[3 * at + 1] = a;
-                out[3 * at + 2] = b;
-            }
+        pair_test(p, i, l, a, b);
+        if ((i64)at < cap) {
+            out[3 * at + 0] = l;
+            out[3 * at + 1] = a;
+            out[3 * at + 2] = b;
         }
-        carry += total;
-        __syncthreads();
+        at++;
     }
 }
 
 // ---- multi sweep --------------------------------------------------------------
-__global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem) {
+__global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem,
+                                                                 u32 *__restrict__ hitbits) {
     __shared__ u64 s1[33], s2[33];
     u64 nr = 0, nm = 0;
     for (int c = 0; c < SW_CHUNKS; c++) {
         i64 ub = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
+        u64 r0 = nr;
         multi_visit(p, ub, [&](i64, i64, i64 size) { nr++; nm += (u64)size; });
+        unsigned m = __ballot_sync(FULL, nr != r0);
+        if ((threadIdx.x & 31u) == 0) hitbits[ub >> 5] = m;
     }
     u64 tr, tm;
     block_incl_sum<SW_THREADS, u64>(nr, s1, &tr);
@@ -76,40 +89,40 @@ __global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u6
     }
 }
 
+// write pass: one warp per tile; a lane re-walks only the closing slots flagged in its ballot word
 __global__ void __launch_bounds__(SW_THREADS)
-multi_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u64 *__restrict__ tile_mem, i64 *__restrict__ hdr, i64 hdr_cap,
-                   i64 *__restrict__ members, i64 mem_cap) {
-    __shared__ u64 s1[33], s2[33];
-    u64 carry_r = tile_rec[blockIdx.x], carry_m = tile_mem[blockIdx.x];
-    for (int c = 0; c < SW_CHUNKS; c++) {
-        i64 ub = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
-        u64 nr = 0, nm = 0;
+multi_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u64 *__restrict__ tile_mem, const u32 *__restrict__ hitbits, i64 tiles,
+                   i64 *__restrict__ hdr, i64 hdr_cap, i64 *__restrict__ members, i64 mem_cap) {
+    const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
+    if (tile >= tiles) return;  // warp-uniform
+    const unsigned lane = threadIdx.x & 31u;
+    const i64 word = tile * (SW_TILE / 32) + lane;
+    const u32 bits0 = word * 32 < p.n ? hitbits[word] : 0u;
+    u64 nr = 0, nm = 0;
+    for (u32 bits = bits0; bits; bits &= bits - 1u) {
+        i64 ub = word * 32 + (__ffs((int)bits) - 1);
         multi_visit(p, ub, [&](i64, i64, i64 size) { nr++; nm += (u64)size; });
-        u64 tr, tm;
-        u64 ir = block_incl_sum<SW_THREADS, u64>(nr, s1, &tr);
-        u64 im = block_incl_sum<SW_THREADS, u64>(nm, s2, &tm);
-        u64 at_r = carry_r + ir - nr, at_m = carry_m + im - nm;
-        if (nr) {
-            multi_visit(p, ub, [&](i64 l, i64 lb, i64 size) {
-                if ((i64)at_r < hdr_cap) {
-                    hdr[3 * at_r + 0] = l;
-                    hdr[3 * at_r + 1] = size;
-                    hdr[3 * at_r + 2] = (i64)at_m;
+    }
+    u64 ir = warp_incl_sum(nr), im = warp_incl_sum(nm);
+    u64 at_r = tile_rec[tile] + ir - nr, at_m = tile_mem[tile] + im - nm;
+    for (u32 bits = bits0; bits; bits &= bits - 1u) {
+        i64 ub = word * 32 + (__ffs((int)bits) - 1);
+        multi_visit(p, ub, [&](i64 l, i64 lb, i64 size) {
+            if ((i64)at_r < hdr_cap) {
+                hdr[3 * at_r + 0] = l;
+                hdr[3 * at_r + 1] = size;
+                hdr[3 * at_r + 2] = (i64)at_m;
+            }
+            for (i64 x = 0; x < size; x++) {
+                if ((i64)at_m < mem_cap) {
+                    i64 pos = p.SA[lb + x];
+                    members[2 * at_m + 0] = sample_of(p, pos);
+                    members[2 * at_m + 1] = pos;
                 }
-                for (i64 x = 0; x < size; x++) {
-                    if ((i64)at_m < mem_cap) {
-                        i64 pos = p.SA[lb + x];
-                        members[2 * at_m + 0] = sample_of(p, pos);
-                        members[2 * at_m + 1] = pos;
-                    }
-                    at_m++;
-                }
-                at_r++;
-            });
-        }
-        carry_r += tr;
-        carry_m += tm;
-        __syncthreads();
+                at_m++;
+            }
+            at_r++;
+        });
     }
 }
 
@@ -140,7 +153,8 @@ __global__ void __launch_bounds__(1024) sweep_tilescan_kernel(u64 *__restrict__ 
 
 size_t sweep_scratch_bytes(i64 n) {
     i64 tiles = (n + SW_TILE - 1) / SW_TILE;
-    return (size_t)(2 * tiles + 8) * 8 + 512;
+    // [tile_rec][tile_mem][totals 8 words][hit bits: one u32 per 32 slots, padded to whole tiles]
+    return (size_t)(2 * tiles + 8) * 8 + (size_t)tiles * (SW_TILE / 32) * 4 + 512;
 }
 
 int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count) {
@@ -150,7 +164,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count) 
     u64 *tile_rec = (u64 *)scratch;
     u64 *totals = tile_rec + 2 * tiles;
     RV_TRY(prof_begin(st));
-    RV_LAUNCH(pair_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec);
+    RV_LAUNCH(pair_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, (u64 *)nullptr, tiles, totals);
     st.launches += 2;
@@ -165,7 +179,9 @@ int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, 
     if (p.n < 2) return RV_OK;
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
     RV_TRY(prof_begin(st));
-    RV_LAUNCH(pair_write_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, (const u64 *)scratch, d_out, cap);
+    const u64 *tile_rec = (const u64 *)scratch;
+    const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
+    RV_LAUNCH(pair_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_out, cap);
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
     st.launches++;
     RV_KCHECK();
@@ -179,7 +195,7 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     u64 *tile_rec = (u64 *)scratch, *tile_mem = tile_rec + tiles;
     u64 *totals = tile_rec + 2 * tiles;
     RV_TRY(prof_begin(st));
-    RV_LAUNCH(multi_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, tile_mem);
+    RV_LAUNCH(multi_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
     st.launches += 2;
@@ -196,7 +212,9 @@ int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr,
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
     const u64 *tile_rec = (const u64 *)scratch, *tile_mem = tile_rec + tiles;
     RV_TRY(prof_begin(st));
-    RV_LAUNCH(multi_write_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, d_hdr, hdr_cap, d_mem, mem_cap);
+    const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
+    RV_LAUNCH(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
+              d_mem, mem_cap);
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
     st.launches++;
     RV_KCHECK();
