@@ -195,7 +195,6 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
                 int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start) {
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
-    __shared__ u32 s_fin[PR_WARPS][PR_MAXT];            // suffix at every local slot after placement (0xFFFFFFFF: not placed here)
     __shared__ int s_lcp[PR_WARPS][PR_MAXT];
     __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
     __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group; 0xFF: not a small group
@@ -389,10 +388,16 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     __syncwarp();
 
     // ---- place the warp's groups: slot = group start + number of smaller mates ----
-    u32 *fin = s_fin[w];
-    for (int t = (int)lane; t < nt; t += 32) fin[t] = 0xFFFFFFFFu;
-    __syncwarp();
-    for (int t = (int)lane; t < nt; t += 32) {
+    // The final order of the chunk's suffixes replaces ssa[] (shared memory is also L1 capacity here: no second
+    // array); every lane keeps its <= PR_ROUNDS entries in registers across the overwrite.
+    u32 my_suf[PR_ROUNDS];
+    int my_f[PR_ROUNDS];
+#pragma unroll
+    for (int k = 0; k < PR_ROUNDS; k++) {
+        const int t = k * 32 + (int)lane;
+        my_f[k] = -1;
+        my_suf[k] = 0;
+        if (t >= nt) continue;
         unsigned L = sL[t];
         if (L == 0xFFu) continue;  // member of a group with more than SA_SMALL_G suffixes: stage 4
         const int t0 = t - (int)L;
@@ -408,9 +413,17 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         u32 suf = ssa[t];
         SA[slot] = (int)suf;
         rank[suf] = (int)slot;
-        fin[t0 + (int)r] = suf;
         if (r > 0) LCP[slot] = lcpv[t];
+        my_f[k] = t0 + (int)r;
+        my_suf[k] = suf;
     }
+    __syncwarp();
+    u32 *fin = ssa;
+    for (int t = (int)lane; t < nt; t += 32) fin[t] = 0xFFFFFFFFu;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < PR_ROUNDS; k++)
+        if (my_f[k] >= 0) fin[my_f[k]] = my_suf[k];
     __syncwarp();
     // ---- the first slot of every group: its left neighbour differs inside the k-mer, one short direct comparison.
     //      (The first slot of the chunk has its neighbour in another warp: sa_chunkhead_kernel.) ----
@@ -629,6 +642,17 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const unsigned blocks = (unsigned)((n + 255) / 256);
     RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((n + 1023) / 1024 + 1), 1024, 0, st.s, dT, n, B.bar, B.bar1);
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
+#ifndef RV_EMU
+    {   // shared memory is carved out of the same 228 KB as L1, and this kernel lives on L1 hits for its text gathers
+        static int carve_done = -2;
+        int want = -1;
+        if (const char *e = getenv("RV_PAIRS_CARVEOUT")) want = atoi(e);  // tuning hook: percent of the array used as shared memory
+        if (want != carve_done) {
+            if (want >= 0) cudaFuncSetAttribute(sa_pairs_kernel<KeyT>, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+            carve_done = want;
+        }
+    }
+#endif
     RV_TRY(prof_begin(st));
     RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, B.bar1, k,
               dSA, dISA, dLCP, B.deferred, B.small + 257, B.chunk_start);
