@@ -307,11 +307,16 @@ static int run_pair(rv_index *h, const SweepArgs &a, int64_t *count) {
     if (!count) return RV_ERR_ARG;
     h->last_kind = 0;
     RV_TRY(h->sw.reserve(sweep_scratch_bytes(a.n)));
+    if (h->res.cap == 0) RV_TRY(h->res.reserve((size_t)1 << 20));
+    // speculative write into the buffer at hand; redone only if the count outgrows it
     i64 c = 0;
-    RV_TRY(sweep_pair_count(h->st, a, h->sw.base, &c));
-    RV_TRY(h->res.reserve(pad256((size_t)(c > 0 ? c : 1) * 24)));
+    const i64 cap = (i64)(h->res.cap / 24);
+    RV_TRY(sweep_pair_count(h->st, a, h->sw.base, &c, (i64 *)h->res.base, cap));
+    if (c > cap) {
+        RV_TRY(h->res.reserve(pad256((size_t)c * 24 * 2)));
+        RV_TRY(sweep_pair_write(h->st, a, h->sw.base, (i64 *)h->res.base, c));
+    }
     h->d_rows = (i64 *)h->res.base;
-    if (c > 0) RV_TRY(sweep_pair_write(h->st, a, h->sw.base, h->d_rows, c));
     h->last_kind = 1;
     h->last_rec = c;
     h->last_mem = 0;
@@ -324,13 +329,23 @@ static int run_multi(rv_index *h, const SweepArgs &a, int64_t *nrec, int64_t *nm
     h->last_kind = 0;
     if (a.main_nsamples > 2 && !a.SO) { set_error("multi sweep: SO missing for %d samples", a.main_nsamples); return RV_ERR_STATE; }
     RV_TRY(h->sw.reserve(sweep_scratch_bytes(a.n)));
+    if (h->res.cap == 0) RV_TRY(h->res.reserve((size_t)1 << 20));
+    // layout of the result buffer: first third header rows (24 B), the rest member rows (16 B)
     i64 r = 0, m = 0;
-    RV_TRY(sweep_multi_count(h->st, a, h->sw.base, &r, &m));
-    size_t hdr_bytes = pad256((size_t)(r > 0 ? r : 1) * 24);
-    RV_TRY(h->res.reserve(hdr_bytes + pad256((size_t)(m > 0 ? m : 1) * 16)));
+    size_t hdr_bytes = pad256(h->res.cap / 3);
+    i64 hdr_cap = (i64)(hdr_bytes / 24), mem_cap = (i64)((h->res.cap - hdr_bytes) / 16);
+    RV_TRY(sweep_multi_count(h->st, a, h->sw.base, &r, &m, (i64 *)h->res.base, hdr_cap, (i64 *)(h->res.base + hdr_bytes), mem_cap));
+    if (r > hdr_cap || m > mem_cap) {
+        size_t need_hdr = pad256((size_t)(r > 0 ? r : 1) * 24 * 2), need_mem = pad256((size_t)(m > 0 ? m : 1) * 16 * 2);
+        size_t total = 3 * (need_hdr > need_mem / 2 ? need_hdr : need_mem / 2) + 1024;
+        RV_TRY(h->res.reserve(total));
+        hdr_bytes = pad256(h->res.cap / 3);
+        hdr_cap = (i64)(hdr_bytes / 24);
+        mem_cap = (i64)((h->res.cap - hdr_bytes) / 16);
+        RV_TRY(sweep_multi_write(h->st, a, h->sw.base, (i64 *)h->res.base, hdr_cap, (i64 *)(h->res.base + hdr_bytes), mem_cap));
+    }
     h->d_rows = (i64 *)h->res.base;
     h->d_members = (i64 *)(h->res.base + hdr_bytes);
-    if (r > 0) RV_TRY(sweep_multi_write(h->st, a, h->sw.base, h->d_rows, r, h->d_members, m));
     h->last_kind = 2;
     h->last_rec = r;
     h->last_mem = m;

@@ -443,7 +443,15 @@ sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, con
     if (c >= nchunks) return;
     int j = chunk_start[c];
     if (j < 0) return;
-    LCP[j] = j == 0 ? 0 : direct_lcp((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
+    if (j == 0) {
+        LCP[0] = 0;
+        return;
+    }
+    // this pass is enqueued before the host knows whether stage 4 is needed: a slot of a group that was not placed
+    // yet may still hold anything, and is rewritten later
+    u32 p = (u32)SA[j], q = (u32)SA[j - 1];
+    if (p >= (u32)n || q >= (u32)n) return;
+    LCP[j] = direct_lcp((const u32 *)T, (u32)n, p, q, bar0, bar1);
 }
 
 // Stage 4: `need` marks the slots whose LCP entry the comparison stage did not
@@ -660,13 +668,14 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     st.launches += 2;
     u32 lg = 0;
     RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
-    RV_CUDA(cudaStreamSynchronize(st.s));
-    *large = lg != 0;
-    if (!*large) {
+    {   // enqueue the chunk-head LCP pass before waiting for the flag: when stage 4 turns out to be needed it
+        // rewrites these few entries anyway (sa_lcp_need_kernel / Kasai)
         const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
         RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP);
         st.launches++;
     }
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    *large = lg != 0;
     RV_KCHECK();
     *keys_out = keys;
     *sa_out = sa;

@@ -157,7 +157,10 @@ size_t sweep_scratch_bytes(i64 n) {
     return (size_t)(2 * tiles + 8) * 8 + (size_t)tiles * (SW_TILE / 32) * 4 + 512;
 }
 
-int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count) {
+// count pass + tile scan; when a result buffer is already at hand (d_spec, cap_spec rows) the write pass is
+// enqueued right behind them, before the host reads the count back -- one synchronisation instead of two.
+// The caller re-runs sweep_pair_write if the count turns out to exceed cap_spec.
+int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, i64 *d_spec, i64 cap_spec) {
     *count = 0;
     if (p.n < 2) return RV_OK;
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
@@ -170,6 +173,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count) 
     st.launches += 2;
     u64 h[2];
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
+    if (d_spec && cap_spec > 0) RV_TRY(sweep_pair_write(st, p, scratch, d_spec, cap_spec));
     RV_CUDA(cudaStreamSynchronize(st.s));
     *count = (i64)h[0];
     return RV_OK;
@@ -188,7 +192,8 @@ int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, 
     return RV_OK;
 }
 
-int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem) {
+int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem, i64 *d_hdr_spec, i64 hdr_cap_spec, i64 *d_mem_spec,
+                      i64 mem_cap_spec) {
     *nrec = *nmem = 0;
     if (p.n < 2) return RV_OK;
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
@@ -201,6 +206,8 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     st.launches += 2;
     u64 h[2];
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
+    if (d_hdr_spec && hdr_cap_spec > 0 && mem_cap_spec > 0)
+        RV_TRY(sweep_multi_write(st, p, scratch, d_hdr_spec, hdr_cap_spec, d_mem_spec, mem_cap_spec));
     RV_CUDA(cudaStreamSynchronize(st.s));
     *nrec = (i64)h[0];
     *nmem = (i64)h[1];

@@ -20,9 +20,10 @@ struct SweepArgs {
 };
 
 size_t sweep_scratch_bytes(i64 n);
-int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count);
+int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, i64 *d_spec, i64 cap_spec);
 int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, i64 cap);
-int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem);
+int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem, i64 *d_hdr_spec, i64 hdr_cap_spec, i64 *d_mem_spec,
+                      i64 mem_cap_spec);
 int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr, i64 hdr_cap, i64 *d_mem, i64 mem_cap);
 
 }  // namespace rv
