@@ -88,7 +88,7 @@ typedef struct rv_kernel_profile {
     int64_t launches_total; /* every kernel this handle launched since creation */
 } rv_kernel_profile;
 int rv_profile(rv_index *idx, int32_t enable);
-int rv_get_profile(const rv_index *idx, rv_kernel_profile *out);
+int rv_get_profile(rv_index *idx, rv_kernel_profile *out);
 int64_t rv_index_n(const rv_index *idx);
 
 /* Getters: copy an array to host memory. idx_bits 32 -> int32 entries (LCP int32),

@@ -133,8 +133,8 @@ void rv_index_free(rv_index *h) {
     h->res.release();
     for (int i = 0; i < 6; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    if (h->st.pe0) cudaEventDestroy(h->st.pe0);
-    if (h->st.pe1) cudaEventDestroy(h->st.pe1);
+    prof_collect(h->st);
+    for (cudaEvent_t e : h->st.free_events) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->st.s);
     delete h;
 }
@@ -224,10 +224,7 @@ int64_t rv_index_n(const rv_index *h) { return h ? h->n : 0; }
 
 int rv_profile(rv_index *h, int32_t enable) {
     if (!h) return RV_ERR_ARG;
-    if (enable && !h->st.pe0) {
-        RV_CUDA(cudaEventCreate(&h->st.pe0));
-        RV_CUDA(cudaEventCreate(&h->st.pe1));
-    }
+    RV_TRY(prof_collect(h->st));
     h->st.prof = enable != 0;
     for (int k = 0; k < 4; k++) {
         h->st.prof_ms[k] = 0;
@@ -236,8 +233,9 @@ int rv_profile(rv_index *h, int32_t enable) {
     }
     return RV_OK;
 }
-int rv_get_profile(const rv_index *h, rv_kernel_profile *out) {
+int rv_get_profile(rv_index *h, rv_kernel_profile *out) {
     if (!h || !out) return RV_ERR_ARG;
+    RV_TRY(prof_collect(h->st));
     for (int k = 0; k < 4; k++) {
         out->ms[k] = h->st.prof_ms[k];
         out->launches[k] = h->st.prof_launches[k];

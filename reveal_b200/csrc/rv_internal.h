@@ -5,6 +5,7 @@
 #include "../../include/reveal_b200.h"
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 namespace rv {
 
@@ -53,32 +54,68 @@ struct PhaseTimes {  // device milliseconds (CUDA events on the build stream)
     int launches = 0;
 };
 
+struct ProfRec {
+    cudaEvent_t e0, e1;
+    int slot;
+    long long launches, bytes;
+};
+
 struct Stream {
     cudaStream_t s = 0;
     int launches = 0;           // kernels launched by this library on the stream since the last reset
     long long launches_total = 0;
-    // optional per-kernel profile of the dominant kernel (radix pass), CUDA events on this stream
+    // optional per-kernel profile: event pairs recorded around runs of one kernel, resolved lazily
+    // (prof_collect) so that profiling adds no synchronisation to the measured step
     bool prof = false;
-    cudaEvent_t pe0 = 0, pe1 = 0;
+    std::vector<ProfRec> pending;
+    std::vector<cudaEvent_t> free_events;
+    cudaEvent_t cur0 = 0;
     double prof_ms[4] = {0, 0, 0, 0};          // per slot (enum rv_prof_slot): summed kernel time
     long long prof_launches[4] = {0, 0, 0, 0};
     long long prof_bytes[4] = {0, 0, 0, 0};    // algorithmic bytes moved by those launches
 };
 
-// bracket a run of launches of one kernel with events (profile mode only; the end syncs the stream)
+inline int prof_event(Stream &st, cudaEvent_t *e) {
+    if (!st.free_events.empty()) {
+        *e = st.free_events.back();
+        st.free_events.pop_back();
+        return RV_OK;
+    }
+    RV_CUDA(cudaEventCreate(e));
+    return RV_OK;
+}
 inline int prof_begin(Stream &st) {
-    if (st.prof) RV_CUDA(cudaEventRecord(st.pe0, st.s));
+    if (!st.prof) return RV_OK;
+    RV_TRY(prof_event(st, &st.cur0));
+    RV_CUDA(cudaEventRecord(st.cur0, st.s));
     return RV_OK;
 }
 inline int prof_end(Stream &st, int slot, long long launches, long long bytes) {
     if (!st.prof) return RV_OK;
-    float ms = 0;
-    RV_CUDA(cudaEventRecord(st.pe1, st.s));
-    RV_CUDA(cudaEventSynchronize(st.pe1));
-    RV_CUDA(cudaEventElapsedTime(&ms, st.pe0, st.pe1));
-    st.prof_ms[slot] += ms;
-    st.prof_launches[slot] += launches;
-    st.prof_bytes[slot] += bytes;
+    ProfRec r;
+    r.e0 = st.cur0;
+    RV_TRY(prof_event(st, &r.e1));
+    RV_CUDA(cudaEventRecord(r.e1, st.s));
+    r.slot = slot;
+    r.launches = launches;
+    r.bytes = bytes;
+    st.pending.push_back(r);
+    return RV_OK;
+}
+// resolve the recorded pairs (synchronises the stream)
+inline int prof_collect(Stream &st) {
+    if (st.pending.empty()) return RV_OK;
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    for (ProfRec &r : st.pending) {
+        float ms = 0;
+        RV_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        st.prof_ms[r.slot] += ms;
+        st.prof_launches[r.slot] += r.launches;
+        st.prof_bytes[r.slot] += r.bytes;
+        st.free_events.push_back(r.e0);
+        st.free_events.push_back(r.e1);
+    }
+    st.pending.clear();
     return RV_OK;
 }
 
