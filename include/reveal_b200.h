@@ -70,6 +70,11 @@ void rv_index_free(rv_index *idx);
  * unless rc, in which case the handle works on its own copy). */
 int rv_build(rv_index *idx, const uint8_t *T, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
 int rv_build_device(rv_index *idx, const uint8_t *dT, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc);
+/* construct() with the suffix array (and optionally the LCP array) read from the reference's cache files
+ * (index(sa=..., lcp=...), interface.c:224-231,255-262; raw little-endian int32): uploads them, derives the
+ * inverse SA (interface.c:235-238), computes the LCP array when LCP == NULL, builds SO. */
+int rv_build_cached(rv_index *idx, const uint8_t *T, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc, const int32_t *SA,
+                    const int32_t *LCP);
 int rv_get_times(const rv_index *idx, rv_times *out);
 
 /* Optional per-kernel profile: when enabled the library brackets the launches of its heavy kernels

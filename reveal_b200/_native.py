@@ -42,6 +42,7 @@ SIGNATURES = {
     "rv_index_free": (None, [c_vp]),
     "rv_build": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_int32]),
     "rv_build_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_int32]),
+    "rv_build_cached": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
     "rv_get_times": (ctypes.c_int, [c_vp, ctypes.POINTER(Times)]),
     "rv_index_n": (ctypes.c_int64, [c_vp]),
     "rv_profile": (ctypes.c_int, [c_vp, ctypes.c_int32]),

@@ -139,7 +139,8 @@ void rv_index_free(rv_index *h) {
     delete h;
 }
 
-static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc) {
+static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc,
+                        const int32_t *hSA = nullptr, const int32_t *hLCP = nullptr) {
     if (!h || !T || n <= 0 || nsamples < 1 || (nsamples > 1 && !nsep)) {
         set_error(n <= 0 ? "No text to index." : "rv_build: bad argument");  // interface.c:177-180
         return RV_ERR_ARG;
@@ -186,7 +187,23 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     if (rc) RV_TRY(revcomp_suffix(st, h->dT, h->nsep[0], n));
     RV_CUDA(cudaEventRecord(h->ev[2], st.s));
     bool lcp_done = false;
-    RV_TRY(sa_build(st, h->arena, h->dT, n, h->dSA, h->dISA, h->dLCP, &lcp_done, &pt));
+    if (hSA) {  // suffix array (and maybe LCP) from a cache file (interface.c:224-231, 255-262)
+        RV_CUDA(cudaMemcpyAsync(h->dSA, hSA, (size_t)n * 4, cudaMemcpyHostToDevice, st.s));
+        u32 *d_bad = (u32 *)h->arena.take<u32>(64);
+        if (!d_bad) { set_error("rv_build: arena too small"); return RV_ERR_NOMEM; }
+        RV_CUDA(cudaMemsetAsync(d_bad, 0, 4, st.s));
+        RV_TRY(isa_build(st, n, h->dSA, h->dISA, d_bad));
+        u32 bad = 0;
+        RV_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st.s));
+        RV_CUDA(cudaStreamSynchronize(st.s));
+        if (bad) { set_error("the suffix array passed in is not a permutation of 0..n-1"); return RV_ERR_ARG; }
+        if (hLCP) {
+            RV_CUDA(cudaMemcpyAsync(h->dLCP, hLCP, (size_t)n * 4, cudaMemcpyHostToDevice, st.s));
+            lcp_done = true;
+        }
+    } else {
+        RV_TRY(sa_build(st, h->arena, h->dT, n, h->dSA, h->dISA, h->dLCP, &lcp_done, &pt));
+    }
     RV_CUDA(cudaEventRecord(h->ev[3], st.s));
     if (!lcp_done) RV_TRY(lcp_build(st, h->dT, n, h->dSA, h->dISA, h->dLCP));
     RV_CUDA(cudaEventRecord(h->ev[4], st.s));
@@ -213,6 +230,12 @@ int rv_build(rv_index *h, const uint8_t *T, int64_t n, const int64_t *nsep, int3
 }
 int rv_build_device(rv_index *h, const uint8_t *dT, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc) {
     return build_common(h, dT, true, n, nsep, nsamples, rc);
+}
+
+int rv_build_cached(rv_index *h, const uint8_t *T, int64_t n, const int64_t *nsep, int32_t nsamples, int32_t rc, const int32_t *SA,
+                    const int32_t *LCP) {
+    if (!SA) { set_error("rv_build_cached: SA missing"); return RV_ERR_ARG; }
+    return build_common(h, T, false, n, nsep, nsamples, rc, SA, LCP);
 }
 
 int rv_get_times(const rv_index *h, rv_times *out) {

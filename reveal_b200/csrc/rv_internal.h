@@ -127,6 +127,7 @@ size_t sa_workspace_bytes(i64 n);
 int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt);
 
 int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
+int isa_build(Stream &st, i64 n, const int *dSA, int *dISA, u32 *d_bad);
 int so_build(Stream &st, i64 n, const i64 *dNsep, int nsamples, unsigned short *dSO);
 int revcomp_suffix(Stream &st, unsigned char *dT, i64 start, i64 n);
 

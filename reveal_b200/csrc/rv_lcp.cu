@@ -52,6 +52,35 @@ int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const 
     return RV_OK;
 }
 
+// SAi[SA[i]] = i  (interface.c:235-238) -- only used when the suffix array comes from a cache file
+__global__ void __launch_bounds__(256) isa_scatter_kernel(const int *__restrict__ SA, i64 n, int *__restrict__ ISA, u32 *__restrict__ bad) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = SA[i];
+    if (s < 0 || s >= n) {
+        *bad = 1u;  // not a permutation of 0..n-1: a stale or foreign cache file
+        return;
+    }
+    ISA[s] = (int)i;
+}
+
+// every slot must have won its scatter: a value that occurs twice leaves one of the two slots unanswered
+__global__ void __launch_bounds__(256) isa_verify_kernel(const int *__restrict__ SA, i64 n, const int *__restrict__ ISA, u32 *__restrict__ bad) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = SA[i];
+    if (s < 0 || s >= n || ISA[s] != (int)i) *bad = 1u;
+}
+
+int isa_build(Stream &st, i64 n, const int *dSA, int *dISA, u32 *d_bad) {
+    if (n <= 0) return RV_OK;
+    RV_LAUNCH(isa_scatter_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, dSA, n, dISA, d_bad);
+    RV_LAUNCH(isa_verify_kernel, (unsigned)((n + 255) / 256), 256, 0, st.s, dSA, n, dISA, d_bad);
+    st.launches += 2;
+    RV_KCHECK();
+    return RV_OK;
+}
+
 // SO[p] = number of sample separators strictly before p  (nsep[k] = position of the last '$' of sample k)
 __global__ void __launch_bounds__(256) so_fill_kernel(i64 n, const i64 *__restrict__ nsep, int nsamples, unsigned short *__restrict__ SO) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;

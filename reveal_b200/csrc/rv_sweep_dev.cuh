@@ -37,6 +37,15 @@ __device__ __forceinline__ int sample_of(const SweepArgs &p, i64 pos) { return p
 
 // ismultimum (reveal.c:227-259) for the interval [lb,ub] of value l > 0
 __device__ __forceinline__ bool multi_ok(const SweepArgs &p, i64 lb, i64 ub) {
+    // a conjunction of two order-independent predicates: the left-maximality test (which rejects most candidates of
+    // similar genomes) runs first, the per-member sample look-ups only for the survivors
+    bool maximal = false;
+    for (i64 j = lb; j < ub; j++)
+        if (left_maximal(p.T, p.SA[j], p.SA[j + 1])) {
+            maximal = true;
+            break;
+        }
+    if (!maximal) return false;
     if (p.main_nsamples == 2) {
         if ((p.SA[ub] > p.nsep0) == (p.SA[lb] > p.nsep0)) return false;
     } else if (p.main_nsamples <= 64) {
@@ -53,9 +62,7 @@ __device__ __forceinline__ bool multi_ok(const SweepArgs &p, i64 lb, i64 ub) {
                 if ((int)p.SO[p.SA[q]] == s) return false;
         }
     }
-    for (i64 j = lb; j < ub; j++)
-        if (left_maximal(p.T, p.SA[j], p.SA[j + 1])) return true;
-    return false;
+    return true;
 }
 
 // Visits every reportable interval that closes at slot ub, inner first.

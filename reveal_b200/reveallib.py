@@ -118,24 +118,40 @@ class index(object):
             raise error("rc=1 needs a second sample.")
         if self._n == 0:
             raise error("No text to index.")  # interface.c:177-180
-        if self._safile or self._lcpfile:
-            raise error("precomputed sa/lcp files are not supported by the B200 build path")
         L = self._lib()
         T = self._text()
         nsep = np.asarray(self._nsep, dtype=np.int64)
         h = self._handle()
-        self._call(L.rv_build(h, T.ctypes.data, self._n, nsep.ctypes.data if len(nsep) else None, self._nsamples, rc))
+        if self._safile:
+            # precomputed arrays from the reference's cache files (interface.c:224-231, 255-262): raw saidx_t / lcp_t
+            it = np.int64 if self._bits == 64 else np.int32
+            sa = np.fromfile(self._safile, dtype=it, count=self._n)
+            if len(sa) != self._n:
+                raise error("suffix array file %s holds %d entries, expected %d" % (self._safile, len(sa), self._n))
+            sa = np.ascontiguousarray(sa, dtype=np.int32)
+            lcp = None
+            if self._lcpfile:
+                lcp = np.fromfile(self._lcpfile, dtype=np.uint32 if self._bits == 64 else np.int32, count=self._n)
+                if len(lcp) != self._n:
+                    raise error("lcp file %s holds %d entries, expected %d" % (self._lcpfile, len(lcp), self._n))
+                lcp = np.ascontiguousarray(lcp, dtype=np.int32)
+            self._call(L.rv_build_cached(h, T.ctypes.data, self._n, nsep.ctypes.data if len(nsep) else None, self._nsamples, rc,
+                                         sa.ctypes.data, lcp.ctypes.data if lcp is not None else None))
+        elif self._lcpfile:
+            raise error("an lcp file needs its suffix array file (sa=...) as well")
+        else:
+            self._call(L.rv_build(h, T.ctypes.data, self._n, nsep.ctypes.data if len(nsep) else None, self._nsamples, rc))
         self._rc = rc
         self._nT = self._n
         if rc:
             # the reference reverse-complements its T in place (interface.c:168-172): mirror the device text
             self._call(L.rv_get_text(h, T.ctypes.data))
             self._chunks = [T.tobytes()]
+        self._built = True
         if self._cache == 1:  # interface.c:182-189,273-285
             T.tofile(".reveal.t")
             self._array("SA").tofile(".reveal.sa")
             self._array("LCP").tofile(".reveal.lcp")
-        self._built = True
         self.main = self
         return None
 
