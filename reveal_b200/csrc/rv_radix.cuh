@@ -65,6 +65,57 @@ inline size_t radix_scratch_bytes(i64 n) {
     return (size_t)(2 * RS_MAXPASS * RS_BINS + 8 + 32) * 4 + (size_t)RS_MAXPASS * tiles * RS_BINS * 4 + 512;
 }
 
+// Keys that are never materialised: key[i] = first k symbols of suffix i of the text as a base-`base` number
+// (rv_sa.cu stage 2), value[i] = i.  The histogram kernel and the first digit pass compute them on the fly, so
+// the 8-12 bytes per suffix of a key/value array are neither written nor read back.
+struct TextKeySrc {
+    const unsigned char *T;
+    i64 n;
+    u32 base;
+    int k;
+    u64 top;  // base^(k-1)
+    unsigned short code[256];
+};
+static const int TK_PER = 16;  // consecutive positions whose keys one thread rolls
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT text_key_first(const TextKeySrc &s, const unsigned short *s_code, i64 i0) {
+    KeyT key = 0;
+    for (int t = 0; t < s.k; t++) {
+        i64 p = i0 + t;
+        key = key * (KeyT)s.base + (KeyT)(p < s.n ? s_code[s.T[p]] : 0);
+    }
+    return key;
+}
+template <typename KeyT>
+__device__ __forceinline__ KeyT text_key_next(const TextKeySrc &s, const unsigned short *s_code, i64 p, KeyT key) {
+    KeyT first = (KeyT)s_code[s.T[p]];                           // symbol leaving the window
+    KeyT next = (KeyT)(p + s.k < s.n ? s_code[s.T[p + s.k]] : 0);  // symbol entering it
+    return (key - first * (KeyT)s.top) * (KeyT)s.base + next;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src, RadixPlan plan, u32 *__restrict__ ghist) {
+    __shared__ u32 sh[RS_MAXPASS * RS_BINS];
+    __shared__ unsigned short s_code[256];
+    s_code[threadIdx.x] = src.code[threadIdx.x];  // RS_THREADS == 256
+    for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const i64 stride = (i64)gridDim.x * RS_THREADS * TK_PER;
+    for (i64 i0 = ((i64)blockIdx.x * RS_THREADS + threadIdx.x) * TK_PER; i0 < src.n; i0 += stride) {
+        KeyT key = text_key_first<KeyT>(src, s_code, i0);
+        for (int j = 0; j < TK_PER && i0 + j < src.n; j++) {
+            for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * RS_BINS + ((u32)(key >> plan.shift[p]) & plan.mask[p])], 1u);
+            key = text_key_next<KeyT>(src, s_code, i0 + j, key);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) {
+        u32 c = sh[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT *__restrict__ keys, i64 n, RadixPlan plan, u32 *__restrict__ ghist) {
     __shared__ u32 sh[RS_MAXPASS * RS_BINS];
@@ -94,10 +145,10 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict_
     gbase[blockIdx.x * RS_BINS + threadIdx.x] = inc - c;
 }
 
-template <typename KeyT, bool HAS_VAL>
+template <typename KeyT, bool HAS_VAL, bool FROM_TEXT>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin, u32 *__restrict__ vout,
-               i64 n, int shift, u32 mask, int dbits, const u32 *__restrict__ gbase, u32 *status, u32 *ticket) {
+               i64 n, int shift, u32 mask, int dbits, const u32 *__restrict__ gbase, u32 *status, u32 *ticket, TextKeySrc src) {
     __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> running per-warp offsets inside the bucket
     __shared__ u32 s_start[RS_BINS];             // first tile-local slot of each bucket
     __shared__ u32 s_off[RS_BINS];               // global slot of a bucket's first item minus s_start (mod 2^32)
@@ -119,10 +170,35 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
     KeyT key[RS_IPT];
     const int wbase = (int)w * 32 * RS_IPT;
     u32 *wh = s_whist + w * RS_BINS;
+    if (FROM_TEXT) {
+        // keys of RS_IPT consecutive suffixes rolled per thread, exchanged through shared memory into the striped order
+        unsigned short *s_code = (unsigned short *)s_off;  // 512 B: s_off is written much later
+        s_code[tid] = src.code[tid];
+        __syncthreads();
+        const i64 i0 = base + (i64)tid * RS_IPT;
+        if (i0 < n) {
+            KeyT kk = text_key_first<KeyT>(src, s_code, i0);
 #pragma unroll
-    for (int k = 0; k < RS_IPT; k++) {
-        int idx = wbase + k * 32 + (int)l;
-        key[k] = idx < cnt ? kin[base + idx] : (KeyT)0;
+            for (int j = 0; j < RS_IPT; j++) {
+                if (i0 + j < n) {
+                    s_keys[tid * RS_IPT + j] = kk;
+                    kk = text_key_next<KeyT>(src, s_code, i0 + j, kk);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) {
+            int idx = wbase + k * 32 + (int)l;
+            key[k] = idx < cnt ? s_keys[idx] : (KeyT)0;
+        }
+        __syncthreads();  // s_keys is reused as the bucket-ordered staging area below
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) {
+            int idx = wbase + k * 32 + (int)l;
+            key[k] = idx < cnt ? kin[base + idx] : (KeyT)0;
+        }
     }
 #pragma unroll
     for (int k = 0; k < RS_IPT; k++) {
@@ -180,7 +256,7 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             int idx = wbase + k * 32 + (int)l;
-            val[k] = idx < cnt ? vin[base + idx] : 0u;
+            val[k] = FROM_TEXT ? (u32)(base + idx) : (idx < cnt ? vin[base + idx] : 0u);
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
@@ -219,10 +295,12 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
 // Sorts n pairs by the digits of `plan` (least significant first), ping-ponging
 // between (k0,v0) and (k1,v1).  On return *result_in_0 tells where the sorted
 // pairs are.  `scratch` needs radix_scratch_bytes(n).  Stable.
+// With `text` the input pairs are virtual (TextKeySrc): nothing is read from (k0,v0), the first pass writes (k1,v1).
 template <typename KeyT>
-int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, const RadixPlan &plan, void *scratch, bool *result_in_0) {
+int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, const RadixPlan &plan, void *scratch, bool *result_in_0,
+                     const TextKeySrc *text = nullptr) {
     *result_in_0 = true;
-    if (n <= 1 || plan.npass == 0) return RV_OK;
+    if (n <= 0 || plan.npass == 0 || (n <= 1 && !text)) return RV_OK;
     if (n >= (i64)1 << 30) {
         set_error("radix_sort_pairs: n=%lld exceeds the 2^30 look-back word limit", (long long)n);
         return RV_ERR_UNSUPPORTED;
@@ -235,28 +313,46 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     size_t zero_bytes = (size_t)(2 * RS_MAXPASS * RS_BINS + 32) * 4 + (size_t)plan.npass * tiles * RS_BINS * 4;
     RV_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, st.s));
     int hist_blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
-    RV_LAUNCH((rs_hist_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st.s, k0, n, plan, ghist);
+    TextKeySrc none;
+    memset(&none, 0, sizeof none);
+    if (text) {
+        RV_LAUNCH((rs_hist_text_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st.s, *text, plan, ghist);
+    } else {
+        RV_LAUNCH((rs_hist_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st.s, k0, n, plan, ghist);
+    }
     RV_LAUNCH(rs_scan_kernel, plan.npass, RS_BINS, 0, st.s, ghist, gbase);
     st.launches += 2;
     const size_t smem = (size_t)RS_TILE * (sizeof(KeyT) + 4);
     static bool attr_done = false;
     if (!attr_done) {
-        auto kfn = rs_pass_kernel<KeyT, true>;
+        auto kfn = rs_pass_kernel<KeyT, true, false>;
+        auto kft = rs_pass_kernel<KeyT, true, true>;
         (void)kfn;
+        (void)kft;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     bool in0 = true;
     RV_TRY(prof_begin(st));
     for (int p = 0; p < plan.npass; p++) {
-        RV_LAUNCH((rs_pass_kernel<KeyT, true>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0,
-                  in0 ? v0 : v1, in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS,
-                  status + (size_t)p * tiles * RS_BINS, ticket + p);
+        if (p == 0 && text) {
+            RV_LAUNCH((rs_pass_kernel<KeyT, true, true>), (unsigned)tiles, RS_THREADS, smem, st.s, (const KeyT *)nullptr, k1, (const u32 *)nullptr, v1, n,
+                      plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS, status + (size_t)p * tiles * RS_BINS, ticket + p,
+                      *text);
+        } else {
+            RV_LAUNCH((rs_pass_kernel<KeyT, true, false>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0, in0 ? v0 : v1,
+                      in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS,
+                      status + (size_t)p * tiles * RS_BINS, ticket + p, none);
+        }
         st.launches++;
         in0 = !in0;
     }
     RV_KCHECK();
-    RV_TRY(prof_end(st, RV_PROF_RADIX_PASS, plan.npass, (long long)plan.npass * n * (long long)(sizeof(KeyT) + 4) * 2));
+    // algorithmic bytes: a virtual first pass reads one text byte per pair instead of key + value
+    long long pair_bytes = (long long)(sizeof(KeyT) + 4);
+    long long bytes = (long long)plan.npass * n * pair_bytes * 2 - (text ? n * (pair_bytes - 1) : 0);
+    RV_TRY(prof_end(st, RV_PROF_RADIX_PASS, plan.npass, bytes));
     *result_in_0 = in0;
     return RV_OK;
 }

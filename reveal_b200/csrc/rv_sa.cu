@@ -13,6 +13,8 @@
 //   2. key[i] = first k symbols of suffix i as a base-(sigma+1) number (order preserving); k is
 //      the shortest prefix that separates ~4n random k-mers, in a 32-bit key when that fits
 //      (DNA + '$': 12 symbols) else a 64-bit key; hand-written onesweep radix sort of (key, i).
+//      The keys are virtual: the histogram kernel and the first digit pass roll them from the
+//      text (TextKeySrc in rv_radix.cuh), no key array is written before the first scatter.
 //   3. Equal-key runs are "groups".  Similar genomes give groups of a few homologous positions
 //      whose suffixes agree for ~1/divergence characters.  Groups of <= SA_SMALL_G suffixes are
 //      ordered by ALL-PAIRS direct comparison: one thread per member walks its earlier group
@@ -51,32 +53,6 @@ __global__ void __launch_bounds__(256) sa_bytehist_kernel(const unsigned char *_
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&sh[T[i]], 1u);
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-
-// key[i] = sum_t code(T[i+t]) * base^(k-1-t)  (code 0 past the end); val[i] = i.
-// Each thread rolls the key over KG_PER consecutive positions.
-static const int KG_PER = 8;
-template <typename KeyT>
-__global__ void __launch_bounds__(256) sa_keygen_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 base, int k, KeyT top,
-                                                       KeyT *__restrict__ keys, u32 *__restrict__ vals) {
-    __shared__ unsigned short s_code[256];
-    s_code[threadIdx.x] = tab.code[threadIdx.x];
-    __syncthreads();
-    i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * KG_PER;
-    if (i0 >= n) return;
-    KeyT key = 0;
-    for (int t = 0; t < k; t++) {
-        i64 p = i0 + t;
-        key = key * (KeyT)base + (KeyT)(p < n ? s_code[T[p]] : 0);
-    }
-    for (int j = 0; j < KG_PER && i0 + j < n; j++) {
-        keys[i0 + j] = key;
-        vals[i0 + j] = (u32)(i0 + j);
-        i64 p = i0 + j;
-        KeyT first = (KeyT)s_code[T[p]];                       // symbol leaving the window
-        KeyT next = (KeyT)(p + k < n ? s_code[T[p + k]] : 0);  // symbol entering it
-        key = (key - first * top) * (KeyT)base + next;          // top = base^(k-1)
-    }
 }
 
 // ---- group geometry ---------------------------------------------------------------------
@@ -635,13 +611,18 @@ template <typename KeyT>
 static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, u32 base, int k,
                             int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, bool *large, PhaseTimes *pt) {
     KeyT *k0 = (KeyT *)B.k0, *k1 = (KeyT *)B.k1;
-    KeyT top = 1;
-    for (int t = 1; t < k; t++) top *= (KeyT)base;
-    i64 kg_threads = (n + KG_PER - 1) / KG_PER;
-    RV_LAUNCH((sa_keygen_kernel<KeyT>), (unsigned)((kg_threads + 255) / 256), 256, 0, st.s, dT, n, tab, base, k, top, k0, B.v0);
-    st.launches++;
+    // the (key, suffix) pairs are virtual: the histogram kernel and the first digit pass roll the k-mer keys
+    // straight from the text (TextKeySrc), so no key array is written before the first scatter
+    TextKeySrc src;
+    src.T = dT;
+    src.n = n;
+    src.base = base;
+    src.k = k;
+    src.top = 1;
+    for (int t = 1; t < k; t++) src.top *= (u64)base;
+    memcpy(src.code, tab.code, sizeof src.code);
     bool in0;
-    RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0));
+    RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0, &src));
     if (pt) pt->sa_sorted_items += n;
     KeyT *keys = in0 ? k0 : k1;
     u32 *sa = in0 ? B.v0 : B.v1;
