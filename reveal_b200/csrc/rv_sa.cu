@@ -248,11 +248,6 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     unsigned sha = 0, shb = 0;
     u32 lo_a = 0, lo_b = 0;
     const u32 n32 = (u32)n;
-    // A finished comparison parks its result here and the lane moves on; the results are booked (barrier
-    // bitmap, shared-memory atomics) when enough lanes hold one, so that path runs with many lanes at once.
-    bool pending = false;
-    u32 p_x = 0, p_len = 0;
-    int p_big = 0;
     for (;;) {
         // refill (warp-uniform condition)
         while (round < rounds && (qn - next) < 64u) {
@@ -285,18 +280,6 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             round++;
             __syncwarp();
         }
-        {
-            unsigned pend = __ballot_sync(FULL, pending);
-            // book when half the warp is waiting, or when nothing is left to compare
-            if (pend && ((unsigned)__popc(pend) >= 16u || (!__any_sync(FULL, active) && (int)(qn - next) <= 0 && round >= rounds))) {
-                if (pending) {
-                    u32 lcp = first_barrier(bar0, bar1, p_x, p_len);
-                    atomicAdd(&cnt[p_big >> 2], 1u << (8 * (p_big & 3)));
-                    atomicMax(&lcpv[p_big], (int)lcp);
-                    pending = false;
-                }
-            }
-        }
         unsigned idle = __ballot_sync(FULL, !active);
         if (!active) {
             u32 idx = next + (u32)__popc(idle & lanemask_lt());
@@ -324,8 +307,8 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             next += taken < avail ? taken : avail;
         }
         if (!__any_sync(FULL, active)) {
-            if (round >= rounds && !__any_sync(FULL, pending)) break;
-            continue;  // ring empty: refill if slots are left, else book the parked results
+            if (round >= rounds) break;
+            continue;  // ring empty but slots left: refill
         }
         if (active) {
             u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
@@ -369,17 +352,11 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                 }
             }
             if (done) {
-                // park: common prefix (cut at the first '$'/'N' when booked) and the slot of the larger suffix,
-                // which gains a smaller mate; a lane that still holds an older result books that one first
-                if (pending) {
-                    u32 lcp = first_barrier(bar0, bar1, p_x, p_len);
-                    atomicAdd(&cnt[p_big >> 2], 1u << (8 * (p_big & 3)));
-                    atomicMax(&lcpv[p_big], (int)lcp);
-                }
-                p_x = x;
-                p_len = (u32)skip + match;
-                p_big = x_less ? ty : tx;
-                pending = true;
+                // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
+                u32 lcp = first_barrier(bar0, bar1, x, (u32)skip + match);
+                int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
+                atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
+                atomicMax(&lcpv[big], (int)lcp);
                 active = false;
             }
         }
