@@ -119,12 +119,40 @@ __device__ __forceinline__ u32 first_barrier(const u32 *__restrict__ bar0, const
     }
 }
 
-// barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison, 16 bytes per step
+// Text as the comparison loops see it: SB bits per symbol in little-endian 32-bit words (symbol i of a word
+// in bits [SB*i, SB*i+SB)).  SB = 8: the raw bytes of T.  SB = 4: order-preserving dense codes packed two per
+// byte (sa_pack4_kernel) when the alphabet has at most 15 symbols -- DNA with '$', 'N' and a few IUPAC codes --
+// which halves the words a comparison has to fetch.  Zero padded past the end.
+template <int SB> struct Sym {
+    static const u32 LOG_SPW = SB == 8 ? 2u : 3u;   // log2(symbols per word)
+    static const u32 SPW = 1u << LOG_SPW;
+    static const u32 LOG_SB = SB == 8 ? 3u : 2u;
+    static const u32 STEP = 4u * SPW;                // symbols per comparison step (4 words per suffix)
+    static const u32 MASK = (1u << SB) - 1u;
+};
+
+__global__ void __launch_bounds__(256) sa_pack4_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ P, i64 words) {
+    __shared__ unsigned short s_code[256];
+    s_code[threadIdx.x] = tab.code[threadIdx.x];
+    __syncthreads();
+    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    u32 v = 0;
+    for (int j = 0; j < 8; j++) {
+        i64 i = w * 8 + j;
+        if (i < n) v |= ((u32)s_code[T[i]] & 15u) << (4 * j);
+    }
+    P[w] = v;
+}
+
+// barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison, 4 words per step
+template <int SB>
 __device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u32 p, u32 q, const u32 *__restrict__ bar0,
                                           const u32 *__restrict__ bar1) {
+    typedef Sym<SB> S;
     const u32 lenmin = n32 - (p > q ? p : q);
-    const u32 *pa = W + (p >> 2), *pb = W + (q >> 2);
-    const unsigned sha = (p & 3u) * 8u, shb = (q & 3u) * 8u;
+    const u32 *pa = W + (p >> S::LOG_SPW), *pb = W + (q >> S::LOG_SPW);
+    const unsigned sha = (p & (S::SPW - 1u)) * SB, shb = (q & (S::SPW - 1u)) * SB;
     u32 lo_a = *pa, lo_b = *pb;
     u32 h = 0, match = lenmin;
     while (h < lenmin) {
@@ -137,11 +165,11 @@ __device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u3
         if (d0 | d1 | d2 | d3) {
             u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
             u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-            u32 at = h + wsel * 4u + ((u32)(__ffs((int)dd) - 1) >> 3);
+            u32 at = h + wsel * S::SPW + ((u32)(__ffs((int)dd) - 1) >> S::LOG_SB);
             match = at < lenmin ? at : lenmin;
             break;
         }
-        h += 16u;
+        h += S::STEP;
         pa += 4;
         pb += 4;
         lo_a = a4;
@@ -165,9 +193,9 @@ static const int PR_QCAP = 512;                        // ring of work items per
 // smaller mate (-> its place inside the group) and the pair's common prefix (-> its LCP entry = the
 // largest over its smaller mates); both live in shared memory because a group never leaves its warp.
 // The warp then places its groups: SA, inverse SA and LCP.
-template <typename KeyT>
+template <typename KeyT, int SB>
 __global__ void __launch_bounds__(PR_THREADS, 10)
-sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const unsigned char *__restrict__ T,
+sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W,
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
                 int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start) {
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
@@ -177,7 +205,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     __shared__ unsigned short s_queue[PR_WARPS][PR_QCAP];
     __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];     // bit t: slot t starts a group
     __shared__ u32 s_def[PR_WARPS][PR_ROUNDS];          // bit t0: the group starting at t0 is deferred to stage 4
-    const u32 *__restrict__ W = (const u32 *)T;
+    typedef Sym<SB> S;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     u32 *ssa = s_sa[w];
     int *lcpv = s_lcp[w];
@@ -292,10 +320,10 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                 p = x + (u32)skip;
                 q = y + (u32)skip;
                 lenmin = n32 - (p > q ? p : q);
-                pa = W + (p >> 2);
-                pb = W + (q >> 2);
-                sha = (p & 3u) * 8u;
-                shb = (q & 3u) * 8u;
+                pa = W + (p >> S::LOG_SPW);
+                pb = W + (q >> S::LOG_SPW);
+                sha = (p & (S::SPW - 1u)) * SB;
+                shb = (q & (S::SPW - 1u)) * SB;
                 lo_a = *pa;
                 lo_b = *pb;
                 h = 0;
@@ -325,18 +353,18 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                 u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
                 u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
                 u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
-                u32 bsh = (u32)(__ffs((int)dd) - 1) & ~7u;  // bit offset of the first differing byte
-                u32 at = h + wsel * 4u + (bsh >> 3);        // counted from p / q
+                u32 bsh = (u32)(__ffs((int)dd) - 1) & ~(u32)(SB - 1);  // bit offset of the first differing symbol
+                u32 at = h + wsel * S::SPW + (bsh >> S::LOG_SB);       // counted from p / q
                 done = true;
                 if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
                     match = lenmin;
                     x_less = p > q;  // the shorter suffix (larger start) sorts first
                 } else {
                     match = at;
-                    x_less = ((va >> bsh) & 0xffu) < ((vb >> bsh) & 0xffu);
+                    x_less = ((va >> bsh) & S::MASK) < ((vb >> bsh) & S::MASK);
                 }
             } else {
-                h += 16u;
+                h += S::STEP;
                 pa += 4;
                 pb += 4;
                 lo_a = a4;
@@ -407,7 +435,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         if (f == 0 || !((head[f >> 5] >> (f & 31)) & 1u)) continue;
         u32 a = fin[f], b = fin[f - 1];
         if (a == 0xFFFFFFFFu || b == 0xFFFFFFFFu) continue;  // stage 4 will finish these (sa_lcp_need_kernel)
-        LCP[s + f] = direct_lcp(W, n32, a, b, bar0, bar1);
+        LCP[s + f] = direct_lcp<SB>(W, n32, a, b, bar0, bar1);
     }
 }
 
@@ -427,7 +455,7 @@ sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, con
     // yet may still hold anything, and is rewritten later
     u32 p = (u32)SA[j], q = (u32)SA[j - 1];
     if (p >= (u32)n || q >= (u32)n) return;
-    LCP[j] = direct_lcp((const u32 *)T, (u32)n, p, q, bar0, bar1);
+    LCP[j] = direct_lcp<8>((const u32 *)T, (u32)n, p, q, bar0, bar1);
 }
 
 // Stage 4: `need` marks the slots whose LCP entry the comparison stage did not
@@ -447,7 +475,7 @@ sa_lcp_need_kernel(const unsigned char *__restrict__ need, i64 n, const unsigned
                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
     i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || !need[j]) return;
-    LCP[j] = j == 0 ? 0 : direct_lcp((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
+    LCP[j] = j == 0 ? 0 : direct_lcp<8>((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
 }
 
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
@@ -594,7 +622,7 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + a / 64 + 8192 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + a / 64 + a / 2 + 8192 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
@@ -602,6 +630,7 @@ struct SaBuffers {
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
     unsigned char *deferred, *need;
     int *chunk_start;  // first slot of every warp chunk of sa_pairs_kernel
+    u32 *packed;       // 4-bit packed text, n/8 + 16 words
     u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
     void *rscratch;
 };
@@ -631,20 +660,21 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const unsigned blocks = (unsigned)((n + 255) / 256);
     RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((n + 1023) / 1024 + 1), 1024, 0, st.s, dT, n, B.bar, B.bar1);
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
-#ifndef RV_EMU
-    {   // shared memory is carved out of the same 228 KB as L1, and this kernel lives on L1 hits for its text gathers
-        static int carve_done = -2;
-        int want = -1;
-        if (const char *e = getenv("RV_PAIRS_CARVEOUT")) want = atoi(e);  // tuning hook: percent of the array used as shared memory
-        if (want != carve_done) {
-            if (want >= 0) cudaFuncSetAttribute(sa_pairs_kernel<KeyT>, cudaFuncAttributePreferredSharedMemoryCarveout, want);
-            carve_done = want;
-        }
+    // text for the comparisons: 4-bit packed codes when the alphabet allows (sigma <= 15), else the raw bytes
+    const bool packed = base <= 16 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
+    const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
+    if (packed) {
+        const i64 words = n / 8 + 16;
+        RV_LAUNCH(sa_pack4_kernel, (unsigned)((words + 255) / 256), 256, 0, st.s, dT, n, tab, B.packed, words);
+        st.launches++;
+        RV_TRY(prof_begin(st));
+        RV_LAUNCH((sa_pairs_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)B.packed, B.bar, B.bar1, k, dSA, dISA, dLCP,
+                  B.deferred, B.small + 257, B.chunk_start);
+    } else {
+        RV_TRY(prof_begin(st));
+        RV_LAUNCH((sa_pairs_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)dT, B.bar, B.bar1, k, dSA, dISA, dLCP,
+                  B.deferred, B.small + 257, B.chunk_start);
     }
-#endif
-    RV_TRY(prof_begin(st));
-    RV_LAUNCH((sa_pairs_kernel<KeyT>), (unsigned)((n + pr_per_block - 1) / pr_per_block), PR_THREADS, 0, st.s, keys, sa, n, dT, B.bar, B.bar1, k,
-              dSA, dISA, dLCP, B.deferred, B.small + 257, B.chunk_start);
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 2;
     u32 lg = 0;
@@ -745,9 +775,10 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.deferred = ws.take<unsigned char>(n);
     B.need = ws.take<unsigned char>(n);
     B.chunk_start = ws.take<int>(n / PR_CHUNK + 2 * PR_WARPS + 8);
+    B.packed = ws.take<u32>(n / 8 + 16);
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
-    if (!B.deferred || !B.need || !B.chunk_start || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    if (!B.deferred || !B.need || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;

@@ -64,3 +64,12 @@ def test_emu_both_key_widths(emu_lib, monkeypatch, bits):
     check_against_oracle(emu_lib, T, nsep, 3, minl=6)
     check_against_golden(emu_lib, load_golden("tandem"))
     check_against_golden(emu_lib, load_golden("all_A"))
+
+
+def test_emu_byte_comparison_path(emu_lib, monkeypatch):
+    """RV_SA_NO_PACK forces the byte-wise comparison loops that large alphabets use."""
+    monkeypatch.setenv("RV_SA_NO_PACK", "1")
+    rng = np.random.default_rng(33)
+    T, nsep, _ = P.assemble(random_related(rng, 3, 2500, 4))
+    check_against_oracle(emu_lib, T, nsep, 3, minl=6)
+    check_against_golden(emu_lib, load_golden("with_N_d2"))

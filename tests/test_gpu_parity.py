@@ -171,3 +171,11 @@ def test_cuda_long_identical_and_repeats(cuda_lib):
     s1 = s0[:7000] + b"G" + s0[7001:20000] + rep * 3 + s0[20000:]
     T, nsep, _ = P.assemble([[s0], [s1]])
     check_against_oracle(cuda_lib, T, nsep, 2, minl=8)
+
+
+def test_cuda_byte_comparison_path(cuda_lib, monkeypatch):
+    """RV_SA_NO_PACK forces the byte-wise comparison loops that large alphabets use."""
+    monkeypatch.setenv("RV_SA_NO_PACK", "1")
+    T, nsep, ns = synth.workload(3, 300000, seed=8)
+    check_against_oracle(cuda_lib, T, nsep, ns, minl=20)
+    check_against_golden(cuda_lib, load_golden("with_N_d2"))
