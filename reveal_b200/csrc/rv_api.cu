@@ -112,6 +112,16 @@ int rv_index_create(rv_index **out, void *stream) {
         }
         h->own_stream = true;
     }
+    {
+        void *pp = nullptr;
+        cudaError_t e = cudaMallocHost(&pp, 2048);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocHost failed: %s", cudaGetErrorString(e));
+            delete h;
+            return RV_ERR_CUDA;
+        }
+        h->st.pinned = (u32 *)pp;
+    }
     for (int i = 0; i < 6; i++) {
         cudaError_t e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) {
@@ -135,6 +145,7 @@ void rv_index_free(rv_index *h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     prof_collect(h->st);
     for (cudaEvent_t e : h->st.free_events) cudaEventDestroy(e);
+    if (h->st.pinned) cudaFreeHost(h->st.pinned);
     if (h->own_stream) cudaStreamDestroy(h->st.s);
     delete h;
 }
@@ -185,6 +196,7 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     if (nsamples > 1) RV_CUDA(cudaMemcpyAsync(h->dNsep, h->nsep.data(), (size_t)(nsamples - 1) * 8, cudaMemcpyHostToDevice, st.s));
     RV_CUDA(cudaEventRecord(h->ev[1], st.s));
     if (rc) RV_TRY(revcomp_suffix(st, h->dT, h->nsep[0], n));
+    if (nsamples > 2) RV_TRY(so_build(st, n, h->dNsep, nsamples, h->dSO));  // independent of the suffix array
     RV_CUDA(cudaEventRecord(h->ev[2], st.s));
     bool lcp_done = false;
     if (hSA) {  // suffix array (and maybe LCP) from a cache file (interface.c:224-231, 255-262)
@@ -207,13 +219,12 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
     RV_CUDA(cudaEventRecord(h->ev[3], st.s));
     if (!lcp_done) RV_TRY(lcp_build(st, h->dT, n, h->dSA, h->dISA, h->dLCP));
     RV_CUDA(cudaEventRecord(h->ev[4], st.s));
-    if (nsamples > 2) RV_TRY(so_build(st, n, h->dNsep, nsamples, h->dSO));
     RV_CUDA(cudaEventRecord(h->ev[5], st.s));
     RV_CUDA(cudaStreamSynchronize(st.s));
     RV_KCHECK();
     rv_times &t = h->times;
     RV_CUDA(cudaEventElapsedTime(&t.h2d_ms, h->ev[0], h->ev[1]));
-    RV_CUDA(cudaEventElapsedTime(&t.pack_ms, h->ev[1], h->ev[2]));
+    RV_CUDA(cudaEventElapsedTime(&t.pack_ms, h->ev[1], h->ev[2]));  // revcomp (+ SO fill)
     RV_CUDA(cudaEventElapsedTime(&t.sa_ms, h->ev[2], h->ev[3]));
     RV_CUDA(cudaEventElapsedTime(&t.lcp_ms, h->ev[3], h->ev[4]));
     RV_CUDA(cudaEventElapsedTime(&t.so_ms, h->ev[4], h->ev[5]));

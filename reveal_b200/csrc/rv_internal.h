@@ -60,8 +60,17 @@ struct ProfRec {
     long long launches, bytes;
 };
 
+// alphabet of the last text built on a handle: lets the next build start without waiting for its histogram
+struct AlphaCache {
+    bool valid = false;
+    unsigned short code[256];
+    int sigma = 0, sigma_eff = 0;
+};
+
 struct Stream {
     cudaStream_t s = 0;
+    u32 *pinned = nullptr;      // 2 KB of pinned host memory for small asynchronous read-backs
+    AlphaCache alpha;
     int launches = 0;           // kernels launched by this library on the stream since the last reset
     long long launches_total = 0;
     // optional per-kernel profile: event pairs recorded around runs of one kernel, resolved lazily
@@ -124,7 +133,8 @@ size_t sa_workspace_bytes(i64 n);
 // Builds SA and ISA (=final ranks) of the byte string dT[0..n) into dSA/dISA (int32).  dT must be 8-byte
 // aligned and readable (zero padded) up to n+16.  When the comparison stage could place every suffix the
 // barrier-aware LCP array is complete as well (*lcp_done); otherwise the caller runs lcp_build.
-int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt);
+int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt,
+             bool fresh_alphabet = false);
 
 int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
 int isa_build(Stream &st, i64 n, const int *dSA, int *dISA, u32 *d_bad);

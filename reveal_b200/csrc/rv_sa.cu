@@ -638,7 +638,7 @@ struct SaBuffers {
 // stages 2-3 for one key width; on return *keys_out / *sa_out hold the sorted keys and suffixes
 template <typename KeyT>
 static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, u32 base, int k,
-                            int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, bool *large, PhaseTimes *pt) {
+                            int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, PhaseTimes *pt) {
     KeyT *k0 = (KeyT *)B.k0, *k1 = (KeyT *)B.k1;
     // the (key, suffix) pairs are virtual: the histogram kernel and the first digit pass roll the k-mer keys
     // straight from the text (TextKeySrc), so no key array is written before the first scatter
@@ -677,16 +677,12 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     }
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 2;
-    u32 lg = 0;
-    RV_CUDA(cudaMemcpyAsync(&lg, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
-    {   // enqueue the chunk-head LCP pass before waiting for the flag: when stage 4 turns out to be needed it
+    {   // the chunk-head LCP pass is enqueued before anyone knows whether stage 4 is needed: when it is, stage 4
         // rewrites these few entries anyway (sa_lcp_need_kernel / Kasai)
         const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
         RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP);
         st.launches++;
     }
-    RV_CUDA(cudaStreamSynchronize(st.s));
-    *large = lg != 0;
     RV_KCHECK();
     *keys_out = keys;
     *sa_out = sa;
@@ -751,13 +747,15 @@ static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *ke
     return RV_OK;
 }
 
-int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt) {
+int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt,
+             bool fresh_alphabet) {
     *lcp_done = false;
     if (n <= 0) return RV_OK;
     if (n >= ((i64)1 << 30)) {
         set_error("sa_build: n=%lld not supported yet (limit 2^30-1)", (long long)n);
         return RV_ERR_UNSUPPORTED;
     }
+    const size_t ws_mark = ws.off;
     SaBuffers B;
     B.k0 = ws.take<u64>(n);
     B.k1 = ws.take<u64>(n);
@@ -784,8 +782,10 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         return RV_ERR_NOMEM;
     }
 
-    // 1. alphabet
-    u32 hist[256];
+    // 1. alphabet.  The histogram always runs, but when the handle has built a text before, the build starts at once
+    //    with that text's code table and the histogram is only checked at the single synchronisation point below
+    //    (a symbol the table lacks -> rebuild with the fresh table).  The first build on a handle waits for it.
+    u32 *hist = st.pinned;  // [0..255] counts, [256] stage-4 flag
     RV_CUDA(cudaMemsetAsync(B.small, 0, 512 * 4, st.s));
     {
         i64 blocks = (n + 256 * 64 - 1) / (256 * 64);
@@ -794,15 +794,26 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         st.launches++;
     }
     RV_CUDA(cudaMemcpyAsync(hist, B.small, 256 * 4, cudaMemcpyDeviceToHost, st.s));
-    RV_CUDA(cudaStreamSynchronize(st.s));
+    const bool speculative = st.alpha.valid && !fresh_alphabet;
     CodeTable tab;
-    memset(&tab, 0, sizeof tab);
     int sigma = 0, sigma_eff = 0;
-    for (int c = 0; c < 256; c++)
-        if (hist[c]) {
-            tab.code[c] = (unsigned short)(++sigma);
-            if ((u64)hist[c] * 32 >= (u64)n) sigma_eff++;  // symbols that carry the entropy (ACGT, not '$'/N/IUPAC)
-        }
+    if (speculative) {
+        memcpy(tab.code, st.alpha.code, sizeof tab.code);
+        sigma = st.alpha.sigma;
+        sigma_eff = st.alpha.sigma_eff;
+    } else {
+        RV_CUDA(cudaStreamSynchronize(st.s));
+        memset(&tab, 0, sizeof tab);
+        for (int c = 0; c < 256; c++)
+            if (hist[c]) {
+                tab.code[c] = (unsigned short)(++sigma);
+                if ((u64)hist[c] * 32 >= (u64)n) sigma_eff++;  // symbols that carry the entropy (ACGT, not '$'/N/IUPAC)
+            }
+        st.alpha.valid = true;
+        memcpy(st.alpha.code, tab.code, sizeof tab.code);
+        st.alpha.sigma = sigma;
+        st.alpha.sigma_eff = sigma_eff;
+    }
     if (sigma_eff < 2) sigma_eff = 2;
     const u32 base = (u32)sigma + 1;  // digits 0..sigma
     // shortest k with sigma_eff^k >= 4n: random k-mers are then mostly unique
@@ -831,28 +842,41 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     for (int t = 0; t < k; t++) maxkey *= base;  // base^k fits by construction (k64 may give exactly 2^64 -> wraps to 0)
     const int key_bits = use32 ? bits_for(maxkey - 1) : (maxkey == 0 ? 64 : bits_for(maxkey - 1));
 
-    bool large = false;
     u32 *sa = nullptr, *sa_free = nullptr;
     i64 first_active = 0;
     const unsigned blocks = (unsigned)((n + 255) / 256);
+    u32 *keys32 = nullptr;
+    u64 *keys64 = nullptr;
     if (use32) {
-        u32 *keys = nullptr;
-        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
-        if (large) {
-            RV_LAUNCH((sa_need_kernel<u32>), blocks, 256, 0, st.s, keys, n, B.deferred, B.need);
+        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys32, &sa, &sa_free, pt));
+    } else {
+        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys64, &sa, &sa_free, pt));
+    }
+    // ---- the one synchronisation point of a build: is stage 4 needed, and (speculative start) was the alphabet right ----
+    RV_CUDA(cudaMemcpyAsync(hist + 256, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    if (speculative) {
+        bool ok = true;
+        for (int c = 0; c < 256; c++)
+            if (hist[c] && !tab.code[c]) ok = false;  // a symbol the cached table has no code for
+        if (!ok) {
+            ws.off = ws_mark;  // give the workspace back and start over with this text's own alphabet
+            return sa_build(st, ws, dT, n, dSA, dISA, dLCP, lcp_done, pt, true);
+        }
+    }
+    bool large = hist[256] != 0;
+    if (large) {
+        if (use32) {
+            RV_LAUNCH((sa_need_kernel<u32>), blocks, 256, 0, st.s, keys32, n, B.deferred, B.need);
             st.launches++;
             // round 0 reads the u32 keys that live in the first half of k0 or k1; later rounds reuse both
             // buffers as u64 keys, so move the u32 keys out of the way (posB is free until round 2)
-            RV_CUDA(cudaMemcpyAsync(B.posB, keys, (size_t)n * 4, cudaMemcpyDeviceToDevice, st.s));
+            RV_CUDA(cudaMemcpyAsync(B.posB, keys32, (size_t)n * 4, cudaMemcpyDeviceToDevice, st.s));
             RV_TRY(doubling<u32>(st, B, n, k, B.posB, sa, sa_free, dSA, dISA, &first_active, pt));
-        }
-    } else {
-        u64 *keys = nullptr;
-        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys, &sa, &sa_free, &large, pt));
-        if (large) {
-            RV_LAUNCH((sa_need_kernel<u64>), blocks, 256, 0, st.s, keys, n, B.deferred, B.need);
+        } else {
+            RV_LAUNCH((sa_need_kernel<u64>), blocks, 256, 0, st.s, keys64, n, B.deferred, B.need);
             st.launches++;
-            RV_TRY(doubling<u64>(st, B, n, k, keys, sa, sa_free, dSA, dISA, &first_active, pt));
+            RV_TRY(doubling<u64>(st, B, n, k, keys64, sa, sa_free, dSA, dISA, &first_active, pt));
         }
     }
     if (large && first_active <= n / 16) {

@@ -7,7 +7,7 @@ import pytest
 
 import oracle.port as P
 from conftest import golden_names, load_golden
-from util import check_against_golden, check_against_oracle, random_related
+from util import check_handle_reuse, check_against_golden, check_against_oracle, random_related
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -73,3 +73,7 @@ def test_emu_byte_comparison_path(emu_lib, monkeypatch):
     T, nsep, _ = P.assemble(random_related(rng, 3, 2500, 4))
     check_against_oracle(emu_lib, T, nsep, 3, minl=6)
     check_against_golden(emu_lib, load_golden("with_N_d2"))
+
+
+def test_emu_handle_reuse_alphabet_cache(emu_lib):
+    check_handle_reuse(emu_lib)

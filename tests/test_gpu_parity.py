@@ -9,7 +9,7 @@ import pytest
 import oracle.port as P
 from conftest import golden_names, load_golden
 from reveal_b200 import synth
-from util import NativeIndex, assert_same, check_against_golden, check_against_oracle, random_related
+from util import check_handle_reuse, NativeIndex, assert_same, check_against_golden, check_against_oracle, random_related
 
 pytestmark = pytest.mark.gpu
 
@@ -179,3 +179,7 @@ def test_cuda_byte_comparison_path(cuda_lib, monkeypatch):
     T, nsep, ns = synth.workload(3, 300000, seed=8)
     check_against_oracle(cuda_lib, T, nsep, ns, minl=20)
     check_against_golden(cuda_lib, load_golden("with_N_d2"))
+
+
+def test_cuda_handle_reuse_alphabet_cache(cuda_lib):
+    check_handle_reuse(cuda_lib)

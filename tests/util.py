@@ -20,6 +20,15 @@ class NativeIndex:
         ns = np.asarray(nsep, dtype=np.int64)
         _native.check(L, L.rv_build(self.h, self.T.ctypes.data, self.n, ns.ctypes.data if len(ns) else None, self.nsamples, int(rc)))
 
+    def rebuild(self, T, nsep, nsamples, rc=0):
+        """Another build on the same handle (workspace and alphabet cache are reused)."""
+        L = self.L
+        self.T = np.ascontiguousarray(T, dtype=np.uint8)
+        self.n = len(self.T)
+        self.nsamples = int(nsamples)
+        ns = np.asarray(nsep, dtype=np.int64)
+        _native.check(L, L.rv_build(self.h, self.T.ctypes.data, self.n, ns.ctypes.data if len(ns) else None, self.nsamples, int(rc)))
+
     def close(self):
         if self.h is not None:
             self.L.rv_index_free(self.h)
@@ -130,3 +139,28 @@ def random_related(rng, nsamples, length, sigma=4, snp=0.02, alphabet=b"ACGT"):
         g[m] = rng.integers(0, sigma, size=int(m.sum()))
         out.append([al[g].tobytes()])
     return out
+
+
+def check_handle_reuse(L):
+    """Several builds on ONE handle: the second build starts speculatively with the first text's alphabet; a text
+    with a symbol that alphabet lacks must be rebuilt, a text with fewer symbols must not be disturbed."""
+    import oracle.port as P
+    rng = np.random.default_rng(5)
+    texts = [random_related(rng, 2, 3000, 4),                                # A C G T $
+             random_related(rng, 2, 2500, 6, alphabet=b"ACGTNR"),             # + N R : superset -> redo
+             random_related(rng, 3, 2000, 2, alphabet=b"AC"),                 # subset
+             random_related(rng, 2, 2200, 16, alphabet=b"ACGTNRYKMSWBDHVn")]  # 17 symbols: byte comparison path
+    idx = None
+    for samples in texts:
+        T, nsep, _ = P.assemble(samples)
+        ns = len(samples)
+        if idx is None:
+            idx = NativeIndex(L, T, nsep, ns)
+        else:
+            idx.rebuild(T, nsep, ns)
+        o = P.Index(T, nsep, ns)
+        assert_same(idx.arr("SA"), o.SA, "SA")
+        assert_same(idx.arr("SAi"), o.SAi, "SAi")
+        assert_same(idx.arr("LCP"), o.LCP, "LCP")
+        assert_same(idx.mums(5, 1), o.getmums(5, rem=True), "getmums")
+    idx.close()
