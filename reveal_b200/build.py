@@ -13,7 +13,8 @@ OUT = os.path.join(_HERE, "libreveal_b200.so")
 OBJ = os.path.join(_HERE, "csrc", "build")
 UNITS = ["rv_api", "rv_sa", "rv_lcp", "rv_sweep", "rv_split"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+EXTRA = os.environ.get("RV_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 

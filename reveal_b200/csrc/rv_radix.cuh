@@ -15,7 +15,10 @@ namespace rv {
 
 static const int RS_THREADS = 256;
 static const int RS_WARPS = RS_THREADS / 32;
-static const int RS_IPT = 16;
+#ifndef RV_RS_IPT
+#define RV_RS_IPT 16
+#endif
+static const int RS_IPT = RV_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
 static const int RS_BINS = 256;
 static const int RS_MAXPASS = 8;
@@ -145,8 +148,11 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict_
     gbase[blockIdx.x * RS_BINS + threadIdx.x] = inc - c;
 }
 
+#ifndef RV_RS_MINBLOCKS
+#define RV_RS_MINBLOCKS 4
+#endif
 template <typename KeyT, bool HAS_VAL, bool FROM_TEXT>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, RV_RS_MINBLOCKS)
 rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin, u32 *__restrict__ vout,
                i64 n, int shift, u32 mask, int dbits, const u32 *__restrict__ gbase, u32 *status, u32 *ticket, TextKeySrc src) {
     __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> running per-warp offsets inside the bucket
