@@ -43,3 +43,60 @@ def gather_rows(rows, dst=0, group=None):
     if rank != dst:
         return None
     return [bufs[r][:counts[r]] for r in range(world)]
+
+
+def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
+    """Index build + MUM sweep of independent units, sharded over the ranks of `group`.
+
+    units: list of (T uint8 array, nsep int64 array, nsamples) -- e.g. the sub-intervals of a recursion frontier
+    rebuilt as independent indexes, the jobs of `--order=sequential --chunksize`, or a forward / reverse-complement
+    pair.  Every rank builds the units `partition` assigns to it on its own GPU; the MUM records are
+    gathered to rank 0 (the only collective).  Returns on rank 0 a list with one int64 array per unit -- pair rows
+    (l, a, b) for two samples, multi-MUM header rows (l, n, first) otherwise -- and None on the other ranks.
+    `lib` is the C-ABI library object (default: the CUDA library; tests inject the emulated one)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _native
+    L = lib if lib is not None else _native.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = partition([len(u[0]) for u in units], world)[rank]
+    h = ctypes.c_void_p()
+    _native.check(L, L.rv_index_create(ctypes.byref(h), None))
+    blocks = []
+    try:
+        for uid in mine:
+            T, nsep, ns = units[uid]
+            T = np.ascontiguousarray(T, dtype=np.uint8)
+            nsep = np.ascontiguousarray(nsep, dtype=np.int64)
+            _native.check(L, L.rv_build(h, T.ctypes.data, len(T), nsep.ctypes.data if len(nsep) else None, int(ns), 0))
+            if ns == 2:
+                c = ctypes.c_int64()
+                _native.check(L, L.rv_mums_pair_count(h, int(minl), 1, ctypes.byref(c)))
+                rows = np.empty((c.value, 3), dtype=np.int64)
+                _native.check(L, L.rv_mums_pair_fetch(h, rows.ctypes.data, c.value))
+            else:
+                nr, nm = ctypes.c_int64(), ctypes.c_int64()
+                _native.check(L, L.rv_mums_multi_count(h, int(minl), int(minn), ctypes.byref(nr), ctypes.byref(nm)))
+                rows = np.empty((nr.value, 3), dtype=np.int64)
+                mem = np.empty((nm.value, 2), dtype=np.int64)
+                _native.check(L, L.rv_mums_multi_fetch(h, rows.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+            # tag every row with its unit so that one gather carries all units of the rank
+            tagged = np.concatenate([np.full((len(rows), 1), uid, dtype=np.int64), rows], axis=1)
+            blocks.append(tagged)
+    finally:
+        L.rv_index_free(h)
+    local = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, 4), dtype=np.int64)
+    t = torch.from_numpy(local)
+    if device is not None:
+        t = t.to(device)
+    if world == 1:
+        parts = [t]
+    else:
+        parts = gather_rows(t, dst=0, group=group)
+        if rank != 0:
+            return None
+    allrows = torch.cat(parts, dim=0).cpu().numpy()
+    return [allrows[allrows[:, 0] == uid][:, 1:] for uid in range(len(units))]

@@ -183,3 +183,26 @@ def test_cuda_byte_comparison_path(cuda_lib, monkeypatch):
 
 def test_cuda_handle_reuse_alphabet_cache(cuda_lib):
     check_handle_reuse(cuda_lib)
+
+
+def test_cuda_anchor_units_single_rank(cuda_lib):
+    """shard.anchor_units on one GPU (no process group): every unit's rows equal the oracle's."""
+    from reveal_b200 import shard
+    rng = np.random.default_rng(12)
+    units = []
+    for ns, length in ((2, 30000), (3, 12000), (2, 5000)):
+        T, nsep, _ = P.assemble(random_related(rng, ns, length, 4))
+        units.append((T, np.asarray(nsep, dtype=np.int64), ns))
+    got = shard.anchor_units(units, minl=10, lib=cuda_lib)
+    for (T, nsep, ns), rows in zip(units, got):
+        o = P.Index(T, nsep, ns)
+        want = o.getmums(10, rem=True) if ns == 2 else o.getmultimums(10, 2)[0]
+        assert_same(rows, want, "unit rows")
+
+
+def test_cuda_full_size_c4_properties(cuda_lib):
+    """BASELINE configs[3] size (2 x 100 Mbp, n = 2e8, 64-bit k-mer keys): size-independent properties only."""
+    T, nsep, ns = synth.workload(2, 100_000_000, seed=1)
+    with NativeIndex(cuda_lib, T, nsep, ns) as idx:
+        mums = _properties(T, nsep, ns, idx, 20)
+        assert len(mums) > 500000

@@ -53,3 +53,51 @@ def test_gather_rows_world2_gloo():
     assert gathered[1] == []
     all_units = sorted(u for r in res for u in r[0])
     assert all_units == [0, 1, 2, 3]
+
+
+def _anchor_worker(rank, world, port, q, lib_path):
+    import numpy as np
+    import oracle.port as P
+    from reveal_b200 import _native
+    from util import random_related
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = _native.bind(lib_path)  # the emulated kernels stand in for the GPUs of the box
+    rng = np.random.default_rng(42)  # same units on every rank
+    units = []
+    for length in (1800, 600, 1200, 900, 300):
+        T, nsep, _ = P.assemble(random_related(rng, 2, length, 4))
+        units.append((T, np.asarray(nsep, dtype=np.int64), 2))
+    got = shard.anchor_units(units, minl=8, lib=L)
+    if rank == 0:
+        ok = True
+        for (T, nsep, ns), rows in zip(units, got):
+            o = P.Index(T, nsep, ns)
+            ok = ok and np.array_equal(rows, o.getmums(8, rem=True))
+        q.put(("rank0", ok, [len(r) for r in got]))
+    else:
+        q.put(("rank%d" % rank, got is None, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_anchor_units_sharded_world2_gloo(emu_lib):
+    """Independent index builds sharded over two ranks (emulated kernels), MUM rows gathered to rank 0 and
+    compared with the oracle unit by unit."""
+    import sys
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "_build", "libreveal_emu.so")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_anchor_worker, args=(r, 2, port, q, lib_path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for name, ok, _ in res:
+        assert ok, name
+    counts = [r[2] for r in res if r[2] is not None][0]
+    assert len(counts) == 5 and sum(counts) > 0
