@@ -45,6 +45,47 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 __device__ __forceinline__ u32 ld_volatile(const u32 *p) { return *(const volatile u32 *)p; }
 __device__ __forceinline__ void st_volatile(u32 *p, u32 v) { *(volatile u32 *)p = v; }
 
+// ---- TMA: 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+: cp.async.bulk / UBLKCP) ----------
+// dst, src 16-byte aligned, bytes a multiple of 16.  One thread arms the barrier with the byte count and issues
+// the copies; every thread of the block then waits on the barrier's phase.
+#ifdef RV_EMU
+// emulation: word = [phase bit 63 | pending bytes]; the copy happens at issue, waiting threads yield until the phase flips
+__device__ __forceinline__ void mbar_init(u64 *bar, u32) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { *bar += bytes; }
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    memcpy(dst, src, bytes);
+    *bar -= bytes;
+    if ((*bar & 0xffffffffull) == 0) *bar ^= 1ull << 63;
+    emu::S().progress++;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    while (((*(volatile u64 *)bar) >> 63) == (u64)parity) rv_emu_spin();
+}
+#else
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+#endif
+
 // ---- warp / block scan helpers (warp-shuffle based) ---------------------------
 template <class T> __device__ __forceinline__ T warp_incl_sum(T v) {
 #pragma unroll

@@ -13,6 +13,9 @@
 
 namespace rv {
 
+#ifndef RV_TMA_ON
+#define RV_TMA_ON 1
+#endif
 static const int RS_THREADS = 256;
 static const int RS_WARPS = RS_THREADS / 32;
 #ifndef RV_RS_IPT
@@ -160,17 +163,29 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
     __shared__ u32 s_off[RS_BINS];               // global slot of a bucket's first item minus s_start (mod 2^32)
     __shared__ u32 s_scan[33];
     __shared__ u32 s_tile;
+    __shared__ __align__(8) u64 s_bar;  // mbarrier of the tile's TMA loads
     RV_DYN_SMEM(unsigned char, smem);
     KeyT *s_keys = (KeyT *)smem;
     u32 *s_vals = (u32 *)(smem + (size_t)RS_TILE * sizeof(KeyT));
 
     const unsigned tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid == 0) {
+        s_tile = atomicAdd(ticket, 1u);
+        mbar_init(&s_bar, 1);
+    }
     for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
     const i64 base = (i64)tile * RS_TILE;
     const int cnt = (int)((n - base) < (i64)RS_TILE ? (n - base) : (i64)RS_TILE);
+    // full tiles of real pairs arrive by TMA: two bulk copies (keys, values) land in the staging area in input
+    // order, the threads pick their striped items out of shared memory instead of issuing 32 global loads each
+    const bool by_tma = !FROM_TEXT && cnt == RS_TILE && RV_TMA_ON;
+    if (by_tma && tid == 0) {
+        mbar_expect_tx(&s_bar, (u32)(RS_TILE * (sizeof(KeyT) + (HAS_VAL ? 4 : 0))));
+        tma_load_1d(s_keys, kin + base, (u32)(RS_TILE * sizeof(KeyT)), &s_bar);
+        if (HAS_VAL) tma_load_1d(s_vals, vin + base, (u32)(RS_TILE * 4), &s_bar);
+    }
 
     // ---- load (warp-striped: a warp owns 32*IPT consecutive pairs) + early per-warp bucket counts ----
     KeyT key[RS_IPT];
@@ -199,6 +214,11 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
             key[k] = idx < cnt ? s_keys[idx] : (KeyT)0;
         }
         __syncthreads();  // s_keys is reused as the bucket-ordered staging area below
+    } else if (by_tma) {
+        mbar_wait(&s_bar, 0);
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) key[k] = s_keys[wbase + k * 32 + (int)l];
+        // (the __syncthreads after the early counts separates these reads from the bucket-ordered staging writes)
     } else {
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
@@ -262,8 +282,9 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             int idx = wbase + k * 32 + (int)l;
-            val[k] = FROM_TEXT ? (u32)(base + idx) : (idx < cnt ? vin[base + idx] : 0u);
+            val[k] = FROM_TEXT ? (u32)(base + idx) : (by_tma ? s_vals[idx] : (idx < cnt ? vin[base + idx] : 0u));
         }
+        if (by_tma) __syncthreads();  // every thread has its values out of the input-ordered area
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             int idx = wbase + k * 32 + (int)l;
