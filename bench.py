@@ -191,16 +191,21 @@ def run_ours(args, rank, world, local_rank):
             _native.check(L, L.rv_mums_multi_count(h, MINL, MINN, ctypes.byref(cnt), ctypes.byref(nmem)))
         return cnt.value
 
+    gatherer = {}
+
     def gather_results():
-        """N > 1: MUM records of every rank to rank 0 over NCCL (the only collective on the path)."""
+        """N > 1: MUM records of every rank to rank 0 over NCCL (the only collective on the path): one gather of
+        fixed-capacity blocks per step, no host synchronisation (reveal_b200.shard.FixedGather)."""
         if world == 1:
             return
         from reveal_b200 import shard
         p, k = ctypes.c_void_p(), ctypes.c_int64()
         _native.check(L, L.rv_result_device(h, ctypes.byref(p), ctypes.byref(k), None, None))
         with torch.cuda.stream(stream):  # same stream as the sweep kernels that produced the rows
+            if "g" not in gatherer:
+                gatherer["g"] = shard.FixedGather(max(4096, 2 * k.value), 3, dev)
             mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
-            shard.gather_rows(mine, dst=0)
+            gatherer["g"].gather(mine)
 
     def step_resident():
         _native.check(L, L.rv_build_device(h, ctypes.c_void_p(dT.data_ptr()), n, nsep.ctypes.data, ns, 0))
@@ -246,6 +251,10 @@ def run_ours(args, rank, world, local_rank):
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
+    if world > 1:
+        parts = gatherer["g"].check()  # rank 0: every rank's rows of the last step arrived (raises on overflow)
+        if rank == 0:
+            assert len(parts) == world and all(len(x) > 0 for x in parts)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     prof = _native.KernelProfile()
     _native.check(L, L.rv_get_profile(h, ctypes.byref(prof)))

@@ -101,3 +101,42 @@ def test_anchor_units_sharded_world2_gloo(emu_lib):
         assert ok, name
     counts = [r[2] for r in res if r[2] is not None][0]
     assert len(counts) == 5 and sum(counts) > 0
+
+
+def _fixed_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = shard.FixedGather(8, 3, torch.device("cpu"))
+    for step in range(3):
+        k = 3 + rank * 2 + step
+        rows = torch.arange(k * 3, dtype=torch.int64).reshape(k, 3) + 100 * rank
+        g.gather(rows)
+    parts = g.check()
+    parts = None if parts is None else [p.tolist() for p in parts]  # views into the receive buffers: copy before the next gather
+    overflow = False
+    g.gather(torch.zeros((20, 3), dtype=torch.int64))  # more rows than the capacity
+    try:
+        g.check()
+    except OverflowError:
+        overflow = True
+    q.put((rank, parts, overflow))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fixed_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 100
+    procs = [ctx.Process(target=_fixed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r for r in [q.get(timeout=120) for _ in range(2)]}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1][1] is None
+    parts = res[0][1]
+    assert len(parts[0]) == 5 and len(parts[1]) == 7 and parts[1][0] == [100, 101, 102]
+    assert res[0][2] is True
