@@ -205,12 +205,21 @@ def run_ours(args, rank, world, local_rank):
             if "g" not in gatherer:
                 gatherer["g"] = shard.FixedGather(max(4096, 2 * k.value), 3, dev)
             mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
-            gatherer["g"].gather(mine)
+            g = gatherer["g"]
+            g.gather(mine)        # enqueued on the communication stream: overlaps the next step's index build
+            g.wait_previous()     # ... but a step does not end before the gather of the step before it has landed
+
+    gather_evs = []
 
     def step_resident():
         _native.check(L, L.rv_build_device(h, ctypes.c_void_p(dT.data_ptr()), n, nsep.ctypes.data, ns, 0))
         k = sweep()
-        gather_results()
+        if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            gather_results()
+            g1.record(stream)
+            gather_evs.append((g0, g1))
         return k
 
     def step_e2e():
@@ -248,6 +257,9 @@ def run_ours(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         nm = step_resident()
+        if world > 1 and _ == args.steps - 1:
+            with torch.cuda.stream(stream):
+                gatherer["g"].wait_all()  # the last step's gather is inside the timed region
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
@@ -256,6 +268,7 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             assert len(parts) == world and all(len(x) > 0 for x in parts)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_evs[-args.steps:]) / args.steps if gather_evs else 0.0
     prof = _native.KernelProfile()
     _native.check(L, L.rv_get_profile(h, ctypes.byref(prof)))
     times = _native.Times()
@@ -305,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "flushed between timed steps (256 MiB write)", "sharding": "independent index build per rank; NCCL gather of MUM records" if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n + 8 * len(nsep)), "d2h_bytes_per_step": int(d2h + 32),
                         "ms_per_step": e2e_ms_max / args.steps},
-                "gpu_launches": launches,
+                "gpu_launches": launches, "gather_ms_per_step": gather_ms,
                 # the dominant kernel = largest measured share of the step; algorithmic bytes per slot: include/reveal_b200.h, DESIGN.md
                 "roofline": {"bound": "hbm", "kernel": top.get("kernel"), "achieved": top.get("achieved"), "peak": peak, "unit": "GB/s",
                              "frac": top.get("frac"), "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,

@@ -48,33 +48,75 @@ def gather_rows(rows, dst=0, group=None):
 class FixedGather(object):
     """Variable-length gather in ONE collective and without a host synchronisation: every rank sends a block of
     fixed capacity whose first row carries its row count; `dst` checks the counts afterwards (`check`).  For
-    steady pipelines (same-sized units step after step) this replaces the count all_gather + padded gather."""
+    steady pipelines (same-sized units step after step) this replaces the count all_gather + padded gather.
+
+    On CUDA the collective runs on its own stream with two send/receive buffer sets, so the gather of step i
+    overlaps the index build of step i+1: `gather` only enqueues, `wait_previous` makes the compute stream wait
+    for the gather of the step before (whose buffers are about to be reused), `wait_all` for everything."""
 
     def __init__(self, capacity, cols, device, group=None, dst=0):
         self.cap, self.cols, self.group, self.dst = int(capacity), int(cols), group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.send = torch.zeros((self.cap + 1, self.cols), dtype=torch.int64, device=device)
-        self.recv = [torch.empty_like(self.send) for _ in range(self.world)] if self.rank == dst else None
+        self.cuda = torch.device(device).type == "cuda"
+        nbuf = 2 if self.cuda else 1
+        self.send = [torch.zeros((self.cap + 1, self.cols), dtype=torch.int64, device=device) for _ in range(nbuf)]
+        self.recv = [[torch.empty_like(self.send[0]) for _ in range(self.world)] if self.rank == dst else None for _ in range(nbuf)]
+        self.step = 0
+        self.last = 0
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device=device)
+            self.done = [None] * nbuf
 
     def gather(self, rows):
+        b = self.step % len(self.send)
+        send = self.send[b]
         k = rows.shape[0]
-        self.send[0, 0] = k                       # device-side write, no sync
+        send[0, 0] = k                            # device-side write, no sync
         m = min(k, self.cap)
         if m:
-            self.send[1:m + 1] = rows[:m]
-        dist.gather(self.send, self.recv, dst=self.dst, group=self.group)
+            send[1:m + 1] = rows[:m]
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ready)
+                dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
+                self.done[b] = torch.cuda.Event()
+                self.done[b].record(self.comm)
+        else:
+            dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
+        self.last = b
+        self.step += 1
+
+    def wait_previous(self):
+        """The current stream waits for the gather issued one step before the last one (buffer about to be reused)."""
+        if self.cuda and self.step >= 2:
+            ev = self.done[(self.step - 2) % len(self.send)]
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def wait_all(self):
+        if self.cuda:
+            for ev in self.done:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
 
     def check(self):
-        """On dst: per-rank row tensors of the LAST gather; raises if a rank had more rows than the capacity."""
+        """On dst: per-rank row tensors of the LAST gather (views into its receive buffers); raises if a rank had
+        more rows than the capacity."""
+        if self.cuda:
+            self.comm.synchronize()
         if self.rank != self.dst:
             return None
         out = []
+        recv = self.recv[self.last]
         for r in range(self.world):
-            k = int(self.recv[r][0, 0].item())
+            k = int(recv[r][0, 0].item())
             if k > self.cap:
                 raise OverflowError("rank %d produced %d rows, gather capacity %d" % (r, k, self.cap))
-            out.append(self.recv[r][1:k + 1])
+            out.append(recv[r][1:k + 1])
         return out
 
 
