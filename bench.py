@@ -334,6 +334,8 @@ def run_ours(args, rank, world, local_rank):
         emit(line)
     L.rv_index_free(h)
     if world > 1:
+        if "g" in gatherer:
+            gatherer["g"].close()
         dist.destroy_process_group()
 
 

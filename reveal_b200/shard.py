@@ -58,18 +58,57 @@ class FixedGather(object):
         self.cap, self.cols, self.group, self.dst = int(capacity), int(cols), group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.cuda = torch.device(device).type == "cuda"
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
         nbuf = 2 if self.cuda else 1
         self.send = [torch.zeros((self.cap + 1, self.cols), dtype=torch.int64, device=device) for _ in range(nbuf)]
         self.recv = [[torch.empty_like(self.send[0]) for _ in range(self.world)] if self.rank == dst else None for _ in range(nbuf)]
         self.step = 0
         self.last = 0
         if self.cuda:
+            # the collective is ENQUEUED by a helper thread as well: torch.distributed spends ~0.1-0.2 ms of host
+            # time per call, during which the main thread is already enqueueing the next index build
+            import queue
+            import threading
             self.comm = torch.cuda.Stream(device=device)
             self.done = [None] * nbuf
+            self.issued = [threading.Event() for _ in range(nbuf)]
+            for e in self.issued:
+                e.set()
+            self.jobs = queue.Queue()
+            self.error = None
+            self.worker = threading.Thread(target=self._run, daemon=True)
+            self.worker.start()
+
+    def _run(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            b, ready = job
+            try:
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ready)
+                    dist.gather(self.send[b], self.recv[b], dst=self.dst, group=self.group)
+                    ev = torch.cuda.Event()
+                    ev.record(self.comm)
+                    self.done[b] = ev
+            except Exception as exc:  # surfaced by wait_* / check on the main thread
+                self.error = exc
+            self.issued[b].set()
+
+    def close(self):
+        if self.cuda and self.worker.is_alive():
+            self.jobs.put(None)
+            self.worker.join(timeout=10)
 
     def gather(self, rows):
         b = self.step % len(self.send)
+        if self.cuda:
+            self.issued[b].wait()  # the helper has long issued the gather that used this buffer two steps ago
+            if self.error is not None:
+                raise self.error
         send = self.send[b]
         k = rows.shape[0]
         send[0, 0] = k                            # device-side write, no sync
@@ -77,36 +116,40 @@ class FixedGather(object):
         if m:
             send[1:m + 1] = rows[:m]
         if self.cuda:
-            cur = torch.cuda.current_stream()
             ready = torch.cuda.Event()
-            ready.record(cur)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(ready)
-                dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
-                self.done[b] = torch.cuda.Event()
-                self.done[b].record(self.comm)
+            ready.record(torch.cuda.current_stream())
+            self.issued[b].clear()
+            self.jobs.put((b, ready))
         else:
             dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
         self.last = b
         self.step += 1
 
+    def _wait(self, b):
+        self.issued[b].wait()
+        if self.error is not None:
+            raise self.error
+        if self.done[b] is not None:
+            torch.cuda.current_stream().wait_event(self.done[b])
+
     def wait_previous(self):
         """The current stream waits for the gather issued one step before the last one (buffer about to be reused)."""
         if self.cuda and self.step >= 2:
-            ev = self.done[(self.step - 2) % len(self.send)]
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
+            self._wait((self.step - 2) % len(self.send))
 
     def wait_all(self):
         if self.cuda:
-            for ev in self.done:
-                if ev is not None:
-                    torch.cuda.current_stream().wait_event(ev)
+            for b in range(len(self.send)):
+                self._wait(b)
 
     def check(self):
         """On dst: per-rank row tensors of the LAST gather (views into its receive buffers); raises if a rank had
         more rows than the capacity."""
         if self.cuda:
+            for e in self.issued:
+                e.wait()
+            if self.error is not None:
+                raise self.error
             self.comm.synchronize()
         if self.rank != self.dst:
             return None
