@@ -199,14 +199,13 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             return
         from reveal_b200 import shard
-        p, k = ctypes.c_void_p(), ctypes.c_int64()
-        _native.check(L, L.rv_result_device(h, ctypes.byref(p), ctypes.byref(k), None, None))
         with torch.cuda.stream(stream):  # same stream as the sweep kernels that produced the rows
             if "g" not in gatherer:
-                gatherer["g"] = shard.FixedGather(max(4096, 2 * k.value), 3, dev)
-            mine = torch.as_tensor(DevArray(p.value, (k.value, 3), "<i8"), device=dev) if k.value else torch.empty((0, 3), dtype=torch.int64, device=dev)
+                gatherer["g"] = shard.FixedGather(max(4096, 2 * cnt.value), 3, dev)
             g = gatherer["g"]
-            g.gather(mine)        # enqueued on the communication stream: overlaps the next step's index build
+            send = g.next_send()
+            _native.check(L, L.rv_result_pack_device(h, ctypes.c_void_p(send.data_ptr()), g.cap))  # count + rows, async on `stream`
+            g.submit()            # enqueued on the communication stream: overlaps the next step's index build
             g.wait_previous()     # ... but a step does not end before the gather of the step before it has landed
 
     gather_evs = []

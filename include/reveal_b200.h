@@ -122,6 +122,10 @@ int rv_mums_multi_fetch(rv_index *idx, int64_t *hdr, int64_t hdr_cap, int64_t *m
  * as int64 pairs; NULL when empty), for callers that gather over NCCL. */
 int rv_result_device(rv_index *idx, const int64_t **d_rows, int64_t *nrows, const int64_t **d_members, int64_t *nmembers);
 
+/* Packs the last sweep's rows for a fixed-capacity gather: d_dst[0] = row count, d_dst[3..] = the first
+ * min(count, cap_rows) rows (int64 triples), asynchronously on the handle's stream. */
+int rv_result_pack_device(rv_index *idx, int64_t *d_dst, int64_t cap_rows);
+
 /* Sweeps over caller-supplied device arrays of a SUB-index that shares the
  * main text (the children of reveal.c:582-664 split; RevealIndex.main): the
  * same kernels, used by the recursion.  dSO may be NULL iff main_nsamples == 2. */

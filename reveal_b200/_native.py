@@ -70,6 +70,7 @@ SIGNATURES = {
                                    ctypes.c_int64, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_vp)]),
     "rv_rec_stats": (ctypes.c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_double)]),
     "rv_sub_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
+    "rv_result_pack_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_sweep_pair_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_sweep_multi_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

@@ -487,6 +487,17 @@ int rv_result_device(rv_index *h, const int64_t **d_rows, int64_t *nrows, const 
     return RV_OK;
 }
 
+int rv_result_pack_device(rv_index *h, int64_t *d_dst, int64_t cap_rows) {
+    if (!h || h->last_kind == 0 || !d_dst) { set_error("no sweep result"); return RV_ERR_STATE; }
+    // the count travels through the pinned scratch word so that the copy below can stay asynchronous
+    int64_t *cnt = (int64_t *)(h->st.pinned + 300);
+    *cnt = h->last_rec;
+    RV_CUDA(cudaMemcpyAsync(d_dst, cnt, 8, cudaMemcpyHostToDevice, h->st.s));
+    i64 m = h->last_rec < cap_rows ? h->last_rec : cap_rows;
+    if (m > 0) RV_CUDA(cudaMemcpyAsync(d_dst + 3, h->d_rows, (size_t)m * 24, cudaMemcpyDeviceToDevice, h->st.s));
+    return RV_OK;
+}
+
 int rv_sweep_pair_device(rv_index *h, const uint8_t *dT, const int32_t *dSA, const int32_t *dLCP, int64_t n, int64_t nT, int64_t nsep0,
                          int32_t rc, int32_t flavour, int32_t minl, int64_t *count) {
     if (!h || !dT || !dSA || !dLCP || n < 0) return RV_ERR_ARG;

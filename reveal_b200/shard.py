@@ -103,18 +103,28 @@ class FixedGather(object):
             self.jobs.put(None)
             self.worker.join(timeout=10)
 
-    def gather(self, rows):
+    def next_send(self):
+        """The send block of the coming gather, for callers that fill it themselves (row 0 = count, rows 1.. = data,
+        e.g. rv_result_pack_device) and then call submit()."""
         b = self.step % len(self.send)
         if self.cuda:
             self.issued[b].wait()  # the helper has long issued the gather that used this buffer two steps ago
             if self.error is not None:
                 raise self.error
-        send = self.send[b]
+        return self.send[b]
+
+    def gather(self, rows):
+        send = self.next_send()
         k = rows.shape[0]
         send[0, 0] = k                            # device-side write, no sync
         m = min(k, self.cap)
         if m:
             send[1:m + 1] = rows[:m]
+        self.submit()
+
+    def submit(self):
+        b = self.step % len(self.send)
+        send = self.send[b]
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
