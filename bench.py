@@ -169,7 +169,9 @@ def run_ours(args, rank, world, local_rank):
     L = _native.lib()
     _native.check(L, L.rv_set_device(local_rank))
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a mismatched or stuck gather must abort the run, not hold 8 GPUs for minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
 
     T, nsep, ns, desc = make_workload(args.workload, seed=1 + rank)
     n = len(T)

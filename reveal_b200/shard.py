@@ -55,10 +55,15 @@ class FixedGather(object):
     for the gather of the step before (whose buffers are about to be reused), `wait_all` for everything."""
 
     def __init__(self, capacity, cols, device, group=None, dst=0):
-        self.cap, self.cols, self.group, self.dst = int(capacity), int(cols), group, dst
+        self.cols, self.group, self.dst = int(cols), group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
+        # every rank must send a block of the SAME size: agree on the largest requested capacity (one collective,
+        # at construction time)
+        c = torch.tensor([int(capacity)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX, group=group)
+        self.cap = int(c.item())
         self.cuda = self.device.type == "cuda"
         nbuf = 2 if self.cuda else 1
         self.send = [torch.zeros((self.cap + 1, self.cols), dtype=torch.int64, device=device) for _ in range(nbuf)]
