@@ -51,8 +51,9 @@ class FixedGather(object):
     steady pipelines (same-sized units step after step) this replaces the count all_gather + padded gather.
 
     On CUDA the collective runs on its own stream with two send/receive buffer sets, so the gather of step i
-    overlaps the index build of step i+1: `gather` only enqueues, `wait_previous` makes the compute stream wait
-    for the gather of the step before (whose buffers are about to be reused), `wait_all` for everything."""
+    overlaps the index build of step i+1: `submit` only enqueues, `wait_previous` makes the compute stream wait
+    for the gather of the step before (whose buffers are about to be reused), `wait_all` for everything.
+    All collectives are issued by the calling thread, in program order -- the same order on every rank."""
 
     def __init__(self, capacity, cols, device, group=None, dst=0):
         self.cols, self.group, self.dst = int(cols), group, dst
@@ -71,52 +72,19 @@ class FixedGather(object):
         self.step = 0
         self.last = 0
         if self.cuda:
-            # the collective is ENQUEUED by a helper thread as well: torch.distributed spends ~0.1-0.2 ms of host
-            # time per call, during which the main thread is already enqueueing the next index build
-            import queue
-            import threading
             self.comm = torch.cuda.Stream(device=device)
             self.done = [None] * nbuf
-            self.issued = [threading.Event() for _ in range(nbuf)]
-            for e in self.issued:
-                e.set()
-            self.jobs = queue.Queue()
-            self.error = None
-            self.worker = threading.Thread(target=self._run, daemon=True)
-            self.worker.start()
-
-    def _run(self):
-        torch.cuda.set_device(self.device)
-        while True:
-            job = self.jobs.get()
-            if job is None:
-                return
-            b, ready = job
-            try:
-                with torch.cuda.stream(self.comm):
-                    self.comm.wait_event(ready)
-                    dist.gather(self.send[b], self.recv[b], dst=self.dst, group=self.group)
-                    ev = torch.cuda.Event()
-                    ev.record(self.comm)
-                    self.done[b] = ev
-            except Exception as exc:  # surfaced by wait_* / check on the main thread
-                self.error = exc
-            self.issued[b].set()
 
     def close(self):
-        if self.cuda and self.worker.is_alive():
-            self.jobs.put(None)
-            self.worker.join(timeout=10)
+        pass
+
+    def drain(self):
+        pass
 
     def next_send(self):
         """The send block of the coming gather, for callers that fill it themselves (row 0 = count, rows 1.. = data,
         e.g. rv_result_pack_device) and then call submit()."""
-        b = self.step % len(self.send)
-        if self.cuda:
-            self.issued[b].wait()  # the helper has long issued the gather that used this buffer two steps ago
-            if self.error is not None:
-                raise self.error
-        return self.send[b]
+        return self.send[self.step % len(self.send)]
 
     def gather(self, rows):
         send = self.next_send()
@@ -133,38 +101,33 @@ class FixedGather(object):
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
-            self.issued[b].clear()
-            self.jobs.put((b, ready))
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ready)
+                dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
+                self.done[b] = torch.cuda.Event()
+                self.done[b].record(self.comm)
         else:
             dist.gather(send, self.recv[b], dst=self.dst, group=self.group)
         self.last = b
         self.step += 1
 
-    def _wait(self, b):
-        self.issued[b].wait()
-        if self.error is not None:
-            raise self.error
-        if self.done[b] is not None:
-            torch.cuda.current_stream().wait_event(self.done[b])
-
     def wait_previous(self):
         """The current stream waits for the gather issued one step before the last one (buffer about to be reused)."""
         if self.cuda and self.step >= 2:
-            self._wait((self.step - 2) % len(self.send))
+            ev = self.done[(self.step - 2) % len(self.send)]
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
 
     def wait_all(self):
         if self.cuda:
-            for b in range(len(self.send)):
-                self._wait(b)
+            for ev in self.done:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
 
     def check(self):
         """On dst: per-rank row tensors of the LAST gather (views into its receive buffers); raises if a rank had
         more rows than the capacity."""
         if self.cuda:
-            for e in self.issued:
-                e.wait()
-            if self.error is not None:
-                raise self.error
             self.comm.synchronize()
         if self.rank != self.dst:
             return None

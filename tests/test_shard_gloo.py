@@ -107,7 +107,8 @@ def _fixed_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    g = shard.FixedGather(8, 3, torch.device("cpu"))
+    g = shard.FixedGather(6 + 2 * rank, 3, torch.device("cpu"))  # ranks ask for different capacities: they must agree on 8
+    assert g.cap == 8
     for step in range(3):
         k = 3 + rank * 2 + step
         rows = torch.arange(k * 3, dtype=torch.int64).reshape(k, 3) + 100 * rank
