@@ -116,6 +116,9 @@ int rv_mums_pair_fetch(rv_index *idx, int64_t *rows, int64_t cap);
  * member rows (sample, position), list order = the reference's pop order,
  * members in SA-rank order. */
 int rv_mums_multi_count(rv_index *idx, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
+/* getmultimems (reveal.c:292-434 + ismultimem :261-290): lcp-intervals of any size whose members cover >= minn
+ * samples; hdr rows (l, n_samples, first_member).  Fetched with rv_mums_multi_fetch.  At most 64 samples. */
+int rv_mems_multi_count(rv_index *idx, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem);
 int rv_mums_multi_fetch(rv_index *idx, int64_t *hdr, int64_t hdr_cap, int64_t *members, int64_t mem_cap);
 
 /* Device pointers of the last sweep result (rows / hdr as int64 triples, members

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rv_mums_pair_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_mums_pair_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_mums_multi_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
+    "rv_mems_multi_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
     "rv_mums_multi_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_result_device": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i64p, ctypes.POINTER(c_vp), c_i64p]),
     "rv_sub_root": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),

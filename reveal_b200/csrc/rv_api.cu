@@ -462,6 +462,31 @@ int rv_mums_multi_count(rv_index *h, int32_t minl, int32_t minn, int64_t *nrec, 
     return run_multi(h, a, nrec, nmem);
 }
 
+int rv_mems_multi_count(rv_index *h, int32_t minl, int32_t minn, int64_t *nrec, int64_t *nmem) {
+    RV_TRY(need_built(h));
+    if (!nrec || !nmem) return RV_ERR_ARG;
+    if (h->nsamples > 64) { set_error("getmultimems: more than 64 samples are not supported"); return RV_ERR_UNSUPPORTED; }
+    if (h->nsamples < 2) { set_error("getmultimems needs at least two samples"); return RV_ERR_STATE; }
+    SweepArgs a = root_args(h);
+    a.minl = minl;
+    a.minn = minn;
+    h->last_kind = 0;
+    RV_TRY(h->sw.reserve(mems_scratch_bytes(a.n)));
+    i64 r = 0, m = 0;
+    RV_TRY(sweep_mems_count(h->st, a, h->sw.base, &r, &m));
+    size_t hdr_bytes = pad256((size_t)(r > 0 ? r : 1) * 24);
+    RV_TRY(h->res.reserve(hdr_bytes + pad256((size_t)(m > 0 ? m : 1) * 16)));
+    h->d_rows = (i64 *)h->res.base;
+    h->d_members = (i64 *)(h->res.base + hdr_bytes);
+    if (r > 0) RV_TRY(sweep_mems_write(h->st, a, h->sw.base, h->d_rows, r, h->d_members, m));
+    h->last_kind = 2;
+    h->last_rec = r;
+    h->last_mem = m;
+    *nrec = r;
+    *nmem = m;
+    return RV_OK;
+}
+
 int rv_mums_multi_fetch(rv_index *h, int64_t *hdr, int64_t hdr_cap, int64_t *members, int64_t mem_cap) {
     if (!h || h->last_kind != 2) { set_error("no multi sweep result to fetch"); return RV_ERR_STATE; }
     i64 r = h->last_rec < hdr_cap ? h->last_rec : hdr_cap;

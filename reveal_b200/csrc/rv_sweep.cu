@@ -126,6 +126,63 @@ multi_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u64 *__r
     }
 }
 
+// ---- multi-MEM sweep: one thread per segment start (see mem_walk) ----------------------------------------------
+__global__ void __launch_bounds__(SW_THREADS) mems_count_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb,
+                                                                u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem, u32 *__restrict__ hitbits) {
+    __shared__ u64 s1[33], s2[33];
+    u64 nr = 0, nm = 0;
+    for (int c = 0; c < SW_CHUNKS; c++) {
+        i64 i = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
+        u64 r0 = nr;
+        if (mem_segment_start(p, i)) mem_walk(p, i, st_l, st_lb, [&](i64, i64, i64, i64 size) { nr++; nm += (u64)size; });
+        unsigned m = __ballot_sync(FULL, nr != r0);
+        if ((threadIdx.x & 31u) == 0) hitbits[i >> 5] = m;
+    }
+    u64 tr, tm;
+    block_incl_sum<SW_THREADS, u64>(nr, s1, &tr);
+    block_incl_sum<SW_THREADS, u64>(nm, s2, &tm);
+    if (threadIdx.x == 0) {
+        tile_rec[blockIdx.x] = tr;
+        tile_mem[blockIdx.x] = tm;
+    }
+}
+
+__global__ void __launch_bounds__(SW_THREADS)
+mems_write_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb, const u64 *__restrict__ tile_rec, const u64 *__restrict__ tile_mem,
+                  const u32 *__restrict__ hitbits, i64 tiles, i64 *__restrict__ hdr, i64 hdr_cap, i64 *__restrict__ members, i64 mem_cap) {
+    const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
+    if (tile >= tiles) return;  // warp-uniform
+    const unsigned lane = threadIdx.x & 31u;
+    const i64 word = tile * (SW_TILE / 32) + lane;
+    const u32 bits0 = word * 32 < p.n ? hitbits[word] : 0u;
+    u64 nr = 0, nm = 0;
+    for (u32 bits = bits0; bits; bits &= bits - 1u) {
+        i64 i = word * 32 + (__ffs((int)bits) - 1);
+        mem_walk(p, i, st_l, st_lb, [&](i64, i64, i64, i64 size) { nr++; nm += (u64)size; });
+    }
+    u64 ir = warp_incl_sum(nr), im = warp_incl_sum(nm);
+    u64 at_r = tile_rec[tile] + ir - nr, at_m = tile_mem[tile] + im - nm;
+    for (u32 bits = bits0; bits; bits &= bits - 1u) {
+        i64 i = word * 32 + (__ffs((int)bits) - 1);
+        mem_walk(p, i, st_l, st_lb, [&](i64 l, i64 c, i64 lb, i64 size) {
+            if ((i64)at_r < hdr_cap) {
+                hdr[3 * at_r + 0] = l;
+                hdr[3 * at_r + 1] = c;          // number of distinct samples (reveal.c:353), NOT the member count
+                hdr[3 * at_r + 2] = (i64)at_m;
+            }
+            for (i64 x = 0; x < size; x++) {
+                if ((i64)at_m < mem_cap) {
+                    i64 pos = p.SA[lb + x];
+                    members[2 * at_m + 0] = sample_of(p, pos);
+                    members[2 * at_m + 1] = pos;
+                }
+                at_m++;
+            }
+            at_r++;
+        });
+    }
+}
+
 // single block: in-place exclusive scan of up to two u64 arrays; totals -> out[0], out[1]
 __global__ void __launch_bounds__(1024) sweep_tilescan_kernel(u64 *__restrict__ a, u64 *__restrict__ b, i64 tiles, u64 *__restrict__ out) {
     __shared__ u64 s1[33], s2[33];
@@ -223,6 +280,57 @@ int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr,
     RV_LAUNCH(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
               d_mem, mem_cap);
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
+    st.launches++;
+    RV_KCHECK();
+    return RV_OK;
+}
+
+}  // namespace rv
+
+namespace rv {
+
+// getmultimems: scratch = sweep scratch followed by the two stack arrays (n ints each)
+size_t mems_scratch_bytes(i64 n) { return sweep_scratch_bytes(n) + (size_t)(n + 64) * 8 + 512; }
+
+static void mems_layout(void *scratch, i64 n, u64 **tile_rec, u64 **tile_mem, u64 **totals, u32 **hitbits, int **st_l, int **st_lb, i64 *tiles) {
+    *tiles = (n + SW_TILE - 1) / SW_TILE;
+    *tile_rec = (u64 *)scratch;
+    *tile_mem = *tile_rec + *tiles;
+    *totals = *tile_rec + 2 * *tiles;
+    *hitbits = (u32 *)(*tile_rec + 2 * *tiles + 8);
+    unsigned char *after = (unsigned char *)scratch + (sweep_scratch_bytes(n) + 255) / 256 * 256;
+    *st_l = (int *)after;
+    *st_lb = *st_l + (n + 32);
+}
+
+int sweep_mems_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem) {
+    *nrec = *nmem = 0;
+    if (p.n < 2) return RV_OK;
+    u64 *tile_rec, *tile_mem, *totals;
+    u32 *hitbits;
+    int *st_l, *st_lb;
+    i64 tiles;
+    mems_layout(scratch, p.n, &tile_rec, &tile_mem, &totals, &hitbits, &st_l, &st_lb, &tiles);
+    RV_LAUNCH(mems_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits);
+    RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
+    st.launches += 2;
+    u64 h[2];
+    RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    *nrec = (i64)h[0];
+    *nmem = (i64)h[1];
+    return RV_OK;
+}
+
+int sweep_mems_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr, i64 hdr_cap, i64 *d_mem, i64 mem_cap) {
+    if (p.n < 2) return RV_OK;
+    u64 *tile_rec, *tile_mem, *totals;
+    u32 *hitbits;
+    int *st_l, *st_lb;
+    i64 tiles;
+    mems_layout(scratch, p.n, &tile_rec, &tile_mem, &totals, &hitbits, &st_l, &st_lb, &tiles);
+    const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
+    RV_LAUNCH(mems_write_kernel, wblocks, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits, tiles, d_hdr, hdr_cap, d_mem, mem_cap);
     st.launches++;
     RV_KCHECK();
     return RV_OK;

@@ -26,4 +26,8 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
                       i64 mem_cap_spec);
 int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr, i64 hdr_cap, i64 *d_mem, i64 mem_cap);
 
+size_t mems_scratch_bytes(i64 n);
+int sweep_mems_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i64 *nmem);
+int sweep_mems_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr, i64 hdr_cap, i64 *d_mem, i64 mem_cap);
+
 }  // namespace rv

@@ -84,4 +84,62 @@ template <class F> __device__ __forceinline__ void multi_visit(const SweepArgs &
     }
 }
 
+
+// ---- multi-MEM walk (getmultimems, reveal.c:292-434 + ismultimem :261-290) --------------------------------
+// The reference's lcp-interval stack walk reports intervals of ANY size whose members cover >= minn samples, and
+// its `continue` at reveal.c:340-342 (taken when an interval is a multi-MEM of too few samples) skips the
+// `lb = i_lb` hand-over, which changes the left boundary RECORDED for the interval pushed next -- so the output
+// depends on the walk itself and cannot be restated per interval.  But the walk decomposes: a position with
+// LCP < minl pops every entry that could ever be reported, and an entry of value >= minl only ever inherits its
+// left boundary from entries of value >= minl popped at the same position.  So every maximal run of positions with
+// LCP >= minl ("segment") is walked by its own thread with its own stack (slots [i0, ...) of two global arrays:
+// the depth never exceeds the run length), exactly as the reference walks it.
+__device__ __forceinline__ bool mem_ok(const SweepArgs &p, i64 l, i64 lb, i64 ub, int &c) {
+    c = 0;
+    if (l <= 0) return false;
+    if (p.main_nsamples == 2) {
+        c = 1;  // reveal.c:267: exactly one of the two flags is incremented
+    } else {
+        u64 seen = 0;
+        for (i64 j = lb; j <= ub; j++) seen |= 1ull << p.SO[p.SA[j]];
+        c = __popcll(seen);
+    }
+    for (i64 j = lb; j < ub; j++)
+        if (left_maximal(p.T, p.SA[j], p.SA[j + 1])) return true;
+    return false;
+}
+
+__device__ __forceinline__ bool mem_segment_start(const SweepArgs &p, i64 i) {
+    if (i < 1 || i >= p.n) return false;
+    if (p.LCP[i] < p.minl) return false;
+    return i == 1 || p.LCP[i - 1] < p.minl;
+}
+
+// walks the segment that starts at i0; emit(l, c, lb, size) in the reference's pop order
+template <class F> __device__ __forceinline__ void mem_walk(const SweepArgs &p, i64 i0, int *__restrict__ st_l, int *__restrict__ st_lb, F emit) {
+    int *sl = st_l + i0, *slb = st_lb + i0;
+    i64 depth = 0;
+    for (i64 i = i0;; i++) {
+        const i64 cur = i < p.n ? (i64)p.LCP[i] : -1;  // -1: the final flush (reveal.c:390-434) closes everything at n-1
+        i64 lb = i - 1;
+        while (depth > 0 && cur < (i64)sl[depth - 1]) {
+            depth--;
+            const i64 l = sl[depth], ilb = slb[depth], iub = i - 1, size = iub - ilb + 1;
+            bool skip_handover = false;
+            int c = 0;
+            if (l >= p.minl && size >= p.minn && mem_ok(p, l, ilb, iub, c)) {
+                if (c < p.minn) skip_handover = true;  // the reference's `continue` (reveal.c:340-342)
+                else emit(l, (i64)c, ilb, size);
+            }
+            if (!skip_handover) lb = ilb;
+        }
+        if (i >= p.n || cur < p.minl) break;
+        if (depth == 0 || cur > (i64)sl[depth - 1]) {
+            sl[depth] = (int)cur;
+            slb[depth] = (int)lb;
+            depth++;
+        }
+    }
+}
+
 }  // namespace rv

@@ -199,6 +199,30 @@ class index(object):
             out.append((l, n, tuple(mem[first:first + n])))
         return out
 
+    def getmultimems_arrays(self, minlength=0, minn=2):
+        """(hdr int64 [k,3] rows (l, n_samples, first_member), members int64 [m,2]); a record's members run to the next
+        record's first_member."""
+        if not self._built:
+            raise error("Index not yet constructed.")
+        L, h = self._lib(), self._handle()
+        nr, nm = ctypes.c_int64(), ctypes.c_int64()
+        self._call(L.rv_mems_multi_count(h, int(minlength), int(minn), ctypes.byref(nr), ctypes.byref(nm)))
+        hdr = np.empty((nr.value, 3), dtype=np.int64)
+        mem = np.empty((nm.value, 2), dtype=np.int64)
+        self._call(L.rv_mums_multi_fetch(h, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+        return hdr, mem
+
+    def getmultimems(self, minlength=0, minn=2):
+        """[(l, n_samples, ((sample, pos), ...)), ...]  -- reveal.c:292-434."""
+        hdr, mem = self.getmultimems_arrays(minlength, minn)
+        mem = [tuple(x) for x in mem.tolist()]
+        out = []
+        rows = hdr.tolist()
+        for k, (l, c, first) in enumerate(rows):
+            end = rows[k + 1][2] if k + 1 < len(rows) else len(mem)
+            out.append((l, c, tuple(mem[first:end])))
+        return out
+
     def align(self, mumpicker, align, threads=0, wpen=0, wscore=0, minl=0, minn=0):
         if not self._built:
             raise error("Index not yet constructed, alignment stopped.")  # interface.c:295-298

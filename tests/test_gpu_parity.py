@@ -206,3 +206,24 @@ def test_cuda_full_size_c4_properties(cuda_lib):
     with NativeIndex(cuda_lib, T, nsep, ns) as idx:
         mums = _properties(T, nsep, ns, idx, 20)
         assert len(mums) > 500000
+
+
+def test_cuda_getmultimems_matches_oracle(cuda_lib):
+    """getmultimems through the drop-in class, incl. the reference's `continue` quirk, vs the oracle."""
+    from reveal_b200 import reveallib
+    rng = np.random.default_rng(99)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    base = al[rng.integers(0, 4, size=30000)].tobytes()
+    rep = base[500:900]
+    raw = [base + rep + base[:1000], base[:20000] + b"T" + base[20001:] + rep, rep + base[1000:25000] + rep + rep, base[5000:28000]]
+    idx = reveallib.index()
+    for k, s in enumerate(raw):
+        idx.addsample("s%d" % k)
+        idx.addsequence(s.decode())
+    idx.construct()
+    T = np.frombuffer(idx.T.encode(), np.uint8)
+    o = P.Index(T, idx.nsep, 4)
+    for minl, minn in ((20, 2), (12, 3), (30, 4)):
+        got = idx.getmultimems(minl, minn)
+        assert got == P.multi_to_tuples(*o.getmultimems(minl, minn))
+        assert len(got) > 0

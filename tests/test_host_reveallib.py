@@ -135,3 +135,37 @@ def test_cache_files_round_trip(emu_reveallib, tmp_path, monkeypatch):
             c.addsequence(s)
     with pytest.raises(emu_reveallib.error):
         c.construct()
+
+
+@needs_ref
+@pytest.mark.parametrize("minl,minn", [(3, 2), (2, 3), (6, 2), (1, 2), (0, 2)])
+def test_getmultimems_matches_reference(emu_reveallib, minl, minn):
+    """getmultimems incl. the reference's `continue` quirk (reveal.c:340-342), against the unmodified extension."""
+    rng = np.random.default_rng(minl * 10 + minn)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    base = al[rng.integers(0, 4, size=400)].tobytes().decode()
+    rep = base[50:90]
+    samples = [[base + rep + base[:100]], [base[:200] + "T" + base[201:] + rep], [rep + base[100:350] + rep + rep]]
+    ours, ref = build_both(emu_reveallib, samples)
+    want = [tuple(m) for m in ref.getmultimems(minlength=minl, minn=minn)]
+    got = ours.getmultimems(minl, minn)
+    assert got == want
+    if minl >= 2:
+        assert len(want) > 0
+
+
+def test_getmultimems_matches_oracle_port(emu_reveallib):
+    import oracle.port as P
+    from util import random_related
+    rng = np.random.default_rng(99)
+    samples = random_related(rng, 4, 1500, 3, snp=0.05)
+    idx = emu_reveallib.index()
+    for k, seqs in enumerate(samples):
+        idx.addsample("s%d" % k)
+        for s in seqs:
+            idx.addsequence(s.decode())
+    idx.construct()
+    T = np.frombuffer(idx.T.encode(), np.uint8)
+    o = P.Index(T, idx.nsep, 4)
+    for minl, minn in ((5, 2), (4, 3), (8, 4)):
+        assert idx.getmultimems(minl, minn) == P.multi_to_tuples(*o.getmultimems(minl, minn))
