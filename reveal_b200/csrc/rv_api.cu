@@ -160,8 +160,9 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
         set_error("rv_build: n=%lld not supported (limit 2^30-1 characters per index)", (long long)n);
         return RV_ERR_UNSUPPORTED;
     }
-    if (rc && nsamples < 2) {
-        set_error("rv_build: rc=1 needs at least two samples");
+    if (rc && (nsamples < 2 || nsep[0] < 0 || nsep[0] >= n)) {
+        // the reference would reverse-complement from T + nsep[0] = T - 1 (interface.c:170): undefined there, refused here
+        set_error("rv_build: rc=1 needs two samples and a non-empty first sample");
         return RV_ERR_ARG;
     }
     h->built = false;
