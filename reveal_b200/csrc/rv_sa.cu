@@ -69,14 +69,30 @@ __device__ __forceinline__ void run_lengths(const KeyT *__restrict__ keys, i64 A
 // ---- stage 3: all-pairs comparison inside small groups -------------------------------------
 // Two-level barrier bitmap: bit i of bar0[] is set iff T[i] is '$' or 'N' (the reference's LCP
 // barrier, interface.c:107); bit w of bar1[] is set iff word w of bar0 is non-zero.
-__global__ void __launch_bounds__(1024) sa_barrier_bits_kernel(const unsigned char *__restrict__ T, i64 n, u32 *__restrict__ bar0, u32 *__restrict__ bar1) {
+// One pass over T: the barrier bitmaps and (PACK) the 4-bit packed text (8 symbols per word, symbol i in bits 4i..4i+3).
+template <bool PACK>
+__global__ void __launch_bounds__(1024) sa_textprep_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ bar0,
+                                                          u32 *__restrict__ bar1, u32 *__restrict__ packed) {
     __shared__ u32 s_nz[32];
+    __shared__ unsigned short s_code[256];
+    if (PACK) {
+        if (threadIdx.x < 256) s_code[threadIdx.x] = tab.code[threadIdx.x];
+        __syncthreads();
+    }
     i64 i = (i64)blockIdx.x * 1024 + threadIdx.x;
     unsigned char c = i < n ? T[i] : 0;
     unsigned m = __ballot_sync(FULL, c == '$' || c == 'N');
     if ((threadIdx.x & 31u) == 0) {
         bar0[i >> 5] = m;
         s_nz[threadIdx.x >> 5] = m ? 1u : 0u;
+    }
+    if (PACK) {
+        // 8 consecutive lanes hold the 8 symbols of one packed word: OR-reduce their nibbles with shuffles
+        u32 v = i < n ? (((u32)s_code[c] & 15u) << (4 * (threadIdx.x & 7u))) : 0u;
+        v |= __shfl_xor_sync(FULL, v, 1);
+        v |= __shfl_xor_sync(FULL, v, 2);
+        v |= __shfl_xor_sync(FULL, v, 4);
+        if ((threadIdx.x & 7u) == 0) packed[i >> 3] = v;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -121,7 +137,7 @@ __device__ __forceinline__ u32 first_barrier(const u32 *__restrict__ bar0, const
 
 // Text as the comparison loops see it: SB bits per symbol in little-endian 32-bit words (symbol i of a word
 // in bits [SB*i, SB*i+SB)).  SB = 8: the raw bytes of T.  SB = 4: order-preserving dense codes packed two per
-// byte (sa_pack4_kernel) when the alphabet has at most 15 symbols -- DNA with '$', 'N' and a few IUPAC codes --
+// byte (sa_textprep_kernel) when the alphabet has at most 15 symbols -- DNA with '$', 'N' and a few IUPAC codes --
 // which halves the words a comparison has to fetch.  Zero padded past the end.
 template <int SB> struct Sym {
     static const u32 LOG_SPW = SB == 8 ? 2u : 3u;   // log2(symbols per word)
@@ -130,20 +146,6 @@ template <int SB> struct Sym {
     static const u32 STEP = 4u * SPW;                // symbols per comparison step (4 words per suffix)
     static const u32 MASK = (1u << SB) - 1u;
 };
-
-__global__ void __launch_bounds__(256) sa_pack4_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ P, i64 words) {
-    __shared__ unsigned short s_code[256];
-    s_code[threadIdx.x] = tab.code[threadIdx.x];
-    __syncthreads();
-    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= words) return;
-    u32 v = 0;
-    for (int j = 0; j < 8; j++) {
-        i64 i = w * 8 + j;
-        if (i < n) v |= ((u32)s_code[T[i]] & 15u) << (4 * j);
-    }
-    P[w] = v;
-}
 
 // barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison, 4 words per step
 template <int SB>
@@ -658,19 +660,18 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     // comparison stage
     RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    RV_LAUNCH(sa_barrier_bits_kernel, (unsigned)((n + 1023) / 1024 + 1), 1024, 0, st.s, dT, n, B.bar, B.bar1);
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
     // text for the comparisons: 4-bit packed codes when the alphabet allows (sigma <= 15), else the raw bytes
     const bool packed = base <= 16 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
     const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
+    const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);  // one block past the end: zero padding of the packed text
     if (packed) {
-        const i64 words = n / 8 + 16;
-        RV_LAUNCH(sa_pack4_kernel, (unsigned)((words + 255) / 256), 256, 0, st.s, dT, n, tab, B.packed, words);
-        st.launches++;
+        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
         RV_TRY(prof_begin(st));
         RV_LAUNCH((sa_pairs_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)B.packed, B.bar, B.bar1, k, dSA, dISA, dLCP,
                   B.deferred, B.small + 257, B.chunk_start);
     } else {
+        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
         RV_TRY(prof_begin(st));
         RV_LAUNCH((sa_pairs_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)dT, B.bar, B.bar1, k, dSA, dISA, dLCP,
                   B.deferred, B.small + 257, B.chunk_start);
@@ -773,7 +774,7 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.deferred = ws.take<unsigned char>(n);
     B.need = ws.take<unsigned char>(n);
     B.chunk_start = ws.take<int>(n / PR_CHUNK + 2 * PR_WARPS + 8);
-    B.packed = ws.take<u32>(n / 8 + 16);
+    B.packed = ws.take<u32>(n / 8 + 300);  // sa_textprep_kernel writes whole 1024-symbol blocks, one block past the end
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
     if (!B.deferred || !B.need || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
