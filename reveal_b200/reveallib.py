@@ -223,6 +223,32 @@ class index(object):
             out.append((l, c, tuple(mem[first:end])))
         return out
 
+    def copy(self):
+        """A second index over the same text with its own SA / SAi / LCP / SO (interface.c:432-470).  The arrays are
+        uploaded into the copy's device handle (no rebuild)."""
+        if not self._built:
+            raise error("Index not yet constructed.")
+        new = type(self)()
+        new.samples = list(self.samples)
+        new.nodes = set(self.nodes)
+        new._chunks = [self._text().tobytes()]
+        new._n = self._n
+        new._nsep = list(self._nsep)
+        new._nsamples = self._nsamples
+        T = new._text()
+        nsep = np.asarray(new._nsep, dtype=np.int64)
+        sa = np.ascontiguousarray(self._array("SA"), dtype=np.int32)
+        lcp = np.ascontiguousarray(self._array("LCP"), dtype=np.int32)
+        L = new._lib()
+        # rc = 0: the text handed over is already the indexed (possibly reverse-complemented) one
+        new._call(L.rv_build_cached(new._handle(), T.ctypes.data, new._n, nsep.ctypes.data if len(nsep) else None, new._nsamples, 0,
+                                    sa.ctypes.data, lcp.ctypes.data))
+        new._rc = self._rc
+        new._nT = self._nT
+        new._built = True
+        new.main = new
+        return new
+
     def align(self, mumpicker, align, threads=0, wpen=0, wscore=0, minl=0, minn=0):
         if not self._built:
             raise error("Index not yet constructed, alignment stopped.")  # interface.c:295-298

@@ -169,3 +169,17 @@ def test_getmultimems_matches_oracle_port(emu_reveallib):
     o = P.Index(T, idx.nsep, 4)
     for minl, minn in ((5, 2), (4, 3), (8, 4)):
         assert idx.getmultimems(minl, minn) == P.multi_to_tuples(*o.getmultimems(minl, minn))
+
+
+def test_copy_is_independent(emu_reveallib):
+    a = emu_reveallib.index()
+    for k, seqs in enumerate(SAMPLES):
+        a.addsample("s%d" % k)
+        for s in seqs:
+            a.addsequence(s)
+    a.construct()
+    b = a.copy()
+    assert b.SA == a.SA and b.SAi == a.SAi and b.LCP == a.LCP and b.SO == a.SO and b.T == a.T and b.nsep == a.nsep
+    assert b.getmultimums(3, 2) == a.getmultimums(3, 2)
+    del a
+    assert len(b.getmultimums(3, 2)) > 0
