@@ -180,9 +180,18 @@ __device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u3
     return (int)first_barrier(bar0, bar1, p, match);
 }
 
-static const int PR_THREADS = 128;
+#ifndef RV_PR_THREADS
+#define RV_PR_THREADS 128
+#endif
+#ifndef RV_PR_CHUNK
+#define RV_PR_CHUNK 256
+#endif
+#ifndef RV_PR_MINBLOCKS
+#define RV_PR_MINBLOCKS 10
+#endif
+static const int PR_THREADS = RV_PR_THREADS;
 static const int PR_WARPS = PR_THREADS / 32;
-static const int PR_CHUNK = 256;                       // nominal SA slots per warp
+static const int PR_CHUNK = RV_PR_CHUNK;               // nominal SA slots per warp
 static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched to whole groups (<= SA_SMALL_G more), padded to rounds
 static const int PR_ROUNDS = PR_MAXT / 32;
 static const int PR_QCAP = 512;                        // ring of work items per warp (>= one worst-case round of 32*15)
@@ -196,7 +205,7 @@ static const int PR_QCAP = 512;                        // ring of work items per
 // largest over its smaller mates); both live in shared memory because a group never leaves its warp.
 // The warp then places its groups: SA, inverse SA and LCP.
 template <typename KeyT, int SB>
-__global__ void __launch_bounds__(PR_THREADS, 10)
+__global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
 sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W,
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
                 int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start) {
