@@ -59,13 +59,29 @@ def measured_traffic(kernel, workload):
 
 
 def peaks():
+    """HBM roofline denominator: the driver-measured copy bandwidth when MEASURED_PEAKS.json exists, else the fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
-                if k in d:
-                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+
+            def find(obj):
+                if isinstance(obj, dict):
+                    for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
+                        if isinstance(obj.get(k), (int, float)):
+                            return float(obj[k])
+                    for k, v in obj.items():  # tolerate other spellings / nesting: first numeric "hbm*" entry in GB/s range
+                        if isinstance(v, (int, float)) and "hbm" in k.lower() and 500 < float(v) < 20000:
+                            return float(v)
+                    for v in obj.values():
+                        r = find(v)
+                        if r:
+                            return r
+                return None
+
+            v = find(d)
+            if v:
+                return v, "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
