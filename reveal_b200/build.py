@@ -51,5 +51,25 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_extension(force=False):
+    """Compile the CPython extension modules reveal_b200/reveallib*.so and reveallib64*.so (host side of the drop-in)."""
+    import sysconfig
+    src = os.path.join(CSRC, "ext", "reveallib_module.cpp")
+    inc = sysconfig.get_paths()["include"]
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    outs = []
+    for name, defs in (("reveallib", []), ("reveallib64", ["-DSA64=1"])):
+        out = os.path.join(_HERE, name + suffix)
+        outs.append(out)
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "..", "include", "reveal_b200.h"))):
+            continue
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I" + inc] + defs + [src, "-o", out, "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for %s:\n%s\n%s" % (name, r.stdout, r.stderr))
+    return outs
+
+
 if __name__ == "__main__":
+    print(build_extension(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

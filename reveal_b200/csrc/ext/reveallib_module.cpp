@@ -1,0 +1,789 @@
+// reveallib_module.cpp -- the compiled CPython extension `reveallib` / `reveallib64`: the host side of the drop-in.
+//
+// Mirrors the reference's extension (reveallib/interface.c + the `aligner` of reveallib/reveal.c) symbol for symbol:
+//   type `index`      interface.c:841-881     ctor kwargs sa, lcp, cache      interface.c:515-518
+//   methods           interface.c:474-487     addsample addsequence construct align getmums getmultimums
+//                                             getmultimems copy
+//   getters           interface.c:731-785     n depth nsamples samples nodes leftnode rightnode nsep SA SAi SO LCP T
+//   exception         interface.c:933-936     reveallib.error
+// but holds no algorithm: every array operation goes through the C-ABI of libreveal_b200.so (include/reveal_b200.h),
+// which is dlopen'ed when the module is imported.  There is no CPU path: without that library, or without a GPU,
+// the calls raise.  Child indexes of the recursion are `index` objects too, as in the reference (reveal.c:1136-1207).
+// Built twice: module name reveallib (default) and, with -DSA64, reveallib64 (reveal.h:7-13: same numbers in wider
+// integers; the 32-bit total-length guard of addsequence is off).
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../../include/reveal_b200.h"
+
+#ifdef SA64
+#define MODNAME "reveallib64"
+#define MODINIT PyInit_reveallib64
+#else
+#define MODNAME "reveallib"
+#define MODINIT PyInit_reveallib
+#endif
+
+// ---- the C-ABI, resolved at run time ---------------------------------------------------------------------------------
+#define RV_API_LIST(X)                                                                                                  \
+    X(rv_last_error) X(rv_version) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
+    X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
+    X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_free) X(rv_sub_get)    \
+    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step)
+
+struct Api {
+#define X(name) decltype(&::name) name = nullptr;
+    RV_API_LIST(X)
+#undef X
+    void *handle = nullptr;
+    std::string path;
+};
+static Api g_api;
+static PyObject *RevealError = nullptr;
+
+static bool load_library(const char *path) {
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        PyErr_Format(PyExc_ImportError,
+                     MODNAME ": cannot load %s (%s); build the CUDA library first "
+                             "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.",
+                     path, dlerror());
+        return false;
+    }
+    Api a;
+#define X(name)                                                                                    \
+    a.name = (decltype(a.name))dlsym(h, #name);                                                    \
+    if (!a.name) {                                                                                 \
+        PyErr_Format(PyExc_ImportError, MODNAME ": %s lacks the symbol %s", path, #name);          \
+        dlclose(h);                                                                                \
+        return false;                                                                              \
+    }
+    RV_API_LIST(X)
+#undef X
+    a.handle = h;
+    a.path = path;
+    g_api = a;  // a previously loaded library stays mapped: live handles may still point into it
+    return true;
+}
+
+static bool api_ready() {
+    if (g_api.handle) return true;
+    PyErr_SetString(PyExc_ImportError, MODNAME ": libreveal_b200.so is not loaded");
+    return false;
+}
+
+// ---- the index type ----------------------------------------------------------------------------------------------------
+struct Index {
+    PyObject_HEAD
+    // root state
+    rv_index *h;
+    std::string *T;              // host copy of the text (root only)
+    std::vector<int64_t> *nsep;
+    int nsamples, rc, depth, cache, built, tdirty;
+    int64_t n, nT;
+    std::string *safile, *lcpfile;
+    // recursion state
+    rv_sub *sub;                 // device view (children; the root gets one during align)
+    Index *mainidx;              // borrowed-with-reference: the root this child belongs to (NULL for a root)
+    PyObject *samples, *nodes, *left_node, *right_node, *skipmums;
+};
+
+static PyTypeObject IndexType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+
+static int fail_native(int status) {
+    if (status == 0) return 0;
+    PyErr_SetString(RevealError, g_api.rv_last_error ? g_api.rv_last_error() : "native call failed");
+    return -1;
+}
+
+static Index *root_of(Index *self) { return self->mainidx ? self->mainidx : self; }
+
+static int ensure_handle(Index *self) {
+    if (!api_ready()) return -1;
+    if (self->h) return 0;
+    return fail_native(g_api.rv_index_create(&self->h, nullptr));
+}
+
+static PyObject *index_new(PyTypeObject *type, PyObject *, PyObject *) {
+    Index *self = (Index *)type->tp_alloc(type, 0);
+    if (!self) return nullptr;
+    self->h = nullptr;
+    self->T = new std::string();
+    self->nsep = new std::vector<int64_t>();
+    self->safile = new std::string();
+    self->lcpfile = new std::string();
+    self->nsamples = self->rc = self->depth = self->cache = self->built = self->tdirty = 0;
+    self->n = self->nT = 0;
+    self->sub = nullptr;
+    self->mainidx = nullptr;
+    self->samples = PyList_New(0);
+    self->nodes = PySet_New(nullptr);
+    self->skipmums = PyList_New(0);
+    Py_INCREF(Py_None);
+    self->left_node = Py_None;
+    Py_INCREF(Py_None);
+    self->right_node = Py_None;
+    return (PyObject *)self;
+}
+
+static int index_init(Index *self, PyObject *args, PyObject *kwds) {
+    static const char *kwlist[] = {"sa", "lcp", "cache", nullptr};  // interface.c:515-518
+    const char *sa = "", *lcp = "";
+    int cache = 0;
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "|ssi", (char **)kwlist, &sa, &lcp, &cache)) return -1;
+    *self->safile = sa;
+    *self->lcpfile = lcp;
+    self->cache = cache;
+    return 0;
+}
+
+static void index_dealloc(Index *self) {
+    if (self->sub && g_api.rv_sub_free) g_api.rv_sub_free(self->sub);
+    if (self->h && g_api.rv_index_free) g_api.rv_index_free(self->h);
+    delete self->T;
+    delete self->nsep;
+    delete self->safile;
+    delete self->lcpfile;
+    Py_XDECREF(self->samples);
+    Py_XDECREF(self->nodes);
+    Py_XDECREF(self->left_node);
+    Py_XDECREF(self->right_node);
+    Py_XDECREF(self->skipmums);
+    Py_XDECREF((PyObject *)self->mainidx);
+    Py_TYPE(self)->tp_free((PyObject *)self);
+}
+
+// ---- text assembly (interface.c:18-95) ------------------------------------------------------------------------------------
+static PyObject *index_addsample(Index *self, PyObject *args) {
+    PyObject *sample = PyTuple_Size(args) > 0 ? PyTuple_GetItem(args, 0) : nullptr;
+    if (!sample) {
+        PyErr_SetString(RevealError, "Specify name of sample as argument.");
+        return nullptr;
+    }
+    if (!PyUnicode_Check(sample)) {
+        PyErr_SetString(RevealError, "Sample name has to be a string.");
+        return nullptr;
+    }
+    PyList_Append(self->samples, sample);
+    if (self->nsamples > 0) self->nsep->push_back(self->n - 1);  // position of the last '$' of the previous sample
+    self->nsamples++;
+    Py_RETURN_NONE;
+}
+
+static PyObject *index_addsequence(Index *self, PyObject *args) {
+    const char *seq;
+    Py_ssize_t l;
+    if (!PyArg_ParseTuple(args, "s#", &seq, &l)) return nullptr;
+#ifndef SA64
+    if ((uint64_t)self->n + (uint64_t)(l + 1) + 1 > (uint64_t)INT32_MAX) {  // interface.c:61-68
+        PyErr_SetString(RevealError, "Total amount of sequence too large, use \"reveal <subcommand> --64\" to use 64 bit suffix arrays instead.");
+        return nullptr;
+    }
+#endif
+    int64_t s = self->n;
+    self->T->append(seq, (size_t)l);
+    self->T->push_back('$');
+    self->n += l + 1;
+    PyObject *intv = Py_BuildValue("(L,L)", (long long)s, (long long)(self->n - 1));
+    if (!intv) return nullptr;
+    PySet_Add(self->nodes, intv);
+    return intv;
+}
+
+// ---- construct (interface.c:160-291) ----------------------------------------------------------------------------------------
+static bool read_ints(const std::string &path, int64_t n, bool wide, std::vector<int32_t> &out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    out.resize((size_t)n);
+    bool ok = true;
+    if (wide) {
+        std::vector<int64_t> tmp((size_t)n);
+        ok = fread(tmp.data(), 8, (size_t)n, f) == (size_t)n;
+        for (int64_t i = 0; ok && i < n; i++) out[(size_t)i] = (int32_t)tmp[(size_t)i];
+    } else {
+        ok = fread(out.data(), 4, (size_t)n, f) == (size_t)n;
+    }
+    fclose(f);
+    return ok;
+}
+
+static PyObject *index_construct(Index *self, PyObject *args, PyObject *kwds) {
+    static const char *kwlist[] = {"rc", nullptr};
+    int rc = 0;
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "|i", (char **)kwlist, &rc)) return nullptr;
+    rc = rc == 1 ? 1 : 0;
+    if (self->mainidx) {
+        PyErr_SetString(RevealError, "construct() on a child index");
+        return nullptr;
+    }
+    if (self->n == 0) {
+        PyErr_SetString(RevealError, "No text to index.");  // interface.c:177-180
+        return nullptr;
+    }
+    if (rc && self->nsamples < 2) {
+        PyErr_SetString(RevealError, "rc=1 needs a second sample.");
+        return nullptr;
+    }
+    if (ensure_handle(self) != 0) return nullptr;
+    const int64_t *nsep = self->nsep->empty() ? nullptr : self->nsep->data();
+    int status;
+    if (!self->safile->empty()) {  // precomputed arrays (interface.c:224-231, 255-262): raw saidx_t / lcp_t
+#ifdef SA64
+        const bool wide = true;
+#else
+        const bool wide = false;
+#endif
+        std::vector<int32_t> sa, lcp;
+        if (!read_ints(*self->safile, self->n, wide, sa)) {
+            PyErr_Format(RevealError, "cannot read %lld suffix array entries from %s", (long long)self->n, self->safile->c_str());
+            return nullptr;
+        }
+        bool have_lcp = !self->lcpfile->empty();
+        if (have_lcp && !read_ints(*self->lcpfile, self->n, false, lcp)) {  // lcp_t is 32 bits in both builds
+            PyErr_Format(RevealError, "cannot read %lld lcp entries from %s", (long long)self->n, self->lcpfile->c_str());
+            return nullptr;
+        }
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_build_cached(self->h, (const uint8_t *)self->T->data(), self->n, nsep, self->nsamples, rc, sa.data(),
+                                       have_lcp ? lcp.data() : nullptr);
+        Py_END_ALLOW_THREADS;
+    } else if (!self->lcpfile->empty()) {
+        PyErr_SetString(RevealError, "an lcp file needs its suffix array file (sa=...) as well");
+        return nullptr;
+    } else {
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_build(self->h, (const uint8_t *)self->T->data(), self->n, nsep, self->nsamples, rc);
+        Py_END_ALLOW_THREADS;
+    }
+    if (fail_native(status) != 0) return nullptr;
+    self->rc = rc;
+    self->nT = self->n;
+    self->built = 1;
+    self->tdirty = rc;  // the reference reverse-complements its T in place (interface.c:168-172)
+    self->depth = 0;
+    if (self->cache == 1) {  // interface.c:182-189, 273-285
+        std::vector<int32_t> buf((size_t)self->n);
+        FILE *f = fopen(".reveal.t", "wb");
+        if (f) { fwrite(self->T->data(), 1, (size_t)self->n, f); fclose(f); }
+        if (g_api.rv_get_sa(self->h, buf.data(), 32) == 0 && (f = fopen(".reveal.sa", "wb"))) {
+#ifdef SA64
+            for (int64_t i = 0; i < self->n; i++) { int64_t v = buf[(size_t)i]; fwrite(&v, 8, 1, f); }
+#else
+            fwrite(buf.data(), 4, (size_t)self->n, f);
+#endif
+            fclose(f);
+        }
+        if (g_api.rv_get_lcp(self->h, buf.data(), 32) == 0 && (f = fopen(".reveal.lcp", "wb"))) {
+            fwrite(buf.data(), 4, (size_t)self->n, f);
+            fclose(f);
+        }
+    }
+    Py_RETURN_NONE;
+}
+
+static int need_built(Index *self, PyObject *exc, const char *msg) {
+    Index *r = root_of(self);
+    if (r->built) return 0;
+    PyErr_SetString(exc, msg);
+    return -1;
+}
+
+// ---- sweeps ------------------------------------------------------------------------------------------------------------------
+static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vector<int64_t> &mem, int64_t nrec, int64_t nmem, bool counts_are_sizes) {
+    PyObject *lst = PyList_New((Py_ssize_t)nrec);
+    if (!lst) return nullptr;
+    for (int64_t k = 0; k < nrec; k++) {
+        int64_t l = hdr[3 * k], cnt = hdr[3 * k + 1], first = hdr[3 * k + 2];
+        int64_t end = counts_are_sizes ? first + cnt : (k + 1 < nrec ? hdr[3 * (k + 1) + 2] : nmem);
+        PyObject *members = PyTuple_New((Py_ssize_t)(end - first));
+        for (int64_t x = first; x < end; x++)
+            PyTuple_SET_ITEM(members, (Py_ssize_t)(x - first), Py_BuildValue("(i,L)", (int)mem[2 * x], (long long)mem[2 * x + 1]));
+        PyObject *rec = Py_BuildValue("(L,i,N)", (long long)l, (int)cnt, members);  // reveal.c:497 / :353
+        PyList_SET_ITEM(lst, (Py_ssize_t)k, rec);
+    }
+    return lst;
+}
+
+static PyObject *index_getmums(Index *self, PyObject *args) {
+    int minl = 0;
+    if (!PyArg_ParseTuple(args, "i", &minl)) return nullptr;
+    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) {
+        if (self->mainidx) PyErr_SetString(RevealError, "getmums() on a child index");
+        return nullptr;
+    }
+    int64_t k = 0;
+    int status;
+    Py_BEGIN_ALLOW_THREADS;
+    status = g_api.rv_mums_pair_count(self->h, minl, 0, &k);
+    Py_END_ALLOW_THREADS;
+    if (fail_native(status) != 0) return nullptr;
+    std::vector<int64_t> rows((size_t)(3 * k + 3));
+    if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
+    PyObject *lst = PyList_New((Py_ssize_t)k);
+    for (int64_t i = 0; i < k; i++)  // (l, (a, b), rc): reveal.c:102-106
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, Py_BuildValue("(L,(L,L),i)", (long long)rows[3 * i], (long long)rows[3 * i + 1], (long long)rows[3 * i + 2], self->rc));
+    return lst;
+}
+
+static PyObject *multi_common(Index *self, PyObject *args, PyObject *kwds, bool mems) {
+    static const char *kwlist[] = {"minlength", "minn", nullptr};
+    int minl = 0, minn = 2;
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "|ii", (char **)kwlist, &minl, &minn)) return nullptr;
+    if (need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
+    int64_t nr = 0, nm = 0;
+    int status;
+    std::vector<int64_t> hdr, mem;
+    if (self->mainidx) {  // a child of the recursion: sweep its own arrays
+        if (mems) {
+            PyErr_SetString(RevealError, "getmultimems() on a child index is not supported");
+            return nullptr;
+        }
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_sub_mums_multi(self->sub, minl, minn, &nr, &nm);
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+        hdr.resize((size_t)(3 * nr + 3));
+        mem.resize((size_t)(2 * nm + 2));
+        if (fail_native(g_api.rv_sub_fetch(self->sub, hdr.data(), nr, mem.data(), nm)) != 0) return nullptr;
+    } else {
+        Py_BEGIN_ALLOW_THREADS;
+        status = mems ? g_api.rv_mems_multi_count(self->h, minl, minn, &nr, &nm) : g_api.rv_mums_multi_count(self->h, minl, minn, &nr, &nm);
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+        hdr.resize((size_t)(3 * nr + 3));
+        mem.resize((size_t)(2 * nm + 2));
+        if (fail_native(g_api.rv_mums_multi_fetch(self->h, hdr.data(), nr, mem.data(), nm)) != 0) return nullptr;
+    }
+    return multi_to_list(hdr, mem, nr, nm, !mems);
+}
+static PyObject *index_getmultimums(Index *self, PyObject *args, PyObject *kwds) { return multi_common(self, args, kwds, false); }
+static PyObject *index_getmultimems(Index *self, PyObject *args, PyObject *kwds) { return multi_common(self, args, kwds, true); }
+
+// ---- the recursion: `align` (interface.c:293-415) and the single-threaded `aligner` loop (reveal.c:731-1338) ---------------------
+static bool parse_intervals(PyObject *obj, std::vector<int64_t> &flat, int64_t &total, std::vector<int64_t> &begins) {
+    flat.clear();
+    begins.clear();
+    total = 0;
+    PyObject *iter = PyObject_GetIter(obj);
+    if (!iter) return false;
+    PyObject *tup;
+    while ((tup = PyIter_Next(iter))) {
+        long long b, e;
+        if (!PyArg_ParseTuple(tup, "LL", &b, &e)) {
+            Py_DECREF(tup);
+            Py_DECREF(iter);
+            return false;
+        }
+        flat.push_back(b);
+        flat.push_back(e);
+        begins.push_back(b);
+        total += e - b;
+        Py_DECREF(tup);
+    }
+    Py_DECREF(iter);
+    return !PyErr_Occurred();
+}
+
+// number of distinct samples among the interval starts (reveal.c:1026-1041)
+static int count_samples(Index *root, const std::vector<int64_t> &begins) {
+    if (begins.empty()) return 0;
+    if (root->nsamples > 2) {
+        std::vector<char> seen((size_t)root->nsamples, 0);
+        int c = 0;
+        for (int64_t b : begins) {
+            size_t lo = 0, hi = root->nsep->size();  // SO[begin] = number of separators before begin
+            while (lo < hi) {
+                size_t mid = (lo + hi) >> 1;
+                if ((*root->nsep)[mid] < b) lo = mid + 1; else hi = mid;
+            }
+            if (lo < seen.size() && !seen[lo]) { seen[lo] = 1; c++; }
+        }
+        return c;
+    }
+    int64_t nsep0 = (*root->nsep)[0];
+    int left = 0, right = 0;
+    for (int64_t b : begins) {
+        if (b < nsep0) left = 1;
+        else if (b > nsep0) right = 1;
+    }
+    return left + right;
+}
+
+static Index *new_child(Index *root, rv_sub *sub, int64_t n, int depth, int nsamples, PyObject *nodes, PyObject *left, PyObject *right, PyObject *skip) {
+    Index *c = (Index *)index_new(&IndexType, nullptr, nullptr);
+    if (!c) return nullptr;
+    c->sub = sub;
+    c->n = n;
+    c->nT = root->nT;
+    c->depth = depth;
+    c->nsamples = nsamples;
+    c->rc = root->rc;
+    c->built = 1;
+    Py_INCREF((PyObject *)root);
+    c->mainidx = root;
+    Py_INCREF(nodes);
+    Py_SETREF(c->nodes, nodes);
+    Py_INCREF(left);
+    Py_SETREF(c->left_node, left);
+    Py_INCREF(right);
+    Py_SETREF(c->right_node, right);
+    Py_INCREF(skip);
+    Py_SETREF(c->skipmums, skip);
+    return c;
+}
+
+// MUMs of a (sub)index in the shape the reference hands to mumpicker (reveal.c:802-829)
+static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
+    int64_t nr = 0, nm = 0;
+    int status;
+    if (root->nsamples > 2) {
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_sub_mums_multi(sub, minl, minn, &nr, &nm);
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+        std::vector<int64_t> hdr((size_t)(3 * nr + 3)), mem((size_t)(2 * nm + 2));
+        if (fail_native(g_api.rv_sub_fetch(sub, hdr.data(), nr, mem.data(), nm)) != 0) return nullptr;
+        return multi_to_list(hdr, mem, nr, nm, true);
+    }
+    Py_BEGIN_ALLOW_THREADS;
+    status = g_api.rv_sub_mums_pair(sub, minl, &nr);
+    Py_END_ALLOW_THREADS;
+    if (fail_native(status) != 0) return nullptr;
+    std::vector<int64_t> rows((size_t)(3 * nr + 3));
+    if (fail_native(g_api.rv_sub_fetch(sub, rows.data(), nr, nullptr, 0)) != 0) return nullptr;
+    PyObject *lst = PyList_New((Py_ssize_t)nr);
+    for (int64_t i = 0; i < nr; i++)  // (l, 2, ((0, a), (1, b))): reveal.c:167-169
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, Py_BuildValue("(L,i,((i,L),(i,L)))", (long long)rows[3 * i], 2, 0, (long long)rows[3 * i + 1], 1, (long long)rows[3 * i + 2]));
+    return lst;
+}
+
+static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
+    static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn", nullptr};  // interface.c:303
+    PyObject *mumpicker, *graphalign;
+    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0;
+    if (self->mainidx || !self->built) {
+        PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
+        return nullptr;
+    }
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiii", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn))
+        return nullptr;
+    // `threads` is accepted for signature compatibility: the reference serialises its callback sections on a global
+    // mutex (reveal.c:779-780) and the device work of a step is already parallel; steps run in the reference's LIFO order.
+    self->depth = 0;
+    if (self->sub) {
+        g_api.rv_sub_free(self->sub);
+        self->sub = nullptr;
+    }
+    if (fail_native(g_api.rv_sub_root(self->h, &self->sub)) != 0) return nullptr;
+    std::vector<Index *> queue;  // owned references
+    Py_INCREF((PyObject *)self);
+    queue.push_back(self);
+    bool ok = true;
+    PyObject *kw_minl = PyLong_FromLong(minl);
+    std::vector<int64_t> lead, trail, par, match, lead_b, trail_b, par_b, match_b;
+    while (ok && !queue.empty()) {
+        Index *idx = queue.back();  // LIFO (reveal.c:21-26)
+        queue.pop_back();
+        PyObject *pick = nullptr, *result = nullptr, *mums = nullptr;
+        do {
+            if (!PyCallable_Check(mumpicker)) {
+                PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
+                ok = false;
+                break;
+            }
+            int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
+            if (!precomputed) {
+                mums = extract_mums(self, idx->sub, minl, minn);
+                if (!mums) { ok = false; break; }
+            } else {
+                mums = idx->skipmums;
+                Py_INCREF(mums);
+            }
+            PyObject *cargs = Py_BuildValue("(OO)", mums, (PyObject *)idx);
+            PyObject *ckw = Py_BuildValue("{s:O,s:O}", "precomputed", precomputed ? Py_True : Py_False, "minlength", kw_minl);
+            pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
+            Py_DECREF(cargs);
+            Py_DECREF(ckw);
+            if (!pick) { ok = false; break; }
+            if (!PyTuple_Check(pick)) {
+                PyErr_SetString(RevealError, "**** call to mumpicker failed");
+                ok = false;
+                break;
+            }
+            if (PyTuple_Size(pick) == 0) break;  // no more MUMs in this sub-index
+            PyObject *mumobject, *skipleft, *skipright, *spd;
+            if (!PyArg_ParseTuple(pick, "OOO", &mumobject, &skipleft, &skipright)) { ok = false; break; }
+            long long mum_l;
+            int mum_n;
+            if (!PyArg_ParseTuple(mumobject, "LiO", &mum_l, &mum_n, &spd)) { ok = false; break; }
+            std::vector<int64_t> mum_sp((size_t)(mum_n > 0 ? mum_n : 1));
+            for (int i = 0; i < mum_n; i++) {
+                PyObject *tup = PySequence_GetItem(spd, i);
+                PyObject *pos = tup ? PySequence_GetItem(tup, 1) : nullptr;
+                mum_sp[(size_t)i] = pos ? PyLong_AsLongLong(pos) : 0;
+                Py_XDECREF(pos);
+                Py_XDECREF(tup);
+            }
+            if (PyErr_Occurred()) { ok = false; break; }
+            result = PyObject_CallFunctionObjArgs(graphalign, (PyObject *)idx, mumobject, nullptr);  // reveal.c:939
+            if (!result) { ok = false; break; }
+            if (result == Py_None) break;
+            if (!PyTuple_Check(result)) {
+                PyErr_SetString(RevealError, "**** call to graphalign failed");
+                ok = false;
+                break;
+            }
+            PyObject *leading, *trailing, *matching, *rest, *merged, *newleft, *newright;
+            if (!PyArg_ParseTuple(result, "OOOOOOO", &leading, &trailing, &matching, &rest, &merged, &newleft, &newright)) {
+                PyErr_Clear();  // the reference silently drops an unparsable result (reveal.c:987-999)
+                break;
+            }
+            int64_t leadn, trailn, parn, matchn;
+            if (!parse_intervals(leading, lead, leadn, lead_b) || !parse_intervals(trailing, trail, trailn, trail_b) ||
+                !parse_intervals(rest, par, parn, par_b) || !parse_intervals(matching, match, matchn, match_b)) {
+                ok = false;
+                break;
+            }
+            int32_t sweep[3] = {PyObject_Length(skipleft) == 0, PyObject_Length(skipright) == 0, 1};
+            rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+            int status;
+            Py_BEGIN_ALLOW_THREADS;
+            status = g_api.rv_sub_step(idx->sub, lead.data(), (int32_t)lead_b.size(), trail.data(), (int32_t)trail_b.size(), par.data(),
+                                       (int32_t)par_b.size(), mum_sp.data(), mum_n, mum_l, match.data(), (int32_t)match_b.size(), sweep, minl, minn, kids);
+            Py_END_ALLOW_THREADS;
+            if (fail_native(status) != 0) { ok = false; break; }
+            self->tdirty = 1;  // matched bases were lower-cased on the device (reveal.c:1230-1234)
+            const int depth = idx->depth + 1;
+            PyObject *empty = PyList_New(0);
+            Index *i_par = kids[2] ? new_child(self, kids[2], parn, depth, count_samples(self, par_b), rest, idx->left_node, idx->right_node, empty) : nullptr;
+            Index *i_lead = kids[0] ? new_child(self, kids[0], leadn, depth, count_samples(self, lead_b), leading, idx->left_node, newright, skipleft) : nullptr;
+            Index *i_trail = kids[1] ? new_child(self, kids[1], trailn, depth, count_samples(self, trail_b), trailing, newleft, idx->right_node, skipright) : nullptr;
+            Py_DECREF(empty);
+            if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
+            if (i_lead) queue.push_back(i_lead);
+            if (i_trail) queue.push_back(i_trail);
+        } while (0);
+        Py_XDECREF(mums);
+        Py_XDECREF(pick);
+        Py_XDECREF(result);
+        // the device view of a processed sub-index is released right away, like the reference frees SA/LCP
+        if (idx->sub) {
+            g_api.rv_sub_free(idx->sub);
+            idx->sub = nullptr;
+        }
+        Py_DECREF((PyObject *)idx);
+    }
+    for (Index *q : queue) {
+        if (q->sub) {
+            g_api.rv_sub_free(q->sub);
+            q->sub = nullptr;
+        }
+        Py_DECREF((PyObject *)q);
+    }
+    Py_DECREF(kw_minl);
+    if (!ok) return nullptr;
+    Py_RETURN_NONE;
+}
+
+// ---- copy (interface.c:432-470) -----------------------------------------------------------------------------------------------
+static PyObject *index_copy(Index *self, PyObject *) {
+    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
+    Index *c = (Index *)index_new(&IndexType, nullptr, nullptr);
+    if (!c) return nullptr;
+    if (self->tdirty) {
+        if (fail_native(g_api.rv_get_text(self->h, (uint8_t *)&(*self->T)[0])) != 0) { Py_DECREF(c); return nullptr; }
+        self->tdirty = 0;
+    }
+    *c->T = *self->T;
+    *c->nsep = *self->nsep;
+    c->n = self->n;
+    c->nT = self->nT;
+    c->nsamples = self->nsamples;
+    c->rc = self->rc;
+    Py_SETREF(c->samples, PySequence_List(self->samples));
+    Py_SETREF(c->nodes, PySet_New(self->nodes));
+    std::vector<int32_t> sa((size_t)self->n), lcp((size_t)self->n);
+    if (ensure_handle(c) != 0 || fail_native(g_api.rv_get_sa(self->h, sa.data(), 32)) != 0 || fail_native(g_api.rv_get_lcp(self->h, lcp.data(), 32)) != 0 ||
+        fail_native(g_api.rv_build_cached(c->h, (const uint8_t *)c->T->data(), c->n, c->nsep->empty() ? nullptr : c->nsep->data(), c->nsamples, 0, sa.data(),
+                                          lcp.data())) != 0) {
+        Py_DECREF(c);
+        return nullptr;
+    }
+    c->built = 1;
+    return (PyObject *)c;
+}
+
+// ---- getters (interface.c:539-785) ----------------------------------------------------------------------------------------------
+static PyObject *ints_to_list(const std::vector<int32_t> &v, bool as_unsigned) {
+    PyObject *lst = PyList_New((Py_ssize_t)v.size());
+    if (!lst) return nullptr;
+    for (size_t i = 0; i < v.size(); i++)
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, as_unsigned ? PyLong_FromUnsignedLong((uint32_t)v[i]) : PyLong_FromLong(v[i]));
+    return lst;
+}
+
+static PyObject *get_array(Index *self, int which) {  // 0 SA, 1 SAi, 2 LCP
+    if (need_built(self, PyExc_TypeError, "Index not yet constructed.") != 0) return nullptr;
+    Index *r = root_of(self);
+    std::vector<int32_t> v;
+    int status;
+    if (self->mainidx && which != 1) {
+        if (!self->sub) {
+            PyErr_SetString(PyExc_TypeError, "Index not yet constructed.");  // SA/LCP of a processed sub-index are freed
+            return nullptr;
+        }
+        v.resize((size_t)self->n);
+        status = g_api.rv_sub_get(self->sub, which == 0 ? 0 : 1, v.data());
+    } else {
+        v.resize((size_t)r->n);
+        status = which == 0 ? g_api.rv_get_sa(r->h, v.data(), 32) : (which == 1 ? g_api.rv_get_sai(r->h, v.data(), 32) : g_api.rv_get_lcp(r->h, v.data(), 32));
+    }
+    if (fail_native(status) != 0) return nullptr;
+#ifdef SA64
+    return ints_to_list(v, which == 2);  // lcp_t is unsigned in the 64-bit build (reveal.h:8-9)
+#else
+    return ints_to_list(v, false);
+#endif
+}
+static PyObject *get_SA(Index *self, void *) { return get_array(self, 0); }
+static PyObject *get_SAi(Index *self, void *) { return get_array(self, 1); }
+static PyObject *get_LCP(Index *self, void *) { return get_array(self, 2); }
+
+static PyObject *get_SO(Index *self, void *) {
+    Index *r = root_of(self);
+    if (!r->built || r->nsamples <= 2) {
+        PyErr_SetString(PyExc_TypeError, "SO not available.");  // interface.c:575-579
+        return nullptr;
+    }
+    std::vector<uint16_t> v((size_t)r->n);
+    if (fail_native(g_api.rv_get_so(r->h, v.data())) != 0) return nullptr;
+    PyObject *lst = PyList_New((Py_ssize_t)v.size());
+    for (size_t i = 0; i < v.size(); i++) PyList_SET_ITEM(lst, (Py_ssize_t)i, PyLong_FromLong(v[i]));
+    return lst;
+}
+
+static PyObject *get_T(Index *self, void *) {
+    Index *r = root_of(self);
+    if (r->built && r->tdirty) {  // rc or align changed the device text: refresh the host copy
+        if (fail_native(g_api.rv_get_text(r->h, (uint8_t *)&(*r->T)[0])) != 0) return nullptr;
+        r->tdirty = 0;
+    }
+    return PyUnicode_DecodeLatin1(r->T->data(), (Py_ssize_t)r->T->size(), nullptr);
+}
+
+static PyObject *get_n(Index *self, void *) { return PyLong_FromLongLong(self->n); }
+static PyObject *get_depth(Index *self, void *) { return PyLong_FromLong(self->depth); }
+static PyObject *get_nsamples(Index *self, void *) { return PyLong_FromLong(self->nsamples); }
+static PyObject *get_samples(Index *self, void *) { PyObject *o = root_of(self)->samples; Py_INCREF(o); return o; }
+static PyObject *get_nodes(Index *self, void *) { Py_INCREF(self->nodes); return self->nodes; }
+static PyObject *get_leftnode(Index *self, void *) { Py_INCREF(self->left_node); return self->left_node; }
+static PyObject *get_rightnode(Index *self, void *) { Py_INCREF(self->right_node); return self->right_node; }
+static PyObject *get_skipmums(Index *self, void *) { Py_INCREF(self->skipmums); return self->skipmums; }
+static PyObject *get_nsep(Index *self, void *) {
+    Index *r = root_of(self);
+    PyObject *lst = PyList_New((Py_ssize_t)r->nsep->size());
+    for (size_t i = 0; i < r->nsep->size(); i++) PyList_SET_ITEM(lst, (Py_ssize_t)i, PyLong_FromLongLong((*r->nsep)[i]));
+    return lst;
+}
+static PyObject *get_main(Index *self, void *) {
+    PyObject *o = (PyObject *)root_of(self);
+    Py_INCREF(o);
+    return o;
+}
+
+static PyObject *index_times(Index *self, PyObject *) {
+    Index *r = root_of(self);
+    if (!r->h) Py_RETURN_NONE;
+    rv_times t;
+    if (fail_native(g_api.rv_get_times(r->h, &t)) != 0) return nullptr;
+    return Py_BuildValue("{s:f,s:f,s:f,s:f,s:f,s:f,s:i,s:i,s:L}", "h2d_ms", t.h2d_ms, "pack_ms", t.pack_ms, "sa_ms", t.sa_ms, "lcp_ms", t.lcp_ms, "so_ms",
+                         t.so_ms, "total_ms", t.total_ms, "sa_rounds", t.sa_rounds, "launches", t.launches, "sa_sorted_items", (long long)t.sa_sorted_items);
+}
+
+static PyObject *index_reduce(Index *, PyObject *) { Py_RETURN_NONE; }  // interface.c:417-422
+
+static PyMethodDef index_methods[] = {
+    {"align", (PyCFunction)index_align, METH_VARARGS | METH_KEYWORDS, nullptr},
+    {"copy", (PyCFunction)index_copy, METH_NOARGS, nullptr},
+    {"addsample", (PyCFunction)index_addsample, METH_VARARGS, nullptr},
+    {"addsequence", (PyCFunction)index_addsequence, METH_VARARGS, nullptr},
+    {"construct", (PyCFunction)index_construct, METH_VARARGS | METH_KEYWORDS, nullptr},
+    {"getmultimums", (PyCFunction)index_getmultimums, METH_VARARGS | METH_KEYWORDS, nullptr},
+    {"getmultimems", (PyCFunction)index_getmultimems, METH_VARARGS | METH_KEYWORDS, nullptr},
+    {"getmums", (PyCFunction)index_getmums, METH_VARARGS, nullptr},
+    {"times", (PyCFunction)index_times, METH_NOARGS, "device milliseconds of the last construct() per phase"},
+    {"__reduce__", (PyCFunction)index_reduce, METH_NOARGS, "For pickle"},
+    {nullptr, nullptr, 0, nullptr}};
+
+static PyGetSetDef index_getset[] = {
+    {"n", (getter)get_n, nullptr, "Number of characters in the index.", nullptr},
+    {"depth", (getter)get_depth, nullptr, "Depth of the index within the recursion tree.", nullptr},
+    {"nsamples", (getter)get_nsamples, nullptr, "Number of samples in the index.", nullptr},
+    {"samples", (getter)get_samples, nullptr, "Sample/file names used in the index.", nullptr},
+    {"nodes", (getter)get_nodes, nullptr, "The set of intervals (nodes) associated with the index.", nullptr},
+    {"leftnode", (getter)get_leftnode, nullptr, "Interval of the node bounding the index on the left.", nullptr},
+    {"rightnode", (getter)get_rightnode, nullptr, "Interval of the node bounding the index on the right.", nullptr},
+    {"skipmums", (getter)get_skipmums, nullptr, "Precomputed MUMs handed down by the mumpicker.", nullptr},
+    {"nsep", (getter)get_nsep, nullptr, "Positions of the sentinels that separate the samples.", nullptr},
+    {"SA", (getter)get_SA, nullptr, "The suffix array of the concatenation of input texts.", nullptr},
+    {"SAi", (getter)get_SAi, nullptr, "The inverse of the suffix array.", nullptr},
+    {"SO", (getter)get_SO, nullptr, "Sample id of every text position (more than two samples).", nullptr},
+    {"LCP", (getter)get_LCP, nullptr, "Longest common prefix of consecutive suffixes.", nullptr},
+    {"T", (getter)get_T, nullptr, "The concatenation of the input texts.", nullptr},
+    {"main", (getter)get_main, nullptr, "The root index.", nullptr},
+    {nullptr, nullptr, nullptr, nullptr, nullptr}};
+
+// ---- module -------------------------------------------------------------------------------------------------------------------------
+static PyObject *mod_load(PyObject *, PyObject *args) {
+    const char *path;
+    if (!PyArg_ParseTuple(args, "s", &path)) return nullptr;
+    if (!load_library(path)) return nullptr;
+    Py_RETURN_NONE;
+}
+static PyObject *mod_library(PyObject *, PyObject *) {
+    if (!g_api.handle) Py_RETURN_NONE;
+    return Py_BuildValue("(s,s)", g_api.path.c_str(), g_api.rv_version());
+}
+
+static PyMethodDef module_methods[] = {
+    {"_load", mod_load, METH_VARARGS, "Load a shared library exporting the C-ABI of include/reveal_b200.h (tests inject the emulated kernels)."},
+    {"_library", mod_library, METH_NOARGS, "(path, version) of the loaded C-ABI library."},
+    {nullptr, nullptr, 0, nullptr}};
+
+static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, MODNAME,
+                                       "REVEAL index with the build, the MUM sweeps and the recursion steps on a B200 (libreveal_b200.so).", -1,
+                                       module_methods};
+
+PyMODINIT_FUNC MODINIT(void) {
+    IndexType.tp_name = MODNAME ".index";
+    IndexType.tp_basicsize = sizeof(Index);
+    IndexType.tp_flags = Py_TPFLAGS_DEFAULT | Py_TPFLAGS_BASETYPE;
+    IndexType.tp_doc = "index objects";
+    IndexType.tp_new = index_new;
+    IndexType.tp_init = (initproc)index_init;
+    IndexType.tp_dealloc = (destructor)index_dealloc;
+    IndexType.tp_methods = index_methods;
+    IndexType.tp_getset = index_getset;
+    if (PyType_Ready(&IndexType) < 0) return nullptr;
+    PyObject *m = PyModule_Create(&moduledef);
+    if (!m) return nullptr;
+    Py_INCREF(&IndexType);
+    PyModule_AddObject(m, "index", (PyObject *)&IndexType);
+    RevealError = PyErr_NewException(MODNAME ".error", nullptr, nullptr);
+    Py_INCREF(RevealError);
+    PyModule_AddObject(m, "error", RevealError);
+    // default library: libreveal_b200.so next to this module
+    Dl_info info;
+    if (dladdr((void *)&MODINIT, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t slash = p.rfind('/');
+        p = (slash == std::string::npos ? std::string(".") : p.substr(0, slash)) + "/libreveal_b200.so";
+        if (!load_library(p.c_str())) PyErr_Clear();  // import succeeds; every call raises until a library is loaded
+    }
+    return m;
+}

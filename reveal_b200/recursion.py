@@ -136,7 +136,7 @@ def _extract(main, sub, minl, minn):
 
 
 def align(main, mumpicker, graphalign, threads=0, wpen=0, wscore=0, minl=0, minn=0):
-    from .reveallib import error
+    from .reveallib_ctypes import error
     minl = int(minl)
     minn = int(minn)
     L = main._lib()

@@ -1,6 +1,7 @@
-"""`reveallib` -- drop-in for the reference's CPython extension module of the same
-name (reveallib/interface.c + reveal.c), with the index build and the MUM sweeps
-running as sm_100a CUDA through libreveal_b200.so.
+"""`reveallib_ctypes` -- the ctypes twin of the compiled extension `reveal_b200.reveallib`
+(csrc/ext/reveallib_module.cpp): the same mirror of the reference's CPython extension
+(reveallib/interface.c + reveal.c) written in Python over the C-ABI, kept as the readable
+binding and for environments without a C++ compiler.
 
 Mirrors the `index` type of the reference (interface.c:841-881):
 

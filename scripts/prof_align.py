@@ -1,7 +1,7 @@
 import cProfile, pstats, sys, os, io
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 from align_callbacks import make_callbacks
-from reveal_b200 import reveallib, synth
+from reveal_b200 import reveallib_ctypes as reveallib, synth
 gs = synth.genomes(2, 500000, seed=1)
 idx = reveallib.index()
 for k, g in enumerate(gs):

@@ -37,12 +37,35 @@ def emu_lib():
     return _native.bind(os.path.join(ROOT, "tests", "emu", "_build", "libreveal_emu.so"))
 
 
-@pytest.fixture()
-def emu_reveallib(emu_lib, monkeypatch):
-    """reveal_b200.reveallib with the emulated kernels injected in place of the CUDA library."""
-    from reveal_b200 import _native, reveallib
-    monkeypatch.setattr(_native, "_lib", emu_lib)
-    return reveallib
+class _Impl(object):
+    """One implementation of the drop-in surface: .index / .error (32-bit module) and .index64."""
+
+    def __init__(self, name, mod32, mod64):
+        self.name, self.index, self.error, self.index64, self.mod32, self.mod64 = name, mod32.index, mod32.error, mod64.index, mod32, mod64
+
+
+@pytest.fixture(params=["ext", "ctypes"])
+def emu_reveallib(request, emu_lib, monkeypatch):
+    """The drop-in `index` type with the emulated kernels injected in place of the CUDA library, once as the compiled
+    CPython extension (reveal_b200.reveallib, csrc/ext/reveallib_module.cpp) and once as its ctypes twin."""
+    emu_path = os.path.join(ROOT, "tests", "emu", "_build", "libreveal_emu.so")
+    if request.param == "ctypes":
+        from reveal_b200 import _native, reveallib64_ctypes, reveallib_ctypes
+        monkeypatch.setattr(_native, "_lib", emu_lib)
+        yield _Impl("ctypes", reveallib_ctypes, reveallib64_ctypes)
+        return
+    from reveal_b200 import build
+    build.build_extension()
+    from reveal_b200 import reveallib, reveallib64
+    reveallib._load(emu_path)
+    reveallib64._load(emu_path)
+    try:
+        yield _Impl("ext", reveallib, reveallib64)
+    finally:
+        product = os.path.join(ROOT, "reveal_b200", "libreveal_b200.so")
+        if os.path.exists(product):
+            reveallib._load(product)
+            reveallib64._load(product)
 
 
 @pytest.fixture(scope="session")

@@ -43,3 +43,18 @@ def test_product_loader_never_points_at_the_emulation():
     assert _native.LIB_PATH.endswith(os.path.join("reveal_b200", "libreveal_b200.so"))
     src = open(os.path.join(ROOT, "reveal_b200", "_native.py")).read()
     assert "emu" not in src and "oracle" not in src
+
+
+def test_extension_modules_build_and_import():
+    """The compiled drop-in modules (csrc/ext/reveallib_module.cpp) build, import and expose the reference's surface."""
+    outs = build.build_extension()
+    assert len(outs) == 2 and all(os.path.exists(o) for o in outs)
+    from reveal_b200 import reveallib, reveallib64
+    for mod in (reveallib, reveallib64):
+        for name in ("addsample", "addsequence", "construct", "align", "getmums", "getmultimums", "getmultimems", "copy",
+                     "n", "depth", "nsamples", "samples", "nodes", "leftnode", "rightnode", "nsep", "SA", "SAi", "SO", "LCP", "T"):
+            assert hasattr(mod.index, name), name
+        assert issubclass(mod.error, Exception)
+        idx = mod.index(sa="", lcp="", cache=0)
+        idx.addsample("a")
+        assert idx.addsequence("ACGT") == (0, 4) and idx.n == 5 and idx.nsamples == 1
