@@ -350,15 +350,18 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     RV_LAUNCH(rs_scan_kernel, plan.npass, RS_BINS, 0, st.s, ghist, gbase);
     st.launches += 2;
     const size_t smem = (size_t)RS_TILE * (sizeof(KeyT) + 4);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};  // per device: a process may drive several GPUs (rv_set_device)
+    int dev = 0;
+    RV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr_done[dev]) {
         auto kfn = rs_pass_kernel<KeyT, true, false>;
         auto kft = rs_pass_kernel<KeyT, true, true>;
         (void)kfn;
         (void)kft;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done[dev] = true;
     }
     bool in0 = true;
     RV_TRY(prof_begin(st));
