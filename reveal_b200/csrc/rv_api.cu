@@ -63,6 +63,7 @@ struct rv_index {
     rv_times times;
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
     void *pool = nullptr;  // DevPool of rv_split.cu (children of the recursion)
+    int device = 0;        // the GPU this handle lives on (the current device at rv_index_create)
 };
 
 extern "C" void rv_pool_destroy(void *pool);
@@ -101,6 +102,7 @@ int rv_index_create(rv_index **out, void *stream) {
     }
     rv_index *h = new rv_index();
     memset(&h->times, 0, sizeof h->times);
+    cudaGetDevice(&h->device);
     if (stream) {
         h->st.s = (cudaStream_t)stream;
     } else {
@@ -165,6 +167,7 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
         set_error("rv_build: rc=1 needs two samples and a non-empty first sample");
         return RV_ERR_ARG;
     }
+    RV_CUDA(cudaSetDevice(h->device));
     h->built = false;
     h->last_kind = 0;
     h->n = n;
@@ -283,6 +286,7 @@ int rv_get_profile(rv_index *h, rv_kernel_profile *out) {
 static int need_built(const rv_index *h) {
     if (!h) { set_error("null index handle"); return RV_ERR_ARG; }
     if (!h->built) { set_error("index not constructed"); return RV_ERR_STATE; }
+    RV_CUDA(cudaSetDevice(h->device));  // every entry point passes through here or build_common: stay on the handle's GPU
     return RV_OK;
 }
 
