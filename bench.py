@@ -209,18 +209,45 @@ def run_ours(args, rank, world, local_rank):
             _native.check(L, L.rv_mums_multi_count(h, MINL, MINN, ctypes.byref(cnt), ctypes.byref(nmem)))
         return cnt.value
 
+    def result_rows():
+        """Rows of the last sweep on the host (pair rows, or the hdr rows of a multi sweep)."""
+        k = cnt.value
+        out = np.empty((k, 3), np.int64)
+        if ns == 2:
+            _native.check(L, L.rv_mums_pair_fetch(h, out.ctypes.data, k))
+        else:
+            mem = np.empty((nmem.value, 2), np.int64)
+            _native.check(L, L.rv_mums_multi_fetch(h, out.ctypes.data, k, mem.ctypes.data, nmem.value))
+        return out
+
     gatherer = {}
 
     def gather_results():
-        """N > 1: MUM records of every rank to rank 0 over NCCL (the only collective on the path): one gather of
-        fixed-capacity blocks per step, no host synchronisation (reveal_b200.shard.FixedGather)."""
+        """N > 1: MUM records of every rank to rank 0, no host synchronisation.  Preferred transport: mapped peer
+        blocks (reveal_b200.shard.PeerGather) -- the pack kernel stores each rank's rows straight into rank 0's HBM
+        over NVLink / NVSwitch, nothing on the data path is a collective.  If the box cannot map peer memory every
+        rank falls back together to one NCCL gather of fixed-capacity blocks per step (shard.FixedGather)."""
         if world == 1:
             return
         from reveal_b200 import shard
         with torch.cuda.stream(stream):  # same stream as the sweep kernels that produced the rows
             if "g" not in gatherer:
-                gatherer["g"] = shard.FixedGather(max(4096, 2 * cnt.value), 3, dev)
+                cap = max(4096, 2 * cnt.value)
+                try:
+                    if os.environ.get("RV_BENCH_GATHER", "peer") != "peer":
+                        raise RuntimeError("RV_BENCH_GATHER asks for the NCCL gather")
+                    gatherer["g"] = shard.PeerGather(cap, 3, L, dev, depth=2)
+                    gatherer["kind"] = "peer"
+                except RuntimeError as e:
+                    if rank == 0:
+                        print("[bench] peer blocks not used (%s): NCCL gather" % e, file=sys.stderr)
+                    gatherer["g"] = shard.FixedGather(cap, 3, dev)
+                    gatherer["kind"] = "nccl"
             g = gatherer["g"]
+            if gatherer["kind"] == "peer":
+                _native.check(L, L.rv_result_pack_device(h, ctypes.c_void_p(g.slot()), g.cap))  # count + rows into rank 0's ring
+                g.advance()
+                return
             send = g.next_send()
             _native.check(L, L.rv_result_pack_device(h, ctypes.c_void_p(send.data_ptr()), g.cap))  # count + rows, async on `stream`
             g.submit()            # enqueued on the communication stream: overlaps the next step's index build
@@ -253,8 +280,6 @@ def run_ours(args, rank, world, local_rank):
         return k, d2h
 
     def barrier():
-        if "g" in gatherer:
-            gatherer["g"].drain()  # the helper thread's gathers are issued before this thread issues a collective
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -276,16 +301,31 @@ def run_ours(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         nm = step_resident()
-        if world > 1 and _ == args.steps - 1:
+        if world > 1 and _ == args.steps - 1 and gatherer["kind"] == "nccl":
             with torch.cuda.stream(stream):
                 gatherer["g"].wait_all()  # the last step's gather is inside the timed region
+            # (peer blocks: the pack kernel's stores ARE the transfer; they are complete when e1 is reached)
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
     if world > 1:
-        parts = gatherer["g"].check()  # rank 0: every rank's rows of the last step arrived (raises on overflow)
-        if rank == 0:
-            assert len(parts) == world and all(len(x) > 0 for x in parts)
+        # rank 0: every rank's rows of the last step arrived (raises on overflow / on a block that is not the last pack's)
+        if gatherer["kind"] == "peer":
+            parts = gatherer["g"].check(expect_seq=gatherer["g"].step)
+            mine = result_rows()  # every rank: (row count, wrapping sum of its rows) of the last step, to compare on rank 0
+            sig = torch.tensor([mine.shape[0], int(mine.sum(dtype=np.int64))], dtype=torch.int64, device=dev)
+            sigs = [torch.zeros_like(sig) for _ in range(world)]
+            dist.all_gather(sigs, sig)
+            if rank == 0:
+                assert len(parts) == world and all(len(rows) > 0 for rows, _ in parts)
+                assert np.array_equal(parts[0][0], mine), "rank 0's own block differs from its sweep result"
+                for r in range(world):
+                    got = [parts[r][0].shape[0], int(parts[r][0].sum(dtype=np.int64))]
+                    assert got == sigs[r].tolist(), "rank %d: rows in rank 0's ring differ from what the rank produced" % r
+        else:
+            parts = gatherer["g"].check()
+            if rank == 0:
+                assert len(parts) == world and all(len(x) > 0 for x in parts)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     gather_ms = sum(a.elapsed_time(b) for a, b in gather_evs[-args.steps:]) / args.steps if gather_evs else 0.0
     prof = _native.KernelProfile()
@@ -306,8 +346,6 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.summary() if sampler else None
 
-    if "g" in gatherer:
-        gatherer["g"].drain()
     tmax = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     ntot = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -336,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "bases_per_step_per_gpu": n, "mums_per_step": nm, "minl": MINL, "minn": MINN,
-                           "l2": "flushed between timed steps (256 MiB write)", "sharding": "independent index build per rank; NCCL gather of MUM records" if world > 1 else "single GPU"},
+                           "l2": "flushed between timed steps (256 MiB write)", "sharding": ("independent index build per rank; MUM records to rank 0 through " + ("mapped peer blocks (NVLink stores, no collective)" if gatherer.get("kind") == "peer" else "one NCCL gather per step")) if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n + 8 * len(nsep)), "d2h_bytes_per_step": int(d2h + 32),
                         "ms_per_step": e2e_ms_max / args.steps},
                 "gpu_launches": launches, "gather_ms_per_step": gather_ms,

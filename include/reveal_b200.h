@@ -125,9 +125,24 @@ int rv_mums_multi_fetch(rv_index *idx, int64_t *hdr, int64_t hdr_cap, int64_t *m
  * as int64 pairs; NULL when empty), for callers that gather over NCCL. */
 int rv_result_device(rv_index *idx, const int64_t **d_rows, int64_t *nrows, const int64_t **d_members, int64_t *nmembers);
 
-/* Packs the last sweep's rows for a fixed-capacity gather: d_dst[0] = row count, d_dst[3..] = the first
- * min(count, cap_rows) rows (int64 triples), asynchronously on the handle's stream. */
+/* Packs the last sweep's rows for a fixed-capacity gather: d_dst[0] = row count, d_dst[1] = the number of packs
+ * done on this handle so far (a sequence number the collector can check), d_dst[3..] = the first
+ * min(count, cap_rows) rows (int64 triples); one kernel, asynchronous on the handle's stream.  d_dst may be local
+ * memory or a mapped peer block (rv_peer_open). */
 int rv_result_pack_device(rv_index *idx, int64_t *d_dst, int64_t cap_rows);
+
+/* Peer blocks (multi-GPU, one box): device memory that the collecting rank allocates and the other ranks (one
+ * process per GPU) map through CUDA IPC, so that rv_result_pack_device can write a rank's rows straight into the
+ * collector's HBM over NVLink / NVSwitch -- no collective and no rendezvous on the data path
+ * (reveal_b200/shard.py:PeerGather).  `handle` is RV_PEER_HANDLE_BYTES opaque bytes to hand to the other
+ * processes; rv_peer_open maps it (in another process than the allocating one), rv_peer_close unmaps,
+ * rv_peer_free releases the allocation, rv_peer_read copies from a peer block to host memory (synchronous). */
+#define RV_PEER_HANDLE_BYTES 64
+int rv_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle);
+int rv_peer_open(const uint8_t *handle, void **d_ptr);
+int rv_peer_close(void *d_ptr);
+int rv_peer_free(void *d_ptr);
+int rv_peer_read(const void *d_src, void *host_dst, int64_t bytes);
 
 /* Sweeps over caller-supplied device arrays of a SUB-index that shares the
  * main text (the children of reveal.c:582-664 split; RevealIndex.main): the

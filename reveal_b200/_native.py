@@ -72,6 +72,11 @@ SIGNATURES = {
     "rv_rec_stats": (ctypes.c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_double)]),
     "rv_sub_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_result_pack_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
+    "rv_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
+    "rv_peer_open": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "rv_peer_close": (ctypes.c_int, [c_vp]),
+    "rv_peer_free": (ctypes.c_int, [c_vp]),
+    "rv_peer_read": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_sweep_pair_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_sweep_multi_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

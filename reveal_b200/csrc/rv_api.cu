@@ -1,6 +1,13 @@
 // rv_api.cu -- the C-ABI of libreveal_b200.so (see include/reveal_b200.h for the
 // reference interface each entry point replaces).
 #include "../../include/reveal_b200.h"
+#ifdef RV_EMU  // peer blocks of the emulated build: POSIX shared memory
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
+#include <string>
+#endif
 #include "rv_internal.h"
 #include "rv_sweep.h"
 #include <stdarg.h>
@@ -42,6 +49,13 @@ void Arena::release() {
 
 using namespace rv;
 
+// Header row (count, sequence number of this pack on the handle, 0) followed by the first m result rows.
+__global__ void pack_rows_kernel(i64 *__restrict__ dst, const i64 *__restrict__ rows, i64 m, i64 count, i64 seq) {
+    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 3 * (m + 1)) return;
+    dst[w] = w >= 3 ? rows[w - 3] : (w == 0 ? count : (w == 1 ? seq : 0));
+}
+
 struct rv_index {
     Stream st;
     bool own_stream = false;
@@ -59,6 +73,7 @@ struct rv_index {
     // last sweep
     int last_kind = 0;  // 1 pair, 2 multi
     i64 last_rec = 0, last_mem = 0;
+    i64 pack_seq = 0;      // number of rv_result_pack_device calls on this handle (header word 1 of a packed block)
     i64 *d_rows = nullptr, *d_members = nullptr;
     rv_times times;
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
@@ -518,13 +533,110 @@ int rv_result_device(rv_index *h, const int64_t **d_rows, int64_t *nrows, const 
 }
 
 int rv_result_pack_device(rv_index *h, int64_t *d_dst, int64_t cap_rows) {
-    if (!h || h->last_kind == 0 || !d_dst) { set_error("no sweep result"); return RV_ERR_STATE; }
-    // the count travels through the pinned scratch word so that the copy below can stay asynchronous
-    int64_t *cnt = (int64_t *)(h->st.pinned + 300);
-    *cnt = h->last_rec;
-    RV_CUDA(cudaMemcpyAsync(d_dst, cnt, 8, cudaMemcpyHostToDevice, h->st.s));
+    if (!h || h->last_kind == 0 || !d_dst || cap_rows < 0) { set_error("no sweep result"); return RV_ERR_STATE; }
+    RV_CUDA(cudaSetDevice(h->device));
     i64 m = h->last_rec < cap_rows ? h->last_rec : cap_rows;
-    if (m > 0) RV_CUDA(cudaMemcpyAsync(d_dst + 3, h->d_rows, (size_t)m * 24, cudaMemcpyDeviceToDevice, h->st.s));
+    i64 words = 3 * (m + 1);
+    h->pack_seq++;
+    // one launch: header row + rows.  d_dst may be a peer block (rv_peer_open): plain stores over NVLink
+    RV_LAUNCH(pack_rows_kernel, (unsigned)((words + 255) / 256), 256, 0, h->st.s, d_dst, (const i64 *)h->d_rows, m, (i64)h->last_rec,
+              (i64)h->pack_seq);
+    RV_KCHECK();
+    h->st.launches++;
+    h->st.launches_total++;
+    return RV_OK;
+}
+
+// ---- peer blocks: memory of the collecting rank mapped by the other processes of the box ------------------
+#ifdef RV_EMU
+}  // extern "C"
+namespace rv {
+// The emulated build has no CUDA IPC: POSIX shared memory stands in, so that the host-side protocol of
+// PeerGather (handle exchange, block offsets, reuse) runs between real processes in the CPU tests.
+struct EmuPeer { std::string name; size_t bytes; bool owner; };
+static std::map<void *, EmuPeer> g_emu_peers;
+static int emu_map(const char *name, size_t bytes, bool create, void **out) {
+    int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) { set_error("shm_open(%s) failed", name); return RV_ERR_CUDA; }
+    if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); set_error("ftruncate failed"); return RV_ERR_NOMEM; }
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { if (create) shm_unlink(name); set_error("mmap failed"); return RV_ERR_NOMEM; }
+    g_emu_peers[p] = EmuPeer{name, bytes, create};
+    *out = p;
+    return RV_OK;
+}
+}  // namespace rv
+extern "C" {
+int rv_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle) {
+    if (bytes <= 0 || !d_ptr || !handle) return RV_ERR_ARG;
+    static int serial = 0;
+    memset(handle, 0, RV_PEER_HANDLE_BYTES);
+    snprintf((char *)handle, 48, "/rvemu_%d_%d", (int)getpid(), serial++);
+    memcpy(handle + 48, &bytes, 8);
+    return emu_map((const char *)handle, (size_t)bytes, true, d_ptr);
+}
+int rv_peer_open(const uint8_t *handle, void **d_ptr) {
+    if (!handle || !d_ptr) return RV_ERR_ARG;
+    int64_t bytes = 0;
+    memcpy(&bytes, handle + 48, 8);
+    char name[49];
+    memcpy(name, handle, 48);
+    name[48] = 0;
+    if (bytes <= 0 || name[0] != '/') { set_error("rv_peer_open: not a peer handle"); return RV_ERR_ARG; }
+    return emu_map(name, (size_t)bytes, false, d_ptr);
+}
+static int emu_unmap(void *p, bool owner) {
+    auto it = g_emu_peers.find(p);
+    if (it == g_emu_peers.end() || it->second.owner != owner) { set_error("not a peer block of this process"); return RV_ERR_ARG; }
+    munmap(p, it->second.bytes);
+    if (owner) shm_unlink(it->second.name.c_str());
+    g_emu_peers.erase(it);
+    return RV_OK;
+}
+int rv_peer_close(void *d_ptr) { return emu_unmap(d_ptr, false); }
+int rv_peer_free(void *d_ptr) { return emu_unmap(d_ptr, true); }
+#else
+int rv_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= RV_PEER_HANDLE_BYTES, "handle size");
+    if (bytes <= 0 || !d_ptr || !handle) return RV_ERR_ARG;
+    *d_ptr = nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);  // plain cudaMalloc: IPC handles cannot name pool allocations
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e)); return RV_ERR_NOMEM; }
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, p);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(p); set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return RV_ERR_CUDA; }
+    memset(handle, 0, RV_PEER_HANDLE_BYTES);
+    memcpy(handle, &hd, sizeof(hd));
+    *d_ptr = p;
+    return RV_OK;
+}
+int rv_peer_open(const uint8_t *handle, void **d_ptr) {
+    if (!handle || !d_ptr) return RV_ERR_ARG;
+    *d_ptr = nullptr;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    // maps the allocation into this process and enables peer access to its device (NVLink / NVSwitch) on first use
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); *d_ptr = nullptr; set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return RV_ERR_CUDA; }
+    return RV_OK;
+}
+int rv_peer_close(void *d_ptr) {
+    if (!d_ptr) return RV_ERR_ARG;
+    RV_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RV_OK;
+}
+int rv_peer_free(void *d_ptr) {
+    if (!d_ptr) return RV_ERR_ARG;
+    RV_CUDA(cudaFree(d_ptr));
+    return RV_OK;
+}
+#endif
+int rv_peer_read(const void *d_src, void *host_dst, int64_t bytes) {
+    if (!d_src || !host_dst || bytes < 0) return RV_ERR_ARG;
+    if (bytes) RV_CUDA(cudaMemcpy(host_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return RV_OK;
 }
 

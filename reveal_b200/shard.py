@@ -141,6 +141,108 @@ class FixedGather(object):
         return out
 
 
+class PeerGather(object):
+    """One-sided variant of FixedGather for ranks that share one box: `dst` allocates `depth` rings of one
+    fixed-capacity block per rank in ITS device memory, every other rank maps that allocation (CUDA IPC, C-ABI
+    rv_peer_*), and rv_result_pack_device(handle, slot(), cap) writes a rank's block straight into dst's HBM over
+    NVLink / NVSwitch.  Nothing on the data path is a collective: no rendezvous between ranks, no NCCL launch, no
+    host work besides the pack launch itself -- ranks only meet in the constructor, in check() and in close().
+
+    A block written at step s is overwritten at step s + depth: dst has to check() at least every `depth` steps if
+    it wants every step's rows (a steady pipeline that only consumes the last step, like bench.py, never waits).
+    Construction is collective; it raises RuntimeError on EVERY rank when the mapping failed on any of them, so
+    callers can fall back to FixedGather together."""
+
+    def __init__(self, capacity, cols, lib, device, group=None, dst=0, depth=2):
+        import ctypes
+
+        import numpy as np
+        self._ct, self._np = ctypes, np
+        self.lib, self.group, self.dst, self.depth, self.cols = lib, group, dst, int(depth), int(cols)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        c = torch.tensor([int(capacity)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX, group=group)
+        self.cap = int(c.item())
+        self.block = ((self.cap + 1) * self.cols * 8 + 255) // 256 * 256   # bytes per (ring, rank) block
+        self.base = None
+        self.step = 0
+        handle = torch.zeros(64, dtype=torch.uint8)
+        ok = 1
+        if self.rank == dst:
+            p = ctypes.c_void_p()
+            hb = (ctypes.c_uint8 * 64)()
+            if lib.rv_peer_alloc(self.block * self.world * self.depth, ctypes.byref(p), hb) == 0:
+                self.base = p.value
+                handle = torch.tensor(list(hb), dtype=torch.uint8)
+            else:
+                ok = 0
+        handle = handle.to(self.device)
+        dist.broadcast(handle, src=dst, group=group)
+        if self.rank != dst:
+            hb = (ctypes.c_uint8 * 64)(*handle.cpu().tolist())
+            p = ctypes.c_void_p()
+            if any(hb) and lib.rv_peer_open(hb, ctypes.byref(p)) == 0:
+                self.base = p.value
+            else:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            err = lib.rv_last_error().decode() if not ok else "another rank failed"
+            self._release()
+            raise RuntimeError("peer blocks unavailable: " + err)
+
+    def slot(self):
+        """Device address (in dst's memory) of this rank's block for the coming step."""
+        return self.base + ((self.step % self.depth) * self.world + self.rank) * self.block
+
+    def advance(self):
+        self.step += 1
+
+    def check(self, expect_seq=None):
+        """Collective.  Call after the device work of the last step is complete on the calling rank
+        (stream / device synchronised): waits for every rank, then returns on dst the per-rank (rows, seq) of the
+        LAST step -- int64 numpy arrays [k, cols] copied out of the ring -- and None elsewhere.  Raises on dst if
+        a rank had more rows than the capacity, or if `expect_seq` is given and a block carries another sequence
+        number (= it was not written by that rank's latest pack)."""
+        np, ctypes = self._np, self._ct
+        dist.barrier(group=self.group)
+        if self.rank != self.dst or self.step == 0:
+            return None
+        ring = (self.step - 1) % self.depth
+        out = []
+        for r in range(self.world):
+            blk = np.empty(self.block // 8, dtype=np.int64)
+            src = self.base + (ring * self.world + r) * self.block
+            if self.lib.rv_peer_read(ctypes.c_void_p(src), blk.ctypes.data, self.block) != 0:
+                raise RuntimeError(self.lib.rv_last_error().decode())
+            k, seq = int(blk[0]), int(blk[1])
+            if k > self.cap:
+                raise OverflowError("rank %d produced %d rows, gather capacity %d" % (r, k, self.cap))
+            if expect_seq is not None and seq != expect_seq:
+                raise RuntimeError("rank %d: block carries pack #%d, expected #%d" % (r, seq, expect_seq))
+            out.append((blk[self.cols:self.cols * (k + 1)].reshape(k, self.cols), seq))
+        return out
+
+    def _release(self):
+        if self.base is not None:
+            if self.rank == self.dst:
+                self.lib.rv_peer_free(self._ct.c_void_p(self.base))
+            else:
+                self.lib.rv_peer_close(self._ct.c_void_p(self.base))
+            self.base = None
+
+    def close(self):
+        """Collective: the mappings go first, then dst frees the allocation."""
+        if self.rank != self.dst:
+            self._release()
+        dist.barrier(group=self.group)
+        if self.rank == self.dst:
+            self._release()
+
+
 def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
     """Index build + MUM sweep of independent units, sharded over the ranks of `group`.
 

@@ -141,3 +141,103 @@ def test_fixed_gather_world2_gloo():
     parts = res[0][1]
     assert len(parts[0]) == 5 and len(parts[1]) == 7 and parts[1][0] == [100, 101, 102]
     assert res[0][2] is True
+
+
+class _BrokenOpen(object):
+    """The C-ABI library with a failing rv_peer_open (what a box without CUDA IPC would look like)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        return getattr(self._lib, name)
+
+    def rv_peer_open(self, handle, out):
+        return -2
+
+
+def _peer_worker(rank, world, port, q, lib_path):
+    import ctypes
+
+    import numpy as np
+    import oracle.port as P
+    from reveal_b200 import _native
+    from util import random_related
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = _native.bind(lib_path)
+    cpu = torch.device("cpu")
+    # a box where the mapping fails on one rank: every rank gets the same RuntimeError (collective fallback decision)
+    failed = False
+    try:
+        shard.PeerGather(16, 3, _BrokenOpen(L) if rank == 1 else L, cpu)
+    except RuntimeError:
+        failed = True
+    rng = np.random.default_rng(7)
+    units = []  # [step][rank]
+    for step in range(3):
+        units.append([P.assemble(random_related(rng, 2, 500 + 200 * r + 100 * step, 4)) for r in range(world)])
+    h = ctypes.c_void_p()
+    _native.check(L, L.rv_index_create(ctypes.byref(h), None))
+    g = shard.PeerGather(40 + 10 * rank, 3, L, cpu, depth=2)  # different requests: the ranks agree on the largest
+    cap_ok = g.cap == 50
+    cnt = ctypes.c_int64()
+    for step in range(3):  # three steps through a ring of two: the first block is overwritten
+        T, nsep, _ = units[step][rank]
+        nsep = np.asarray(nsep, dtype=np.int64)
+        _native.check(L, L.rv_build(h, T.ctypes.data, len(T), nsep.ctypes.data, 2, 0))
+        _native.check(L, L.rv_mums_pair_count(h, 8, 1, ctypes.byref(cnt)))
+        _native.check(L, L.rv_result_pack_device(h, ctypes.c_void_p(g.slot()), g.cap))
+        g.advance()
+    parts = g.check(expect_seq=3)
+    ok = None
+    if rank == 0:
+        ok = len(parts) == world
+        for r in range(world):
+            T, nsep, _ = units[2][r]
+            want = np.asarray(P.Index(T, nsep, 2).getmums(8, rem=True), dtype=np.int64).reshape(-1, 3)
+            ok = ok and np.array_equal(parts[r][0], want) and len(want) > 0
+    stale = False
+    try:
+        g.check(expect_seq=2)  # a stale block would carry another sequence number
+    except RuntimeError:
+        stale = True
+    g.close()
+    # more rows than the capacity: only min(count, cap) rows are written, check() reports it on dst
+    g2 = shard.PeerGather(2, 3, L, cpu)
+    _native.check(L, L.rv_result_pack_device(h, ctypes.c_void_p(g2.slot()), g2.cap))
+    g2.advance()
+    overflow = False
+    try:
+        g2.check()
+    except OverflowError:
+        overflow = True
+    g2.close()
+    L.rv_index_free(h)
+    q.put((rank, failed, cap_ok, ok, stale, overflow))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_gather_world2_gloo(emu_lib):
+    """One-sided gather through mapped peer blocks between two real processes (emulated kernels; POSIX shared
+    memory stands in for CUDA IPC): rows of the last step of both ranks, ring reuse, sequence numbers, overflow,
+    and the collective failure that lets callers fall back to FixedGather."""
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "_build", "libreveal_emu.so")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q, lib_path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r for r in [q.get(timeout=300) for _ in range(2)]}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        assert res[rank][1] is True, "broken mapping must raise on every rank"
+        assert res[rank][2] is True
+    assert res[0][3] is True and res[1][3] is None
+    assert res[0][4] is True and res[0][5] is True       # dst detects stale blocks and overflow
+    assert res[1][4] is False and res[1][5] is False     # the other ranks only take part in the barrier

@@ -164,3 +164,37 @@ def check_handle_reuse(L):
         assert_same(idx.arr("LCP"), o.LCP, "LCP")
         assert_same(idx.mums(5, 1), o.getmums(5, rem=True), "getmums")
     idx.close()
+
+
+def check_pack_block(L):
+    """rv_result_pack_device into a peer block allocated by this process (rv_peer_alloc / rv_peer_read / rv_peer_free):
+    header row (count, pack sequence number, 0) and the rows, with room to spare and with a capacity below the count."""
+    import ctypes
+
+    import oracle.port as P
+    from reveal_b200 import _native
+    rng = np.random.default_rng(21)
+    T, nsep, _ = P.assemble(random_related(rng, 2, 4000, 4))
+    idx = NativeIndex(L, T, nsep, 2)
+    want = np.asarray(P.Index(T, nsep, 2).getmums(6, rem=True), dtype=np.int64).reshape(-1, 3)
+    assert_same(idx.mums(6, 1), want, "getmums")
+    k = len(want)
+    assert k > 8
+    p = ctypes.c_void_p()
+    handle = (ctypes.c_uint8 * 64)()
+    nbytes = (k + 9) * 24
+    _native.check(L, L.rv_peer_alloc(nbytes, ctypes.byref(p), handle))
+    assert p.value and any(handle)
+    try:
+        for seq, cap in ((1, k + 8), (2, 5), (3, 0)):
+            _native.check(L, L.rv_result_pack_device(idx.h, p, cap))
+            blk = np.full((k + 9) * 3, -7, dtype=np.int64)
+            idx.arr("SA")  # a fetch synchronises the handle's stream
+            _native.check(L, L.rv_peer_read(p, blk.ctypes.data, nbytes))
+            m = min(k, cap)
+            assert blk[:3].tolist() == [k, seq, 0]
+            assert_same(blk[3:3 * (m + 1)].reshape(m, 3), want[:m], "packed rows")
+    finally:
+        _native.check(L, L.rv_peer_free(p))
+    assert L.rv_peer_alloc(0, ctypes.byref(p), handle) != 0
+    idx.close()
