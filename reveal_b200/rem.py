@@ -1,0 +1,769 @@
+"""REM -- recursive exact matching: the driver that turns the GPU index into an alignment graph.
+
+Host-side mirror of the reference's `reveal rem` for FASTA input, Python 3, on top of the drop-in `reveallib`:
+the reference entry points keep their names and meaning --
+
+  align_genomes(args) -> (G, idx)      reveal/rem.py:511-611   (args: the namespace of `reveal rem`, see rem_args)
+  align(aobjs, ...)   -> (G, idx)      reveal/rem.py:616-712   (library call on (name, sequence) tuples)
+  graphalign(idx, mum)                 reveal/rem.py:317-382   callback 2 of index.align
+  graphmumpicker(mums, idx, ...)       reveal/schemes.py:197-361  callback 1 of index.align
+  chain / trim_overlap / segment       reveal/schemes.py:20-191
+  gapcost                              reveal/utils.py:162-183
+  prune_nodes                          reveal/rem.py:385-446
+  fasta_reader / read_fasta / write_gfa  reveal/utils.py:79-144, 304-375, 710-839
+
+-- and G is the same networkx (Multi)DiGraph: nodes are `Interval(begin, end)` in index coordinates with
+attributes `offsets` {path id: offset in that path} and `aligned`, edges carry `paths` (set of path ids),
+`ofrom`, `oto`; G.graph holds paths / path2id / id2path / id2end / startnodes / endnodes.
+
+What is different from the reference is the plumbing: no module-level globals (one `Rem` object per alignment owns
+the graph and the position -> node map, so several alignments can live in one process), the position lookup is a
+sorted map instead of an interval tree (nodes never overlap), and chaining is evaluated with numpy over all
+candidate predecessors at once instead of a Python loop per pair.  Results are checked against graphs minted
+from the reference's own driver (tests/golden/make_rem_golden.py, tests/test_rem.py).
+"""
+import argparse
+import collections
+import gzip
+import logging
+import math
+import os
+import sys
+import uuid
+
+import networkx as nx
+import numpy as np
+from sortedcontainers import SortedDict
+
+log = logging.getLogger("reveal_b200.rem")
+
+
+class Interval(collections.namedtuple("Interval", ["begin", "end"])):
+    """A graph node: the half-open range [begin, end) of the index text it spells."""
+    __slots__ = ()
+
+
+def _real(G, sid):
+    return not G.graph["id2path"][sid].startswith("*")
+
+
+# ------------------------------------------------------------------------------------------------
+# scoring (reveal/utils.py:162-183, reveal/schemes.py:20-191)
+def gapcost(pointa, pointb, model="sumofpairs", convex=False, lambda_=1, epsilon_=0):
+    """Penalty for the gap between two anchors given as per-sample coordinates (utils.py:162-183)."""
+    assert len(pointa) == len(pointb)
+    k = len(pointa)
+    if model == "star-avg":
+        return abs(sum(pointa[i] - pointb[i] for i in range(k))) // k
+    if model == "star-med":
+        return sorted(abs(pointa[i] - pointb[i]) for i in range(k))[k // 2]
+    if model != "sumofpairs":
+        log.warning("Unknown penalty model: %s.", model)
+        return 0
+    dist = [abs(pointa[i] - pointb[i]) for i in range(k)]
+    p = min(dist) * epsilon_ if epsilon_ > 0 else 0
+    for i in range(k):
+        for j in range(i + 1, k):
+            d = abs(dist[i] - dist[j])
+            p += (math.log(d + 1) if convex else d) * lambda_
+    return p
+
+
+def _gap_matrix(ends, starts, model):
+    """gapcost of every candidate predecessor (rows of `ends`, [m, k]) against one anchor (`starts`, [k])."""
+    dist = np.abs(ends - starts[None, :])
+    k = dist.shape[1]
+    if model == "star-avg":
+        return np.abs((ends - starts[None, :]).sum(axis=1)) // k
+    if model == "star-med":
+        return np.sort(dist, axis=1)[:, k // 2]
+    pen = np.zeros(dist.shape[0], dtype=np.int64)
+    for i in range(k):
+        for j in range(i + 1, k):
+            pen += np.abs(dist[:, i] - dist[:, j])
+    return pen
+
+
+def chain(mums, left, right, gcmodel="sumofpairs", wscore=1, wpen=1):
+    """Best-scoring colinear chain of anchors between the bounds `left` and `right` (schemes.py:20-104).
+
+    mums, left, right: (l, n, {sample: offset}).  Returns [(mum, score), ...] from the LAST anchor of the chain
+    to the first, like the reference (its caller reverses it).
+
+    An anchor may follow every earlier anchor (in the order of the first sample's coordinate) that ends before it
+    in every sample; its score is the best predecessor score + wscore * l * n(n-1)/2 - wpen * gapcost.  Equal
+    totals are resolved as the reference's sorted `active` list does: higher predecessor score first, then the
+    predecessor that became available earlier, then the one processed earlier.
+    """
+    if len(mums) == 0:
+        return []
+    ref = sorted(mums[0][2].keys())[0]
+    order = sorted(list(mums) + [right], key=lambda m: m[2][ref])
+    keys = list(right[2].keys())
+    m = len(order)
+    # row 0 is `left`, rows 1..m the anchors in processing order
+    start = np.empty((m + 1, len(keys)), dtype=np.int64)
+    length = np.zeros(m + 1, dtype=np.int64)
+    gain = np.zeros(m + 1, dtype=np.int64)
+    start[0] = [left[2][k] for k in keys]
+    for r, mum in enumerate(order, 1):
+        start[r] = [mum[2][k] for k in keys]
+        length[r] = mum[0]
+        gain[r] = wscore * (mum[0] * ((mum[1] * (mum[1] - 1)) // 2))
+    end = start + length[:, None]
+    score = np.zeros(m + 1, dtype=np.int64)
+    joined = np.full(m + 1, -1, dtype=np.int64)     # iteration at which a processed anchor became a candidate
+    joined[0] = 0
+    link = np.zeros(m + 1, dtype=np.int64)
+    for r in range(1, m + 1):
+        ok = (end[:r] <= start[r][None, :]).all(axis=1)
+        fresh = ok & (joined[:r] < 0)
+        joined[:r][fresh] = r
+        cand = np.nonzero(ok)[0]
+        s = score[cand] + gain[r]
+        total = s - wpen * _gap_matrix(end[cand], start[r], gcmodel)
+        best = cand[total == total.max()]
+        if len(best) > 1:
+            best = best[np.lexsort((best, joined[best], -score[best]))]
+        link[r] = best[0]
+        score[r] = total.max()
+    log.debug("Best score is: %d", score[m])
+    path = []
+    r = link[m]                                    # order[m-1] is `right` itself: the chain starts at its predecessor
+    while r != 0:
+        path.append((order[r - 1], int(score[r])))
+        r = link[r]
+    return path
+
+
+def segment(mums):
+    """The group of anchors over one and the same set of samples with the largest (total length x #samples)
+    (schemes.py:107-125)."""
+    groups = collections.OrderedDict()
+    for mum in mums:
+        groups.setdefault(tuple(sorted(gid for gid, _ in mum[2])), []).append(mum)
+    best, pick = 0, None
+    for part, members in groups.items():
+        z = sum(m[0] for m in members) * len(part)
+        if z > best:
+            best, pick = z, part
+    return groups[pick]
+
+
+def trim_overlap(mums):
+    """Removes overlap between anchors, one coordinate (= member slot of the anchor tuples) at a time
+    (schemes.py:161-191): anchors contained in their neighbour go, overlapping ends are cut back."""
+    for coord in range(len(mums[0][2])):
+        if len(mums) <= 1:
+            break
+        mums.sort(key=lambda m: (m[2][coord][1], -m[0]))
+        ends = [m[2][coord][1] + m[0] for m in mums]
+        # the reference's filter indexes mums[i-1] with i == 0 too, i.e. compares the first anchor with the LAST one
+        mums = [mum for i, mum in enumerate(mums) if (i == 0 and ends[1] > ends[0]) or ends[i - 1] < ends[i]]
+        if len(mums) <= 1:
+            break
+        trimmed = [mums[0]]
+        for mum in mums[1:]:
+            prev = trimmed[-1]
+            overlap = prev[2][coord][1] + prev[0] - mum[2][coord][1]
+            if overlap > 0:
+                if prev[0] - overlap > 0:
+                    trimmed[-1] = (prev[0] - overlap, prev[1], prev[2])
+                else:
+                    del trimmed[-1]
+                if mum[0] - overlap > 0:
+                    trimmed.append((mum[0] - overlap, mum[1], tuple((k, v + overlap) for k, v in mum[2])))
+            else:
+                trimmed.append(mum)
+        mums = trimmed
+    return mums
+
+
+# ------------------------------------------------------------------------------------------------
+def rem_args(inputfiles=(), **overrides):
+    """The option namespace of `reveal rem` with its defaults (reveal/reveal.py:74-99)."""
+    a = dict(inputfiles=list(inputfiles), output=None, threads=0, minlength=20, pcutoff=1e-8, minn=2, gcmodel="sumofpairs",
+             wpen=1, wscore=1, seedsize=10000, maxmums=1000, sa="", lcp="", cache=False, sa64=False, toupper=True, maxsize=None,
+             contigs=True, trim=True, splitchain="largest", maxdepth=None)
+    unknown = set(overrides) - set(a)
+    if unknown:
+        raise TypeError("unknown rem option(s): %s" % ", ".join(sorted(unknown)))
+    a.update(overrides)
+    return argparse.Namespace(**a)
+
+
+class Rem(object):
+    """One alignment in progress: the graph, the position -> node map and the two callbacks of index.align."""
+
+    def __init__(self, args, G=None):
+        self.args = args
+        self.G = nx.MultiDiGraph() if G is None else G
+        self.multi = isinstance(self.G, nx.MultiDiGraph)
+        self.where = SortedDict()          # begin -> end of every Interval node
+        for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict), ("startnodes", list),
+                           ("endnodes", list)):
+            self.G.graph.setdefault(key, empty())
+
+    # ---- position -> node ------------------------------------------------------------------
+    def node_at(self, pos):
+        i = self.where.bisect_right(pos) - 1
+        if i >= 0:
+            begin, end = self.where.peekitem(i)
+            if pos < end:
+                return Interval(begin, end)
+        raise KeyError("no node covers index position %d" % pos)
+
+    # ---- input -----------------------------------------------------------------------------
+    def add_sequence(self, index, name, seq):
+        """One path of the graph = one sequence of the index, between its own start and end marker nodes
+        (utils.py:326-347)."""
+        g = self.G.graph
+        name = name.replace(":", "").replace(";", "")
+        if name in g["paths"]:
+            raise ValueError("Fasta with this name: \"%s\" is already contained in the graph." % name)
+        sid = len(g["paths"])
+        g["paths"].append(name)
+        g["path2id"][name] = sid
+        g["id2path"][sid] = name
+        g["id2end"][sid] = len(seq)
+        begin, end = index.addsequence(seq)
+        node = Interval(begin, end)
+        self.where[begin] = end
+        first, last = uuid.uuid4().hex, uuid.uuid4().hex
+        self.G.add_node(first, offsets={sid: 0}, endpoint=True)
+        g["startnodes"].append(first)
+        self.G.add_node(node, offsets={sid: 0}, aligned=0)
+        self.G.add_node(last, offsets={sid: len(seq)}, endpoint=True)
+        g["endnodes"].append(last)
+        self.G.add_edge(first, node, paths={sid}, ofrom="+", oto="+")
+        self.G.add_edge(node, last, paths={sid}, ofrom="+", oto="+")
+
+    def read_fasta(self, fasta, index, contigs=True, toupper=True):
+        """contigs=True: the file is ONE sample whose sequences are its contigs; else every sequence is a sample
+        (utils.py:304-375)."""
+        if contigs:
+            index.addsample(os.path.basename(fasta))
+        for name, seq in fasta_reader(fasta, toupper=toupper):
+            if not contigs:
+                index.addsample(name)
+            self.add_sequence(index, name, seq)
+
+    # ---- graph surgery -----------------------------------------------------------------------
+    def _edges_in(self, node):
+        return [(u, d) for u, _, d in self.G.in_edges(node, data=True)]
+
+    def _edges_out(self, node):
+        return [(v, d) for _, v, d in self.G.out_edges(node, data=True)]
+
+    def breaknode(self, node, pos, l):
+        """Cuts [pos, pos+l) out of `node`; returns the matching piece and the set of left-over pieces
+        (rem.py:14-131)."""
+        G = self.G
+        piece = Interval(pos, pos + l)
+        if piece == node:
+            del self.where[node.begin]
+            return node, set()
+        att = G.nodes[node]
+        ins, outs = self._edges_in(node), self._edges_out(node)
+        shift = pos - node.begin
+        mid_off = {s: o + shift for s, o in att["offsets"].items()}
+        suf_off = {s: o + shift + l for s, o in att["offsets"].items()}
+        # paths that run through the node on the other strand get mirrored edges between the pieces
+        pos_paths, neg_paths = set(), set()
+        if not ins and not outs:
+            pos_paths = set(att["offsets"])
+        for _, d in ins:
+            (neg_paths if d["oto"] == "-" else pos_paths).update(d["paths"])
+        for _, d in outs:
+            (neg_paths if d["ofrom"] == "-" else pos_paths).update(d["paths"])
+        assert not (pos_paths & neg_paths), "paths traverse node %s on both strands" % (node,)
+        del self.where[node.begin]
+        G.add_node(piece, offsets=mid_off, aligned=0)
+        others = set()
+        head = tail = piece
+        if node.begin != pos:
+            head = Interval(node.begin, pos)
+            G.add_node(head, offsets=att["offsets"], aligned=0)
+            G.add_edge(head, piece, paths=set(pos_paths), ofrom="+", oto="+")
+            if neg_paths:
+                G.add_edge(piece, head, paths=set(neg_paths), ofrom="-", oto="-")
+            self.where[head.begin] = head.end
+            others.add(head)
+        if node.end != pos + l:
+            tail = Interval(pos + l, node.end)
+            G.add_node(tail, offsets=suf_off, aligned=0)
+            G.add_edge(piece, tail, paths=set(pos_paths), ofrom="+", oto="+")
+            if neg_paths:
+                G.add_edge(tail, piece, paths=set(neg_paths), ofrom="-", oto="-")
+            self.where[tail.begin] = tail.end
+            others.add(tail)
+        G.remove_node(node)
+        for u, d in ins:
+            G.add_edge(u, head if d["oto"] == "+" else tail, **d)
+        for v, d in outs:
+            G.add_edge(tail if d["ofrom"] == "+" else head, v, **d)
+        return piece, others
+
+    def mergenodes(self, group):
+        """Folds the nodes of `group` into its first member: offsets united, edges re-attached, parallel edges with
+        the same orientation united by their paths (rem.py:133-205)."""
+        G = self.G
+        keep = group[0]
+        offsets = {}
+        for node in group:
+            offsets.update(G.nodes[node]["offsets"])
+        G.nodes[keep]["offsets"] = offsets
+        G.nodes[keep]["aligned"] = 1
+        for node in group[1:]:
+            if self.multi:
+                for u, _, d in list(G.in_edges(node, data=True)):
+                    for u2, _, d2 in G.in_edges(keep, data=True):
+                        if type(u2) is type(u) and u2 == u and d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
+                            d2["paths"].update(d["paths"])
+                            break
+                    else:
+                        G.add_edge(u, keep, **d)
+                for _, v, d in list(G.out_edges(node, data=True)):
+                    for _, v2, d2 in G.out_edges(keep, data=True):
+                        if type(v2) is type(v) and v2 == v and d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
+                            d2["paths"].update(d["paths"])
+                            break
+                    else:
+                        G.add_edge(keep, v, **d)
+            else:
+                for u, _, d in list(G.in_edges(node, data=True)):
+                    if G.has_edge(u, keep):
+                        G[u][keep]["paths"].update(d["paths"])
+                    else:
+                        G.add_edge(u, keep, **d)
+                for _, v, d in list(G.out_edges(node, data=True)):
+                    if G.has_edge(keep, v):
+                        G[keep][v]["paths"].update(d["paths"])
+                    else:
+                        G.add_edge(keep, v, **d)
+            G.remove_node(node)
+        return keep
+
+    def _neighbours(self, node, backwards):
+        """Neighbours over edges that carry at least one real (non '*') path (rem.py:207-233)."""
+        G = self.G
+        adj = G.pred[node] if backwards else G.succ[node]
+        for other, edges in adj.items():
+            bundle = edges.values() if self.multi else (edges,)
+            if any(_real(G, p) for e in bundle for p in e["paths"]):
+                yield other
+
+    def _reach(self, source, backwards=False, through=()):
+        """Breadth-first walk that stops at aligned nodes (class 1) and at the start/end markers (class 2) and runs
+        on through unaligned ones (class 0), and through the aligned nodes listed in `through` (rem.py:235-262)."""
+        G = self.G
+        seen = {source}
+        queue = collections.deque([source])
+        while queue:
+            for child in self._neighbours(queue.popleft(), backwards):
+                if child in seen:
+                    continue
+                seen.add(child)
+                data = G.nodes[child]
+                if "aligned" not in data:
+                    yield child, 2
+                elif data["aligned"] == 0 or child in through:
+                    queue.append(child)
+                    yield child, 0
+                else:
+                    yield child, 1
+
+    def segmentgraph(self, node, nodes):
+        """Splits the intervals of a (sub)index around the freshly merged `node` into those that lie strictly
+        before it, strictly after it, and the rest (rem.py:264-315)."""
+        sides = []
+        for backwards in (False, True):
+            side, stops = set(), set()
+            for c, kind in self._reach(node, backwards):
+                (side if kind == 0 else stops).add(c)
+            if len(stops) > 1:  # keep only what every stop reaches when walking back towards the node
+                back = set()
+                for stop in stops:
+                    back.update(c for c, kind in self._reach(stop, not backwards, through=stops) if kind == 0)
+                side &= back
+            sides.append({(c.begin, c.end) for c in side if isinstance(c, Interval)} & nodes)
+        trailing, leading = sides
+        return leading, trailing, nodes - (leading | trailing)
+
+    # ---- callback 2: graphalign(index, mum) (rem.py:317-382) --------------------------------
+    def graphalign(self, index, mum):
+        try:
+            l, n, spd = mum
+            nodes = index.nodes
+            G = self.G
+            pieces = []
+            matching = set()
+            for _, pos in spd:
+                matching.add((pos, pos + l))
+                old = self.node_at(pos)
+                assert old.end - old.begin >= l
+                piece, others = self.breaknode(old, pos, l)
+                pieces.append(piece)
+                nodes.remove((old.begin, old.end))
+                for o in others:
+                    nodes.add((o.begin, o.end))
+            merged = self.mergenodes(pieces)
+            msamples = set(G.nodes[merged]["offsets"])
+            leading, trailing, rest = self.segmentgraph(merged, set(nodes))
+            newleft = newright = merged
+            # a side whose intervals belong to samples outside the match is not cleanly cut by it: keep the old bound
+            if any(not set(G.nodes[Interval(*iv)]["offsets"]) <= msamples for iv in leading):
+                newright = index.rightnode
+            if any(not set(G.nodes[Interval(*iv)]["offsets"]) <= msamples for iv in trailing):
+                newleft = index.leftnode
+            return leading, trailing, matching, rest, merged, newleft, newright
+        except Exception:
+            log.exception("graphalign failed")
+            raise
+
+    # ---- callback 1: graphmumpicker (schemes.py:197-361) -----------------------------------
+    def _lookup(self, mum):
+        """Anchor in index coordinates -> (l, n, {path id: offset in the path}) (schemes.py:127-150)."""
+        G = self.G
+        l, _, spd = mum
+        n = 0
+        point = {}
+        for _, pos in spd:
+            node = self.node_at(pos)
+            data = G.nodes[node]
+            rel = pos - node.begin
+            for k, off in data["offsets"].items():
+                if _real(G, k):
+                    n += 1
+                    point[k] = off + rel
+        return (l, n, point)
+
+    def _bounds(self, idx, keys):
+        G = self.G
+        if idx.leftnode is not None:
+            off = G.nodes[idx.leftnode]["offsets"]
+            left = {k: off[k] + (idx.leftnode[1] - idx.leftnode[0]) - 1 for k in keys}
+        else:
+            left = {k: -1 for k in keys}
+        if idx.rightnode is not None:
+            off = G.nodes[idx.rightnode]["offsets"]
+            right = {k: off[k] for k in keys}
+        else:
+            right = {k: G.graph["id2end"][k] for k in keys}
+        return (0, 0, left), (0, 0, right)
+
+    def _small_enough(self, idx):
+        """--maxbubblesize: true when every path between the bounds of idx is at most args.maxsize long."""
+        G = self.G
+        real = [G.graph["path2id"][p] for p in G.graph["paths"] if not p.startswith("*")]
+        if idx.leftnode is None:
+            lo = {k: 0 for k in real}
+        else:
+            off = G.nodes[idx.leftnode]["offsets"]
+            lo = {k: off[k] + (idx.leftnode[1] - idx.leftnode[0]) for k in off}
+        ro = {k: G.graph["id2end"][k] for k in real} if idx.rightnode is None else G.nodes[idx.rightnode]["offsets"]
+        return all(ro[k] - lo[k] <= self.args.maxsize for k in set(lo) & set(ro))
+
+    def graphmumpicker(self, mums, idx, precomputed=False, minlength=0):
+        try:
+            args = self.args
+            if len(mums) == 0:
+                return ()
+            if precomputed:  # a chain handed down by the parent: split at its middle (schemes.py:346-351)
+                half = len(mums) // 2
+                return mums[half][0], mums[:half], mums[half + 1:]
+            if args.maxdepth is not None and idx.depth > args.maxdepth:
+                return ()
+            if args.maxsize is not None and self._small_enough(idx):
+                return ()
+            picked = [m for m in mums if m[1] == idx.nsamples]
+            if not picked and idx.nsamples > 2:
+                picked = segment(mums)
+            if not picked:
+                return ()
+            if args.trim:
+                picked = trim_overlap(picked)
+                if not picked:
+                    return ()
+            picked.sort(key=lambda m: m[0], reverse=True)
+            origin = {}
+            rel = []
+            for m in picked:
+                r = self._lookup(m)
+                rel.append(r)
+                origin[tuple(r[2].values())] = m
+            rel.sort(key=lambda m: (m[1], m[0]))
+            rel = [m for m in rel if m[2].keys() == rel[-1][2].keys()]
+            left, right = self._bounds(idx, list(rel[-1][2].keys()))
+            skipleft, skipright = [], []
+            if len(rel) == 1:
+                split = rel[0]
+            else:
+                if len(rel) > args.maxmums:
+                    rel = rel[-args.maxmums:]
+                chained = chain(rel, left, right, gcmodel=args.gcmodel, wscore=args.wscore, wpen=args.wpen)[::-1]
+                if not chained:
+                    return ()
+                if args.splitchain == "balanced":
+                    split, opt = None, None
+                    for m, _ in chained:
+                        lseq = rseq = 0
+                        for crd in m[2]:
+                            lseq = m[2][crd]
+                            rseq = right[2][crd] - m[2][crd] + m[0]
+                        if opt is None or abs(lseq - rseq) < opt:
+                            opt, split = abs(lseq - rseq), m
+                else:
+                    split = sorted(chained, key=lambda c: c[0][0])[-1][0]
+                if args.seedsize > 0:
+                    side, at_split = skipleft, 0
+                    for m, score in chained:
+                        if m == split:
+                            at_split, side = score, skipright
+                            continue
+                        side.append((origin[tuple(m[2].values())], score - at_split))
+                    skipleft = [(m, s) for m, s in skipleft if m[0] >= args.seedsize]
+                    skipright = [(m, s) for m, s in skipright if m[0] >= args.seedsize]
+            split = origin[tuple(split[2].values())]
+            if minlength == 0:  # no length threshold: keep the anchor only if it is unlikely to occur by chance
+                tests = 1
+                for k in left[2]:
+                    tests *= right[2][k] - left[2][k]
+                p = (.25 ** (split[1] - 1)) ** split[0]
+                if p > 0:
+                    p = 1 - math.exp(math.log(1 - p) * tests)
+                if p > args.pcutoff:
+                    return ()
+            return split, skipleft, skipright
+        except Exception:
+            log.exception("graphmumpicker failed")
+            raise
+
+    # ---- after the recursion ---------------------------------------------------------------------
+    def prune_nodes(self, T=""):
+        """Merges sibling nodes that spell the same sequence and have no other '+' neighbour on the shared side,
+        until nothing changes (rem.py:385-446)."""
+        G = self.G
+
+        def plus(edges, pick):
+            return [e[pick] for e in edges if e[2]["ofrom"] == "+" and e[2]["oto"] == "+"]
+
+        def spelled(node):
+            data = G.nodes[node]
+            if "seq" in data:
+                return data["seq"]
+            return T[node.begin:node.end] if isinstance(node, Interval) else None
+
+        changed = True
+        while changed:
+            changed = False
+            for node in list(G.nodes()):
+                if node not in G:
+                    continue
+                for forward in (True, False):
+                    neis = plus(G.out_edges(node, data=True), 1) if forward else plus(G.in_edges(node, data=True), 0)
+                    by_seq = collections.OrderedDict()
+                    for nei in neis:
+                        seq = spelled(nei)
+                        if seq is not None:
+                            by_seq.setdefault(seq, []).append(nei)
+                    for group in by_seq.values():
+                        if len(group) < 2:
+                            continue
+                        if forward:
+                            lonely = all(len(plus(G.in_edges(v, data=True), 0)) <= 1 for v in group)
+                        else:
+                            lonely = all(len(plus(G.out_edges(v, data=True), 1)) <= 1 for v in group)
+                        if lonely:
+                            for v in group[1:]:
+                                if isinstance(v, Interval):
+                                    self.where.pop(v.begin, None)
+                            self.mergenodes(group)
+                            changed = True
+
+
+# ------------------------------------------------------------------------------------------------
+def fasta_reader(fn, toupper=True, keepdash=False):
+    """(name, sequence) of every record of a (gzipped) FASTA file (utils.py:79-144, default options)."""
+    name, chunks = None, []
+    with (gzip.open(fn, "rt") if fn.endswith(".gz") else open(fn, "r")) as f:
+        for line in f:
+            line = line.rstrip()
+            if line.startswith(">"):
+                if chunks and any(chunks):
+                    yield name, "".join(chunks)
+                name, chunks = line.replace(">", "").replace("\t", ""), []
+            else:
+                if toupper:
+                    line = line.upper()
+                if not keepdash:
+                    line = line.replace("-", "")
+                chunks.append(line)
+    if chunks and any(chunks):
+        yield name, "".join(chunks)
+
+
+def _index_module(sa64=False):
+    from . import reveallib, reveallib64
+    return reveallib64 if sa64 else reveallib
+
+
+def align_genomes(args, index_module=None):
+    """FASTA files -> (alignment graph, index) (rem.py:511-611).  `args`: see rem_args; `index_module` lets tests
+    run the driver on another build of the drop-in extension."""
+    mod = index_module if index_module is not None else _index_module(args.sa64)
+    idx = mod.index(sa=args.sa, lcp=args.lcp, cache=args.cache)
+    rem = Rem(args)
+    for fn in args.inputfiles:
+        if fn.endswith(".gfa") or fn.endswith(".gfa.gz"):
+            raise NotImplementedError("graph input (.gfa) is not part of this driver yet: %s" % fn)
+        rem.read_fasta(fn, idx, contigs=args.contigs, toupper=args.toupper)
+    if len(idx.samples) <= 1:
+        raise ValueError("Specify at least 2 targets to construct alignment. In case of multi-fasta, consider contigs=False.")
+    idx.construct()
+    idx.align(rem.graphmumpicker, rem.graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength,
+              minn=args.minn)
+    return rem.G, idx
+
+
+def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targetsample=None, maxsamples=None, maxmums=10000, wpen=1,
+          wscore=1, sa64=False, pcutoff=1e-8, gcmodel="sumofpairs", maxsize=None, trim=True, index_module=None):
+    """Library entry: aligns (name, sequence) tuples, one sample each, between one shared start and end marker;
+    returns (DiGraph, index) with the markers removed and equal siblings merged (rem.py:616-712)."""
+    args = rem_args(minlength=minlength, minn=minn, seedsize=seedsize if seedsize is not None else 0, threads=threads, maxmums=maxmums,
+                    wpen=wpen, wscore=wscore, sa64=sa64, pcutoff=pcutoff, gcmodel=gcmodel, maxsize=maxsize, trim=trim)
+    mod = index_module if index_module is not None else _index_module(sa64)
+    idx = mod.index()
+    rem = Rem(args, nx.DiGraph())
+    G = rem.G
+    first, last = uuid.uuid4().hex, uuid.uuid4().hex
+    G.add_node(first)
+    G.add_node(last)
+    for name, seq in aobjs:
+        idx.addsample(name)
+        begin, end = idx.addsequence(seq.upper())
+        if end - begin > 0:
+            node = Interval(begin, end)
+            rem.where[begin] = end
+            sid = len(G.graph["paths"])
+            G.graph["path2id"][name] = sid
+            G.graph["id2path"][sid] = name
+            G.graph["id2end"][sid] = len(seq)
+            G.graph["paths"].append(name)
+            G.add_node(node, offsets={sid: 0}, aligned=0)
+            G.add_edge(first, node, paths={sid}, ofrom="+", oto="+")
+            G.add_edge(node, last, paths={sid}, ofrom="+", oto="+")
+    idx.construct()
+    idx.align(rem.graphmumpicker, rem.graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
+    rem.prune_nodes(T=idx.T)
+    G.remove_node(first)
+    G.remove_node(last)
+    return G, idx
+
+
+def prune_nodes(G, T=""):
+    """Module-level form of Rem.prune_nodes for graphs made by align_genomes (rem.py:385)."""
+    Rem(rem_args(), G).prune_nodes(T=T)
+
+
+def aligned_bases(G, idx):
+    """(aligned bases, total bases, aligned nodes) as `reveal rem` reports them (rem.py:470-490)."""
+    T = idx.T
+    total = idx.n - T.count("$") - T.count("N")
+    bases = nodes = 0
+    for node, data in G.nodes(data=True):
+        if isinstance(node, str) or not data.get("aligned"):
+            continue
+        nodes += 1
+        length = node.end - node.begin
+        if idx.nsamples > 2:
+            bases += length * sum(1 for k in data["offsets"] if _real(G, k))
+        else:
+            bases += 2 * length
+    return bases, total, nodes
+
+
+def write_gfa(G, T, outputfile="reference.gfa", toupper=True):
+    """GFA 1 with S, L and P lines; segment ids number the nodes in graph order (utils.py:710-839).  Sequence of
+    aligned nodes is written upper-case (align_cmd runs seq2node(toupper=True) first, utils.py:1036-1045)."""
+    if not outputfile.endswith(".gfa") and not outputfile.endswith(".gfa.gz"):
+        outputfile += ".gfa.gz"
+    order = [n for n in (nx.topological_sort(G) if not isinstance(G, nx.MultiDiGraph) else G.nodes()) if not isinstance(n, str)]
+    ids = {n: i + 1 for i, n in enumerate(order)}
+    with (gzip.open(outputfile, "wt") if outputfile.endswith(".gz") else open(outputfile, "w")) as f:
+        f.write("H\tVN:Z:1.0\tCL:Z:%s\n" % " ".join(sys.argv))
+        for node in order:
+            data = G.nodes[node]
+            seq = data["seq"] if "seq" in data else T[node.begin:node.end]
+            if toupper and data.get("aligned"):
+                seq = seq.upper()
+            f.write("S\t%d\t%s\n" % (ids[node], seq))
+            for _, to, d in G.out_edges(node, data=True):
+                if not isinstance(to, str):
+                    f.write("L\t%d\t%s\t%d\t%s\t%s\n" % (ids[node], d.get("ofrom", "+"), ids[to], d.get("oto", "+"), d.get("cigar", "0M")))
+        for name, sid in G.graph["path2id"].items():
+            walk = []
+            for start in G.graph["startnodes"]:
+                if start in G and sid in G.nodes[start]["offsets"]:
+                    node = start
+                    while True:
+                        nxt = [(v, d) for _, v, d in G.out_edges(node, data=True) if sid in d["paths"]]
+                        if len(nxt) != 1:
+                            log.warning("path %s stops or forks at %s", name, node)
+                            break
+                        node, d = nxt[0]
+                        if node in G.graph["endnodes"]:
+                            break
+                        if not isinstance(node, str):
+                            walk.append("%d%s" % (ids[node], d.get("oto", "+")))
+                    break
+            f.write("P\t%s\t%s\t%s\n" % (name, ",".join(walk), ",".join("0M" for _ in walk)))
+    return outputfile
+
+
+def align_cmd(args):
+    """`reveal rem` for FASTA input: align, merge equal siblings (more than two paths), report, write the GFA
+    (rem.py:448-509).  Returns (G, idx, output file)."""
+    G, idx = align_genomes(args)
+    if args.output is None:
+        args.output = "_".join(os.path.basename(f).split(".")[0] for f in args.inputfiles) + ".gfa.gz"
+    T = idx.T
+    if len(G.graph["paths"]) > 2:
+        prune_nodes(G, T=T)
+    bases, total, nodes = aligned_bases(G, idx)
+    log.info("%s (%.2f%% identity, %d bases out of %d aligned, %d nodes out of %d aligned).",
+             "-".join(os.path.basename(f) for f in args.inputfiles), 100.0 * bases / max(total, 1), bases, total, nodes, G.number_of_nodes())
+    out = write_gfa(G, T, outputfile=args.output)
+    return G, idx, out
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(prog="python -m reveal_b200.rem", description="Recursive exact matching of FASTA files into a GFA graph.")
+    p.add_argument("inputfiles", nargs="+")
+    p.add_argument("-o", "--output", dest="output")
+    p.add_argument("-t", "--threads", dest="threads", type=int, default=0)
+    p.add_argument("-m", dest="minlength", type=int, default=20)
+    p.add_argument("-p", dest="pcutoff", type=float, default=1e-8)
+    p.add_argument("-n", dest="minn", type=int, default=2)
+    p.add_argument("--gcmodel", dest="gcmodel", choices=["sumofpairs", "star-avg", "star-med"], default="sumofpairs")
+    p.add_argument("--wp", dest="wpen", type=int, default=1)
+    p.add_argument("--ws", dest="wscore", type=int, default=1)
+    p.add_argument("--seedsize", dest="seedsize", type=int, default=10000)
+    p.add_argument("--maxmums", dest="maxmums", type=int, default=1000)
+    p.add_argument("--sa", dest="sa", default="")
+    p.add_argument("--lcp", dest="lcp", default="")
+    p.add_argument("--cache", dest="cache", default=False, action="store_true")
+    p.add_argument("--64", dest="sa64", default=False, action="store_true")
+    p.add_argument("--noupper", dest="toupper", action="store_false", default=True)
+    p.add_argument("--maxbubblesize", dest="maxsize", type=int, default=None)
+    p.add_argument("--nocontigs", dest="contigs", default=True, action="store_false")
+    p.add_argument("--notrim", dest="trim", default=True, action="store_false")
+    ns = p.parse_args(argv)
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
+    args = rem_args(**vars(ns))
+    _, _, out = align_cmd(args)
+    log.info("Graph written to: %s", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,9 @@ CASES = [  # name, inputs (reference test files, or ("synth", n_genomes, length,
     ("t1_t2", ["t1.fa", "t2.fa"], {"minlength": 5}),
     ("d1_d2", ["d1.fa", "d2.fa"], {"minlength": 10}),
     ("1e_1f_nocontigs", ["1e.fa", "1f.fa"], {"contigs": False, "minlength": 12}),
+    ("synth2_4k", ("synth", 2, 4000, 21), {"minlength": 12}),           # small enough for the emulated kernels (CPU tests)
+    ("synth3_3k", ("synth", 3, 3000, 22), {"minlength": 10}),
+    ("synth4_2k_seed", ("synth", 4, 2000, 23), {"minlength": 8, "seedsize": 30, "minn": 3}),
     ("synth2_200k", ("synth", 2, 200000, 11), {}),
     ("synth3_60k", ("synth", 3, 60000, 12), {}),
     ("synth5_30k_n3", ("synth", 5, 30000, 13), {"minn": 3, "minlength": 15}),

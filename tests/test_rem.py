@@ -1,0 +1,160 @@
+"""The REM driver (reveal_b200/rem.py) against alignment graphs minted from the reference's own driver running on the
+reference's own compiled extension (tests/golden/make_rem_golden.py): same nodes (per-path offsets, length, sequence,
+aligned flag), same edges with orientations and paths, same walk of every path, same lower-cased text."""
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_rem_golden as M  # noqa: E402  (canonical form + case table; it touches /root/reference only when run as a script)
+
+from reveal_b200 import rem, synth  # noqa: E402
+
+GOLDEN = os.path.join(HERE, "golden", "rem")
+
+
+def load(name):
+    return json.loads(gzip.open(os.path.join(GOLDEN, name + ".json.gz")).read())
+
+
+def case_files(gold, tmp_path):
+    files = []
+    if "synth" in gold:
+        ng, length, seed = gold["synth"]
+        for k, g in enumerate(synth.genomes(ng, length, seed=seed)):
+            files.append(str(tmp_path / ("g%d.fa" % k)))
+            M.write_fasta(files[-1], "g%d" % k, g.tobytes().decode())
+        return files
+    inputs = load("inputs")
+    for fn in gold["inputs"]:
+        files.append(str(tmp_path / fn))
+        with open(files[-1], "w") as f:
+            for name, seq in inputs[fn]:
+                f.write(">%s\n%s\n" % (name, seq))
+    return files
+
+
+def run_case(name, tmp_path, index_module):
+    gold = load(name)
+    args = rem.rem_args(case_files(gold, tmp_path), **gold["args"])
+    G, idx = rem.align_genomes(args, index_module=index_module)
+    T = idx.T
+    if len(G.graph["paths"]) > 2:
+        rem.prune_nodes(G, T=T)
+    got = M.canonical(G, T)
+    assert [len(got["nodes"]), len(got["edges"]), sum(n[2] != 0 for n in got["nodes"])] == gold["counts"]
+    assert rem.aligned_bases(G, idx)[0] == gold["aligned_bases"] or idx.nsamples > 2
+    assert got["T_sha1"] == gold["T_sha1"]
+    for k in ("nodes", "edges", "walks", "T_lower"):
+        if k in gold:
+            assert got[k] == gold[k], k
+        else:
+            assert M.digest(got[k]) == gold[k + "_sha1"], k
+    return G, idx
+
+
+def test_chain_matches_pairwise_definition():
+    """The vectorised chain against a direct O(m^2) evaluation of the same recurrence on random anchors."""
+    rng = np.random.default_rng(3)
+    for trial in range(30):
+        k = int(rng.integers(2, 5))
+        m = int(rng.integers(1, 40))
+        mums = []
+        for _ in range(m):
+            base = int(rng.integers(0, 2000))
+            mums.append((int(rng.integers(5, 60)), k, {s: base + int(rng.integers(-40, 40)) + 100 * s for s in range(k)}))
+        if len({mm[2][0] for mm in mums}) < m:
+            continue
+        left = (0, 0, {s: -1000 + 100 * s for s in range(k)})
+        right = (0, 0, {s: 4000 + 100 * s for s in range(k)})
+        got = rem.chain(list(mums), left, right)
+        # direct evaluation
+        order = sorted(mums + [right], key=lambda x: x[2][0])
+        score = {id(left): 0}
+        link = {}
+        done = [left]
+        for mm in order:
+            best = None
+            for a in done:
+                if all(a[2][c] + a[0] <= mm[2][c] for c in mm[2]):
+                    w = score[id(a)] + mm[0] * (mm[1] * (mm[1] - 1) // 2) - rem.gapcost([a[2][c] + a[0] for c in mm[2]], [mm[2][c] for c in mm[2]])
+                    if best is None or w > best[0]:
+                        best = (w, a)
+            score[id(mm)], link[id(mm)] = best
+            done.append(mm)
+        assert (got[0][1] if got else None) == (score[id(link[id(right)])] if link[id(right)] is not left else None)
+        total = score[id(right)]
+        # the returned chain is colinear and adds up to the best total
+        chain = [c for c, _ in got][::-1]
+        for a, b in zip(chain, chain[1:]):
+            assert all(a[2][c] + a[0] <= b[2][c] for c in a[2])
+        acc, prev = 0, left
+        for c in chain + [right]:
+            acc += c[0] * (c[1] * (c[1] - 1) // 2) - rem.gapcost([prev[2][x] + prev[0] for x in c[2]], [c[2][x] for x in c[2]])
+            prev = c
+        assert acc == total
+
+
+def test_trim_overlap_and_gapcost_small_cases():
+    a = (10, 2, ((0, 0), (1, 100)))
+    b = (10, 2, ((0, 5), (1, 105)))      # overlaps a by 5 in both samples
+    c = (4, 2, ((0, 2), (1, 300)))       # contained in a in sample 0
+    out = rem.trim_overlap([a, b])
+    assert sorted(out) == sorted([(5, 2, ((0, 0), (1, 100))), (5, 2, ((0, 10), (1, 110)))])
+    # the reference's containment filter (schemes.py:171) judges the FIRST anchor by its successor: with c right
+    # behind it, a itself is dropped together with c
+    assert rem.trim_overlap([a, b, c]) == [b]
+    assert rem.gapcost([0, 0, 0], [3, 5, 10]) == 2 + 7 + 5
+    assert rem.gapcost([0, 0], [4, 9], model="star-med") == 9
+    assert rem.gapcost([1, 2], [4, 9], model="star-avg") == 5
+
+
+@pytest.mark.parametrize("name", ["t1_t2", "synth2_4k", "synth3_3k", "synth4_2k_seed"])
+def test_rem_emulated_small(emu_reveallib, tmp_path, name):
+    run_case(name, tmp_path, emu_reveallib.mod32)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in M.CASES])
+def test_rem_driver_on_reference_extension(tmp_path, name):
+    """The driver alone: run on the reference's own compiled extension (oracle/_ref) it must rebuild the golden
+    graphs exactly, whatever the size -- separates driver parity from index parity."""
+    import oracle.ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    run_case(name, tmp_path, R.module(32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [c[0] for c in M.CASES])
+def test_rem_matches_reference_graph_on_gpu(tmp_path, name):
+    from reveal_b200 import reveallib
+    run_case(name, tmp_path, reveallib)
+
+
+@pytest.mark.gpu
+def test_rem_gfa_spells_the_inputs(tmp_path):
+    """write_gfa: walking every P line over the S lines gives back the input sequence."""
+    from reveal_b200 import reveallib
+    gold = load("1a_1b_1c")
+    files = case_files(gold, tmp_path)
+    args = rem.rem_args(files, output=str(tmp_path / "out.gfa"))
+    G, idx, out = rem.align_cmd(args)
+    seg, paths = {}, {}
+    for line in open(out):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "S":
+            seg[f[1]] = f[2]
+        elif f[0] == "P":
+            paths[f[1]] = [x[:-1] for x in f[2].split(",")]
+    want = {}
+    for fn in files:
+        for name, seq in rem.fasta_reader(fn):
+            want[name] = seq
+    assert set(paths) == set(want)
+    for name in want:
+        assert "".join(seg[s] for s in paths[name]).upper() == want[name]
