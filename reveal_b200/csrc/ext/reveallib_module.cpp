@@ -750,7 +750,86 @@ static PyObject *mod_library(PyObject *, PyObject *) {
     return Py_BuildValue("(s,s)", g_api.path.c_str(), g_api.rv_version());
 }
 
+// chain_dp(start, length, gain, wpen, model, link, score) -- the O(m^2) chaining recurrence of the REM driver
+// (reveal_b200/rem.py:chain; reference: reveal/schemes.py:20-104 with utils.gapcost) on int64 buffers:
+//   start [m+1][k] coordinates (row 0 = the left bound, rows 1..m the anchors in processing order, row m = the right bound),
+//   length/gain [m+1]; model 0 = sumofpairs, 1 = star-avg, 2 = star-med; writes link[m+1] and score[m+1].
+// Row r may follow every earlier row that ends at or before it in every coordinate; equal totals go to the predecessor with
+// the higher score, then to the one that became available earlier, then to the one processed earlier.
+static PyObject *mod_chain_dp(PyObject *, PyObject *args) {
+    Py_buffer bs, bl, bg, bk, bc;
+    long long wpen;
+    int model;
+    if (!PyArg_ParseTuple(args, "y*y*y*Liw*w*", &bs, &bl, &bg, &wpen, &model, &bk, &bc)) return nullptr;
+    const Py_ssize_t rows = bl.len / 8;
+    const Py_ssize_t k = rows ? bs.len / 8 / rows : 0;
+    PyObject *ret = nullptr;
+    if (rows < 1 || k < 1 || bs.len != rows * k * 8 || bg.len != rows * 8 || bk.len != rows * 8 || bc.len != rows * 8 || k > 64) {
+        PyErr_SetString(PyExc_ValueError, "chain_dp: inconsistent buffer sizes");
+    } else {
+        const int64_t *start = (const int64_t *)bs.buf, *length = (const int64_t *)bl.buf, *gain = (const int64_t *)bg.buf;
+        int64_t *link = (int64_t *)bk.buf, *score = (int64_t *)bc.buf;
+        std::vector<int64_t> joined(rows, -1);
+        joined[0] = 0;
+        link[0] = 0;
+        score[0] = 0;
+        int64_t dist[64];
+        Py_BEGIN_ALLOW_THREADS
+        for (Py_ssize_t r = 1; r < rows; r++) {
+            const int64_t *sr = start + r * k;
+            Py_ssize_t best = -1;
+            int64_t best_total = 0;
+            for (Py_ssize_t i = 0; i < r; i++) {
+                const int64_t *si = start + i * k;
+                bool ok = true;
+                for (Py_ssize_t c = 0; c < k; c++) {
+                    int64_t d = sr[c] - (si[c] + length[i]);
+                    if (d < 0) { ok = false; break; }
+                    dist[c] = d;
+                }
+                if (!ok) continue;
+                if (joined[i] < 0) joined[i] = r;
+                int64_t pen = 0;
+                if (model == 0) {
+                    for (Py_ssize_t a = 0; a < k; a++)
+                        for (Py_ssize_t b = a + 1; b < k; b++) pen += dist[a] > dist[b] ? dist[a] - dist[b] : dist[b] - dist[a];
+                } else if (model == 1) {
+                    int64_t sum = 0;
+                    for (Py_ssize_t c = 0; c < k; c++) sum += dist[c];  // all distances are >= 0 here
+                    pen = sum / k;
+                } else {
+                    int64_t tmp[64];
+                    memcpy(tmp, dist, sizeof(int64_t) * k);
+                    for (Py_ssize_t a = 1; a < k; a++) {  // insertion sort, k is the number of samples
+                        int64_t v = tmp[a];
+                        Py_ssize_t b = a;
+                        while (b > 0 && tmp[b - 1] > v) { tmp[b] = tmp[b - 1]; b--; }
+                        tmp[b] = v;
+                    }
+                    pen = tmp[k / 2];
+                }
+                const int64_t total = score[i] + gain[r] - wpen * pen;
+                bool take = best < 0 || total > best_total;
+                if (!take && total == best_total) {
+                    if (score[i] != score[best]) take = score[i] > score[best];
+                    else if (joined[i] != joined[best]) take = joined[i] < joined[best];
+                }
+                if (take) { best = i; best_total = total; }
+            }
+            if (best < 0) { best = 0; best_total = 0; }  // cannot happen with a proper left bound
+            link[r] = best;
+            score[r] = best_total;
+        }
+        Py_END_ALLOW_THREADS
+        ret = Py_None;
+        Py_INCREF(ret);
+    }
+    PyBuffer_Release(&bs); PyBuffer_Release(&bl); PyBuffer_Release(&bg); PyBuffer_Release(&bk); PyBuffer_Release(&bc);
+    return ret;
+}
+
 static PyMethodDef module_methods[] = {
+    {"chain_dp", mod_chain_dp, METH_VARARGS, "Chaining recurrence of the REM driver on int64 buffers (see reveal_b200/rem.py:chain)."},
     {"_load", mod_load, METH_VARARGS, "Load a shared library exporting the C-ABI of include/reveal_b200.h (tests inject the emulated kernels)."},
     {"_library", mod_library, METH_NOARGS, "(path, version) of the loaded C-ABI library."},
     {nullptr, nullptr, 0, nullptr}};

@@ -18,11 +18,12 @@ attributes `offsets` {path id: offset in that path} and `aligned`, edges carry `
 
 What is different from the reference is the plumbing: no module-level globals (one `Rem` object per alignment owns
 the graph and the position -> node map, so several alignments can live in one process), the position lookup is a
-sorted map instead of an interval tree (nodes never overlap), and chaining is evaluated with numpy over all
+sorted array instead of an interval tree (nodes never overlap), and chaining is evaluated with numpy over all
 candidate predecessors at once instead of a Python loop per pair.  Results are checked against graphs minted
 from the reference's own driver (tests/golden/make_rem_golden.py, tests/test_rem.py).
 """
 import argparse
+import bisect
 import collections
 import gzip
 import logging
@@ -33,7 +34,6 @@ import uuid
 
 import networkx as nx
 import numpy as np
-from sortedcontainers import SortedDict
 
 log = logging.getLogger("reveal_b200.rem")
 
@@ -110,11 +110,33 @@ def chain(mums, left, right, gcmodel="sumofpairs", wscore=1, wpen=1):
         start[r] = [mum[2][k] for k in keys]
         length[r] = mum[0]
         gain[r] = wscore * (mum[0] * ((mum[1] * (mum[1] - 1)) // 2))
-    end = start + length[:, None]
     score = np.zeros(m + 1, dtype=np.int64)
+    link = np.zeros(m + 1, dtype=np.int64)
+    if _native_chain is not None and gcmodel in _MODELS:
+        _native_chain(start, length, gain, int(wpen), _MODELS[gcmodel], link, score)
+    else:
+        _chain_numpy(start, length, gain, wpen, gcmodel, link, score)
+    log.debug("Best score is: %d", score[m])
+    path = []
+    r = link[m]                                    # order[m-1] is `right` itself: the chain starts at its predecessor
+    while r != 0:
+        path.append((order[r - 1], int(score[r])))
+        r = link[r]
+    return path
+
+
+_MODELS = {"sumofpairs": 0, "star-avg": 1, "star-med": 2}
+try:  # the recurrence in C++ (csrc/ext/reveallib_module.cpp:mod_chain_dp); the numpy form below is its portable twin
+    from .reveallib import chain_dp as _native_chain
+except ImportError:  # extension not built (e.g. a source checkout used with the ctypes twin)
+    _native_chain = None
+
+
+def _chain_numpy(start, length, gain, wpen, gcmodel, link, score):
+    m = len(length) - 1
+    end = start + length[:, None]
     joined = np.full(m + 1, -1, dtype=np.int64)     # iteration at which a processed anchor became a candidate
     joined[0] = 0
-    link = np.zeros(m + 1, dtype=np.int64)
     for r in range(1, m + 1):
         ok = (end[:r] <= start[r][None, :]).all(axis=1)
         fresh = ok & (joined[:r] < 0)
@@ -127,13 +149,6 @@ def chain(mums, left, right, gcmodel="sumofpairs", wscore=1, wpen=1):
             best = best[np.lexsort((best, joined[best], -score[best]))]
         link[r] = best[0]
         score[r] = total.max()
-    log.debug("Best score is: %d", score[m])
-    path = []
-    r = link[m]                                    # order[m-1] is `right` itself: the chain starts at its predecessor
-    while r != 0:
-        path.append((order[r - 1], int(score[r])))
-        r = link[r]
-    return path
 
 
 def segment(mums):
@@ -199,19 +214,31 @@ class Rem(object):
         self.args = args
         self.G = nx.MultiDiGraph() if G is None else G
         self.multi = isinstance(self.G, nx.MultiDiGraph)
-        self.where = SortedDict()          # begin -> end of every Interval node
+        self.begins = []                   # sorted begin of every Interval node (bisect: C speed on the hot lookup)
+        self.end_of = {}                   # begin -> end
+        self._all_real = None
         for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict), ("startnodes", list),
                            ("endnodes", list)):
             self.G.graph.setdefault(key, empty())
 
     # ---- position -> node ------------------------------------------------------------------
     def node_at(self, pos):
-        i = self.where.bisect_right(pos) - 1
+        i = bisect.bisect_right(self.begins, pos) - 1
         if i >= 0:
-            begin, end = self.where.peekitem(i)
+            begin = self.begins[i]
+            end = self.end_of[begin]
             if pos < end:
                 return Interval(begin, end)
         raise KeyError("no node covers index position %d" % pos)
+
+    def _track(self, begin, end):
+        bisect.insort(self.begins, begin)
+        self.end_of[begin] = end
+
+    def _untrack(self, begin):
+        if begin in self.end_of:
+            del self.end_of[begin]
+            del self.begins[bisect.bisect_left(self.begins, begin)]
 
     # ---- input -----------------------------------------------------------------------------
     def add_sequence(self, index, name, seq):
@@ -228,7 +255,7 @@ class Rem(object):
         g["id2end"][sid] = len(seq)
         begin, end = index.addsequence(seq)
         node = Interval(begin, end)
-        self.where[begin] = end
+        self._track(begin, end)
         first, last = uuid.uuid4().hex, uuid.uuid4().hex
         self.G.add_node(first, offsets={sid: 0}, endpoint=True)
         g["startnodes"].append(first)
@@ -249,11 +276,25 @@ class Rem(object):
             self.add_sequence(index, name, seq)
 
     # ---- graph surgery -----------------------------------------------------------------------
+    # edge lists straight from the adjacency dicts, in the order networkx' in_edges / out_edges views would give them
     def _edges_in(self, node):
-        return [(u, d) for u, _, d in self.G.in_edges(node, data=True)]
+        pred = self.G._pred[node]
+        if self.multi:
+            return [(u, d) for u, keyed in pred.items() for d in keyed.values()]
+        return list(pred.items())
 
     def _edges_out(self, node):
-        return [(v, d) for _, v, d in self.G.out_edges(node, data=True)]
+        succ = self.G._succ[node]
+        if self.multi:
+            return [(v, d) for v, keyed in succ.items() for d in keyed.values()]
+        return list(succ.items())
+
+    def _only_real_paths(self):
+        """True when no path is a '*' (hidden) path -- always the case for FASTA input; lets the walks skip the
+        per-edge path filter."""
+        if self._all_real is None or self._all_real[0] != len(self.G.graph["id2path"]):
+            self._all_real = (len(self.G.graph["id2path"]), all(not p.startswith("*") for p in self.G.graph["id2path"].values()))
+        return self._all_real[1]
 
     def breaknode(self, node, pos, l):
         """Cuts [pos, pos+l) out of `node`; returns the matching piece and the set of left-over pieces
@@ -261,7 +302,7 @@ class Rem(object):
         G = self.G
         piece = Interval(pos, pos + l)
         if piece == node:
-            del self.where[node.begin]
+            self._untrack(node.begin)
             return node, set()
         att = G.nodes[node]
         ins, outs = self._edges_in(node), self._edges_out(node)
@@ -277,7 +318,7 @@ class Rem(object):
         for _, d in outs:
             (neg_paths if d["ofrom"] == "-" else pos_paths).update(d["paths"])
         assert not (pos_paths & neg_paths), "paths traverse node %s on both strands" % (node,)
-        del self.where[node.begin]
+        self._untrack(node.begin)
         G.add_node(piece, offsets=mid_off, aligned=0)
         others = set()
         head = tail = piece
@@ -287,7 +328,7 @@ class Rem(object):
             G.add_edge(head, piece, paths=set(pos_paths), ofrom="+", oto="+")
             if neg_paths:
                 G.add_edge(piece, head, paths=set(neg_paths), ofrom="-", oto="-")
-            self.where[head.begin] = head.end
+            self._track(head.begin, head.end)
             others.add(head)
         if node.end != pos + l:
             tail = Interval(pos + l, node.end)
@@ -295,7 +336,7 @@ class Rem(object):
             G.add_edge(piece, tail, paths=set(pos_paths), ofrom="+", oto="+")
             if neg_paths:
                 G.add_edge(tail, piece, paths=set(neg_paths), ofrom="-", oto="-")
-            self.where[tail.begin] = tail.end
+            self._track(tail.begin, tail.end)
             others.add(tail)
         G.remove_node(node)
         for u, d in ins:
@@ -316,16 +357,16 @@ class Rem(object):
         G.nodes[keep]["aligned"] = 1
         for node in group[1:]:
             if self.multi:
-                for u, _, d in list(G.in_edges(node, data=True)):
-                    for u2, _, d2 in G.in_edges(keep, data=True):
-                        if type(u2) is type(u) and u2 == u and d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
+                for u, d in self._edges_in(node):
+                    for d2 in G._pred[keep].get(u, {}).values():  # an edge u -> keep with the same orientation: unite the paths
+                        if d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
                             d2["paths"].update(d["paths"])
                             break
                     else:
                         G.add_edge(u, keep, **d)
-                for _, v, d in list(G.out_edges(node, data=True)):
-                    for _, v2, d2 in G.out_edges(keep, data=True):
-                        if type(v2) is type(v) and v2 == v and d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
+                for v, d in self._edges_out(node):
+                    for d2 in G._succ[keep].get(v, {}).values():
+                        if d2["oto"] == d["oto"] and d2["ofrom"] == d["ofrom"]:
                             d2["paths"].update(d["paths"])
                             break
                     else:
@@ -347,11 +388,15 @@ class Rem(object):
     def _neighbours(self, node, backwards):
         """Neighbours over edges that carry at least one real (non '*') path (rem.py:207-233)."""
         G = self.G
-        adj = G.pred[node] if backwards else G.succ[node]
+        adj = G._pred[node] if backwards else G._succ[node]
+        if self._only_real_paths():
+            return adj  # every edge carries at least one path
+        out = []
         for other, edges in adj.items():
             bundle = edges.values() if self.multi else (edges,)
             if any(_real(G, p) for e in bundle for p in e["paths"]):
-                yield other
+                out.append(other)
+        return out
 
     def _reach(self, source, backwards=False, through=()):
         """Breadth-first walk that stops at aligned nodes (class 1) and at the start/end markers (class 2) and runs
@@ -425,15 +470,17 @@ class Rem(object):
     def _lookup(self, mum):
         """Anchor in index coordinates -> (l, n, {path id: offset in the path}) (schemes.py:127-150)."""
         G = self.G
+        nodes = G._node
+        begins, end_of = self.begins, self.end_of
+        all_real = self._only_real_paths()
         l, _, spd = mum
         n = 0
         point = {}
         for _, pos in spd:
-            node = self.node_at(pos)
-            data = G.nodes[node]
-            rel = pos - node.begin
-            for k, off in data["offsets"].items():
-                if _real(G, k):
+            begin = begins[bisect.bisect_right(begins, pos) - 1]
+            rel = pos - begin
+            for k, off in nodes[(begin, end_of[begin])]["offsets"].items():
+                if all_real or _real(G, k):
                     n += 1
                     point[k] = off + rel
         return (l, n, point)
@@ -577,7 +624,7 @@ class Rem(object):
                         if lonely:
                             for v in group[1:]:
                                 if isinstance(v, Interval):
-                                    self.where.pop(v.begin, None)
+                                    self._untrack(v.begin)
                             self.mergenodes(group)
                             changed = True
 
@@ -644,7 +691,7 @@ def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targe
         begin, end = idx.addsequence(seq.upper())
         if end - begin > 0:
             node = Interval(begin, end)
-            rem.where[begin] = end
+            rem._track(begin, end)
             sid = len(G.graph["paths"])
             G.graph["path2id"][name] = sid
             G.graph["id2path"][sid] = name

@@ -100,6 +100,32 @@ def test_chain_matches_pairwise_definition():
         assert acc == total
 
 
+@pytest.mark.parametrize("model", ["sumofpairs", "star-avg", "star-med"])
+def test_native_chain_equals_numpy_chain(model):
+    """chain_dp of the compiled extension against its numpy twin: same links and scores, ties included."""
+    if rem._native_chain is None:
+        pytest.skip("extension module not built")
+    rng = np.random.default_rng(9)
+    for trial in range(60):
+        k = int(rng.integers(1, 6))
+        m = int(rng.integers(1, 120))
+        start = np.sort(rng.integers(0, 300 if trial % 2 else 5000, size=(m + 1, 1)), axis=0) + rng.integers(-30, 30, size=(m + 1, k))
+        start[0] = -100
+        start[m] = 10000
+        length = rng.integers(1, 40, size=m + 1)
+        length[0] = length[m] = 0
+        gain = rng.integers(0, 50, size=m + 1) * (1 if trial % 3 else 0)   # every third trial: all gains 0 -> many ties
+        out = []
+        for fn in (lambda *a: rem._native_chain(a[0], a[1], a[2], 2, rem._MODELS[model], a[3], a[4]),
+                   lambda *a: rem._chain_numpy(a[0], a[1], a[2], 2, model, a[3], a[4])):
+            link = np.zeros(m + 1, dtype=np.int64)
+            score = np.zeros(m + 1, dtype=np.int64)
+            fn(np.ascontiguousarray(start, dtype=np.int64), np.ascontiguousarray(length, dtype=np.int64),
+               np.ascontiguousarray(gain, dtype=np.int64), link, score)
+            out.append((link.tolist(), score.tolist()))
+        assert out[0] == out[1]
+
+
 def test_trim_overlap_and_gapcost_small_cases():
     a = (10, 2, ((0, 0), (1, 100)))
     b = (10, 2, ((0, 5), (1, 105)))      # overlaps a by 5 in both samples
