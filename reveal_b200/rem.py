@@ -1,6 +1,6 @@
 """REM -- recursive exact matching: the driver that turns the GPU index into an alignment graph.
 
-Host-side mirror of the reference's `reveal rem` for FASTA input, Python 3, on top of the drop-in `reveallib`:
+Host-side mirror of the reference's `reveal rem` (FASTA and GFA input), Python 3, on top of the drop-in `reveallib`:
 the reference entry points keep their names and meaning --
 
   align_genomes(args) -> (G, idx)      reveal/rem.py:511-611   (args: the namespace of `reveal rem`, see rem_args)
@@ -274,6 +274,111 @@ class Rem(object):
             if not contigs:
                 index.addsample(name)
             self.add_sequence(index, name, seq)
+
+    def read_gfa(self, gfafile, index):
+        """A GFA 1 graph as ONE sample of the index: every segment becomes its own `$`-terminated sequence and a
+        node, links become edges, P lines give every node its per-path offsets and every traversed edge its paths;
+        untraversed edges and nodes are dropped and each connected component gets one shared start and one shared
+        end marker (utils.py:377-657, the `index is not None` form used by rem)."""
+        G = self.G
+        g = G.graph
+        index.addsample(os.path.basename(gfafile))
+        node_of = {}
+        links, walks = [], []
+        with (gzip.open(gfafile, "rt") if gfafile.endswith(".gz") else open(gfafile, "r")) as f:
+            for line in f:
+                if line.startswith("S"):
+                    cols = line.strip().split("\t")
+                    seq = cols[2] if len(cols) > 2 else ""
+                    begin, end = index.addsequence(seq.upper())
+                    node = Interval(begin, end)
+                    self._track(begin, end)
+                    G.add_node(node, aligned=0, offsets={})
+                    node_of[int(cols[1])] = node
+                elif line.startswith("L"):
+                    links.append(line)
+                elif line.startswith("P"):
+                    walks.append(line)
+        for line in links:
+            e = line.strip().split("\t")
+            if not self.multi and (e[2] != "+" or e[4] != "+"):
+                continue  # a plain DiGraph only holds the forward-forward links
+            tags = {"ofrom": e[2], "oto": e[4]}
+            if len(e) > 5:
+                tags["cigar"] = e[5]
+            if "*" in e:
+                for tag in e[7:]:
+                    key, _, value = tag.split(":")
+                    tags[key.lower()] = value
+            tags["paths"] = set()
+            G.add_edge(node_of[int(e[1])], node_of[int(e[3])], **tags)
+        if not walks:
+            raise ValueError("No paths defined in GFA: %s" % gfafile)
+        firsts, lasts = set(), set()
+        for line in walks:
+            cols = line.rstrip().split("\t")
+            name = cols[1]
+            if not self.multi and name.startswith("*"):
+                continue
+            if name in g["paths"] or name in g["path2id"]:
+                raise ValueError("Graph already contains path for: %s" % name)
+            sid = len(g["path2id"])
+            g["paths"].append(name)
+            g["path2id"][name] = sid
+            g["id2path"][sid] = name
+            steps = [(int(x[:-1]), x[-1:]) for x in cols[2].split(",")]
+            offset = 0
+            prev = prev_orient = None
+            for nid, orient in steps:
+                node = node_of[nid]
+                G.nodes[node]["offsets"][sid] = offset
+                offset += node.end - node.begin
+                if prev is not None:
+                    if node not in G[prev]:
+                        raise ValueError("Path %s steps to segment %d over a link the graph does not define" % (name, nid))
+                    if self.multi:
+                        for d in G[prev][node].values():
+                            if d["oto"] == orient and d["ofrom"] == prev_orient:
+                                d["paths"].add(sid)
+                                break
+                        else:
+                            raise ValueError("Path %s: no link with orientation %s%s into segment %d" % (name, prev_orient, orient, nid))
+                    else:
+                        G[prev][node]["paths"].add(sid)
+                prev, prev_orient = node, orient
+            first, last = uuid.uuid4().hex, uuid.uuid4().hex
+            G.add_node(first, offsets={sid: 0}, endpoint=True)
+            G.add_edge(first, node_of[steps[0][0]], paths={sid}, ofrom="+", oto=steps[0][1])
+            firsts.add(first)
+            G.add_node(last, offsets={sid: offset}, endpoint=True)
+            G.add_edge(node_of[steps[-1][0]], last, paths={sid}, ofrom=steps[-1][1], oto="+")
+            lasts.add(last)
+            g["id2end"][sid] = offset
+        G.remove_edges_from([(u, v) for u, v, d in G.edges(data=True) if not d["paths"]])
+        for node in [n for n, d in G.nodes(data=True) if not d["offsets"]]:
+            if isinstance(node, Interval):
+                self._untrack(node.begin)
+            G.remove_node(node)
+        # one start and one end marker per connected component, in place of one pair per path
+        for comp in [c for c in nx.weakly_connected_components(G)]:
+            for markers, bucket, forward in ((lasts, "endnodes", False), (firsts, "startnodes", True)):
+                mine = [n for n in comp if n in markers]
+                if not mine:
+                    continue
+                shared = uuid.uuid4().hex
+                G.add_node(shared, offsets={}, seq="", endpoint=True)
+                g[bucket].append(shared)
+                for marker in mine:
+                    G.nodes[shared]["offsets"].update(G.nodes[marker]["offsets"])
+                    for other in list(G.successors(marker) if forward else G.predecessors(marker)):
+                        d = (G[marker][other] if forward else G[other][marker])
+                        d = d[0] if self.multi else d
+                        u, v = (shared, other) if forward else (other, shared)
+                        if not self.multi and G.has_edge(u, v):
+                            G[u][v]["paths"].update(d["paths"])
+                        else:
+                            G.add_edge(u, v, paths=d["paths"], ofrom=d["ofrom"], oto=d["oto"])
+            G.remove_nodes_from([n for n in comp if n in firsts or n in lasts])
 
     # ---- graph surgery -----------------------------------------------------------------------
     # edge lists straight from the adjacency dicts, in the order networkx' in_edges / out_edges views would give them
@@ -656,15 +761,16 @@ def _index_module(sa64=False):
 
 
 def align_genomes(args, index_module=None):
-    """FASTA files -> (alignment graph, index) (rem.py:511-611).  `args`: see rem_args; `index_module` lets tests
+    """FASTA and GFA files -> (alignment graph, index) (rem.py:511-611).  `args`: see rem_args; `index_module` lets tests
     run the driver on another build of the drop-in extension."""
     mod = index_module if index_module is not None else _index_module(args.sa64)
     idx = mod.index(sa=args.sa, lcp=args.lcp, cache=args.cache)
     rem = Rem(args)
     for fn in args.inputfiles:
         if fn.endswith(".gfa") or fn.endswith(".gfa.gz"):
-            raise NotImplementedError("graph input (.gfa) is not part of this driver yet: %s" % fn)
-        rem.read_fasta(fn, idx, contigs=args.contigs, toupper=args.toupper)
+            rem.read_gfa(fn, idx)
+        else:
+            rem.read_fasta(fn, idx, contigs=args.contigs, toupper=args.toupper)
     if len(idx.samples) <= 1:
         raise ValueError("Specify at least 2 targets to construct alignment. In case of multi-fasta, consider contigs=False.")
     idx.construct()

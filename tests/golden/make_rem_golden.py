@@ -44,6 +44,8 @@ PATCHES = [
     (r"xrange", "range"),
     (r"^class IntervalPatched\(intervaltree\.Interval\):", "class IntervalPatched(intervaltree.Interval):\n    __hash__=intervaltree.Interval.__hash__"),  # py3 drops __hash__ when __eq__ is defined
     (r"for node,data in G\.nodes\(data=True\):", "for node,data in list(G.nodes(data=True)):"),  # networkx 1 returned a list (rem.py:389)
+    (r"f=fopen\(outputfile,'wb'\)", "f=fopen(outputfile,'w')"),   # write_gfa writes str (utils.py:720); plain .gfa only here
+    (r" or type\(G\)==nx\.classes\.graphviews\.Sub(Multi)?DiGraph", ""),   # class names of networkx 2.0 (utils.py:730-733)
     (r"^import bubbles$", "bubbles=None"),                      # not used on this path
     (r"^import intervaltree$", "import rv_intervaltree as intervaltree"),
     (r"^from intervaltree import", "from rv_intervaltree import"),
@@ -168,6 +170,10 @@ CASES = [  # name, inputs (reference test files, or ("synth", n_genomes, length,
     ("synth2_4k", ("synth", 2, 4000, 21), {"minlength": 12}),           # small enough for the emulated kernels (CPU tests)
     ("synth3_3k", ("synth", 3, 3000, 22), {"minlength": 10}),
     ("synth4_2k_seed", ("synth", 4, 2000, 23), {"minlength": 8, "seedsize": 30, "minn": 3}),
+    # graph input (utils.read_gfa): the inputs are graphs the reference driver itself wrote from synthetic genomes
+    ("gfa_x_gfa_4x20k", ("graphs", 4, 20000, 31, [[0, 1], [2, 3]]), {}),
+    ("gfa_x_fasta_3x10k", ("graphs", 3, 10000, 32, [[0, 1], 2]), {"minlength": 15}),
+    ("gfa3_x_gfa2_5x3k", ("graphs", 5, 3000, 33, [[0, 1, 2], [3, 4]]), {"minlength": 10}),   # small: emulated kernels
     ("synth2_200k", ("synth", 2, 200000, 11), {}),
     ("synth3_60k", ("synth", 3, 60000, 12), {}),
     ("synth5_30k_n3", ("synth", 5, 30000, 13), {"minn": 3, "minlength": 15}),
@@ -190,7 +196,30 @@ def write_fasta(path, name, seq):
 
 def run_case(rem, tmp, inputs, overrides):
     out = {}
-    if isinstance(inputs, tuple):
+    if isinstance(inputs, tuple) and inputs[0] == "graphs":
+        from reveal_b200 import synth
+        _, ng, length, seed, groups = inputs
+        fastas = []
+        for k, g in enumerate(synth.genomes(ng, length, seed=seed)):
+            fastas.append(os.path.join(tmp, "%s_g%d.fa" % (seed, k)))
+            write_fasta(fastas[-1], "g%d" % k, g.tobytes().decode())
+        files, texts = [], []
+        for gi, group in enumerate(groups):
+            if isinstance(group, list):  # align the group first and write its graph as the reference does (align_cmd)
+                G, idx = rem.align_genomes(default_args([fastas[k] for k in group]))
+                T = idx.T
+                if len(G.graph["paths"]) > 2:
+                    rem.prune_nodes(G, T=T)
+                rem.seq2node(G, T, remap=False)
+                path = os.path.join(tmp, "%s_graph%d.gfa" % (seed, gi))
+                rem.write_gfa(G, T, outputfile=path)
+                files.append(path)
+                texts.append(["graph%d.gfa" % gi, open(path).read()])
+            else:
+                files.append(fastas[group])
+                texts.append(["g%d.fa" % group, open(fastas[group]).read()])
+        out["files"] = texts  # the input files themselves (graphs as the reference wrote them)
+    elif isinstance(inputs, tuple):
         from reveal_b200 import synth
         _, ng, length, seed = inputs
         files = []
