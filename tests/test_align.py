@@ -6,6 +6,7 @@ gpu-marked cases run the CUDA library."""
 import numpy as np
 import pytest
 
+import oracle.port as P
 import oracle.ref as R
 from align_callbacks import make_callbacks
 from util import random_related
@@ -91,3 +92,54 @@ def test_align_matches_reference_cuda(ns, length, minl, minn, maxsteps):
     samples = [[g.tobytes()] for g in gs]
     steps = compare(run_reference(samples, minl, minn, maxsteps), run_ours(reveallib, samples, minl, minn, maxsteps))
     assert steps > 10
+
+
+def test_align_callback_failure_is_reported_and_leaves_no_wreckage(emu_reveallib):
+    """A callback that raises in the middle of the recursion: align() raises (the reference sets err_flag and returns
+    NULL with reveallib.error, interface.c:366-370,409-414), every queued child is released, and the module keeps
+    working afterwards."""
+    from align_callbacks import make_callbacks
+    rng = np.random.default_rng(77)
+    T, nsep, _ = P.assemble(random_related(rng, 2, 2500, 4))
+    seqs = [s for s in bytes(T).decode().split("$") if s]
+
+    def fresh():
+        idx = emu_reveallib.index()
+        for k, s in enumerate(seqs):
+            idx.addsample("s%d" % k)
+            idx.addsequence(s)
+        idx.construct()
+        return idx
+
+    for bad in ("mumpicker", "graphalign", "garbage"):
+        log = []
+        mp, ga = make_callbacks(log, minlen=8)
+        calls = {"n": 0}
+
+        def picker(mums, idx, precomputed=False, minlength=0):
+            calls["n"] += 1
+            if bad == "mumpicker" and calls["n"] == 4:
+                raise ValueError("picker broke")
+            if bad == "garbage" and calls["n"] == 4:
+                return 42  # not a tuple: "call to mumpicker failed" (reveal.c:839-847)
+            return mp(mums, idx, precomputed=precomputed, minlength=minlength)
+
+        def aligner(idx, mum):
+            if bad == "graphalign" and calls["n"] >= 4:
+                raise RuntimeError("graphalign broke")
+            return ga(idx, mum)
+
+        idx = fresh()
+        with pytest.raises((emu_reveallib.error, ValueError, RuntimeError)):
+            idx.align(picker, aligner, minl=8, minn=2)
+        assert calls["n"] >= 4
+        del idx
+    # the module is still healthy: a complete alignment equals the reference's
+    log_a, log_b = [], []
+    idx = fresh()
+    mp, ga = make_callbacks(log_a, minlen=8)
+    idx.align(mp, ga, minl=8, minn=2)
+    ref = R.index_from_samples([[s] for s in seqs])
+    mp, ga = make_callbacks(log_b, minlen=8)
+    ref.align(mp, ga, minl=8, minn=2)
+    assert len(log_a) == len(log_b) and idx.T == ref.T[:ref.n]
