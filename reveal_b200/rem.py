@@ -217,6 +217,7 @@ class Rem(object):
         self.begins = []                   # sorted begin of every Interval node (bisect: C speed on the hot lookup)
         self.end_of = {}                   # begin -> end
         self._all_real = None
+        self._coords = {}                  # index position -> ((path id, coordinate in that path), ...), see _lookup
         for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict), ("startnodes", list),
                            ("endnodes", list)):
             self.G.graph.setdefault(key, empty())
@@ -573,21 +574,27 @@ class Rem(object):
 
     # ---- callback 1: graphmumpicker (schemes.py:197-361) -----------------------------------
     def _lookup(self, mum):
-        """Anchor in index coordinates -> (l, n, {path id: offset in the path}) (schemes.py:127-150)."""
-        G = self.G
-        nodes = G._node
-        begins, end_of = self.begins, self.end_of
-        all_real = self._only_real_paths()
+        """Anchor in index coordinates -> (l, n, {path id: offset in the path}) (schemes.py:127-150).
+
+        The per-path coordinates of an index position never change while the position is still unaligned (breaking
+        a node shifts the offsets of its pieces by exactly the cut, and only matched -- then aligned -- pieces are
+        ever merged), and anchors only ever lie in unaligned text, so they are looked up once per position."""
+        known = self._coords
         l, _, spd = mum
         n = 0
         point = {}
         for _, pos in spd:
-            begin = begins[bisect.bisect_right(begins, pos) - 1]
-            rel = pos - begin
-            for k, off in nodes[(begin, end_of[begin])]["offsets"].items():
-                if all_real or _real(G, k):
-                    n += 1
-                    point[k] = off + rel
+            coords = known.get(pos)
+            if coords is None:
+                G = self.G
+                begins = self.begins
+                begin = begins[bisect.bisect_right(begins, pos) - 1]
+                rel = pos - begin
+                all_real = self._only_real_paths()
+                coords = known[pos] = tuple((k, off + rel) for k, off in G._node[(begin, self.end_of[begin])]["offsets"].items()
+                                            if all_real or _real(G, k))
+            n += len(coords)
+            point.update(coords)
         return (l, n, point)
 
     def _bounds(self, idx, keys):
