@@ -151,6 +151,8 @@ def test_trim_overlap_and_gapcost_small_cases():
 
 @pytest.mark.parametrize("name", ["t1_t2", "synth2_4k", "synth3_3k", "synth4_2k_seed", "gfa3_x_gfa2_5x3k"])
 def test_rem_emulated_small(emu_reveallib, tmp_path, name):
+    if emu_reveallib.name == "ctypes" and name not in ("t1_t2", "synth2_4k"):
+        pytest.skip("the ctypes twin runs the two smallest cases (suite time)")
     run_case(name, tmp_path, emu_reveallib.mod32)
 
 
