@@ -390,6 +390,7 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(T, nsep, ns)
+            line["rem_configs0"] = rem_configs0()
         emit(line)
     L.rv_index_free(h)
     if world > 1:
@@ -423,6 +424,41 @@ def cpu_baseline(T, nsep, ns):
     tot = time.perf_counter() - t0
     return {"value": n / tot, "unit": "bases/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
             "sample": "the full workload once through the oracle port (SA-IS + Kasai + sweep)", "mums": int(k)}
+
+
+def rem_configs0():
+    """Secondary figure: BASELINE configs[0] -- `rem` of the reference's 1a.fa + 1b.fa -- end to end
+    through the REM driver (reveal_b200/rem.py): FASTA files -> alignment graph, aligned bases as the reference
+    counts them per second of wall time, on the B200 library and, with the same driver, on the reference's own
+    compiled extension (CPU, oracle/_ref).  The recursion is callback-bound, so this moves with the driver."""
+    import gzip
+    import tempfile
+    try:
+        from reveal_b200 import rem, reveallib
+        inputs = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "rem", "inputs.json.gz")).read())
+        with tempfile.TemporaryDirectory() as tmp:
+            files = []
+            for fn in ("1a.fa", "1b.fa"):
+                files.append(os.path.join(tmp, fn))
+                with open(files[-1], "w") as f:
+                    for name, seq in inputs[fn]:
+                        f.write(">%s\n%s\n" % (name, seq))
+
+            def run(module):
+                t0 = time.perf_counter()
+                G, idx = rem.align_genomes(rem.rem_args(files), index_module=module)
+                dt = time.perf_counter() - t0
+                bases, total, nodes = rem.aligned_bases(G, idx)
+                return {"seconds": dt, "aligned_bases": bases, "total_bases": total, "aligned_nodes": nodes, "aligned_bases_per_s": bases / dt}
+
+            run(reveallib)
+            out = {"workload": "rem 1a.fa 1b.fa (-m 20 -n 2), FASTA files -> alignment graph", "b200": run(reveallib)}
+            import oracle.ref as R
+            if R.available():
+                out["reference_extension_same_driver"] = run(R.module(32))
+            return out
+    except Exception as e:  # a secondary figure must never cost the bench line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 _REAL_STDOUT = None
