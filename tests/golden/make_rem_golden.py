@@ -170,6 +170,12 @@ CASES = [  # name, inputs (reference test files, or ("synth", n_genomes, length,
     ("synth2_4k", ("synth", 2, 4000, 21), {"minlength": 12}),           # small enough for the emulated kernels (CPU tests)
     ("synth3_3k", ("synth", 3, 3000, 22), {"minlength": 10}),
     ("synth4_2k_seed", ("synth", 4, 2000, 23), {"minlength": 8, "seedsize": 30, "minn": 3}),
+    # option branches of graphmumpicker / chain on small inputs
+    ("synth2_4k_m0_pvalue", ("synth", 2, 4000, 24), {"minlength": 0}),            # significance cut-off instead of a length
+    ("synth3_3k_maxsize", ("synth", 3, 3000, 25), {"minlength": 10, "maxsize": 200}),
+    ("synth3_3k_star_avg", ("synth", 3, 3000, 26), {"minlength": 10, "gcmodel": "star-avg"}),
+    ("synth3_3k_star_med", ("synth", 3, 3000, 27), {"minlength": 10, "gcmodel": "star-med", "wpen": 3, "wscore": 2}),
+    ("1c_1d_noupper", ["1c.fa", "1d.fa"], {"toupper": False}),                  # 1d.fa is lower-case: no matches without upper-casing
     # graph input (utils.read_gfa): the inputs are graphs the reference driver itself wrote from synthetic genomes
     ("gfa_x_gfa_4x20k", ("graphs", 4, 20000, 31, [[0, 1], [2, 3]]), {}),
     ("gfa_x_fasta_3x10k", ("graphs", 3, 10000, 32, [[0, 1], 2]), {"minlength": 15}),

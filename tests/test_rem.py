@@ -149,7 +149,7 @@ def test_trim_overlap_and_gapcost_small_cases():
     assert rem.gapcost([1, 2], [4, 9], model="star-avg") == 5
 
 
-@pytest.mark.parametrize("name", ["t1_t2", "synth2_4k", "synth3_3k", "synth4_2k_seed", "gfa3_x_gfa2_5x3k"])
+@pytest.mark.parametrize("name", ["t1_t2", "synth2_4k", "synth3_3k", "synth4_2k_seed", "gfa3_x_gfa2_5x3k", "synth2_4k_m0_pvalue"])
 def test_rem_emulated_small(emu_reveallib, tmp_path, name):
     if emu_reveallib.name == "ctypes" and name not in ("t1_t2", "synth2_4k"):
         pytest.skip("the ctypes twin runs the two smallest cases (suite time)")
