@@ -166,6 +166,11 @@ def test_rem_driver_on_reference_extension(tmp_path, name):
     run_case(name, tmp_path, R.module(32))
 
 
+def test_rem_emulated_wide_index_module(emu_reveallib, tmp_path):
+    """The same driver on reveallib64 (wider integers on the way out of the extension)."""
+    run_case("synth3_3k", tmp_path, emu_reveallib.mod64)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", [c[0] for c in M.CASES])
 def test_rem_matches_reference_graph_on_gpu(tmp_path, name):
