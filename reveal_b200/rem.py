@@ -218,8 +218,7 @@ class Rem(object):
         self.end_of = {}                   # begin -> end
         self._all_real = None
         self._coords = {}                  # index position -> ((path id, coordinate in that path), ...), see _lookup
-        for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict), ("startnodes", list),
-                           ("endnodes", list)):
+        for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict)):
             self.G.graph.setdefault(key, empty())
 
     # ---- position -> node ------------------------------------------------------------------
@@ -246,6 +245,8 @@ class Rem(object):
         """One path of the graph = one sequence of the index, between its own start and end marker nodes
         (utils.py:326-347)."""
         g = self.G.graph
+        g.setdefault("startnodes", [])
+        g.setdefault("endnodes", [])
         name = name.replace(":", "").replace(";", "")
         if name in g["paths"]:
             raise ValueError("Fasta with this name: \"%s\" is already contained in the graph." % name)
@@ -283,6 +284,8 @@ class Rem(object):
         end marker (utils.py:377-657, the `index is not None` form used by rem)."""
         G = self.G
         g = G.graph
+        g.setdefault("startnodes", [])
+        g.setdefault("endnodes", [])
         index.addsample(os.path.basename(gfafile))
         node_of = {}
         links, walks = [], []
@@ -863,7 +866,10 @@ def write_gfa(G, T, outputfile="reference.gfa", toupper=True):
                     f.write("L\t%d\t%s\t%d\t%s\t%s\n" % (ids[node], d.get("ofrom", "+"), ids[to], d.get("oto", "+"), d.get("cigar", "0M")))
         for name, sid in G.graph["path2id"].items():
             walk = []
-            for start in G.graph["startnodes"]:
+            if "startnodes" not in G.graph:  # a graph of align(): no markers, the path is its nodes in offset order
+                on_path = [n for n in order if sid in G.nodes[n]["offsets"]]
+                walk = ["%d+" % ids[n] for n in sorted(on_path, key=lambda n: G.nodes[n]["offsets"][sid])]
+            for start in G.graph.get("startnodes", ()):
                 if start in G and sid in G.nodes[start]["offsets"]:
                     node = start
                     while True:

@@ -137,6 +137,10 @@ def canonical(G, T):
     walks = {}
     for name, sid in G.graph["path2id"].items():
         walk = []
+        if "startnodes" not in G.graph:  # rem.align(): markers already removed -- the path in offset order
+            on_path = [n for n, d in G.nodes(data=True) if not isinstance(n, str) and sid in d["offsets"]]
+            walks[name] = [rank[key(n)] for n in sorted(on_path, key=lambda n: G.nodes[n]["offsets"][sid])]
+            continue
         for start in G.graph["startnodes"]:
             if sid in G.nodes[start]["offsets"]:
                 node = start
@@ -176,6 +180,9 @@ CASES = [  # name, inputs (reference test files, or ("synth", n_genomes, length,
     ("synth3_3k_star_avg", ("synth", 3, 3000, 26), {"minlength": 10, "gcmodel": "star-avg"}),
     ("synth3_3k_star_med", ("synth", 3, 3000, 27), {"minlength": 10, "gcmodel": "star-med", "wpen": 3, "wscore": 2}),
     ("1c_1d_noupper", ["1c.fa", "1d.fa"], {"toupper": False}),                  # 1d.fa is lower-case: no matches without upper-casing
+    # the library entry rem.align() on (name, sequence) tuples: plain DiGraph, shared start / end marker, prune_nodes
+    ("align_api_3x3k", ("align", 3, 3000, 41), {"minlength": 10, "seedsize": 0}),
+    ("align_api_2x4k", ("align", 2, 4000, 42), {"minlength": 12, "seedsize": 0, "trim": False}),
     # graph input (utils.read_gfa): the inputs are graphs the reference driver itself wrote from synthetic genomes
     ("gfa_x_gfa_4x20k", ("graphs", 4, 20000, 31, [[0, 1], [2, 3]]), {}),
     ("gfa_x_fasta_3x10k", ("graphs", 3, 10000, 32, [[0, 1], 2]), {"minlength": 15}),
@@ -202,6 +209,17 @@ def write_fasta(path, name, seq):
 
 def run_case(rem, tmp, inputs, overrides):
     out = {}
+    if isinstance(inputs, tuple) and inputs[0] == "align":
+        from reveal_b200 import synth
+        _, ng, length, seed = inputs
+        aobjs = [("g%d" % k, g.tobytes().decode()) for k, g in enumerate(synth.genomes(ng, length, seed=seed))]
+        G, idx = rem.align(aobjs, **overrides)
+        out["align"] = [ng, length, seed]
+        out.update(canonical(G, idx.T))
+        out["counts"] = [len(out["nodes"]), len(out["edges"]), sum(n[2] != 0 for n in out["nodes"])]
+        out["aligned_bases"] = sum(n[1] * len(n[0]) for n in out["nodes"] if n[2] != 0)
+        out["args"] = dict(overrides)
+        return out
     if isinstance(inputs, tuple) and inputs[0] == "graphs":
         from reveal_b200 import synth
         _, ng, length, seed, groups = inputs

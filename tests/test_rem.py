@@ -47,11 +47,17 @@ def case_files(gold, tmp_path):
 
 def run_case(name, tmp_path, index_module):
     gold = load(name)
-    args = rem.rem_args(case_files(gold, tmp_path), **gold["args"])
-    G, idx = rem.align_genomes(args, index_module=index_module)
-    T = idx.T
-    if len(G.graph["paths"]) > 2:
-        rem.prune_nodes(G, T=T)
+    if "align" in gold:  # the library entry on (name, sequence) tuples
+        ng, length, seed = gold["align"]
+        aobjs = [("g%d" % k, g.tobytes().decode()) for k, g in enumerate(synth.genomes(ng, length, seed=seed))]
+        G, idx = rem.align(aobjs, index_module=index_module, **gold["args"])
+        T = idx.T
+    else:
+        args = rem.rem_args(case_files(gold, tmp_path), **gold["args"])
+        G, idx = rem.align_genomes(args, index_module=index_module)
+        T = idx.T
+        if len(G.graph["paths"]) > 2:
+            rem.prune_nodes(G, T=T)
     got = M.canonical(G, T)
     assert [len(got["nodes"]), len(got["edges"]), sum(n[2] != 0 for n in got["nodes"])] == gold["counts"]
     assert sum(n[1] * len(n[0]) for n in got["nodes"] if n[2] != 0) == gold["aligned_bases"]
