@@ -57,6 +57,8 @@ CASES = [
 @needs_ref
 @pytest.mark.parametrize("name,ns,length,sigma,minl,minn", CASES)
 def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma, minl, minn):
+    if emu_reveallib.name == "ctypes" and name in ("triple", "five"):
+        pytest.skip("the ctypes twin runs a subset (suite time); the device code is the same")
     rng = np.random.default_rng(len(name) * 100 + length)
     samples = random_related(rng, ns, length, sigma, snp=0.03)
     steps = compare(run_reference(samples, minl, minn), run_ours(emu_reveallib, samples, minl, minn))
@@ -67,6 +69,8 @@ def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma
 @pytest.mark.parametrize("small_maxn,bubble_maxn", [("0", "100000"), ("0", "0"), ("600", "0")])
 def test_align_general_step_paths_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn):
     """RV_SMALL_MAXN / RV_BUBBLE_BLOCK_MAXN force the multi-kernel step and the grid-wide bubble detection."""
+    if emu_reveallib.name == "ctypes" and (small_maxn, bubble_maxn) != ("0", "0"):
+        pytest.skip("the ctypes twin runs one setting (suite time); these switches act below the C-ABI")
     monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
     monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
     rng = np.random.default_rng(77)
@@ -100,7 +104,7 @@ def test_align_callback_failure_is_reported_and_leaves_no_wreckage(emu_reveallib
     working afterwards."""
     from align_callbacks import make_callbacks
     rng = np.random.default_rng(77)
-    T, nsep, _ = P.assemble(random_related(rng, 2, 2500, 4))
+    T, nsep, _ = P.assemble(random_related(rng, 2, 1200, 4))
     seqs = [s for s in bytes(T).decode().split("$") if s]
 
     def fresh():

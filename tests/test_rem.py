@@ -174,6 +174,8 @@ def test_rem_driver_on_reference_extension(tmp_path, name):
 
 def test_rem_emulated_wide_index_module(emu_reveallib, tmp_path):
     """The same driver on reveallib64 (wider integers on the way out of the extension)."""
+    if emu_reveallib.name == "ctypes":
+        pytest.skip("compiled extension only (suite time)")
     run_case("synth3_3k", tmp_path, emu_reveallib.mod64)
 
 
