@@ -67,6 +67,15 @@ def build_extension(force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ failed for %s:\n%s\n%s" % (name, r.stdout, r.stderr))
+    # the alignment graph of the REM driver (host code, no CUDA)
+    src = os.path.join(CSRC, "ext", "remcore_module.cpp")
+    out = os.path.join(_HERE, "remcore" + suffix)
+    outs.append(out)
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I" + inc, src, "-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for remcore:\n%s\n%s" % (r.stdout, r.stderr))
     return outs
 
 

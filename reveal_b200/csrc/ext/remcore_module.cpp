@@ -1,0 +1,681 @@
+// remcore -- the alignment graph of the REM driver while the recursion runs, in C++ (host code).
+//
+// reveal_b200/rem.py keeps the graph as a networkx (Multi)DiGraph, like the reference (reveal/rem.py).  One recursion step
+// cuts the matched piece out of one node per sample, folds the pieces into one node and walks the neighbourhood to sort the
+// intervals of the sub-index into "before", "after" and "beside" the new node (graphalign -> breaknode, mergenodes,
+// segmentgraph; reference: reveal/rem.py:14-382).  On networkx dictionaries that is ~0.2 ms of interpreter time per aligned
+// MUM and the largest share of an end-to-end `rem`.  This module holds the same graph in flat vectors for the duration of the
+// recursion: rem.py loads it from the networkx graph after the input is read (Graph.add_node / add_edge), calls
+// Graph.graphalign from the callback, asks it for path coordinates (coords / node_offsets) in the mumpicker, and rebuilds the
+// networkx graph from Graph.export() afterwards.  Same semantics as the Python methods of rem.Rem, which stay as the readable
+// twin; tests/test_rem.py runs the golden graphs through both.
+//
+// Nodes are intervals [begin, end) of the index text (unique begin) or marker nodes (start / end of paths, any hashable
+// Python object).  Edges carry ofrom / oto ('+' / '-'), a set of path ids and, rarely, extra GFA tags (kept as a dict).
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <deque>
+#include <map>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct Edge {
+    int u, v;
+    char ofrom, oto;
+    std::vector<int32_t> paths;  // sorted, unique
+    PyObject *extra;             // dict of further attributes (cigar ...) or nullptr
+    bool alive;
+};
+
+struct Node {
+    int64_t begin, end;          // interval nodes
+    PyObject *key;               // marker nodes: the Python object that names them (owned); nullptr for intervals
+    int aligned;                 // -1: attribute absent (markers)
+    PyObject *extra;             // dict of further node attributes (endpoint, seq ...) or nullptr
+    std::vector<std::pair<int32_t, int64_t>> offsets;  // insertion-ordered, like the dict it mirrors
+    std::vector<int> out, in;    // edge ids, insertion order (dead ones are skipped and compacted lazily)
+    bool alive;
+};
+
+static void unite(std::vector<int32_t> &into, const std::vector<int32_t> &from) {
+    std::vector<int32_t> r;
+    r.reserve(into.size() + from.size());
+    std::set_union(into.begin(), into.end(), from.begin(), from.end(), std::back_inserter(r));
+    into.swap(r);
+}
+
+struct Graph {
+    PyObject_HEAD
+    bool multi;
+    PyObject *interval_cls;
+    std::vector<Node> *nodes;
+    std::vector<Edge> *edges;
+    std::unordered_map<int64_t, int> *by_begin;   // every alive interval node
+    std::map<int64_t, int> *tracked;              // unaligned interval nodes only: position -> node lookups
+    std::vector<char> *real;                      // per path id: not a '*' path
+    PyObject *markers;                            // dict: marker object -> node id
+    std::vector<uint32_t> *seen, *mark;           // epoch-stamped visit marks of the walks (no clearing per walk)
+    uint32_t epoch;
+};
+
+static int new_node(Graph *g) {
+    g->nodes->emplace_back();
+    Node &n = g->nodes->back();
+    n.begin = n.end = 0;
+    n.key = nullptr;
+    n.extra = nullptr;
+    n.aligned = -1;
+    n.alive = true;
+    return (int)g->nodes->size() - 1;
+}
+
+static int add_interval(Graph *g, int64_t b, int64_t e, int aligned, bool track) {
+    int id = new_node(g);
+    Node &n = (*g->nodes)[id];
+    n.begin = b;
+    n.end = e;
+    n.aligned = aligned;
+    (*g->by_begin)[b] = id;
+    if (track) (*g->tracked)[b] = id;
+    return id;
+}
+
+static bool is_real(const Graph *g, int32_t sid) { return sid < 0 || (size_t)sid >= g->real->size() || (*g->real)[sid]; }
+
+// networkx semantics: a MultiDiGraph always gets a new parallel edge; a DiGraph updates the attributes of an existing one
+static int add_edge(Graph *g, int u, int v, char ofrom, char oto, const std::vector<int32_t> &paths, PyObject *extra) {
+    if (!g->multi) {
+        for (int eid : (*g->nodes)[u].out) {
+            Edge &e = (*g->edges)[eid];
+            if (e.alive && e.v == v) {
+                e.ofrom = ofrom;
+                e.oto = oto;
+                e.paths = paths;
+                if (extra) {
+                    Py_INCREF(extra);
+                    Py_XSETREF(e.extra, extra);
+                }
+                return eid;
+            }
+        }
+    }
+    Edge e;
+    e.u = u;
+    e.v = v;
+    e.ofrom = ofrom;
+    e.oto = oto;
+    e.paths = paths;
+    e.extra = extra;
+    Py_XINCREF(extra);
+    e.alive = true;
+    g->edges->push_back(e);
+    int eid = (int)g->edges->size() - 1;
+    (*g->nodes)[u].out.push_back(eid);
+    (*g->nodes)[v].in.push_back(eid);
+    return eid;
+}
+
+static void compact(Graph *g, std::vector<int> &list) {
+    size_t w = 0;
+    for (size_t r = 0; r < list.size(); r++)
+        if ((*g->edges)[list[r]].alive) list[w++] = list[r];
+    list.resize(w);
+}
+
+static void remove_node(Graph *g, int id) {
+    Node &n = (*g->nodes)[id];
+    for (int eid : n.out) {
+        Edge &e = (*g->edges)[eid];
+        if (!e.alive) continue;
+        e.alive = false;
+        Py_CLEAR(e.extra);
+        if (e.v != id) compact(g, (*g->nodes)[e.v].in);
+    }
+    for (int eid : n.in) {
+        Edge &e = (*g->edges)[eid];
+        if (!e.alive) continue;
+        e.alive = false;
+        Py_CLEAR(e.extra);
+        if (e.u != id) compact(g, (*g->nodes)[e.u].out);
+    }
+    n.out.clear();
+    n.in.clear();
+    if (!n.key) {
+        auto it = g->by_begin->find(n.begin);
+        if (it != g->by_begin->end() && it->second == id) g->by_begin->erase(it);
+        auto jt = g->tracked->find(n.begin);
+        if (jt != g->tracked->end() && jt->second == id) g->tracked->erase(jt);
+    }
+    n.alive = false;
+    n.offsets.clear();
+    Py_CLEAR(n.extra);
+}
+
+static int node_at(Graph *g, int64_t pos) {
+    auto it = g->tracked->upper_bound(pos);
+    if (it == g->tracked->begin()) return -1;
+    --it;
+    const Node &n = (*g->nodes)[it->second];
+    return pos < n.end ? it->second : -1;
+}
+
+struct EdgeCopy {
+    int other;
+    char ofrom, oto;
+    std::vector<int32_t> paths;
+    PyObject *extra;  // borrowed while the original edge is alive; INCREF'd by add_edge when re-attached
+};
+
+// rem.Rem.breaknode (reference: rem.py:14-131): cut [pos, pos+l) out of node `id`; returns the matching piece, the left-over
+// pieces go to `others`
+static int breaknode(Graph *g, int id, int64_t pos, int64_t l, std::vector<int> &others) {
+    std::vector<Node> &N = *g->nodes;
+    if (N[id].begin == pos && N[id].end == pos + l) {
+        g->tracked->erase(N[id].begin);
+        return id;
+    }
+    const int64_t nb = N[id].begin, ne = N[id].end;
+    std::vector<EdgeCopy> ins, outs;
+    std::vector<PyObject *> held;
+    for (int eid : N[id].in) {
+        Edge &e = (*g->edges)[eid];
+        if (e.alive) { ins.push_back(EdgeCopy{e.u, e.ofrom, e.oto, e.paths, e.extra}); if (e.extra) { Py_INCREF(e.extra); held.push_back(e.extra); } }
+    }
+    for (int eid : N[id].out) {
+        Edge &e = (*g->edges)[eid];
+        if (e.alive) { outs.push_back(EdgeCopy{e.v, e.ofrom, e.oto, e.paths, e.extra}); if (e.extra) { Py_INCREF(e.extra); held.push_back(e.extra); } }
+    }
+    std::vector<int32_t> pos_paths, neg_paths;
+    if (ins.empty() && outs.empty())
+        for (auto &kv : N[id].offsets) pos_paths.push_back(kv.first);
+    for (auto &c : ins)
+        for (int32_t p : c.paths) (c.oto == '-' ? neg_paths : pos_paths).push_back(p);
+    for (auto &c : outs)
+        for (int32_t p : c.paths) (c.ofrom == '-' ? neg_paths : pos_paths).push_back(p);
+    for (auto *v : {&pos_paths, &neg_paths}) {
+        std::sort(v->begin(), v->end());
+        v->erase(std::unique(v->begin(), v->end()), v->end());
+    }
+    const std::vector<std::pair<int32_t, int64_t>> base = N[id].offsets;
+    const int64_t shift = pos - nb;
+    g->tracked->erase(nb);
+    g->by_begin->erase(nb);  // the head piece (if any) takes over this begin
+    int piece = add_interval(g, pos, pos + l, 0, false);
+    for (auto &kv : base) (*g->nodes)[piece].offsets.emplace_back(kv.first, kv.second + shift);
+    int head = piece, tail = piece;
+    if (nb != pos) {
+        head = add_interval(g, nb, pos, 0, true);
+        (*g->nodes)[head].offsets = base;
+        add_edge(g, head, piece, '+', '+', pos_paths, nullptr);
+        if (!neg_paths.empty()) add_edge(g, piece, head, '-', '-', neg_paths, nullptr);
+        others.push_back(head);
+    }
+    if (ne != pos + l) {
+        tail = add_interval(g, pos + l, ne, 0, true);
+        for (auto &kv : base) (*g->nodes)[tail].offsets.emplace_back(kv.first, kv.second + shift + l);
+        add_edge(g, piece, tail, '+', '+', pos_paths, nullptr);
+        if (!neg_paths.empty()) add_edge(g, tail, piece, '-', '-', neg_paths, nullptr);
+        others.push_back(tail);
+    }
+    remove_node(g, id);  // its begin may belong to the head piece by now: remove_node only erases map entries that still name `id`
+    for (auto &c : ins) add_edge(g, c.other, c.oto == '+' ? head : tail, c.ofrom, c.oto, c.paths, c.extra);
+    for (auto &c : outs) add_edge(g, c.ofrom == '+' ? tail : head, c.other, c.ofrom, c.oto, c.paths, c.extra);
+    for (PyObject *o : held) Py_DECREF(o);
+    return piece;
+}
+
+// rem.Rem.mergenodes (reference: rem.py:133-205)
+static int mergenodes(Graph *g, const std::vector<int> &group) {
+    std::vector<Node> &N = *g->nodes;
+    const int keep = group[0];
+    std::vector<std::pair<int32_t, int64_t>> offsets;
+    for (int id : group)
+        for (auto &kv : N[id].offsets) {
+            bool found = false;
+            for (auto &have : offsets)
+                if (have.first == kv.first) { have.second = kv.second; found = true; break; }
+            if (!found) offsets.push_back(kv);
+        }
+    N[keep].offsets = offsets;
+    N[keep].aligned = 1;
+    for (size_t k = 1; k < group.size(); k++) {
+        const int id = group[k];
+        std::vector<int> ins, outs;
+        for (int eid : N[id].in) if ((*g->edges)[eid].alive) ins.push_back(eid);
+        for (int eid : N[id].out) if ((*g->edges)[eid].alive) outs.push_back(eid);
+        for (int eid : ins) {
+            const Edge e = (*g->edges)[eid];
+            bool merged = false;
+            for (int kid : (*g->nodes)[keep].in) {
+                Edge &k2 = (*g->edges)[kid];
+                if (!k2.alive || k2.u != e.u) continue;
+                if (!g->multi || (k2.oto == e.oto && k2.ofrom == e.ofrom)) { unite(k2.paths, e.paths); merged = true; break; }
+            }
+            if (!merged) add_edge(g, e.u, keep, e.ofrom, e.oto, e.paths, e.extra);
+        }
+        for (int eid : outs) {
+            const Edge e = (*g->edges)[eid];
+            bool merged = false;
+            for (int kid : (*g->nodes)[keep].out) {
+                Edge &k2 = (*g->edges)[kid];
+                if (!k2.alive || k2.v != e.v) continue;
+                if (!g->multi || (k2.oto == e.oto && k2.ofrom == e.ofrom)) { unite(k2.paths, e.paths); merged = true; break; }
+            }
+            if (!merged) add_edge(g, keep, e.v, e.ofrom, e.oto, e.paths, e.extra);
+        }
+        remove_node(g, id);
+    }
+    return keep;
+}
+
+static bool edge_counts(const Graph *g, const Edge &e) {
+    for (int32_t p : e.paths)
+        if (is_real(g, p)) return true;
+    return false;
+}
+
+// rem.Rem._reach (reference bfs, rem.py:235-262): class 0 = unaligned (walked through), 1 = aligned (stop), 2 = marker (stop)
+static void reach(Graph *g, int source, bool backwards, const std::vector<int> *through, std::vector<std::pair<int, int>> &out) {
+    std::vector<Node> &N = *g->nodes;
+    std::vector<uint32_t> &seen = *g->seen;
+    if (seen.size() < N.size()) seen.resize(N.size() + N.size() / 2 + 16, 0);
+    const uint32_t tick = ++g->epoch;
+    std::deque<int> queue;
+    seen[source] = tick;
+    queue.push_back(source);
+    while (!queue.empty()) {
+        int cur = queue.front();
+        queue.pop_front();
+        const std::vector<int> &adj = backwards ? N[cur].in : N[cur].out;
+        for (int eid : adj) {
+            const Edge &e = (*g->edges)[eid];
+            if (!e.alive || !edge_counts(g, e)) continue;
+            int child = backwards ? e.u : e.v;
+            if (seen[child] == tick) continue;
+            seen[child] = tick;
+            const Node &c = N[child];
+            if (c.aligned < 0) {
+                out.emplace_back(child, 2);
+            } else if (c.aligned == 0 || (through && std::find(through->begin(), through->end(), child) != through->end())) {
+                queue.push_back(child);
+                out.emplace_back(child, 0);
+            } else {
+                out.emplace_back(child, 1);
+            }
+        }
+    }
+}
+
+static PyObject *interval_tuple(int64_t b, int64_t e) { return Py_BuildValue("(LL)", (long long)b, (long long)e); }
+
+// one side of rem.Rem.segmentgraph: the unaligned interval nodes strictly behind (or before) `node`, as a Python set of
+// (begin, end) tuples restricted to `members`
+static PyObject *side_of(Graph *g, int node, bool backwards, PyObject *members) {
+    std::vector<std::pair<int, int>> found;
+    reach(g, node, backwards, nullptr, found);
+    std::vector<int> side, stops;
+    for (auto &f : found) (f.second == 0 ? side : stops).push_back(f.first);
+    if (stops.size() > 1) {
+        std::vector<uint32_t> &back = *g->mark;
+        if (back.size() < g->nodes->size()) back.resize(g->nodes->size() + g->nodes->size() / 2 + 16, 0);
+        const uint32_t tag = ++g->epoch;
+        for (int stop : stops) {
+            std::vector<std::pair<int, int>> r;
+            reach(g, stop, !backwards, &stops, r);
+            for (auto &f : r)
+                if (f.second == 0) back[f.first] = tag;
+        }
+        std::vector<int> kept;
+        for (int s : side)
+            if (back[s] == tag) kept.push_back(s);
+        side.swap(kept);
+    }
+    PyObject *res = PySet_New(nullptr);
+    if (!res) return nullptr;
+    for (int s : side) {
+        const Node &n = (*g->nodes)[s];
+        if (n.key) continue;
+        PyObject *t = interval_tuple(n.begin, n.end);
+        if (!t) { Py_DECREF(res); return nullptr; }
+        int has = PySet_Contains(members, t);
+        if (has < 0 || (has && PySet_Add(res, t) < 0)) { Py_DECREF(t); Py_DECREF(res); return nullptr; }
+        Py_DECREF(t);
+    }
+    return res;
+}
+
+static int find_node(Graph *g, PyObject *key) {
+    if (PyTuple_Check(key) && PyTuple_GET_SIZE(key) >= 2 && PyLong_Check(PyTuple_GET_ITEM(key, 0))) {
+        long long b = PyLong_AsLongLong(PyTuple_GET_ITEM(key, 0));
+        auto it = g->by_begin->find(b);
+        if (it == g->by_begin->end()) { PyErr_Format(PyExc_KeyError, "no interval node starts at %lld", b); return -1; }
+        return it->second;
+    }
+    PyObject *v = PyDict_GetItemWithError(g->markers, key);
+    if (!v) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, key); return -1; }
+    return (int)PyLong_AsLong(v);
+}
+
+static bool subset_of(const std::vector<std::pair<int32_t, int64_t>> &offs, const std::vector<std::pair<int32_t, int64_t>> &msamples) {
+    for (auto &kv : offs) {
+        bool in = false;
+        for (auto &m : msamples)
+            if (m.first == kv.first) { in = true; break; }
+        if (!in) return false;
+    }
+    return true;
+}
+
+// ---- Python methods -----------------------------------------------------------------------------------------------------------
+static PyObject *Graph_new(PyTypeObject *type, PyObject *, PyObject *) {
+    Graph *g = (Graph *)type->tp_alloc(type, 0);
+    if (!g) return nullptr;
+    g->multi = true;
+    g->interval_cls = nullptr;
+    g->nodes = new std::vector<Node>();
+    g->edges = new std::vector<Edge>();
+    g->by_begin = new std::unordered_map<int64_t, int>();
+    g->tracked = new std::map<int64_t, int>();
+    g->real = new std::vector<char>();
+    g->seen = new std::vector<uint32_t>();
+    g->mark = new std::vector<uint32_t>();
+    g->epoch = 0;
+    g->markers = PyDict_New();
+    return (PyObject *)g;
+}
+
+static int Graph_init(Graph *g, PyObject *args, PyObject *) {
+    int multi = 1;
+    PyObject *cls = nullptr, *real = nullptr;
+    if (!PyArg_ParseTuple(args, "pOO", &multi, &cls, &real)) return -1;
+    g->multi = multi != 0;
+    Py_INCREF(cls);
+    Py_XSETREF(g->interval_cls, cls);
+    PyObject *it = PyObject_GetIter(real);
+    if (!it) return -1;
+    g->real->clear();
+    while (PyObject *x = PyIter_Next(it)) {
+        g->real->push_back(PyObject_IsTrue(x) ? 1 : 0);
+        Py_DECREF(x);
+    }
+    Py_DECREF(it);
+    return PyErr_Occurred() ? -1 : 0;
+}
+
+static void Graph_dealloc(Graph *g) {
+    if (g->nodes)
+        for (Node &n : *g->nodes) { Py_XDECREF(n.key); Py_XDECREF(n.extra); }
+    if (g->edges)
+        for (Edge &e : *g->edges) Py_XDECREF(e.extra);
+    delete g->nodes;
+    delete g->edges;
+    delete g->by_begin;
+    delete g->tracked;
+    delete g->real;
+    delete g->seen;
+    delete g->mark;
+    Py_XDECREF(g->markers);
+    Py_XDECREF(g->interval_cls);
+    Py_TYPE(g)->tp_free((PyObject *)g);
+}
+
+static bool read_offsets(PyObject *d, std::vector<std::pair<int32_t, int64_t>> &out) {
+    PyObject *k, *v;
+    Py_ssize_t p = 0;
+    while (PyDict_Next(d, &p, &k, &v)) out.emplace_back((int32_t)PyLong_AsLong(k), (int64_t)PyLong_AsLongLong(v));
+    return !PyErr_Occurred();
+}
+
+static bool read_paths(PyObject *s, std::vector<int32_t> &out) {
+    PyObject *it = PyObject_GetIter(s);
+    if (!it) return false;
+    while (PyObject *x = PyIter_Next(it)) {
+        out.push_back((int32_t)PyLong_AsLong(x));
+        Py_DECREF(x);
+    }
+    Py_DECREF(it);
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return !PyErr_Occurred();
+}
+
+// add_node(key, aligned or None, offsets dict, extra dict or None)
+static PyObject *Graph_add_node(Graph *g, PyObject *args) {
+    PyObject *key, *aligned, *offsets, *extra;
+    if (!PyArg_ParseTuple(args, "OOOO", &key, &aligned, &offsets, &extra)) return nullptr;
+    int al = aligned == Py_None ? -1 : (int)PyLong_AsLong(aligned);
+    int id;
+    if (PyTuple_Check(key) && PyTuple_GET_SIZE(key) >= 2 && PyLong_Check(PyTuple_GET_ITEM(key, 0))) {
+        long long b = PyLong_AsLongLong(PyTuple_GET_ITEM(key, 0)), e = PyLong_AsLongLong(PyTuple_GET_ITEM(key, 1));
+        id = add_interval(g, b, e, al, al == 0);
+    } else {
+        id = new_node(g);
+        Node &n = (*g->nodes)[id];
+        n.key = key;
+        Py_INCREF(key);
+        n.aligned = al;
+        PyObject *idobj = PyLong_FromLong(id);
+        PyDict_SetItem(g->markers, key, idobj);
+        Py_DECREF(idobj);
+    }
+    Node &n = (*g->nodes)[id];
+    if (offsets != Py_None && !read_offsets(offsets, n.offsets)) return nullptr;
+    if (extra != Py_None && PyDict_Size(extra) > 0) { n.extra = extra; Py_INCREF(extra); }
+    if (PyErr_Occurred()) return nullptr;
+    Py_RETURN_NONE;
+}
+
+// add_edge(u, v, ofrom, oto, paths, extra dict or None)
+static PyObject *Graph_add_edge(Graph *g, PyObject *args) {
+    PyObject *u, *v, *paths, *extra;
+    const char *ofrom, *oto;
+    if (!PyArg_ParseTuple(args, "OOssOO", &u, &v, &ofrom, &oto, &paths, &extra)) return nullptr;
+    int iu = find_node(g, u);
+    if (iu < 0) return nullptr;
+    int iv = find_node(g, v);
+    if (iv < 0) return nullptr;
+    std::vector<int32_t> p;
+    if (!read_paths(paths, p)) return nullptr;
+    add_edge(g, iu, iv, ofrom[0], oto[0], p, (extra != Py_None && PyDict_Size(extra) > 0) ? extra : nullptr);
+    Py_RETURN_NONE;
+}
+
+static PyObject *offsets_dict(const std::vector<std::pair<int32_t, int64_t>> &offs) {
+    PyObject *d = PyDict_New();
+    if (!d) return nullptr;
+    for (auto &kv : offs) {
+        PyObject *k = PyLong_FromLong(kv.first), *v = PyLong_FromLongLong(kv.second);
+        PyDict_SetItem(d, k, v);
+        Py_DECREF(k);
+        Py_DECREF(v);
+    }
+    return d;
+}
+
+// coords(pos) -> ((path id, coordinate), ...) over the real paths of the unaligned node that covers index position pos
+static PyObject *Graph_coords(Graph *g, PyObject *arg) {
+    long long pos = PyLong_AsLongLong(arg);
+    if (pos == -1 && PyErr_Occurred()) return nullptr;
+    int id = node_at(g, pos);
+    if (id < 0) { PyErr_Format(PyExc_KeyError, "no node covers index position %lld", pos); return nullptr; }
+    const Node &n = (*g->nodes)[id];
+    const int64_t rel = pos - n.begin;
+    Py_ssize_t cnt = 0;
+    for (auto &kv : n.offsets) cnt += is_real(g, kv.first);
+    PyObject *t = PyTuple_New(cnt);
+    Py_ssize_t w = 0;
+    for (auto &kv : n.offsets)
+        if (is_real(g, kv.first)) PyTuple_SET_ITEM(t, w++, Py_BuildValue("(iL)", (int)kv.first, (long long)(kv.second + rel)));
+    return t;
+}
+
+// node_offsets(node) -> {path id: offset}
+static PyObject *Graph_node_offsets(Graph *g, PyObject *key) {
+    int id = find_node(g, key);
+    if (id < 0) return nullptr;
+    return offsets_dict((*g->nodes)[id].offsets);
+}
+
+// graphalign(nodes, leftnode, rightnode, l, positions) -> (leading, trailing, matching, rest, merged, newleft, newright)
+// rem.Rem.graphalign (reference: rem.py:317-382); `nodes` (the set of the sub-index) is updated in place
+static PyObject *Graph_graphalign(Graph *g, PyObject *args) {
+    PyObject *nodes, *leftnode, *rightnode, *positions;
+    long long l;
+    if (!PyArg_ParseTuple(args, "OOOLO", &nodes, &leftnode, &rightnode, &l, &positions)) return nullptr;
+    if (!PySet_Check(nodes)) { PyErr_SetString(PyExc_TypeError, "nodes must be a set"); return nullptr; }
+    PyObject *seq = PySequence_Fast(positions, "positions must be a sequence");
+    if (!seq) return nullptr;
+    std::vector<int> pieces;
+    PyObject *matching = PySet_New(nullptr);
+    const Py_ssize_t np = PySequence_Fast_GET_SIZE(seq);
+    for (Py_ssize_t k = 0; k < np; k++) {
+        long long pos = PyLong_AsLongLong(PySequence_Fast_GET_ITEM(seq, k));
+        if (pos == -1 && PyErr_Occurred()) { Py_DECREF(seq); Py_DECREF(matching); return nullptr; }
+        PyObject *m = interval_tuple(pos, pos + l);
+        PySet_Add(matching, m);
+        Py_DECREF(m);
+        int old = node_at(g, pos);
+        if (old < 0 || (*g->nodes)[old].end - pos < l) {
+            PyErr_Format(PyExc_KeyError, "no unaligned node holds [%lld, %lld)", pos, pos + l);
+            Py_DECREF(seq); Py_DECREF(matching);
+            return nullptr;
+        }
+        PyObject *oldt = interval_tuple((*g->nodes)[old].begin, (*g->nodes)[old].end);
+        std::vector<int> others;
+        int piece = breaknode(g, old, pos, l, others);
+        pieces.push_back(piece);
+        if (PySet_Discard(nodes, oldt) < 0) { Py_DECREF(oldt); Py_DECREF(seq); Py_DECREF(matching); return nullptr; }
+        Py_DECREF(oldt);
+        for (int o : others) {
+            PyObject *t = interval_tuple((*g->nodes)[o].begin, (*g->nodes)[o].end);
+            PySet_Add(nodes, t);
+            Py_DECREF(t);
+        }
+    }
+    Py_DECREF(seq);
+    if (pieces.empty()) { Py_DECREF(matching); PyErr_SetString(PyExc_ValueError, "a match needs at least one position"); return nullptr; }
+    int merged = mergenodes(g, pieces);
+    const std::vector<std::pair<int32_t, int64_t>> msamples = (*g->nodes)[merged].offsets;
+    PyObject *members = PySet_New(nodes);
+    PyObject *trailing = members ? side_of(g, merged, false, members) : nullptr;
+    PyObject *leading = trailing ? side_of(g, merged, true, members) : nullptr;
+    PyObject *rest = nullptr, *merged_obj = nullptr, *ret = nullptr;
+    if (leading) {
+        rest = PySet_New(members);
+        PyObject *it;
+        for (PyObject *side : {leading, trailing}) {
+            it = PyObject_GetIter(side);
+            while (PyObject *x = PyIter_Next(it)) { PySet_Discard(rest, x); Py_DECREF(x); }
+            Py_DECREF(it);
+        }
+        const Node &mn = (*g->nodes)[merged];
+        merged_obj = PyObject_CallFunction(g->interval_cls, "LL", (long long)mn.begin, (long long)mn.end);
+    }
+    if (merged_obj) {
+        PyObject *newleft = merged_obj, *newright = merged_obj;
+        // a side with intervals of samples outside the match is not cleanly cut by it: keep the old bound
+        for (int which = 0; which < 2; which++) {
+            PyObject *side = which == 0 ? leading : trailing;
+            PyObject *it = PyObject_GetIter(side);
+            while (PyObject *x = PyIter_Next(it)) {
+                int id = find_node(g, x);
+                Py_DECREF(x);
+                if (id < 0) { PyErr_Clear(); continue; }
+                if (!subset_of((*g->nodes)[id].offsets, msamples)) {
+                    if (which == 0) newright = rightnode; else newleft = leftnode;
+                    break;
+                }
+            }
+            Py_DECREF(it);
+        }
+        ret = PyTuple_Pack(7, leading, trailing, matching, rest, merged_obj, newleft, newright);
+    }
+    Py_XDECREF(members); Py_XDECREF(trailing); Py_XDECREF(leading); Py_XDECREF(rest); Py_XDECREF(merged_obj); Py_DECREF(matching);
+    return ret;
+}
+
+// export() -> (nodes, edges): nodes = [(key, aligned or None, offsets dict, extra or None)], edges = [(u, v, ofrom, oto, paths set, extra or None)]
+static PyObject *Graph_export(Graph *g, PyObject *) {
+    PyObject *nodes = PyList_New(0), *edges = PyList_New(0);
+    std::vector<PyObject *> keys(g->nodes->size(), nullptr);
+    for (size_t i = 0; i < g->nodes->size(); i++) {
+        const Node &n = (*g->nodes)[i];
+        if (!n.alive) continue;
+        PyObject *key;
+        if (n.key) { key = n.key; Py_INCREF(key); }
+        else key = PyObject_CallFunction(g->interval_cls, "LL", (long long)n.begin, (long long)n.end);
+        if (!key) { Py_DECREF(nodes); Py_DECREF(edges); return nullptr; }
+        keys[i] = key;
+        PyObject *al = n.aligned < 0 ? (Py_INCREF(Py_None), Py_None) : PyLong_FromLong(n.aligned);
+        PyObject *offs = offsets_dict(n.offsets);
+        PyObject *row = PyTuple_Pack(4, key, al, offs, n.extra ? n.extra : Py_None);
+        PyList_Append(nodes, row);
+        Py_DECREF(row); Py_DECREF(al); Py_DECREF(offs);
+    }
+    // edges in the order networkx would hold them: by source node, then by insertion
+    for (size_t i = 0; i < g->nodes->size(); i++) {
+        const Node &n = (*g->nodes)[i];
+        if (!n.alive) continue;
+        for (int eid : n.out) {
+            const Edge &e = (*g->edges)[eid];
+            if (!e.alive) continue;
+            PyObject *paths = PySet_New(nullptr);
+            for (int32_t p : e.paths) { PyObject *x = PyLong_FromLong(p); PySet_Add(paths, x); Py_DECREF(x); }
+            char f[2] = {e.ofrom, 0}, t[2] = {e.oto, 0};
+            PyObject *row = Py_BuildValue("(OOssOO)", keys[e.u], keys[e.v], f, t, paths, e.extra ? e.extra : Py_None);
+            PyList_Append(edges, row);
+            Py_DECREF(row); Py_DECREF(paths);
+        }
+    }
+    for (PyObject *k : keys) Py_XDECREF(k);
+    PyObject *ret = PyTuple_Pack(2, nodes, edges);
+    Py_DECREF(nodes); Py_DECREF(edges);
+    return ret;
+}
+
+static PyObject *Graph_stats(Graph *g, PyObject *) {
+    long alive_n = 0, alive_e = 0;
+    for (const Node &n : *g->nodes) alive_n += n.alive;
+    for (const Edge &e : *g->edges) alive_e += e.alive;
+    return Py_BuildValue("(llll)", alive_n, alive_e, (long)g->nodes->size(), (long)g->edges->size());
+}
+
+static PyMethodDef Graph_methods[] = {
+    {"add_node", (PyCFunction)Graph_add_node, METH_VARARGS, "add_node(key, aligned or None, offsets, extra or None)"},
+    {"add_edge", (PyCFunction)Graph_add_edge, METH_VARARGS, "add_edge(u, v, ofrom, oto, paths, extra or None)"},
+    {"coords", (PyCFunction)Graph_coords, METH_O, "coords(pos) -> ((path id, coordinate), ...) of the real paths through index position pos"},
+    {"node_offsets", (PyCFunction)Graph_node_offsets, METH_O, "node_offsets(node) -> {path id: offset}"},
+    {"graphalign", (PyCFunction)Graph_graphalign, METH_VARARGS,
+     "graphalign(nodes, leftnode, rightnode, l, positions) -> (leading, trailing, matching, rest, merged, newleft, newright)"},
+    {"export", (PyCFunction)Graph_export, METH_NOARGS, "export() -> (node rows, edge rows) of the alive graph"},
+    {"stats", (PyCFunction)Graph_stats, METH_NOARGS, "(alive nodes, alive edges, node slots, edge slots)"},
+    {nullptr, nullptr, 0, nullptr}};
+
+static PyTypeObject GraphType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+
+static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "remcore",
+                                       "Alignment graph of the REM driver during the recursion (see reveal_b200/rem.py).", -1, nullptr};
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) PyObject *PyInit_remcore(void) {
+    GraphType.tp_name = "remcore.Graph";
+    GraphType.tp_basicsize = sizeof(Graph);
+    GraphType.tp_flags = Py_TPFLAGS_DEFAULT;
+    GraphType.tp_doc = "Graph(multi, interval_class, real_path_flags)";
+    GraphType.tp_new = Graph_new;
+    GraphType.tp_init = (initproc)Graph_init;
+    GraphType.tp_dealloc = (destructor)Graph_dealloc;
+    GraphType.tp_methods = Graph_methods;
+    if (PyType_Ready(&GraphType) < 0) return nullptr;
+    PyObject *m = PyModule_Create(&moduledef);
+    if (!m) return nullptr;
+    Py_INCREF(&GraphType);
+    PyModule_AddObject(m, "Graph", (PyObject *)&GraphType);
+    return m;
+}

@@ -132,6 +132,12 @@ except ImportError:  # extension not built (e.g. a source checkout used with the
     _native_chain = None
 
 
+try:  # the alignment graph in C++ for the duration of the recursion (csrc/ext/remcore_module.cpp); Rem's own methods are its twin
+    from . import remcore as _remcore
+except ImportError:
+    _remcore = None
+
+
 def _chain_numpy(start, length, gain, wpen, gcmodel, link, score):
     m = len(length) - 1
     end = start + length[:, None]
@@ -218,6 +224,7 @@ class Rem(object):
         self.end_of = {}                   # begin -> end
         self._all_real = None
         self._coords = {}                  # index position -> ((path id, coordinate in that path), ...), see _lookup
+        self.core = None                   # remcore.Graph while the recursion runs (see recursion_graph)
         for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict)):
             self.G.graph.setdefault(key, empty())
 
@@ -384,6 +391,53 @@ class Rem(object):
                             G.add_edge(u, v, paths=d["paths"], ofrom=d["ofrom"], oto=d["oto"])
             G.remove_nodes_from([n for n in comp if n in firsts or n in lasts])
 
+    # ---- the graph during the recursion ----------------------------------------------------------
+    def recursion_graph(self):
+        """Context manager around index.align(): moves the graph into remcore.Graph (flat C++ vectors; graphalign and
+        the coordinate look-ups of the mumpicker then run there) and rebuilds the networkx graph from it afterwards.
+        Without the compiled module, or with RV_REM_PYTHON_GRAPH=1, the recursion works on the networkx graph itself."""
+        return _RecursionGraph(self)
+
+    def _load_core(self):
+        if _remcore is None or os.environ.get("RV_REM_PYTHON_GRAPH", "0") not in ("", "0"):
+            return
+        G = self.G
+        ids = G.graph["id2path"]
+        core = _remcore.Graph(self.multi, Interval, [not ids[sid].startswith("*") for sid in range(len(ids))])
+        for node, d in G.nodes(data=True):
+            extra = {k: v for k, v in d.items() if k not in ("offsets", "aligned")}
+            core.add_node(node, d.get("aligned"), d.get("offsets") or {}, extra or None)
+        for u, v, d in G.edges(data=True):
+            extra = {k: x for k, x in d.items() if k not in ("paths", "ofrom", "oto")}
+            core.add_edge(u, v, d["ofrom"], d["oto"], d["paths"], extra or None)
+        self.core = core
+
+    def _unload_core(self):
+        core, self.core = self.core, None
+        if core is None:
+            return
+        G = self.G
+        nodes, edges = core.export()
+        keep = dict(G.graph)
+        G.clear()
+        G.graph.update(keep)
+        self.begins, self.end_of = [], {}
+        for key, aligned, offsets, extra in nodes:
+            attrs = dict(extra) if extra else {}
+            attrs["offsets"] = offsets
+            if aligned is not None:
+                attrs["aligned"] = aligned
+                if aligned == 0:
+                    self.end_of[key.begin] = key.end
+            G.add_node(key, **attrs)
+        self.begins = sorted(self.end_of)
+        for u, v, ofrom, oto, paths, extra in edges:
+            attrs = dict(extra) if extra else {}
+            G.add_edge(u, v, paths=paths, ofrom=ofrom, oto=oto, **attrs)
+
+    def _offsets_of(self, node):
+        return self.core.node_offsets(node) if self.core is not None else self.G.nodes[node]["offsets"]
+
     # ---- graph surgery -----------------------------------------------------------------------
     # edge lists straight from the adjacency dicts, in the order networkx' in_edges / out_edges views would give them
     def _edges_in(self, node):
@@ -548,6 +602,8 @@ class Rem(object):
     def graphalign(self, index, mum):
         try:
             l, n, spd = mum
+            if self.core is not None:
+                return self.core.graphalign(index.nodes, index.leftnode, index.rightnode, l, [pos for _, pos in spd])
             nodes = index.nodes
             G = self.G
             pieces = []
@@ -588,6 +644,8 @@ class Rem(object):
         point = {}
         for _, pos in spd:
             coords = known.get(pos)
+            if coords is None and self.core is not None:
+                coords = known[pos] = self.core.coords(pos)
             if coords is None:
                 G = self.G
                 begins = self.begins
@@ -603,12 +661,12 @@ class Rem(object):
     def _bounds(self, idx, keys):
         G = self.G
         if idx.leftnode is not None:
-            off = G.nodes[idx.leftnode]["offsets"]
+            off = self._offsets_of(idx.leftnode)
             left = {k: off[k] + (idx.leftnode[1] - idx.leftnode[0]) - 1 for k in keys}
         else:
             left = {k: -1 for k in keys}
         if idx.rightnode is not None:
-            off = G.nodes[idx.rightnode]["offsets"]
+            off = self._offsets_of(idx.rightnode)
             right = {k: off[k] for k in keys}
         else:
             right = {k: G.graph["id2end"][k] for k in keys}
@@ -621,9 +679,9 @@ class Rem(object):
         if idx.leftnode is None:
             lo = {k: 0 for k in real}
         else:
-            off = G.nodes[idx.leftnode]["offsets"]
+            off = self._offsets_of(idx.leftnode)
             lo = {k: off[k] + (idx.leftnode[1] - idx.leftnode[0]) for k in off}
-        ro = {k: G.graph["id2end"][k] for k in real} if idx.rightnode is None else G.nodes[idx.rightnode]["offsets"]
+        ro = {k: G.graph["id2end"][k] for k in real} if idx.rightnode is None else self._offsets_of(idx.rightnode)
         return all(ro[k] - lo[k] <= self.args.maxsize for k in set(lo) & set(ro))
 
     def graphmumpicker(self, mums, idx, precomputed=False, minlength=0):
@@ -744,6 +802,19 @@ class Rem(object):
                             changed = True
 
 
+class _RecursionGraph(object):
+    def __init__(self, rem):
+        self.rem = rem
+
+    def __enter__(self):
+        self.rem._load_core()
+        return self.rem
+
+    def __exit__(self, *exc):
+        self.rem._unload_core()
+        return False
+
+
 # ------------------------------------------------------------------------------------------------
 def fasta_reader(fn, toupper=True, keepdash=False):
     """(name, sequence) of every record of a (gzipped) FASTA file (utils.py:79-144, default options)."""
@@ -784,8 +855,9 @@ def align_genomes(args, index_module=None):
     if len(idx.samples) <= 1:
         raise ValueError("Specify at least 2 targets to construct alignment. In case of multi-fasta, consider contigs=False.")
     idx.construct()
-    idx.align(rem.graphmumpicker, rem.graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength,
-              minn=args.minn)
+    with rem.recursion_graph():
+        idx.align(rem.graphmumpicker, rem.graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength,
+                  minn=args.minn)
     return rem.G, idx
 
 
@@ -817,7 +889,8 @@ def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targe
             G.add_edge(first, node, paths={sid}, ofrom="+", oto="+")
             G.add_edge(node, last, paths={sid}, ofrom="+", oto="+")
     idx.construct()
-    idx.align(rem.graphmumpicker, rem.graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
+    with rem.recursion_graph():
+        idx.align(rem.graphmumpicker, rem.graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
     rem.prune_nodes(T=idx.T)
     G.remove_node(first)
     G.remove_node(last)

@@ -162,13 +162,21 @@ def test_rem_emulated_small(emu_reveallib, tmp_path, name):
     run_case(name, tmp_path, emu_reveallib.mod32)
 
 
+@pytest.mark.parametrize("graph", ["native", "python"])
 @pytest.mark.parametrize("name", [c[0] for c in M.CASES])
-def test_rem_driver_on_reference_extension(tmp_path, name):
+def test_rem_driver_on_reference_extension(tmp_path, monkeypatch, name, graph):
     """The driver alone: run on the reference's own compiled extension (oracle/_ref) it must rebuild the golden
-    graphs exactly, whatever the size -- separates driver parity from index parity."""
+    graphs exactly, whatever the size -- separates driver parity from index parity.  Once with the graph of the
+    recursion in C++ (remcore.Graph) and once on the networkx graph itself (the Python twin of the same methods)."""
     import oracle.ref as R
     if not R.available():
         pytest.skip("oracle/_ref not built")
+    if graph == "python":
+        monkeypatch.setenv("RV_REM_PYTHON_GRAPH", "1")
+        if name == "synth2_1m":
+            pytest.skip("largest case: native graph only (suite time)")
+    else:
+        assert rem._remcore is not None, "reveal_b200/remcore extension module not built"
     run_case(name, tmp_path, R.module(32))
 
 
