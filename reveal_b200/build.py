@@ -61,7 +61,8 @@ def build_extension(force=False):
     for name, defs in (("reveallib", []), ("reveallib64", ["-DSA64=1"])):
         out = os.path.join(_HERE, name + suffix)
         outs.append(out)
-        if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "..", "include", "reveal_b200.h"))):
+        deps = (src, os.path.join(CSRC, "ext", "chain_dp.h"), os.path.join(_HERE, "..", "include", "reveal_b200.h"))
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(d) for d in deps):
             continue
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I" + inc] + defs + [src, "-o", out, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,7 +72,7 @@ def build_extension(force=False):
     src = os.path.join(CSRC, "ext", "remcore_module.cpp")
     out = os.path.join(_HERE, "remcore" + suffix)
     outs.append(out)
-    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "ext", "chain_dp.h"))):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I" + inc, src, "-o", out]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

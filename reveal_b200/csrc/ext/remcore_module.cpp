@@ -22,6 +22,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include "chain_dp.h"
+
 namespace {
 
 struct Edge {
@@ -58,6 +60,7 @@ struct Graph {
     std::unordered_map<int64_t, int> *by_begin;   // every alive interval node
     std::map<int64_t, int> *tracked;              // unaligned interval nodes only: position -> node lookups
     std::vector<char> *real;                      // per path id: not a '*' path
+    std::vector<int64_t> *id2end;                 // per path id: length of the path
     PyObject *markers;                            // dict: marker object -> node id
     std::vector<uint32_t> *seen, *mark;           // epoch-stamped visit marks of the walks (no clearing per walk)
     uint32_t epoch;
@@ -382,6 +385,7 @@ static PyObject *Graph_new(PyTypeObject *type, PyObject *, PyObject *) {
     g->by_begin = new std::unordered_map<int64_t, int>();
     g->tracked = new std::map<int64_t, int>();
     g->real = new std::vector<char>();
+    g->id2end = new std::vector<int64_t>();
     g->seen = new std::vector<uint32_t>();
     g->mark = new std::vector<uint32_t>();
     g->epoch = 0;
@@ -391,8 +395,19 @@ static PyObject *Graph_new(PyTypeObject *type, PyObject *, PyObject *) {
 
 static int Graph_init(Graph *g, PyObject *args, PyObject *) {
     int multi = 1;
-    PyObject *cls = nullptr, *real = nullptr;
-    if (!PyArg_ParseTuple(args, "pOO", &multi, &cls, &real)) return -1;
+    PyObject *cls = nullptr, *real = nullptr, *ends = nullptr;
+    if (!PyArg_ParseTuple(args, "pOOO", &multi, &cls, &real, &ends)) return -1;
+    {
+        PyObject *it = PyObject_GetIter(ends);
+        if (!it) return -1;
+        g->id2end->clear();
+        while (PyObject *x = PyIter_Next(it)) {
+            g->id2end->push_back((int64_t)PyLong_AsLongLong(x));
+            Py_DECREF(x);
+        }
+        Py_DECREF(it);
+        if (PyErr_Occurred()) return -1;
+    }
     g->multi = multi != 0;
     Py_INCREF(cls);
     Py_XSETREF(g->interval_cls, cls);
@@ -417,6 +432,7 @@ static void Graph_dealloc(Graph *g) {
     delete g->by_begin;
     delete g->tracked;
     delete g->real;
+    delete g->id2end;
     delete g->seen;
     delete g->mark;
     Py_XDECREF(g->markers);
@@ -599,40 +615,353 @@ static PyObject *Graph_graphalign(Graph *g, PyObject *args) {
     return ret;
 }
 
-// export() -> (nodes, edges): nodes = [(key, aligned or None, offsets dict, extra or None)], edges = [(u, v, ofrom, oto, paths set, extra or None)]
+// ---- the mumpicker (rem.Rem.graphmumpicker, default flow; reference: schemes.py:197-361) ---------------------------------------
+struct Mum {
+    int64_t l;
+    long n;
+    std::vector<std::pair<long, int64_t>> sp;  // (sample of the index, position), in the order of the tuple
+    PyObject *orig;                            // the caller's tuple while the anchor is untouched (borrowed)
+    PyObject *spd;                             // the caller's position tuple while the positions are untouched (borrowed)
+};
+
+struct Rel {
+    int64_t l;
+    long n;
+    std::vector<std::pair<int32_t, int64_t>> point;  // (path id, coordinate), insertion-ordered like the dict it mirrors
+    int src;                                         // index into the picked anchors
+    std::vector<int64_t> values() const {
+        std::vector<int64_t> v;
+        for (auto &kv : point) v.push_back(kv.second);
+        return v;
+    }
+};
+
+static bool parse_mums(PyObject *list, std::vector<Mum> &out) {
+    PyObject *seq = PySequence_Fast(list, "mums must be a sequence");
+    if (!seq) return false;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    out.reserve(n);
+    for (Py_ssize_t i = 0; i < n; i++) {
+        PyObject *t = PySequence_Fast_GET_ITEM(seq, i);
+        if (!PyTuple_Check(t) || PyTuple_GET_SIZE(t) < 3) { PyErr_SetString(PyExc_TypeError, "anchor: (l, n, positions) expected"); Py_DECREF(seq); return false; }
+        Mum m;
+        m.l = PyLong_AsLongLong(PyTuple_GET_ITEM(t, 0));
+        m.n = PyLong_AsLong(PyTuple_GET_ITEM(t, 1));
+        m.orig = t;
+        m.spd = PyTuple_GET_ITEM(t, 2);
+        PyObject *sp = PySequence_Fast(m.spd, "anchor positions must be a sequence");
+        if (!sp) { Py_DECREF(seq); return false; }
+        for (Py_ssize_t k = 0; k < PySequence_Fast_GET_SIZE(sp); k++) {
+            PyObject *pr = PySequence_Fast_GET_ITEM(sp, k);
+            if (!PyTuple_Check(pr) || PyTuple_GET_SIZE(pr) < 2) { PyErr_SetString(PyExc_TypeError, "anchor position: (sample, pos) expected"); Py_DECREF(sp); Py_DECREF(seq); return false; }
+            m.sp.emplace_back(PyLong_AsLong(PyTuple_GET_ITEM(pr, 0)), (int64_t)PyLong_AsLongLong(PyTuple_GET_ITEM(pr, 1)));
+        }
+        Py_DECREF(sp);
+        out.push_back(std::move(m));
+    }
+    Py_DECREF(seq);
+    return !PyErr_Occurred();
+}
+
+static PyObject *mum_object(const Mum &m) {
+    if (m.orig) { Py_INCREF(m.orig); return m.orig; }
+    PyObject *spd;
+    if (m.spd) { spd = m.spd; Py_INCREF(spd); }
+    else {
+        spd = PyTuple_New((Py_ssize_t)m.sp.size());
+        for (size_t k = 0; k < m.sp.size(); k++) PyTuple_SET_ITEM(spd, k, Py_BuildValue("(lL)", m.sp[k].first, (long long)m.sp[k].second));
+    }
+    PyObject *r = Py_BuildValue("(LlO)", (long long)m.l, m.n, spd);
+    Py_DECREF(spd);
+    return r;
+}
+
+// schemes.trim_overlap (schemes.py:161-191), one coordinate (= member slot) at a time
+static void trim_overlap(std::vector<Mum> &mums) {
+    if (mums.empty()) return;
+    const size_t ncoord = mums[0].sp.size();
+    for (size_t coord = 0; coord < ncoord; coord++) {
+        if (mums.size() <= 1) break;
+        std::stable_sort(mums.begin(), mums.end(), [coord](const Mum &a, const Mum &b) {
+            if (a.sp[coord].second != b.sp[coord].second) return a.sp[coord].second < b.sp[coord].second;
+            return a.l > b.l;
+        });
+        const size_t n = mums.size();
+        std::vector<int64_t> ends(n);
+        for (size_t i = 0; i < n; i++) ends[i] = mums[i].sp[coord].second + mums[i].l;
+        std::vector<Mum> kept;
+        for (size_t i = 0; i < n; i++)  // the reference compares the FIRST anchor with its successor, or (i-1 = -1) with the last one
+            if ((i == 0 && ends[1] > ends[0]) || ends[(i + n - 1) % n] < ends[i]) kept.push_back(mums[i]);
+        mums.swap(kept);
+        if (mums.size() <= 1) break;
+        std::vector<Mum> trimmed;
+        trimmed.push_back(mums[0]);
+        for (size_t i = 1; i < mums.size(); i++) {
+            Mum mum = mums[i];
+            const Mum &prev = trimmed.back();
+            const int64_t overlap = prev.sp[coord].second + prev.l - mum.sp[coord].second;
+            if (overlap > 0) {
+                if (prev.l - overlap > 0) {
+                    trimmed.back().l -= overlap;
+                    trimmed.back().orig = nullptr;
+                } else {
+                    trimmed.pop_back();
+                }
+                if (mum.l - overlap > 0) {
+                    mum.l -= overlap;
+                    for (auto &p : mum.sp) p.second += overlap;
+                    mum.orig = nullptr;
+                    mum.spd = nullptr;
+                    trimmed.push_back(mum);
+                }
+            } else {
+                trimmed.push_back(mum);
+            }
+        }
+        mums.swap(trimmed);
+    }
+}
+
+// pick(mums, nsamples, leftnode, rightnode, trim, maxmums, model, wscore, wpen, seedsize) -> () | (anchor, skipleft, skipright)
+static PyObject *Graph_pick(Graph *g, PyObject *args) {
+    PyObject *list, *leftnode, *rightnode;
+    long nsamples, maxmums;
+    int trim, model;
+    long long wscore, wpen, seedsize;
+    if (!PyArg_ParseTuple(args, "OlOOpliLLL", &list, &nsamples, &leftnode, &rightnode, &trim, &maxmums, &model, &wscore, &wpen, &seedsize)) return nullptr;
+    std::vector<Mum> all;
+    if (!parse_mums(list, all)) return nullptr;
+    std::vector<Mum> picked;
+    for (auto &m : all)
+        if (m.n == nsamples) picked.push_back(m);
+    if (picked.empty() && nsamples > 2) {  // schemes.segment: the sample group with the largest total length x group size
+        std::vector<std::vector<long>> parts;
+        std::vector<std::vector<int>> members;
+        for (size_t i = 0; i < all.size(); i++) {
+            std::vector<long> part;
+            for (auto &p : all[i].sp) part.push_back(p.first);
+            std::sort(part.begin(), part.end());
+            size_t at = 0;
+            for (; at < parts.size(); at++)
+                if (parts[at] == part) break;
+            if (at == parts.size()) { parts.push_back(part); members.emplace_back(); }
+            members[at].push_back((int)i);
+        }
+        int64_t best = 0;
+        int pick = -1;
+        for (size_t at = 0; at < parts.size(); at++) {
+            int64_t z = 0;
+            for (int i : members[at]) z += all[i].l;
+            z *= (int64_t)parts[at].size();
+            if (z > best) { best = z; pick = (int)at; }
+        }
+        if (pick >= 0)
+            for (int i : members[pick]) picked.push_back(all[i]);
+    }
+    if (picked.empty()) return PyTuple_New(0);
+    if (trim) {
+        trim_overlap(picked);
+        if (picked.empty()) return PyTuple_New(0);
+    }
+    std::stable_sort(picked.begin(), picked.end(), [](const Mum &a, const Mum &b) { return a.l > b.l; });
+    // anchors in path coordinates (schemes.lookup / maptooffsets)
+    std::vector<Rel> rel(picked.size());
+    std::map<std::vector<int64_t>, int> origin;
+    for (size_t i = 0; i < picked.size(); i++) {
+        Rel &r = rel[i];
+        r.l = picked[i].l;
+        r.n = 0;
+        r.src = (int)i;
+        for (auto &p : picked[i].sp) {
+            int id = node_at(g, p.second);
+            if (id < 0) { PyErr_Format(PyExc_KeyError, "no node covers index position %lld", (long long)p.second); return nullptr; }
+            const Node &nd = (*g->nodes)[id];
+            const int64_t shift = p.second - nd.begin;
+            for (auto &kv : nd.offsets) {
+                if (!is_real(g, kv.first)) continue;
+                r.n++;
+                bool found = false;
+                for (auto &have : r.point)
+                    if (have.first == kv.first) { have.second = kv.second + shift; found = true; break; }
+                if (!found) r.point.emplace_back(kv.first, kv.second + shift);
+            }
+        }
+        origin[r.values()] = (int)i;
+    }
+    std::stable_sort(rel.begin(), rel.end(), [](const Rel &a, const Rel &b) { return a.n != b.n ? a.n < b.n : a.l < b.l; });
+    auto keyset = [](const Rel &r) {
+        std::vector<int32_t> k;
+        for (auto &kv : r.point) k.push_back(kv.first);
+        std::sort(k.begin(), k.end());
+        return k;
+    };
+    {
+        const std::vector<int32_t> want = keyset(rel.back());
+        std::vector<Rel> same;
+        for (auto &r : rel)
+            if (keyset(r) == want) same.push_back(r);
+        rel.swap(same);
+    }
+    std::vector<int32_t> keys;
+    for (auto &kv : rel.back().point) keys.push_back(kv.first);
+    const size_t k = keys.size();
+    if (k == 0 || k > 64) { PyErr_SetString(PyExc_ValueError, "anchor over no path or over more than 64 paths"); return nullptr; }
+    // bounds of the sub-index in path coordinates
+    std::vector<int64_t> left(k), right(k);
+    for (int side = 0; side < 2; side++) {
+        PyObject *bound = side == 0 ? leftnode : rightnode;
+        if (bound == Py_None) {
+            for (size_t c = 0; c < k; c++) {
+                if (side == 0) left[c] = -1;
+                else {
+                    if (keys[c] < 0 || (size_t)keys[c] >= g->id2end->size()) { PyErr_SetString(PyExc_KeyError, "path without a length"); return nullptr; }
+                    right[c] = (*g->id2end)[keys[c]];
+                }
+            }
+            continue;
+        }
+        int id = find_node(g, bound);
+        if (id < 0) return nullptr;
+        const Node &nd = (*g->nodes)[id];
+        for (size_t c = 0; c < k; c++) {
+            bool found = false;
+            for (auto &kv : nd.offsets)
+                if (kv.first == keys[c]) {
+                    if (side == 0) left[c] = kv.second + (nd.end - nd.begin) - 1; else right[c] = kv.second;
+                    found = true;
+                    break;
+                }
+            if (!found) { PyErr_Format(PyExc_KeyError, "path %d does not run through the bounding node", (int)keys[c]); return nullptr; }
+        }
+    }
+    auto coord_of = [](const Rel &r, int32_t key) -> int64_t {
+        for (auto &kv : r.point)
+            if (kv.first == key) return kv.second;
+        return 0;
+    };
+    std::vector<std::pair<int, int64_t>> skipleft, skipright;  // (picked index, score relative to the split)
+    int split = -1;                                             // index into rel
+    if (rel.size() == 1) {
+        split = 0;
+    } else {
+        if (maxmums > 0 && (long)rel.size() > maxmums) rel.erase(rel.begin(), rel.end() - maxmums);
+        else if (maxmums <= 0 && !rel.empty()) { /* rel[-0:] is the whole list in Python as well */ }
+        // schemes.chain: anchors + the right bound in the order of the smallest path id's coordinate
+        int32_t ref = rel[0].point[0].first;
+        for (auto &kv : rel[0].point) ref = std::min(ref, kv.first);
+        const size_t m = rel.size() + 1;
+        std::vector<int> order(m);
+        for (size_t i = 0; i < m; i++) order[i] = (int)i;  // index rel.size() stands for the right bound
+        size_t refcol = 0;
+        for (size_t c = 0; c < k; c++)
+            if (keys[c] == ref) refcol = c;
+        auto refcoord = [&](int i) { return (size_t)i == rel.size() ? right[refcol] : coord_of(rel[i], ref); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return refcoord(a) < refcoord(b); });
+        std::vector<int64_t> start((m + 1) * k), length(m + 1, 0), gain(m + 1, 0), link(m + 1, 0), score(m + 1, 0);
+        for (size_t c = 0; c < k; c++) start[c] = left[c];
+        for (size_t r = 1; r <= m; r++) {
+            const int i = order[r - 1];
+            if ((size_t)i == rel.size()) {
+                for (size_t c = 0; c < k; c++) start[r * k + c] = right[c];
+            } else {
+                for (size_t c = 0; c < k; c++) start[r * k + c] = coord_of(rel[i], keys[c]);
+                length[r] = rel[i].l;
+                gain[r] = wscore * (rel[i].l * ((rel[i].n * (rel[i].n - 1)) / 2));
+            }
+        }
+        rv_chain_dp(start.data(), length.data(), gain.data(), (long)(m + 1), (long)k, (int64_t)wpen, model, link.data(), score.data());
+        // the right bound sorts last (anchors lie inside the bounds; it was appended last and the sort is stable): back-track
+        // from the last row, like rem.chain
+        std::vector<std::pair<int, int64_t>> chained;  // (rel index, score), first anchor of the chain first
+        for (int64_t r = link[m]; r != 0; r = link[r]) {
+            if ((size_t)order[r - 1] == rel.size()) continue;  // never the bound itself
+            chained.emplace_back(order[r - 1], score[r]);
+        }
+        std::reverse(chained.begin(), chained.end());
+        if (chained.empty()) return PyTuple_New(0);
+        for (auto &c : chained)  // "largest": the last of the longest anchors of the chain
+            if (split < 0 || rel[c.first].l >= rel[split].l) split = c.first;
+        if (seedsize > 0) {
+            bool after = false;
+            int64_t at_split = 0;
+            for (auto &c : chained) {
+                if (c.first == split) { at_split = c.second; after = true; continue; }
+                auto it = origin.find(rel[c.first].values());
+                if (it == origin.end()) continue;
+                if (picked[it->second].l < seedsize) continue;
+                (after ? skipright : skipleft).emplace_back(it->second, c.second - at_split);
+            }
+        }
+    }
+    auto it = origin.find(rel[split].values());
+    if (it == origin.end()) { PyErr_SetString(PyExc_RuntimeError, "picked anchor lost its origin"); return nullptr; }
+    PyObject *anchor = mum_object(picked[it->second]);
+    PyObject *lists[2];
+    for (int side = 0; side < 2; side++) {
+        auto &src = side == 0 ? skipleft : skipright;
+        lists[side] = PyList_New((Py_ssize_t)src.size());
+        for (size_t i = 0; i < src.size(); i++) {
+            PyObject *mo = mum_object(picked[src[i].first]);
+            PyList_SET_ITEM(lists[side], i, Py_BuildValue("(NL)", mo, (long long)src[i].second));
+        }
+    }
+    return Py_BuildValue("(NNN)", anchor, lists[0], lists[1]);
+}
+
+// export() -> (nodes, edges): nodes = [(key, attribute dict)], edges = [(u, v, attribute dict)] -- the attribute dicts are
+// complete (offsets / aligned / extras; paths / ofrom / oto / extras) and freshly made, ready to be placed in a networkx graph
 static PyObject *Graph_export(Graph *g, PyObject *) {
     PyObject *nodes = PyList_New(0), *edges = PyList_New(0);
+    PyObject *s_offsets = PyUnicode_InternFromString("offsets"), *s_aligned = PyUnicode_InternFromString("aligned");
+    PyObject *s_paths = PyUnicode_InternFromString("paths"), *s_ofrom = PyUnicode_InternFromString("ofrom"), *s_oto = PyUnicode_InternFromString("oto");
+    PyObject *plus = PyUnicode_InternFromString("+"), *minus = PyUnicode_InternFromString("-");
     std::vector<PyObject *> keys(g->nodes->size(), nullptr);
-    for (size_t i = 0; i < g->nodes->size(); i++) {
+    bool ok = true;
+    for (size_t i = 0; ok && i < g->nodes->size(); i++) {
         const Node &n = (*g->nodes)[i];
         if (!n.alive) continue;
         PyObject *key;
         if (n.key) { key = n.key; Py_INCREF(key); }
         else key = PyObject_CallFunction(g->interval_cls, "LL", (long long)n.begin, (long long)n.end);
-        if (!key) { Py_DECREF(nodes); Py_DECREF(edges); return nullptr; }
+        if (!key) { ok = false; break; }
         keys[i] = key;
-        PyObject *al = n.aligned < 0 ? (Py_INCREF(Py_None), Py_None) : PyLong_FromLong(n.aligned);
+        PyObject *attrs = n.extra ? PyDict_Copy(n.extra) : PyDict_New();
         PyObject *offs = offsets_dict(n.offsets);
-        PyObject *row = PyTuple_Pack(4, key, al, offs, n.extra ? n.extra : Py_None);
+        PyDict_SetItem(attrs, s_offsets, offs);
+        Py_DECREF(offs);
+        if (n.aligned >= 0) {
+            PyObject *al = PyLong_FromLong(n.aligned);
+            PyDict_SetItem(attrs, s_aligned, al);
+            Py_DECREF(al);
+        }
+        PyObject *row = PyTuple_Pack(2, key, attrs);
         PyList_Append(nodes, row);
-        Py_DECREF(row); Py_DECREF(al); Py_DECREF(offs);
+        Py_DECREF(row);
+        Py_DECREF(attrs);
     }
     // edges in the order networkx would hold them: by source node, then by insertion
-    for (size_t i = 0; i < g->nodes->size(); i++) {
+    for (size_t i = 0; ok && i < g->nodes->size(); i++) {
         const Node &n = (*g->nodes)[i];
         if (!n.alive) continue;
         for (int eid : n.out) {
             const Edge &e = (*g->edges)[eid];
             if (!e.alive) continue;
+            PyObject *attrs = e.extra ? PyDict_Copy(e.extra) : PyDict_New();
             PyObject *paths = PySet_New(nullptr);
             for (int32_t p : e.paths) { PyObject *x = PyLong_FromLong(p); PySet_Add(paths, x); Py_DECREF(x); }
-            char f[2] = {e.ofrom, 0}, t[2] = {e.oto, 0};
-            PyObject *row = Py_BuildValue("(OOssOO)", keys[e.u], keys[e.v], f, t, paths, e.extra ? e.extra : Py_None);
+            PyDict_SetItem(attrs, s_paths, paths);
+            Py_DECREF(paths);
+            PyDict_SetItem(attrs, s_ofrom, e.ofrom == '-' ? minus : plus);
+            PyDict_SetItem(attrs, s_oto, e.oto == '-' ? minus : plus);
+            PyObject *row = PyTuple_Pack(3, keys[e.u], keys[e.v], attrs);
             PyList_Append(edges, row);
-            Py_DECREF(row); Py_DECREF(paths);
+            Py_DECREF(row);
+            Py_DECREF(attrs);
         }
     }
     for (PyObject *k : keys) Py_XDECREF(k);
+    for (PyObject *o : {s_offsets, s_aligned, s_paths, s_ofrom, s_oto, plus, minus}) Py_DECREF(o);
+    if (!ok) { Py_DECREF(nodes); Py_DECREF(edges); return nullptr; }
     PyObject *ret = PyTuple_Pack(2, nodes, edges);
     Py_DECREF(nodes); Py_DECREF(edges);
     return ret;
@@ -652,6 +981,8 @@ static PyMethodDef Graph_methods[] = {
     {"node_offsets", (PyCFunction)Graph_node_offsets, METH_O, "node_offsets(node) -> {path id: offset}"},
     {"graphalign", (PyCFunction)Graph_graphalign, METH_VARARGS,
      "graphalign(nodes, leftnode, rightnode, l, positions) -> (leading, trailing, matching, rest, merged, newleft, newright)"},
+    {"pick", (PyCFunction)Graph_pick, METH_VARARGS,
+     "pick(mums, nsamples, leftnode, rightnode, trim, maxmums, model, wscore, wpen, seedsize) -> () | (anchor, skipleft, skipright)"},
     {"export", (PyCFunction)Graph_export, METH_NOARGS, "export() -> (node rows, edge rows) of the alive graph"},
     {"stats", (PyCFunction)Graph_stats, METH_NOARGS, "(alive nodes, alive edges, node slots, edge slots)"},
     {nullptr, nullptr, 0, nullptr}};
@@ -667,7 +998,7 @@ extern "C" __attribute__((visibility("default"))) PyObject *PyInit_remcore(void)
     GraphType.tp_name = "remcore.Graph";
     GraphType.tp_basicsize = sizeof(Graph);
     GraphType.tp_flags = Py_TPFLAGS_DEFAULT;
-    GraphType.tp_doc = "Graph(multi, interval_class, real_path_flags)";
+    GraphType.tp_doc = "Graph(multi, interval_class, real_path_flags, path_lengths)";
     GraphType.tp_new = Graph_new;
     GraphType.tp_init = (initproc)Graph_init;
     GraphType.tp_dealloc = (destructor)Graph_dealloc;

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../../include/reveal_b200.h"
+#include "chain_dp.h"
 
 #ifdef SA64
 #define MODNAME "reveallib64"
@@ -769,57 +770,8 @@ static PyObject *mod_chain_dp(PyObject *, PyObject *args) {
     } else {
         const int64_t *start = (const int64_t *)bs.buf, *length = (const int64_t *)bl.buf, *gain = (const int64_t *)bg.buf;
         int64_t *link = (int64_t *)bk.buf, *score = (int64_t *)bc.buf;
-        std::vector<int64_t> joined(rows, -1);
-        joined[0] = 0;
-        link[0] = 0;
-        score[0] = 0;
-        int64_t dist[64];
         Py_BEGIN_ALLOW_THREADS
-        for (Py_ssize_t r = 1; r < rows; r++) {
-            const int64_t *sr = start + r * k;
-            Py_ssize_t best = -1;
-            int64_t best_total = 0;
-            for (Py_ssize_t i = 0; i < r; i++) {
-                const int64_t *si = start + i * k;
-                bool ok = true;
-                for (Py_ssize_t c = 0; c < k; c++) {
-                    int64_t d = sr[c] - (si[c] + length[i]);
-                    if (d < 0) { ok = false; break; }
-                    dist[c] = d;
-                }
-                if (!ok) continue;
-                if (joined[i] < 0) joined[i] = r;
-                int64_t pen = 0;
-                if (model == 0) {
-                    for (Py_ssize_t a = 0; a < k; a++)
-                        for (Py_ssize_t b = a + 1; b < k; b++) pen += dist[a] > dist[b] ? dist[a] - dist[b] : dist[b] - dist[a];
-                } else if (model == 1) {
-                    int64_t sum = 0;
-                    for (Py_ssize_t c = 0; c < k; c++) sum += dist[c];  // all distances are >= 0 here
-                    pen = sum / k;
-                } else {
-                    int64_t tmp[64];
-                    memcpy(tmp, dist, sizeof(int64_t) * k);
-                    for (Py_ssize_t a = 1; a < k; a++) {  // insertion sort, k is the number of samples
-                        int64_t v = tmp[a];
-                        Py_ssize_t b = a;
-                        while (b > 0 && tmp[b - 1] > v) { tmp[b] = tmp[b - 1]; b--; }
-                        tmp[b] = v;
-                    }
-                    pen = tmp[k / 2];
-                }
-                const int64_t total = score[i] + gain[r] - wpen * pen;
-                bool take = best < 0 || total > best_total;
-                if (!take && total == best_total) {
-                    if (score[i] != score[best]) take = score[i] > score[best];
-                    else if (joined[i] != joined[best]) take = joined[i] < joined[best];
-                }
-                if (take) { best = i; best_total = total; }
-            }
-            if (best < 0) { best = 0; best_total = 0; }  // cannot happen with a proper left bound
-            link[r] = best;
-            score[r] = best_total;
-        }
+        rv_chain_dp(start, length, gain, (long)rows, (long)k, (int64_t)wpen, model, link, score);
         Py_END_ALLOW_THREADS
         ret = Py_None;
         Py_INCREF(ret);

@@ -403,7 +403,9 @@ class Rem(object):
             return
         G = self.G
         ids = G.graph["id2path"]
-        core = _remcore.Graph(self.multi, Interval, [not ids[sid].startswith("*") for sid in range(len(ids))])
+        ends = G.graph["id2end"]
+        core = _remcore.Graph(self.multi, Interval, [not ids[sid].startswith("*") for sid in range(len(ids))],
+                              [ends[sid] for sid in range(len(ids))])
         for node, d in G.nodes(data=True):
             extra = {k: v for k, v in d.items() if k not in ("offsets", "aligned")}
             core.add_node(node, d.get("aligned"), d.get("offsets") or {}, extra or None)
@@ -417,23 +419,47 @@ class Rem(object):
         if core is None:
             return
         G = self.G
-        nodes, edges = core.export()
+        import gc
+        was_on = gc.isenabled()
+        gc.disable()  # a burst of long-lived containers: generational collections in the middle of it only re-scan them
+        try:
+            self._rebuild_from(core)
+        finally:
+            if was_on:
+                gc.enable()
+
+    def _rebuild_from(self, core):
+        G = self.G
+        nodes, edges = core.export()   # [(node, attributes)], [(u, v, attributes)], attribute dicts freshly made
         keep = dict(G.graph)
         G.clear()
         G.graph.update(keep)
-        self.begins, self.end_of = [], {}
-        for key, aligned, offsets, extra in nodes:
-            attrs = dict(extra) if extra else {}
-            attrs["offsets"] = offsets
-            if aligned is not None:
-                attrs["aligned"] = aligned
-                if aligned == 0:
-                    self.end_of[key.begin] = key.end
-            G.add_node(key, **attrs)
+        self.end_of = {}
+        if type(G) in (nx.MultiDiGraph, nx.DiGraph):
+            # hundreds of thousands of nodes and edges: placed straight into the adjacency dicts, the way add_node / add_edge do
+            node_of, succ, pred = G._node, G._succ, G._pred
+            for key, attrs in nodes:
+                node_of[key] = attrs
+                succ[key] = {}
+                pred[key] = {}
+            if self.multi:
+                for u, v, attrs in edges:
+                    keyed = succ[u].get(v)
+                    if keyed is None:
+                        keyed = succ[u][v] = pred[v][u] = {}
+                    keyed[len(keyed)] = attrs
+            else:
+                for u, v, attrs in edges:
+                    succ[u][v] = pred[v][u] = attrs
+        else:
+            for key, attrs in nodes:
+                G.add_node(key, **attrs)
+            for u, v, attrs in edges:
+                G.add_edge(u, v, **attrs)
+        for key, attrs in nodes:
+            if attrs.get("aligned") == 0:
+                self.end_of[key.begin] = key.end
         self.begins = sorted(self.end_of)
-        for u, v, ofrom, oto, paths, extra in edges:
-            attrs = dict(extra) if extra else {}
-            G.add_edge(u, v, paths=paths, ofrom=ofrom, oto=oto, **attrs)
 
     def _offsets_of(self, node):
         return self.core.node_offsets(node) if self.core is not None else self.G.nodes[node]["offsets"]
@@ -696,6 +722,11 @@ class Rem(object):
                 return ()
             if args.maxsize is not None and self._small_enough(idx):
                 return ()
+            if (self.core is not None and args.splitchain == "largest" and minlength != 0 and args.gcmodel in _MODELS
+                    and os.environ.get("RV_REM_PYTHON_PICK", "0") in ("", "0")):
+                # the default flow below, in C++ on the graph that lives there during the recursion (remcore.Graph.pick)
+                return self.core.pick(mums, idx.nsamples, idx.leftnode, idx.rightnode, bool(args.trim), int(args.maxmums),
+                                      _MODELS[args.gcmodel], int(args.wscore), int(args.wpen), int(args.seedsize))
             picked = [m for m in mums if m[1] == idx.nsamples]
             if not picked and idx.nsamples > 2:
                 picked = segment(mums)
@@ -807,11 +838,21 @@ class _RecursionGraph(object):
         self.rem = rem
 
     def __enter__(self):
+        import gc
+        self.gc_was_on = gc.isenabled()
         self.rem._load_core()
+        # The recursion allocates millions of short-lived tuples (MUM lists) next to a large, long-lived heap; none of it is
+        # cyclic garbage, so generational collections in the middle of it are pure overhead: switched off until the end.
+        gc.disable()
         return self.rem
 
     def __exit__(self, *exc):
-        self.rem._unload_core()
+        import gc
+        try:
+            self.rem._unload_core()
+        finally:
+            if self.gc_was_on:
+                gc.enable()
         return False
 
 
