@@ -187,6 +187,9 @@ CASES = [  # name, inputs (reference test files, or ("synth", n_genomes, length,
     ("gfa_x_gfa_4x20k", ("graphs", 4, 20000, 31, [[0, 1], [2, 3]]), {}),
     ("gfa_x_fasta_3x10k", ("graphs", 3, 10000, 32, [[0, 1], 2]), {"minlength": 15}),
     ("gfa3_x_gfa2_5x3k", ("graphs", 5, 3000, 33, [[0, 1, 2], [3, 4]]), {"minlength": 10}),   # small: emulated kernels
+    # a hand-made graph in which one path runs through a segment on the reverse strand ('-' links): the mirrored edges
+    # of breaknode.  Segments are slices of one synthetic genome, the second input is that genome with mutations.
+    ("gfa_reverse_strand_x_fasta", ("revgraph", 6000, 51), {"minlength": 12}),
     ("synth2_200k", ("synth", 2, 200000, 11), {}),
     ("synth3_60k", ("synth", 3, 60000, 12), {}),
     ("synth5_30k_n3", ("synth", 5, 30000, 13), {"minn": 3, "minlength": 15}),
@@ -209,7 +212,22 @@ def write_fasta(path, name, seq):
 
 def run_case(rem, tmp, inputs, overrides):
     out = {}
-    if isinstance(inputs, tuple) and inputs[0] == "align":
+    if isinstance(inputs, tuple) and inputs[0] == "revgraph":
+        from reveal_b200 import synth
+        _, length, seed = inputs
+        g0, g1 = [g.tobytes().decode() for g in synth.genomes(2, length, seed=seed)]
+        cuts = [0, length // 4, length // 2, 3 * length // 4, length]
+        segs = [g0[cuts[i]:cuts[i + 1]] for i in range(4)]
+        gfa = "H\tVN:Z:1.0\n" + "".join("S\t%d\t%s\n" % (i + 1, sq) for i, sq in enumerate(segs))
+        gfa += "L\t1\t+\t2\t+\t0M\nL\t2\t+\t3\t+\t0M\nL\t3\t+\t4\t+\t0M\n"      # path fwd: 1+ 2+ 3+ 4+
+        gfa += "L\t1\t+\t3\t-\t0M\nL\t3\t-\t2\t-\t0M\nL\t2\t-\t4\t+\t0M\n"      # path inv: 1+ 3- 2- 4+ (middle inverted)
+        gfa += "P\tfwd\t1+,2+,3+,4+\t0M,0M,0M\nP\tinv\t1+,3-,2-,4+\t0M,0M,0M\n"
+        gpath, fpath = os.path.join(tmp, "%s_rev.gfa" % seed), os.path.join(tmp, "%s_q.fa" % seed)
+        open(gpath, "w").write(gfa)
+        write_fasta(fpath, "query", g1)
+        out["files"] = [["rev.gfa", gfa], ["q.fa", open(fpath).read()]]
+        files = [gpath, fpath]
+    elif isinstance(inputs, tuple) and inputs[0] == "align":
         from reveal_b200 import synth
         _, ng, length, seed = inputs
         aobjs = [("g%d" % k, g.tobytes().decode()) for k, g in enumerate(synth.genomes(ng, length, seed=seed))]
@@ -220,7 +238,7 @@ def run_case(rem, tmp, inputs, overrides):
         out["aligned_bases"] = sum(n[1] * len(n[0]) for n in out["nodes"] if n[2] != 0)
         out["args"] = dict(overrides)
         return out
-    if isinstance(inputs, tuple) and inputs[0] == "graphs":
+    elif isinstance(inputs, tuple) and inputs[0] == "graphs":
         from reveal_b200 import synth
         _, ng, length, seed, groups = inputs
         fastas = []
