@@ -216,3 +216,22 @@ def test_rem_gfa_spells_the_inputs(tmp_path):
     assert set(paths) == set(want)
     for name in want:
         assert "".join(seg[s] for s in paths[name]).upper() == want[name]
+
+
+def test_rem_inconsistent_intervals_are_refused(emu_reveallib, tmp_path):
+    """A graph whose paths run through one segment on both strands over parallel links: graphalign hands back
+    leading intervals that are not part of the sub-index.  The reference's C aligner writes out of bounds on this
+    input (segmentation fault); here the step is refused with reveallib.error."""
+    if emu_reveallib.name == "ctypes":
+        pytest.skip("compiled extension only (suite time)")
+    length = 3000
+    g0, g1 = [g.tobytes().decode() for g in synth.genomes(2, length, seed=51)]
+    cuts = [0, length // 3, 2 * length // 3, length]
+    gfa = "H\tVN:Z:1.0\n" + "".join("S\t%d\t%s\n" % (i + 1, g0[cuts[i]:cuts[i + 1]]) for i in range(3))
+    gfa += "L\t1\t+\t2\t+\t0M\nL\t2\t+\t3\t+\t0M\nL\t1\t+\t2\t-\t0M\nL\t2\t-\t3\t+\t0M\n"
+    gfa += "P\tfwd\t1+,2+,3+\t0M,0M\nP\tinv\t1+,2-,3+\t0M,0M\n"
+    (tmp_path / "rev.gfa").write_text(gfa)
+    (tmp_path / "q.fa").write_text(">q\n%s\n" % g1)
+    args = rem.rem_args([str(tmp_path / "rev.gfa"), str(tmp_path / "q.fa")], minlength=12)
+    with pytest.raises(emu_reveallib.error, match="intervals cover"):
+        rem.align_genomes(args, index_module=emu_reveallib.mod32)
