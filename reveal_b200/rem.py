@@ -795,12 +795,17 @@ class Rem(object):
         """Merges sibling nodes that spell the same sequence and have no other '+' neighbour on the shared side,
         until nothing changes (rem.py:385-446)."""
         G = self.G
+        succ, pred, attrs = G._succ, G._pred, G._node   # the adjacency dicts themselves: this loop visits every node repeatedly
+        multi = self.multi
 
-        def plus(edges, pick):
-            return [e[pick] for e in edges if e[2]["ofrom"] == "+" and e[2]["oto"] == "+"]
+        def plus(adj):
+            """Neighbours over forward-forward edges, one entry per such edge."""
+            if multi:
+                return [v for v, keyed in adj.items() for d in keyed.values() if d["ofrom"] == "+" and d["oto"] == "+"]
+            return [v for v, d in adj.items() if d["ofrom"] == "+" and d["oto"] == "+"]
 
         def spelled(node):
-            data = G.nodes[node]
+            data = attrs[node]
             if "seq" in data:
                 return data["seq"]
             return T[node.begin:node.end] if isinstance(node, Interval) else None
@@ -808,24 +813,23 @@ class Rem(object):
         changed = True
         while changed:
             changed = False
-            for node in list(G.nodes()):
-                if node not in G:
+            for node in list(attrs):
+                if node not in attrs:
                     continue
                 for forward in (True, False):
-                    neis = plus(G.out_edges(node, data=True), 1) if forward else plus(G.in_edges(node, data=True), 0)
+                    adj = succ[node] if forward else pred[node]
+                    if len(adj) < 2:
+                        continue  # fewer than two neighbours: nothing to merge on this side
                     by_seq = collections.OrderedDict()
-                    for nei in neis:
+                    for nei in plus(adj):
                         seq = spelled(nei)
                         if seq is not None:
                             by_seq.setdefault(seq, []).append(nei)
                     for group in by_seq.values():
                         if len(group) < 2:
                             continue
-                        if forward:
-                            lonely = all(len(plus(G.in_edges(v, data=True), 0)) <= 1 for v in group)
-                        else:
-                            lonely = all(len(plus(G.out_edges(v, data=True), 1)) <= 1 for v in group)
-                        if lonely:
+                        back = pred if forward else succ
+                        if all(len(plus(back[v])) <= 1 for v in group):
                             for v in group[1:]:
                                 if isinstance(v, Interval):
                                     self._untrack(v.begin)
