@@ -48,8 +48,9 @@ def test_product_loader_never_points_at_the_emulation():
 def test_extension_modules_build_and_import():
     """The compiled drop-in modules (csrc/ext/reveallib_module.cpp) build, import and expose the reference's surface."""
     outs = build.build_extension()
-    assert len(outs) == 2 and all(os.path.exists(o) for o in outs)
-    from reveal_b200 import reveallib, reveallib64
+    assert len(outs) == 3 and all(os.path.exists(o) for o in outs)   # reveallib, reveallib64, remcore
+    from reveal_b200 import remcore, reveallib, reveallib64
+    assert callable(reveallib.chain_dp) and all(hasattr(remcore.Graph, m) for m in ("graphalign", "pick", "coords", "export"))
     for mod in (reveallib, reveallib64):
         for name in ("addsample", "addsequence", "construct", "align", "getmums", "getmultimums", "getmultimems", "copy",
                      "n", "depth", "nsamples", "samples", "nodes", "leftnode", "rightnode", "nsep", "SA", "SAi", "SO", "LCP", "T"):
