@@ -88,14 +88,36 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock and throttle reasons during the timed region: through NVML (nvidia_ml_py, a sample every 5 ms --
+    the timed region of a default run is a few milliseconds long) or, if that is not usable, through nvidia-smi."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}  # nvml.h
 
     def __init__(self, gpu):
         threading.Thread.__init__(self, daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.source = gpu, [], False, "nvidia-smi"
+        self.sm, self.mx, self.mask = [], [], 0
+
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.mx.append(int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        self.sm.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))   # raises here if NVML is unusable
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.sm.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.mask |= int(reasons(h))
+            time.sleep(0.005)
 
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -109,11 +131,17 @@ class ClockSampler(threading.Thread):
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        if self.source == "nvml":
+            sm, mx = self.sm, self.mx
+            reasons = [nm for nm in self.NAMES if self.mask & self.BITS[nm]]
+            n = len(sm)
+        else:
+            sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+            mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+            reasons = [nm for i, nm in enumerate(self.NAMES) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+            n = len(self.rows)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": n,
+                "source": self.source}
 
 
 def make_workload(name, seed):
