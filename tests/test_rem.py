@@ -235,3 +235,32 @@ def test_rem_inconsistent_intervals_are_refused(emu_reveallib, tmp_path):
     args = rem.rem_args([str(tmp_path / "rev.gfa"), str(tmp_path / "q.fa")], minlength=12)
     with pytest.raises(emu_reveallib.error, match="intervals cover"):
         rem.align_genomes(args, index_module=emu_reveallib.mod32)
+
+
+def test_rem_native_graph_equals_python_graph_fuzz(tmp_path, monkeypatch):
+    """Random inputs and option mixes: the recursion on remcore.Graph (C++ graphalign + pick) and on the networkx
+    graph (the Python twin) must give the same canonical graph.  Runs on the reference extension (fast, CPU)."""
+    import oracle.ref as R
+    if not R.available() or rem._remcore is None:
+        pytest.skip("needs oracle/_ref and the remcore module")
+    rng = np.random.default_rng(2024)
+    for trial in range(30):
+        ng = int(rng.integers(2, 5))
+        length = int(rng.integers(1500, 6000))
+        files = []
+        for k, g in enumerate(synth.genomes(ng, length, seed=1000 + trial, snp=float(rng.choice([0.01, 0.03])), indel=0.002)):
+            files.append(str(tmp_path / ("t%d_g%d.fa" % (trial, k))))
+            M.write_fasta(files[-1], "g%d" % k, g.tobytes().decode())
+        opts = dict(minlength=int(rng.integers(8, 20)), minn=int(rng.integers(2, ng + 1)), trim=bool(rng.integers(0, 2)),
+                    seedsize=int(rng.choice([0, 15, 10000])), maxmums=int(rng.choice([2, 5, 1000])), wpen=int(rng.integers(0, 4)),
+                    wscore=int(rng.integers(1, 4)), gcmodel=str(rng.choice(["sumofpairs", "star-avg", "star-med"])))
+        got = []
+        for mode in ("0", "1"):
+            monkeypatch.setenv("RV_REM_PYTHON_GRAPH", mode)
+            G, idx = rem.align_genomes(rem.rem_args(files, **opts), index_module=R.module(32))
+            T = idx.T
+            if ng > 2:
+                rem.prune_nodes(G, T=T)
+            got.append(M.canonical(G, T))
+        assert got[0] == got[1], (trial, opts)
+        assert sum(n[2] != 0 for n in got[0]["nodes"]) > 0 or opts["minlength"] > 15, (trial, opts)
