@@ -40,6 +40,7 @@ PATCHES = [
     (r"\)/2\)", ")//2)"),                                       # py2 integer division (schemes.py:71)
     (r"len\(chainedmums\)/2", "len(chainedmums)//2"),           # schemes.py:349-351
     (r"len\(pointa\)/2", "len(pointa)//2"),                     # utils.py:169
+    (r"\)\)/len\(pointa\)", "))//len(pointa)"),                  # utils.py:166 (star-avg): integer division of integers
     (r"if tmpw>w or w==None:", "if w==None or tmpw>w:"),        # py2: int > None is True
     (r"xrange", "range"),
     (r"^class IntervalPatched\(intervaltree\.Interval\):", "class IntervalPatched(intervaltree.Interval):\n    __hash__=intervaltree.Interval.__hash__"),  # py3 drops __hash__ when __eq__ is defined
@@ -258,7 +259,9 @@ def run_case(rem, tmp, inputs, overrides):
                 path = os.path.join(tmp, "%s_graph%d.gfa" % (seed, gi))
                 rem.write_gfa(G, T, outputfile=path)
                 files.append(path)
-                texts.append(["graph%d.gfa" % gi, open(path).read()])
+                text = re.sub(r"^H\t[^\n]*\n", "H\tVN:Z:1.0\n", open(path).read())   # drop CL:Z:<command line> from the header
+                open(path, "w").write(text)
+                texts.append(["graph%d.gfa" % gi, text])
             else:
                 files.append(fastas[group])
                 texts.append(["g%d.fa" % group, open(fastas[group]).read()])

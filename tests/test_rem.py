@@ -264,3 +264,46 @@ def test_rem_native_graph_equals_python_graph_fuzz(tmp_path, monkeypatch):
             got.append(M.canonical(G, T))
         assert got[0] == got[1], (trial, opts)
         assert sum(n[2] != 0 for n in got[0]["nodes"]) > 0 or opts["minlength"] > 15, (trial, opts)
+
+
+def test_rem_driver_equals_reference_driver_fuzz(tmp_path):
+    """Build container only (needs /root/reference): the reference's own driver, rendered for Python 3 into a
+    temporary directory exactly as tests/golden/make_rem_golden.py does, against this driver on random genomes and
+    option mixes -- both on the reference's compiled extension."""
+    import importlib
+    import logging
+    import oracle.ref as R
+    if not os.path.isdir(os.path.join(M.REF, "reveal")) or not R.available():
+        pytest.skip("reference tree not present")
+    rendered = tmp_path / "rendered"
+    rendered.mkdir()
+    M.render(str(rendered))
+    logging.TRACE = 1
+    logging.trace = lambda msg, *a, **k: logging.log(1, msg, *a, **k)
+    sys.path.insert(0, str(rendered))
+    sys.path.insert(0, os.path.dirname(HERE))
+    try:
+        refrem = importlib.import_module("rem")
+        rng = np.random.default_rng(77)
+        for trial in range(25):
+            ng = int(rng.integers(2, 5))
+            length = int(rng.integers(1500, 8000))
+            files = []
+            for k, g in enumerate(synth.genomes(ng, length, seed=2000 + trial, snp=float(rng.choice([0.01, 0.04])), indel=0.002)):
+                files.append(str(tmp_path / ("r%d_g%d.fa" % (trial, k))))
+                M.write_fasta(files[-1], "g%d" % k, g.tobytes().decode())
+            opts = dict(minlength=int(rng.integers(8, 20)), minn=int(rng.integers(2, ng + 1)), trim=bool(rng.integers(0, 2)),
+                        seedsize=int(rng.choice([0, 15, 10000])), maxmums=int(rng.choice([2, 5, 1000])), wpen=int(rng.integers(1, 4)),
+                        wscore=int(rng.integers(1, 4)), gcmodel=str(rng.choice(["sumofpairs", "star-avg", "star-med"])))
+            G1, i1 = refrem.align_genomes(M.default_args(files, **opts))
+            T1 = i1.T
+            G2, i2 = rem.align_genomes(rem.rem_args(files, **opts), index_module=R.module(32))
+            T2 = i2.T
+            if ng > 2:
+                refrem.prune_nodes(G1, T=T1)
+                rem.prune_nodes(G2, T=T2)
+            assert M.canonical(G1, T1) == M.canonical(G2, T2), (trial, opts)
+    finally:
+        sys.path.remove(str(rendered))
+        for name in ("rem", "schemes", "utils", "reveallib", "reveallib64", "rv_intervaltree"):
+            sys.modules.pop(name, None)
