@@ -321,3 +321,39 @@ def test_rem_driver_equals_reference_driver_fuzz(tmp_path):
         sys.path.remove(str(rendered))
         for name in ("rem", "schemes", "utils", "reveallib", "reveallib64", "rv_intervaltree"):
             sys.modules.pop(name, None)
+
+
+def test_remcore_refuses_bad_input_without_crashing():
+    """The C++ graph reports misuse as Python exceptions."""
+    if rem._remcore is None:
+        pytest.skip("remcore module not built")
+    g = rem._remcore.Graph(True, rem.Interval, [True, True], [100, 100])
+    g.add_node(rem.Interval(0, 100), 0, {0: 0}, None)
+    g.add_node(rem.Interval(101, 201), 0, {1: 0}, None)
+    g.add_node("start", None, {0: 0, 1: 0}, {"endpoint": True})
+    g.add_edge("start", rem.Interval(0, 100), "+", "+", {0}, None)
+    g.add_edge("start", (101, 201), "+", "+", {1}, {"cigar": "0M"})
+    assert g.stats()[:2] == (3, 2)
+    assert g.coords(150) == ((1, 49),) and g.node_offsets((0, 100)) == {0: 0}
+    with pytest.raises(KeyError):
+        g.coords(100)                       # the separator between the two sequences belongs to no node
+    with pytest.raises(KeyError):
+        g.add_edge("nowhere", (0, 100), "+", "+", {0}, None)
+    with pytest.raises(KeyError):
+        g.node_offsets((5, 100))
+    nodes = {(0, 100), (101, 201)}
+    with pytest.raises(KeyError):
+        g.graphalign(nodes, None, None, 20, [90, 150])      # [90, 110) does not fit into its node
+    with pytest.raises(TypeError):
+        g.graphalign([(0, 100)], None, None, 20, [10, 150])  # nodes must be the set of the sub-index
+    with pytest.raises(TypeError):
+        g.pick([(10, 2)], 2, None, None, True, 1000, 0, 1, 1, 0)
+    assert g.pick([], 2, None, None, True, 1000, 0, 1, 1, 0) == ()
+    # a proper step still works afterwards
+    lead, trail, matching, rest, merged, newleft, newright = g.graphalign(nodes, None, None, 20, [10, 111])
+    assert merged == rem.Interval(10, 30) and matching == {(10, 30), (111, 131)}
+    assert lead == {(0, 10), (101, 111)} and trail == {(30, 100), (131, 201)} and rest == set()
+    assert nodes == {(0, 10), (30, 100), (101, 111), (131, 201)} and newleft == merged and newright == merged
+    n, e = g.export()
+    assert len(n) == 6 and {k for k, _ in n} >= {rem.Interval(10, 30), "start"}
+    assert [a for k, a in n if k == rem.Interval(10, 30)][0] == {"offsets": {0: 10, 1: 10}, "aligned": 1}
