@@ -134,7 +134,9 @@ int rv_result_pack_device(rv_index *idx, int64_t *d_dst, int64_t cap_rows);
 /* Peer blocks (multi-GPU, one box): device memory that the collecting rank allocates and the other ranks (one
  * process per GPU) map through CUDA IPC, so that rv_result_pack_device can write a rank's rows straight into the
  * collector's HBM over NVLink / NVSwitch -- no collective and no rendezvous on the data path
- * (reveal_b200/shard.py:PeerGather).  `handle` is RV_PEER_HANDLE_BYTES opaque bytes to hand to the other
+ * (reveal_b200/shard.py:PeerGather).  No counterpart in the reference, which is single-process (the
+ * path shards as independent index builds, the only exchange is the MUM records travelling to the rank that runs
+ * the callbacks).  `handle` is RV_PEER_HANDLE_BYTES opaque bytes to hand to the other
  * processes; rv_peer_open maps it (in another process than the allocating one), rv_peer_close unmaps,
  * rv_peer_free releases the allocation, rv_peer_read copies from a peer block to host memory (synchronous). */
 #define RV_PEER_HANDLE_BYTES 64
