@@ -983,10 +983,11 @@ def write_gfa(G, T, outputfile="reference.gfa", toupper=True):
                 if not isinstance(to, str):
                     f.write("L\t%d\t%s\t%d\t%s\t%s\n" % (ids[node], d.get("ofrom", "+"), ids[to], d.get("oto", "+"), d.get("cigar", "0M")))
         for name, sid in G.graph["path2id"].items():
-            walk = []
+            walk, overlaps = [], []   # one overlap per link between two segments of the walk
             if "startnodes" not in G.graph:  # a graph of align(): no markers, the path is its nodes in offset order
                 on_path = [n for n in order if sid in G.nodes[n]["offsets"]]
                 walk = ["%d+" % ids[n] for n in sorted(on_path, key=lambda n: G.nodes[n]["offsets"][sid])]
+                overlaps = ["0M"] * max(0, len(walk) - 1)
             for start in G.graph.get("startnodes", ()):
                 if start in G and sid in G.nodes[start]["offsets"]:
                     node = start
@@ -995,13 +996,16 @@ def write_gfa(G, T, outputfile="reference.gfa", toupper=True):
                         if len(nxt) != 1:
                             log.warning("path %s stops or forks at %s", name, node)
                             break
+                        prev = node
                         node, d = nxt[0]
                         if node in G.graph["endnodes"]:
                             break
                         if not isinstance(node, str):
                             walk.append("%d%s" % (ids[node], d.get("oto", "+")))
+                            if not isinstance(prev, str):
+                                overlaps.append(d.get("cigar", "0M"))
                     break
-            f.write("P\t%s\t%s\t%s\n" % (name, ",".join(walk), ",".join("0M" for _ in walk)))
+            f.write("P\t%s\t%s\t%s\n" % (name, ",".join(walk), ",".join(overlaps)))
     return outputfile
 
 

@@ -357,3 +357,42 @@ def test_remcore_refuses_bad_input_without_crashing():
     n, e = g.export()
     assert len(n) == 6 and {k for k, _ in n} >= {rem.Interval(10, 30), "start"}
     assert [a for k, a in n if k == rem.Interval(10, 30)][0] == {"offsets": {0: 10, 1: 10}, "aligned": 1}
+
+
+def test_write_gfa_equals_reference_writer(tmp_path):
+    """Build container only: on the SAME graph object the reference's seq2node + write_gfa (rendered for Python 3) and
+    this repository's write_gfa must produce the same file (header line aside: it carries the command line)."""
+    import importlib
+    import logging
+    import oracle.ref as R
+    if not os.path.isdir(os.path.join(M.REF, "reveal")) or not R.available():
+        pytest.skip("reference tree not present")
+    rendered = tmp_path / "rendered"
+    rendered.mkdir()
+    M.render(str(rendered))
+    logging.TRACE = 1
+    logging.trace = lambda msg, *a, **k: logging.log(1, msg, *a, **k)
+    sys.path.insert(0, str(rendered))
+    try:
+        refutils = importlib.import_module("utils")
+        for name in ("1a_1b", "1a_1b_1c", "gfa_x_fasta_3x10k"):
+            gold = load(name)
+            args = rem.rem_args(case_files(gold, tmp_path), **gold["args"])
+            G, idx = rem.align_genomes(args, index_module=R.module(32))
+            T = idx.T
+            if len(G.graph["paths"]) > 2:
+                rem.prune_nodes(G, T=T)
+            mine = rem.write_gfa(G, T, outputfile=str(tmp_path / (name + "_mine.gfa")))
+            # the reference looks nodes up by its own Interval type: same (begin, end), so relabel onto it
+            import networkx as nx
+            H = nx.relabel_nodes(G, {n: refutils.Interval(n.begin, n.end) for n in G if not isinstance(n, str)}, copy=True)
+            refutils.seq2node(H, T, remap=False)
+            theirs = str(tmp_path / (name + "_ref.gfa"))
+            refutils.write_gfa(H, T, outputfile=theirs)
+            a = [x for x in open(mine).read().splitlines() if not x.startswith("H")]
+            b = [x for x in open(theirs).read().splitlines() if not x.startswith("H")]
+            assert a == b, name
+    finally:
+        sys.path.remove(str(rendered))
+        for mod in ("rem", "schemes", "utils", "reveallib", "reveallib64", "rv_intervaltree"):
+            sys.modules.pop(mod, None)
