@@ -591,6 +591,61 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     Py_RETURN_NONE;
 }
 
+// ---- splitindex (reveal.c:1515-1748): one recursion step driven from Python -------------------------------------------------------
+// splitindex(leading, trailing, matching, rest, merged, newleft, newright, skipleft, skipright) -> (lead | None, trail | None, par | None)
+// The same device step as inside align(): label scatter, T lower-casing of the matching intervals, 3-way split, bubble_sort of the
+// leading child.  The matching intervals must all have one length (they are the occurrences of one exact match).
+static PyObject *index_splitindex(Index *idx, PyObject *args) {
+    PyObject *leading, *trailing, *matching, *rest, *merged, *newleft, *newright, *skipleft, *skipright;
+    if (!PyArg_ParseTuple(args, "OOOOOOOOO", &leading, &trailing, &matching, &rest, &merged, &newleft, &newright, &skipleft, &skipright)) return nullptr;
+    Index *root = root_of(idx);
+    if (!root->built) {
+        PyErr_SetString(RevealError, "Index not yet constructed.");
+        return nullptr;
+    }
+    if (!idx->sub) {
+        if (idx->mainidx) {
+            PyErr_SetString(RevealError, "splitindex: the arrays of this sub-index were already released");
+            return nullptr;
+        }
+        if (fail_native(g_api.rv_sub_root(root->h, &idx->sub)) != 0) return nullptr;
+    }
+    std::vector<int64_t> lead, trail, par, match, lead_b, trail_b, par_b, match_b;
+    int64_t leadn, trailn, parn, matchn;
+    if (!parse_intervals(leading, lead, leadn, lead_b) || !parse_intervals(trailing, trail, trailn, trail_b) ||
+        !parse_intervals(rest, par, parn, par_b) || !parse_intervals(matching, match, matchn, match_b))
+        return nullptr;
+    int64_t mum_l = match_b.empty() ? 0 : match[1] - match[0];
+    for (size_t k = 0; k < match_b.size(); k++)
+        if (match[2 * k + 1] - match[2 * k] != mum_l) {
+            PyErr_SetString(RevealError, "splitindex: matching intervals of different lengths are not supported");
+            return nullptr;
+        }
+    if (match_b.empty()) match_b.push_back(0);
+    int32_t sweep[3] = {0, 0, 0};
+    rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+    const int32_t nmatch = (int32_t)(match.size() / 2);
+    int status;
+    Py_BEGIN_ALLOW_THREADS;
+    status = g_api.rv_sub_step(idx->sub, lead.data(), (int32_t)lead_b.size(), trail.data(), (int32_t)trail_b.size(), par.data(), (int32_t)par_b.size(),
+                               match_b.data(), nmatch, mum_l, match.data(), nmatch, sweep, 0, 2, kids);
+    Py_END_ALLOW_THREADS;
+    if (fail_native(status) != 0) return nullptr;
+    root->tdirty = 1;
+    const int depth = idx->depth + 1;
+    PyObject *empty = PyList_New(0);
+    PyObject *out[3];
+    Index *c;
+    c = kids[0] ? new_child(root, kids[0], leadn, depth, count_samples(root, lead_b), leading, idx->left_node, newright, skipleft) : nullptr;
+    out[0] = c ? (PyObject *)c : (Py_INCREF(Py_None), Py_None);
+    c = kids[1] ? new_child(root, kids[1], trailn, depth, count_samples(root, trail_b), trailing, newleft, idx->right_node, skipright) : nullptr;
+    out[1] = c ? (PyObject *)c : (Py_INCREF(Py_None), Py_None);
+    c = kids[2] ? new_child(root, kids[2], parn, depth, count_samples(root, par_b), rest, idx->left_node, idx->right_node, empty) : nullptr;
+    out[2] = c ? (PyObject *)c : (Py_INCREF(Py_None), Py_None);
+    Py_DECREF(empty);
+    return Py_BuildValue("(NNN)", out[0], out[1], out[2]);
+}
+
 // ---- copy (interface.c:432-470) -----------------------------------------------------------------------------------------------
 static PyObject *index_copy(Index *self, PyObject *) {
     if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
@@ -710,6 +765,8 @@ static PyObject *index_reduce(Index *, PyObject *) { Py_RETURN_NONE; }  // inter
 
 static PyMethodDef index_methods[] = {
     {"align", (PyCFunction)index_align, METH_VARARGS | METH_KEYWORDS, nullptr},
+    {"splitindex", (PyCFunction)index_splitindex, METH_VARARGS,
+     "splitindex(leading, trailing, matching, rest, merged, newleft, newright, skipleft, skipright) -> (lead, trail, par): one recursion step."},
     {"copy", (PyCFunction)index_copy, METH_NOARGS, nullptr},
     {"addsample", (PyCFunction)index_addsample, METH_VARARGS, nullptr},
     {"addsequence", (PyCFunction)index_addsequence, METH_VARARGS, nullptr},

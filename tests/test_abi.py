@@ -52,7 +52,7 @@ def test_extension_modules_build_and_import():
     from reveal_b200 import remcore, reveallib, reveallib64
     assert callable(reveallib.chain_dp) and all(hasattr(remcore.Graph, m) for m in ("graphalign", "pick", "coords", "export"))
     for mod in (reveallib, reveallib64):
-        for name in ("addsample", "addsequence", "construct", "align", "getmums", "getmultimums", "getmultimems", "copy",
+        for name in ("addsample", "addsequence", "construct", "align", "splitindex", "getmums", "getmultimums", "getmultimems", "copy",
                      "n", "depth", "nsamples", "samples", "nodes", "leftnode", "rightnode", "nsep", "SA", "SAi", "SO", "LCP", "T"):
             assert hasattr(mod.index, name), name
         assert issubclass(mod.error, Exception)

@@ -147,3 +147,58 @@ def test_align_callback_failure_is_reported_and_leaves_no_wreckage(emu_reveallib
     mp, ga = make_callbacks(log_b, minlen=8)
     ref.align(mp, ga, minl=8, minn=2)
     assert len(log_a) == len(log_b) and idx.T == ref.T[:ref.n]
+
+
+@needs_ref
+@pytest.mark.parametrize("ns,length,minl", [(3, 1000, 8), (4, 700, 7), (5, 500, 7)])   # the reference's getmultimums needs SO: N > 2
+def test_splitindex_matches_reference(emu_reveallib, ns, length, minl):
+    """index.splitindex (reveal.c:1515-1748): the recursion driven from Python, two levels deep, against the
+    reference's own splitindex -- children's n / nsamples / depth / nodes / bounds / SA / LCP and the text."""
+    if emu_reveallib.name == "ctypes":
+        pytest.skip("splitindex is part of the compiled extension")
+    rng = np.random.default_rng(900 + ns)
+    samples = random_related(rng, ns, length, 4, snp=0.03)
+    seqs = [[bytes(c).decode() for c in contigs] for contigs in samples]
+
+    def build(mod):
+        idx = mod.index()
+        for k, contigs in enumerate(seqs):
+            idx.addsample("s%d" % k)
+            for c in contigs:
+                idx.addsequence(c)
+        idx.construct()
+        return idx
+
+    def describe(child):
+        if child is None:
+            return None
+        return (child.n, child.nsamples, child.depth, sorted(child.nodes), child.leftnode, child.rightnode, list(child.SA), list(child.LCP))
+
+    ours, ref = build(emu_reveallib.mod32), build(R.module(32))
+    frontier = [(ours, ref)]
+    steps = 0
+    for level in range(3):
+        nxt = []
+        for a, b in frontier:
+            ma = a.getmultimums(minlength=minl, minn=2)
+            mb = b.getmultimums(minlength=minl, minn=2)
+            assert [tuple(m) for m in ma] == [tuple(m) for m in mb]
+            picks = []
+            for idx, mums in ((a, ma), (b, mb)):
+                mp, ga = make_callbacks([], minlen=minl)
+                pick = mp(mums, idx)
+                picks.append((pick, ga(idx, pick[0]) if pick else None))
+            if not picks[0][0] or picks[0][1] is None:
+                continue
+            (pa, ra), (pb, rb) = picks
+            assert ra == rb
+            ka = a.splitindex(*ra, [], [])
+            kb = b.splitindex(*rb, [], [])
+            steps += 1
+            for ca, cb in zip(ka, kb):
+                assert describe(ca) == describe(cb)
+                if ca is not None and ca.n > 1:
+                    nxt.append((ca, cb))
+        frontier = nxt
+    assert steps >= 3
+    assert ours.T == ref.T[:ref.n]
