@@ -396,3 +396,35 @@ def test_write_gfa_equals_reference_writer(tmp_path):
         sys.path.remove(str(rendered))
         for mod in ("rem", "schemes", "utils", "reveallib", "reveallib64", "rv_intervaltree"):
             sys.modules.pop(mod, None)
+
+
+def test_rem_gzipped_input_and_output(tmp_path):
+    """FASTA.gz in, GFA.gz out, GFA.gz back in: same graph as with plain files (reference extension as the index)."""
+    import oracle.ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    gold = load("synth3_3k")
+    plain = case_files(gold, tmp_path)
+    zipped = []
+    for fn in plain:
+        zipped.append(fn + ".gz")
+        with gzip.open(zipped[-1], "wt") as f:
+            f.write(open(fn).read())
+    results = []
+    for files in (plain, zipped):
+        G, idx = rem.align_genomes(rem.rem_args(files, **gold["args"]), index_module=R.module(32))
+        rem.prune_nodes(G, T=idx.T)
+        results.append((G, idx))
+    a, b = (M.canonical(G, idx.T) for G, idx in results)
+    a["walks"] = sorted(a["walks"].values())
+    b["walks"] = sorted(b["walks"].values())
+    assert a == b
+    G, idx = results[1]
+    out = rem.write_gfa(G, idx.T, outputfile=str(tmp_path / "graph"))          # no extension: .gfa.gz is added
+    assert out.endswith(".gfa.gz") and gzip.open(out, "rt").readline().startswith("H\tVN:Z:1.0")
+    # the written graph as input again, against one more sequence
+    extra = str(tmp_path / "extra.fa.gz")
+    with gzip.open(extra, "wt") as f:
+        f.write(">extra\n%s\n" % synth.genomes(1, 3000, seed=22)[0].tobytes().decode())
+    G2, idx2 = rem.align_genomes(rem.rem_args([out, extra], minlength=10), index_module=R.module(32))
+    assert len(G2.graph["paths"]) == 4 and rem.aligned_bases(G2, idx2)[0] > 0
