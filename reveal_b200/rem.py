@@ -1026,7 +1026,7 @@ def align_cmd(args):
 
 
 def main(argv=None):
-    p = argparse.ArgumentParser(prog="python -m reveal_b200.rem", description="Recursive exact matching of FASTA files into a GFA graph.")
+    p = argparse.ArgumentParser(prog="python -m reveal_b200.rem", description="Recursive exact matching of FASTA / GFA files into a GFA graph.")
     p.add_argument("inputfiles", nargs="+")
     p.add_argument("-o", "--output", dest="output")
     p.add_argument("-t", "--threads", dest="threads", type=int, default=0)
