@@ -377,24 +377,31 @@ def run_ours(args, rank, world, local_rank):
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
+    gather_check = None
     if world > 1:
-        # rank 0: every rank's rows of the last step arrived (raises on overflow / on a block that is not the last pack's)
-        if gatherer["kind"] == "peer":
-            parts = gatherer["g"].check(expect_seq=gatherer["g"].step)
-            mine = result_rows()  # every rank: (row count, wrapping sum of its rows) of the last step, to compare on rank 0
-            sig = torch.tensor([mine.shape[0], int(mine.sum(dtype=np.int64))], dtype=torch.int64, device=dev)
-            sigs = [torch.zeros_like(sig) for _ in range(world)]
-            dist.all_gather(sigs, sig)
-            if rank == 0:
-                assert len(parts) == world and all(len(rows) > 0 for rows, _ in parts)
-                assert np.array_equal(parts[0][0], mine), "rank 0's own block differs from its sweep result"
-                for r in range(world):
-                    got = [parts[r][0].shape[0], int(parts[r][0].sum(dtype=np.int64))]
-                    assert got == sigs[r].tolist(), "rank %d: rows in rank 0's ring differ from what the rank produced" % r
-        else:
-            parts = gatherer["g"].check()
-            if rank == 0:
-                assert len(parts) == world and all(len(x) > 0 for x in parts)
+        # rank 0: every rank's rows of the last step arrived.  A failed check is REPORTED in the JSON line ("gather_check") and on
+        # stderr instead of raised: rank 0 dying here would leave the other ranks waiting in the collectives that follow.
+        try:
+            if gatherer["kind"] == "peer":
+                mine = result_rows()  # every rank: (row count, wrapping sum of its rows) of the last step, to compare on rank 0
+                sig = torch.tensor([mine.shape[0], int(mine.sum(dtype=np.int64))], dtype=torch.int64, device=dev)
+                sigs = [torch.zeros_like(sig) for _ in range(world)]
+                dist.all_gather(sigs, sig)
+                parts = gatherer["g"].check(expect_seq=gatherer["g"].step)   # barrier inside; raises on overflow / stale blocks (rank 0)
+                if rank == 0:
+                    assert len(parts) == world and all(len(rows) > 0 for rows, _ in parts), "a rank delivered no rows"
+                    assert np.array_equal(parts[0][0], mine), "rank 0's own block differs from its sweep result"
+                    for r in range(world):
+                        got = [parts[r][0].shape[0], int(parts[r][0].sum(dtype=np.int64))]
+                        assert got == sigs[r].tolist(), "rank %d: rows in rank 0's ring differ from what the rank produced" % r
+            else:
+                parts = gatherer["g"].check()
+                if rank == 0:
+                    assert len(parts) == world and all(len(x) > 0 for x in parts), "a rank delivered no rows"
+            gather_check = "ok: rows of every rank verified on rank 0 after the timed region"
+        except Exception as e:
+            gather_check = "FAILED: %s: %s" % (type(e).__name__, e)
+            print("[bench] rank %d: gather check %s" % (rank, gather_check), file=sys.stderr)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     gather_ms = sum(a.elapsed_time(b) for a, b in gather_evs[-args.steps:]) / args.steps if gather_evs else 0.0
     prof = _native.KernelProfile()
@@ -446,7 +453,7 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "flushed between timed steps (256 MiB write)", "sharding": ("independent index build per rank; MUM records to rank 0 through " + ("mapped peer blocks (NVLink stores, no collective)" if gatherer.get("kind") == "peer" else "one NCCL gather per step")) if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n + 8 * len(nsep)), "d2h_bytes_per_step": int(d2h + 32),
                         "ms_per_step": e2e_ms_max / args.steps},
-                "gpu_launches": launches, "gather_ms_per_step": gather_ms,
+                "gpu_launches": launches, "gather_ms_per_step": gather_ms, "gather_check": gather_check,
                 # the dominant kernel = largest measured share of the step; algorithmic bytes per slot: include/reveal_b200.h, DESIGN.md
                 "roofline": {"bound": "hbm", "kernel": top.get("kernel"), "achieved": top.get("achieved"), "peak": peak, "unit": "GB/s",
                              "frac": top.get("frac"), "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
