@@ -39,6 +39,10 @@ WORKLOADS = {
     "c3": (5, 5_000_000, "5 synthetic 5 Mbp genomes, simultaneous rem anchor (BASELINE configs[2])"),
     "c4": (2, 100_000_000, "2 synthetic 100 Mbp genomes (BASELINE configs[3], root build + sweep)"),
     "tiny": (2, 200_000, "2 synthetic 200 kbp genomes (plumbing)"),
+    # repeat-bearing inputs (SURVEY 8d "realistic repeat-bearing check"): the doubling rounds and the LCP fallback run here
+    "real": (2, 0, "reference fixtures tests/123a.fa + 123b.fa (3 + 3 Aspergillus niger contigs, n = 10 754 553; committed compact copy tests/golden/real/asp_niger.npz), rem -m 20 -n 2"),
+    "repeats": (2, 5_000_000, "2 synthetic 5 Mbp genomes on a repeat-bearing ancestor (interspersed families, tandem arrays, segmental duplications, N runs), rem -m 20 -n 2"),
+    "graph": (2, 10_000_000, "graph-like text: 2 samples of 10 Mbp cut into 5e5 contigs each (one '$' per node, SURVEY 8 C5)"),
 }
 MINL, MINN = 20, 2
 METRIC = "aligned bases/sec (rem anchor phase: index build + MUM sweep)"
@@ -147,7 +151,16 @@ class ClockSampler(threading.Thread):
 def make_workload(name, seed):
     from reveal_b200 import synth
     g, length, desc = WORKLOADS[name]
-    T, nsep, ns = synth.workload(g, length, seed=seed)
+    if name == "real":
+        a, b, _ = synth.load_packed_fixture(os.path.join(ROOT, "tests", "golden", "real", "asp_niger.npz"))
+        T, nsep = synth.concat([a, b])
+        return T, nsep, 2, desc
+    if name == "repeats":
+        T, nsep, ns = synth.repeat_workload(g, length, seed=seed)
+    elif name == "graph":
+        T, nsep, ns = synth.graph_like_workload(500_000, 20, seed=seed)
+    else:
+        T, nsep, ns = synth.workload(g, length, seed=seed)
     return T, nsep, ns, desc
 
 

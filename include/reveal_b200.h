@@ -62,6 +62,13 @@ int rv_set_device(int device);
 int rv_index_create(rv_index **out, void *stream);
 void rv_index_free(rv_index *idx);
 
+/* Pinned host memory for the text handed to rv_build: the extension's addsequence (interface.c:45-95, which reallocs
+ * its T) appends straight into such a block, so construct() is one DMA without a staging copy.  Blocks -- like the
+ * device workspaces of freed handles -- are kept by the library for the next user; rv_trim() releases what is cached. */
+int rv_host_alloc(int64_t bytes, void **ptr);
+void rv_host_free(void *ptr);
+int rv_trim(void);
+
 /* construct(): T = concatenated text of n bytes ('$' after every sequence,
  * interface.c:71-85), nsep[k] = position of the last '$' of sample k
  * (nsamples-1 entries, interface.c:36-43), rc = 1 reverse-complements
@@ -84,7 +91,7 @@ enum rv_prof_slot {
     RV_PROF_RADIX_PASS = 0, /* rs_pass_kernel: items x (key + 4 B suffix) x (read + write) */
     RV_PROF_PAIRS = 1,      /* sa_pairs_kernel: n x (key + 4 B suffix read; SA + SAi + LCP = 12 B written) */
     RV_PROF_SWEEP = 2,      /* pair / multi sweep kernels (count + write): n x 9 B (11 B with SO) per pass */
-    RV_PROF_LCP = 3         /* lcp_kasai_kernel (fallback): n x 13 B */
+    RV_PROF_LCP = 3         /* lcp_sparse_kernel (entries of the suffixes the doubling rounds placed): 13 B per marked position + n/8 */
 };
 typedef struct rv_kernel_profile {
     double ms[4];

@@ -24,7 +24,7 @@ class Times(ctypes.Structure):
 
 
 class KernelProfile(ctypes.Structure):
-    SLOTS = ("rs_pass_kernel", "sa_pairs_kernel", "sweep kernels", "lcp_kasai_kernel")
+    SLOTS = ("rs_pass_kernel", "sa_pairs_kernel", "sweep kernels", "lcp_sparse_kernel")
     _fields_ = [("ms", ctypes.c_double * 4), ("launches", ctypes.c_int64 * 4), ("bytes", ctypes.c_int64 * 4),
                 ("launches_total", ctypes.c_int64)]
 
@@ -38,6 +38,9 @@ SIGNATURES = {
     "rv_version": (ctypes.c_char_p, []),
     "rv_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
     "rv_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "rv_host_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_vp)]),
+    "rv_host_free": (None, [c_vp]),
+    "rv_trim": (ctypes.c_int, []),
     "rv_index_create": (ctypes.c_int, [ctypes.POINTER(c_vp), c_vp]),
     "rv_index_free": (None, [c_vp]),
     "rv_build": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_int32]),

@@ -15,6 +15,7 @@
 #include <Python.h>
 #include <dlfcn.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -32,7 +33,7 @@
 
 // ---- the C-ABI, resolved at run time ---------------------------------------------------------------------------------
 #define RV_API_LIST(X)                                                                                                  \
-    X(rv_last_error) X(rv_version) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
+    X(rv_last_error) X(rv_version) X(rv_host_alloc) X(rv_host_free) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
     X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
     X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_free) X(rv_sub_get)    \
     X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step)
@@ -78,12 +79,67 @@ static bool api_ready() {
     return false;
 }
 
+// ---- host copy of the text: grows like the reference's realloc'ed T (interface.c:70-83), but in pinned memory from the
+// library (rv_host_alloc) so that construct() is one DMA; plain malloc while the library is not loaded or refuses ----------
+struct HostText {
+    char *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    HostText() {}
+    HostText(const HostText &) = delete;
+    HostText &operator=(const HostText &) = delete;
+    ~HostText() { drop(); }
+    void drop() {
+        if (p) {
+            if (pinned) g_api.rv_host_free(p); else free(p);
+        }
+        p = nullptr;
+        n = cap = 0;
+    }
+    bool reserve(size_t need) {
+        if (need <= cap) return true;
+        size_t c = cap ? cap * 2 : (size_t)1 << 12;
+        while (c < need) c *= 2;
+        char *q = nullptr;
+        bool pin = false;
+        void *vp = nullptr;
+        if (c >= ((size_t)1 << 16) && g_api.rv_host_alloc && g_api.rv_host_alloc((int64_t)c, &vp) == 0) {
+            q = (char *)vp;
+            pin = true;
+        } else {
+            q = (char *)malloc(c);
+        }
+        if (!q) return false;
+        if (n) memcpy(q, p, n);
+        size_t keep = n;
+        drop();
+        p = q;
+        n = keep;
+        cap = c;
+        pinned = pin;
+        return true;
+    }
+    bool append(const char *src, size_t len) {
+        if (!reserve(n + len + 1)) return false;
+        memcpy(p + n, src, len);
+        n += len;
+        return true;
+    }
+    bool push_back(char c) { return append(&c, 1); }
+    bool assign(const HostText &o) {
+        n = 0;
+        return append(o.p, o.n);
+    }
+    const char *data() const { return p ? p : ""; }
+    size_t size() const { return n; }
+};
+
 // ---- the index type ----------------------------------------------------------------------------------------------------
 struct Index {
     PyObject_HEAD
     // root state
     rv_index *h;
-    std::string *T;              // host copy of the text (root only)
+    HostText *T;                 // host copy of the text (root only)
     std::vector<int64_t> *nsep;
     int nsamples, rc, depth, cache, built, tdirty;
     int64_t n, nT;
@@ -114,7 +170,7 @@ static PyObject *index_new(PyTypeObject *type, PyObject *, PyObject *) {
     Index *self = (Index *)type->tp_alloc(type, 0);
     if (!self) return nullptr;
     self->h = nullptr;
-    self->T = new std::string();
+    self->T = new HostText();
     self->nsep = new std::vector<int64_t>();
     self->safile = new std::string();
     self->lcpfile = new std::string();
@@ -187,8 +243,7 @@ static PyObject *index_addsequence(Index *self, PyObject *args) {
     }
 #endif
     int64_t s = self->n;
-    self->T->append(seq, (size_t)l);
-    self->T->push_back('$');
+    if (!self->T->append(seq, (size_t)l) || !self->T->push_back('$')) return PyErr_NoMemory();
     self->n += l + 1;
     PyObject *intv = Py_BuildValue("(L,L)", (long long)s, (long long)(self->n - 1));
     if (!intv) return nullptr;
@@ -302,9 +357,16 @@ static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vecto
         int64_t l = hdr[3 * k], cnt = hdr[3 * k + 1], first = hdr[3 * k + 2];
         int64_t end = counts_are_sizes ? first + cnt : (k + 1 < nrec ? hdr[3 * (k + 1) + 2] : nmem);
         PyObject *members = PyTuple_New((Py_ssize_t)(end - first));
-        for (int64_t x = first; x < end; x++)
-            PyTuple_SET_ITEM(members, (Py_ssize_t)(x - first), Py_BuildValue("(i,L)", (int)mem[2 * x], (long long)mem[2 * x + 1]));
-        PyObject *rec = Py_BuildValue("(L,i,N)", (long long)l, (int)cnt, members);  // reveal.c:497 / :353
+        for (int64_t x = first; x < end; x++) {
+            PyObject *sp = PyTuple_New(2);
+            PyTuple_SET_ITEM(sp, 0, PyLong_FromLong((long)mem[2 * x]));
+            PyTuple_SET_ITEM(sp, 1, PyLong_FromLongLong((long long)mem[2 * x + 1]));
+            PyTuple_SET_ITEM(members, (Py_ssize_t)(x - first), sp);
+        }
+        PyObject *rec = PyTuple_New(3);  // (l, n, ((sample, position), ...)): reveal.c:497 / :353
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)l));
+        PyTuple_SET_ITEM(rec, 1, PyLong_FromLong((long)cnt));
+        PyTuple_SET_ITEM(rec, 2, members);
         PyList_SET_ITEM(lst, (Py_ssize_t)k, rec);
     }
     return lst;
@@ -326,8 +388,19 @@ static PyObject *index_getmums(Index *self, PyObject *args) {
     std::vector<int64_t> rows((size_t)(3 * k + 3));
     if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
     PyObject *lst = PyList_New((Py_ssize_t)k);
-    for (int64_t i = 0; i < k; i++)  // (l, (a, b), rc): reveal.c:102-106
-        PyList_SET_ITEM(lst, (Py_ssize_t)i, Py_BuildValue("(L,(L,L),i)", (long long)rows[3 * i], (long long)rows[3 * i + 1], (long long)rows[3 * i + 2], self->rc));
+    if (!lst) return nullptr;
+    PyObject *rcobj = PyLong_FromLong(self->rc);
+    for (int64_t i = 0; i < k; i++) {  // (l, (a, b), rc): reveal.c:102-106 -- built without format parsing, this list is the bulk of the call
+        PyObject *ab = PyTuple_New(2), *rec = PyTuple_New(3);
+        PyTuple_SET_ITEM(ab, 0, PyLong_FromLongLong((long long)rows[3 * i + 1]));
+        PyTuple_SET_ITEM(ab, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));
+        PyTuple_SET_ITEM(rec, 1, ab);
+        Py_INCREF(rcobj);
+        PyTuple_SET_ITEM(rec, 2, rcobj);
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, rec);
+    }
+    Py_DECREF(rcobj);
     return lst;
 }
 
@@ -458,8 +531,26 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
     std::vector<int64_t> rows((size_t)(3 * nr + 3));
     if (fail_native(g_api.rv_sub_fetch(sub, rows.data(), nr, nullptr, 0)) != 0) return nullptr;
     PyObject *lst = PyList_New((Py_ssize_t)nr);
-    for (int64_t i = 0; i < nr; i++)  // (l, 2, ((0, a), (1, b))): reveal.c:167-169
-        PyList_SET_ITEM(lst, (Py_ssize_t)i, Py_BuildValue("(L,i,((i,L),(i,L)))", (long long)rows[3 * i], 2, 0, (long long)rows[3 * i + 1], 1, (long long)rows[3 * i + 2]));
+    PyObject *two = PyLong_FromLong(2), *zero = PyLong_FromLong(0), *one = PyLong_FromLong(1);
+    for (int64_t i = 0; i < nr; i++) {  // (l, 2, ((0, a), (1, b))): reveal.c:167-169
+        PyObject *sa = PyTuple_New(2), *sb = PyTuple_New(2), *mem = PyTuple_New(2), *rec = PyTuple_New(3);
+        Py_INCREF(zero);
+        PyTuple_SET_ITEM(sa, 0, zero);
+        PyTuple_SET_ITEM(sa, 1, PyLong_FromLongLong((long long)rows[3 * i + 1]));
+        Py_INCREF(one);
+        PyTuple_SET_ITEM(sb, 0, one);
+        PyTuple_SET_ITEM(sb, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
+        PyTuple_SET_ITEM(mem, 0, sa);
+        PyTuple_SET_ITEM(mem, 1, sb);
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));
+        Py_INCREF(two);
+        PyTuple_SET_ITEM(rec, 1, two);
+        PyTuple_SET_ITEM(rec, 2, mem);
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, rec);
+    }
+    Py_DECREF(two);
+    Py_DECREF(zero);
+    Py_DECREF(one);
     return lst;
 }
 
@@ -652,10 +743,10 @@ static PyObject *index_copy(Index *self, PyObject *) {
     Index *c = (Index *)index_new(&IndexType, nullptr, nullptr);
     if (!c) return nullptr;
     if (self->tdirty) {
-        if (fail_native(g_api.rv_get_text(self->h, (uint8_t *)&(*self->T)[0])) != 0) { Py_DECREF(c); return nullptr; }
+        if (fail_native(g_api.rv_get_text(self->h, (uint8_t *)self->T->p)) != 0) { Py_DECREF(c); return nullptr; }
         self->tdirty = 0;
     }
-    *c->T = *self->T;
+    if (!c->T->assign(*self->T)) { Py_DECREF(c); return PyErr_NoMemory(); }
     *c->nsep = *self->nsep;
     c->n = self->n;
     c->nT = self->nT;
@@ -726,7 +817,7 @@ static PyObject *get_SO(Index *self, void *) {
 static PyObject *get_T(Index *self, void *) {
     Index *r = root_of(self);
     if (r->built && r->tdirty) {  // rc or align changed the device text: refresh the host copy
-        if (fail_native(g_api.rv_get_text(r->h, (uint8_t *)&(*r->T)[0])) != 0) return nullptr;
+        if (fail_native(g_api.rv_get_text(r->h, (uint8_t *)r->T->p)) != 0) return nullptr;
         r->tdirty = 0;
     }
     return PyUnicode_DecodeLatin1(r->T->data(), (Py_ssize_t)r->T->size(), nullptr);
@@ -797,9 +888,14 @@ static PyGetSetDef index_getset[] = {
     {nullptr, nullptr, nullptr, nullptr, nullptr}};
 
 // ---- module -------------------------------------------------------------------------------------------------------------------------
+static bool g_test_hooks = false;  // REVEAL_B200_TEST_HOOKS=1 in the environment when the module was imported
 static PyObject *mod_load(PyObject *, PyObject *args) {
     const char *path;
     if (!PyArg_ParseTuple(args, "s", &path)) return nullptr;
+    if (!g_test_hooks) {
+        PyErr_SetString(PyExc_RuntimeError, MODNAME "._load is a test hook: it only works when REVEAL_B200_TEST_HOOKS=1 was set before the import");
+        return nullptr;
+    }
     if (!load_library(path)) return nullptr;
     Py_RETURN_NONE;
 }
@@ -865,6 +961,10 @@ PyMODINIT_FUNC MODINIT(void) {
     RevealError = PyErr_NewException(MODNAME ".error", nullptr, nullptr);
     Py_INCREF(RevealError);
     PyModule_AddObject(m, "error", RevealError);
+    {
+        const char *e = getenv("REVEAL_B200_TEST_HOOKS");
+        g_test_hooks = e && e[0] == '1';
+    }
     // default library: libreveal_b200.so next to this module
     Dl_info info;
     if (dladdr((void *)&MODINIT, &info) && info.dli_fname) {

@@ -12,6 +12,7 @@
 #include "rv_sweep.h"
 #include <stdarg.h>
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 
 namespace rv {
@@ -25,9 +26,50 @@ void set_error(const char *fmt, ...) {
     va_end(va);
 }
 
+// Device slabs of released arenas and pinned host blocks wait here for the next user: a caller that creates one index object
+// per alignment (the extension does) would otherwise pay cudaMalloc + cudaFree (both synchronise the device) and a
+// cudaHostAlloc (page locking: milliseconds) per construct().
+struct Cached { void *p; size_t bytes; int device; };
+static std::mutex g_cache_mu;
+static std::vector<Cached> g_dev_cache, g_host_cache, g_host_live;
+static const size_t CACHE_SLOTS = 4;
+
+static void *cache_take(std::vector<Cached> &c, size_t bytes, int device, size_t *got) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int best = -1;
+    for (int i = 0; i < (int)c.size(); i++)
+        if (c[i].device == device && c[i].bytes >= bytes && (best < 0 || c[i].bytes < c[best].bytes)) best = i;
+    if (best < 0) return nullptr;
+    void *p = c[best].p;
+    *got = c[best].bytes;
+    c.erase(c.begin() + best);
+    return p;
+}
+// returns the block that has to be released for real (the smallest one when the cache is full), or nullptr
+static void *cache_put(std::vector<Cached> &c, void *p, size_t bytes, int device) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    c.push_back(Cached{p, bytes, device});
+    if (c.size() <= CACHE_SLOTS) return nullptr;
+    int worst = 0;
+    for (int i = 1; i < (int)c.size(); i++)
+        if (c[i].bytes < c[worst].bytes) worst = i;
+    void *out = c[worst].p;
+    c.erase(c.begin() + worst);
+    return out;
+}
+
 int Arena::reserve(size_t bytes) {
     if (bytes <= cap) return RV_OK;
     release();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t got = 0;
+    if (void *c = cache_take(g_dev_cache, bytes, dev, &got)) {
+        base = (unsigned char *)c;
+        cap = got;
+        off = 0;
+        return RV_OK;
+    }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
@@ -40,7 +82,12 @@ int Arena::reserve(size_t bytes) {
     return RV_OK;
 }
 void Arena::release() {
-    if (base) cudaFree(base);
+    // callers synchronise the stream that used the slab first (rv_index_free; reserve() on a grown request runs between builds)
+    if (base) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (void *drop = cache_put(g_dev_cache, base, cap, dev)) cudaFree(drop);
+    }
     base = nullptr;
     cap = off = 0;
 }
@@ -103,6 +150,72 @@ int rv_device_count(int *count) {
 }
 int rv_set_device(int device) {
     RV_CUDA(cudaSetDevice(device));
+    return RV_OK;
+}
+
+int rv_host_alloc(int64_t bytes, void **ptr) {
+    if (bytes <= 0 || !ptr) return RV_ERR_ARG;
+    size_t got = 0;
+    if (void *c = cache_take(g_host_cache, (size_t)bytes, -1, &got)) {
+        *ptr = c;
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_host_live.push_back(Cached{c, got, -1});
+        return RV_OK;
+    }
+    void *p = nullptr;
+#ifdef RV_EMU
+    p = malloc((size_t)bytes);
+    if (!p) { set_error("malloc(%lld) failed", (long long)bytes); return RV_ERR_NOMEM; }
+#else
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return RV_ERR_NOMEM;
+    }
+#endif
+    *ptr = p;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_host_live.push_back(Cached{p, (size_t)bytes, -1});
+    return RV_OK;
+}
+static void host_release(void *p) {
+#ifdef RV_EMU
+    free(p);
+#else
+    cudaFreeHost(p);
+#endif
+}
+void rv_host_free(void *ptr) {
+    if (!ptr) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_host_live.size(); i++)
+            if (g_host_live[i].p == ptr) {
+                bytes = g_host_live[i].bytes;
+                g_host_live.erase(g_host_live.begin() + (long)i);
+                break;
+            }
+    }
+    if (!bytes) return;  // not one of ours
+    if (void *drop = cache_put(g_host_cache, ptr, bytes, -1)) host_release(drop);
+}
+int rv_trim(void) {
+    std::vector<Cached> d, h;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        d.swap(g_dev_cache);
+        h.swap(g_host_cache);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (Cached &c : d) {
+        cudaSetDevice(c.device);
+        cudaFree(c.p);
+    }
+    cudaSetDevice(cur);
+    for (Cached &c : h) host_release(c.p);
     return RV_OK;
 }
 
@@ -236,7 +349,7 @@ static int build_common(rv_index *h, const uint8_t *T, bool T_on_device, int64_t
         RV_TRY(sa_build(st, h->arena, h->dT, n, h->dSA, h->dISA, h->dLCP, &lcp_done, &pt));
     }
     RV_CUDA(cudaEventRecord(h->ev[3], st.s));
-    if (!lcp_done) RV_TRY(lcp_build(st, h->dT, n, h->dSA, h->dISA, h->dLCP));
+    if (!lcp_done) RV_TRY(lcp_build(st, h->arena, h->dT, n, h->dSA, h->dISA, h->dLCP));
     RV_CUDA(cudaEventRecord(h->ev[4], st.s));
     RV_CUDA(cudaEventRecord(h->ev[5], st.s));
     RV_CUDA(cudaStreamSynchronize(st.s));

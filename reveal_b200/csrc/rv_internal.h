@@ -63,8 +63,9 @@ struct ProfRec {
 // alphabet of the last text built on a handle: lets the next build start without waiting for its histogram
 struct AlphaCache {
     bool valid = false;
-    unsigned short code[256];
-    int sigma = 0, sigma_eff = 0;
+    unsigned short code[256];  // exact dense codes 1..sigma of the symbols present (0: absent), byte order
+    unsigned short kcls[256];  // k-mer key class of every symbol: monotone in the byte value, rare symbols merged into a neighbour
+    int sigma = 0, sigma_eff = 0, kbase = 2;
 };
 
 struct Stream {
@@ -136,7 +137,7 @@ size_t sa_workspace_bytes(i64 n);
 int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, int *dISA, int *dLCP, bool *lcp_done, PhaseTimes *pt,
              bool fresh_alphabet = false);
 
-int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
+int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP);
 int isa_build(Stream &st, i64 n, const int *dSA, int *dISA, u32 *d_bad);
 int so_build(Stream &st, i64 n, const i64 *dNsep, int nsamples, unsigned short *dSO);
 int revcomp_suffix(Stream &st, unsigned char *dT, i64 start, i64 n);

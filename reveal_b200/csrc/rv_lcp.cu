@@ -1,56 +1,11 @@
-// rv_lcp.cu -- barrier-aware LCP array, sample-id array and reverse complement.
+// rv_lcp.cu -- inverse suffix array from a cached suffix array, sample-id array and reverse complement.
 //
-// lcp_build replaces compute_lcp (reveallib/interface.c:97-114): Kasai et al.
-// with the reference's barrier rule -- the extension loop stops when the two
-// characters differ OR the character is '$' or 'N' (interface.c:107) -- so
-//   LCP[r] = min( lcp(T[SA[r-1]..], T[SA[r]..]), distance from SA[r] to the next '$'/'N' ),  LCP[0] = 0.
-// The value is order-free, so text positions are cut into chunks that run
-// Kasai's carry (h-1 is a lower bound for the next position) independently.
+// (compute_lcp, reveallib/interface.c:97-114, lives with the suffix-array builder: rv_sa.cu, lcp_sparse_kernel / lcp_build.)
 // so_build replaces build_SO (interface.c:116-134); revcomp_suffix replaces
 // revcomp + comp_tab (interface.c:136-158) as used by construct (interface.c:168-172).
 #include "rv_internal.h"
 
 namespace rv {
-
-__global__ void __launch_bounds__(128) lcp_kasai_kernel(const unsigned char *__restrict__ T, i64 n, const int *__restrict__ SA,
-                                                       const int *__restrict__ ISA, int *__restrict__ LCP, int chunk) {
-    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    i64 i0 = c * chunk;
-    if (i0 >= n) return;
-    i64 i1 = i0 + chunk < n ? i0 + chunk : n;
-    i64 h = 0;
-    for (i64 i = i0; i < i1; i++) {
-        int r = ISA[i];
-        if (r == 0) {
-            LCP[0] = 0;
-            h = 0;
-            continue;
-        }
-        i64 j = SA[r - 1];
-        while (i + h < n && j + h < n) {
-            unsigned char a = T[i + h];
-            if (a != T[j + h] || a == '$' || a == 'N') break;
-            h++;
-        }
-        LCP[r] = (int)h;
-        if (h > 0) h--;
-    }
-}
-
-int lcp_build(Stream &st, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP) {
-    if (n <= 0) return RV_OK;
-    // chunk length: enough threads to fill the machine, long enough to amortise the restart of h
-    i64 chunk = n / (148 * 2048);
-    if (chunk < 32) chunk = 32;
-    if (chunk > 256) chunk = 256;
-    i64 threads = (n + chunk - 1) / chunk;
-    RV_TRY(prof_begin(st));
-    RV_LAUNCH(lcp_kasai_kernel, (unsigned)((threads + 127) / 128), 128, 0, st.s, dT, n, dSA, dISA, dLCP, (int)chunk);
-    RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
-    st.launches++;
-    RV_KCHECK();
-    return RV_OK;
-}
 
 // SAi[SA[i]] = i  (interface.c:235-238) -- only used when the suffix array comes from a cache file
 __global__ void __launch_bounds__(256) isa_scatter_kernel(const int *__restrict__ SA, i64 n, int *__restrict__ ISA, u32 *__restrict__ bad) {

@@ -71,34 +71,58 @@ inline size_t radix_scratch_bytes(i64 n) {
     return (size_t)(2 * RS_MAXPASS * RS_BINS + 8 + 32) * 4 + (size_t)RS_MAXPASS * tiles * RS_BINS * 4 + 512;
 }
 
-// Keys that are never materialised: key[i] = first k symbols of suffix i of the text as a base-`base` number
-// (rv_sa.cu stage 2), value[i] = i.  The histogram kernel and the first digit pass compute them on the fly, so
+// Keys that are never materialised: key[i] = the first k symbols of suffix i of the text as a base-`base` number over the
+// symbol CLASSES (rv_sa.cu stage 2), value[i] = i.  The histogram kernel and the first digit pass compute them on the fly, so
 // the 8-12 bytes per suffix of a key/value array are neither written nor read back.
+//
+// Classes: every frequent symbol (the ones that carry the entropy: ACGT) has a digit of its own, in byte order.  A rare symbol
+// ('$', N, a stray IUPAC letter) and "past the end of the text" END the key: a rare symbol takes the digit of the next frequent
+// symbol above it and the remaining digits are 0; with no frequent symbol above it takes the largest digit and the remaining
+// digits are the largest, too; past the end is digit 0 followed by zeros.  This keeps the key order-preserving
+// (suffix a < suffix b  =>  key a <= key b) with `base` = number of frequent symbols -- 2 bits per base for DNA whatever else
+// occurs in the text -- and ties mean nothing: equal keys only say "not ordered yet".
 struct TextKeySrc {
     const unsigned char *T;
     i64 n;
     u32 base;
     int k;
-    u64 top;  // base^(k-1)
-    unsigned short code[256];
+    u64 top;                  // base^(k-1)
+    u64 pw[64];               // base^j (j < k)
+    unsigned short code[256]; // bits 0-7 digit, bit 8 rare (ends the key), bit 9 fill the rest with the largest digit
 };
 static const int TK_PER = 16;  // consecutive positions whose keys one thread rolls
+static const u32 TK_RARE = 0x100u, TK_MAXFILL = 0x200u;
 
-template <typename KeyT>
-__device__ __forceinline__ KeyT text_key_first(const TextKeySrc &s, const unsigned short *s_code, i64 i0) {
-    KeyT key = 0;
-    for (int t = 0; t < s.k; t++) {
-        i64 p = i0 + t;
-        key = key * (KeyT)s.base + (KeyT)(p < s.n ? s_code[s.T[p]] : 0);
+template <typename KeyT> struct KeyRoller {
+    KeyT raw;     // all k digits, no truncation
+    u64 rm, xm;   // bit t: symbol t of the window is rare / rare with max fill
+    __device__ __forceinline__ u32 sym(const TextKeySrc &s, const unsigned short *s_code, i64 p) const { return p < s.n ? (u32)s_code[s.T[p]] : TK_RARE; }
+    __device__ __forceinline__ void first(const TextKeySrc &s, const unsigned short *s_code, i64 i0) {
+        raw = 0;
+        rm = xm = 0;
+        for (int t = 0; t < s.k; t++) {
+            u32 c = sym(s, s_code, i0 + t);
+            raw = raw * (KeyT)s.base + (KeyT)(c & 0xffu);
+            rm |= (u64)((c >> 8) & 1u) << t;
+            xm |= (u64)((c >> 9) & 1u) << t;
+        }
     }
-    return key;
-}
-template <typename KeyT>
-__device__ __forceinline__ KeyT text_key_next(const TextKeySrc &s, const unsigned short *s_code, i64 p, KeyT key) {
-    KeyT first = (KeyT)s_code[s.T[p]];                           // symbol leaving the window
-    KeyT next = (KeyT)(p + s.k < s.n ? s_code[s.T[p + s.k]] : 0);  // symbol entering it
-    return (key - first * (KeyT)s.top) * (KeyT)s.base + next;
-}
+    // window i -> i+1
+    __device__ __forceinline__ void next(const TextKeySrc &s, const unsigned short *s_code, i64 p) {
+        u32 out = sym(s, s_code, p), in = sym(s, s_code, p + s.k);
+        raw = (raw - (KeyT)(out & 0xffu) * (KeyT)s.top) * (KeyT)s.base + (KeyT)(in & 0xffu);
+        rm = (rm >> 1) | ((u64)((in >> 8) & 1u) << (s.k - 1));
+        xm = (xm >> 1) | ((u64)((in >> 9) & 1u) << (s.k - 1));
+    }
+    __device__ __forceinline__ KeyT key(const TextKeySrc &s) const {
+        if (rm == 0) return raw;
+        const int d = __ffsll((long long)rm) - 1;  // first rare symbol of the window: the key ends there
+        const KeyT P = (KeyT)s.pw[s.k - 1 - d];
+        KeyT kk = raw - raw % P;
+        if ((xm >> d) & 1ull) kk += P - 1;
+        return kk;
+    }
+};
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src, RadixPlan plan, u32 *__restrict__ ghist) {
@@ -109,10 +133,12 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src
     __syncthreads();
     const i64 stride = (i64)gridDim.x * RS_THREADS * TK_PER;
     for (i64 i0 = ((i64)blockIdx.x * RS_THREADS + threadIdx.x) * TK_PER; i0 < src.n; i0 += stride) {
-        KeyT key = text_key_first<KeyT>(src, s_code, i0);
+        KeyRoller<KeyT> kr;
+        kr.first(src, s_code, i0);
         for (int j = 0; j < TK_PER && i0 + j < src.n; j++) {
+            const KeyT key = kr.key(src);
             for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * RS_BINS + ((u32)(key >> plan.shift[p]) & plan.mask[p])], 1u);
-            key = text_key_next<KeyT>(src, s_code, i0 + j, key);
+            kr.next(src, s_code, i0 + j);
         }
     }
     __syncthreads();
@@ -198,12 +224,13 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
         __syncthreads();
         const i64 i0 = base + (i64)tid * RS_IPT;
         if (i0 < n) {
-            KeyT kk = text_key_first<KeyT>(src, s_code, i0);
+            KeyRoller<KeyT> kr;
+            kr.first(src, s_code, i0);
 #pragma unroll
             for (int j = 0; j < RS_IPT; j++) {
                 if (i0 + j < n) {
-                    s_keys[tid * RS_IPT + j] = kk;
-                    kk = text_key_next<KeyT>(src, s_code, i0 + j, kk);
+                    s_keys[tid * RS_IPT + j] = kr.key(src);
+                    kr.next(src, s_code, i0 + j);
                 }
             }
         }

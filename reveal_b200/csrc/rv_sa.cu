@@ -208,7 +208,8 @@ template <typename KeyT, int SB>
 __global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
 sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W,
                 const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
-                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start) {
+                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start,
+                u32 *__restrict__ needbits) {
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
     __shared__ int s_lcp[PR_WARPS][PR_MAXT];
     __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
@@ -322,10 +323,15 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         unsigned idle = __ballot_sync(FULL, !active);
         if (!active) {
             u32 idx = next + (u32)__popc(idle & lanemask_lt());
-            if ((int)(qn - idx) > 0) {
+            bool take = (int)(qn - idx) > 0;
+            if (take) {
                 u32 it = queue[idx & (PR_QCAP - 1)];
                 tx = (int)(it >> 4);
                 ty = tx - (int)(it & 15u);
+                const int t0 = tx - (int)sL[tx];
+                take = !((sdef[t0 >> 5] >> (t0 & 31)) & 1u);  // the group was given up (stage 4 orders it): its other pairs are moot
+            }
+            if (take) {
                 x = ssa[tx];
                 u32 y = ssa[ty];
                 p = x + (u32)skip;
@@ -384,10 +390,14 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
                     done = true;
                     match = lenmin;
                     x_less = p > q;
-                } else if (h >= (u32)SA_CMP_CAP) {  // too long: let the doubling rounds order this group
-                    int t0 = tx - (int)sL[tx];
-                    atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
-                    active = false;
+                } else if ((h & 511u) == 0u) {
+                    const int t0 = tx - (int)sL[tx];
+                    if (h >= (u32)SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                        atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
+                        active = false;
+                    } else if ((sdef[t0 >> 5] >> (t0 & 31)) & 1u) {
+                        active = false;  // another pair of the group already gave up
+                    }
                 }
             }
             if (done) {
@@ -414,13 +424,17 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         my_suf[k] = 0;
         if (t >= nt) continue;
         unsigned L = sL[t];
-        if (L == 0xFFu) continue;  // member of a group with more than SA_SMALL_G suffixes: stage 4
+        if (L == 0xFFu) {  // member of a group with more than SA_SMALL_G suffixes: stage 4
+            SA[s + t] = -1;  // "not placed": what the neighbours' LCP passes see until stage 4 fills the slot
+            continue;
+        }
         const int t0 = t - (int)L;
         if ((sdef[t0 >> 5] >> (t0 & 31)) & 1u) {
             if (L == 0) {
                 deferred[s + t] = 1;
                 *flag_large = 1u;
             }
+            SA[s + t] = -1;
             continue;
         }
         u32 r = (cnt[t >> 2] >> (8 * (t & 3))) & 0xffu;
@@ -445,7 +459,11 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     for (int f = (int)lane; f < nt; f += 32) {
         if (f == 0 || !((head[f >> 5] >> (f & 31)) & 1u)) continue;
         u32 a = fin[f], b = fin[f - 1];
-        if (a == 0xFFFFFFFFu || b == 0xFFFFFFFFu) continue;  // stage 4 will finish these (sa_lcp_need_kernel)
+        if (a == 0xFFFFFFFFu) continue;  // stage 4 places the slot and marks the suffix for the LCP pass that follows it
+        if (b == 0xFFFFFFFFu) {          // the left neighbour is not known yet: this suffix's LCP entry comes from that pass too
+            atomicOr(&needbits[a >> 5], 1u << (a & 31u));
+            continue;
+        }
         LCP[s + f] = direct_lcp<SB>(W, n32, a, b, bar0, bar1);
     }
 }
@@ -453,7 +471,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
 // LCP entry of the first slot of every warp chunk of sa_pairs_kernel
 __global__ void __launch_bounds__(256)
 sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
-                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
+                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP, u32 *__restrict__ needbits) {
     i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     int j = chunk_start[c];
@@ -462,31 +480,77 @@ sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, con
         LCP[0] = 0;
         return;
     }
-    // this pass is enqueued before the host knows whether stage 4 is needed: a slot of a group that was not placed
-    // yet may still hold anything, and is rewritten later
-    u32 p = (u32)SA[j], q = (u32)SA[j - 1];
-    if (p >= (u32)n || q >= (u32)n) return;
-    LCP[j] = direct_lcp<8>((const u32 *)T, (u32)n, p, q, bar0, bar1);
+    // this pass is enqueued before the host knows whether stage 4 is needed: slots it will fill hold -1 until then
+    const int p = SA[j], q = SA[j - 1];
+    if (p < 0) return;
+    if (q < 0) {
+        atomicOr(&needbits[(u32)p >> 5], 1u << ((u32)p & 31u));
+        return;
+    }
+    LCP[j] = direct_lcp<8>((const u32 *)T, (u32)n, (u32)p, (u32)q, bar0, bar1);
 }
 
-// Stage 4: `need` marks the slots whose LCP entry the comparison stage did not
-// produce (group heads, members of groups that went through the doubling rounds).
-template <typename KeyT>
-__global__ void __launch_bounds__(256)
-sa_need_kernel(const KeyT *__restrict__ keys, i64 n, const unsigned char *__restrict__ deferred, unsigned char *__restrict__ need) {
-    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    int L, R;
-    run_lengths(keys, n, j, SA_SMALL_G, L, R);
-    need[j] = (L == 0 || L + R + 1 > SA_SMALL_G || deferred[j - L]) ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256)
-sa_lcp_need_kernel(const unsigned char *__restrict__ need, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
-                   const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP) {
-    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || !need[j]) return;
-    LCP[j] = j == 0 ? 0 : direct_lcp<8>((const u32 *)T, (u32)n, (u32)SA[j], (u32)SA[j - 1], bar0, bar1);
+// ---- LCP entries of the suffixes stage 4 placed (and of their right neighbours in the suffix array) ----------------------------
+// needbits: one bit per TEXT position whose LCP entry is still missing.  Kasai's amortisation needs text order: consecutive marked
+// positions i, i+1 have lcp(i+1, Phi(i+1)) >= lcp(i, Phi(i)) - 1, so inside a long repeat every suffix costs one comparison step
+// instead of a comparison of the whole remaining repeat.  One thread walks LS_WORDS words of the bitmap; unmarked stretches
+// (entries the comparison stage already delivered) cost one load per 32 positions.  With every bit set this IS Kasai et al. in
+// chunks of 32*LS_WORDS positions on the packed text; it replaces compute_lcp (interface.c:97-114) for repeat-heavy inputs.
+static const int LS_WORDS = 2;
+template <int SB>
+__global__ void __launch_bounds__(128)
+lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict__ W, const u32 *__restrict__ bar0, const u32 *__restrict__ bar1,
+                  const int *__restrict__ SA, const int *__restrict__ ISA, int *__restrict__ LCP) {
+    typedef Sym<SB> S;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 w0 = t * LS_WORDS, nwords = (n + 31) / 32;
+    if (w0 >= nwords) return;
+    const u32 n32 = (u32)n;
+    u32 h = 0;
+    i64 prev = -2;
+    for (i64 w = w0; w < w0 + LS_WORDS && w < nwords; w++) {
+        for (u32 bits = needbits[w]; bits; bits &= bits - 1u) {
+            const i64 i = w * 32 + (__ffs((int)bits) - 1);
+            if (i >= n) break;
+            const int r = ISA[i];
+            if (r == 0) {
+                LCP[0] = 0;
+                prev = -2;
+                continue;
+            }
+            const u32 j = (u32)SA[r - 1];
+            h = (i == prev + 1 && h > 0u) ? h - 1u : 0u;
+            prev = i;
+            // extend the match from offset h, 4 words per suffix and step
+            const u32 p = (u32)i + h, q = j + h;
+            const u32 lenmin = n32 - (p > q ? p : q);
+            const u32 *pa = W + (p >> S::LOG_SPW), *pb = W + (q >> S::LOG_SPW);
+            const unsigned sha = (p & (S::SPW - 1u)) * SB, shb = (q & (S::SPW - 1u)) * SB;
+            u32 lo_a = *pa, lo_b = *pb, g = 0, match = lenmin;
+            while (g < lenmin) {
+                u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+                u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
+                u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
+                u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+                u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+                u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+                if (d0 | d1 | d2 | d3) {
+                    u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
+                    u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+                    u32 at = g + wsel * S::SPW + ((u32)(__ffs((int)dd) - 1) >> S::LOG_SB);
+                    match = at < lenmin ? at : lenmin;
+                    break;
+                }
+                g += S::STEP;
+                pa += 4;
+                pb += 4;
+                lo_a = a4;
+                lo_b = b4;
+            }
+            h += match;
+            LCP[r] = (int)first_barrier(bar0, bar1, (u32)i, h);  // the reference's '$'/'N' cut (interface.c:107) on the way out only
+        }
+    }
 }
 
 // ---- stage 4: prefix doubling ---------------------------------------------------------------
@@ -497,6 +561,23 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ 
     if (e >= A) return;
     i64 p = (i64)sa[e] + h;
     u32 k2 = p < n ? (u32)rank[p] + 1u : 0u;
+    keys[e] = ((u64)grp[e] << 32) | (u64)k2;
+}
+
+// Exact refinement round of stage 4: second key = the kx symbols at sa[e]+off as a base-(sigma+1) number over the EXACT codes
+// (0 = past the end).  The k-mer keys of stage 2 merge rare symbols into a neighbouring digit, so a group of equal keys shares
+// only the CLASS string of its first k symbols; before the doubling rounds may treat ranks as "order by the first h symbols"
+// the groups that reach stage 4 are refined by the true symbols of those positions.
+__global__ void __launch_bounds__(256) sa_exact_gather_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ grp, const unsigned char *__restrict__ T,
+                                                             CodeTable tab, i64 A, i64 n, i64 off, int kx, u32 xbase, u64 *__restrict__ keys) {
+    __shared__ unsigned short s_code[256];
+    s_code[threadIdx.x] = tab.code[threadIdx.x];
+    __syncthreads();
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A) return;
+    i64 p = (i64)sa[e] + off;
+    u32 k2 = 0;
+    for (int t = 0; t < kx; t++, p++) k2 = k2 * xbase + (p < n ? (u32)s_code[T[p]] : 0u);
     keys[e] = ((u64)grp[e] << 32) | (u64)k2;
 }
 
@@ -572,7 +653,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(AP_THREADS)
 sa_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, const u32 *__restrict__ pos, i64 A, int G,
                 const unsigned char *__restrict__ deferred, const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt,
-                int *__restrict__ SA, int *__restrict__ rank, u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2) {
+                int *__restrict__ SA, int *__restrict__ rank, u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2,
+                u32 *__restrict__ needbits) {
     __shared__ u32 s1[33], s2[33];
     __shared__ u32 s_im[AP_THREADS];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
@@ -618,6 +700,7 @@ sa_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, const
                 pos2[dst] = slot;
                 grp2[dst] = g;
                 dst++;
+                if (needbits) atomicOr(&needbits[s >> 5], 1u << (s & 31u));  // round 0: every suffix stage 4 orders needs its LCP entry
             }
         }
     }
@@ -639,7 +722,8 @@ size_t sa_workspace_bytes(i64 n) {
 struct SaBuffers {
     u64 *k0, *k1;
     u32 *v0, *v1, *posA, *posB, *grpA, *grpB, *tile_max, *tile_cnt, *small;
-    unsigned char *deferred, *need;
+    unsigned char *deferred;
+    u32 *needbits;     // one bit per text position: LCP entry still missing after the comparison stage (lcp_sparse_kernel)
     int *chunk_start;  // first slot of every warp chunk of sa_pairs_kernel
     u32 *packed;       // 4-bit packed text, n/8 + 16 words
     u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
@@ -648,8 +732,9 @@ struct SaBuffers {
 
 // stages 2-3 for one key width; on return *keys_out / *sa_out hold the sorted keys and suffixes
 template <typename KeyT>
-static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, u32 base, int k,
-                            int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, PhaseTimes *pt) {
+static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, int sigma, u32 base, int k,
+                            int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, bool *packed_out,
+                            PhaseTimes *pt) {
     KeyT *k0 = (KeyT *)B.k0, *k1 = (KeyT *)B.k1;
     // the (key, suffix) pairs are virtual: the histogram kernel and the first digit pass roll the k-mer keys
     // straight from the text (TextKeySrc), so no key array is written before the first scatter
@@ -660,7 +745,9 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     src.k = k;
     src.top = 1;
     for (int t = 1; t < k; t++) src.top *= (u64)base;
-    memcpy(src.code, tab.code, sizeof src.code);
+    src.pw[0] = 1;
+    for (int t = 1; t < 64; t++) src.pw[t] = t < k ? src.pw[t - 1] * (u64)base : 0;
+    memcpy(src.code, st.alpha.kcls, sizeof src.code);  // key digits = classes (rare symbols merged), not the exact codes
     bool in0;
     RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0, &src));
     if (pt) pt->sa_sorted_items += n;
@@ -668,70 +755,85 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     u32 *sa = in0 ? B.v0 : B.v1;
     // comparison stage
     RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    RV_CUDA(cudaMemsetAsync(B.needbits, 0, (size_t)(n / 32 + 2) * 4, st.s));
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
     // text for the comparisons: 4-bit packed codes when the alphabet allows (sigma <= 15), else the raw bytes
-    const bool packed = base <= 16 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
+    const bool packed = sigma <= 15 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
+    // Equal keys do not promise equal first k symbols (merged classes, "past the end" shares digit 0): the comparisons
+    // start at the suffix itself.
+    const int skip = 0;
     const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
     const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);  // one block past the end: zero padding of the packed text
     if (packed) {
         RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
         RV_TRY(prof_begin(st));
-        RV_LAUNCH((sa_pairs_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)B.packed, B.bar, B.bar1, k, dSA, dISA, dLCP,
-                  B.deferred, B.small + 257, B.chunk_start);
+        RV_LAUNCH((sa_pairs_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)B.packed, B.bar, B.bar1, skip, dSA, dISA, dLCP,
+                  B.deferred, B.small + 257, B.chunk_start, B.needbits);
     } else {
         RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
         RV_TRY(prof_begin(st));
-        RV_LAUNCH((sa_pairs_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)dT, B.bar, B.bar1, k, dSA, dISA, dLCP,
-                  B.deferred, B.small + 257, B.chunk_start);
+        RV_LAUNCH((sa_pairs_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)dT, B.bar, B.bar1, skip, dSA, dISA, dLCP,
+                  B.deferred, B.small + 257, B.chunk_start, B.needbits);
     }
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 2;
-    {   // the chunk-head LCP pass is enqueued before anyone knows whether stage 4 is needed: when it is, stage 4
-        // rewrites these few entries anyway (sa_lcp_need_kernel / Kasai)
+    {   // the chunk-head LCP pass is enqueued before anyone knows whether stage 4 is needed: slots that stage 4 still has to
+        // fill read -1 and the entry is left to lcp_sparse_kernel
         const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
-        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP);
+        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP,
+                  B.needbits);
         st.launches++;
     }
     RV_KCHECK();
     *keys_out = keys;
+    *packed_out = packed;
     *sa_out = sa;
     *sa_free = in0 ? B.v1 : B.v0;
     return RV_OK;
 }
 
-// doubling rounds; round 0 works on the initial keys (KeyT), later rounds on (rank : rank) u64 keys
+// Stage 4.  Round 0 works on the stage-2 keys (KeyT): it places nothing new but collects the entries of the groups the comparison
+// stage left alone into the active list.  Then exact refinement rounds over the first k symbols (sa_exact_gather_kernel), then
+// the doubling rounds on (rank : rank) u64 keys.
 template <typename KeyT>
-static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *keys0, u32 *sa, u32 *sa_alt, int *dSA, int *dISA, i64 *first_active,
-                    PhaseTimes *pt) {
+static int doubling(Stream &st, const SaBuffers &B, const unsigned char *dT, const CodeTable &tab, int sigma, i64 n, int k, const KeyT *keys0, u32 *sa,
+                    u32 *sa_alt, int *dSA, int *dISA, i64 *first_active, PhaseTimes *pt) {
     u32 *pos = nullptr, *grp = nullptr;  // current active list is (sa, pos, grp)
     u32 *pos_next = B.posA, *grp_next = B.grpA;
     u64 *keys = B.k0, *keys_alt = B.k1;  // free once round 0 has consumed keys0 (which may alias one of them)
     i64 A = n;
     const int nbits = bits_for((u64)n);  // ranks < n, second key <= n
-    i64 h = k;
+    const u32 xbase = (u32)sigma + 1;
+    int kx = 0, xbits = 0;               // symbols (and bits) of one exact second key
+    {
+        u64 v = 1;
+        while (v * xbase <= 4294967296ull && kx < 32) { v *= xbase; kx++; }
+        xbits = bits_for(v - 1);
+    }
+    i64 covered = 0;  // leading symbols of every active group known to be equal (exactly)
+    i64 h = 0;
     for (int round = 0;; round++) {
         const i64 tiles = (A + AP_TILE - 1) / AP_TILE;
         if (round == 0) {
             RV_LAUNCH((sa_reduce_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, pos, A, SA_SMALL_G, B.deferred, B.tile_max, B.tile_cnt);
             RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
             RV_LAUNCH((sa_apply_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, sa, pos, A, SA_SMALL_G, B.deferred, B.tile_max,
-                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next);
+                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next, B.needbits);
         } else {
             RV_LAUNCH((sa_reduce_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
                       B.tile_cnt);
             RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
             RV_LAUNCH((sa_apply_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
-                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next);
+                      B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next, (u32 *)nullptr);
         }
         st.launches += 3;
-        u32 nactive = 0;
-        RV_CUDA(cudaMemcpyAsync(&nactive, B.small + 256, 4, cudaMemcpyDeviceToHost, st.s));
+        RV_CUDA(cudaMemcpyAsync(st.pinned + 310, B.small + 256, 4, cudaMemcpyDeviceToHost, st.s));
         RV_CUDA(cudaStreamSynchronize(st.s));
+        const u32 nactive = st.pinned[310];
         if (pt) pt->sa_rounds = round + 1;
         if (round == 0) *first_active = nactive;
         if (nactive == 0) break;
-        if (h >= n) {
+        if (covered >= k && h >= n) {
             set_error("sa_build: internal error, %u suffixes still tied at h=%lld >= n", nactive, (long long)h);
             return RV_ERR_STATE;
         }
@@ -742,16 +844,25 @@ static int doubling(Stream &st, const SaBuffers &B, i64 n, int k, const KeyT *ke
         grp = grp_next;
         pos_next = (pos == B.posA) ? B.posB : B.posA;
         grp_next = (grp == B.grpA) ? B.grpB : B.grpA;
-        RV_LAUNCH(sa_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dISA, A, n, h, keys);
+        RadixPlan plan;
+        if (covered < k) {  // exact refinement of the symbols [covered, covered + kx)
+            RV_LAUNCH(sa_exact_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dT, tab, A, n, covered, kx, xbase, keys);
+            plan = make_plan(0, xbits, 32, 32 + nbits);
+            covered += kx;
+            h = covered;
+        } else {
+            RV_LAUNCH(sa_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dISA, A, n, h, keys);
+            plan = make_plan(0, nbits, 32, 32 + nbits);
+            h *= 2;
+        }
         st.launches++;
         bool r0;
-        RV_TRY(radix_sort_pairs<u64>(st, keys, keys_alt, sa, sa_alt, A, make_plan(0, nbits, 32, 32 + nbits), B.rscratch, &r0));
+        RV_TRY(radix_sort_pairs<u64>(st, keys, keys_alt, sa, sa_alt, A, plan, B.rscratch, &r0));
         if (pt) pt->sa_sorted_items += A;
         if (!r0) {
             { u64 *t = keys; keys = keys_alt; keys_alt = t; }
             { u32 *t = sa; sa = sa_alt; sa_alt = t; }
         }
-        h *= 2;
     }
     RV_KCHECK();
     return RV_OK;
@@ -781,12 +892,12 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.rscratch = ws.take<unsigned char>(radix_scratch_bytes(n));
     B.small = ws.take<u32>(512);  // [0..255] byte histogram, [256] active count, [257] "stage 4 needed"
     B.deferred = ws.take<unsigned char>(n);
-    B.need = ws.take<unsigned char>(n);
+    B.needbits = ws.take<u32>(n / 32 + 2);
     B.chunk_start = ws.take<int>(n / PR_CHUNK + 2 * PR_WARPS + 8);
     B.packed = ws.take<u32>(n / 8 + 300);  // sa_textprep_kernel writes whole 1024-symbol blocks, one block past the end
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
-    if (!B.deferred || !B.need || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    if (!B.deferred || !B.needbits || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;
@@ -806,26 +917,45 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     RV_CUDA(cudaMemcpyAsync(hist, B.small, 256 * 4, cudaMemcpyDeviceToHost, st.s));
     const bool speculative = st.alpha.valid && !fresh_alphabet;
     CodeTable tab;
-    int sigma = 0, sigma_eff = 0;
-    if (speculative) {
-        memcpy(tab.code, st.alpha.code, sizeof tab.code);
-        sigma = st.alpha.sigma;
-        sigma_eff = st.alpha.sigma_eff;
-    } else {
+    if (!speculative) {
         RV_CUDA(cudaStreamSynchronize(st.s));
-        memset(&tab, 0, sizeof tab);
-        for (int c = 0; c < 256; c++)
-            if (hist[c]) {
-                tab.code[c] = (unsigned short)(++sigma);
-                if ((u64)hist[c] * 32 >= (u64)n) sigma_eff++;  // symbols that carry the entropy (ACGT, not '$'/N/IUPAC)
+        AlphaCache &al = st.alpha;
+        memset(al.code, 0, sizeof al.code);
+        memset(al.kcls, 0, sizeof al.kcls);
+        al.sigma = al.sigma_eff = 0;
+        // Exact codes: every symbol present, in byte order (the packed text of the comparisons).
+        // Key classes: only the symbols that carry the entropy (>= 1/32 of the text: ACGT, not '$' / N / a stray IUPAC
+        // letter) get a digit of their own; every other symbol shares the digit of the nearest frequent symbol below
+        // it (digit 0 if there is none), and so does "past the end of the text".  The map is monotone in the byte
+        // value, so equal-or-smaller suffixes get equal-or-smaller keys and the comparison stage settles the ties --
+        // for DNA the key is the 2-bit packed k-mer: 16 symbols per 32-bit key whatever else occurs in the text.
+        bool freq[256];
+        for (int c = 0; c < 256; c++) {
+            freq[c] = hist[c] && (u64)hist[c] * 32 >= (u64)n;
+            if (hist[c]) al.code[c] = (unsigned short)(++al.sigma);
+            if (freq[c]) al.sigma_eff++;
+        }
+        al.kbase = al.sigma_eff < 2 ? 2 : al.sigma_eff;
+        // key digit of every byte value (TextKeySrc in rv_radix.cuh): frequent symbols 0..f-1 in byte order; any other byte ends the
+        // key with the digit of the next frequent symbol above it + zero fill, or the largest digit + max fill if there is none
+        int above = -1;  // digit of the nearest frequent symbol above c
+        {
+            int cls = al.sigma_eff;
+            for (int c = 255; c >= 0; c--) {
+                if (freq[c]) {
+                    above = --cls;
+                    al.kcls[c] = (unsigned short)cls;
+                } else {
+                    al.kcls[c] = above >= 0 ? (unsigned short)(above | 0x100) : (unsigned short)((al.kbase - 1) | 0x300);
+                }
             }
-        st.alpha.valid = true;
-        memcpy(st.alpha.code, tab.code, sizeof tab.code);
-        st.alpha.sigma = sigma;
-        st.alpha.sigma_eff = sigma_eff;
+        }
+        if (al.sigma_eff < 2) al.sigma_eff = 2;
+        al.valid = true;
     }
-    if (sigma_eff < 2) sigma_eff = 2;
-    const u32 base = (u32)sigma + 1;  // digits 0..sigma
+    memcpy(tab.code, st.alpha.code, sizeof tab.code);
+    const int sigma = st.alpha.sigma, sigma_eff = st.alpha.sigma_eff;
+    const u32 base = (u32)st.alpha.kbase;  // digits 0..base-1
     // shortest k with sigma_eff^k >= 4n: random k-mers are then mostly unique
     int k_need = 1;
     {
@@ -838,29 +968,43 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         while (v * base <= lim && kk < 64) { v *= base; kk++; }
         return kk;
     };
+    auto bits_of_k = [&](int kk) {  // bits of the largest k-symbol key
+        u64 m = 1;
+        for (int t = 0; t < kk; t++) m *= base;  // base^64 may wrap to 0 for base 2: 64 bits
+        return m == 0 ? 64 : bits_for(m - 1);
+    };
+    auto passes_of_k = [&](int kk) { return (bits_of_k(kk) + 7) / 8; };
     const int k32 = capacity(32), k64 = capacity(64);
-    // a 32-bit key is taken when it is at most 1 symbol short of k_need (4x fewer distinct k-mers): the
-    // comparison stage absorbs the slightly larger groups and the sort moves 8 instead of 12 bytes per pair
+    // 32-bit keys whenever k_need - 1 symbols fit (a key one symbol short of k_need has 'base' times fewer distinct
+    // values: the comparison stage absorbs the slightly larger groups).  Within the 32-bit range k is chosen by digit
+    // passes: one symbol less if that saves a whole 8-bit pass, else as many symbols as the passes hold anyway.
     bool use32 = k32 >= 1 && k32 + 1 >= k_need;
     if (const char *force = getenv("RV_SA_KEY_BITS")) {  // test hook: exercise both key widths on small inputs
         if (force[0] == '6') use32 = false;
         if (force[0] == '3') use32 = true;
     }
-    int k = use32 ? k32 : (k_need < k64 ? k_need : k64);
+    int k;
+    if (use32) {
+        int kn = k_need < k32 ? k_need : k32;
+        int target = passes_of_k(kn);
+        if (kn > 1 && passes_of_k(kn - 1) < target) target = passes_of_k(kn - 1);
+        k = kn > 1 ? kn - 1 : 1;
+        while (k + 1 <= k32 && passes_of_k(k + 1) <= target) k++;
+    } else {
+        k = k_need < k64 ? k_need : k64;
+    }
     if (k < 1) k = 1;
-    u64 maxkey = 1;
-    for (int t = 0; t < k; t++) maxkey *= base;  // base^k fits by construction (k64 may give exactly 2^64 -> wraps to 0)
-    const int key_bits = use32 ? bits_for(maxkey - 1) : (maxkey == 0 ? 64 : bits_for(maxkey - 1));
+    const int key_bits = bits_of_k(k);
 
     u32 *sa = nullptr, *sa_free = nullptr;
     i64 first_active = 0;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    bool packed = false;
     u32 *keys32 = nullptr;
     u64 *keys64 = nullptr;
     if (use32) {
-        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys32, &sa, &sa_free, pt));
+        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys32, &sa, &sa_free, &packed, pt));
     } else {
-        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, base, k, key_bits, dSA, dISA, dLCP, &keys64, &sa, &sa_free, pt));
+        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys64, &sa, &sa_free, &packed, pt));
     }
     // ---- the one synchronisation point of a build: is stage 4 needed, and (speculative start) was the alphabet right ----
     RV_CUDA(cudaMemcpyAsync(hist + 256, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));
@@ -874,30 +1018,55 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
             return sa_build(st, ws, dT, n, dSA, dISA, dLCP, lcp_done, pt, true);
         }
     }
-    bool large = hist[256] != 0;
+    const bool large = hist[256] != 0;
     if (large) {
         if (use32) {
-            RV_LAUNCH((sa_need_kernel<u32>), blocks, 256, 0, st.s, keys32, n, B.deferred, B.need);
-            st.launches++;
             // round 0 reads the u32 keys that live in the first half of k0 or k1; later rounds reuse both
             // buffers as u64 keys, so move the u32 keys out of the way (posB is free until round 2)
             RV_CUDA(cudaMemcpyAsync(B.posB, keys32, (size_t)n * 4, cudaMemcpyDeviceToDevice, st.s));
-            RV_TRY(doubling<u32>(st, B, n, k, B.posB, sa, sa_free, dSA, dISA, &first_active, pt));
+            RV_TRY(doubling<u32>(st, B, dT, tab, sigma, n, k, B.posB, sa, sa_free, dSA, dISA, &first_active, pt));
         } else {
-            RV_LAUNCH((sa_need_kernel<u64>), blocks, 256, 0, st.s, keys64, n, B.deferred, B.need);
-            st.launches++;
-            RV_TRY(doubling<u64>(st, B, n, k, keys64, sa, sa_free, dSA, dISA, &first_active, pt));
+            RV_TRY(doubling<u64>(st, B, dT, tab, sigma, n, k, keys64, sa, sa_free, dSA, dISA, &first_active, pt));
         }
-    }
-    if (large && first_active <= n / 16) {
-        // few suffixes needed the doubling rounds: finish their LCP entries (and every group head's) by direct
-        // comparison; with many (long repeats) Kasai's amortised walk in rv_lcp.cu is the better tool
-        RV_LAUNCH(sa_lcp_need_kernel, blocks, 256, 0, st.s, B.need, n, dT, B.bar, B.bar1, dSA, dLCP);
+        // LCP entries of everything stage 4 placed, and of the slots right after such a suffix: Kasai's walk over the marked
+        // text positions (a handful for a stray long match, all of them for a text that is one big repeat)
+        const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
+        RV_TRY(prof_begin(st));
+        if (packed) {
+            RV_LAUNCH((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, B.bar, B.bar1, dSA, dISA, dLCP);
+        } else {
+            RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)dT, B.bar, B.bar1, dSA, dISA, dLCP);
+        }
+        RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)first_active * 13 + n / 8));
         st.launches++;
         RV_KCHECK();
-        large = false;
     }
-    *lcp_done = !large;
+    *lcp_done = true;
+    return RV_OK;
+}
+
+// compute_lcp (interface.c:97-114) for a suffix array that did not come from sa_build (cache files): every position marked,
+// byte text.  The two-level barrier bitmap is built on the way.
+int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP) {
+    if (n <= 0) return RV_OK;
+    const size_t ws_mark = ws.off;
+    u32 *bar = ws.take<u32>(n / 32 + 98), *bar1 = ws.take<u32>(n / 1024 + 8), *needbits = ws.take<u32>(n / 32 + 2);
+    if (!bar || !bar1 || !needbits) {
+        set_error("lcp_build: workspace too small");
+        return RV_ERR_NOMEM;
+    }
+    CodeTable tab;
+    memset(&tab, 0, sizeof tab);
+    const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);
+    RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, bar, bar1, (u32 *)nullptr);
+    RV_CUDA(cudaMemsetAsync(needbits, 0xff, (size_t)(n / 32 + 2) * 4, st.s));
+    const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
+    RV_TRY(prof_begin(st));
+    RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bar, bar1, dSA, dISA, dLCP);
+    RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
+    st.launches += 2;
+    RV_KCHECK();
+    ws.off = ws_mark;  // stream-ordered: later users of the workspace are enqueued behind these kernels
     return RV_OK;
 }
 

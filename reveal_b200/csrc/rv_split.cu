@@ -37,7 +37,7 @@ static const int INF_LCP = 0x7fffffff;
 // ---- label scatter ---------------------------------------------------------------------------
 // intervals k = 0..m-1: text positions [ibeg[k], ibeg[k]+len) get label lab[k]; pre[k] = exclusive prefix of lengths
 __global__ void __launch_bounds__(256) label_kernel(const i64 *__restrict__ ibeg, const i64 *__restrict__ pre, const unsigned char *__restrict__ lab,
-                                                   int m, i64 total, const int *__restrict__ SAi, unsigned char *__restrict__ D) {
+                                                   int m, i64 total, const int *__restrict__ SAi, unsigned char *__restrict__ D, i64 n) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
     int lo = 0, hi = m - 1;  // last k with pre[k] <= g
@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(256) label_kernel(const i64 *__restrict__ ibeg
         if (pre[mid] <= g) lo = mid; else hi = mid - 1;
     }
     i64 j = ibeg[lo] + (g - pre[lo]);
-    D[SAi[j]] = lab[lo];
+    // a position that is not a suffix of this parent carries some other sub-index's rank: never write outside D
+    // (the class counts checked by the host afterwards then report the bad interval)
+    const i64 r = SAi[j];
+    if (r >= 0 && r < n) D[r] = lab[lo];
 }
 
 __global__ void __launch_bounds__(256) lower_kernel(const i64 *__restrict__ ibeg, const i64 *__restrict__ pre, int m, i64 total, unsigned char *__restrict__ T) {
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(32) split_tilescan_kernel(SplitState *__restri
 __global__ void __launch_bounds__(SP_THREADS)
 split_apply_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, const unsigned char *__restrict__ D, i64 n,
                    const SplitState *__restrict__ tiles, int *__restrict__ SAi, int *__restrict__ sa0, int *__restrict__ lcp0,
-                   int *__restrict__ sa1, int *__restrict__ lcp1, int *__restrict__ sa2, int *__restrict__ lcp2) {
+                   int *__restrict__ sa1, int *__restrict__ lcp1, int *__restrict__ sa2, int *__restrict__ lcp2, u32 cn0, u32 cn1, u32 cn2) {
     __shared__ SplitState s_warp[32];
     i64 base = (i64)blockIdx.x * SP_TILE + (i64)threadIdx.x * SP_IPT;
     SplitState st = split_identity();
@@ -193,7 +196,7 @@ split_apply_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, cons
         int out_m;
         u32 rank = cls >= 0 ? run.cnt[cls] : 0u;
         split_step(run, folded(LCP, D, i), cls, out_m);
-        if (cls >= 0) {
+        if (cls >= 0 && rank < (cls == 0 ? cn0 : (cls == 1 ? cn1 : cn2))) {  // more entries than the intervals cover: reported by the count check
             int *csa = cls == 0 ? sa0 : (cls == 1 ? sa1 : sa2);
             int *clcp = cls == 0 ? lcp0 : (cls == 1 ? lcp1 : lcp2);
             int s = SA[i];
@@ -820,6 +823,22 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
     Stream &st = *v.st;
     const i64 n = parent->n;
     if (n <= 0) return RV_OK;
+    // scratch blocks go back to the pool and unfinished children are released on EVERY way out of this function
+    struct Lease {
+        DevPool *pool;
+        std::vector<void *> blocks;
+        rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+        int take(size_t bytes, void **out) {
+            int r = pool->take(bytes, out);
+            if (r == RV_OK) blocks.push_back(*out);
+            return r;
+        }
+        ~Lease() {
+            for (void *p : blocks) pool->give(p);  // stream-ordered reuse: later users are enqueued behind the kernels above
+            for (int q = 0; q < 3; q++) rv_sub_free(kids[q]);
+        }
+    } lease;
+    lease.pool = pool;
 
     // ---- flatten the intervals on the host (host logic: counts like reveal.c:1017-1117) ----
     std::vector<i64> ibeg, pre;
@@ -858,7 +877,7 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
     size_t words = (size_t)2 * m1 + 2 * m2 + bbeg.size() + 8;
     size_t bytes = (words * 8 + (size_t)m1 + 64 + 15) / 16 * 16;  // d_counts lives in the (aligned) last 32 bytes
     void *dtab = nullptr;
-    RV_TRY(pool->take(bytes, &dtab));
+    RV_TRY(lease.take(bytes, &dtab));
     std::vector<unsigned char> host(bytes, 0);
     i64 *hw = (i64 *)host.data();
     i64 *h_ibeg = hw, *h_pre = hw + m1, *h_mbeg = hw + 2 * m1, *h_mpre = hw + 2 * m1 + m2, *h_bbeg = hw + 2 * m1 + 2 * m2;
@@ -874,51 +893,50 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
 
     // ---- D labels ----
     void *dD = nullptr;
-    RV_TRY(pool->take((size_t)n, &dD));
+    RV_TRY(lease.take((size_t)n, &dD));
     unsigned char *D = (unsigned char *)dD;
     RV_CUDA(cudaMemsetAsync(D, 0, (size_t)n, st.s));
     if (total1 > 0) {
-        RV_LAUNCH(label_kernel, (unsigned)((total1 + 255) / 256), 256, 0, st.s, d_ibeg, d_pre, d_lab, m1, total1, v.ISA, D);
+        RV_LAUNCH(label_kernel, (unsigned)((total1 + 255) / 256), 256, 0, st.s, d_ibeg, d_pre, d_lab, m1, total1, v.ISA, D, n);
         st.launches++;
     }
     if (mtotal > 0) {  // matched bases override (reveal.c:1112-1116)
         void *d3 = nullptr;
-        RV_TRY(pool->take((size_t)m2 + 64, &d3));
+        RV_TRY(lease.take((size_t)m2 + 64, &d3));
         RV_CUDA(cudaMemsetAsync(d3, 3, (size_t)m2, st.s));
-        RV_LAUNCH(label_kernel, (unsigned)((mtotal + 255) / 256), 256, 0, st.s, d_mbeg, d_mpre, (const unsigned char *)d3, m2, mtotal, v.ISA, D);
+        RV_LAUNCH(label_kernel, (unsigned)((mtotal + 255) / 256), 256, 0, st.s, d_mbeg, d_mpre, (const unsigned char *)d3, m2, mtotal, v.ISA, D, n);
         st.launches++;
-        pool->give(d3);  // stream-ordered reuse: later users are enqueued behind this kernel
     }
 
     // ---- children ----
-    rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+    rv_sub **kids = lease.kids;
     for (int c = 0; c < 3; c++)
         if (cls_n[c] > 0) {
             rv_sub *k = new rv_sub();
             k->main = parent->main;
             k->n = cls_n[c];
             k->owns = true;
+            kids[c] = k;  // from here on the lease frees it (rv_sub_free gives its arrays back to the pool)
             void *p1 = nullptr, *p2 = nullptr;
-            int r1 = pool->take((size_t)(cls_n[c] + 2) * 4, &p1);
-            int r2 = r1 == RV_OK ? pool->take((size_t)(cls_n[c] + 2) * 4, &p2) : r1;
-            if (r1 != RV_OK || r2 != RV_OK) { delete k; return RV_ERR_NOMEM; }
+            RV_TRY(pool->take((size_t)(cls_n[c] + 2) * 4, &p1));
             k->SA = (int *)p1;
+            RV_TRY(pool->take((size_t)(cls_n[c] + 2) * 4, &p2));
             k->LCP = (int *)p2;
-            kids[c] = k;
         }
     const i64 ntiles = (n + SP_TILE - 1) / SP_TILE;
     void *dtiles = nullptr;
-    RV_TRY(pool->take((size_t)ntiles * sizeof(SplitState) + 64, &dtiles));
+    RV_TRY(lease.take((size_t)ntiles * sizeof(SplitState) + 64, &dtiles));
     SplitState *tiles = (SplitState *)dtiles;
     u32 *d_counts = (u32 *)((unsigned char *)dtab + bytes - 32);
     RV_LAUNCH(split_reduce_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, parent->LCP, D, n, tiles);
     RV_LAUNCH(split_tilescan_kernel, 1, 32, 0, st.s, tiles, ntiles, d_counts);
     RV_LAUNCH(split_apply_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, parent->SA, parent->LCP, D, n, tiles, v.ISA,
               kids[0] ? kids[0]->SA : nullptr, kids[0] ? kids[0]->LCP : nullptr, kids[1] ? kids[1]->SA : nullptr,
-              kids[1] ? kids[1]->LCP : nullptr, kids[2] ? kids[2]->SA : nullptr, kids[2] ? kids[2]->LCP : nullptr);
+              kids[1] ? kids[1]->LCP : nullptr, kids[2] ? kids[2]->SA : nullptr, kids[2] ? kids[2]->LCP : nullptr, (u32)cls_n[0], (u32)cls_n[1],
+              (u32)cls_n[2]);
     st.launches += 3;
     // the labelled positions must be exactly the parent's suffixes of each class: check the device counts
-    u32 hc[3] = {0, 0, 0};
+    u32 *hc = st.pinned + 300;  // pinned: the copy is really asynchronous, the kernels below are enqueued behind it at once
     RV_CUDA(cudaMemcpyAsync(hc, d_counts, 12, cudaMemcpyDeviceToHost, st.s));
 
     // ---- mark the matched bases in T (reveal.c:1230-1234) ----
@@ -935,7 +953,7 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
             RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, (int)bbeg.size());
             st.launches++;
         } else {
-            RV_TRY(pool->take((size_t)(BB_CAP + 16) * 4, &dcand));
+            RV_TRY(lease.take((size_t)(BB_CAP + 16) * 4, &dcand));
             int *cand = (int *)dcand, *cand_cnt = cand + BB_CAP;
             RV_CUDA(cudaMemsetAsync(cand_cnt, 0, 4, st.s));
             i64 blocks = (kids[0]->n + 255) / 256;
@@ -949,17 +967,15 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
     }
     RV_CUDA(cudaStreamSynchronize(st.s));
     RV_KCHECK();
-    pool->give(dtab);
-    pool->give(dD);
-    pool->give(dtiles);
-    pool->give(dcand);
     for (int c = 0; c < 3; c++)
         if ((i64)hc[c] != cls_n[c]) {
             set_error("rv_sub_split: class %d has %u suffixes in the parent but the intervals cover %lld positions", c, hc[c], (long long)cls_n[c]);
-            for (int q = 0; q < 3; q++) rv_sub_free(kids[q]);
             return RV_ERR_ARG;
         }
-    for (int c = 0; c < 3; c++) children[c] = kids[c];
+    for (int c = 0; c < 3; c++) {
+        children[c] = kids[c];
+        kids[c] = nullptr;  // handed over
+    }
     return RV_OK;
 }
 

@@ -228,7 +228,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, 
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, (u64 *)nullptr, tiles, totals);
     st.launches += 2;
-    u64 h[2];
+    u64 *h = (u64 *)(st.pinned + 304);  // pinned: the read-back is asynchronous and the speculative write pass is enqueued before the host waits
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
     if (d_spec && cap_spec > 0) RV_TRY(sweep_pair_write(st, p, scratch, d_spec, cap_spec));
     RV_CUDA(cudaStreamSynchronize(st.s));
@@ -261,7 +261,7 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
     st.launches += 2;
-    u64 h[2];
+    u64 *h = (u64 *)(st.pinned + 304);
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
     if (d_hdr_spec && hdr_cap_spec > 0 && mem_cap_spec > 0)
         RV_TRY(sweep_multi_write(st, p, scratch, d_hdr_spec, hdr_cap_spec, d_mem_spec, mem_cap_spec));
@@ -314,7 +314,7 @@ int sweep_mems_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i
     RV_LAUNCH(mems_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits);
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
     st.launches += 2;
-    u64 h[2];
+    u64 *h = (u64 *)(st.pinned + 304);
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
     RV_CUDA(cudaStreamSynchronize(st.s));
     *nrec = (i64)h[0];

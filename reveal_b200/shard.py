@@ -249,8 +249,10 @@ def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
     units: list of (T uint8 array, nsep int64 array, nsamples) -- e.g. the sub-intervals of a recursion frontier
     rebuilt as independent indexes, the jobs of `--order=sequential --chunksize`, or a forward / reverse-complement
     pair.  Every rank builds the units `partition` assigns to it on its own GPU; the MUM records are
-    gathered to rank 0 (the only collective).  Returns on rank 0 a list with one int64 array per unit -- pair rows
-    (l, a, b) for two samples, multi-MUM header rows (l, n, first) otherwise -- and None on the other ranks.
+    gathered to rank 0 (two tagged variable-length gathers: record rows, member rows).  Returns on rank 0 a list with
+    one entry per unit -- pair rows (l, a, b) for two samples; for more samples the tuple (hdr, members) exactly as
+    rv_mums_multi_fetch delivers it: header rows (l, n, first) and the (sample, position) member rows `first` indexes
+    -- and None on the other ranks.
     `lib` is the C-ABI library object (default: the CUDA library; tests inject the emulated one)."""
     import ctypes
 
@@ -263,7 +265,7 @@ def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
     mine = partition([len(u[0]) for u in units], world)[rank]
     h = ctypes.c_void_p()
     _native.check(L, L.rv_index_create(ctypes.byref(h), None))
-    blocks = []
+    blocks, mblocks = [], []
     try:
         for uid in mine:
             T, nsep, ns = units[uid]
@@ -281,20 +283,32 @@ def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
                 rows = np.empty((nr.value, 3), dtype=np.int64)
                 mem = np.empty((nm.value, 2), dtype=np.int64)
                 _native.check(L, L.rv_mums_multi_fetch(h, rows.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+                # the member rows travel too (tagged like the records): `first` of a header row indexes the unit's own
+                # member rows, whose order a tagged gather keeps
+                mblocks.append(np.concatenate([np.full((len(mem), 1), uid, dtype=np.int64), mem], axis=1))
             # tag every row with its unit so that one gather carries all units of the rank
             tagged = np.concatenate([np.full((len(rows), 1), uid, dtype=np.int64), rows], axis=1)
             blocks.append(tagged)
     finally:
         L.rv_index_free(h)
-    local = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, 4), dtype=np.int64)
-    t = torch.from_numpy(local)
-    if device is not None:
-        t = t.to(device)
-    if world == 1:
-        parts = [t]
-    else:
+    any_multi = any(u[2] != 2 for u in units)  # known to every rank: the second gather is collective
+
+    def collect(parts_local, cols):
+        local = np.concatenate(parts_local, axis=0) if parts_local else np.zeros((0, cols), dtype=np.int64)
+        t = torch.from_numpy(local)
+        if device is not None:
+            t = t.to(device)
+        if world == 1:
+            return t.cpu().numpy()
         parts = gather_rows(t, dst=0, group=group)
-        if rank != 0:
-            return None
-    allrows = torch.cat(parts, dim=0).cpu().numpy()
-    return [allrows[allrows[:, 0] == uid][:, 1:] for uid in range(len(units))]
+        return torch.cat(parts, dim=0).cpu().numpy() if rank == 0 else None
+
+    allrows = collect(blocks, 4)
+    allmem = collect(mblocks, 3) if any_multi else None
+    if rank != 0:
+        return None
+    out = []
+    for uid, u in enumerate(units):
+        rows = allrows[allrows[:, 0] == uid][:, 1:]
+        out.append(rows if u[2] == 2 else (rows, allmem[allmem[:, 0] == uid][:, 1:]))
+    return out

@@ -1,5 +1,7 @@
 import glob
 import os
+
+os.environ.setdefault("REVEAL_B200_TEST_HOOKS", "1")  # reveallib._load (library injection) only works with this set before the import
 import subprocess
 import sys
 

@@ -198,10 +198,14 @@ def test_cuda_anchor_units_single_rank(cuda_lib):
         T, nsep, _ = P.assemble(random_related(rng, ns, length, 4))
         units.append((T, np.asarray(nsep, dtype=np.int64), ns))
     got = shard.anchor_units(units, minl=10, lib=cuda_lib)
-    for (T, nsep, ns), rows in zip(units, got):
+    for (T, nsep, ns), res in zip(units, got):
         o = P.Index(T, nsep, ns)
-        want = o.getmums(10, rem=True) if ns == 2 else o.getmultimums(10, 2)[0]
-        assert_same(rows, want, "unit rows")
+        if ns == 2:
+            assert_same(res, o.getmums(10, rem=True), "unit rows")
+        else:
+            oh, om = o.getmultimums(10, 2)
+            assert_same(res[0], oh, "unit hdr rows")
+            assert_same(res[1], om, "unit member rows")
 
 
 def test_cuda_full_size_c4_properties(cuda_lib):
@@ -231,3 +235,60 @@ def test_cuda_getmultimems_matches_oracle(cuda_lib):
         got = idx.getmultimems(minl, minn)
         assert got == P.multi_to_tuples(*o.getmultimems(minl, minn))
         assert len(got) > 0
+
+
+# ---- repeat-bearing inputs at Mbp scale (the doubling rounds and the LCP fallback run here) -----------------------------------
+@pytest.mark.parametrize("tag,expect", [("2", 6427), ("3", 17596), ("123", 24596)])
+def test_cuda_real_data_matches_reference(cuda_lib, tag, expect):
+    """The reference's own repeat-bearing fixtures (2a/2b, 3a/3b, 123a/123b; n up to 10 754 553): SA / SAi / LCP digests and the
+    getmums(20) list of the UNMODIFIED reference (tests/golden/make_real_golden.py), known-answer counts of BASELINE.md section 2."""
+    from util import check_against_real
+    info = {}
+
+    def build(T, nsep):
+        with NativeIndex(cuda_lib, T, nsep, 2) as idx:
+            info.update(idx.times())
+            return idx.arr("SA"), idx.arr("SAi"), idx.arr("LCP"), idx.mums(20)
+
+    assert check_against_real(build, tag) == expect
+    print("real %s: %s" % (tag, info))
+
+
+def test_cuda_repeat_genomes_full_size(cuda_lib):
+    """2 x 5 Mbp on a repeat-bearing ancestor (families, tandem arrays, segmental duplications, N runs) vs the oracle."""
+    T, nsep, ns = synth.repeat_workload(2, 5_000_000, seed=1)
+    o = P.Index(T, nsep, ns)
+    with NativeIndex(cuda_lib, T, nsep, ns) as idx:
+        assert idx.times()["sa_rounds"] > 0, "this input is meant to need the doubling rounds"
+        assert_same(idx.arr("SA"), o.SA, "SA")
+        assert_same(idx.arr("SAi"), o.SAi, "SAi")
+        assert_same(idx.arr("LCP"), o.LCP, "LCP")
+        assert_same(idx.mums(20, 1), o.getmums(20, rem=True), "getmums_rem")
+        hdr, mem = idx.multimums(20, 2)
+        oh, om = o.getmultimums(20, 2)
+        assert_same(hdr, oh, "getmultimums hdr")
+        assert_same(mem, om, "getmultimums members")
+
+
+def test_cuda_repeat_genomes_three_samples(cuda_lib):
+    T, nsep, ns = synth.repeat_workload(3, 1_500_000, seed=2)
+    check_against_oracle(cuda_lib, T, nsep, ns, minl=20)
+
+
+def test_cuda_graph_like_text(cuda_lib):
+    """One '$' per node: 2 x 2.5e5 contigs of ~20 bp (the text shape of graph input), n = 1.05e7."""
+    T, nsep, ns = synth.graph_like_workload(250_000, 20, seed=3)
+    check_against_oracle(cuda_lib, T, nsep, ns, minl=12)
+
+
+def test_cuda_highly_repetitive(cuda_lib):
+    """Kasai-fallback territory: most suffixes go through the doubling rounds (long tandem arrays, many identical copies)."""
+    rng = np.random.default_rng(17)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    unit = al[rng.integers(0, 4, size=3000)].tobytes()
+    s0 = unit * 120 + al[rng.integers(0, 4, size=50000)].tobytes() + (b"ACGTTGCA" * 20000)
+    s1 = bytearray(s0)
+    for p in rng.integers(0, len(s1), size=300):
+        s1[p] = al[rng.integers(0, 4)]
+    T, nsep, _ = P.assemble([[s0], [bytes(s1)]])
+    check_against_oracle(cuda_lib, T, nsep, 2, minl=20)

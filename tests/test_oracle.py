@@ -80,3 +80,16 @@ def test_oracle_vs_reference_multi():
     mm = ridx.getmultimums(minlength=20, minn=2)
     assert len(mm) == 558
     assert P.multi_to_tuples(*o.getmultimums(20, 2)) == [tuple(x) for x in mm]
+
+
+@pytest.mark.parametrize("tag,expect", [("1", 553), ("2", 6427)])
+def test_oracle_matches_reference_on_real_data(tag, expect):
+    """The reference's real-data fixtures (repeat-bearing Aspergillus niger contigs) from the committed
+    compact copy: the restatement reproduces the unmodified reference's SA / SAi / LCP digests and its getmums(20) list."""
+    from util import check_against_real
+
+    def build(T, nsep):
+        o = P.Index(T, nsep, 2)
+        return o.SA, o.SAi, o.LCP, o.getmums(20)
+
+    assert check_against_real(build, tag) == expect

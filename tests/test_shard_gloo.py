@@ -66,16 +66,20 @@ def _anchor_worker(rank, world, port, q, lib_path):
     L = _native.bind(lib_path)  # the emulated kernels stand in for the GPUs of the box
     rng = np.random.default_rng(42)  # same units on every rank
     units = []
-    for length in (1800, 600, 1200, 900, 300):
-        T, nsep, _ = P.assemble(random_related(rng, 2, length, 4))
-        units.append((T, np.asarray(nsep, dtype=np.int64), 2))
+    for length, ns in ((1800, 2), (600, 3), (1200, 2), (900, 4), (300, 2)):  # pair units and multi-sample units mixed
+        T, nsep, _ = P.assemble(random_related(rng, ns, length, 4))
+        units.append((T, np.asarray(nsep, dtype=np.int64), ns))
     got = shard.anchor_units(units, minl=8, lib=L)
     if rank == 0:
         ok = True
-        for (T, nsep, ns), rows in zip(units, got):
+        for (T, nsep, ns), res in zip(units, got):
             o = P.Index(T, nsep, ns)
-            ok = ok and np.array_equal(rows, o.getmums(8, rem=True))
-        q.put(("rank0", ok, [len(r) for r in got]))
+            if ns == 2:
+                ok = ok and np.array_equal(res, o.getmums(8, rem=True))
+            else:  # header rows AND the member rows their `first` column indexes (positions of every multi-MUM)
+                oh, om = o.getmultimums(8, 2)
+                ok = ok and np.array_equal(res[0], oh) and np.array_equal(res[1], om) and len(om) > 0
+        q.put(("rank0", ok, [len(r) if not isinstance(r, tuple) else len(r[0]) for r in got]))
     else:
         q.put(("rank%d" % rank, got is None, None))
     dist.barrier()

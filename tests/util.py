@@ -1,6 +1,7 @@
 """Shared helpers of the parity tests: run one build + sweeps through the C-ABI
 (any library exporting it) and through the oracle, and compare bit-exactly."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -198,3 +199,34 @@ def check_pack_block(L):
         _native.check(L, L.rv_peer_free(p))
     assert L.rv_peer_alloc(0, ctypes.byref(p), handle) != 0
     idx.close()
+
+
+REAL_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real", "asp_niger.npz")
+REAL_PAIRS = {"1": (0,), "2": (1,), "3": (2,), "123": (0, 1, 2)}
+
+
+def load_real(tag):
+    """(T, nsep, answers) of one of the reference's real-data pairs (1a/1b, 2a/2b, 3a/3b, 123a/123b) from the committed
+    compact fixture; answers = the unmodified reference's n, sha256 of SA / SAi / LCP and its getmums(20) rows."""
+    from reveal_b200 import synth
+    a, b, z = synth.load_packed_fixture(REAL_FIXTURE, REAL_PAIRS[tag])
+    T, nsep = synth.concat([a, b])
+    ans = {k: z["ans%s_%s" % (tag, k)] for k in ("n", "sa", "sai", "lcp", "mums")}
+    return T, nsep, ans
+
+
+def digest32(arr):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(arr, dtype=np.int32)).tobytes()).hexdigest()
+
+
+def check_against_real(build, tag):
+    """build(T, nsep) -> object with .SA/.SAi/.LCP arrays (callables or arrays) and mums(minl); compares with the reference's answers."""
+    T, nsep, ans = load_real(tag)
+    assert len(T) == int(ans["n"])
+    SA, SAi, LCP, mums = build(T, nsep)
+    assert digest32(SA) == str(ans["sa"]), "SA differs from the reference's"
+    assert digest32(SAi) == str(ans["sai"]), "SAi differs from the reference's"
+    assert digest32(LCP) == str(ans["lcp"]), "LCP differs from the reference's"
+    assert_same(np.asarray(mums, dtype=np.int64).reshape(-1, 3), ans["mums"].astype(np.int64), "getmums(20)")
+    return len(mums)
