@@ -164,6 +164,13 @@ def make_workload(name, seed):
     return T, nsep, ns, desc
 
 
+def config_block(desc, bases_per_unit, mums, units):
+    """The `config` object of the JSON line: the SAME keys in both arms (the driver compares them key by key)."""
+    return {"workload": desc, "bases_per_step_per_gpu": int(bases_per_unit), "mums_per_step": int(mums), "minl": MINL, "minn": MINN,
+            "units": int(units), "l2": "flushed between timed steps (256 MiB write)",
+            "sharding": "single unit" if units == 1 else "one independent index build per unit (GPU rank / host process); MUM records to rank 0"}
+
+
 # ------------------------------------------------------------------------------------------
 _REF_UNIT = {}
 
@@ -183,11 +190,11 @@ def _ref_unit_step(job):
         _REF_UNIT.clear()
         _REF_UNIT[job] = (seqs, ns)
     seqs, ns = _REF_UNIT[job]
+    t0 = time.perf_counter()   # the timed region is the user's call sequence, as in the B200 arm's e2e leg
     idx = R.module(32).index()
     for k, s in enumerate(seqs):
         idx.addsample("g%d" % k)
         idx.addsequence(s)
-    t0 = time.perf_counter()
     idx.construct()
     mums = idx.getmums(MINL) if ns == 2 else idx.getmultimums(minlength=MINL, minn=MINN)
     return time.perf_counter() - t0, len(mums), sum(len(s) + 1 for s in seqs)
@@ -216,34 +223,35 @@ def run_reference(args, rank, world):
         t0 = time.perf_counter()
         res = pool.map(_ref_unit_step, jobs, chunksize=1) if pool else [_ref_unit_step(jobs[0])]
         wall = time.perf_counter() - t0
-        # one unit: the build + sweep alone (sequence loading excluded); several units: wall time of the concurrent batch
-        return (res[0][0] if not pool else wall), res[0][1], sum(r[2] for r in res)
+        # one unit: its own timed region (index() .. getmums()); several units: wall time of the concurrent batch
+        return (res[0][0] if not pool else wall), res[0][1], sum(r[2] for r in res), res[0][2]
 
     # bounded sample: if the full workload would not finish K + W steps in about four minutes, every step uses a prefix of
     # each genome (throughput per base is what is reported)
     frac = 1.0
-    dt, nm, bases = step(frac)
+    dt, nm, bases, bases0 = step(frac)
+    full_bases0, full_nm = bases0, nm   # unit 0 of the workload the config names; a bounded sample of it may be timed below
     budget = float(os.environ.get("RV_REF_BUDGET_S", "240"))
     planned = args.steps + max(args.warmup, 1) - 1
     if dt * planned > budget:
         frac = max(0.02, budget / (dt * planned))
-        dt, nm, bases = step(frac)
+        dt, nm, bases, _ = step(frac)
     for _ in range(max(args.warmup, 1) - 1):
         step(frac)
     tot = 0.0
     for _ in range(args.steps):
-        dt, nm, bases = step(frac)
+        dt, nm, bases, _ = step(frac)
         tot += dt
     if pool:
         pool.close()
     value = bases * args.steps / tot
     sample = "the full workload per step" if frac >= 1.0 else "the first %.0f %% of every genome per step" % (100 * frac)
-    sample += " (construct + getmums%s through the reference extension's Python API" % ("" if WORKLOADS[args.workload][0] == 2 else "/getmultimums")
+    sample += " (index() + addsample/addsequence + construct + getmums%s through the reference extension's Python API" % ("" if WORKLOADS[args.workload][0] == 2 else "/getmultimums")
     sample += "; %d independent units in %d processes at once)" % (units, cores) if units > 1 else ")"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "bases_per_step": bases, "mums_per_step_unit0": nm, "minl": MINL, "minn": MINN, "units": units},
+            "config": config_block(desc, full_bases0, full_nm, units),
             "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -348,6 +356,24 @@ def run_ours(args, rank, world, local_rank):
             gather_evs.append((g0, g1))
         return k
 
+    # the drop-in surface: what a user of the reference calls (reveal/rem.py:560-575 feeds the index like this)
+    from reveal_b200 import reveallib
+    bounds = [0] + [int(x) + 1 for x in nsep] + [n]
+    seqs = [T[bounds[k]:bounds[k + 1] - 1].tobytes().decode("ascii") for k in range(ns)]
+
+    def step_api():
+        """index() -> addsample/addsequence -> construct() -> getmums()/getmultimums() with its Python list: host strings in,
+        Python objects out.  A new index object per step, like one `rem` run."""
+        idx = reveallib.index()
+        for k, sq in enumerate(seqs):
+            idx.addsample("g%d" % k)
+            idx.addsequence(sq)
+        idx.construct()
+        mums = idx.getmums(MINL) if ns == 2 else idx.getmultimums(minlength=MINL, minn=MINN)
+        k = len(mums)
+        d2h = k * 24 if ns == 2 else k * 24 + sum(len(m[2]) for m in mums) * 16
+        return k, d2h
+
     def step_e2e():
         _native.check(L, L.rv_build(h, ctypes.c_void_p(hT.data_ptr()), n, nsep.ctypes.data, ns, 0))
         k = sweep()
@@ -367,6 +393,10 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    t_cold = time.perf_counter()
+    k_cold, _ = step_api()      # the very first call of the process through the drop-in: CUDA context, module load, first allocations
+    torch.cuda.synchronize()
+    cold_first_call_s = time.perf_counter() - t_cold
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # ---- timed: device-resident input -----------------------------------------------------
@@ -379,7 +409,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     evs = []
     for _ in range(args.steps):
-        flush.fill_(1)  # evict L2 between timed iterations (inputs are smaller than L2)
+        with torch.cuda.stream(stream):
+            flush.fill_(1)  # evict L2 between timed iterations (inputs are smaller than L2); on the library's stream, so it is ordered before e0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         nm = step_resident()
@@ -422,25 +453,37 @@ def run_ours(args, rank, world, local_rank):
     times = _native.Times()
     _native.check(L, L.rv_get_times(h, ctypes.byref(times)))
     _native.check(L, L.rv_profile(h, 0))
-    # ---- timed: end to end from pinned host memory through the C-ABI -----------------------
+    # ---- timed: end to end from pinned host memory through the C-ABI (secondary: e2e_cabi) -----------------------
     step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        step_e2e()
+    barrier()
+    cabi_s = time.perf_counter() - t0
+    # ---- timed: end to end through the drop-in extension (the headline e2e): host strings in, Python list out --------------
+    for _ in range(2):
+        step_api()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        k, d2h = step_e2e()
+        k, d2h = step_api()
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert k == nm == k_cold, "the drop-in returned %d MUMs, the C-ABI sweep %d" % (k, nm)
     clocks = sampler.summary() if sampler else None
 
-    tmax = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([dev_ms, e2e_s * 1e3, cabi_s * 1e3], dtype=torch.float64, device=dev)
     ntot = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(ntot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
+    dev_ms_max, e2e_ms_max, cabi_ms_max = float(tmax[0]), float(tmax[1]), float(tmax[2])
     total_bases = float(ntot[0])
 
     if rank == 0:
@@ -462,10 +505,14 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
-                "config": {"workload": desc, "bases_per_step_per_gpu": n, "mums_per_step": nm, "minl": MINL, "minn": MINN,
-                           "l2": "flushed between timed steps (256 MiB write)", "sharding": ("independent index build per rank; MUM records to rank 0 through " + ("mapped peer blocks (NVLink stores, no collective)" if gatherer.get("kind") == "peer" else "one NCCL gather per step")) if world > 1 else "single GPU"},
+                "config": config_block(desc, n, nm, world),
+                "transport": ("mapped peer blocks (NVLink stores, no collective)" if gatherer.get("kind") == "peer" else "one NCCL gather per step") if world > 1 else None,
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n + 8 * len(nsep)), "d2h_bytes_per_step": int(d2h + 32),
-                        "ms_per_step": e2e_ms_max / args.steps},
+                        "ms_per_step": e2e_ms_max / args.steps,
+                        "what": "reveallib.index(): addsample/addsequence (host str) -> construct() -> getmums()/getmultimums() incl. its Python list, a new index object per step",
+                        "cold_first_call_ms": cold_first_call_s * 1e3},
+                "e2e_cabi": {"value": total_bases * args.steps / (cabi_ms_max * 1e-3), "unit": "bases/s", "ms_per_step": cabi_ms_max / args.steps,
+                             "what": "rv_build from pinned host memory + sweep + rows into a pinned buffer on a warm handle (no Python objects)"},
                 "gpu_launches": launches, "gather_ms_per_step": gather_ms, "gather_check": gather_check,
                 # the dominant kernel = largest measured share of the step; algorithmic bytes per slot: include/reveal_b200.h, DESIGN.md
                 "roofline": {"bound": "hbm", "kernel": top.get("kernel"), "achieved": top.get("achieved"), "peak": peak, "unit": "GB/s",

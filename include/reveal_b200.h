@@ -89,14 +89,18 @@ int rv_get_times(const rv_index *idx, rv_times *out);
  * ALGORITHMIC bytes (stated per slot below and in DESIGN.md) until the next rv_profile(idx, 1). */
 enum rv_prof_slot {
     RV_PROF_RADIX_PASS = 0, /* rs_pass_kernel: items x (key + 4 B suffix) x (read + write) */
-    RV_PROF_PAIRS = 1,      /* sa_pairs_kernel: n x (key + 4 B suffix read; SA + SAi + LCP = 12 B written) */
+    RV_PROF_PAIRS = 1,      /* sa_place_kernel: n x (key + 4 B suffix read; SA + SAi + LCP = 12 B written) */
     RV_PROF_SWEEP = 2,      /* pair / multi sweep kernels (count + write): n x 9 B (11 B with SO) per pass */
-    RV_PROF_LCP = 3         /* lcp_sparse_kernel (entries of the suffixes the doubling rounds placed): 13 B per marked position + n/8 */
+    RV_PROF_LCP = 3,        /* lcp_sparse_kernel (entries of the suffixes the doubling rounds placed): 13 B per marked position + n/8 */
+    RV_PROF_LEAD = 4,       /* sa_lead_kernel: n x (key + 4 B suffix) read, sampled pairs compared and recorded */
+    RV_PROF_TEXT = 5,       /* passes over the text: byte histogram, k-mer digit histograms, barrier bitmaps + packed text: n x 1 B each */
+    RV_PROF_ROUNDS = 6,     /* stage 4 (refinement / doubling rounds): key gather, group scan and placement kernels, 24 B per active suffix */
+    RV_PROF_SLOTS = 8
 };
 typedef struct rv_kernel_profile {
-    double ms[4];
-    int64_t launches[4];
-    int64_t bytes[4];
+    double ms[RV_PROF_SLOTS];
+    int64_t launches[RV_PROF_SLOTS];
+    int64_t bytes[RV_PROF_SLOTS];
     int64_t launches_total; /* every kernel this handle launched since creation */
 } rv_kernel_profile;
 int rv_profile(rv_index *idx, int32_t enable);

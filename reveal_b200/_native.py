@@ -24,8 +24,8 @@ class Times(ctypes.Structure):
 
 
 class KernelProfile(ctypes.Structure):
-    SLOTS = ("rs_pass_kernel", "sa_pairs_kernel", "sweep kernels", "lcp_sparse_kernel")
-    _fields_ = [("ms", ctypes.c_double * 4), ("launches", ctypes.c_int64 * 4), ("bytes", ctypes.c_int64 * 4),
+    SLOTS = ("rs_pass_kernel", "sa_place_kernel", "sweep kernels", "lcp_sparse_kernel", "sa_lead_kernel", "text passes", "stage-4 round kernels", "")
+    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_int64 * 8), ("bytes", ctypes.c_int64 * 8),
                 ("launches_total", ctypes.c_int64)]
 
     def as_dict(self):

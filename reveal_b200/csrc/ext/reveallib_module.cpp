@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -554,6 +555,14 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
     return lst;
 }
 
+// wall time of the parts of the last align() (seconds): where a recursion spends its time
+struct AlignStats {
+    double extract = 0, pick = 0, galign = 0, parse = 0, step = 0, child = 0, total = 0;
+    long long steps = 0, picks = 0;
+};
+static AlignStats g_align_stats;
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn", nullptr};  // interface.c:303
     PyObject *mumpicker, *graphalign;
@@ -576,6 +585,9 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     Py_INCREF((PyObject *)self);
     queue.push_back(self);
     bool ok = true;
+    AlignStats &as = g_align_stats;
+    as = AlignStats();
+    const double t_begin = now_s();
     PyObject *kw_minl = PyLong_FromLong(minl);
     std::vector<int64_t> lead, trail, par, match, lead_b, trail_b, par_b, match_b;
     while (ok && !queue.empty()) {
@@ -589,9 +601,11 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                 break;
             }
             int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
+            double t0 = now_s(), t1;
             if (!precomputed) {
                 mums = extract_mums(self, idx->sub, minl, minn);
                 if (!mums) { ok = false; break; }
+                t1 = now_s(); as.extract += t1 - t0; t0 = t1;
             } else {
                 mums = idx->skipmums;
                 Py_INCREF(mums);
@@ -601,6 +615,8 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
             Py_DECREF(cargs);
             Py_DECREF(ckw);
+            t1 = now_s(); as.pick += t1 - t0; t0 = t1;
+            as.picks++;
             if (!pick) { ok = false; break; }
             if (!PyTuple_Check(pick)) {
                 PyErr_SetString(RevealError, "**** call to mumpicker failed");
@@ -622,7 +638,9 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                 Py_XDECREF(tup);
             }
             if (PyErr_Occurred()) { ok = false; break; }
+            t0 = now_s();
             result = PyObject_CallFunctionObjArgs(graphalign, (PyObject *)idx, mumobject, nullptr);  // reveal.c:939
+            t1 = now_s(); as.galign += t1 - t0; t0 = t1;
             if (!result) { ok = false; break; }
             if (result == Py_None) break;
             if (!PyTuple_Check(result)) {
@@ -644,10 +662,13 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             int32_t sweep[3] = {PyObject_Length(skipleft) == 0, PyObject_Length(skipright) == 0, 1};
             rv_sub *kids[3] = {nullptr, nullptr, nullptr};
             int status;
+            t1 = now_s(); as.parse += t1 - t0; t0 = t1;
             Py_BEGIN_ALLOW_THREADS;
             status = g_api.rv_sub_step(idx->sub, lead.data(), (int32_t)lead_b.size(), trail.data(), (int32_t)trail_b.size(), par.data(),
                                        (int32_t)par_b.size(), mum_sp.data(), mum_n, mum_l, match.data(), (int32_t)match_b.size(), sweep, minl, minn, kids);
             Py_END_ALLOW_THREADS;
+            t1 = now_s(); as.step += t1 - t0; t0 = t1;
+            as.steps++;
             if (fail_native(status) != 0) { ok = false; break; }
             self->tdirty = 1;  // matched bases were lower-cased on the device (reveal.c:1230-1234)
             const int depth = idx->depth + 1;
@@ -659,6 +680,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
             if (i_lead) queue.push_back(i_lead);
             if (i_trail) queue.push_back(i_trail);
+            as.child += now_s() - t0;
         } while (0);
         Py_XDECREF(mums);
         Py_XDECREF(pick);
@@ -678,8 +700,15 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
         Py_DECREF((PyObject *)q);
     }
     Py_DECREF(kw_minl);
+    as.total = now_s() - t_begin;
     if (!ok) return nullptr;
     Py_RETURN_NONE;
+}
+
+static PyObject *mod_align_stats(PyObject *, PyObject *) {
+    const AlignStats &a = g_align_stats;
+    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:L,s:L}", "total_s", a.total, "sweep_fetch_s", a.extract, "mumpicker_s", a.pick, "graphalign_s", a.galign,
+                         "parse_s", a.parse, "device_step_s", a.step, "children_s", a.child, "steps", a.steps, "mumpicker_calls", a.picks);
 }
 
 // ---- splitindex (reveal.c:1515-1748): one recursion step driven from Python -------------------------------------------------------
@@ -937,6 +966,7 @@ static PyMethodDef module_methods[] = {
     {"chain_dp", mod_chain_dp, METH_VARARGS, "Chaining recurrence of the REM driver on int64 buffers (see reveal_b200/rem.py:chain)."},
     {"_load", mod_load, METH_VARARGS, "Load a shared library exporting the C-ABI of include/reveal_b200.h (tests inject the emulated kernels)."},
     {"_library", mod_library, METH_NOARGS, "(path, version) of the loaded C-ABI library."},
+    {"align_stats", mod_align_stats, METH_NOARGS, "Wall time of the parts of the last index.align() of this module (seconds), and its step count."},
     {nullptr, nullptr, 0, nullptr}};
 
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, MODNAME,

@@ -392,7 +392,7 @@ int rv_profile(rv_index *h, int32_t enable) {
     if (!h) return RV_ERR_ARG;
     RV_TRY(prof_collect(h->st));
     h->st.prof = enable != 0;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < RV_PROF_SLOTS; k++) {
         h->st.prof_ms[k] = 0;
         h->st.prof_launches[k] = 0;
         h->st.prof_bytes[k] = 0;
@@ -402,7 +402,7 @@ int rv_profile(rv_index *h, int32_t enable) {
 int rv_get_profile(rv_index *h, rv_kernel_profile *out) {
     if (!h || !out) return RV_ERR_ARG;
     RV_TRY(prof_collect(h->st));
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < RV_PROF_SLOTS; k++) {
         out->ms[k] = h->st.prof_ms[k];
         out->launches[k] = h->st.prof_launches[k];
         out->bytes[k] = h->st.prof_bytes[k];

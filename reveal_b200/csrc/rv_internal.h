@@ -80,9 +80,9 @@ struct Stream {
     std::vector<ProfRec> pending;
     std::vector<cudaEvent_t> free_events;
     cudaEvent_t cur0 = 0;
-    double prof_ms[4] = {0, 0, 0, 0};          // per slot (enum rv_prof_slot): summed kernel time
-    long long prof_launches[4] = {0, 0, 0, 0};
-    long long prof_bytes[4] = {0, 0, 0, 0};    // algorithmic bytes moved by those launches
+    double prof_ms[RV_PROF_SLOTS] = {0};          // per slot (enum rv_prof_slot): summed kernel time
+    long long prof_launches[RV_PROF_SLOTS] = {0};
+    long long prof_bytes[RV_PROF_SLOTS] = {0};    // algorithmic bytes moved by those launches
 };
 
 inline int prof_event(Stream &st, cudaEvent_t *e) {

@@ -67,12 +67,17 @@ __device__ __forceinline__ void run_lengths(const KeyT *__restrict__ keys, i64 A
 }
 
 // ---- stage 3: all-pairs comparison inside small groups -------------------------------------
-// Two-level barrier bitmap: bit i of bar0[] is set iff T[i] is '$' or 'N' (the reference's LCP
-// barrier, interface.c:107); bit w of bar1[] is set iff word w of bar0 is non-zero.
+// Three-level barrier bitmap: bit i of b0[] is set iff T[i] is '$' or 'N' (the reference's LCP barrier, interface.c:107);
+// bit w of b1[] iff word w of b0 is non-zero; bit v of b2[] iff word v of b1 is non-zero (one b2 word covers 32768 positions,
+// so the '$'/'N' cut of an LCP value of a million costs ~30 loads, not 30000).
+struct Barriers {
+    const u32 *b0, *b1, *b2;
+};
 // One pass over T: the barrier bitmaps and (PACK) the 4-bit packed text (8 symbols per word, symbol i in bits 4i..4i+3).
+// b2 must be zeroed before the launch.
 template <bool PACK>
 __global__ void __launch_bounds__(1024) sa_textprep_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ bar0,
-                                                          u32 *__restrict__ bar1, u32 *__restrict__ packed) {
+                                                          u32 *__restrict__ bar1, u32 *__restrict__ bar2, u32 *__restrict__ packed) {
     __shared__ u32 s_nz[32];
     __shared__ unsigned short s_code[256];
     if (PACK) {
@@ -97,42 +102,64 @@ __global__ void __launch_bounds__(1024) sa_textprep_kernel(const unsigned char *
     __syncthreads();
     if (threadIdx.x < 32) {
         unsigned nz = __ballot_sync(FULL, s_nz[threadIdx.x] != 0u);
-        if (threadIdx.x == 0) bar1[blockIdx.x] = nz;
+        if (threadIdx.x == 0) {
+            bar1[blockIdx.x] = nz;
+            if (nz) atomicOr(&bar2[blockIdx.x >> 5], 1u << (blockIdx.x & 31u));
+        }
     }
 }
 
 // offset of the first barrier character in T[x .. x+len), or len
-__device__ __forceinline__ u32 first_barrier(const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, u32 x, u32 len) {
+__device__ __forceinline__ u32 first_barrier(const Barriers &B, u32 x, u32 len) {
     if (len == 0u) return 0u;
     u32 w = x >> 5;
-    const u32 wl = (x + len - 1u) >> 5;
-    if (wl - w < 32u) {  // at most two level-1 words cover the range: usually "nothing here"
+    const u32 wl = (x + len - 1u) >> 5;  // last level-0 word of the range
+    // The usual answer is "none", and level 1 (n/1024 words: cache resident) can say so alone when the range lies within two
+    // of its words: level 0 is only touched when a barrier is near.
+    if ((wl >> 5) - (w >> 5) <= 1u) {
         const u32 v = w >> 5, vl = wl >> 5;
-        u32 m = bar1[v] >> (w & 31u);                   // words w .. end of level-1 word v
+        u32 m = B.b1[v] >> (w & 31u);                   // words w .. end of level-1 word v
         if (v == vl) {
-            u32 span = wl - w;
+            const u32 span = wl - w;
             if (span < 31u) m &= (2u << span) - 1u;
         } else {
-            u32 last = wl & 31u;                         // words 0 .. last of level-1 word vl
-            u32 m2 = bar1[vl];
+            const u32 last = wl & 31u;                   // words 0 .. last of level-1 word vl
+            u32 m2 = B.b1[vl];
             if (last < 31u) m2 &= (2u << last) - 1u;
             m |= m2;
         }
         if (m == 0u) return len;
     }
-    u32 sh = x & 31u;
-    u32 bits = bar0[w] >> sh;
-    u32 base = 0, have = 32u - sh;
-    for (;;) {
+    {
+        const u32 bits = B.b0[w] >> (x & 31u);
         if (bits) {
-            u32 at = base + (u32)(__ffs((int)bits) - 1);
+            const u32 at = (u32)(__ffs((int)bits) - 1);
             return at < len ? at : len;
         }
-        base += have;
-        if (base >= len) return len;
-        bits = bar0[++w];
-        have = 32u;
     }
+    w++;
+    while (w <= wl) {
+        u32 v = w >> 5;
+        const u32 m = B.b1[v] >> (w & 31u);  // level-0 words w .. end of level-1 word v
+        if (m) {
+            w += (u32)(__ffs((int)m) - 1);
+            if (w > wl) return len;
+            const u32 at = (w << 5) + (u32)(__ffs((int)B.b0[w]) - 1) - x;
+            return at < len ? at : len;
+        }
+        v++;  // next non-empty level-1 word, through level 2
+        for (;;) {
+            if ((v << 5) > wl) return len;
+            const u32 m2 = B.b2[v >> 5] >> (v & 31u);
+            if (m2) {
+                v += (u32)(__ffs((int)m2) - 1);
+                break;
+            }
+            v = ((v >> 5) + 1u) << 5;
+        }
+        w = v << 5;
+    }
+    return len;
 }
 
 // Text as the comparison loops see it: SB bits per symbol in little-endian 32-bit words (symbol i of a word
@@ -147,37 +174,69 @@ template <int SB> struct Sym {
     static const u32 MASK = (1u << SB) - 1u;
 };
 
-// barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison, 4 words per step
+// Suffixes p and q are known to agree on their first h0 symbols: extends the comparison, one step = 4 words per suffix,
+// funnel-shifted to the suffix start, XOR, first set bit.  Returns false when `cap` more symbols brought no decision;
+// else lcp = common prefix and p_less = "suffix p sorts before suffix q" (a suffix that is a prefix of the other sorts first).
 template <int SB>
-__device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u32 p, u32 q, const u32 *__restrict__ bar0,
-                                          const u32 *__restrict__ bar1) {
+__device__ __forceinline__ bool fwd_compare(const u32 *__restrict__ W, u32 n32, u32 p, u32 q, u32 h0, u32 cap, u32 &lcp, bool &p_less) {
     typedef Sym<SB> S;
     const u32 lenmin = n32 - (p > q ? p : q);
-    const u32 *pa = W + (p >> S::LOG_SPW), *pb = W + (q >> S::LOG_SPW);
-    const unsigned sha = (p & (S::SPW - 1u)) * SB, shb = (q & (S::SPW - 1u)) * SB;
+    if (h0 >= lenmin) {
+        lcp = lenmin;
+        p_less = p > q;
+        return true;
+    }
+    const u32 pp = p + h0, qq = q + h0;
+    const u32 *pa = W + (pp >> S::LOG_SPW), *pb = W + (qq >> S::LOG_SPW);
+    const unsigned sha = (pp & (S::SPW - 1u)) * SB, shb = (qq & (S::SPW - 1u)) * SB;
     u32 lo_a = *pa, lo_b = *pb;
-    u32 h = 0, match = lenmin;
-    while (h < lenmin) {
-        u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
-        u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
-        u32 d0 = __funnelshift_r(lo_a, a1, sha) ^ __funnelshift_r(lo_b, b1, shb);
-        u32 d1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
-        u32 d2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
-        u32 d3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+    u32 h = h0;
+    const u32 stop = h0 + cap;
+    for (;;) {
+        const u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+        const u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
+        const u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
+        const u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
+        const u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
+        const u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
+        const u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
         if (d0 | d1 | d2 | d3) {
-            u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
-            u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-            u32 at = h + wsel * S::SPW + ((u32)(__ffs((int)dd) - 1) >> S::LOG_SB);
-            match = at < lenmin ? at : lenmin;
-            break;
+            const u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
+            const u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
+            const u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
+            const u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
+            const u32 bsh = (u32)(__ffs((int)dd) - 1) & ~(u32)(SB - 1);  // bit offset of the first differing symbol
+            const u32 at = h + wsel * S::SPW + (bsh >> S::LOG_SB);
+            if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
+                lcp = lenmin;
+                p_less = p > q;
+            } else {
+                lcp = at;
+                p_less = ((va >> bsh) & S::MASK) < ((vb >> bsh) & S::MASK);
+            }
+            return true;
         }
         h += S::STEP;
+        if (h >= lenmin) {
+            lcp = lenmin;
+            p_less = p > q;
+            return true;
+        }
+        if (h >= stop) return false;
         pa += 4;
         pb += 4;
         lo_a = a4;
         lo_b = b4;
     }
-    return (int)first_barrier(bar0, bar1, p, match);
+}
+
+// barrier-aware LCP of suffixes p and q (p = the one whose entry it is) by direct comparison
+template <int SB>
+__device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u32 p, u32 q, const Barriers &B) {
+    u32 lcp = 0;
+    bool less;
+    fwd_compare<SB>(W, n32, p, q, 0u, 0xC0000000u, lcp, less);
+    return (int)first_barrier(B, p, lcp);
 }
 
 #ifndef RV_PR_THREADS
@@ -194,43 +253,27 @@ static const int PR_WARPS = PR_THREADS / 32;
 static const int PR_CHUNK = RV_PR_CHUNK;               // nominal SA slots per warp
 static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched to whole groups (<= SA_SMALL_G more), padded to rounds
 static const int PR_ROUNDS = PR_MAXT / 32;
-static const int PR_QCAP = 512;                        // ring of work items per warp (>= one worst-case round of 32*15)
+static const int PL_CAP = 512;                         // pair items per warp (a power of two >= 32 * 15 + 31)
+static const int ET_WAYS = 8;                          // entries per bucket of the sampled-pair table
 
-// One warp owns a run of whole groups (about PR_CHUNK consecutive SA slots).  Every pair (member,
-// earlier mate) of a small group becomes a work item in the warp's shared-memory ring; lanes pull the
-// next item whenever they are idle and the ring is refilled as it runs low, so the lanes stay busy
-// until the chunk is done.  A comparison step covers 16 text bytes: five aligned 32-bit words per
-// suffix funnel-shifted to the suffix start, XOR, first set bit.  The larger suffix of a pair gains one
-// smaller mate (-> its place inside the group) and the pair's common prefix (-> its LCP entry = the
-// largest over its smaller mates); both live in shared memory because a group never leaves its warp.
-// The warp then places its groups: SA, inverse SA and LCP.
-template <typename KeyT, int SB>
-__global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
-sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W,
-                const u32 *__restrict__ bar0, const u32 *__restrict__ bar1, int skip, int *__restrict__ SA, int *__restrict__ rank,
-                int *__restrict__ LCP, unsigned char *__restrict__ deferred, u32 *__restrict__ flag_large, int *__restrict__ chunk_start,
-                u32 *__restrict__ needbits) {
-    __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
-    __shared__ int s_lcp[PR_WARPS][PR_MAXT];
-    __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
-    __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group; 0xFF: not a small group
-    __shared__ unsigned short s_queue[PR_WARPS][PR_QCAP];
-    __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];     // bit t: slot t starts a group
-    __shared__ u32 s_def[PR_WARPS][PR_ROUNDS];          // bit t0: the group starting at t0 is deferred to stage 4
-    typedef Sym<SB> S;
+// The comparison stage works on runs of whole groups: one warp owns about PR_CHUNK consecutive slots of the sorted (key, suffix)
+// list, stretched at both ends to group boundaries.  Both kernels of the stage start with the same staging: suffixes into shared
+// memory, one "starts a group" bit per slot (ballots over neighbouring keys, no loads beyond the keys themselves).
+struct PairChunk {
+    u32 *ssa;      // [PR_MAXT] staged suffixes
+    u32 *head;     // [-1 .. PR_ROUNDS] bit t: slot t starts a group (head[-1] and head[PR_ROUNDS] are zero: 64-bit windows)
+    i64 s;         // first slot of the run
+    int nt;        // slots in the run
+    int rounds;
+    int end_closed;  // the last group of the run really ends with the run
+};
+template <typename KeyT>
+__device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, u32 *s_head_raw /*[PR_ROUNDS+2]*/) {
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    u32 *ssa = s_sa[w];
-    int *lcpv = s_lcp[w];
-    u32 *cnt = s_cnt[w];
-    unsigned char *sL = s_L[w];
-    unsigned short *queue = s_queue[w];
-    u32 *head = s_head[w] + 1;  // head[-1] and head[PR_ROUNDS] exist (zero) for the 64-bit windows
-    u32 *sdef = s_def[w];
-
-    // ---- the warp's run of whole groups: [s, end) ----
+    c.head = s_head_raw + 1;
     const i64 c0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
     i64 s = c0, end = c0 + PR_CHUNK < n ? c0 + PR_CHUNK : n;
-    int end_closed = 1;  // the last group of the run really ends at `end`
+    int end_closed = 1;
     if (lane == 0 && c0 < n) {
         if (c0 > 0) {
             int L, R;
@@ -248,166 +291,213 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     }
     s = __shfl_sync(FULL, s, 0);
     end = __shfl_sync(FULL, end, 0);
-    end_closed = __shfl_sync(FULL, end_closed, 0);
-    const int nt = c0 < n && end > s ? (int)(end - s) : 0;  // local slots t = 0 .. nt-1
-    if (lane == 0) chunk_start[(i64)blockIdx.x * PR_WARPS + w] = nt ? (int)s : -1;  // its LCP entry: sa_chunkhead_kernel
-    if (nt == 0) return;  // warp-uniform
-    const int rounds = (nt + 31) / 32;
-
-    // ---- stage suffixes, group heads and per-slot state ----
-    if (lane < 2) s_head[w][lane ? PR_ROUNDS + 1 : 0] = 0u;
-    for (int r = 0; r < rounds; r++) {
+    c.end_closed = __shfl_sync(FULL, end_closed, 0);
+    c.s = s;
+    c.nt = c0 < n && end > s ? (int)(end - s) : 0;
+    c.rounds = (c.nt + 31) / 32;
+    if (c.nt == 0) return;  // warp-uniform
+    if (lane < 2) s_head_raw[lane ? PR_ROUNDS + 1 : 0] = 0u;
+    for (int r = 0; r < c.rounds; r++) {
         const int t = r * 32 + (int)lane;
         const i64 e = s + t;
-        const bool valid = t < nt;
+        const bool valid = t < c.nt;
         KeyT k = valid ? keys[e] : (KeyT)0;
         KeyT kp = __shfl_up_sync(FULL, k, 1);
         if (lane == 0) kp = (valid && e > 0) ? keys[e - 1] : (KeyT)0;
-        bool is_head = valid && (e == 0 || k != kp);
-        unsigned hm = __ballot_sync(FULL, is_head);
-        if (lane == 0) {
-            head[r] = hm;
-            sdef[r] = 0u;
-        }
-        ssa[t] = valid ? sa[e] : 0u;
-        lcpv[t] = 0;
-        if ((lane & 3u) == 0) cnt[t >> 2] = 0u;
+        const bool is_head = valid && (e == 0 || k != kp);
+        const unsigned hm = __ballot_sync(FULL, is_head);
+        if (lane == 0) c.head[r] = hm;
+        c.ssa[t] = valid ? sa[e] : 0u;
     }
-    for (int r = rounds; r < PR_ROUNDS; r++)
-        if (lane == 0) head[r] = 0u;
+    for (int r = c.rounds; r < PR_ROUNDS; r++)
+        if (lane == 0) c.head[r] = 0u;
+    __syncwarp();
+}
+// members to the left / right of slot t inside its group; false when the group has more than SA_SMALL_G members (or is cut by the run's end)
+__device__ __forceinline__ bool pair_chunk_group(const PairChunk &c, int t, int &L, int &R) {
+    const int round = t >> 5;
+    const unsigned b = (unsigned)t & 31u;
+    const u64 v = ((u64)c.head[round] << 32) | (u64)c.head[round - 1];
+    const u64 below = v & ((2ull << (32u + b)) - 1ull);  // heads at or before t
+    L = below ? (int)(32u + b) - (63 - __clzll((long long)below)) : 0xFF;
+    const u64 v2 = (((u64)c.head[round + 1] << 32) | (u64)c.head[round]) >> (b + 1u);  // heads after t
+    R = v2 ? __ffsll((long long)v2) - 1 : 0xFF;
+    if (R != 0xFF && t + R + 1 > c.nt) R = 0xFF;                                        // (cannot happen: no head bits beyond nt)
+    if (R == 0xFF && t + 33 >= c.nt) R = c.end_closed ? c.nt - 1 - t : 0xFF;            // the run ends the group
+    return L != 0xFF && R != 0xFF && L + R + 1 <= SA_SMALL_G;
+}
+
+// Similar genomes put homologous positions x (one genome) and y (the other) into one group for as long as the genomes agree:
+// the pairs (x, y), (x+1, y+1), ... lie on one DIAGONAL and lcp(x+1, y+1) = lcp(x, y) - 1.  Comparing every pair down to its
+// mismatch costs  (match length)^2 / 2  symbols per diagonal -- and far more inside repeats.  Instead:
+//   sa_lead_kernel   only pairs whose smaller position x is a multiple of S (= one comparison step, 32 packed symbols) are
+//                    compared to the end (cap SA_CMP_CAP); the result goes into a table keyed by (x, y).
+//   sa_place_kernel  every pair compares ONE step; if that step finds no mismatch, the pair's diagonal has passed the sampled
+//                    position x' = next multiple of S, and  lcp(x, y) = (x' - x) + lcp(x', y + x' - x)  is one table look-up.
+//                    A look-up that finds nothing (the sampled pair sits in a large or postponed group, its bucket overflowed,
+//                    or it never was a pair because the k-mers at x' differ) just continues the comparison.
+// Table: (n/S + 1) buckets of ET_WAYS 64-bit entries  [y : 32 | lcp : 31 | x sorts first : 1], 0 = empty, bucket = x / S.
+template <typename KeyT, int SB>
+__global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
+sa_lead_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W, u64 *__restrict__ etab) {
+    __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
+    __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];
+    __shared__ unsigned short s_list[PR_WARPS][PR_MAXT];
+    typedef Sym<SB> S;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    PairChunk c;
+    c.ssa = s_sa[w];
+    pair_chunk_setup(c, keys, sa, n, s_head[w]);
+    if (c.nt == 0) return;
+    unsigned short *list = s_list[w];
+    // the sampled members of small groups that have mates
+    u32 nlist = 0;
+    for (int r = 0; r < c.rounds; r++) {
+        const int t = r * 32 + (int)lane;
+        int L = 0, R = 0;
+        const bool samp = t < c.nt && (c.ssa[t] & (S::STEP - 1u)) == 0u && pair_chunk_group(c, t, L, R) && L + R > 0;
+        const unsigned m = __ballot_sync(FULL, samp);
+        if (samp) list[nlist + (u32)__popc(m & lanemask_lt())] = (unsigned short)t;
+        nlist += (u32)__popc(m);
+    }
+    __syncwarp();
+    const u32 n32 = (u32)n;
+    for (u32 i = lane; i < nlist; i += 32) {
+        const int t = list[i];
+        int L, R;
+        pair_chunk_group(c, t, L, R);
+        const u32 x = c.ssa[t];
+        u64 *bucket = etab + (size_t)(x >> (S::LOG_SPW + 2u)) * ET_WAYS;
+        for (int m = t - L; m <= t + R; m++) {
+            const u32 y = c.ssa[m];
+            if (y <= x) continue;
+            u32 lcp;
+            bool x_less;
+            if (!fwd_compare<SB>(W, n32, x, y, 0u, (u32)SA_CMP_CAP, lcp, x_less)) continue;  // too long: not recorded
+            const u64 val = ((u64)y << 32) | ((u64)lcp << 1) | (x_less ? 1ull : 0ull);
+            for (int e = 0; e < ET_WAYS; e++)
+                if (atomicCAS(bucket + e, 0ull, val) == 0ull) break;
+        }
+    }
+}
+
+__device__ __forceinline__ bool etab_find(const u64 *__restrict__ etab, u32 bucket, u64 first, u32 y, u32 &lcp, bool &x_less) {
+    const u64 *b = etab + (size_t)bucket * ET_WAYS;
+#pragma unroll 1
+    for (int e = 0; e < ET_WAYS; e++) {
+        const u64 v = e ? b[e] : first;  // entry 0 was loaded ahead by the caller
+        if (v == 0ull) return false;
+        if ((u32)(v >> 32) == y) {
+            lcp = (u32)(v >> 1) & 0x7fffffffu;
+            x_less = (v & 1ull) != 0ull;
+            return true;
+        }
+    }
+    return false;
+}
+
+// lcp and order of the suffixes at positions x < y of one group: the pair's own record if x is a sampled position; else one
+// comparison step and, if that step found no difference, the record of the sampled pair further down the diagonal; else (no
+// record) the comparison goes on.  false: still undecided SA_CMP_CAP symbols later.
+template <int SB>
+__device__ __forceinline__ bool resolve_pair(const u32 *__restrict__ W, u32 n32, const u64 *__restrict__ etab, u32 x, u32 y, u32 &lcp, bool &x_less) {
+    typedef Sym<SB> S;
+    const u32 xo = x & (S::STEP - 1u);
+    const u32 cc = xo ? S::STEP - xo : 0u;  // the diagonal reaches its sampled position after cc matching symbols
+    const u32 lenmin = n32 - y;
+    const u32 bucket = (x + cc) >> (S::LOG_SPW + 2u);
+    const u64 first = cc < lenmin ? etab[(size_t)bucket * ET_WAYS] : 0ull;  // in flight while the step below runs
+    if (xo == 0u && etab_find(etab, bucket, first, y, lcp, x_less)) return true;
+    if (fwd_compare<SB>(W, n32, x, y, 0u, S::STEP, lcp, x_less)) return true;  // one step
+    u32 l2;
+    if (xo != 0u && cc < lenmin && etab_find(etab, bucket, first, y + cc, l2, x_less)) {
+        lcp = cc + l2;
+        return true;
+    }
+    return fwd_compare<SB>(W, n32, x, y, S::STEP, (u32)SA_CMP_CAP, lcp, x_less);
+}
+
+// Every member of a small group meets each earlier member once; the larger suffix of a pair gains one smaller mate (-> its place
+// inside the group) and the pair's common prefix (-> its LCP entry = the largest over its smaller mates, cut at the first '$'/'N'
+// when it is written); both live in shared memory because a group never leaves its warp.  The warp then places its groups: SA,
+// inverse SA and LCP.  A pair that is still undecided SA_CMP_CAP symbols after its look-up postpones its group to stage 4.
+template <typename KeyT, int SB>
+__global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
+sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W, Barriers bars,
+                const u64 *__restrict__ etab, int *__restrict__ SA, int *__restrict__ rank, int *__restrict__ LCP, unsigned char *__restrict__ deferred,
+                u32 *__restrict__ flag_large, int *__restrict__ chunk_start, u32 *__restrict__ needbits) {
+    __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
+    __shared__ u32 s_lcp[PR_WARPS][PR_MAXT];
+    __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
+    __shared__ unsigned char s_L[PR_WARPS][PR_MAXT];    // members to the left inside the group; 0xFF: not a small group
+    __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];
+    __shared__ u32 s_def[PR_WARPS][PR_ROUNDS];          // bit t0: the group starting at t0 is postponed to stage 4
+    __shared__ unsigned short s_pairs[PR_WARPS][PL_CAP];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    PairChunk c;
+    c.ssa = s_sa[w];
+    u32 *ssa = c.ssa, *lcpv = s_lcp[w], *cnt = s_cnt[w], *sdef = s_def[w];
+    unsigned char *sL = s_L[w];
+    pair_chunk_setup(c, keys, sa, n, s_head[w]);
+    const int nt = c.nt;
+    const i64 s = c.s;
+    if (lane == 0) chunk_start[(i64)blockIdx.x * PR_WARPS + w] = nt ? (int)s : -1;  // its LCP entry: sa_chunkhead_kernel
+    if (nt == 0) return;  // warp-uniform
+    const int rounds = c.rounds;
+    for (int r = 0; r < rounds; r++) {
+        const int t = r * 32 + (int)lane;
+        int L = 0xFF, R;
+        bool small = false;
+        if (t < nt) small = pair_chunk_group(c, t, L, R);
+        sL[t] = small ? (unsigned char)L : (unsigned char)0xFF;
+        if (t < nt && !small && L == 0) *flag_large = 1u;
+        lcpv[t] = 0u;
+        if ((lane & 3u) == 0) cnt[t >> 2] = 0u;
+        if (lane == 0) sdef[r] = 0u;
+    }
     __syncwarp();
 
-    // ---- unified loop: refill the ring when it runs low, pull items, compare ----
-    u32 qn = 0, next = 0;  // ring: items [next, qn)
-    int round = 0;
-    bool active = false;
-    int tx = 0, ty = 0;
-    u32 x = 0;
-    u32 p = 0, q = 0, lenmin = 0, h = 0;  // n < 2^30: text offsets fit 32 bits
-    const u32 *pa = W, *pb = W;
-    unsigned sha = 0, shb = 0;
-    u32 lo_a = 0, lo_b = 0;
+    // ---- pairs: every (member, earlier mate) of a small group becomes an item of a shared-memory list; the lanes take the
+    //      items 32 at a time, so they stay busy whatever the group sizes are ----
     const u32 n32 = (u32)n;
-    for (;;) {
-        // refill (warp-uniform condition)
-        while (round < rounds && (qn - next) < 64u) {
-            const int t = round * 32 + (int)lane;
-            int c = 0;
-            if (t < nt) {
-                const unsigned b = (unsigned)t & 31u;
-                // previous head at or before t: window = head[round-1] : head[round]
-                u64 v = ((u64)head[round] << 32) | (u64)head[round - 1];
-                u64 below = v & ((2ull << (32u + b)) - 1ull);
-                int L = below ? (int)(32u + b) - (63 - __clzll((long long)below)) : 0xFF;
-                // next head after t: window = head[round] : head[round+1]
-                u64 v2 = (((u64)head[round + 1] << 32) | (u64)head[round]) >> (b + 1u);
-                int R;
-                if (v2) R = __ffsll((long long)v2) - 1;
-                else R = 0xFF;
-                if (R != 0xFF && t + R + 1 > nt) R = 0xFF;          // (cannot happen: no head bits beyond nt)
-                if (R == 0xFF && t + 33 >= nt) R = end_closed ? nt - 1 - t : 0xFF;  // the run ends the group
-                const bool small = L != 0xFF && R != 0xFF && L + R + 1 <= SA_SMALL_G;
-                sL[t] = small ? (unsigned char)L : (unsigned char)0xFF;
-                if (small) c = L;
-                else if (L == 0) *flag_large = 1u;
-            }
-            u32 inc = warp_incl_sum((u32)c);
-            u32 total = __shfl_sync(FULL, inc, 31);
-            if ((qn - next) + total > (u32)PR_QCAP) break;  // no room yet: drain first (sL rewritten later, same values)
-            u32 at = qn + inc - (u32)c;
-            for (int d = 1; d <= c; d++) queue[(at + d - 1) & (PR_QCAP - 1)] = (unsigned short)(((u32)t << 4) | (u32)d);
+    unsigned short *plist = s_pairs[w];
+    u32 qn = 0, next = 0;  // items [next, qn) of the ring
+    for (int r = 0; r <= rounds; r++) {
+        if (r < rounds) {
+            const int t = r * 32 + (int)lane;
+            const int L = t < nt ? (int)sL[t] : 0xFF;
+            const u32 cpairs = L == 0xFF ? 0u : (u32)L;
+            const u32 inc = warp_incl_sum(cpairs);
+            const u32 total = __shfl_sync(FULL, inc, 31);
+            const u32 at = qn + inc - cpairs;
+            for (u32 d = 1; d <= cpairs; d++) plist[(at + d - 1u) & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | d);
             qn += total;
-            round++;
             __syncwarp();
         }
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (!active) {
-            u32 idx = next + (u32)__popc(idle & lanemask_lt());
-            bool take = (int)(qn - idx) > 0;
-            if (take) {
-                u32 it = queue[idx & (PR_QCAP - 1)];
-                tx = (int)(it >> 4);
-                ty = tx - (int)(it & 15u);
+        // drain whole warps' worth (everything after the last round); a round adds at most 32 * 15 items, PL_CAP holds that plus a rest
+        while (qn - next >= 32u || (r == rounds && qn != next)) {
+            const u32 idx = next + lane;
+            if ((int)(qn - idx) > 0) {
+                const u32 it = plist[idx & (PL_CAP - 1)];
+                const int tx = (int)(it >> 4), ty = tx - (int)(it & 15u);
                 const int t0 = tx - (int)sL[tx];
-                take = !((sdef[t0 >> 5] >> (t0 & 31)) & 1u);  // the group was given up (stage 4 orders it): its other pairs are moot
-            }
-            if (take) {
-                x = ssa[tx];
-                u32 y = ssa[ty];
-                p = x + (u32)skip;
-                q = y + (u32)skip;
-                lenmin = n32 - (p > q ? p : q);
-                pa = W + (p >> S::LOG_SPW);
-                pb = W + (q >> S::LOG_SPW);
-                sha = (p & (S::SPW - 1u)) * SB;
-                shb = (q & (S::SPW - 1u)) * SB;
-                lo_a = *pa;
-                lo_b = *pb;
-                h = 0;
-                active = true;
-            }
-        }
-        {
-            u32 taken = (u32)__popc(idle), avail = qn - next;
-            next += taken < avail ? taken : avail;
-        }
-        if (!__any_sync(FULL, active)) {
-            if (round >= rounds) break;
-            continue;  // ring empty but slots left: refill
-        }
-        if (active) {
-            u32 a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
-            u32 b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
-            u32 wa0 = __funnelshift_r(lo_a, a1, sha), wb0 = __funnelshift_r(lo_b, b1, shb);
-            u32 wa1 = __funnelshift_r(a1, a2, sha), wb1 = __funnelshift_r(b1, b2, shb);
-            u32 wa2 = __funnelshift_r(a2, a3, sha), wb2 = __funnelshift_r(b2, b3, shb);
-            u32 wa3 = __funnelshift_r(a3, a4, sha), wb3 = __funnelshift_r(b3, b4, shb);
-            u32 d0 = wa0 ^ wb0, d1 = wa1 ^ wb1, d2 = wa2 ^ wb2, d3 = wa3 ^ wb3;
-            bool done = false, x_less = false;
-            u32 match = 0;
-            if (d0 | d1 | d2 | d3) {
-                u32 wsel = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
-                u32 dd = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-                u32 va = d0 ? wa0 : (d1 ? wa1 : (d2 ? wa2 : wa3));
-                u32 vb = d0 ? wb0 : (d1 ? wb1 : (d2 ? wb2 : wb3));
-                u32 bsh = (u32)(__ffs((int)dd) - 1) & ~(u32)(SB - 1);  // bit offset of the first differing symbol
-                u32 at = h + wsel * S::SPW + (bsh >> S::LOG_SB);       // counted from p / q
-                done = true;
-                if (at >= lenmin) {  // the difference lies beyond the end of the shorter suffix
-                    match = lenmin;
-                    x_less = p > q;  // the shorter suffix (larger start) sorts first
-                } else {
-                    match = at;
-                    x_less = ((va >> bsh) & S::MASK) < ((vb >> bsh) & S::MASK);
-                }
-            } else {
-                h += S::STEP;
-                pa += 4;
-                pb += 4;
-                lo_a = a4;
-                lo_b = b4;
-                if (h >= lenmin) {
-                    done = true;
-                    match = lenmin;
-                    x_less = p > q;
-                } else if ((h & 511u) == 0u) {
-                    const int t0 = tx - (int)sL[tx];
-                    if (h >= (u32)SA_CMP_CAP) {  // too long: let the doubling rounds order this group
+                if (!((sdef[t0 >> 5] >> (t0 & 31)) & 1u)) {  // else given up: stage 4 orders this group
+                    const u32 p = ssa[tx], q = ssa[ty];
+                    const u32 x = p < q ? p : q, y = p < q ? q : p;  // positions: x < y
+                    u32 lcp = 0;
+                    bool x_less = false;
+                    if (resolve_pair<SB>(W, n32, etab, x, y, lcp, x_less)) {
+                        const bool p_less = (p == x) == x_less;
+                        const int big = p_less ? ty : tx;  // the larger suffix gains a smaller mate
+                        atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
+                        atomicMax(&lcpv[big], lcp);
+                    } else {  // too long: let the doubling rounds order this group
                         atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
-                        active = false;
-                    } else if ((sdef[t0 >> 5] >> (t0 & 31)) & 1u) {
-                        active = false;  // another pair of the group already gave up
                     }
                 }
             }
-            if (done) {
-                // common prefix, cut at the first '$'/'N' (same characters in both suffixes up to there)
-                u32 lcp = first_barrier(bar0, bar1, x, (u32)skip + match);
-                int big = x_less ? ty : tx;  // the larger suffix gains a smaller mate
-                atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
-                atomicMax(&lcpv[big], (int)lcp);
-                active = false;
-            }
+            next += (qn - next) < 32u ? (qn - next) : 32u;
+            __syncwarp();
         }
     }
     __syncwarp();
@@ -442,7 +532,7 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         u32 suf = ssa[t];
         SA[slot] = (int)suf;
         rank[suf] = (int)slot;
-        if (r > 0) LCP[slot] = lcpv[t];
+        if (r > 0) LCP[slot] = (int)first_barrier(bars, suf, lcpv[t]);  // the reference's '$'/'N' cut (interface.c:107)
         my_f[k] = t0 + (int)r;
         my_suf[k] = suf;
     }
@@ -454,24 +544,24 @@ sa_pairs_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     for (int k = 0; k < PR_ROUNDS; k++)
         if (my_f[k] >= 0) fin[my_f[k]] = my_suf[k];
     __syncwarp();
-    // ---- the first slot of every group: its left neighbour differs inside the k-mer, one short direct comparison.
+    // ---- the first slot of every group: its left neighbour belongs to another group, one short direct comparison.
     //      (The first slot of the chunk has its neighbour in another warp: sa_chunkhead_kernel.) ----
     for (int f = (int)lane; f < nt; f += 32) {
-        if (f == 0 || !((head[f >> 5] >> (f & 31)) & 1u)) continue;
+        if (f == 0 || !((c.head[f >> 5] >> (f & 31)) & 1u)) continue;
         u32 a = fin[f], b = fin[f - 1];
         if (a == 0xFFFFFFFFu) continue;  // stage 4 places the slot and marks the suffix for the LCP pass that follows it
         if (b == 0xFFFFFFFFu) {          // the left neighbour is not known yet: this suffix's LCP entry comes from that pass too
             atomicOr(&needbits[a >> 5], 1u << (a & 31u));
             continue;
         }
-        LCP[s + f] = direct_lcp<SB>(W, n32, a, b, bar0, bar1);
+        LCP[s + f] = direct_lcp<SB>(W, n32, a, b, bars);
     }
 }
 
 // LCP entry of the first slot of every warp chunk of sa_pairs_kernel
 __global__ void __launch_bounds__(256)
-sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, const unsigned char *__restrict__ T, const u32 *__restrict__ bar0,
-                    const u32 *__restrict__ bar1, const int *__restrict__ SA, int *__restrict__ LCP, u32 *__restrict__ needbits) {
+sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, const unsigned char *__restrict__ T, Barriers bars,
+                    const int *__restrict__ SA, int *__restrict__ LCP, u32 *__restrict__ needbits) {
     i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     int j = chunk_start[c];
@@ -487,7 +577,7 @@ sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, con
         atomicOr(&needbits[(u32)p >> 5], 1u << ((u32)p & 31u));
         return;
     }
-    LCP[j] = direct_lcp<8>((const u32 *)T, (u32)n, (u32)p, (u32)q, bar0, bar1);
+    LCP[j] = direct_lcp<8>((const u32 *)T, (u32)n, (u32)p, (u32)q, bars);
 }
 
 // ---- LCP entries of the suffixes stage 4 placed (and of their right neighbours in the suffix array) ----------------------------
@@ -499,8 +589,7 @@ sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, con
 static const int LS_WORDS = 2;
 template <int SB>
 __global__ void __launch_bounds__(128)
-lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict__ W, const u32 *__restrict__ bar0, const u32 *__restrict__ bar1,
-                  const int *__restrict__ SA, const int *__restrict__ ISA, int *__restrict__ LCP) {
+lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict__ W, Barriers bars, const int *__restrict__ SA, const int *__restrict__ ISA, int *__restrict__ LCP) {
     typedef Sym<SB> S;
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 w0 = t * LS_WORDS, nwords = (n + 31) / 32;
@@ -548,7 +637,7 @@ lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict
                 lo_b = b4;
             }
             h += match;
-            LCP[r] = (int)first_barrier(bar0, bar1, (u32)i, h);  // the reference's '$'/'N' cut (interface.c:107) on the way out only
+            LCP[r] = (int)first_barrier(bars, (u32)i, h);  // the reference's '$'/'N' cut (interface.c:107) on the way out only
         }
     }
 }
@@ -716,7 +805,7 @@ size_t sa_workspace_bytes(i64 n) {
     size_t a = (size_t)((n + 63) / 64 * 64);
     i64 tiles = (n + AP_TILE - 1) / AP_TILE;
     // keys x2 (u64), vals x2, pos x2, grp x2 (u32), deferred (u8), tile aggregates, radix scratch, small stuff
-    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + a / 64 + a / 2 + 8192 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
+    return a * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + a / 8 + a / 256 + a / 64 + a / 2 + a * 4 + 65536 + (size_t)tiles * 8 + radix_scratch_bytes(n) + 16 * 256 * 16 + (1 << 16);
 }
 
 struct SaBuffers {
@@ -726,7 +815,8 @@ struct SaBuffers {
     u32 *needbits;     // one bit per text position: LCP entry still missing after the comparison stage (lcp_sparse_kernel)
     int *chunk_start;  // first slot of every warp chunk of sa_pairs_kernel
     u32 *packed;       // 4-bit packed text, n/8 + 16 words
-    u32 *bar, *bar1;  // two-level barrier bitmap: n/32 + 34 words, n/1024 + 2 words
+    u32 *bar, *bar1, *bar2;  // three-level barrier bitmap: n/32 + 98, n/1024 + 8, n/32768 + 8 words
+    u64 *etab;         // sampled-pair table of the comparison stage: (n/16 + 2) buckets of ET_WAYS entries
     void *rscratch;
 };
 
@@ -759,29 +849,42 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
     // text for the comparisons: 4-bit packed codes when the alphabet allows (sigma <= 15), else the raw bytes
     const bool packed = sigma <= 15 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
-    // Equal keys do not promise equal first k symbols (merged classes, "past the end" shares digit 0): the comparisons
-    // start at the suffix itself.
-    const int skip = 0;
+    // (Equal keys do not promise equal first k symbols -- a rare symbol ends the key -- so the comparisons start at the suffix itself.)
     const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
     const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);  // one block past the end: zero padding of the packed text
+    const Barriers bars = {B.bar, B.bar1, B.bar2};
+    RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
+    const int step_syms = packed ? 32 : 16;
+    RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, st.s));
+    RV_TRY(prof_begin(st));
     if (packed) {
-        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
-        RV_TRY(prof_begin(st));
-        RV_LAUNCH((sa_pairs_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)B.packed, B.bar, B.bar1, skip, dSA, dISA, dLCP,
-                  B.deferred, B.small + 257, B.chunk_start, B.needbits);
+        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     } else {
-        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.packed);
-        RV_TRY(prof_begin(st));
-        RV_LAUNCH((sa_pairs_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, (const u32 *)dT, B.bar, B.bar1, skip, dSA, dISA, dLCP,
-                  B.deferred, B.small + 257, B.chunk_start, B.needbits);
+        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
+    }
+    RV_TRY(prof_end(st, RV_PROF_TEXT, 1, (long long)n));
+    const u32 *W = packed ? (const u32 *)B.packed : (const u32 *)dT;
+    RV_TRY(prof_begin(st));
+    if (packed) {
+        RV_LAUNCH((sa_lead_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
+    } else {
+        RV_LAUNCH((sa_lead_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
+    }
+    RV_TRY(prof_end(st, RV_PROF_LEAD, 1, (long long)n * (long long)(sizeof(KeyT) + 4)));
+    RV_TRY(prof_begin(st));
+    if (packed) {
+        RV_LAUNCH((sa_place_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
+                  B.small + 257, B.chunk_start, B.needbits);
+    } else {
+        RV_LAUNCH((sa_place_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
+                  B.small + 257, B.chunk_start, B.needbits);
     }
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
-    st.launches += 2;
+    st.launches += 3;
     {   // the chunk-head LCP pass is enqueued before anyone knows whether stage 4 is needed: slots that stage 4 still has to
         // fill read -1 and the entry is left to lcp_sparse_kernel
         const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
-        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, B.bar, B.bar1, dSA, dLCP,
-                  B.needbits);
+        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, bars, dSA, dLCP, B.needbits);
         st.launches++;
     }
     RV_KCHECK();
@@ -897,7 +1000,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.packed = ws.take<u32>(n / 8 + 300);  // sa_textprep_kernel writes whole 1024-symbol blocks, one block past the end
     B.bar = ws.take<u32>(n / 32 + 98);
     B.bar1 = ws.take<u32>(n / 1024 + 8);
-    if (!B.deferred || !B.needbits || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
+    B.bar2 = ws.take<u32>(n / 32768 + 8);
+    B.etab = ws.take<u64>((size_t)(n / 16 + 2) * ET_WAYS);
+    if (!B.deferred || !B.needbits || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.bar2 || !B.etab || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
         !B.rscratch || !B.small) {
         set_error("sa_build: workspace too small");
         return RV_ERR_NOMEM;
@@ -1031,11 +1136,12 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         // LCP entries of everything stage 4 placed, and of the slots right after such a suffix: Kasai's walk over the marked
         // text positions (a handful for a stray long match, all of them for a text that is one big repeat)
         const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
+        const Barriers bars = {B.bar, B.bar1, B.bar2};
         RV_TRY(prof_begin(st));
         if (packed) {
-            RV_LAUNCH((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, B.bar, B.bar1, dSA, dISA, dLCP);
+            RV_LAUNCH((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, bars, dSA, dISA, dLCP);
         } else {
-            RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)dT, B.bar, B.bar1, dSA, dISA, dLCP);
+            RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
         }
         RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)first_active * 13 + n / 8));
         st.launches++;
@@ -1050,19 +1156,21 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
 int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP) {
     if (n <= 0) return RV_OK;
     const size_t ws_mark = ws.off;
-    u32 *bar = ws.take<u32>(n / 32 + 98), *bar1 = ws.take<u32>(n / 1024 + 8), *needbits = ws.take<u32>(n / 32 + 2);
-    if (!bar || !bar1 || !needbits) {
+    u32 *bar = ws.take<u32>(n / 32 + 98), *bar1 = ws.take<u32>(n / 1024 + 8), *bar2 = ws.take<u32>(n / 32768 + 8), *needbits = ws.take<u32>(n / 32 + 2);
+    if (!bar || !bar1 || !bar2 || !needbits) {
         set_error("lcp_build: workspace too small");
         return RV_ERR_NOMEM;
     }
     CodeTable tab;
     memset(&tab, 0, sizeof tab);
     const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);
-    RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, bar, bar1, (u32 *)nullptr);
+    RV_CUDA(cudaMemsetAsync(bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
+    RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, bar, bar1, bar2, (u32 *)nullptr);
+    const Barriers bars = {bar, bar1, bar2};
     RV_CUDA(cudaMemsetAsync(needbits, 0xff, (size_t)(n / 32 + 2) * 4, st.s));
     const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
     RV_TRY(prof_begin(st));
-    RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bar, bar1, dSA, dISA, dLCP);
+    RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
     RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
     st.launches += 2;
     RV_KCHECK();

@@ -233,6 +233,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, 
     if (d_spec && cap_spec > 0) RV_TRY(sweep_pair_write(st, p, scratch, d_spec, cap_spec));
     RV_CUDA(cudaStreamSynchronize(st.s));
     *count = (i64)h[0];
+    if (st.prof && d_spec && cap_spec > 0) st.prof_bytes[RV_PROF_SWEEP] += (long long)(*count < cap_spec ? *count : cap_spec) * (24 + 13);  // rows written + the slots re-read for them
     return RV_OK;
 }
 
@@ -243,7 +244,8 @@ int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, 
     const u64 *tile_rec = (const u64 *)scratch;
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
     RV_LAUNCH(pair_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_out, cap);
-    RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
+    // the sparse pass reads one hit bit per slot and a tile offset per 1024 slots; the rows it writes are booked by the caller
+    RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)(p.n / 8 + tiles * 8)));
     st.launches++;
     RV_KCHECK();
     return RV_OK;
@@ -268,6 +270,7 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     RV_CUDA(cudaStreamSynchronize(st.s));
     *nrec = (i64)h[0];
     *nmem = (i64)h[1];
+    if (st.prof && d_hdr_spec && hdr_cap_spec > 0 && mem_cap_spec > 0) st.prof_bytes[RV_PROF_SWEEP] += (long long)*nrec * 24 + (long long)*nmem * (16 + 15);
     return RV_OK;
 }
 
@@ -279,7 +282,7 @@ int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr,
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
     RV_LAUNCH(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
               d_mem, mem_cap);
-    RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
+    RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)(p.n / 8 + tiles * 16)));
     st.launches++;
     RV_KCHECK();
     return RV_OK;

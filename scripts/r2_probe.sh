@@ -15,3 +15,7 @@ for w in ${NCU_WORKLOADS:-real repeats}; do
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$w.csv \
     python bench.py --workload $w --steps 1 --warmup 1 --no-cpu > gpurun_out/launches_${w}_run.log 2>&1; echo "ncu launches $w exit $?"
 done
+if [ -n "$NCU_KERNEL" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$NCU_KERNEL -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-1} -f -o gpurun_out/prof_$NCU_KERNEL \
+      python bench.py --workload ${NCU_WORKLOAD:-c2} --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_run.log 2>&1; echo "ncu full exit $?"
+fi
