@@ -486,6 +486,9 @@ def run_ours(args, rank, world, local_rank):
     dev_ms_max, e2e_ms_max, cabi_ms_max = float(tmax[0]), float(tmax[1]), float(tmax[2])
     total_bases = float(ntot[0])
 
+    sharded = None
+    if world > 1 and (args.workload in ("c2", "tiny") or args.rem):
+        sharded = rem_sharded(args.workload, rank, world, dev)
     if rank == 0:
         peak, peak_src = peaks()
         value = total_bases * args.steps / (dev_ms_max * 1e-3)
@@ -527,6 +530,10 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(T, nsep, ns)
             line["rem_configs0"] = rem_configs0()
+            if args.workload in ("c2", "tiny") or args.rem:
+                line["rem_end_to_end"] = rem_end_to_end(args.workload)
+        if world > 1:
+            line["rem_sharded"] = sharded
         emit(line)
     L.rv_index_free(h)
     if world > 1:
@@ -560,6 +567,98 @@ def cpu_baseline(T, nsep, ns):
     tot = time.perf_counter() - t0
     return {"value": n / tot, "unit": "bases/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
             "sample": "the full workload once through the oracle port (SA-IS + Kasai + sweep)", "mums": int(k)}
+
+
+def _write_genome_files(workload, seed, tmp):
+    """FASTA files of a synthetic workload (one per genome, 100 columns), or of the 1a/1b reference pair for 'c1'."""
+    from reveal_b200 import synth
+    g, length, _ = WORKLOADS[workload]
+    files = []
+    for k, seq in enumerate(synth.genomes(g, length, seed=seed)):
+        files.append(os.path.join(tmp, "g%d.fa" % k))
+        text = seq.tobytes().decode()
+        with open(files[-1], "w") as f:
+            f.write(">g%d\n" % k)
+            f.write("\n".join(text[i:i + 100] for i in range(0, len(text), 100)))
+            f.write("\n")
+    return files
+
+
+def _rem_once(files, module, shard=None):
+    """One `rem`: FASTA files -> alignment graph (+ prune for more than two genomes); seconds, aligned bases, where the time went."""
+    from reveal_b200 import rem
+    t0 = time.perf_counter()
+    G, idx = rem.align_genomes(rem.rem_args(files), index_module=module, shard=shard)
+    t1 = time.perf_counter()
+    out = {"align_genomes_s": t1 - t0, "align_stats": module.align_stats() if hasattr(module, "align_stats") else None,
+           "shard_stats": rem.align_genomes.last_shard_stats}
+    if shard is None or shard[0] == 0:
+        if len(G.graph["paths"]) > 2:
+            rem.prune_nodes(G, T=idx.T)
+        bases, total, nodes = rem.aligned_bases(G, idx)
+        out.update({"aligned_bases": bases, "total_bases": total, "aligned_nodes": nodes, "nodes": G.number_of_nodes()})
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+def rem_end_to_end(workload):
+    """First-class secondary figure: `rem` of the bench workload end to end through the driver (FASTA files -> alignment graph,
+    SURVEY 8d(ii)), on the B200 library and -- same driver, same host -- on the reference's own compiled extension (CPU)."""
+    import tempfile
+    try:
+        from reveal_b200 import reveallib
+        with tempfile.TemporaryDirectory() as tmp:
+            files = _write_genome_files(workload, 1, tmp)
+            _rem_once(files, reveallib)   # warm-up of the extension's own handle
+            out = {"workload": "rem " + WORKLOADS[workload][2] + ": FASTA files -> alignment graph", "b200": _rem_once(files, reveallib)}
+            out["b200"]["aligned_bases_per_s"] = out["b200"]["aligned_bases"] / out["b200"]["seconds"]
+            import oracle.ref as R
+            if R.available() and WORKLOADS[workload][0] * WORKLOADS[workload][1] <= 12_000_000:
+                ref = _rem_once(files, R.module(32))
+                ref["aligned_bases_per_s"] = ref["aligned_bases"] / ref["seconds"]
+                out["reference_extension_same_driver"] = ref
+                out["identical_aligned_bases"] = ref["aligned_bases"] == out["b200"]["aligned_bases"] and ref["nodes"] == out["b200"]["nodes"]
+            return out
+    except Exception as e:  # a secondary figure must never cost the bench line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def rem_sharded(workload, rank, world, dev):
+    """STRONG scaling of one alignment (row N1, BASELINE configs[2]/[4]): the same `rem` on 1 GPU (rank 0 alone) and with its
+    recursion sharded over the `world` ranks (reveal_b200.rem.align_genomes(shard=...)): every rank builds the index and runs
+    the tree above the cut, the units below it are shared out, rank 0 collects the graph.  Reports what limits it."""
+    import tempfile
+
+    import torch
+    import torch.distributed as dist
+    from reveal_b200 import reveallib
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            files = _write_genome_files(workload, 1, tmp)
+            one = _rem_once(files, reveallib)     # the whole alignment on 1 GPU: rank 0's run is the one reported, the others' their warm-up
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            mine = _rem_once(files, reveallib, shard=(rank, world))
+            torch.cuda.synchronize()
+            dist.barrier()
+            wall = time.perf_counter() - t0
+            tl = torch.tensor([wall, mine["align_stats"]["total_s"], float(mine["align_stats"]["steps"])], dtype=torch.float64, device=dev)
+            rows = [torch.zeros_like(tl) for _ in range(world)]
+            dist.all_gather(rows, tl)
+            if rank != 0:
+                return None
+            per_rank = [{"rank": r, "wall_s": float(x[0]), "align_s": float(x[1]), "steps": int(x[2])} for r, x in enumerate(rows)]
+            n_wall = max(p["wall_s"] for p in per_rank)
+            return {"workload": "rem " + WORKLOADS[workload][2] + ": ONE alignment, recursion sharded over %d GPUs" % world, "scaling": "strong",
+                    "seconds_1gpu": one["seconds"], "seconds_ngpu": n_wall, "speedup": one["seconds"] / n_wall,
+                    "aligned_bases": mine["aligned_bases"], "aligned_bases_per_s": mine["aligned_bases"] / n_wall,
+                    "identical_to_1gpu": mine["aligned_bases"] == one["aligned_bases"] and mine["nodes"] == one["nodes"] and mine["aligned_nodes"] == one["aligned_nodes"],
+                    "per_rank": per_rank, "rank0_1gpu": one, "rank0_sharded": mine,
+                    "limits": "every rank reads the inputs, builds the root index and runs the tree above the cut (replicated, not divided); "
+                              "the units below the cut divide; rank 0 then unpickles and merges every rank's part of the graph (serial)"}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def rem_configs0():
@@ -619,6 +718,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rem", action="store_true", help="also run `rem` end to end on this workload (default for c2): 1 GPU vs the reference extension, N GPUs sharded")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -114,6 +114,9 @@ int rv_get_sai(rv_index *idx, void *out, int32_t idx_bits);
 int rv_get_lcp(rv_index *idx, void *out, int32_t idx_bits);
 int rv_get_so(rv_index *idx, uint16_t *out);          /* RV_ERR_STATE when nsamples <= 2 (SO is NULL in the reference) */
 int rv_get_text(rv_index *idx, uint8_t *out);         /* T as indexed (after rc) */
+/* Overwrites T[begin .. begin+len) on the device: a rank of a sharded recursion hands the stretches of text it marked (the lower-cased
+ * matched bases, reveal.c:1230-1234) to the rank that collects the alignment. */
+int rv_put_text(rv_index *idx, int64_t begin, const uint8_t *src, int64_t len);
 /* device pointers of the resident arrays (int32 / uint16 / uint8), for callers that stay on the GPU */
 int rv_device_arrays(rv_index *idx, const uint8_t **dT, const int32_t **dSA, const int32_t **dSAi, const int32_t **dLCP, const uint16_t **dSO);
 
@@ -189,8 +192,25 @@ int rv_sub_mums_multi(rv_sub *sub, int32_t minl, int32_t minn, int64_t *nrec, in
 int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
                 int32_t minn, rv_sub **children);
+/* Frontier batching: the sub-indexes waiting on the aligner's queue are independent (reveal.c:1296-1324 pushes up to three per
+ * step; interface.c:316-385 hands them to a worker pool), so every step whose callbacks have run can go to the device together:
+ * the steps whose parent fits one thread block share ONE launch and ONE synchronisation (one block per step), the others take
+ * the general path one after the other.  All parents must belong to one main index; status / children are per step. */
+typedef struct rv_step_desc {
+    rv_sub *parent;
+    const int64_t *lead; int32_t nlead;
+    const int64_t *trail; int32_t ntrail;
+    const int64_t *par; int32_t npar;
+    const int64_t *mum_sp; int32_t mum_n; int64_t mum_l;
+    const int64_t *matching; int32_t nmatch;
+    int32_t sweep[3];      /* in: run the child's MUM sweep in the same launch (leading, trailing, parallel) */
+    rv_sub *children[3];   /* out */
+    int32_t status;        /* out: rv_status of this step */
+} rv_step_desc;
+int rv_sub_step_batch(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn);
 /* steps2[0]/seconds2[0]: recursion steps taken by the single-launch path and their host wall time; [1]: general path */
 int rv_rec_stats(rv_index *idx, int64_t *steps2, double *seconds2);
+int rv_rec_launches(rv_index *idx, int64_t *launches2); /* launches behind those steps: [0] one per batch, [1] general-path calls */
 int rv_sub_fetch(rv_sub *sub, int64_t *rows, int64_t cap_rows, int64_t *members, int64_t cap_members);
 int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                  const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);

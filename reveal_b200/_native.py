@@ -55,6 +55,7 @@ SIGNATURES = {
     "rv_get_lcp": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32]),
     "rv_get_so": (ctypes.c_int, [c_vp, c_vp]),
     "rv_get_text": (ctypes.c_int, [c_vp, c_vp]),
+    "rv_put_text": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_device_arrays": (ctypes.c_int, [c_vp] + [ctypes.POINTER(c_vp)] * 5),
     "rv_mums_pair_count": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_i64p]),
     "rv_mums_pair_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
@@ -73,6 +74,8 @@ SIGNATURES = {
     "rv_sub_step": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32,
                                    ctypes.c_int64, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_vp)]),
     "rv_rec_stats": (ctypes.c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_double)]),
+    "rv_rec_launches": (ctypes.c_int, [c_vp, c_i64p]),
+    "rv_sub_step_batch": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "rv_sub_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_result_pack_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),

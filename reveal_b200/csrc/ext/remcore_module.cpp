@@ -64,6 +64,10 @@ struct Graph {
     PyObject *markers;                            // dict: marker object -> node id
     std::vector<uint32_t> *seen, *mark;           // epoch-stamped visit marks of the walks (no clearing per walk)
     uint32_t epoch;
+    // options of mumpicker(): the default flow of Rem.graphmumpicker as a callable of this object
+    int pk_trim, pk_model;
+    long pk_maxmums, pk_maxdepth;   // maxdepth < 0: none
+    long long pk_wscore, pk_wpen, pk_seedsize;
 };
 
 static int new_node(Graph *g) {
@@ -974,7 +978,96 @@ static PyObject *Graph_stats(Graph *g, PyObject *) {
     return Py_BuildValue("(llll)", alive_n, alive_e, (long)g->nodes->size(), (long)g->edges->size());
 }
 
+// set_picker(trim, maxmums, model, wscore, wpen, seedsize, maxdepth or -1): options of mumpicker()
+static PyObject *Graph_set_picker(Graph *g, PyObject *args) {
+    if (!PyArg_ParseTuple(args, "pliLLLl", &g->pk_trim, &g->pk_maxmums, &g->pk_model, &g->pk_wscore, &g->pk_wpen, &g->pk_seedsize, &g->pk_maxdepth)) return nullptr;
+    Py_RETURN_NONE;
+}
+
+// mumpicker(mums, idx, precomputed=False, minlength=0): the callback index.align() expects (schemes.py:197-361, default options:
+// splitchain="largest", a length threshold, no maxsize) without a Python frame in between -- Rem.graphmumpicker is the readable twin.
+static PyObject *Graph_mumpicker(Graph *g, PyObject *args, PyObject *kwds) {
+    static const char *kwlist[] = {"mums", "idx", "precomputed", "minlength", nullptr};
+    PyObject *mums, *idx, *minlength = nullptr;
+    int precomputed = 0;
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|pO", (char **)kwlist, &mums, &idx, &precomputed, &minlength)) return nullptr;
+    const Py_ssize_t n = PyObject_Length(mums);
+    if (n < 0) return nullptr;
+    if (n == 0) return PyTuple_New(0);
+    if (precomputed) {  // a chain handed down by the parent: split at its middle (schemes.py:346-351)
+        const Py_ssize_t half = n / 2;
+        PyObject *item = PySequence_GetItem(mums, half);
+        if (!item) return nullptr;
+        PyObject *mum = PySequence_GetItem(item, 0);
+        Py_DECREF(item);
+        if (!mum) return nullptr;
+        PyObject *left = PySequence_GetSlice(mums, 0, half), *right = PySequence_GetSlice(mums, half + 1, n);
+        if (!left || !right) { Py_DECREF(mum); Py_XDECREF(left); Py_XDECREF(right); return nullptr; }
+        return Py_BuildValue("(NNN)", mum, left, right);
+    }
+    if (g->pk_maxdepth >= 0) {
+        PyObject *d = PyObject_GetAttrString(idx, "depth");
+        if (!d) return nullptr;
+        const long depth = PyLong_AsLong(d);
+        Py_DECREF(d);
+        if (depth > g->pk_maxdepth) return PyTuple_New(0);
+    }
+    PyObject *ns = PyObject_GetAttrString(idx, "nsamples"), *ln = PyObject_GetAttrString(idx, "leftnode"), *rn = PyObject_GetAttrString(idx, "rightnode");
+    PyObject *ret = nullptr;
+    if (ns && ln && rn) {
+        PyObject *a = Py_BuildValue("(OOOOOlilll)", mums, ns, ln, rn, g->pk_trim ? Py_True : Py_False, g->pk_maxmums, g->pk_model, (long)g->pk_wscore,
+                                    (long)g->pk_wpen, (long)g->pk_seedsize);
+        if (a) {
+            ret = Graph_pick(g, a);
+            Py_DECREF(a);
+        }
+    }
+    Py_XDECREF(ns);
+    Py_XDECREF(ln);
+    Py_XDECREF(rn);
+    return ret;
+}
+
+// graphalign_cb(idx, mum): the second callback of index.align() (rem.py:320-382) on this graph
+static PyObject *Graph_graphalign(Graph *g, PyObject *args);
+static PyObject *Graph_graphalign_cb(Graph *g, PyObject *args) {
+    PyObject *idx, *mum;
+    if (!PyArg_ParseTuple(args, "OO", &idx, &mum)) return nullptr;
+    PyObject *l, *spd;
+    if (!PyTuple_Check(mum) || PyTuple_GET_SIZE(mum) < 3) { PyErr_SetString(PyExc_TypeError, "anchor: (l, n, positions) expected"); return nullptr; }
+    l = PyTuple_GET_ITEM(mum, 0);
+    spd = PyTuple_GET_ITEM(mum, 2);
+    const Py_ssize_t k = PyObject_Length(spd);
+    if (k < 0) return nullptr;
+    PyObject *positions = PyList_New(k);
+    for (Py_ssize_t i = 0; i < k; i++) {
+        PyObject *pr = PySequence_GetItem(spd, i);
+        PyObject *pos = pr ? PySequence_GetItem(pr, 1) : nullptr;
+        Py_XDECREF(pr);
+        if (!pos) { Py_DECREF(positions); return nullptr; }
+        PyList_SET_ITEM(positions, i, pos);
+    }
+    PyObject *nodes = PyObject_GetAttrString(idx, "nodes"), *ln = PyObject_GetAttrString(idx, "leftnode"), *rn = PyObject_GetAttrString(idx, "rightnode");
+    PyObject *ret = nullptr;
+    if (nodes && ln && rn) {
+        PyObject *a = Py_BuildValue("(OOOOO)", nodes, ln, rn, l, positions);
+        if (a) {
+            ret = Graph_graphalign(g, a);
+            Py_DECREF(a);
+        }
+    }
+    Py_XDECREF(nodes);
+    Py_XDECREF(ln);
+    Py_XDECREF(rn);
+    Py_DECREF(positions);
+    return ret;
+}
+
 static PyMethodDef Graph_methods[] = {
+    {"set_picker", (PyCFunction)Graph_set_picker, METH_VARARGS, "set_picker(trim, maxmums, model, wscore, wpen, seedsize, maxdepth or -1): options of mumpicker()"},
+    {"mumpicker", (PyCFunction)(void (*)(void))Graph_mumpicker, METH_VARARGS | METH_KEYWORDS,
+     "mumpicker(mums, idx, precomputed=False, minlength=0) -> () | (anchor, skipleft, skipright): the callback of index.align(), default flow"},
+    {"graphalign_cb", (PyCFunction)Graph_graphalign_cb, METH_VARARGS, "graphalign_cb(idx, mum): the graphalign callback of index.align() on this graph"},
     {"add_node", (PyCFunction)Graph_add_node, METH_VARARGS, "add_node(key, aligned or None, offsets, extra or None)"},
     {"add_edge", (PyCFunction)Graph_add_edge, METH_VARARGS, "add_edge(u, v, ofrom, oto, paths, extra or None)"},
     {"coords", (PyCFunction)Graph_coords, METH_O, "coords(pos) -> ((path id, coordinate), ...) of the real paths through index position pos"},

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -35,9 +36,9 @@
 // ---- the C-ABI, resolved at run time ---------------------------------------------------------------------------------
 #define RV_API_LIST(X)                                                                                                  \
     X(rv_last_error) X(rv_version) X(rv_host_alloc) X(rv_host_free) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
-    X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
+    X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_put_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
     X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_free) X(rv_sub_get)    \
-    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step)
+    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -149,6 +150,7 @@ struct Index {
     rv_sub *sub;                 // device view (children; the root gets one during align)
     Index *mainidx;              // borrowed-with-reference: the root this child belongs to (NULL for a root)
     PyObject *samples, *nodes, *left_node, *right_node, *skipmums;
+    PyObject *shard_units;       // root, after a sharded align(): [(owner rank, nodes of the unit), ...]
 };
 
 static PyTypeObject IndexType = {PyVarObject_HEAD_INIT(nullptr, 0)};
@@ -182,6 +184,7 @@ static PyObject *index_new(PyTypeObject *type, PyObject *, PyObject *) {
     self->samples = PyList_New(0);
     self->nodes = PySet_New(nullptr);
     self->skipmums = PyList_New(0);
+    self->shard_units = PyList_New(0);
     Py_INCREF(Py_None);
     self->left_node = Py_None;
     Py_INCREF(Py_None);
@@ -212,6 +215,7 @@ static void index_dealloc(Index *self) {
     Py_XDECREF(self->left_node);
     Py_XDECREF(self->right_node);
     Py_XDECREF(self->skipmums);
+    Py_XDECREF(self->shard_units);
     Py_XDECREF((PyObject *)self->mainidx);
     Py_TYPE(self)->tp_free((PyObject *)self);
 }
@@ -558,23 +562,68 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
 // wall time of the parts of the last align() (seconds): where a recursion spends its time
 struct AlignStats {
     double extract = 0, pick = 0, galign = 0, parse = 0, step = 0, child = 0, total = 0;
-    long long steps = 0, picks = 0;
+    long long steps = 0, picks = 0, batches = 0;
 };
 static AlignStats g_align_stats;
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// One recursion step whose callbacks have run and whose device part is waiting for the batch launch.
+struct PendingStep {
+    Index *idx = nullptr;                    // owned reference
+    PyObject *pick = nullptr, *result = nullptr;  // owned: keep the borrowed objects below alive
+    PyObject *skipleft = nullptr, *skipright = nullptr, *leading = nullptr, *trailing = nullptr, *rest = nullptr, *newleft = nullptr, *newright = nullptr;
+    std::vector<int64_t> lead, trail, par, match, lead_b, trail_b, par_b, match_b, mum_sp;
+    int64_t leadn = 0, trailn = 0, parn = 0, matchn = 0;
+    long long mum_l = 0;
+    int mum_n = 0;
+    int32_t sweep[3] = {0, 0, 0};
+};
+
+static void release_index_view(Index *idx) {
+    // the device view of a processed sub-index is released right away, like the reference frees SA/LCP
+    if (idx->sub) {
+        g_api.rv_sub_free(idx->sub);
+        idx->sub = nullptr;
+    }
+    Py_DECREF((PyObject *)idx);
+}
+
 static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
-    static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn", nullptr};  // interface.c:303
+    static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn",  // interface.c:303
+                                   "shard_rank", "shard_world", "shard_grain", nullptr};
     PyObject *mumpicker, *graphalign;
-    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0;
+    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 4;
     if (self->mainidx || !self->built) {
         PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
         return nullptr;
     }
-    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiii", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn))
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiiiiii", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn,
+                                     &shard_rank, &shard_world, &shard_grain))
         return nullptr;
-    // `threads` is accepted for signature compatibility: the reference serialises its callback sections on a global
-    // mutex (reveal.c:779-780) and the device work of a step is already parallel; steps run in the reference's LIFO order.
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world || shard_grain < 1) {
+        PyErr_SetString(RevealError, "align: bad shard_rank / shard_world / shard_grain");
+        return nullptr;
+    }
+    // Sharded recursion (one process per GPU, every process holding the same index and the same graph): the sub-indexes of the
+    // recursion are independent, so the tree is cut where its sub-indexes get smaller than n / (shard_grain * shard_world).
+    // Everything above the cut is processed by EVERY rank (same input, same callbacks: same state everywhere, nothing to
+    // exchange); the sub-indexes below it are the units: dealt out by size (largest first to the least loaded rank), and a rank
+    // only descends into its own.  `shard_units` then lists (owner, nodes) of every unit so that the caller can collect the
+    // parts of the graph each rank refined (reveal_b200/rem.py).
+    bool prefix = shard_world > 1;
+    const int64_t unit_max = self->n / ((int64_t)shard_grain * shard_world);
+    std::vector<Index *> units;  // owned references
+    Py_XSETREF(self->shard_units, PyList_New(0));
+    // The reference hands the queue of sub-indexes to `threads` workers (interface.c:338-399), which can only overlap their C
+    // parts: the callback sections are serialised (reveal.c:779-780).  Here the queue's concurrency goes to the device instead:
+    // the sub-indexes on the queue are independent, so their callbacks run one after the other and the device parts of up to
+    // `batch` steps share one launch and one synchronisation (rv_sub_step_batch).  threads <= 1 keeps one step per launch in
+    // the reference's LIFO order; the default (0) and larger values batch.  RV_ALIGN_BATCH overrides the batch size.
+    size_t batch_max = threads == 1 ? 1 : 128;
+    if (const char *e = getenv("RV_ALIGN_BATCH")) {
+        long b = atol(e);
+        if (b >= 1) batch_max = (size_t)b;
+    }
     self->depth = 0;
     if (self->sub) {
         g_api.rv_sub_free(self->sub);
@@ -589,116 +638,186 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     as = AlignStats();
     const double t_begin = now_s();
     PyObject *kw_minl = PyLong_FromLong(minl);
-    std::vector<int64_t> lead, trail, par, match, lead_b, trail_b, par_b, match_b;
+    std::vector<PendingStep *> batch;
+    std::vector<rv_step_desc> descs;
+    for (;;) {
     while (ok && !queue.empty()) {
-        Index *idx = queue.back();  // LIFO (reveal.c:21-26)
-        queue.pop_back();
-        PyObject *pick = nullptr, *result = nullptr, *mums = nullptr;
-        do {
-            if (!PyCallable_Check(mumpicker)) {
-                PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
-                ok = false;
-                break;
+        // ---- callbacks of the sub-indexes on top of the queue (LIFO, reveal.c:21-26), one after the other ----
+        while (ok && !queue.empty() && batch.size() < batch_max) {
+            Index *idx = queue.back();
+            queue.pop_back();
+            if (prefix && idx != self && idx->n <= unit_max) {  // below the cut: a unit, dealt out once the part above the cut is done
+                units.push_back(idx);
+                continue;
             }
-            int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
-            double t0 = now_s(), t1;
-            if (!precomputed) {
-                mums = extract_mums(self, idx->sub, minl, minn);
-                if (!mums) { ok = false; break; }
-                t1 = now_s(); as.extract += t1 - t0; t0 = t1;
+            PyObject *mums = nullptr;
+            PendingStep *ps = new PendingStep();
+            ps->idx = idx;
+            bool staged = false;
+            do {
+                if (!PyCallable_Check(mumpicker)) {
+                    PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
+                    ok = false;
+                    break;
+                }
+                int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
+                double t0 = now_s(), t1;
+                if (!precomputed) {
+                    mums = extract_mums(self, idx->sub, minl, minn);
+                    if (!mums) { ok = false; break; }
+                    t1 = now_s(); as.extract += t1 - t0; t0 = t1;
+                } else {
+                    mums = idx->skipmums;
+                    Py_INCREF(mums);
+                }
+                PyObject *cargs = Py_BuildValue("(OO)", mums, (PyObject *)idx);
+                PyObject *ckw = Py_BuildValue("{s:O,s:O}", "precomputed", precomputed ? Py_True : Py_False, "minlength", kw_minl);
+                ps->pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
+                Py_DECREF(cargs);
+                Py_DECREF(ckw);
+                t1 = now_s(); as.pick += t1 - t0; t0 = t1;
+                as.picks++;
+                if (!ps->pick) { ok = false; break; }
+                if (!PyTuple_Check(ps->pick)) {
+                    PyErr_SetString(RevealError, "**** call to mumpicker failed");
+                    ok = false;
+                    break;
+                }
+                if (PyTuple_Size(ps->pick) == 0) break;  // no more MUMs in this sub-index
+                PyObject *mumobject, *spd;
+                if (!PyArg_ParseTuple(ps->pick, "OOO", &mumobject, &ps->skipleft, &ps->skipright)) { ok = false; break; }
+                if (!PyArg_ParseTuple(mumobject, "LiO", &ps->mum_l, &ps->mum_n, &spd)) { ok = false; break; }
+                ps->mum_sp.assign((size_t)(ps->mum_n > 0 ? ps->mum_n : 1), 0);
+                for (int i = 0; i < ps->mum_n; i++) {
+                    PyObject *tup = PySequence_GetItem(spd, i);
+                    PyObject *pos = tup ? PySequence_GetItem(tup, 1) : nullptr;
+                    ps->mum_sp[(size_t)i] = pos ? PyLong_AsLongLong(pos) : 0;
+                    Py_XDECREF(pos);
+                    Py_XDECREF(tup);
+                }
+                if (PyErr_Occurred()) { ok = false; break; }
+                t0 = now_s();
+                ps->result = PyObject_CallFunctionObjArgs(graphalign, (PyObject *)idx, mumobject, nullptr);  // reveal.c:939
+                t1 = now_s(); as.galign += t1 - t0; t0 = t1;
+                if (!ps->result) { ok = false; break; }
+                if (ps->result == Py_None) break;
+                if (!PyTuple_Check(ps->result)) {
+                    PyErr_SetString(RevealError, "**** call to graphalign failed");
+                    ok = false;
+                    break;
+                }
+                PyObject *matching, *merged;
+                if (!PyArg_ParseTuple(ps->result, "OOOOOOO", &ps->leading, &ps->trailing, &matching, &ps->rest, &merged, &ps->newleft, &ps->newright)) {
+                    PyErr_Clear();  // the reference silently drops an unparsable result (reveal.c:987-999)
+                    break;
+                }
+                if (!parse_intervals(ps->leading, ps->lead, ps->leadn, ps->lead_b) || !parse_intervals(ps->trailing, ps->trail, ps->trailn, ps->trail_b) ||
+                    !parse_intervals(ps->rest, ps->par, ps->parn, ps->par_b) || !parse_intervals(matching, ps->match, ps->matchn, ps->match_b)) {
+                    ok = false;
+                    break;
+                }
+                ps->sweep[0] = PyObject_Length(ps->skipleft) == 0;
+                ps->sweep[1] = PyObject_Length(ps->skipright) == 0;
+                ps->sweep[2] = 1;
+                t1 = now_s(); as.parse += t1 - t0;
+                staged = true;
+            } while (0);
+            Py_XDECREF(mums);
+            if (staged) {
+                batch.push_back(ps);
             } else {
-                mums = idx->skipmums;
-                Py_INCREF(mums);
+                Py_XDECREF(ps->pick);
+                Py_XDECREF(ps->result);
+                release_index_view(idx);
+                delete ps;
             }
-            PyObject *cargs = Py_BuildValue("(OO)", mums, (PyObject *)idx);
-            PyObject *ckw = Py_BuildValue("{s:O,s:O}", "precomputed", precomputed ? Py_True : Py_False, "minlength", kw_minl);
-            pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
-            Py_DECREF(cargs);
-            Py_DECREF(ckw);
-            t1 = now_s(); as.pick += t1 - t0; t0 = t1;
-            as.picks++;
-            if (!pick) { ok = false; break; }
-            if (!PyTuple_Check(pick)) {
-                PyErr_SetString(RevealError, "**** call to mumpicker failed");
-                ok = false;
-                break;
+        }
+        // ---- the device part of every staged step: one call ----
+        if (ok && !batch.empty()) {
+            double t0 = now_s();
+            descs.assign(batch.size(), rv_step_desc());
+            for (size_t i = 0; i < batch.size(); i++) {
+                PendingStep &p = *batch[i];
+                rv_step_desc &d = descs[i];
+                memset(&d, 0, sizeof d);
+                d.parent = p.idx->sub;
+                d.lead = p.lead.data(); d.nlead = (int32_t)p.lead_b.size();
+                d.trail = p.trail.data(); d.ntrail = (int32_t)p.trail_b.size();
+                d.par = p.par.data(); d.npar = (int32_t)p.par_b.size();
+                d.mum_sp = p.mum_sp.data(); d.mum_n = p.mum_n; d.mum_l = p.mum_l;
+                d.matching = p.match.data(); d.nmatch = (int32_t)p.match_b.size();
+                for (int c = 0; c < 3; c++) d.sweep[c] = p.sweep[c];
             }
-            if (PyTuple_Size(pick) == 0) break;  // no more MUMs in this sub-index
-            PyObject *mumobject, *skipleft, *skipright, *spd;
-            if (!PyArg_ParseTuple(pick, "OOO", &mumobject, &skipleft, &skipright)) { ok = false; break; }
-            long long mum_l;
-            int mum_n;
-            if (!PyArg_ParseTuple(mumobject, "LiO", &mum_l, &mum_n, &spd)) { ok = false; break; }
-            std::vector<int64_t> mum_sp((size_t)(mum_n > 0 ? mum_n : 1));
-            for (int i = 0; i < mum_n; i++) {
-                PyObject *tup = PySequence_GetItem(spd, i);
-                PyObject *pos = tup ? PySequence_GetItem(tup, 1) : nullptr;
-                mum_sp[(size_t)i] = pos ? PyLong_AsLongLong(pos) : 0;
-                Py_XDECREF(pos);
-                Py_XDECREF(tup);
-            }
-            if (PyErr_Occurred()) { ok = false; break; }
-            t0 = now_s();
-            result = PyObject_CallFunctionObjArgs(graphalign, (PyObject *)idx, mumobject, nullptr);  // reveal.c:939
-            t1 = now_s(); as.galign += t1 - t0; t0 = t1;
-            if (!result) { ok = false; break; }
-            if (result == Py_None) break;
-            if (!PyTuple_Check(result)) {
-                PyErr_SetString(RevealError, "**** call to graphalign failed");
-                ok = false;
-                break;
-            }
-            PyObject *leading, *trailing, *matching, *rest, *merged, *newleft, *newright;
-            if (!PyArg_ParseTuple(result, "OOOOOOO", &leading, &trailing, &matching, &rest, &merged, &newleft, &newright)) {
-                PyErr_Clear();  // the reference silently drops an unparsable result (reveal.c:987-999)
-                break;
-            }
-            int64_t leadn, trailn, parn, matchn;
-            if (!parse_intervals(leading, lead, leadn, lead_b) || !parse_intervals(trailing, trail, trailn, trail_b) ||
-                !parse_intervals(rest, par, parn, par_b) || !parse_intervals(matching, match, matchn, match_b)) {
-                ok = false;
-                break;
-            }
-            int32_t sweep[3] = {PyObject_Length(skipleft) == 0, PyObject_Length(skipright) == 0, 1};
-            rv_sub *kids[3] = {nullptr, nullptr, nullptr};
             int status;
-            t1 = now_s(); as.parse += t1 - t0; t0 = t1;
             Py_BEGIN_ALLOW_THREADS;
-            status = g_api.rv_sub_step(idx->sub, lead.data(), (int32_t)lead_b.size(), trail.data(), (int32_t)trail_b.size(), par.data(),
-                                       (int32_t)par_b.size(), mum_sp.data(), mum_n, mum_l, match.data(), (int32_t)match_b.size(), sweep, minl, minn, kids);
+            status = g_api.rv_sub_step_batch(descs.data(), (int32_t)descs.size(), minl, minn);
             Py_END_ALLOW_THREADS;
-            t1 = now_s(); as.step += t1 - t0; t0 = t1;
-            as.steps++;
-            if (fail_native(status) != 0) { ok = false; break; }
+            double t1 = now_s(); as.step += t1 - t0; t0 = t1;
+            as.steps += (long long)batch.size();
+            as.batches++;
             self->tdirty = 1;  // matched bases were lower-cased on the device (reveal.c:1230-1234)
-            const int depth = idx->depth + 1;
-            PyObject *empty = PyList_New(0);
-            Index *i_par = kids[2] ? new_child(self, kids[2], parn, depth, count_samples(self, par_b), rest, idx->left_node, idx->right_node, empty) : nullptr;
-            Index *i_lead = kids[0] ? new_child(self, kids[0], leadn, depth, count_samples(self, lead_b), leading, idx->left_node, newright, skipleft) : nullptr;
-            Index *i_trail = kids[1] ? new_child(self, kids[1], trailn, depth, count_samples(self, trail_b), trailing, newleft, idx->right_node, skipright) : nullptr;
-            Py_DECREF(empty);
-            if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
-            if (i_lead) queue.push_back(i_lead);
-            if (i_trail) queue.push_back(i_trail);
+            if (fail_native(status) != 0) {
+                ok = false;
+                for (rv_step_desc &d : descs)   // children of the steps that did succeed
+                    for (int c = 0; c < 3; c++)
+                        if (d.children[c]) g_api.rv_sub_free(d.children[c]);
+            } else {
+                PyObject *empty = PyList_New(0);
+                for (size_t i = 0; i < batch.size(); i++) {
+                    PendingStep &p = *batch[i];
+                    rv_sub **kids = descs[i].children;
+                    const int depth = p.idx->depth + 1;
+                    Index *i_par = kids[2] ? new_child(self, kids[2], p.parn, depth, count_samples(self, p.par_b), p.rest, p.idx->left_node, p.idx->right_node, empty) : nullptr;
+                    Index *i_lead = kids[0] ? new_child(self, kids[0], p.leadn, depth, count_samples(self, p.lead_b), p.leading, p.idx->left_node, p.newright, p.skipleft) : nullptr;
+                    Index *i_trail = kids[1] ? new_child(self, kids[1], p.trailn, depth, count_samples(self, p.trail_b), p.trailing, p.newleft, p.idx->right_node, p.skipright) : nullptr;
+                    if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
+                    if (i_lead) queue.push_back(i_lead);
+                    if (i_trail) queue.push_back(i_trail);
+                }
+                Py_DECREF(empty);
+            }
             as.child += now_s() - t0;
-        } while (0);
-        Py_XDECREF(mums);
-        Py_XDECREF(pick);
-        Py_XDECREF(result);
-        // the device view of a processed sub-index is released right away, like the reference frees SA/LCP
-        if (idx->sub) {
-            g_api.rv_sub_free(idx->sub);
-            idx->sub = nullptr;
         }
-        Py_DECREF((PyObject *)idx);
-    }
-    for (Index *q : queue) {
-        if (q->sub) {
-            g_api.rv_sub_free(q->sub);
-            q->sub = nullptr;
+        for (PendingStep *p : batch) {
+            Py_XDECREF(p->pick);
+            Py_XDECREF(p->result);
+            release_index_view(p->idx);
+            delete p;
         }
-        Py_DECREF((PyObject *)q);
+        batch.clear();
     }
+    if (!ok || !prefix) break;
+    // ---- the part above the cut is done on every rank: deal the units out ----
+    prefix = false;
+    {
+        std::vector<size_t> order(units.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return units[a]->n > units[b]->n; });
+        std::vector<int64_t> load((size_t)shard_world, 0);
+        std::vector<int> owner(units.size(), 0);
+        for (size_t i : order) {
+            int best = 0;
+            for (int r = 1; r < shard_world; r++)
+                if (load[(size_t)r] < load[(size_t)best]) best = r;
+            owner[i] = best;
+            load[(size_t)best] += units[i]->n;
+        }
+        for (size_t i = 0; i < units.size(); i++) {
+            PyObject *nodes = PySequence_Tuple(units[i]->nodes);
+            PyObject *rec = nodes ? Py_BuildValue("(iN)", owner[i], nodes) : nullptr;
+            if (!rec || PyList_Append(self->shard_units, rec) != 0) ok = false;
+            Py_XDECREF(rec);
+        }
+        for (size_t i = units.size(); i-- > 0;) {  // mine go back on the queue (first unit on top), the others are dropped
+            if (ok && owner[i] == shard_rank) queue.push_back(units[i]);
+            else release_index_view(units[i]);
+        }
+        units.clear();
+    }
+    if (!ok) break;
+    }
+    for (Index *q : units) release_index_view(q);
+    for (Index *q : queue) release_index_view(q);
     Py_DECREF(kw_minl);
     as.total = now_s() - t_begin;
     if (!ok) return nullptr;
@@ -707,8 +826,8 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
 
 static PyObject *mod_align_stats(PyObject *, PyObject *) {
     const AlignStats &a = g_align_stats;
-    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:L,s:L}", "total_s", a.total, "sweep_fetch_s", a.extract, "mumpicker_s", a.pick, "graphalign_s", a.galign,
-                         "parse_s", a.parse, "device_step_s", a.step, "children_s", a.child, "steps", a.steps, "mumpicker_calls", a.picks);
+    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:L,s:L,s:L}", "total_s", a.total, "sweep_fetch_s", a.extract, "mumpicker_s", a.pick, "graphalign_s", a.galign,
+                         "parse_s", a.parse, "device_step_s", a.step, "children_s", a.child, "steps", a.steps, "mumpicker_calls", a.picks, "device_batches", a.batches);
 }
 
 // ---- splitindex (reveal.c:1515-1748): one recursion step driven from Python -------------------------------------------------------
@@ -764,6 +883,23 @@ static PyObject *index_splitindex(Index *idx, PyObject *args) {
     out[2] = c ? (PyObject *)c : (Py_INCREF(Py_None), Py_None);
     Py_DECREF(empty);
     return Py_BuildValue("(NNN)", out[0], out[1], out[2]);
+}
+
+// puttext(begin, text): overwrites a stretch of the indexed text (host copy and device) -- used when the parts of a sharded
+// recursion are collected: the owner of a unit sends the stretches whose matched bases it lower-cased.
+static PyObject *index_puttext(Index *self, PyObject *args) {
+    long long begin;
+    const char *txt;
+    Py_ssize_t len;
+    if (!PyArg_ParseTuple(args, "Ls#", &begin, &txt, &len)) return nullptr;
+    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
+    if (begin < 0 || begin + (long long)len > self->n) {
+        PyErr_SetString(RevealError, "puttext: range outside the text");
+        return nullptr;
+    }
+    if (fail_native(g_api.rv_put_text(self->h, begin, (const uint8_t *)txt, (int64_t)len)) != 0) return nullptr;
+    if (!self->tdirty) memcpy(self->T->p + begin, txt, (size_t)len);  // (a dirty host copy is refreshed from the device anyway)
+    Py_RETURN_NONE;
 }
 
 // ---- copy (interface.c:432-470) -----------------------------------------------------------------------------------------------
@@ -860,6 +996,7 @@ static PyObject *get_nodes(Index *self, void *) { Py_INCREF(self->nodes); return
 static PyObject *get_leftnode(Index *self, void *) { Py_INCREF(self->left_node); return self->left_node; }
 static PyObject *get_rightnode(Index *self, void *) { Py_INCREF(self->right_node); return self->right_node; }
 static PyObject *get_skipmums(Index *self, void *) { Py_INCREF(self->skipmums); return self->skipmums; }
+static PyObject *get_shard_units(Index *self, void *) { Py_INCREF(self->shard_units); return self->shard_units; }
 static PyObject *get_nsep(Index *self, void *) {
     Index *r = root_of(self);
     PyObject *lst = PyList_New((Py_ssize_t)r->nsep->size());
@@ -888,6 +1025,7 @@ static PyMethodDef index_methods[] = {
     {"splitindex", (PyCFunction)index_splitindex, METH_VARARGS,
      "splitindex(leading, trailing, matching, rest, merged, newleft, newright, skipleft, skipright) -> (lead, trail, par): one recursion step."},
     {"copy", (PyCFunction)index_copy, METH_NOARGS, nullptr},
+    {"puttext", (PyCFunction)index_puttext, METH_VARARGS, "puttext(begin, text): overwrite a stretch of the indexed text (sharded recursion: collecting the parts)."},
     {"addsample", (PyCFunction)index_addsample, METH_VARARGS, nullptr},
     {"addsequence", (PyCFunction)index_addsequence, METH_VARARGS, nullptr},
     {"construct", (PyCFunction)index_construct, METH_VARARGS | METH_KEYWORDS, nullptr},
@@ -914,6 +1052,7 @@ static PyGetSetDef index_getset[] = {
     {"LCP", (getter)get_LCP, nullptr, "Longest common prefix of consecutive suffixes.", nullptr},
     {"T", (getter)get_T, nullptr, "The concatenation of the input texts.", nullptr},
     {"main", (getter)get_main, nullptr, "The root index.", nullptr},
+    {"shard_units", (getter)get_shard_units, nullptr, "After align(shard_world > 1): [(owner rank, nodes of the unit), ...] of the recursion's cut.", nullptr},
     {nullptr, nullptr, nullptr, nullptr, nullptr}};
 
 // ---- module -------------------------------------------------------------------------------------------------------------------------

@@ -457,6 +457,13 @@ int rv_get_text(rv_index *h, uint8_t *out) {
     RV_CUDA(cudaStreamSynchronize(h->st.s));
     return RV_OK;
 }
+int rv_put_text(rv_index *h, int64_t begin, const uint8_t *src, int64_t len) {
+    RV_TRY(need_built(h));
+    if (!src || begin < 0 || len < 0 || begin + len > h->n) { set_error("rv_put_text: range outside the text"); return RV_ERR_ARG; }
+    if (len) RV_CUDA(cudaMemcpyAsync(h->dT + begin, src, (size_t)len, cudaMemcpyHostToDevice, h->st.s));
+    RV_CUDA(cudaStreamSynchronize(h->st.s));
+    return RV_OK;
+}
 int rv_device_arrays(rv_index *h, const uint8_t **dT, const int32_t **dSA, const int32_t **dSAi, const int32_t **dLCP, const uint16_t **dSO) {
     RV_TRY(need_built(h));
     if (dT) *dT = h->dT;

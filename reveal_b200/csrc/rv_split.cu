@@ -524,7 +524,15 @@ __device__ __forceinline__ void small_sweep(const SmallStepArgs &a, int c, u32 *
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SM_THREADS) small_step_kernel(SmallStepArgs a) {
+// One block per recursion step: block b works on args[b] (a whole frontier of small sub-indexes goes through ONE launch).
+__global__ void __launch_bounds__(SM_THREADS) small_step_kernel(const SmallStepArgs *__restrict__ args) {
+    __shared__ SmallStepArgs a;
+    {
+        const int words = (int)(sizeof(SmallStepArgs) / 4);
+        const u32 *src = (const u32 *)(args + blockIdx.x);
+        for (int i = (int)threadIdx.x; i < words; i += SM_THREADS) ((u32 *)&a)[i] = src[i];
+    }
+    __syncthreads();
     __shared__ unsigned char sD[SM_MAXN];
     __shared__ int s_cand[BB_CAP];
     __shared__ int s_cnt[12];
@@ -674,8 +682,10 @@ struct RecCtx {
     DevPool pool;
     i64 *h_out = nullptr, *d_out = nullptr;
     i64 out_words = 0;
+    SmallStepArgs *h_args = nullptr, *d_args = nullptr;  // host-mapped argument blocks of one batch (SM_BATCH steps)
     // step statistics: [0] single-launch path, [1] general path
     long long steps[2] = {0, 0};
+    long long launches[2] = {0, 0};
     double host_s[2] = {0, 0};
 };
 #include <chrono>
@@ -721,6 +731,7 @@ void rv_pool_destroy(void *pool) {  // called by rv_index_free
     RecCtx *c = (RecCtx *)pool;
     c->pool.destroy();
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_args) cudaFreeHost(c->h_args);
     delete c;
 }
 
@@ -979,25 +990,52 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
     return RV_OK;
 }
 
-// the single-launch path for small parents; *handled = 0 when the step does not qualify
-static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
-                      const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep,
-                      int32_t minl, int32_t minn, rv_sub **children, int *handled) {
+// ---- the single-launch path for small parents, one or many steps per launch -----------------------------------------------------
+static const int SM_BATCH = 256;  // steps per launch at most
+
+struct SmallPrep {   // host side of one step between prepare and collect
+    rv_sub *kids[3] = {nullptr, nullptr, nullptr};
+    i64 cls_n[3] = {0, 0, 0};
+    i64 out_off = 0, out_words = 0;   // this step's share of the host-mapped result buffer
+};
+
+static int small_ctx(MainView &v, RecCtx **out) {
+    RecCtx *ctx = ctx_of(v);
+    if (!ctx->h_out) {
+        const size_t bytes = (size_t)32 << 20;
+        void *hp = nullptr, *dp = nullptr;
+        RV_CUDA(cudaHostAlloc(&hp, bytes, cudaHostAllocMapped));
+        RV_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        ctx->h_out = (i64 *)hp;
+        ctx->d_out = (i64 *)dp;
+        ctx->out_words = (i64)(bytes / 8);
+    }
+    if (!ctx->h_args) {
+        void *hp = nullptr, *dp = nullptr;
+        RV_CUDA(cudaHostAlloc(&hp, sizeof(SmallStepArgs) * SM_BATCH, cudaHostAllocMapped));
+        RV_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        ctx->h_args = (SmallStepArgs *)hp;
+        ctx->d_args = (SmallStepArgs *)dp;
+    }
+    *out = ctx;
+    return RV_OK;
+}
+
+// fills `a` and allocates the children; *handled = 0 when the step does not qualify for the single-block path
+static int small_prepare(const rv_step_desc &d, MainView &v, RecCtx *ctx, int32_t minl, int32_t minn, SmallStepArgs &a, SmallPrep &pp, int *handled) {
     *handled = 0;
-    MainView v;
-    RV_TRY(main_view(parent->main, &v));
+    rv_sub *parent = d.parent;
     const i64 n = parent->n;
     i64 small_maxn = SM_MAXN;
     if (const char *e = getenv("RV_SMALL_MAXN")) {  // test hook: 0 forces the general path
         i64 x = atoll(e);
         if (x < small_maxn) small_maxn = x;
     }
-    if (n <= 0 || n > small_maxn || mum_n > SM_MAXMUM || nmatch > SM_MAXMUM || mum_l <= 0) return RV_OK;
-    SmallStepArgs a;
+    if (n <= 0 || n > small_maxn || d.mum_n > SM_MAXMUM || d.nmatch > SM_MAXMUM || d.mum_l <= 0) return RV_OK;
     memset(&a, 0, sizeof a);
-    i64 total = 0, cls_n[3] = {0, 0, 0};
-    const int64_t *src[3] = {lead, trail, par};
-    const int32_t cnts[3] = {nlead, ntrail, npar};
+    i64 total = 0;
+    const int64_t *src[3] = {d.lead, d.trail, d.par};
+    const int32_t cnts[3] = {d.nlead, d.ntrail, d.npar};
     const unsigned char labels[3] = {1, 2, 4};
     int m1 = 0;
     for (int c = 0; c < 3; c++)
@@ -1011,38 +1049,30 @@ static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const 
             a.lab[m1] = labels[c];
             m1++;
             total += e - b;
-            cls_n[c] += e - b;
+            pp.cls_n[c] += e - b;
         }
-    for (int k = 0; k < mum_n; k++) {
-        if (mum_sp[k] < 0 || mum_sp[k] + mum_l > v.n) { set_error("rv_sub_step: mum out of range"); return RV_ERR_ARG; }
-        a.mbeg[k] = mum_sp[k];
+    for (int k = 0; k < d.mum_n; k++) {
+        if (d.mum_sp[k] < 0 || d.mum_sp[k] + d.mum_l > v.n) { set_error("rv_sub_step: mum out of range"); return RV_ERR_ARG; }
+        a.mbeg[k] = d.mum_sp[k];
     }
-    for (int k = 0; k < nmatch; k++) a.bbeg[k] = matching[2 * k];
-    RecCtx *ctx = ctx_of(v);
-    if (!ctx->h_out) {
-        const size_t bytes = (size_t)8 << 20;
-        void *hp = nullptr, *dp = nullptr;
-        RV_CUDA(cudaHostAlloc(&hp, bytes, cudaHostAllocMapped));
-        RV_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
-        ctx->h_out = (i64 *)hp;
-        ctx->d_out = (i64 *)dp;
-        ctx->out_words = (i64)(bytes / 8);
-    }
+    for (int k = 0; k < d.nmatch; k++) a.bbeg[k] = d.matching[2 * k];
     DevPool *pool = &ctx->pool;
-    rv_sub *kids[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < 3; c++)
-        if (cls_n[c] > 0) {
+        if (pp.cls_n[c] > 0) {
             rv_sub *k = new rv_sub();
             k->main = parent->main;
-            k->n = cls_n[c];
+            k->n = pp.cls_n[c];
             k->owns = true;
+            pp.kids[c] = k;
             void *p1 = nullptr, *p2 = nullptr;
-            int r1 = pool->take((size_t)(cls_n[c] + 2) * 4, &p1);
-            int r2 = r1 == RV_OK ? pool->take((size_t)(cls_n[c] + 2) * 4, &p2) : r1;
-            if (r1 != RV_OK || r2 != RV_OK) { delete k; return RV_ERR_NOMEM; }
+            int r1 = pool->take((size_t)(pp.cls_n[c] + 2) * 4, &p1);
             k->SA = (int *)p1;
+            int r2 = r1 == RV_OK ? pool->take((size_t)(pp.cls_n[c] + 2) * 4, &p2) : r1;
             k->LCP = (int *)p2;
-            kids[c] = k;
+            if (r1 != RV_OK || r2 != RV_OK) {
+                for (int q = 0; q < 3; q++) { rv_sub_free(pp.kids[q]); pp.kids[q] = nullptr; }
+                return RV_ERR_NOMEM;
+            }
         }
     a.T = v.T;
     a.SAi = v.ISA;
@@ -1058,32 +1088,31 @@ static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const 
     a.n = (int)n;
     a.m1 = m1;
     a.total1 = total;
-    a.m2 = mum_n;
-    a.mum_l = mum_l;
-    a.nb = nmatch;
+    a.m2 = d.mum_n;
+    a.mum_l = d.mum_l;
+    a.nb = d.nmatch;
     for (int c = 0; c < 3; c++) {
-        a.cSA[c] = kids[c] ? kids[c]->SA : nullptr;
-        a.cLCP[c] = kids[c] ? kids[c]->LCP : nullptr;
-        a.cn[c] = (int)cls_n[c];
-        a.do_sweep[c] = (sweep && sweep[c]) ? 1 : 0;
+        a.cSA[c] = pp.kids[c] ? pp.kids[c]->SA : nullptr;
+        a.cLCP[c] = pp.kids[c] ? pp.kids[c]->LCP : nullptr;
+        a.cn[c] = (int)pp.cls_n[c];
+        a.do_sweep[c] = d.sweep[c] ? 1 : 0;
     }
-    a.out = ctx->d_out;
-    a.out_words = ctx->out_words;
-    Stream &st = *v.st;
-    RV_LAUNCH(small_step_kernel, 1, SM_THREADS, 0, st.s, a);
-    st.launches++;
-    RV_CUDA(cudaStreamSynchronize(st.s));
-    RV_KCHECK();
-    const i64 *o = ctx->h_out;
+    *handled = 1;
+    return RV_OK;
+}
+
+// after the launch + synchronisation: checks the class counts, hands the children (with their stored sweep results) over
+static int small_collect(rv_step_desc &d, RecCtx *ctx, const SmallPrep &pp, int32_t minl, int32_t minn) {
+    const i64 *o = ctx->h_out + pp.out_off;
     for (int c = 0; c < 3; c++)
-        if (o[12 + c] != cls_n[c]) {
+        if (o[12 + c] != pp.cls_n[c]) {
             set_error("rv_sub_step: class %d has %lld suffixes in the parent but the intervals cover %lld positions", c, (long long)o[12 + c],
-                      (long long)cls_n[c]);
-            for (int q = 0; q < 3; q++) rv_sub_free(kids[q]);
+                      (long long)pp.cls_n[c]);
+            for (int q = 0; q < 3; q++) rv_sub_free(pp.kids[q]);
             return RV_ERR_ARG;
         }
     for (int c = 0; c < 3; c++) {
-        rv_sub *k = kids[c];
+        rv_sub *k = pp.kids[c];
         if (!k) continue;
         const i64 nr = o[4 * c + 0], nm = o[4 * c + 1], off = o[4 * c + 2];
         if (off >= 0) {  // swept and it fitted
@@ -1093,31 +1122,111 @@ static int step_small(rv_sub *parent, const int64_t *lead, int32_t nlead, const 
             k->cminl = minl;
             k->cminn = minn;
         }
-        children[c] = k;
+        d.children[c] = k;
     }
-    *handled = 1;
     return RV_OK;
+}
+
+static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
+                         const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);
+
+// Recursion steps of one main index, as many as the caller has ready (a frontier of independent sub-indexes, reveal.c:1296-1324
+// pushes up to three per step): the steps whose parent fits a thread block go through ONE launch and ONE synchronisation, one
+// block per step; the others take the general path one after the other.  Every step reports its own status.
+int rv_sub_step_batch(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn) {
+    if (!steps || nsteps < 0) return RV_ERR_ARG;
+    if (nsteps == 0) return RV_OK;
+    for (int i = 0; i < nsteps; i++) {
+        if (!steps[i].parent || steps[i].parent->main != steps[0].parent->main) { set_error("rv_sub_step_batch: steps of different indexes"); return RV_ERR_ARG; }
+        steps[i].children[0] = steps[i].children[1] = steps[i].children[2] = nullptr;
+        steps[i].status = RV_OK;
+    }
+    MainView v;
+    RV_TRY(main_view(steps[0].parent->main, &v));
+    RecCtx *ctx = nullptr;
+    RV_TRY(small_ctx(v, &ctx));
+    Stream &st = *v.st;
+    int worst = RV_OK;
+    std::vector<int> general;
+    for (int base = 0; base < nsteps;) {
+        // ---- one launch: the next run of (at most SM_BATCH) steps ----
+        const double t0 = now_s();
+        std::vector<SmallPrep> prep;
+        std::vector<int> which;
+        int i = base;
+        for (; i < nsteps && (int)which.size() < SM_BATCH; i++) {
+            SmallPrep pp;
+            int handled = 0;
+            int r = small_prepare(steps[i], v, ctx, minl, minn, ctx->h_args[which.size()], pp, &handled);
+            if (r != RV_OK) {
+                steps[i].status = r;
+                worst = r;
+                continue;
+            }
+            if (!handled) {
+                general.push_back(i);
+                continue;
+            }
+            which.push_back(i);
+            prep.push_back(pp);
+        }
+        base = i;
+        const int m = (int)which.size();
+        if (m > 0) {
+            // every step gets an equal share of the host-mapped result buffer (a child whose MUMs do not fit is swept again later)
+            const i64 share = (ctx->out_words / m) & ~(i64)7;
+            for (int k = 0; k < m; k++) {
+                prep[k].out_off = share * k;
+                prep[k].out_words = share;
+                ctx->h_args[k].out = ctx->d_out + share * k;
+                ctx->h_args[k].out_words = share;
+            }
+            RV_LAUNCH(small_step_kernel, (unsigned)m, SM_THREADS, 0, st.s, (const SmallStepArgs *)ctx->d_args);
+            st.launches++;
+            RV_CUDA(cudaStreamSynchronize(st.s));
+            RV_KCHECK();
+            for (int k = 0; k < m; k++) {
+                int r = small_collect(steps[which[k]], ctx, prep[k], minl, minn);
+                if (r != RV_OK) {
+                    steps[which[k]].status = r;
+                    worst = r;
+                }
+            }
+            ctx->steps[0] += m;
+            ctx->launches[0]++;
+            ctx->host_s[0] += now_s() - t0;
+        }
+    }
+    for (int i : general) {
+        const double t0 = now_s();
+        rv_step_desc &d = steps[i];
+        int r = split_general(d.parent, d.lead, d.nlead, d.trail, d.ntrail, d.par, d.npar, d.mum_sp, d.mum_n, d.mum_l, d.matching, d.nmatch, d.children);
+        if (r != RV_OK) {
+            d.status = r;
+            worst = r;
+        }
+        ctx->steps[1]++;
+        ctx->launches[1]++;
+        ctx->host_s[1] += now_s() - t0;
+    }
+    return worst;
 }
 
 int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
                 int32_t minn, rv_sub **children) {
     if (!parent || !children) return RV_ERR_ARG;
-    children[0] = children[1] = children[2] = nullptr;
-    int handled = 0;
-    MainView v;
-    RV_TRY(main_view(parent->main, &v));
-    RecCtx *ctx = ctx_of(v);
-    double t0 = now_s();
-    RV_TRY(step_small(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, sweep, minl, minn, children, &handled));
-    if (handled) {
-        ctx->steps[0]++;
-        ctx->host_s[0] += now_s() - t0;
-        return RV_OK;
-    }
-    int r = split_general(parent, lead, nlead, trail, ntrail, par, npar, mum_sp, mum_n, mum_l, matching, nmatch, children);
-    ctx->steps[1]++;
-    ctx->host_s[1] += now_s() - t0;
+    rv_step_desc d;
+    memset(&d, 0, sizeof d);
+    d.parent = parent;
+    d.lead = lead; d.nlead = nlead;
+    d.trail = trail; d.ntrail = ntrail;
+    d.par = par; d.npar = npar;
+    d.mum_sp = mum_sp; d.mum_n = mum_n; d.mum_l = mum_l;
+    d.matching = matching; d.nmatch = nmatch;
+    for (int c = 0; c < 3; c++) d.sweep[c] = sweep ? sweep[c] : 0;
+    int r = rv_sub_step_batch(&d, 1, minl, minn);
+    for (int c = 0; c < 3; c++) children[c] = d.children[c];
     return r;
 }
 
@@ -1135,6 +1244,17 @@ int rv_rec_stats(rv_index *h, int64_t *steps2, double *seconds2) {
         if (steps2) steps2[k] = ctx->steps[k];
         if (seconds2) seconds2[k] = ctx->host_s[k];
     }
+    return RV_OK;
+}
+
+// kernel launches behind those steps: [0] single-launch path (one launch serves a whole batch), [1] general path (calls)
+int rv_rec_launches(rv_index *h, int64_t *launches2) {
+    MainView v;
+    RV_TRY(main_view(h, &v));
+    RecCtx *ctx = ctx_of(v);
+    if (!launches2) return RV_ERR_ARG;
+    launches2[0] = ctx->launches[0];
+    launches2[1] = ctx->launches[1];
     return RV_OK;
 }
 

@@ -225,6 +225,8 @@ class Rem(object):
         self._all_real = None
         self._coords = {}                  # index position -> ((path id, coordinate in that path), ...), see _lookup
         self.core = None                   # remcore.Graph while the recursion runs (see recursion_graph)
+        self.shard = None                  # (rank, world, process group, index) of a sharded recursion, see align_genomes(shard=...)
+        self.shard_stats = None
         for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict)):
             self.G.graph.setdefault(key, empty())
 
@@ -428,9 +430,67 @@ class Rem(object):
             if was_on:
                 gc.enable()
 
+    def _collect_shards(self, nodes, edges):
+        """Sharded recursion (index.align(shard_rank=, shard_world=)): every rank processed the tree above the cut and its own
+        units below it, so its graph is final for the nodes of its units and stale for the units of the others.  The owners
+        send their parts -- node rows, the edge rows touching them, the marked stretches of text -- to rank 0 (one gather of
+        pickled rows: NCCL moves the bytes between GPUs, gloo in the CPU tests), which swaps them in.  Returns the merged rows
+        on rank 0 and the rank's own (partly stale) rows elsewhere."""
+        import bisect
+        import time
+
+        import torch.distributed as dist
+        rank, world, group, idx = self.shard
+        t0 = time.perf_counter()
+        spans = sorted((b, e, owner) for owner, unit in idx.shard_units for b, e in unit)
+        begins = [b for b, _, _ in spans]
+
+        def owner_of(key):
+            if isinstance(key, str):
+                return None
+            i = bisect.bisect_right(begins, key.begin) - 1
+            if i >= 0 and key.begin < spans[i][1]:
+                return spans[i][2]
+            return None
+
+        who = {key: owner_of(key) for key, _ in nodes}
+        T = idx.T
+        markers = [k for k, _ in nodes if isinstance(k, str)]   # start / end markers: random names, same creation order on every rank
+        mine = ([(k, a) for k, a in nodes if who[k] == rank],
+                [(u, v, a) for u, v, a in edges if who.get(u) == rank or who.get(v) == rank],
+                [(b, T[b:e]) for b, e, owner in spans if owner == rank], markers)
+        parts = [None] * world if rank == 0 else None
+        t1 = time.perf_counter()
+        dist.gather_object(mine if rank != 0 else None, parts, dst=0, group=group)
+        t2 = time.perf_counter()
+        self.shard_stats = {"units": len(idx.shard_units), "own_units": sum(1 for o, _ in idx.shard_units if o == rank),
+                            "own_nodes": len(mine[0]), "pack_s": t1 - t0, "gather_s": t2 - t1}
+        if rank != 0:
+            return nodes, edges
+        foreign = {k for k, o in who.items() if o is not None and o != 0}
+        out_nodes = [(k, a) for k, a in nodes if k not in foreign]
+        out_edges = [(u, v, a) for u, v, a in edges if u not in foreign and v not in foreign]
+        for r in range(1, world):
+            pn, pe, pt, their_markers = parts[r]
+            if len(their_markers) != len(markers):
+                raise RuntimeError("sharded recursion: rank %d read other inputs than rank 0" % r)
+            name = dict(zip(their_markers, markers))
+            out_nodes.extend(pn)
+            out_edges.extend((name.get(u, u) if isinstance(u, str) else u, name.get(v, v) if isinstance(v, str) else v, a) for u, v, a in pe)
+            for b, text in pt:
+                idx.puttext(b, text)
+        known = {k for k, _ in out_nodes}
+        for u, v, _ in out_edges:
+            if u not in known or v not in known:
+                raise RuntimeError("sharded recursion: an edge joins the units of two ranks (%r -> %r); align this input unsharded" % (u, v))
+        self.shard_stats["merge_s"] = time.perf_counter() - t2
+        return out_nodes, out_edges
+
     def _rebuild_from(self, core):
         G = self.G
         nodes, edges = core.export()   # [(node, attributes)], [(u, v, attributes)], attribute dicts freshly made
+        if self.shard is not None:
+            nodes, edges = self._collect_shards(nodes, edges)
         keep = dict(G.graph)
         G.clear()
         G.graph.update(keep)
@@ -625,6 +685,20 @@ class Rem(object):
         return leading, trailing, nodes - (leading | trailing)
 
     # ---- callback 2: graphalign(index, mum) (rem.py:317-382) --------------------------------
+    def callbacks(self, minlength):
+        """(mumpicker, graphalign) for index.align().  With the graph in C++ and the default options (splitchain="largest", a length
+        threshold, no maxsize) both are methods of remcore.Graph -- index.align() then runs a whole recursion without entering
+        a Python frame; otherwise the methods of this object, which are their readable twins."""
+        args = self.args
+        core = self.core
+        native = (core is not None and hasattr(core, "mumpicker") and args.splitchain == "largest" and minlength != 0
+                  and args.gcmodel in _MODELS and args.maxsize is None and os.environ.get("RV_REM_PYTHON_PICK", "0") in ("", "0"))
+        if not native:
+            return self.graphmumpicker, self.graphalign
+        core.set_picker(bool(args.trim), int(args.maxmums), _MODELS[args.gcmodel], int(args.wscore), int(args.wpen), int(args.seedsize),
+                        -1 if args.maxdepth is None else int(args.maxdepth))
+        return core.mumpicker, core.graphalign_cb
+
     def graphalign(self, index, mum):
         try:
             l, n, spd = mum
@@ -886,9 +960,14 @@ def _index_module(sa64=False):
     return reveallib64 if sa64 else reveallib
 
 
-def align_genomes(args, index_module=None):
+def align_genomes(args, index_module=None, shard=None):
     """FASTA and GFA files -> (alignment graph, index) (rem.py:511-611).  `args`: see rem_args; `index_module` lets tests
-    run the driver on another build of the drop-in extension."""
+    run the driver on another build of the drop-in extension.
+
+    shard = (rank, world[, process group]): ONE alignment over the `world` processes of a torch.distributed job (one per GPU).
+    Every rank reads the same inputs and builds the same index; the recursion is cut into units that the ranks share out
+    (index.align(shard_rank=, shard_world=)); rank 0 returns the complete graph, the other ranks a graph that is only final
+    for their own units.  Needs the graph in C++ (remcore) and this repository's extension."""
     mod = index_module if index_module is not None else _index_module(args.sa64)
     idx = mod.index(sa=args.sa, lcp=args.lcp, cache=args.cache)
     rem = Rem(args)
@@ -901,8 +980,16 @@ def align_genomes(args, index_module=None):
         raise ValueError("Specify at least 2 targets to construct alignment. In case of multi-fasta, consider contigs=False.")
     idx.construct()
     with rem.recursion_graph():
-        idx.align(rem.graphmumpicker, rem.graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength,
-                  minn=args.minn)
+        mumpicker, graphalign = rem.callbacks(args.minlength)
+        if shard is not None and shard[1] > 1:
+            if rem.core is None:
+                raise RuntimeError("a sharded recursion needs the compiled graph (reveal_b200.remcore)")
+            rem.shard = (int(shard[0]), int(shard[1]), shard[2] if len(shard) > 2 else None, idx)
+            idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn,
+                      shard_rank=rem.shard[0], shard_world=rem.shard[1])
+        else:
+            idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn)
+    align_genomes.last_shard_stats = rem.shard_stats
     return rem.G, idx
 
 
@@ -935,7 +1022,8 @@ def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targe
             G.add_edge(node, last, paths={sid}, ofrom="+", oto="+")
     idx.construct()
     with rem.recursion_graph():
-        idx.align(rem.graphmumpicker, rem.graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
+        mumpicker, graphalign = rem.callbacks(minlength)
+        idx.align(mumpicker, graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
     rem.prune_nodes(T=idx.T)
     G.remove_node(first)
     G.remove_node(last)

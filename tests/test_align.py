@@ -22,7 +22,9 @@ def run_reference(samples, minl, minn, maxsteps=None):
     return log, idx.T[:idx.n]
 
 
-def run_ours(reveallib, samples, minl, minn, maxsteps=None):
+def run_ours(reveallib, samples, minl, minn, maxsteps=None, threads=1):
+    """threads=1: one step per launch in the reference's LIFO order; threads=0 (the default of the drop-in): frontier batching --
+    the device parts of the steps waiting on the queue share one launch, so the sub-indexes are visited in another order."""
     log = []
     idx = reveallib.index()
     for k, seqs in enumerate(samples):
@@ -31,16 +33,33 @@ def run_ours(reveallib, samples, minl, minn, maxsteps=None):
             idx.addsequence(s if isinstance(s, str) else bytes(s).decode("ascii"))
     idx.construct()
     mp, ga = make_callbacks(log, minlen=minl, maxsteps=maxsteps)
-    idx.align(mp, ga, threads=0, minl=minl, minn=minn)
+    idx.align(mp, ga, threads=threads, minl=minl, minn=minn)
     return log, idx.T
 
 
-def compare(a, b):
+def per_subindex(log):
+    """The log as one record per visited sub-index: its pick event and, if a MUM was chosen, the align event that follows it."""
+    out = []
+    for e in log:
+        if e[0] == "pick":
+            out.append([e, None])
+        else:
+            out[-1][1] = e
+    return sorted((repr(p), repr(a)) for p, a in out)
+
+
+def compare(a, b, ordered=True):
+    """ordered: the very same sequence of callback events; else the same SET of visited sub-indexes (every one with the same MUM
+    list, choice and children) in any order -- what frontier batching promises, like the reference's own worker threads."""
     la, ta = a
     lb, tb = b
     assert len(la) == len(lb), "number of callback events differs: %d vs %d" % (len(la), len(lb))
-    for k, (x, y) in enumerate(zip(la, lb)):
-        assert x == y, "event %d differs:\n ref  %s\n ours %s" % (k, str(x)[:600], str(y)[:600])
+    if ordered:
+        for k, (x, y) in enumerate(zip(la, lb)):
+            assert x == y, "event %d differs:\n ref  %s\n ours %s" % (k, str(x)[:600], str(y)[:600])
+    else:
+        for k, (x, y) in enumerate(zip(per_subindex(la), per_subindex(lb))):
+            assert x == y, "sub-index record %d differs:\n ref  %s\n ours %s" % (k, str(x)[:600], str(y)[:600])
     assert ta == tb
     return len([e for e in la if e[0] == "align"])
 
@@ -61,8 +80,10 @@ def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma
         pytest.skip("the ctypes twin runs a subset (suite time); the device code is the same")
     rng = np.random.default_rng(len(name) * 100 + length)
     samples = random_related(rng, ns, length, sigma, snp=0.03)
-    steps = compare(run_reference(samples, minl, minn), run_ours(emu_reveallib, samples, minl, minn))
+    ref = run_reference(samples, minl, minn)
+    steps = compare(ref, run_ours(emu_reveallib, samples, minl, minn, threads=1))
     assert steps > 3
+    assert compare(ref, run_ours(emu_reveallib, samples, minl, minn, threads=0), ordered=False) == steps   # batched frontier
 
 
 @needs_ref
@@ -94,8 +115,11 @@ def test_align_matches_reference_cuda(ns, length, minl, minn, maxsteps):
     from reveal_b200 import reveallib, synth
     gs = synth.genomes(ns, length, seed=9, snp=0.01, indel=0.001)
     samples = [[g.tobytes()] for g in gs]
-    steps = compare(run_reference(samples, minl, minn, maxsteps), run_ours(reveallib, samples, minl, minn, maxsteps))
+    ref = run_reference(samples, minl, minn, maxsteps)
+    steps = compare(ref, run_ours(reveallib, samples, minl, minn, maxsteps, threads=1))
     assert steps > 10
+    if maxsteps is None:  # (a step budget makes the outcome depend on the visiting order)
+        assert compare(ref, run_ours(reveallib, samples, minl, minn, None, threads=0), ordered=False) == steps   # batched frontier
 
 
 def test_align_callback_failure_is_reported_and_leaves_no_wreckage(emu_reveallib):

@@ -45,7 +45,7 @@ def case_files(gold, tmp_path):
     return files
 
 
-def run_case(name, tmp_path, index_module):
+def run_case(name, tmp_path, index_module, shard=None):
     gold = load(name)
     if "align" in gold:  # the library entry on (name, sequence) tuples
         ng, length, seed = gold["align"]
@@ -54,7 +54,9 @@ def run_case(name, tmp_path, index_module):
         T = idx.T
     else:
         args = rem.rem_args(case_files(gold, tmp_path), **gold["args"])
-        G, idx = rem.align_genomes(args, index_module=index_module)
+        G, idx = rem.align_genomes(args, index_module=index_module, shard=shard)
+        if shard is not None and shard[0] != 0:
+            return G, idx   # only rank 0 holds the complete graph of a sharded recursion
         T = idx.T
         if len(G.graph["paths"]) > 2:
             rem.prune_nodes(G, T=T)
@@ -428,3 +430,68 @@ def test_rem_gzipped_input_and_output(tmp_path):
         f.write(">extra\n%s\n" % synth.genomes(1, 3000, seed=22)[0].tobytes().decode())
     G2, idx2 = rem.align_genomes(rem.rem_args([out, extra], minlength=10), index_module=R.module(32))
     assert len(G2.graph["paths"]) == 4 and rem.aligned_bases(G2, idx2)[0] > 0
+
+
+# ---- sharded recursion: ONE alignment over the ranks of a torch.distributed job ----------------------------
+def _shard_worker(rank, world, port, q, names, emu_path, tmp):
+    """One rank: the same inputs, the same index, its own share of the recursion's units; rank 0 checks the collected graph
+    against the golden one (the very graph the unsharded reference driver produced)."""
+    import pathlib
+    import traceback
+
+    import torch.distributed as dist
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from reveal_b200 import reveallib
+        if emu_path:
+            reveallib._load(emu_path)   # the emulated kernels stand in for the GPUs (REVEAL_B200_TEST_HOOKS=1 from conftest)
+        out = []
+        for name in names:
+            d = pathlib.Path(tmp) / ("%s_r%d" % (name, rank))
+            d.mkdir()
+            G, idx = run_case(name, d, reveallib, shard=(rank, world))
+            units = idx.shard_units
+            out.append((name, len(units), sorted({o for o, _ in units}), rem.align_genomes.last_shard_stats["own_nodes"]))
+        dist.barrier()
+        q.put((rank, "ok", out))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, "error", traceback.format_exc()))
+
+
+def _run_sharded(names, emu_path, tmp_path, world=2):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 400
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q, names, emu_path, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=900) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    for rank, status, payload in res:
+        assert status == "ok", "rank %d:\n%s" % (rank, payload)
+    return res
+
+
+def test_rem_sharded_recursion_world2_gloo(emu_lib, tmp_path):
+    """Two ranks (gloo, emulated kernels) share ONE alignment: every rank runs the tree above the cut, the units below it are dealt
+    out, rank 0 collects the refined parts -- and holds exactly the golden graph of the unsharded reference driver."""
+    emu_path = os.path.join(HERE, "emu", "_build", "libreveal_emu.so")
+    res = _run_sharded(["synth2_4k", "synth3_3k", "synth4_2k_seed"], emu_path, tmp_path)
+    for rank, _, cases in res:
+        for name, nunits, owners, own_nodes in cases:
+            assert nunits >= 2 and owners == [0, 1], (name, nunits, owners)   # the cut produced units for both ranks
+            assert own_nodes > 0
+
+
+@pytest.mark.gpu
+def test_rem_sharded_recursion_two_ranks_one_gpu(tmp_path):
+    """The same on the CUDA library: two processes share GPU 0 (the test box has one GPU); graphs of up to 5 x 30 kbp."""
+    res = _run_sharded(["synth2_200k", "synth3_60k", "synth5_30k_n3", "1a_1b"], None, tmp_path)
+    for rank, _, cases in res:
+        for name, nunits, owners, own_nodes in cases:
+            assert owners == [0, 1], (name, nunits, owners)
