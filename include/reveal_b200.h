@@ -215,6 +215,25 @@ int rv_sub_fetch(rv_sub *sub, int64_t *rows, int64_t cap_rows, int64_t *members,
 int rv_sub_split(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                  const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, rv_sub **children);
 
+/* ---- chaining on the device (the step right after MUM extraction) ------------------------------------
+ * The O(m^2) chaining recurrence of the mumpicker (reveal/schemes.py:20-104 `chain`, gap cost reveal/utils.py:162-180) for
+ * nlists anchor lists in ONE launch, one thread block per list.  List j has rows row_off[j] .. row_off[j+1] (row 0 = the left
+ * bound, the last row = the right bound, the anchors in between in processing order), kk[j] coordinates per row stored at
+ * start[start_off[j] ...] row-major; length / gain per row; model 0 = sumofpairs, 1 = star-avg, 2 = star-med.  link[r] = the
+ * predecessor row (list-local), score[r] = the best total.  Host buffers; works on any handle (its stream and staging area). */
+int rv_chain_batch(rv_index *idx, int32_t nlists, const int64_t *row_off, const int64_t *start_off, const int32_t *kk, const int64_t *start,
+                   const int64_t *length, const int64_t *gain, int64_t wpen, int32_t model, int64_t *link, int64_t *score);
+
+/* ---- many tiny indexes in one launch ----------------------------------------------------------------
+ * `finish` / `transform` extend every anchor by indexing its two <= 200 bp flanks on their own (reveal/transformold.py:1170-1240
+ * `extend`: index() / addsequence x 2 / construct() / getmums(minlocallength), four times per anchor).  Unit u is the text
+ * T[off[u] .. off[u+1]) = "ref$qry$" exactly as addsequence assembles it (interface.c:71-85), at most 1024 characters, with
+ * nsep0[u] = the position of its first '$' inside the unit.  One thread block per unit: suffix array, barrier-aware LCP and the
+ * getmums scan (reveal.c:55-116) in shared memory.  rows[u * cap * 3 ...] receives up to cap rows (l, a, b) of unit u in
+ * SA-rank order -- what index.getmums(minl) returns for that pair -- and counts[u] the number found (it may exceed cap). */
+int rv_mums_tiny_batch(rv_index *idx, const uint8_t *T, const int64_t *off, const int64_t *nsep0, int32_t nunits, int32_t minl, int32_t cap,
+                       int64_t *rows, int32_t *counts);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

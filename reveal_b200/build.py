@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libreveal_b200.so")
 OBJ = os.path.join(_HERE, "csrc", "build")
-UNITS = ["rv_api", "rv_sa", "rv_lcp", "rv_sweep", "rv_split"]
+UNITS = ["rv_api", "rv_sa", "rv_lcp", "rv_sweep", "rv_split", "rv_chain", "rv_tiny"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("RV_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -14,7 +14,10 @@
 // Python object).  Edges carry ofrom / oto ('+' / '-'), a set of path ids and, rarely, extra GFA tags (kept as a dict).
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <dlfcn.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string>
 
 #include <algorithm>
 #include <deque>
@@ -22,6 +25,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../../include/reveal_b200.h"
 #include "chain_dp.h"
 
 namespace {
@@ -726,16 +730,36 @@ static void trim_overlap(std::vector<Mum> &mums) {
     }
 }
 
-// pick(mums, nsamples, leftnode, rightnode, trim, maxmums, model, wscore, wpen, seedsize) -> () | (anchor, skipleft, skipright)
-static PyObject *Graph_pick(Graph *g, PyObject *args) {
-    PyObject *list, *leftnode, *rightnode;
-    long nsamples, maxmums;
-    int trim, model;
-    long long wscore, wpen, seedsize;
-    if (!PyArg_ParseTuple(args, "OlOOpliLLL", &list, &nsamples, &leftnode, &rightnode, &trim, &maxmums, &model, &wscore, &wpen, &seedsize)) return nullptr;
-    std::vector<Mum> all;
-    if (!parse_mums(list, all)) return nullptr;
-    std::vector<Mum> picked;
+// One call of the mumpicker's default flow, cut in two at its chaining recurrence so that the recurrences of MANY calls can run
+// together (device: rv_chain_batch, one thread block per list; or the host loop rv_chain_dp):
+//   pick_prepare  anchors of all samples, trim_overlap, path coordinates, bounds, the rows of the recurrence
+//   pick_finish   back-tracking, split anchor, seeds for the children
+struct PickJob {
+    long nsamples = 0, maxmums = 0;
+    int trim = 0, model = 0;
+    long long wscore = 0, wpen = 0, seedsize = 0;
+    PyObject *leftnode = nullptr, *rightnode = nullptr;   // borrowed
+    std::vector<Mum> all, picked;
+    std::vector<Rel> rel;
+    std::map<std::vector<int64_t>, int> origin;
+    std::vector<int32_t> keys;
+    size_t k = 0, m = 0;
+    std::vector<int64_t> left, right;
+    std::vector<int> order;
+    std::vector<int64_t> start, length, gain, link, score;
+    bool need_dp = false;   // start / length / gain hold a recurrence of m + 1 rows; link / score are to be filled
+    bool dp_done = false;
+    int split = -1;
+};
+
+// 1: go on (run the recurrence if need_dp, then pick_finish); 0: the answer is the empty tuple; -1: error set
+static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
+    const long nsamples = J.nsamples, maxmums = J.maxmums;
+    const int trim = J.trim;
+    const long long wscore = J.wscore;
+    PyObject *leftnode = J.leftnode, *rightnode = J.rightnode;
+    std::vector<Mum> &all = J.all, &picked = J.picked;
+    if (!parse_mums(list, all)) return -1;
     for (auto &m : all)
         if (m.n == nsamples) picked.push_back(m);
     if (picked.empty() && nsamples > 2) {  // schemes.segment: the sample group with the largest total length x group size
@@ -762,15 +786,16 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
         if (pick >= 0)
             for (int i : members[pick]) picked.push_back(all[i]);
     }
-    if (picked.empty()) return PyTuple_New(0);
+    if (picked.empty()) return 0;
     if (trim) {
         trim_overlap(picked);
-        if (picked.empty()) return PyTuple_New(0);
+        if (picked.empty()) return 0;
     }
     std::stable_sort(picked.begin(), picked.end(), [](const Mum &a, const Mum &b) { return a.l > b.l; });
     // anchors in path coordinates (schemes.lookup / maptooffsets)
-    std::vector<Rel> rel(picked.size());
-    std::map<std::vector<int64_t>, int> origin;
+    std::vector<Rel> &rel = J.rel;
+    rel.assign(picked.size(), Rel());
+    std::map<std::vector<int64_t>, int> &origin = J.origin;
     for (size_t i = 0; i < picked.size(); i++) {
         Rel &r = rel[i];
         r.l = picked[i].l;
@@ -778,7 +803,7 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
         r.src = (int)i;
         for (auto &p : picked[i].sp) {
             int id = node_at(g, p.second);
-            if (id < 0) { PyErr_Format(PyExc_KeyError, "no node covers index position %lld", (long long)p.second); return nullptr; }
+            if (id < 0) { PyErr_Format(PyExc_KeyError, "no node covers index position %lld", (long long)p.second); return -1; }
             const Node &nd = (*g->nodes)[id];
             const int64_t shift = p.second - nd.begin;
             for (auto &kv : nd.offsets) {
@@ -806,26 +831,28 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
             if (keyset(r) == want) same.push_back(r);
         rel.swap(same);
     }
-    std::vector<int32_t> keys;
+    std::vector<int32_t> &keys = J.keys;
     for (auto &kv : rel.back().point) keys.push_back(kv.first);
-    const size_t k = keys.size();
-    if (k == 0 || k > 64) { PyErr_SetString(PyExc_ValueError, "anchor over no path or over more than 64 paths"); return nullptr; }
+    const size_t k = J.k = keys.size();
+    if (k == 0 || k > 64) { PyErr_SetString(PyExc_ValueError, "anchor over no path or over more than 64 paths"); return -1; }
     // bounds of the sub-index in path coordinates
-    std::vector<int64_t> left(k), right(k);
+    std::vector<int64_t> &left = J.left, &right = J.right;
+    left.assign(k, 0);
+    right.assign(k, 0);
     for (int side = 0; side < 2; side++) {
         PyObject *bound = side == 0 ? leftnode : rightnode;
         if (bound == Py_None) {
             for (size_t c = 0; c < k; c++) {
                 if (side == 0) left[c] = -1;
                 else {
-                    if (keys[c] < 0 || (size_t)keys[c] >= g->id2end->size()) { PyErr_SetString(PyExc_KeyError, "path without a length"); return nullptr; }
+                    if (keys[c] < 0 || (size_t)keys[c] >= g->id2end->size()) { PyErr_SetString(PyExc_KeyError, "path without a length"); return -1; }
                     right[c] = (*g->id2end)[keys[c]];
                 }
             }
             continue;
         }
         int id = find_node(g, bound);
-        if (id < 0) return nullptr;
+        if (id < 0) return -1;
         const Node &nd = (*g->nodes)[id];
         for (size_t c = 0; c < k; c++) {
             bool found = false;
@@ -835,7 +862,7 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
                     found = true;
                     break;
                 }
-            if (!found) { PyErr_Format(PyExc_KeyError, "path %d does not run through the bounding node", (int)keys[c]); return nullptr; }
+            if (!found) { PyErr_Format(PyExc_KeyError, "path %d does not run through the bounding node", (int)keys[c]); return -1; }
         }
     }
     auto coord_of = [](const Rel &r, int32_t key) -> int64_t {
@@ -843,25 +870,29 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
             if (kv.first == key) return kv.second;
         return 0;
     };
-    std::vector<std::pair<int, int64_t>> skipleft, skipright;  // (picked index, score relative to the split)
-    int split = -1;                                             // index into rel
     if (rel.size() == 1) {
-        split = 0;
+        J.split = 0;
     } else {
         if (maxmums > 0 && (long)rel.size() > maxmums) rel.erase(rel.begin(), rel.end() - maxmums);
         else if (maxmums <= 0 && !rel.empty()) { /* rel[-0:] is the whole list in Python as well */ }
         // schemes.chain: anchors + the right bound in the order of the smallest path id's coordinate
         int32_t ref = rel[0].point[0].first;
         for (auto &kv : rel[0].point) ref = std::min(ref, kv.first);
-        const size_t m = rel.size() + 1;
-        std::vector<int> order(m);
+        const size_t m = J.m = rel.size() + 1;
+        std::vector<int> &order = J.order;
+        order.assign(m, 0);
         for (size_t i = 0; i < m; i++) order[i] = (int)i;  // index rel.size() stands for the right bound
         size_t refcol = 0;
         for (size_t c = 0; c < k; c++)
             if (keys[c] == ref) refcol = c;
         auto refcoord = [&](int i) { return (size_t)i == rel.size() ? right[refcol] : coord_of(rel[i], ref); };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return refcoord(a) < refcoord(b); });
-        std::vector<int64_t> start((m + 1) * k), length(m + 1, 0), gain(m + 1, 0), link(m + 1, 0), score(m + 1, 0);
+        std::vector<int64_t> &start = J.start, &length = J.length, &gain = J.gain;
+        start.assign((m + 1) * k, 0);
+        length.assign(m + 1, 0);
+        gain.assign(m + 1, 0);
+        J.link.assign(m + 1, 0);
+        J.score.assign(m + 1, 0);
         for (size_t c = 0; c < k; c++) start[c] = left[c];
         for (size_t r = 1; r <= m; r++) {
             const int i = order[r - 1];
@@ -873,7 +904,23 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
                 gain[r] = wscore * (rel[i].l * ((rel[i].n * (rel[i].n - 1)) / 2));
             }
         }
-        rv_chain_dp(start.data(), length.data(), gain.data(), (long)(m + 1), (long)k, (int64_t)wpen, model, link.data(), score.data());
+        J.need_dp = true;
+    }
+    return 1;
+}
+
+static PyObject *pick_finish(Graph *g, PickJob &J) {
+    std::vector<Mum> &picked = J.picked;
+    std::vector<Rel> &rel = J.rel;
+    std::map<std::vector<int64_t>, int> &origin = J.origin;
+    const long long seedsize = J.seedsize;
+    std::vector<std::pair<int, int64_t>> skipleft, skipright;  // (picked index, score relative to the split)
+    int split = J.split;                                        // index into rel
+    if (J.need_dp || J.dp_done) {
+        const size_t m = J.m;
+        const std::vector<int> &order = J.order;
+        const std::vector<int64_t> &link = J.link, &score = J.score;
+
         // the right bound sorts last (anchors lie inside the bounds; it was appended last and the sort is stable): back-track
         // from the last row, like rem.chain
         std::vector<std::pair<int, int64_t>> chained;  // (rel index, score), first anchor of the chain first
@@ -910,6 +957,27 @@ static PyObject *Graph_pick(Graph *g, PyObject *args) {
         }
     }
     return Py_BuildValue("(NNN)", anchor, lists[0], lists[1]);
+}
+
+
+static inline void pick_dp_host(PickJob &J) {
+    rv_chain_dp(J.start.data(), J.length.data(), J.gain.data(), (long)(J.m + 1), (long)J.k, (int64_t)J.wpen, J.model, J.link.data(), J.score.data());
+}
+
+// pick(mums, nsamples, leftnode, rightnode, trim, maxmums, model, wscore, wpen, seedsize) -> () | (anchor, skipleft, skipright)
+static PyObject *Graph_pick(Graph *g, PyObject *args) {
+    PyObject *list;
+    PickJob J;
+    if (!PyArg_ParseTuple(args, "OlOOpliLLL", &list, &J.nsamples, &J.leftnode, &J.rightnode, &J.trim, &J.maxmums, &J.model, &J.wscore, &J.wpen, &J.seedsize)) return nullptr;
+    const int st = pick_prepare(g, list, J);
+    if (st < 0) return nullptr;
+    if (st == 0) return PyTuple_New(0);
+    if (J.need_dp) {
+        pick_dp_host(J);
+        J.need_dp = false;
+        J.dp_done = true;
+    }
+    return pick_finish(g, J);
 }
 
 // export() -> (nodes, edges): nodes = [(key, attribute dict)], edges = [(u, v, attribute dict)] -- the attribute dicts are
@@ -984,6 +1052,160 @@ static PyObject *Graph_set_picker(Graph *g, PyObject *args) {
     Py_RETURN_NONE;
 }
 
+// ---- the chaining recurrences of a batch on the device -----------------------------------------------------------------------
+// remcore is host code (the graph of the driver); the one numeric kernel of the mumpicker -- the O(m^2) recurrence -- goes
+// through the C-ABI of libreveal_b200.so (rv_chain_batch, csrc/rv_chain.cu) when many lists are waiting (frontier batching) or a
+// list is long.  The library is the one next to this module; without it or without a GPU (the driver running on the
+// reference's CPU extension, as in the CPU tests) the host loop rv_chain_dp does the same arithmetic.  RV_REM_CHAIN=host|device
+// forces one or the other.
+struct ChainApi {
+    bool tried = false, ready = false;
+    std::string path;   // override (tests: the emulated kernels)
+    void *lib = nullptr;
+    rv_index *h = nullptr;
+    decltype(&::rv_index_create) create = nullptr;
+    decltype(&::rv_index_free) destroy = nullptr;
+    decltype(&::rv_chain_batch) chain = nullptr;
+    decltype(&::rv_last_error) last_error = nullptr;
+    long long device_lists = 0, host_lists = 0, launches = 0;
+};
+static ChainApi g_chain;
+
+extern "C" PyObject *PyInit_remcore(void);
+static bool chain_device_ready() {
+    ChainApi &c = g_chain;
+    if (c.tried) return c.ready;
+    c.tried = true;
+    const char *mode = getenv("RV_REM_CHAIN");
+    if (mode && mode[0] == 'h') return false;
+    std::string path = c.path;
+    if (path.empty()) {
+        Dl_info info;
+        if (!dladdr((void *)&PyInit_remcore, &info) || !info.dli_fname) return false;
+        path = info.dli_fname;
+        size_t slash = path.rfind('/');
+        path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/libreveal_b200.so";
+    }
+    c.lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!c.lib) return false;
+    c.create = (decltype(c.create))dlsym(c.lib, "rv_index_create");
+    c.destroy = (decltype(c.destroy))dlsym(c.lib, "rv_index_free");
+    c.chain = (decltype(c.chain))dlsym(c.lib, "rv_chain_batch");
+    c.last_error = (decltype(c.last_error))dlsym(c.lib, "rv_last_error");
+    if (!c.create || !c.destroy || !c.chain || !c.last_error) return false;
+    if (c.create(&c.h, nullptr) != 0) return false;   // no GPU: the host loop it is
+    c.ready = true;
+    return true;
+}
+
+// runs the recurrences of the prepared jobs: the long ones together on the device when that pays, the rest on the host
+static bool run_recurrences(std::vector<PickJob *> &jobs) {
+    static const size_t SMALL = 48;          // rows below which a list is not worth a thread block
+    static const double WORTH = 150000.0;    // sum of rows^2 from which one launch + two copies beat the host loop
+    std::vector<PickJob *> big;
+    double work = 0;
+    for (PickJob *J : jobs) {
+        if (!J->need_dp) continue;
+        if (J->m + 1 >= SMALL) {
+            big.push_back(J);
+            work += (double)(J->m + 1) * (double)(J->m + 1);
+        }
+    }
+    const char *mode = getenv("RV_REM_CHAIN");
+    const bool force = mode && mode[0] == 'd';
+    bool on_device = !big.empty() && (force || work >= WORTH) && chain_device_ready();
+    if (on_device) {
+        // every list in one call; lists may differ in gap model / penalty only across calls of one batch: group by (wpen, model)
+        const int64_t wpen = big[0]->wpen;
+        const int model = big[0]->model;
+        std::vector<int64_t> row_off(1, 0), start_off(1, 0), start, length, gain;
+        std::vector<int32_t> kk;
+        for (PickJob *J : big) {
+            if (J->wpen != wpen || J->model != model) { on_device = false; break; }
+            row_off.push_back(row_off.back() + (int64_t)J->m + 1);
+            start_off.push_back(start_off.back() + (int64_t)J->start.size());
+            kk.push_back((int32_t)J->k);
+            start.insert(start.end(), J->start.begin(), J->start.end());
+            length.insert(length.end(), J->length.begin(), J->length.end());
+            gain.insert(gain.end(), J->gain.begin(), J->gain.end());
+        }
+        if (on_device) {
+            std::vector<int64_t> link((size_t)row_off.back()), score((size_t)row_off.back());
+            int status;
+            Py_BEGIN_ALLOW_THREADS;
+            status = g_chain.chain(g_chain.h, (int32_t)big.size(), row_off.data(), start_off.data(), kk.data(), start.data(), length.data(), gain.data(),
+                                   wpen, model, link.data(), score.data());
+            Py_END_ALLOW_THREADS;
+            if (status != 0) {
+                PyErr_Format(PyExc_RuntimeError, "rv_chain_batch failed: %s", g_chain.last_error());
+                return false;
+            }
+            for (size_t j = 0; j < big.size(); j++) {
+                std::copy(link.begin() + row_off[j], link.begin() + row_off[j + 1], big[j]->link.begin());
+                std::copy(score.begin() + row_off[j], score.begin() + row_off[j + 1], big[j]->score.begin());
+                big[j]->need_dp = false;
+                big[j]->dp_done = true;
+            }
+            g_chain.device_lists += (long long)big.size();
+            g_chain.launches++;
+        }
+    }
+    for (PickJob *J : jobs)
+        if (J->need_dp) {
+            pick_dp_host(*J);
+            J->need_dp = false;
+            J->dp_done = true;
+            g_chain.host_lists++;
+        }
+    return true;
+}
+
+// front part of the mumpicker callback: 0 -> *result is the answer; 1 -> J is prepared (recurrence, then pick_finish); -1 error
+static int mumpicker_front(Graph *g, PyObject *mums, PyObject *idx, int precomputed, PyObject **result, PickJob &J) {
+    *result = nullptr;
+    const Py_ssize_t n = PyObject_Length(mums);
+    if (n < 0) return -1;
+    if (n == 0) { *result = PyTuple_New(0); return *result ? 0 : -1; }
+    if (precomputed) {  // a chain handed down by the parent: split at its middle (schemes.py:346-351)
+        const Py_ssize_t half = n / 2;
+        PyObject *item = PySequence_GetItem(mums, half);
+        if (!item) return -1;
+        PyObject *mum = PySequence_GetItem(item, 0);
+        Py_DECREF(item);
+        if (!mum) return -1;
+        PyObject *left = PySequence_GetSlice(mums, 0, half), *right = PySequence_GetSlice(mums, half + 1, n);
+        if (!left || !right) { Py_DECREF(mum); Py_XDECREF(left); Py_XDECREF(right); return -1; }
+        *result = Py_BuildValue("(NNN)", mum, left, right);
+        return *result ? 0 : -1;
+    }
+    if (g->pk_maxdepth >= 0) {
+        PyObject *d = PyObject_GetAttrString(idx, "depth");
+        if (!d) return -1;
+        const long depth = PyLong_AsLong(d);
+        Py_DECREF(d);
+        if (depth > g->pk_maxdepth) { *result = PyTuple_New(0); return *result ? 0 : -1; }
+    }
+    PyObject *ns = PyObject_GetAttrString(idx, "nsamples"), *ln = PyObject_GetAttrString(idx, "leftnode"), *rn = PyObject_GetAttrString(idx, "rightnode");
+    int st = -1;
+    if (ns && ln && rn) {
+        J.nsamples = PyLong_AsLong(ns);
+        J.leftnode = ln;    // kept alive by the index object for the duration of the call / the batch
+        J.rightnode = rn;
+        J.trim = g->pk_trim;
+        J.maxmums = g->pk_maxmums;
+        J.model = g->pk_model;
+        J.wscore = g->pk_wscore;
+        J.wpen = g->pk_wpen;
+        J.seedsize = g->pk_seedsize;
+        st = pick_prepare(g, mums, J);
+        if (st == 0) { *result = PyTuple_New(0); if (!*result) st = -1; }
+    }
+    Py_XDECREF(ns);
+    Py_XDECREF(ln);
+    Py_XDECREF(rn);
+    return st;
+}
+
 // mumpicker(mums, idx, precomputed=False, minlength=0): the callback index.align() expects (schemes.py:197-361, default options:
 // splitchain="largest", a length threshold, no maxsize) without a Python frame in between -- Rem.graphmumpicker is the readable twin.
 static PyObject *Graph_mumpicker(Graph *g, PyObject *args, PyObject *kwds) {
@@ -991,41 +1213,53 @@ static PyObject *Graph_mumpicker(Graph *g, PyObject *args, PyObject *kwds) {
     PyObject *mums, *idx, *minlength = nullptr;
     int precomputed = 0;
     if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|pO", (char **)kwlist, &mums, &idx, &precomputed, &minlength)) return nullptr;
-    const Py_ssize_t n = PyObject_Length(mums);
-    if (n < 0) return nullptr;
-    if (n == 0) return PyTuple_New(0);
-    if (precomputed) {  // a chain handed down by the parent: split at its middle (schemes.py:346-351)
-        const Py_ssize_t half = n / 2;
-        PyObject *item = PySequence_GetItem(mums, half);
-        if (!item) return nullptr;
-        PyObject *mum = PySequence_GetItem(item, 0);
-        Py_DECREF(item);
-        if (!mum) return nullptr;
-        PyObject *left = PySequence_GetSlice(mums, 0, half), *right = PySequence_GetSlice(mums, half + 1, n);
-        if (!left || !right) { Py_DECREF(mum); Py_XDECREF(left); Py_XDECREF(right); return nullptr; }
-        return Py_BuildValue("(NNN)", mum, left, right);
+    PickJob J;
+    PyObject *result = nullptr;
+    const int st = mumpicker_front(g, mums, idx, precomputed, &result, J);
+    if (st < 0) return nullptr;
+    if (st == 0) return result;
+    std::vector<PickJob *> one(1, &J);
+    if (!run_recurrences(one)) return nullptr;
+    return pick_finish(g, J);
+}
+
+// mumpicker_batch(entries, minlength=0) -> [pick, ...]: the mumpicker for every (mums, idx, precomputed) of a frontier batch of
+// index.align().  The picks of different sub-indexes do not depend on each other (an anchor's path coordinates do not change
+// while its text is unaligned), so all lists are prepared first and their chaining recurrences run together -- on the device
+// (rv_chain_batch) when the batch holds enough work.
+static PyObject *Graph_mumpicker_batch(Graph *g, PyObject *args, PyObject *kwds) {
+    static const char *kwlist[] = {"entries", "minlength", nullptr};
+    PyObject *entries, *minlength = nullptr;
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "O|O", (char **)kwlist, &entries, &minlength)) return nullptr;
+    PyObject *seq = PySequence_Fast(entries, "entries must be a sequence of (mums, idx, precomputed)");
+    if (!seq) return nullptr;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    std::vector<PickJob> jobs((size_t)n);
+    std::vector<PyObject *> results((size_t)n, nullptr);
+    std::vector<int> state((size_t)n, 0);
+    std::vector<PickJob *> pending;
+    bool ok = true;
+    for (Py_ssize_t i = 0; ok && i < n; i++) {
+        PyObject *e = PySequence_Fast_GET_ITEM(seq, i);
+        PyObject *mums, *idx;
+        int precomputed = 0;
+        if (!PyArg_ParseTuple(e, "OO|p", &mums, &idx, &precomputed)) { ok = false; break; }
+        state[(size_t)i] = mumpicker_front(g, mums, idx, precomputed, &results[(size_t)i], jobs[(size_t)i]);
+        if (state[(size_t)i] < 0) ok = false;
+        else if (state[(size_t)i] == 1) pending.push_back(&jobs[(size_t)i]);
     }
-    if (g->pk_maxdepth >= 0) {
-        PyObject *d = PyObject_GetAttrString(idx, "depth");
-        if (!d) return nullptr;
-        const long depth = PyLong_AsLong(d);
-        Py_DECREF(d);
-        if (depth > g->pk_maxdepth) return PyTuple_New(0);
+    if (ok) ok = run_recurrences(pending);
+    PyObject *out = ok ? PyList_New(n) : nullptr;
+    for (Py_ssize_t i = 0; ok && i < n; i++) {
+        if (state[(size_t)i] == 1) results[(size_t)i] = pick_finish(g, jobs[(size_t)i]);
+        if (!results[(size_t)i]) { ok = false; break; }
+        PyList_SET_ITEM(out, i, results[(size_t)i]);
+        results[(size_t)i] = nullptr;
     }
-    PyObject *ns = PyObject_GetAttrString(idx, "nsamples"), *ln = PyObject_GetAttrString(idx, "leftnode"), *rn = PyObject_GetAttrString(idx, "rightnode");
-    PyObject *ret = nullptr;
-    if (ns && ln && rn) {
-        PyObject *a = Py_BuildValue("(OOOOOlilll)", mums, ns, ln, rn, g->pk_trim ? Py_True : Py_False, g->pk_maxmums, g->pk_model, (long)g->pk_wscore,
-                                    (long)g->pk_wpen, (long)g->pk_seedsize);
-        if (a) {
-            ret = Graph_pick(g, a);
-            Py_DECREF(a);
-        }
-    }
-    Py_XDECREF(ns);
-    Py_XDECREF(ln);
-    Py_XDECREF(rn);
-    return ret;
+    for (PyObject *r : results) Py_XDECREF(r);
+    Py_DECREF(seq);
+    if (!ok) { Py_XDECREF(out); return nullptr; }
+    return out;
 }
 
 // graphalign_cb(idx, mum): the second callback of index.align() (rem.py:320-382) on this graph
@@ -1067,6 +1301,9 @@ static PyMethodDef Graph_methods[] = {
     {"set_picker", (PyCFunction)Graph_set_picker, METH_VARARGS, "set_picker(trim, maxmums, model, wscore, wpen, seedsize, maxdepth or -1): options of mumpicker()"},
     {"mumpicker", (PyCFunction)(void (*)(void))Graph_mumpicker, METH_VARARGS | METH_KEYWORDS,
      "mumpicker(mums, idx, precomputed=False, minlength=0) -> () | (anchor, skipleft, skipright): the callback of index.align(), default flow"},
+    {"mumpicker_batch", (PyCFunction)(void (*)(void))Graph_mumpicker_batch, METH_VARARGS | METH_KEYWORDS,
+     "mumpicker_batch([(mums, idx, precomputed), ...], minlength=0) -> [pick, ...]: the mumpicker for a whole frontier batch of index.align(); "
+     "the chaining recurrences of the batch run together (on the device when that pays)"},
     {"graphalign_cb", (PyCFunction)Graph_graphalign_cb, METH_VARARGS, "graphalign_cb(idx, mum): the graphalign callback of index.align() on this graph"},
     {"add_node", (PyCFunction)Graph_add_node, METH_VARARGS, "add_node(key, aligned or None, offsets, extra or None)"},
     {"add_edge", (PyCFunction)Graph_add_edge, METH_VARARGS, "add_edge(u, v, ofrom, oto, paths, extra or None)"},
@@ -1082,8 +1319,30 @@ static PyMethodDef Graph_methods[] = {
 
 static PyTypeObject GraphType = {PyVarObject_HEAD_INIT(nullptr, 0)};
 
+static PyObject *mod_chain_stats(PyObject *, PyObject *) {
+    return Py_BuildValue("{s:O,s:L,s:L,s:L}", "device", g_chain.ready ? Py_True : Py_False, "device_lists", g_chain.device_lists, "host_lists", g_chain.host_lists,
+                         "launches", g_chain.launches);
+}
+static PyObject *mod_set_chain_library(PyObject *, PyObject *args) {
+    const char *path;
+    if (!PyArg_ParseTuple(args, "s", &path)) return nullptr;
+    const char *e = getenv("REVEAL_B200_TEST_HOOKS");
+    if (!e || e[0] != '1') {
+        PyErr_SetString(PyExc_RuntimeError, "remcore._set_chain_library is a test hook (REVEAL_B200_TEST_HOOKS=1)");
+        return nullptr;
+    }
+    if (g_chain.h && g_chain.destroy) g_chain.destroy(g_chain.h);
+    g_chain = ChainApi();
+    g_chain.path = path;
+    Py_RETURN_NONE;
+}
+static PyMethodDef module_methods[] = {
+    {"chain_stats", mod_chain_stats, METH_NOARGS, "where the chaining recurrences of this process ran: lists on the device / on the host, device launches"},
+    {"_set_chain_library", mod_set_chain_library, METH_VARARGS, "test hook: the C-ABI library rv_chain_batch is taken from (the emulated kernels)"},
+    {nullptr, nullptr, 0, nullptr}};
+
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "remcore",
-                                       "Alignment graph of the REM driver during the recursion (see reveal_b200/rem.py).", -1, nullptr};
+                                       "Alignment graph of the REM driver during the recursion (see reveal_b200/rem.py).", -1, module_methods};
 
 }  // namespace
 

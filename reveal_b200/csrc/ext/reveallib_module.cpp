@@ -38,7 +38,7 @@
     X(rv_last_error) X(rv_version) X(rv_host_alloc) X(rv_host_free) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
     X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_put_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
     X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_free) X(rv_sub_get)    \
-    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch)
+    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch) X(rv_mums_tiny_batch)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -241,12 +241,15 @@ static PyObject *index_addsequence(Index *self, PyObject *args) {
     const char *seq;
     Py_ssize_t l;
     if (!PyArg_ParseTuple(args, "s#", &seq, &l)) return nullptr;
-#ifndef SA64
-    if ((uint64_t)self->n + (uint64_t)(l + 1) + 1 > (uint64_t)INT32_MAX) {  // interface.c:61-68
-        PyErr_SetString(RevealError, "Total amount of sequence too large, use \"reveal <subcommand> --64\" to use 64 bit suffix arrays instead.");
+    // The reference refuses texts of 2^31 characters and more in its 32-bit build and sends the user to --64 (interface.c:61-68).
+    // The device arrays of this build hold 30-bit positions in BOTH modules (reveallib64 widens the numbers on the way out,
+    // reveal.h:7-13): the limit is 2^30 - 1 characters per index, said here -- where the text is assembled -- rather than after
+    // gigabytes have been appended.
+    if ((uint64_t)self->n + (uint64_t)(l + 1) + 1 > ((uint64_t)1 << 30)) {
+        PyErr_SetString(RevealError, "Total amount of sequence too large: this build indexes at most 2^30 - 1 characters per index "
+                                     "(32-bit positions on the device, also behind \"--64\" / reveallib64).");
         return nullptr;
     }
-#endif
     int64_t s = self->n;
     if (!self->T->append(seq, (size_t)l) || !self->T->push_back('$')) return PyErr_NoMemory();
     self->n += l + 1;
@@ -590,16 +593,20 @@ static void release_index_view(Index *idx) {
 
 static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn",  // interface.c:303
-                                   "shard_rank", "shard_world", "shard_grain", nullptr};
-    PyObject *mumpicker, *graphalign;
+                                   "shard_rank", "shard_world", "shard_grain", "mumpicker_batch", nullptr};
+    PyObject *mumpicker, *graphalign, *mumpicker_batch = nullptr;
     int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 4;
     if (self->mainidx || !self->built) {
         PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
         return nullptr;
     }
-    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiiiiii", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn,
-                                     &shard_rank, &shard_world, &shard_grain))
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiiiiiiO", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn,
+                                     &shard_rank, &shard_world, &shard_grain, &mumpicker_batch))
         return nullptr;
+    // mumpicker_batch (optional): callable([(mums, idx, precomputed), ...], minlength=) -> [pick, ...] -- the mumpicker for all
+    // sub-indexes of a frontier batch at once (their picks do not depend on each other), so that e.g. their chaining recurrences
+    // can share a device launch (remcore.Graph.mumpicker_batch).  Without it `mumpicker` is called once per sub-index.
+    if (mumpicker_batch == Py_None) mumpicker_batch = nullptr;
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world || shard_grain < 1) {
         PyErr_SetString(RevealError, "align: bad shard_rank / shard_world / shard_grain");
         return nullptr;
@@ -619,7 +626,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     // the sub-indexes on the queue are independent, so their callbacks run one after the other and the device parts of up to
     // `batch` steps share one launch and one synchronisation (rv_sub_step_batch).  threads <= 1 keeps one step per launch in
     // the reference's LIFO order; the default (0) and larger values batch.  RV_ALIGN_BATCH overrides the batch size.
-    size_t batch_max = threads == 1 ? 1 : 128;
+    size_t batch_max = threads == 1 ? 1 : 256;   // sub-indexes taken off the queue per round (the device takes up to 256 steps per launch)
     if (const char *e = getenv("RV_ALIGN_BATCH")) {
         long b = atol(e);
         if (b >= 1) batch_max = (size_t)b;
@@ -642,41 +649,76 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     std::vector<rv_step_desc> descs;
     for (;;) {
     while (ok && !queue.empty()) {
-        // ---- callbacks of the sub-indexes on top of the queue (LIFO, reveal.c:21-26), one after the other ----
-        while (ok && !queue.empty() && batch.size() < batch_max) {
+        // ---- the sub-indexes on top of the queue (LIFO, reveal.c:21-26) and their MUM lists ----
+        std::vector<PendingStep *> cand;
+        std::vector<PyObject *> cand_mums;   // owned
+        std::vector<int> cand_pre;
+        if (!PyCallable_Check(mumpicker)) {
+            PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
+            ok = false;
+        }
+        while (ok && !queue.empty() && cand.size() < batch_max) {
             Index *idx = queue.back();
             queue.pop_back();
             if (prefix && idx != self && idx->n <= unit_max) {  // below the cut: a unit, dealt out once the part above the cut is done
                 units.push_back(idx);
                 continue;
             }
-            PyObject *mums = nullptr;
             PendingStep *ps = new PendingStep();
             ps->idx = idx;
+            cand.push_back(ps);
+            int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
+            PyObject *mums;
+            if (!precomputed) {
+                const double t0 = now_s();
+                mums = extract_mums(self, idx->sub, minl, minn);
+                as.extract += now_s() - t0;
+                if (!mums) ok = false;
+            } else {
+                mums = idx->skipmums;
+                Py_INCREF(mums);
+            }
+            cand_mums.push_back(mums);
+            cand_pre.push_back(precomputed);
+        }
+        // ---- callback 1, mumpicker (reveal.c:851): per sub-index, or for the whole batch in one call ----
+        if (ok && mumpicker_batch && !cand.empty()) {
+            const double t0 = now_s();
+            PyObject *entries = PyList_New((Py_ssize_t)cand.size());
+            for (size_t i = 0; i < cand.size(); i++)
+                PyList_SET_ITEM(entries, (Py_ssize_t)i, Py_BuildValue("(OOO)", cand_mums[i], (PyObject *)cand[i]->idx, cand_pre[i] ? Py_True : Py_False));
+            PyObject *picks = PyObject_CallFunctionObjArgs(mumpicker_batch, entries, kw_minl, nullptr);
+            Py_DECREF(entries);
+            as.pick += now_s() - t0;
+            as.picks += (long long)cand.size();
+            if (!picks) ok = false;
+            else if (!PyList_Check(picks) || PyList_Size(picks) != (Py_ssize_t)cand.size()) {
+                PyErr_SetString(RevealError, "**** mumpicker_batch must return one pick per entry");
+                ok = false;
+            } else {
+                for (size_t i = 0; i < cand.size(); i++) {
+                    cand[i]->pick = PyList_GET_ITEM(picks, (Py_ssize_t)i);
+                    Py_INCREF(cand[i]->pick);
+                }
+            }
+            Py_XDECREF(picks);
+        }
+        // ---- per sub-index: the pick, then callback 2, graphalign (reveal.c:939), one after the other ----
+        for (size_t ci = 0; ci < cand.size(); ci++) {
+            PendingStep *ps = cand[ci];
+            Index *idx = ps->idx;
             bool staged = false;
-            do {
-                if (!PyCallable_Check(mumpicker)) {
-                    PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
-                    ok = false;
-                    break;
-                }
-                int precomputed = PyList_Check(idx->skipmums) ? PyList_Size(idx->skipmums) > 0 : PyObject_Length(idx->skipmums) > 0;
+            if (ok) do {
                 double t0 = now_s(), t1;
-                if (!precomputed) {
-                    mums = extract_mums(self, idx->sub, minl, minn);
-                    if (!mums) { ok = false; break; }
-                    t1 = now_s(); as.extract += t1 - t0; t0 = t1;
-                } else {
-                    mums = idx->skipmums;
-                    Py_INCREF(mums);
+                if (!ps->pick) {
+                    PyObject *cargs = Py_BuildValue("(OO)", cand_mums[ci], (PyObject *)idx);
+                    PyObject *ckw = Py_BuildValue("{s:O,s:O}", "precomputed", cand_pre[ci] ? Py_True : Py_False, "minlength", kw_minl);
+                    ps->pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
+                    Py_DECREF(cargs);
+                    Py_DECREF(ckw);
+                    t1 = now_s(); as.pick += t1 - t0; t0 = t1;
+                    as.picks++;
                 }
-                PyObject *cargs = Py_BuildValue("(OO)", mums, (PyObject *)idx);
-                PyObject *ckw = Py_BuildValue("{s:O,s:O}", "precomputed", precomputed ? Py_True : Py_False, "minlength", kw_minl);
-                ps->pick = PyObject_Call(mumpicker, cargs, ckw);  // reveal.c:851
-                Py_DECREF(cargs);
-                Py_DECREF(ckw);
-                t1 = now_s(); as.pick += t1 - t0; t0 = t1;
-                as.picks++;
                 if (!ps->pick) { ok = false; break; }
                 if (!PyTuple_Check(ps->pick)) {
                     PyErr_SetString(RevealError, "**** call to mumpicker failed");
@@ -722,7 +764,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                 t1 = now_s(); as.parse += t1 - t0;
                 staged = true;
             } while (0);
-            Py_XDECREF(mums);
+            Py_XDECREF(cand_mums[ci]);
             if (staged) {
                 batch.push_back(ps);
             } else {
@@ -1101,7 +1143,98 @@ static PyObject *mod_chain_dp(PyObject *, PyObject *args) {
     return ret;
 }
 
+// getmums_batch(pairs, minlength) -> [getmums list of pair 0, ...]
+// Every (ref, qry) pair of short sequences is an index of its own -- index(); addsample; addsequence(ref); addsample;
+// addsequence(qry); construct(); getmums(minlength) -- the way `extend` of finish / transform indexes the <= 200 bp flanks of
+// every anchor (reveal/transformold.py:1170-1240); the whole list goes through ONE launch (rv_mums_tiny_batch, one thread block
+// per pair).  A pair longer than the block path holds, or with more MUMs than a block reports, is built as a regular index.
+static rv_index *g_batch_ws = nullptr;
+static PyObject *pair_rows_to_list(const int64_t *rows, int64_t k) {
+    PyObject *lst = PyList_New((Py_ssize_t)k);
+    if (!lst) return nullptr;
+    PyObject *zero = PyLong_FromLong(0);
+    for (int64_t i = 0; i < k; i++) {  // (l, (a, b), rc): reveal.c:102-106
+        PyObject *ab = PyTuple_New(2), *rec = PyTuple_New(3);
+        PyTuple_SET_ITEM(ab, 0, PyLong_FromLongLong((long long)rows[3 * i + 1]));
+        PyTuple_SET_ITEM(ab, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));
+        PyTuple_SET_ITEM(rec, 1, ab);
+        Py_INCREF(zero);
+        PyTuple_SET_ITEM(rec, 2, zero);
+        PyList_SET_ITEM(lst, (Py_ssize_t)i, rec);
+    }
+    Py_DECREF(zero);
+    return lst;
+}
+static PyObject *mod_getmums_batch(PyObject *, PyObject *args) {
+    PyObject *pairs;
+    int minl = 0;
+    if (!PyArg_ParseTuple(args, "Oi", &pairs, &minl)) return nullptr;
+    if (!api_ready()) return nullptr;
+    PyObject *seq = PySequence_Fast(pairs, "pairs must be a sequence of (ref, qry)");
+    if (!seq) return nullptr;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    std::string T;
+    std::vector<int64_t> off(1, 0), sep;
+    const int32_t cap = 64;
+    const int64_t tiny_max = 1024;
+    std::vector<char> tiny((size_t)n, 1);
+    std::vector<int64_t> unit_of;   // batch unit -> pair
+    std::string Tb;
+    std::vector<int64_t> boff(1, 0), bsep;
+    for (Py_ssize_t i = 0; i < n; i++) {
+        const char *a, *b;
+        Py_ssize_t la, lb;
+        if (!PyArg_ParseTuple(PySequence_Fast_GET_ITEM(seq, i), "s#s#", &a, &la, &b, &lb)) { Py_DECREF(seq); return nullptr; }
+        off.push_back(off.back() + la + lb + 2);
+        sep.push_back(la);
+        T.append(a, (size_t)la); T.push_back('$'); T.append(b, (size_t)lb); T.push_back('$');
+        if (la + lb + 2 > tiny_max) { tiny[(size_t)i] = 0; continue; }
+        unit_of.push_back(i);
+        Tb.append(a, (size_t)la); Tb.push_back('$'); Tb.append(b, (size_t)lb); Tb.push_back('$');
+        boff.push_back(boff.back() + la + lb + 2);
+        bsep.push_back(la);
+    }
+    Py_DECREF(seq);
+    if (!g_batch_ws && fail_native(g_api.rv_index_create(&g_batch_ws, nullptr)) != 0) return nullptr;
+    const int32_t nu = (int32_t)unit_of.size();
+    std::vector<int64_t> rows((size_t)nu * cap * 3 + 3);
+    std::vector<int32_t> counts((size_t)nu + 1, 0);
+    if (nu > 0) {
+        int status;
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_mums_tiny_batch(g_batch_ws, (const uint8_t *)Tb.data(), boff.data(), bsep.data(), nu, minl, cap, rows.data(), counts.data());
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+    }
+    PyObject *out = PyList_New(n);
+    if (!out) return nullptr;
+    for (int32_t u = 0; u < nu; u++) {
+        const int64_t i = unit_of[(size_t)u];
+        if (counts[(size_t)u] < 0 || counts[(size_t)u] > cap) { tiny[(size_t)i] = 0; continue; }
+        PyObject *lst = pair_rows_to_list(rows.data() + (size_t)u * cap * 3, counts[(size_t)u]);
+        if (!lst) { Py_DECREF(out); return nullptr; }
+        PyList_SET_ITEM(out, (Py_ssize_t)i, lst);
+    }
+    for (Py_ssize_t i = 0; i < n; i++) {  // the pairs the block path did not take: a regular index each
+        if (tiny[(size_t)i]) continue;
+        const int64_t len = off[(size_t)i + 1] - off[(size_t)i];
+        int64_t nsep = sep[(size_t)i], k = 0;
+        int status = g_api.rv_build(g_batch_ws, (const uint8_t *)T.data() + off[(size_t)i], len, &nsep, 2, 0);
+        if (status == 0) status = g_api.rv_mums_pair_count(g_batch_ws, minl, 0, &k);
+        std::vector<int64_t> r((size_t)(3 * k + 3));
+        if (status == 0) status = g_api.rv_mums_pair_fetch(g_batch_ws, r.data(), k);
+        if (fail_native(status) != 0) { Py_DECREF(out); return nullptr; }
+        PyObject *lst = pair_rows_to_list(r.data(), k);
+        if (!lst) { Py_DECREF(out); return nullptr; }
+        PyList_SET_ITEM(out, i, lst);
+    }
+    return out;
+}
+
 static PyMethodDef module_methods[] = {
+    {"getmums_batch", mod_getmums_batch, METH_VARARGS,
+     "getmums_batch([(ref, qry), ...], minlength) -> [getmums list of every pair]: many tiny two-sample indexes in one launch (finish/transform extend)."},
     {"chain_dp", mod_chain_dp, METH_VARARGS, "Chaining recurrence of the REM driver on int64 buffers (see reveal_b200/rem.py:chain)."},
     {"_load", mod_load, METH_VARARGS, "Load a shared library exporting the C-ABI of include/reveal_b200.h (tests inject the emulated kernels)."},
     {"_library", mod_library, METH_NOARGS, "(path, version) of the loaded C-ABI library."},

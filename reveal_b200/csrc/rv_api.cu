@@ -109,6 +109,7 @@ struct rv_index {
     Arena arena;      // resident arrays + build workspace
     Arena sw;         // sweep tile scratch (grow-only)
     Arena res;        // last sweep result (grow-only)
+    Arena chain;      // staging of rv_chain_batch (grow-only)
     i64 n = 0;
     int nsamples = 0, rc = 0;
     std::vector<i64> nsep;
@@ -271,6 +272,7 @@ void rv_index_free(rv_index *h) {
     h->arena.release();
     h->sw.release();
     h->res.release();
+    h->chain.release();
     for (int i = 0; i < 6; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     prof_collect(h->st);
@@ -550,6 +552,17 @@ int main_view(rv_index *h, MainView *out) {
     out->nsamples = h->nsamples;
     out->rc = h->rc;
     out->pool_slot = &h->pool;
+    return RV_OK;
+}
+struct ChainView {
+    Stream *st;
+    Arena *ws;
+};
+int chain_view(rv_index *h, ChainView *out) {  // rv_chain_batch works on any handle, built or not
+    if (!h) { set_error("null index handle"); return RV_ERR_ARG; }
+    RV_CUDA(cudaSetDevice(h->device));
+    out->st = &h->st;
+    out->ws = &h->chain;
     return RV_OK;
 }
 int sub_sweep_pair(rv_index *h, const SweepArgs &a, int64_t *count) { return run_pair(h, a, count); }

@@ -225,6 +225,7 @@ class Rem(object):
         self._all_real = None
         self._coords = {}                  # index position -> ((path id, coordinate in that path), ...), see _lookup
         self.core = None                   # remcore.Graph while the recursion runs (see recursion_graph)
+        self.batch_picker = None           # remcore.Graph.mumpicker_batch when the native callbacks are in use (see callbacks)
         self.shard = None                  # (rank, world, process group, index) of a sharded recursion, see align_genomes(shard=...)
         self.shard_stats = None
         for key, empty in (("paths", list), ("id2path", dict), ("path2id", dict), ("id2end", dict)):
@@ -693,8 +694,10 @@ class Rem(object):
         core = self.core
         native = (core is not None and hasattr(core, "mumpicker") and args.splitchain == "largest" and minlength != 0
                   and args.gcmodel in _MODELS and args.maxsize is None and os.environ.get("RV_REM_PYTHON_PICK", "0") in ("", "0"))
+        self.batch_picker = None
         if not native:
             return self.graphmumpicker, self.graphalign
+        self.batch_picker = getattr(core, "mumpicker_batch", None)   # the picks of a whole frontier batch in one call
         core.set_picker(bool(args.trim), int(args.maxmums), _MODELS[args.gcmodel], int(args.wscore), int(args.wpen), int(args.seedsize),
                         -1 if args.maxdepth is None else int(args.maxdepth))
         return core.mumpicker, core.graphalign_cb
@@ -981,14 +984,15 @@ def align_genomes(args, index_module=None, shard=None):
     idx.construct()
     with rem.recursion_graph():
         mumpicker, graphalign = rem.callbacks(args.minlength)
+        extra = {}
+        if rem.batch_picker is not None and hasattr(mod, "align_stats"):   # this repository's extension: frontier batches
+            extra["mumpicker_batch"] = rem.batch_picker
         if shard is not None and shard[1] > 1:
             if rem.core is None:
                 raise RuntimeError("a sharded recursion needs the compiled graph (reveal_b200.remcore)")
             rem.shard = (int(shard[0]), int(shard[1]), shard[2] if len(shard) > 2 else None, idx)
-            idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn,
-                      shard_rank=rem.shard[0], shard_world=rem.shard[1])
-        else:
-            idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn)
+            extra.update(shard_rank=rem.shard[0], shard_world=rem.shard[1])
+        idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn, **extra)
     align_genomes.last_shard_stats = rem.shard_stats
     return rem.G, idx
 
@@ -1023,7 +1027,8 @@ def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targe
     idx.construct()
     with rem.recursion_graph():
         mumpicker, graphalign = rem.callbacks(minlength)
-        idx.align(mumpicker, graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn)
+        extra = {"mumpicker_batch": rem.batch_picker} if rem.batch_picker is not None and hasattr(mod, "align_stats") else {}
+        idx.align(mumpicker, graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn, **extra)
     rem.prune_nodes(T=idx.T)
     G.remove_node(first)
     G.remove_node(last)

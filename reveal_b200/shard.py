@@ -243,12 +243,20 @@ class PeerGather(object):
             self._release()
 
 
+def fwd_rc_units(T, nsep):
+    """The two index builds `finish` / `transform` need for one reference + contigs pair (transformold.py:142-143,
+    transform.py:255,271): the text as it is, and with the second sample reverse-complemented -- two independent units,
+    i.e. a clean 2-GPU job for anchor_units (BASELINE configs[3])."""
+    return [(T, nsep, 2, 0), (T, nsep, 2, 1)]
+
+
 def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
     """Index build + MUM sweep of independent units, sharded over the ranks of `group`.
 
-    units: list of (T uint8 array, nsep int64 array, nsamples) -- e.g. the sub-intervals of a recursion frontier
-    rebuilt as independent indexes, the jobs of `--order=sequential --chunksize`, or a forward / reverse-complement
-    pair.  Every rank builds the units `partition` assigns to it on its own GPU; the MUM records are
+    units: list of (T uint8 array, nsep int64 array, nsamples[, rc]) -- e.g. the sub-intervals of a recursion frontier
+    rebuilt as independent indexes, the jobs of `--order=sequential --chunksize`, or the forward / reverse-complement
+    pair of `finish` / `transform` (rc = 1: construct(rc=1), the second sample is reverse-complemented on the device first,
+    interface.c:168-172; see fwd_rc_units).  Every rank builds the units `partition` assigns to it on its own GPU; the MUM records are
     gathered to rank 0 (two tagged variable-length gathers: record rows, member rows).  Returns on rank 0 a list with
     one entry per unit -- pair rows (l, a, b) for two samples; for more samples the tuple (hdr, members) exactly as
     rv_mums_multi_fetch delivers it: header rows (l, n, first) and the (sample, position) member rows `first` indexes
@@ -268,13 +276,16 @@ def anchor_units(units, minl=20, minn=2, group=None, device=None, lib=None):
     blocks, mblocks = [], []
     try:
         for uid in mine:
-            T, nsep, ns = units[uid]
+            T, nsep, ns = units[uid][:3]
+            rc = int(units[uid][3]) if len(units[uid]) > 3 else 0
             T = np.ascontiguousarray(T, dtype=np.uint8)
             nsep = np.ascontiguousarray(nsep, dtype=np.int64)
-            _native.check(L, L.rv_build(h, T.ctypes.data, len(T), nsep.ctypes.data if len(nsep) else None, int(ns), 0))
+            _native.check(L, L.rv_build(h, T.ctypes.data, len(T), nsep.ctypes.data if len(nsep) else None, int(ns), rc))
             if ns == 2:
                 c = ctypes.c_int64()
-                _native.check(L, L.rv_mums_pair_count(h, int(minl), 1, ctypes.byref(c)))
+                # pair rows as getmums reports them for the root index (reveal.c:55-116): with rc the second coordinate is already
+                # mapped back to the forward strand (reveal.c:98-100)
+                _native.check(L, L.rv_mums_pair_count(h, int(minl), 0 if rc else 1, ctypes.byref(c)))
                 rows = np.empty((c.value, 3), dtype=np.int64)
                 _native.check(L, L.rv_mums_pair_fetch(h, rows.ctypes.data, c.value))
             else:

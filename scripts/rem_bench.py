@@ -37,7 +37,12 @@ def run(files, module, label):
     t2 = time.perf_counter()
     bases, total, nodes = rem.aligned_bases(G, idx)
     stats = module.align_stats() if hasattr(module, "align_stats") else None
-    return {"arm": label, "align_stats": stats, "seconds": t2 - t0, "align_genomes_s": t1 - t0, "aligned_bases": bases, "total_bases": total,
+    try:
+        from reveal_b200 import remcore
+        chain = remcore.chain_stats()
+    except Exception:
+        chain = None
+    return {"arm": label, "align_stats": stats, "chain_stats": chain, "seconds": t2 - t0, "align_genomes_s": t1 - t0, "aligned_bases": bases, "total_bases": total,
             "aligned_nodes": nodes, "nodes": G.number_of_nodes(), "aligned_bases_per_s": bases / (t2 - t0)}, T
 
 

@@ -180,6 +180,19 @@ def test_splitindex_matches_reference(emu_reveallib, ns, length, minl):
     reference's own splitindex -- children's n / nsamples / depth / nodes / bounds / SA / LCP and the text."""
     if emu_reveallib.name == "ctypes":
         pytest.skip("splitindex is part of the compiled extension")
+    splitindex_case(emu_reveallib.mod32, ns, length, minl)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("ns,length,minl", [(3, 30000, 12), (5, 8000, 10), (4, 200000, 14)])
+def test_splitindex_matches_reference_cuda(ns, length, minl):
+    """The same on the CUDA library, three levels deep, with parents above and below the single-block limit."""
+    from reveal_b200 import reveallib
+    splitindex_case(reveallib, ns, length, minl)
+
+
+def splitindex_case(mod32, ns, length, minl):
     rng = np.random.default_rng(900 + ns)
     samples = random_related(rng, ns, length, 4, snp=0.03)
     seqs = [[bytes(c).decode() for c in contigs] for contigs in samples]
@@ -198,7 +211,7 @@ def test_splitindex_matches_reference(emu_reveallib, ns, length, minl):
             return None
         return (child.n, child.nsamples, child.depth, sorted(child.nodes), child.leftnode, child.rightnode, list(child.SA), list(child.LCP))
 
-    ours, ref = build(emu_reveallib.mod32), build(R.module(32))
+    ours, ref = build(mod32), build(R.module(32))
     frontier = [(ours, ref)]
     steps = 0
     for level in range(3):

@@ -292,3 +292,42 @@ def test_cuda_highly_repetitive(cuda_lib):
         s1[p] = al[rng.integers(0, 4)]
     T, nsep, _ = P.assemble([[s0], [bytes(s1)]])
     check_against_oracle(cuda_lib, T, nsep, 2, minl=20)
+
+
+def test_cuda_sweeps_over_caller_supplied_device_arrays(cuda_lib):
+    """rv_sweep_pair_device / rv_sweep_multi_device: the sweeps over device arrays a caller holds (here: the arrays of a built index,
+    through rv_device_arrays) give the rows of the index's own sweeps."""
+    import ctypes
+
+    from reveal_b200 import _native
+    L = cuda_lib
+    rng = np.random.default_rng(31)
+    for ns, length in ((2, 60000), (4, 25000)):
+        T, nsep, _ = P.assemble(random_related(rng, ns, length, 4))
+        with NativeIndex(L, T, nsep, ns) as idx:
+            ptr = [ctypes.c_void_p() for _ in range(5)]
+            _native.check(L, L.rv_device_arrays(idx.h, *[ctypes.byref(p) for p in ptr]))
+            dT, dSA, dSAi, dLCP, dSO = ptr
+            assert dT.value and dSA.value and dLCP.value and (dSO.value or ns == 2)
+            ws = ctypes.c_void_p()
+            _native.check(L, L.rv_index_create(ctypes.byref(ws), None))   # a second handle as the workspace of the foreign arrays
+            try:
+                if ns == 2:
+                    want = idx.mums(12, 1)
+                    c = ctypes.c_int64()
+                    _native.check(L, L.rv_sweep_pair_device(ws, dT, dSA, dLCP, idx.n, idx.n, int(nsep[0]), 0, 1, 12, ctypes.byref(c)))
+                    rows = np.empty((c.value, 3), np.int64)
+                    _native.check(L, L.rv_mums_pair_fetch(ws, rows.ctypes.data, c.value))
+                    assert_same(rows, want, "rv_sweep_pair_device")
+                    assert len(rows) > 0
+                wh, wm = idx.multimums(12, 2)
+                nr, nm = ctypes.c_int64(), ctypes.c_int64()
+                _native.check(L, L.rv_sweep_multi_device(ws, dT, dSA, dLCP, dSO, idx.n, int(nsep[0]), ns, 12, 2, ctypes.byref(nr), ctypes.byref(nm)))
+                hdr = np.empty((nr.value, 3), np.int64)
+                mem = np.empty((nm.value, 2), np.int64)
+                _native.check(L, L.rv_mums_multi_fetch(ws, hdr.ctypes.data, nr.value, mem.ctypes.data, nm.value))
+                assert_same(hdr, wh, "rv_sweep_multi_device hdr")
+                assert_same(mem, wm, "rv_sweep_multi_device members")
+                assert len(hdr) > 0
+            finally:
+                L.rv_index_free(ws)

@@ -112,6 +112,19 @@ def test_golden_through_the_class(emu_reveallib):
 def test_cache_files_round_trip(emu_reveallib, tmp_path, monkeypatch):
     """cache=1 writes .reveal.t/.sa/.lcp (interface.c:273-285); index(sa=, lcp=) reads them back (:224-231,255-262)."""
     monkeypatch.chdir(tmp_path)
+    cache_round_trip(emu_reveallib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cache_files_round_trip_cuda(tmp_path, monkeypatch):
+    """The same on the CUDA library: rv_build_cached with and without the LCP file (isa_scatter / isa_verify kernels, the
+    sparse Kasai kernel with every position marked), and a suffix array file that is no permutation."""
+    from reveal_b200 import reveallib
+    monkeypatch.chdir(tmp_path)
+    cache_round_trip(reveallib, tmp_path)
+
+
+def cache_round_trip(emu_reveallib, tmp_path):
     a = emu_reveallib.index(cache=1)
     for k, seqs in enumerate(SAMPLES):
         a.addsample("s%d" % k)

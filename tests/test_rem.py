@@ -495,3 +495,21 @@ def test_rem_sharded_recursion_two_ranks_one_gpu(tmp_path):
     for rank, _, cases in res:
         for name, nunits, owners, own_nodes in cases:
             assert owners == [0, 1], (name, nunits, owners)
+
+
+def test_rem_batched_picks_with_device_chaining_emulated(emu_reveallib, tmp_path, monkeypatch):
+    """Frontier batches hand all their MUM lists to remcore.Graph.mumpicker_batch; RV_REM_CHAIN=device sends every chaining recurrence
+    of a batch through rv_chain_batch (here: the emulated kernel) -- the graphs stay the golden ones."""
+    if emu_reveallib.name != "ext":
+        pytest.skip("the batch protocol belongs to the compiled extension")
+    from reveal_b200 import remcore
+    monkeypatch.setenv("RV_REM_CHAIN", "device")
+    remcore._set_chain_library(os.path.join(HERE, "emu", "_build", "libreveal_emu.so"))
+    try:
+        before = remcore.chain_stats()
+        for name in ("synth2_4k", "synth3_3k", "synth4_2k_seed"):
+            run_case(name, tmp_path / name if (tmp_path / name).mkdir() is None else tmp_path, emu_reveallib.mod32)
+        after = remcore.chain_stats()
+        assert after["device"] and after["device_lists"] > before["device_lists"] and after["launches"] > before["launches"]
+    finally:
+        remcore._set_chain_library("")   # back to the library next to the module

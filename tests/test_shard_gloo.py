@@ -69,13 +69,17 @@ def _anchor_worker(rank, world, port, q, lib_path):
     for length, ns in ((1800, 2), (600, 3), (1200, 2), (900, 4), (300, 2)):  # pair units and multi-sample units mixed
         T, nsep, _ = P.assemble(random_related(rng, ns, length, 4))
         units.append((T, np.asarray(nsep, dtype=np.int64), ns))
+    Tp, nsepp, _ = P.assemble(random_related(rng, 2, 1000, 4))
+    units += shard.fwd_rc_units(Tp, np.asarray(nsepp, dtype=np.int64))   # the forward / reverse-complement pair of `finish`
     got = shard.anchor_units(units, minl=8, lib=L)
     if rank == 0:
         ok = True
-        for (T, nsep, ns), res in zip(units, got):
-            o = P.Index(T, nsep, ns)
+        for u, res in zip(units, got):
+            T, nsep, ns = u[:3]
+            rc = u[3] if len(u) > 3 else 0
+            o = P.Index(T, nsep, ns, rc)
             if ns == 2:
-                ok = ok and np.array_equal(res, o.getmums(8, rem=True))
+                ok = ok and np.array_equal(res, o.getmums(8, rem=not rc))
             else:  # header rows AND the member rows their `first` column indexes (positions of every multi-MUM)
                 oh, om = o.getmultimums(8, 2)
                 ok = ok and np.array_equal(res[0], oh) and np.array_equal(res[1], om) and len(om) > 0
@@ -104,7 +108,7 @@ def test_anchor_units_sharded_world2_gloo(emu_lib):
     for name, ok, _ in res:
         assert ok, name
     counts = [r[2] for r in res if r[2] is not None][0]
-    assert len(counts) == 5 and sum(counts) > 0
+    assert len(counts) == 7 and sum(counts) > 0
 
 
 def _fixed_worker(rank, world, port, q):
