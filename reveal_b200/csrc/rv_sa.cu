@@ -74,38 +74,60 @@ struct Barriers {
     const u32 *b0, *b1, *b2;
 };
 // One pass over T: the barrier bitmaps and (PACK) the 4-bit packed text (8 symbols per word, symbol i in bits 4i..4i+3).
-// b2 must be zeroed before the launch.
+// A thread takes 16 consecutive characters (one 128-bit load; T is 16-byte aligned and readable, zero padded, up to n + 64),
+// a block 4096 characters = 4 level-1 words.  b2 must be zeroed before the launch; blocks run one past the end of the text so
+// that the packed text is zero padded.
+static const int TP_THREADS = 256;
+static const int TP_BLOCK = TP_THREADS * 16;
 template <bool PACK>
-__global__ void __launch_bounds__(1024) sa_textprep_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ bar0,
-                                                          u32 *__restrict__ bar1, u32 *__restrict__ bar2, u32 *__restrict__ packed) {
-    __shared__ u32 s_nz[32];
-    __shared__ unsigned short s_code[256];
+__global__ void __launch_bounds__(TP_THREADS) sa_textprep_kernel(const unsigned char *__restrict__ T, i64 n, CodeTable tab, u32 *__restrict__ bar0,
+                                                                u32 *__restrict__ bar1, u32 *__restrict__ bar2, u32 *__restrict__ packed) {
+    __shared__ u32 s_nz[TP_THREADS / 32];
+    __shared__ unsigned char s_code[256];
     if (PACK) {
-        if (threadIdx.x < 256) s_code[threadIdx.x] = tab.code[threadIdx.x];
+        s_code[threadIdx.x] = (unsigned char)(tab.code[threadIdx.x] & 15u);
         __syncthreads();
     }
-    i64 i = (i64)blockIdx.x * 1024 + threadIdx.x;
-    unsigned char c = i < n ? T[i] : 0;
-    unsigned m = __ballot_sync(FULL, c == '$' || c == 'N');
-    if ((threadIdx.x & 31u) == 0) {
-        bar0[i >> 5] = m;
-        s_nz[threadIdx.x >> 5] = m ? 1u : 0u;
+    const i64 i0 = (i64)blockIdx.x * TP_BLOCK + (i64)threadIdx.x * 16;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 < n) q = *(const uint4 *)(T + i0);   // bytes past n (inside the padding) are zero
+    const u32 wv[4] = {q.x, q.y, q.z, q.w};
+    u32 bits = 0, p0 = 0, p1 = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const u32 ch = (wv[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        bits |= (ch == (u32)'$' || ch == (u32)'N') ? (1u << j) : 0u;
+        if (PACK) {
+            const u32 cd = s_code[ch];
+            if (j < 8) p0 |= cd << (4 * j);
+            else p1 |= cd << (4 * (j - 8));
+        }
     }
-    if (PACK) {
-        // 8 consecutive lanes hold the 8 symbols of one packed word: OR-reduce their nibbles with shuffles
-        u32 v = i < n ? (((u32)s_code[c] & 15u) << (4 * (threadIdx.x & 7u))) : 0u;
-        v |= __shfl_xor_sync(FULL, v, 1);
-        v |= __shfl_xor_sync(FULL, v, 2);
-        v |= __shfl_xor_sync(FULL, v, 4);
-        if ((threadIdx.x & 7u) == 0) packed[i >> 3] = v;
+    if (i0 + 16 > n) {  // the last characters of the text: nothing beyond n counts
+        const int keep = i0 < n ? (int)(n - i0) : 0;
+        bits &= keep >= 16 ? 0xffffu : ((1u << keep) - 1u);
+        if (PACK && keep < 16) {
+            if (keep <= 8) { p1 = 0; p0 &= keep == 8 ? 0xffffffffu : ((1u << (4 * keep)) - 1u); }
+            else p1 &= (1u << (4 * (keep - 8))) - 1u;
+        }
+    }
+    if (PACK) *(uint2 *)(packed + (i0 >> 3)) = make_uint2(p0, p1);
+    // two neighbouring threads share one level-0 word
+    const u32 hi = __shfl_down_sync(FULL, bits, 1);
+    const u32 word = bits | (hi << 16);
+    if ((threadIdx.x & 1u) == 0) bar0[i0 >> 5] = word;
+    const unsigned nz = __ballot_sync(FULL, (threadIdx.x & 1u) == 0 && word != 0u);  // bit 2k: word k of this warp's 16
+    if ((threadIdx.x & 31u) == 0) {
+        u32 m = 0;
+        for (int k = 0; k < 16; k++) m |= ((nz >> (2 * k)) & 1u) << k;
+        s_nz[threadIdx.x >> 5] = m;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned nz = __ballot_sync(FULL, s_nz[threadIdx.x] != 0u);
-        if (threadIdx.x == 0) {
-            bar1[blockIdx.x] = nz;
-            if (nz) atomicOr(&bar2[blockIdx.x >> 5], 1u << (blockIdx.x & 31u));
-        }
+    if (threadIdx.x < TP_THREADS / 64) {  // one level-1 word per 1024 characters = two warps
+        const u32 w1 = s_nz[2 * threadIdx.x] | (s_nz[2 * threadIdx.x + 1] << 16);
+        const i64 v = (i64)blockIdx.x * (TP_BLOCK / 1024) + threadIdx.x;
+        bar1[v] = w1;
+        if (w1) atomicOr(&bar2[v >> 5], 1u << (v & 31));
     }
 }
 
@@ -267,6 +289,24 @@ struct PairChunk {
     int rounds;
     int end_closed;  // the last group of the run really ends with the run
 };
+// equal keys to the left (L, capped at 16) and right (R, capped at 15) of slot e, by one 32-key window around it: every lane
+// loads one key, a ballot does the rest (the serial walk of run_lengths would be a chain of dependent loads at the very start
+// of the warp's life).  Warp-uniform result.
+template <typename KeyT>
+__device__ __forceinline__ void window_run(const KeyT *__restrict__ keys, i64 n, i64 e, bool wanted, int &L, int &R) {
+    const unsigned lane = threadIdx.x & 31u;
+    const i64 at = e - 16 + (i64)lane;
+    const bool in = wanted && at >= 0 && at < n;
+    const KeyT k = in ? keys[at] : (KeyT)0;
+    const KeyT k0 = __shfl_sync(FULL, k, 16);
+    const unsigned eq = __ballot_sync(FULL, in && k == k0);
+    L = __clz((int)~(eq << 16));             // consecutive equal keys below bit 16, downwards
+    if (L > 16) L = 16;
+    const unsigned up = eq >> 17;            // bits for e+1 .. e+15
+    R = __ffs((int)~up) - 1;
+    if (R > 15 || R < 0) R = 15;
+}
+
 template <typename KeyT>
 __device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, u32 *s_head_raw /*[PR_ROUNDS+2]*/) {
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -274,43 +314,47 @@ __device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__res
     const i64 c0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
     i64 s = c0, end = c0 + PR_CHUNK < n ? c0 + PR_CHUNK : n;
     int end_closed = 1;
-    if (lane == 0 && c0 < n) {
-        if (c0 > 0) {
-            int L, R;
-            run_lengths(keys, n, c0, SA_SMALL_G, L, R);
-            if (L > 0 && L + R + 1 <= SA_SMALL_G) s = c0 + R + 1;  // that group belongs to the previous warp
-        }
-        if (end < n) {
-            int L, R;
-            run_lengths(keys, n, end, SA_SMALL_G, L, R);
-            if (L > 0) {
-                if (L + R + 1 <= SA_SMALL_G) end = end + R + 1;     // finish the group that straddles the nominal end
-                else end_closed = 0;                                  // a large group runs through the end
-            }
+    {
+        int L0, R0, L1, R1;
+        window_run(keys, n, c0, c0 < n && c0 > 0, L0, R0);
+        window_run(keys, n, end, c0 < n && end < n, L1, R1);
+        if (c0 < n && c0 > 0 && L0 > 0 && L0 + R0 + 1 <= SA_SMALL_G) s = c0 + R0 + 1;  // that group belongs to the previous warp
+        if (c0 < n && end < n && L1 > 0) {
+            if (L1 + R1 + 1 <= SA_SMALL_G) end = end + R1 + 1;     // finish the group that straddles the nominal end
+            else end_closed = 0;                                     // a large group runs through the end
         }
     }
-    s = __shfl_sync(FULL, s, 0);
-    end = __shfl_sync(FULL, end, 0);
-    c.end_closed = __shfl_sync(FULL, end_closed, 0);
+    c.end_closed = end_closed;
     c.s = s;
     c.nt = c0 < n && end > s ? (int)(end - s) : 0;
     c.rounds = (c.nt + 31) / 32;
     if (c.nt == 0) return;  // warp-uniform
     if (lane < 2) s_head_raw[lane ? PR_ROUNDS + 1 : 0] = 0u;
-    for (int r = 0; r < c.rounds; r++) {
+    // every load of the run in flight at once (the round count is small and fixed), then the ballots
+    KeyT kreg[PR_ROUNDS];
+    u32 sreg[PR_ROUNDS];
+    const KeyT kfirst = (lane == 0 && s > 0) ? keys[s - 1] : (KeyT)0;
+#pragma unroll
+    for (int r = 0; r < PR_ROUNDS; r++) {
+        const int t = r * 32 + (int)lane;
+        const bool valid = t < c.nt;
+        kreg[r] = valid ? keys[s + t] : (KeyT)0;
+        sreg[r] = valid ? sa[s + t] : 0u;
+    }
+    KeyT carry = kfirst;  // key of the slot before this round's first (lane 0's left neighbour)
+#pragma unroll
+    for (int r = 0; r < PR_ROUNDS; r++) {
         const int t = r * 32 + (int)lane;
         const i64 e = s + t;
         const bool valid = t < c.nt;
-        KeyT k = valid ? keys[e] : (KeyT)0;
-        KeyT kp = __shfl_up_sync(FULL, k, 1);
-        if (lane == 0) kp = (valid && e > 0) ? keys[e - 1] : (KeyT)0;
-        const bool is_head = valid && (e == 0 || k != kp);
+        KeyT kp = __shfl_up_sync(FULL, kreg[r], 1);
+        if (lane == 0) kp = carry;
+        const bool is_head = valid && (e == 0 || kreg[r] != kp);
         const unsigned hm = __ballot_sync(FULL, is_head);
         if (lane == 0) c.head[r] = hm;
-        c.ssa[t] = valid ? sa[e] : 0u;
+        if (t < PR_MAXT) c.ssa[t] = sreg[r];
+        carry = __shfl_sync(FULL, kreg[r], 31);
     }
-    for (int r = c.rounds; r < PR_ROUNDS; r++)
-        if (lane == 0) c.head[r] = 0u;
     __syncwarp();
 }
 // members to the left / right of slot t inside its group; false when the group has more than SA_SMALL_G members (or is cut by the run's end)
@@ -350,12 +394,11 @@ sa_lead_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n,
     pair_chunk_setup(c, keys, sa, n, s_head[w]);
     if (c.nt == 0) return;
     unsigned short *list = s_list[w];
-    // the sampled members of small groups that have mates
+    // the sampled members of the run (their groups are looked at when a lane takes them)
     u32 nlist = 0;
     for (int r = 0; r < c.rounds; r++) {
         const int t = r * 32 + (int)lane;
-        int L = 0, R = 0;
-        const bool samp = t < c.nt && (c.ssa[t] & (S::STEP - 1u)) == 0u && pair_chunk_group(c, t, L, R) && L + R > 0;
+        const bool samp = t < c.nt && (c.ssa[t] & (S::STEP - 1u)) == 0u;
         const unsigned m = __ballot_sync(FULL, samp);
         if (samp) list[nlist + (u32)__popc(m & lanemask_lt())] = (unsigned short)t;
         nlist += (u32)__popc(m);
@@ -365,18 +408,18 @@ sa_lead_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n,
     for (u32 i = lane; i < nlist; i += 32) {
         const int t = list[i];
         int L, R;
-        pair_chunk_group(c, t, L, R);
+        if (!pair_chunk_group(c, t, L, R) || L + R == 0) continue;
         const u32 x = c.ssa[t];
+        // bucket x / S belongs to this x alone (x is a multiple of S): its entries are written by this lane only, in order
         u64 *bucket = etab + (size_t)(x >> (S::LOG_SPW + 2u)) * ET_WAYS;
-        for (int m = t - L; m <= t + R; m++) {
+        int used = 0;
+        for (int m = t - L; m <= t + R && used < ET_WAYS; m++) {
             const u32 y = c.ssa[m];
             if (y <= x) continue;
             u32 lcp;
             bool x_less;
             if (!fwd_compare<SB>(W, n32, x, y, 0u, (u32)SA_CMP_CAP, lcp, x_less)) continue;  // too long: not recorded
-            const u64 val = ((u64)y << 32) | ((u64)lcp << 1) | (x_less ? 1ull : 0ull);
-            for (int e = 0; e < ET_WAYS; e++)
-                if (atomicCAS(bucket + e, 0ull, val) == 0ull) break;
+            bucket[used++] = ((u64)y << 32) | ((u64)lcp << 1) | (x_less ? 1ull : 0ull);
         }
     }
 }
@@ -815,7 +858,7 @@ struct SaBuffers {
     u32 *needbits;     // one bit per text position: LCP entry still missing after the comparison stage (lcp_sparse_kernel)
     int *chunk_start;  // first slot of every warp chunk of sa_pairs_kernel
     u32 *packed;       // 4-bit packed text, n/8 + 16 words
-    u32 *bar, *bar1, *bar2;  // three-level barrier bitmap: n/32 + 98, n/1024 + 8, n/32768 + 8 words
+    u32 *bar, *bar1, *bar2;  // three-level barrier bitmap: n/32 + 300, n/1024 + 16, n/32768 + 8 words
     u64 *etab;         // sampled-pair table of the comparison stage: (n/16 + 2) buckets of ET_WAYS entries
     void *rscratch;
 };
@@ -851,16 +894,16 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const bool packed = sigma <= 15 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
     // (Equal keys do not promise equal first k symbols -- a rare symbol ends the key -- so the comparisons start at the suffix itself.)
     const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
-    const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);  // one block past the end: zero padding of the packed text
+    const unsigned prep_blocks = (unsigned)((n + TP_BLOCK - 1) / TP_BLOCK + 1);  // one block past the end: zero padding of the packed text
     const Barriers bars = {B.bar, B.bar1, B.bar2};
     RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
     const int step_syms = packed ? 32 : 16;
     RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, st.s));
     RV_TRY(prof_begin(st));
     if (packed) {
-        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
+        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, TP_THREADS, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     } else {
-        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
+        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, TP_THREADS, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     }
     RV_TRY(prof_end(st, RV_PROF_TEXT, 1, (long long)n));
     const u32 *W = packed ? (const u32 *)B.packed : (const u32 *)dT;
@@ -997,9 +1040,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     B.deferred = ws.take<unsigned char>(n);
     B.needbits = ws.take<u32>(n / 32 + 2);
     B.chunk_start = ws.take<int>(n / PR_CHUNK + 2 * PR_WARPS + 8);
-    B.packed = ws.take<u32>(n / 8 + 300);  // sa_textprep_kernel writes whole 1024-symbol blocks, one block past the end
-    B.bar = ws.take<u32>(n / 32 + 98);
-    B.bar1 = ws.take<u32>(n / 1024 + 8);
+    B.packed = ws.take<u32>(n / 8 + 1100);  // sa_textprep_kernel writes whole 4096-symbol blocks, one block past the end
+    B.bar = ws.take<u32>(n / 32 + 300);
+    B.bar1 = ws.take<u32>(n / 1024 + 16);
     B.bar2 = ws.take<u32>(n / 32768 + 8);
     B.etab = ws.take<u64>((size_t)(n / 16 + 2) * ET_WAYS);
     if (!B.deferred || !B.needbits || !B.chunk_start || !B.packed || !B.bar || !B.bar1 || !B.bar2 || !B.etab || !B.k0 || !B.k1 || !B.v0 || !B.v1 || !B.posA || !B.posB || !B.grpA || !B.grpB || !B.tile_max || !B.tile_cnt ||
@@ -1156,16 +1199,16 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
 int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *dSA, const int *dISA, int *dLCP) {
     if (n <= 0) return RV_OK;
     const size_t ws_mark = ws.off;
-    u32 *bar = ws.take<u32>(n / 32 + 98), *bar1 = ws.take<u32>(n / 1024 + 8), *bar2 = ws.take<u32>(n / 32768 + 8), *needbits = ws.take<u32>(n / 32 + 2);
+    u32 *bar = ws.take<u32>(n / 32 + 300), *bar1 = ws.take<u32>(n / 1024 + 16), *bar2 = ws.take<u32>(n / 32768 + 8), *needbits = ws.take<u32>(n / 32 + 2);
     if (!bar || !bar1 || !bar2 || !needbits) {
         set_error("lcp_build: workspace too small");
         return RV_ERR_NOMEM;
     }
     CodeTable tab;
     memset(&tab, 0, sizeof tab);
-    const unsigned prep_blocks = (unsigned)((n + 1023) / 1024 + 1);
+    const unsigned prep_blocks = (unsigned)((n + TP_BLOCK - 1) / TP_BLOCK + 1);
     RV_CUDA(cudaMemsetAsync(bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
-    RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, 1024, 0, st.s, dT, n, tab, bar, bar1, bar2, (u32 *)nullptr);
+    RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, TP_THREADS, 0, st.s, dT, n, tab, bar, bar1, bar2, (u32 *)nullptr);
     const Barriers bars = {bar, bar1, bar2};
     RV_CUDA(cudaMemsetAsync(needbits, 0xff, (size_t)(n / 32 + 2) * 4, st.s));
     const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
