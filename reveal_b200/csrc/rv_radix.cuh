@@ -16,6 +16,9 @@ namespace rv {
 #ifndef RV_TMA_ON
 #define RV_TMA_ON 1
 #endif
+#ifndef RV_RS_MATCH
+#define RV_RS_MATCH 0
+#endif
 static const int RS_THREADS = 256;
 static const int RS_WARPS = RS_THREADS / 32;
 #ifndef RV_RS_IPT
@@ -285,11 +288,16 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
         int idx = wbase + k * 32 + (int)l;
         bool valid = idx < cnt;
         u32 d = (u32)(key[k] >> shift) & mask;
+#if RV_RS_MATCH
+        // one match instruction instead of a ballot per digit bit; lanes past the end of the tile share a value no digit has
+        unsigned peers = __match_any_sync(FULL, valid ? d : 0xffffffffu);
+#else
         unsigned peers = __ballot_sync(FULL, valid);
         for (int b = 0; b < dbits; b++) {
             unsigned bal = __ballot_sync(FULL, (d >> b) & 1u);
             peers &= ((d >> b) & 1u) ? bal : ~bal;
         }
+#endif
         u32 old = 0;
         const int leader = __ffs((int)peers) - 1;  // invalid lanes: garbage, unused
         if (valid && (int)l == leader) {

@@ -39,7 +39,10 @@ static const int AP_IPT = 8;
 static const int AP_TILE = AP_THREADS * AP_IPT;  // 2048 active entries per tile
 
 static const int SA_SMALL_G = 16;     // largest group finished by direct comparison
-static const int SA_CMP_CAP = 4096;   // bytes after which a comparison is deferred to doubling
+#ifndef RV_SA_CMP_CAP
+#define RV_SA_CMP_CAP 65536
+#endif
+static const int SA_CMP_CAP = RV_SA_CMP_CAP;   // symbols after which a comparison gives up and its group is left to stage 4
 
 struct CodeTable {
     unsigned short code[256];  // 0 is reserved for "past the end of the text"

@@ -46,16 +46,11 @@ class _Impl(object):
         self.name, self.index, self.error, self.index64, self.mod32, self.mod64 = name, mod32.index, mod32.error, mod64.index, mod32, mod64
 
 
-@pytest.fixture(params=["ext", "ctypes"])
-def emu_reveallib(request, emu_lib, monkeypatch):
-    """The drop-in `index` type with the emulated kernels injected in place of the CUDA library, once as the compiled
-    CPython extension (reveal_b200.reveallib, csrc/ext/reveallib_module.cpp) and once as its ctypes twin."""
+@pytest.fixture
+def emu_reveallib(emu_lib):
+    """The drop-in `index` type (the compiled CPython extension reveal_b200.reveallib, csrc/ext/reveallib_module.cpp) with the
+    emulated kernels injected in place of the CUDA library."""
     emu_path = os.path.join(ROOT, "tests", "emu", "_build", "libreveal_emu.so")
-    if request.param == "ctypes":
-        from reveal_b200 import _native, reveallib64_ctypes, reveallib_ctypes
-        monkeypatch.setattr(_native, "_lib", emu_lib)
-        yield _Impl("ctypes", reveallib_ctypes, reveallib64_ctypes)
-        return
     from reveal_b200 import build
     build.build_extension()
     from reveal_b200 import reveallib, reveallib64

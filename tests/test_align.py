@@ -76,8 +76,6 @@ CASES = [
 @needs_ref
 @pytest.mark.parametrize("name,ns,length,sigma,minl,minn", CASES)
 def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma, minl, minn):
-    if emu_reveallib.name == "ctypes" and name in ("triple", "five"):
-        pytest.skip("the ctypes twin runs a subset (suite time); the device code is the same")
     rng = np.random.default_rng(len(name) * 100 + length)
     samples = random_related(rng, ns, length, sigma, snp=0.03)
     ref = run_reference(samples, minl, minn)
@@ -90,8 +88,6 @@ def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma
 @pytest.mark.parametrize("small_maxn,bubble_maxn", [("0", "100000"), ("0", "0"), ("600", "0")])
 def test_align_general_step_paths_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn):
     """RV_SMALL_MAXN / RV_BUBBLE_BLOCK_MAXN force the multi-kernel step and the grid-wide bubble detection."""
-    if emu_reveallib.name == "ctypes" and (small_maxn, bubble_maxn) != ("0", "0"):
-        pytest.skip("the ctypes twin runs one setting (suite time); these switches act below the C-ABI")
     monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
     monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
     rng = np.random.default_rng(77)
@@ -178,8 +174,6 @@ def test_align_callback_failure_is_reported_and_leaves_no_wreckage(emu_reveallib
 def test_splitindex_matches_reference(emu_reveallib, ns, length, minl):
     """index.splitindex (reveal.c:1515-1748): the recursion driven from Python, two levels deep, against the
     reference's own splitindex -- children's n / nsamples / depth / nodes / bounds / SA / LCP and the text."""
-    if emu_reveallib.name == "ctypes":
-        pytest.skip("splitindex is part of the compiled extension")
     splitindex_case(emu_reveallib.mod32, ns, length, minl)
 
 

@@ -159,8 +159,6 @@ def test_trim_overlap_and_gapcost_small_cases():
 
 @pytest.mark.parametrize("name", ["t1_t2", "synth2_4k", "synth3_3k", "synth4_2k_seed", "gfa3_x_gfa2_5x3k", "synth2_4k_m0_pvalue"])
 def test_rem_emulated_small(emu_reveallib, tmp_path, name):
-    if emu_reveallib.name == "ctypes" and name not in ("t1_t2", "synth2_4k"):
-        pytest.skip("the ctypes twin runs the two smallest cases (suite time)")
     run_case(name, tmp_path, emu_reveallib.mod32)
 
 
@@ -184,8 +182,6 @@ def test_rem_driver_on_reference_extension(tmp_path, monkeypatch, name, graph):
 
 def test_rem_emulated_wide_index_module(emu_reveallib, tmp_path):
     """The same driver on reveallib64 (wider integers on the way out of the extension)."""
-    if emu_reveallib.name == "ctypes":
-        pytest.skip("compiled extension only (suite time)")
     run_case("synth3_3k", tmp_path, emu_reveallib.mod64)
 
 
@@ -224,8 +220,6 @@ def test_rem_inconsistent_intervals_are_refused(emu_reveallib, tmp_path):
     """A graph whose paths run through one segment on both strands over parallel links: graphalign hands back
     leading intervals that are not part of the sub-index.  The reference's C aligner writes out of bounds on this
     input (segmentation fault); here the step is refused with reveallib.error."""
-    if emu_reveallib.name == "ctypes":
-        pytest.skip("compiled extension only (suite time)")
     length = 3000
     g0, g1 = [g.tobytes().decode() for g in synth.genomes(2, length, seed=51)]
     cuts = [0, length // 3, 2 * length // 3, length]
@@ -500,8 +494,6 @@ def test_rem_sharded_recursion_two_ranks_one_gpu(tmp_path):
 def test_rem_batched_picks_with_device_chaining_emulated(emu_reveallib, tmp_path, monkeypatch):
     """Frontier batches hand all their MUM lists to remcore.Graph.mumpicker_batch; RV_REM_CHAIN=device sends every chaining recurrence
     of a batch through rv_chain_batch (here: the emulated kernel) -- the graphs stay the golden ones."""
-    if emu_reveallib.name != "ext":
-        pytest.skip("the batch protocol belongs to the compiled extension")
     from reveal_b200 import remcore
     monkeypatch.setenv("RV_REM_CHAIN", "device")
     remcore._set_chain_library(os.path.join(HERE, "emu", "_build", "libreveal_emu.so"))

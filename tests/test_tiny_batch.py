@@ -44,8 +44,6 @@ def expected(pairs, minl):
 
 @pytest.mark.parametrize("minl", [8, 20])
 def test_getmums_batch_emulated(emu_reveallib, minl):
-    if emu_reveallib.name != "ext":
-        pytest.skip("module function of the compiled extension")
     pairs = flank_pairs(np.random.default_rng(minl), 40)
     got = emu_reveallib.mod32.getmums_batch(pairs, minl)
     assert got == expected(pairs, minl)
