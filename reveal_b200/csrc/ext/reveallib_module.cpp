@@ -564,7 +564,7 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
 
 // wall time of the parts of the last align() (seconds): where a recursion spends its time
 struct AlignStats {
-    double extract = 0, pick = 0, galign = 0, parse = 0, step = 0, child = 0, total = 0;
+    double extract = 0, pick = 0, galign = 0, parse = 0, step = 0, child = 0, total = 0, prefix = 0;
     long long steps = 0, picks = 0, batches = 0;
 };
 static AlignStats g_align_stats;
@@ -595,7 +595,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn",  // interface.c:303
                                    "shard_rank", "shard_world", "shard_grain", "mumpicker_batch", nullptr};
     PyObject *mumpicker, *graphalign, *mumpicker_batch = nullptr;
-    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 4;
+    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 2;
     if (self->mainidx || !self->built) {
         PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
         return nullptr;
@@ -831,6 +831,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     if (!ok || !prefix) break;
     // ---- the part above the cut is done on every rank: deal the units out ----
     prefix = false;
+    as.prefix = now_s() - t_begin;
     {
         std::vector<size_t> order(units.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
@@ -868,7 +869,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
 
 static PyObject *mod_align_stats(PyObject *, PyObject *) {
     const AlignStats &a = g_align_stats;
-    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:L,s:L,s:L}", "total_s", a.total, "sweep_fetch_s", a.extract, "mumpicker_s", a.pick, "graphalign_s", a.galign,
+    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:d,s:L,s:L,s:L}", "total_s", a.total, "above_cut_s", a.prefix, "sweep_fetch_s", a.extract, "mumpicker_s", a.pick, "graphalign_s", a.galign,
                          "parse_s", a.parse, "device_step_s", a.step, "children_s", a.child, "steps", a.steps, "mumpicker_calls", a.picks, "device_batches", a.batches);
 }
 

@@ -471,7 +471,7 @@ template <typename KeyT, int SB>
 __global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
 sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W, Barriers bars,
                 const u64 *__restrict__ etab, int *__restrict__ SA, int *__restrict__ rank, int *__restrict__ LCP, unsigned char *__restrict__ deferred,
-                u32 *__restrict__ flag_large, int *__restrict__ chunk_start, u32 *__restrict__ needbits) {
+                u32 *__restrict__ flag_large, int *__restrict__ chunk_start, u32 *__restrict__ needbits, int key_digits2) {
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
     __shared__ u32 s_lcp[PR_WARPS][PR_MAXT];
     __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
@@ -599,6 +599,18 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         if (b == 0xFFFFFFFFu) {          // the left neighbour is not known yet: this suffix's LCP entry comes from that pass too
             atomicOr(&needbits[a >> 5], 1u << (a & 31u));
             continue;
+        }
+        if (sizeof(KeyT) == 4 && key_digits2 > 0) {
+            // Neighbouring groups differ inside their keys.  With 2-bit digits and every rare symbol a barrier symbol, the equal
+            // leading digits of the two keys ARE the common prefix, provided no '$'/'N' (and not the end of the text) lies within
+            // those symbols of either suffix -- two key loads and two looks at the cache-resident bitmap level instead of a
+            // comparison on the text.
+            const u32 kc = (u32)keys[s + f], kp = (u32)keys[s + f - 1];
+            const u32 lk = (u32)(__clz((int)(kc ^ kp)) - (32 - 2 * key_digits2)) >> 1;
+            if (a + lk + 1u <= n32 && b + lk + 1u <= n32 && first_barrier(bars, a, lk + 1u) == lk + 1u && first_barrier(bars, b, lk + 1u) == lk + 1u) {
+                LCP[s + f] = (int)lk;
+                continue;
+            }
         }
         LCP[s + f] = direct_lcp<SB>(W, n32, a, b, bars);
     }
@@ -899,6 +911,15 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const unsigned pblocks = (unsigned)((n + pr_per_block - 1) / pr_per_block);
     const unsigned prep_blocks = (unsigned)((n + TP_BLOCK - 1) / TP_BLOCK + 1);  // one block past the end: zero padding of the packed text
     const Barriers bars = {B.bar, B.bar1, B.bar2};
+    // keys whose equal leading digits can stand for the common prefix of neighbouring groups (sa_place_kernel): 2-bit digits,
+    // a 32-bit key, and no rare symbol that is not a '$'/'N' barrier (the bitmap then rules rare symbols out)
+    int key_digits2 = 0;
+    if (sizeof(KeyT) == 4 && base == 4 && !getenv("RV_SA_NO_KEYLCP")) {
+        bool ok = true;
+        for (int c = 0; c < 256; c++)
+            if ((st.alpha.kcls[c] & 0x100) && st.alpha.code[c] && c != '$' && c != 'N') ok = false;
+        if (ok) key_digits2 = k;
+    }
     RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
     const int step_syms = packed ? 32 : 16;
     RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, st.s));
@@ -920,10 +941,10 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     RV_TRY(prof_begin(st));
     if (packed) {
         RV_LAUNCH((sa_place_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
-                  B.small + 257, B.chunk_start, B.needbits);
+                  B.small + 257, B.chunk_start, B.needbits, key_digits2);
     } else {
         RV_LAUNCH((sa_place_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
-                  B.small + 257, B.chunk_start, B.needbits);
+                  B.small + 257, B.chunk_start, B.needbits, key_digits2);
     }
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
     st.launches += 3;

@@ -431,6 +431,113 @@ class Rem(object):
             if was_on:
                 gc.enable()
 
+    # ---- a rank's part of the graph as flat arrays: what travels between the ranks of a sharded recursion ----------------------
+    @staticmethod
+    def _pack_part(nodes, edges, texts, markers):
+        """Node rows, edge rows and marked text stretches as one bytes object of flat numpy arrays (pickling hundreds of
+        thousands of small tuples, dicts and sets costs several times more than filling arrays)."""
+        import io
+        import pickle
+
+        import numpy as np
+        mi = {m: i for i, m in enumerate(markers)}
+        nb = np.fromiter((k.begin for k, _ in nodes), np.int64, len(nodes))
+        ne = np.fromiter((k.end for k, _ in nodes), np.int64, len(nodes))
+        al = np.fromiter((-1 if a.get("aligned") is None else a["aligned"] for _, a in nodes), np.int8, len(nodes))
+        noff = np.fromiter((len(a.get("offsets") or ()) for _, a in nodes), np.int32, len(nodes))
+        osid = np.fromiter((sid for _, a in nodes for sid in (a.get("offsets") or ())), np.int32, int(noff.sum()))
+        oval = np.fromiter((v for _, a in nodes for v in (a.get("offsets") or {}).values()), np.int64, int(noff.sum()))
+        nextra = {i: {k: v for k, v in a.items() if k not in ("offsets", "aligned")} for i, (_, a) in enumerate(nodes) if len(a) > 2}
+
+        def ends(which):
+            b = np.empty(len(edges), np.int64)
+            e = np.empty(len(edges), np.int64)
+            for i, row in enumerate(edges):
+                k = row[which]
+                if isinstance(k, str):
+                    b[i], e[i] = -1 - mi[k], 0
+                else:
+                    b[i], e[i] = k.begin, k.end
+            return b, e
+        ub, ue = ends(0)
+        vb, ve = ends(1)
+        orient = np.fromiter(((a["ofrom"] == "-") | ((a["oto"] == "-") << 1) for _, _, a in edges), np.int8, len(edges))
+        npath = np.fromiter((len(a["paths"]) for _, _, a in edges), np.int32, len(edges))
+        paths = np.fromiter((x for _, _, a in edges for x in a["paths"]), np.int32, int(npath.sum()))
+        eextra = {i: {k: v for k, v in a.items() if k not in ("paths", "ofrom", "oto")} for i, (_, _, a) in enumerate(edges) if len(a) > 3}
+        tb = np.fromiter((b for b, _ in texts), np.int64, len(texts))
+        tl = np.fromiter((len(t) for _, t in texts), np.int64, len(texts))
+        tt = np.frombuffer("".join(t for _, t in texts).encode("latin-1"), np.uint8)
+        buf = io.BytesIO()
+        np.savez(buf, nb=nb, ne=ne, al=al, noff=noff, osid=osid, oval=oval, ub=ub, ue=ue, vb=vb, ve=ve, orient=orient, npath=npath, paths=paths,
+                 tb=tb, tl=tl, tt=tt, extra=np.frombuffer(pickle.dumps((nextra, eextra, len(markers))), np.uint8))
+        return buf.getvalue()
+
+    @staticmethod
+    def _unpack_part(blob, markers):
+        """Inverse of _pack_part; marker ends are spelled with THIS rank's marker names (same creation order on every rank)."""
+        import io
+        import pickle
+
+        import numpy as np
+        z = np.load(io.BytesIO(blob))
+        nextra, eextra, nmark = pickle.loads(z["extra"].tobytes())
+        if nmark != len(markers):
+            raise RuntimeError("sharded recursion: the ranks read different inputs")
+        nb, ne, al, noff = z["nb"].tolist(), z["ne"].tolist(), z["al"].tolist(), z["noff"].tolist()
+        osid, oval = z["osid"].tolist(), z["oval"].tolist()
+        nodes, at = [], 0
+        for i in range(len(nb)):
+            attrs = {"offsets": dict(zip(osid[at:at + noff[i]], oval[at:at + noff[i]]))}
+            if al[i] >= 0:
+                attrs["aligned"] = al[i]
+            at += noff[i]
+            if i in nextra:
+                attrs.update(nextra[i])
+            nodes.append((Interval(nb[i], ne[i]), attrs))
+        ub, ue, vb, ve = z["ub"].tolist(), z["ue"].tolist(), z["vb"].tolist(), z["ve"].tolist()
+        orient, npath, paths = z["orient"].tolist(), z["npath"].tolist(), z["paths"].tolist()
+        edges, at = [], 0
+        for i in range(len(ub)):
+            u = markers[-1 - ub[i]] if ub[i] < 0 else Interval(ub[i], ue[i])
+            v = markers[-1 - vb[i]] if vb[i] < 0 else Interval(vb[i], ve[i])
+            attrs = {"paths": set(paths[at:at + npath[i]]), "ofrom": "-" if orient[i] & 1 else "+", "oto": "-" if orient[i] & 2 else "+"}
+            at += npath[i]
+            if i in eextra:
+                attrs.update(eextra[i])
+            edges.append((u, v, attrs))
+        tb, tl = z["tb"].tolist(), z["tl"].tolist()
+        tt = z["tt"].tobytes().decode("latin-1")
+        texts, at = [], 0
+        for b, ln in zip(tb, tl):
+            texts.append((b, tt[at:at + ln]))
+            at += ln
+        return nodes, edges, texts
+
+    @staticmethod
+    def _gather_blobs(blob, rank, world, group):
+        """bytes of every rank -> list on rank 0 (None elsewhere).  Two collectives on the job's existing communicator (the lengths,
+        then the padded bytes: all_gather); a `gather` would be point-to-point sends, whose NCCL connections are only set up at
+        first use -- that set-up, not the megabytes, was most of the collection time."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        size = torch.tensor([len(blob) if blob is not None else 0], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(size) for _ in range(world)]
+        dist.all_gather(sizes, size, group=group)
+        sizes = [int(x.item()) for x in sizes]
+        width = max(max(sizes), 1)
+        mine = torch.zeros(width, dtype=torch.uint8, device=dev)
+        if blob:
+            mine[:len(blob)] = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(dev)
+        rows = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(rows, mine, group=group)
+        if rank != 0:
+            return None
+        return [rows[r][:sizes[r]].cpu().numpy().tobytes() if sizes[r] else None for r in range(world)]
+
     def _collect_shards(self, nodes, edges):
         """Sharded recursion (index.align(shard_rank=, shard_world=)): every rank processed the tree above the cut and its own
         units below it, so its graph is final for the nodes of its units and stale for the units of the others.  The owners
@@ -457,27 +564,27 @@ class Rem(object):
         who = {key: owner_of(key) for key, _ in nodes}
         T = idx.T
         markers = [k for k, _ in nodes if isinstance(k, str)]   # start / end markers: random names, same creation order on every rank
-        mine = ([(k, a) for k, a in nodes if who[k] == rank],
-                [(u, v, a) for u, v, a in edges if who.get(u) == rank or who.get(v) == rank],
-                [(b, T[b:e]) for b, e, owner in spans if owner == rank], markers)
-        parts = [None] * world if rank == 0 else None
+        own_nodes = sum(1 for k, _ in nodes if who[k] == rank)
+        mine = None
+        if rank != 0:
+            mine = self._pack_part([(k, a) for k, a in nodes if who[k] == rank],
+                                   [(u, v, a) for u, v, a in edges if who.get(u) == rank or who.get(v) == rank],
+                                   [(b, T[b:e]) for b, e, owner in spans if owner == rank], markers)
         t1 = time.perf_counter()
-        dist.gather_object(mine if rank != 0 else None, parts, dst=0, group=group)
+        parts = self._gather_blobs(mine, rank, world, group)
         t2 = time.perf_counter()
         self.shard_stats = {"units": len(idx.shard_units), "own_units": sum(1 for o, _ in idx.shard_units if o == rank),
-                            "own_nodes": len(mine[0]), "pack_s": t1 - t0, "gather_s": t2 - t1}
+                            "own_nodes": own_nodes, "pack_s": t1 - t0, "gather_s": t2 - t1,
+                            "part_bytes": len(mine) if mine is not None else 0}
         if rank != 0:
             return nodes, edges
         foreign = {k for k, o in who.items() if o is not None and o != 0}
         out_nodes = [(k, a) for k, a in nodes if k not in foreign]
         out_edges = [(u, v, a) for u, v, a in edges if u not in foreign and v not in foreign]
         for r in range(1, world):
-            pn, pe, pt, their_markers = parts[r]
-            if len(their_markers) != len(markers):
-                raise RuntimeError("sharded recursion: rank %d read other inputs than rank 0" % r)
-            name = dict(zip(their_markers, markers))
+            pn, pe, pt = self._unpack_part(parts[r], markers)
             out_nodes.extend(pn)
-            out_edges.extend((name.get(u, u) if isinstance(u, str) else u, name.get(v, v) if isinstance(v, str) else v, a) for u, v, a in pe)
+            out_edges.extend(pe)
             for b, text in pt:
                 idx.puttext(b, text)
         known = {k for k, _ in out_nodes}
