@@ -624,10 +624,38 @@ static PyObject *Graph_graphalign(Graph *g, PyObject *args) {
 }
 
 // ---- the mumpicker (rem.Rem.graphmumpicker, default flow; reference: schemes.py:197-361) ---------------------------------------
+// A few elements inline, the heap only beyond that: an anchor has one position per sample (two, mostly), and the mumpicker
+// sorts, copies and filters lists of tens of thousands of anchors at the top of the recursion -- with std::vector members every
+// one of those moves is an allocation.
+template <class T, int N> struct SmallVec {
+    T inl[N];
+    std::vector<T> more;
+    uint32_t count = 0;
+    size_t size() const { return count; }
+    bool empty() const { return count == 0; }
+    T *data() { return count <= (uint32_t)N ? inl : more.data(); }
+    const T *data() const { return count <= (uint32_t)N ? inl : more.data(); }
+    T *begin() { return data(); }
+    T *end() { return data() + count; }
+    const T *begin() const { return data(); }
+    const T *end() const { return data() + count; }
+    T &operator[](size_t i) { return data()[i]; }
+    const T &operator[](size_t i) const { return data()[i]; }
+    void push_back(const T &v) {
+        if (count < (uint32_t)N) inl[count] = v;
+        else {
+            if (count == (uint32_t)N) more.assign(inl, inl + N);
+            more.push_back(v);
+        }
+        count++;
+    }
+    template <class A, class B> void emplace_back(A a, B b) { push_back(T(a, b)); }
+};
+
 struct Mum {
     int64_t l;
     long n;
-    std::vector<std::pair<long, int64_t>> sp;  // (sample of the index, position), in the order of the tuple
+    SmallVec<std::pair<long, int64_t>, 4> sp;  // (sample of the index, position), in the order of the tuple
     PyObject *orig;                            // the caller's tuple while the anchor is untouched (borrowed)
     PyObject *spd;                             // the caller's position tuple while the positions are untouched (borrowed)
 };
@@ -635,12 +663,38 @@ struct Mum {
 struct Rel {
     int64_t l;
     long n;
-    std::vector<std::pair<int32_t, int64_t>> point;  // (path id, coordinate), insertion-ordered like the dict it mirrors
+    SmallVec<std::pair<int32_t, int64_t>, 4> point;  // (path id, coordinate), insertion-ordered like the dict it mirrors
     int src;                                         // index into the picked anchors
-    std::vector<int64_t> values() const {
-        std::vector<int64_t> v;
-        for (auto &kv : point) v.push_back(kv.second);
-        return v;
+    uint64_t value_hash() const {                    // of the coordinate values in order (the reference keys a dict by that tuple)
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ point.size();
+        for (auto &kv : point) h = (h ^ (uint64_t)kv.second) * 0xff51afd7ed558ccdull, h ^= h >> 29;
+        return h;
+    }
+    bool same_values(const Rel &o) const {
+        if (point.size() != o.point.size()) return false;
+        for (size_t i = 0; i < point.size(); i++)
+            if (point[i].second != o.point[i].second) return false;
+        return true;
+    }
+};
+
+// origin: coordinate-value tuple of an anchor -> index of the LAST picked anchor with that tuple (the reference's
+// `origin[tuple(r[2].values())] = m`, schemes.py:236-240).  A hash on the values, verified on the stored copy; the rare tuple
+// whose hash slot was taken over by another tuple is found by a scan from the end.
+struct Origin {
+    std::unordered_map<uint64_t, int> slot;
+    std::vector<Rel> by_src;   // rel of picked anchor i (before the list is sorted and cut)
+    void build(const std::vector<Rel> &rel) {
+        by_src = rel;
+        slot.reserve(rel.size() * 2);
+        for (size_t i = 0; i < rel.size(); i++) slot[rel[i].value_hash()] = (int)i;
+    }
+    int find(const Rel &r) const {
+        auto it = slot.find(r.value_hash());
+        if (it != slot.end() && by_src[(size_t)it->second].same_values(r)) return it->second;
+        for (size_t i = by_src.size(); i-- > 0;)
+            if (by_src[i].same_values(r)) return (int)i;
+        return -1;
     }
 };
 
@@ -741,7 +795,7 @@ struct PickJob {
     PyObject *leftnode = nullptr, *rightnode = nullptr;   // borrowed
     std::vector<Mum> all, picked;
     std::vector<Rel> rel;
-    std::map<std::vector<int64_t>, int> origin;
+    Origin origin;
     std::vector<int32_t> keys;
     size_t k = 0, m = 0;
     std::vector<int64_t> left, right;
@@ -795,7 +849,6 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
     // anchors in path coordinates (schemes.lookup / maptooffsets)
     std::vector<Rel> &rel = J.rel;
     rel.assign(picked.size(), Rel());
-    std::map<std::vector<int64_t>, int> &origin = J.origin;
     for (size_t i = 0; i < picked.size(); i++) {
         Rel &r = rel[i];
         r.l = picked[i].l;
@@ -815,8 +868,8 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
                 if (!found) r.point.emplace_back(kv.first, kv.second + shift);
             }
         }
-        origin[r.values()] = (int)i;
     }
+    J.origin.build(rel);
     std::stable_sort(rel.begin(), rel.end(), [](const Rel &a, const Rel &b) { return a.n != b.n ? a.n < b.n : a.l < b.l; });
     auto keyset = [](const Rel &r) {
         std::vector<int32_t> k;
@@ -912,7 +965,7 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
 static PyObject *pick_finish(Graph *g, PickJob &J) {
     std::vector<Mum> &picked = J.picked;
     std::vector<Rel> &rel = J.rel;
-    std::map<std::vector<int64_t>, int> &origin = J.origin;
+    const Origin &origin = J.origin;
     const long long seedsize = J.seedsize;
     std::vector<std::pair<int, int64_t>> skipleft, skipright;  // (picked index, score relative to the split)
     int split = J.split;                                        // index into rel
@@ -937,16 +990,16 @@ static PyObject *pick_finish(Graph *g, PickJob &J) {
             int64_t at_split = 0;
             for (auto &c : chained) {
                 if (c.first == split) { at_split = c.second; after = true; continue; }
-                auto it = origin.find(rel[c.first].values());
-                if (it == origin.end()) continue;
-                if (picked[it->second].l < seedsize) continue;
-                (after ? skipright : skipleft).emplace_back(it->second, c.second - at_split);
+                const int src = origin.find(rel[c.first]);
+                if (src < 0) continue;
+                if (picked[(size_t)src].l < seedsize) continue;
+                (after ? skipright : skipleft).emplace_back(src, c.second - at_split);
             }
         }
     }
-    auto it = origin.find(rel[split].values());
-    if (it == origin.end()) { PyErr_SetString(PyExc_RuntimeError, "picked anchor lost its origin"); return nullptr; }
-    PyObject *anchor = mum_object(picked[it->second]);
+    const int split_src = origin.find(rel[split]);
+    if (split_src < 0) { PyErr_SetString(PyExc_RuntimeError, "picked anchor lost its origin"); return nullptr; }
+    PyObject *anchor = mum_object(picked[(size_t)split_src]);
     PyObject *lists[2];
     for (int side = 0; side < 2; side++) {
         auto &src = side == 0 ? skipleft : skipright;
