@@ -20,6 +20,7 @@
 #include <string>
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <map>
 #include <unordered_map>
@@ -744,19 +745,22 @@ static void trim_overlap(std::vector<Mum> &mums) {
     const size_t ncoord = mums[0].sp.size();
     for (size_t coord = 0; coord < ncoord; coord++) {
         if (mums.size() <= 1) break;
-        std::stable_sort(mums.begin(), mums.end(), [coord](const Mum &a, const Mum &b) {
-            if (a.sp[coord].second != b.sp[coord].second) return a.sp[coord].second < b.sp[coord].second;
-            return a.l > b.l;
-        });
+        // order by (position in this coordinate, longer first), stable: sorted as small (key, index) records, anchors moved once
         const size_t n = mums.size();
+        struct Key { int64_t pos, l; uint32_t at; };
+        std::vector<Key> keyv(n);
+        for (size_t i = 0; i < n; i++) keyv[i] = Key{mums[i].sp[coord].second, mums[i].l, (uint32_t)i};
+        std::stable_sort(keyv.begin(), keyv.end(), [](const Key &a, const Key &b) { return a.pos != b.pos ? a.pos < b.pos : a.l > b.l; });
         std::vector<int64_t> ends(n);
-        for (size_t i = 0; i < n; i++) ends[i] = mums[i].sp[coord].second + mums[i].l;
+        for (size_t i = 0; i < n; i++) ends[i] = keyv[i].pos + keyv[i].l;
         std::vector<Mum> kept;
+        kept.reserve(n);
         for (size_t i = 0; i < n; i++)  // the reference compares the FIRST anchor with its successor, or (i-1 = -1) with the last one
-            if ((i == 0 && ends[1] > ends[0]) || ends[(i + n - 1) % n] < ends[i]) kept.push_back(mums[i]);
+            if ((i == 0 && ends[1] > ends[0]) || ends[(i + n - 1) % n] < ends[i]) kept.push_back(mums[keyv[i].at]);
         mums.swap(kept);
         if (mums.size() <= 1) break;
         std::vector<Mum> trimmed;
+        trimmed.reserve(mums.size());
         trimmed.push_back(mums[0]);
         for (size_t i = 1; i < mums.size(); i++) {
             Mum mum = mums[i];
@@ -807,13 +811,18 @@ struct PickJob {
 };
 
 // 1: go on (run the recurrence if need_dp, then pick_finish); 0: the answer is the empty tuple; -1: error set
+static double pk_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static double g_pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
+    double pk_t = pk_now(), pk_u;
+#define PK_MARK(i) pk_u = pk_now(); g_pk[i] += pk_u - pk_t; pk_t = pk_u;
     const long nsamples = J.nsamples, maxmums = J.maxmums;
     const int trim = J.trim;
     const long long wscore = J.wscore;
     PyObject *leftnode = J.leftnode, *rightnode = J.rightnode;
     std::vector<Mum> &all = J.all, &picked = J.picked;
     if (!parse_mums(list, all)) return -1;
+    PK_MARK(0)
     for (auto &m : all)
         if (m.n == nsamples) picked.push_back(m);
     if (picked.empty() && nsamples > 2) {  // schemes.segment: the sample group with the largest total length x group size
@@ -845,7 +854,17 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
         trim_overlap(picked);
         if (picked.empty()) return 0;
     }
-    std::stable_sort(picked.begin(), picked.end(), [](const Mum &a, const Mum &b) { return a.l > b.l; });
+    PK_MARK(1)
+    {   // longest first, stable: sort an index permutation, move the anchors once
+        std::vector<uint32_t> perm(picked.size());
+        for (size_t i = 0; i < perm.size(); i++) perm[i] = (uint32_t)i;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return picked[a].l > picked[b].l; });
+        std::vector<Mum> sorted;
+        sorted.reserve(picked.size());
+        for (uint32_t i : perm) sorted.push_back(picked[i]);
+        picked.swap(sorted);
+    }
+    PK_MARK(2)
     // anchors in path coordinates (schemes.lookup / maptooffsets)
     std::vector<Rel> &rel = J.rel;
     rel.assign(picked.size(), Rel());
@@ -869,20 +888,39 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
             }
         }
     }
+    PK_MARK(3)
     J.origin.build(rel);
-    std::stable_sort(rel.begin(), rel.end(), [](const Rel &a, const Rel &b) { return a.n != b.n ? a.n < b.n : a.l < b.l; });
-    auto keyset = [](const Rel &r) {
-        std::vector<int32_t> k;
-        for (auto &kv : r.point) k.push_back(kv.first);
-        std::sort(k.begin(), k.end());
-        return k;
+    PK_MARK(4)
+    {
+        std::vector<uint32_t> perm(rel.size());
+        for (size_t i = 0; i < perm.size(); i++) perm[i] = (uint32_t)i;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rel[a].n != rel[b].n ? rel[a].n < rel[b].n : rel[a].l < rel[b].l; });
+        std::vector<Rel> sorted;
+        sorted.reserve(rel.size());
+        for (uint32_t i : perm) sorted.push_back(rel[i]);
+        rel.swap(sorted);
+    }
+    auto same_keyset = [](const Rel &a, const Rel &b) {  // the same set of path ids (a path id occurs once per anchor)
+        if (a.point.size() != b.point.size()) return false;
+        for (auto &x : a.point) {
+            bool found = false;
+            for (auto &y : b.point)
+                if (y.first == x.first) { found = true; break; }
+            if (!found) return false;
+        }
+        return true;
     };
     {
-        const std::vector<int32_t> want = keyset(rel.back());
-        std::vector<Rel> same;
+        const Rel want = rel.back();
+        bool all = true;
         for (auto &r : rel)
-            if (keyset(r) == want) same.push_back(r);
-        rel.swap(same);
+            if (!same_keyset(r, want)) { all = false; break; }
+        if (!all) {
+            std::vector<Rel> same;
+            for (auto &r : rel)
+                if (same_keyset(r, want)) same.push_back(r);
+            rel.swap(same);
+        }
     }
     std::vector<int32_t> &keys = J.keys;
     for (auto &kv : rel.back().point) keys.push_back(kv.first);
@@ -938,8 +976,9 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
         size_t refcol = 0;
         for (size_t c = 0; c < k; c++)
             if (keys[c] == ref) refcol = c;
-        auto refcoord = [&](int i) { return (size_t)i == rel.size() ? right[refcol] : coord_of(rel[i], ref); };
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return refcoord(a) < refcoord(b); });
+        std::vector<int64_t> refcoord(m);
+        for (size_t i = 0; i < m; i++) refcoord[i] = i == rel.size() ? right[refcol] : coord_of(rel[i], ref);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return refcoord[(size_t)a] < refcoord[(size_t)b]; });
         std::vector<int64_t> &start = J.start, &length = J.length, &gain = J.gain;
         start.assign((m + 1) * k, 0);
         length.assign(m + 1, 0);
@@ -959,6 +998,7 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
         }
         J.need_dp = true;
     }
+    PK_MARK(5)
     return 1;
 }
 
@@ -1372,6 +1412,9 @@ static PyMethodDef Graph_methods[] = {
 
 static PyTypeObject GraphType = {PyVarObject_HEAD_INIT(nullptr, 0)};
 
+static PyObject *mod_pick_phases(PyObject *, PyObject *) {
+    return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d}", "parse", g_pk[0], "filter_trim", g_pk[1], "sort", g_pk[2], "lookup", g_pk[3], "origin", g_pk[4], "rows", g_pk[5]);
+}
 static PyObject *mod_chain_stats(PyObject *, PyObject *) {
     return Py_BuildValue("{s:O,s:L,s:L,s:L}", "device", g_chain.ready ? Py_True : Py_False, "device_lists", g_chain.device_lists, "host_lists", g_chain.host_lists,
                          "launches", g_chain.launches);
@@ -1390,6 +1433,7 @@ static PyObject *mod_set_chain_library(PyObject *, PyObject *args) {
     Py_RETURN_NONE;
 }
 static PyMethodDef module_methods[] = {
+    {"pick_phases", mod_pick_phases, METH_NOARGS, "seconds this process spent in the phases of the mumpicker's preparation (diagnostics)"},
     {"chain_stats", mod_chain_stats, METH_NOARGS, "where the chaining recurrences of this process ran: lists on the device / on the host, device launches"},
     {"_set_chain_library", mod_set_chain_library, METH_VARARGS, "test hook: the C-ABI library rv_chain_batch is taken from (the emulated kernels)"},
     {nullptr, nullptr, 0, nullptr}};

@@ -279,7 +279,10 @@ static const int PR_CHUNK = RV_PR_CHUNK;               // nominal SA slots per w
 static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched to whole groups (<= SA_SMALL_G more), padded to rounds
 static const int PR_ROUNDS = PR_MAXT / 32;
 static const int PL_CAP = 512;                         // pair items per warp (a power of two >= 32 * 15 + 31)
-static const int ET_WAYS = 8;                          // entries per bucket of the sampled-pair table
+#ifndef RV_ET_WAYS
+#define RV_ET_WAYS 8
+#endif
+static const int ET_WAYS = RV_ET_WAYS;                          // entries per bucket of the sampled-pair table
 
 // The comparison stage works on runs of whole groups: one warp owns about PR_CHUNK consecutive slots of the sorted (key, suffix)
 // list, stretched at both ends to group boundaries.  Both kernels of the stage start with the same staging: suffixes into shared
