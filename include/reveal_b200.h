@@ -192,6 +192,11 @@ int rv_sub_mums_multi(rv_sub *sub, int32_t minl, int32_t minn, int64_t *nrec, in
 int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
                 const int64_t *mum_sp, int32_t mum_n, int64_t mum_l, const int64_t *matching, int32_t nmatch, const int32_t *sweep, int32_t minl,
                 int32_t minn, rv_sub **children);
+/* extract (reveal.c:1386-1505): removes the text positions of nintervals (begin, end) pairs from the sub-index in place --
+ * SA / LCP compacted (LCP of a survivor = minimum over the removed run before it), inverse rewritten, bases lower-cased,
+ * bubble_sort with the intervals.  Slot 0 of the result holds the suffix that belongs there (the reference leaves it
+ * uninitialised, reveal.c:1448). */
+int rv_sub_extract(rv_sub *sub, const int64_t *intervals, int32_t nintervals);
 /* Frontier batching: the sub-indexes waiting on the aligner's queue are independent (reveal.c:1296-1324 pushes up to three per
  * step; interface.c:316-385 hands them to a worker pool), so every step whose callbacks have run can go to the device together:
  * the steps whose parent fits one thread block share ONE launch and ONE synchronisation (one block per step), the others take

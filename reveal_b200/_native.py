@@ -75,6 +75,7 @@ SIGNATURES = {
                                    ctypes.c_int64, c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_vp)]),
     "rv_rec_stats": (ctypes.c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_double)]),
     "rv_rec_launches": (ctypes.c_int, [c_vp, c_i64p]),
+    "rv_sub_extract": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32]),
     "rv_mums_tiny_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
     "rv_chain_batch": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, c_vp, c_vp]),
     "rv_sub_step_batch": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),

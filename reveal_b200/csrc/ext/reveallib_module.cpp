@@ -37,8 +37,8 @@
 #define RV_API_LIST(X)                                                                                                  \
     X(rv_last_error) X(rv_version) X(rv_host_alloc) X(rv_host_free) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
     X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_put_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
-    X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_free) X(rv_sub_get)    \
-    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch) X(rv_mums_tiny_batch)
+    X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_n) X(rv_sub_free) X(rv_sub_get)    \
+    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch) X(rv_sub_extract) X(rv_mums_tiny_batch)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -143,7 +143,7 @@ struct Index {
     rv_index *h;
     HostText *T;                 // host copy of the text (root only)
     std::vector<int64_t> *nsep;
-    int nsamples, rc, depth, cache, built, tdirty;
+    int nsamples, rc, depth, cache, built, tdirty, extracted;
     int64_t n, nT;
     std::string *safile, *lcpfile;
     // recursion state
@@ -177,7 +177,7 @@ static PyObject *index_new(PyTypeObject *type, PyObject *, PyObject *) {
     self->nsep = new std::vector<int64_t>();
     self->safile = new std::string();
     self->lcpfile = new std::string();
-    self->nsamples = self->rc = self->depth = self->cache = self->built = self->tdirty = 0;
+    self->nsamples = self->rc = self->depth = self->cache = self->built = self->tdirty = self->extracted = 0;
     self->n = self->nT = 0;
     self->sub = nullptr;
     self->mainidx = nullptr;
@@ -389,12 +389,23 @@ static PyObject *index_getmums(Index *self, PyObject *args) {
     }
     int64_t k = 0;
     int status;
-    Py_BEGIN_ALLOW_THREADS;
-    status = g_api.rv_mums_pair_count(self->h, minl, 0, &k);
-    Py_END_ALLOW_THREADS;
-    if (fail_native(status) != 0) return nullptr;
-    std::vector<int64_t> rows((size_t)(3 * k + 3));
-    if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
+    std::vector<int64_t> rows;
+    if (self->extracted) {  // after extract() the index is its own (SA, LCP) pair over the main text
+        if (self->rc) { PyErr_SetString(RevealError, "getmums() after extract() on a reverse-complement index is not supported"); return nullptr; }
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_sub_mums_pair(self->sub, minl, &k);
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+        rows.resize((size_t)(3 * k + 3));
+        if (fail_native(g_api.rv_sub_fetch(self->sub, rows.data(), k, nullptr, 0)) != 0) return nullptr;
+    } else {
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_mums_pair_count(self->h, minl, 0, &k);
+        Py_END_ALLOW_THREADS;
+        if (fail_native(status) != 0) return nullptr;
+        rows.resize((size_t)(3 * k + 3));
+        if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
+    }
     PyObject *lst = PyList_New((Py_ssize_t)k);
     if (!lst) return nullptr;
     PyObject *rcobj = PyLong_FromLong(self->rc);
@@ -420,7 +431,7 @@ static PyObject *multi_common(Index *self, PyObject *args, PyObject *kwds, bool 
     int64_t nr = 0, nm = 0;
     int status;
     std::vector<int64_t> hdr, mem;
-    if (self->mainidx) {  // a child of the recursion: sweep its own arrays
+    if (self->mainidx || self->extracted) {  // a child of the recursion, or a root after extract(): sweep its own arrays
         if (mems) {
             PyErr_SetString(RevealError, "getmultimems() on a child index is not supported");
             return nullptr;
@@ -632,11 +643,14 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
         if (b >= 1) batch_max = (size_t)b;
     }
     self->depth = 0;
-    if (self->sub) {
-        g_api.rv_sub_free(self->sub);
-        self->sub = nullptr;
+    if (!self->extracted) {  // (after extract() the index already is a view of its own: the recursion starts from that)
+        if (self->sub) {
+            g_api.rv_sub_free(self->sub);
+            self->sub = nullptr;
+        }
+        if (fail_native(g_api.rv_sub_root(self->h, &self->sub)) != 0) return nullptr;
     }
-    if (fail_native(g_api.rv_sub_root(self->h, &self->sub)) != 0) return nullptr;
+    self->extracted = 0;  // align() consumes the root's arrays either way
     std::vector<Index *> queue;  // owned references
     Py_INCREF((PyObject *)self);
     queue.push_back(self);
@@ -928,6 +942,46 @@ static PyObject *index_splitindex(Index *idx, PyObject *args) {
     return Py_BuildValue("(NNN)", out[0], out[1], out[2]);
 }
 
+// extract(intervals) (reveal.c:1386-1505): takes the text positions of the (begin, end) intervals out of the index in place.
+// With rc=1 the intervals of the second sample are mapped back first AND the caller's list is rewritten with the mapped
+// tuples, like the reference does (:1411-1427).
+static PyObject *index_extract(Index *self, PyObject *args) {
+    PyObject *intervals;
+    if (!PyArg_ParseTuple(args, "O", &intervals)) return nullptr;
+    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) {
+        if (self->mainidx) PyErr_SetString(RevealError, "extract() on a child index is not supported");
+        return nullptr;
+    }
+    PyObject *seq = PySequence_Fast(intervals, "intervals must be a sequence of (begin, end)");
+    if (!seq) return nullptr;
+    const Py_ssize_t m = PySequence_Fast_GET_SIZE(seq);
+    std::vector<int64_t> flat;
+    const int64_t nsep0 = self->nsep->empty() ? -1 : (*self->nsep)[0];
+    for (Py_ssize_t x = 0; x < m; x++) {
+        long long b, e;
+        if (!PyArg_ParseTuple(PySequence_Fast_GET_ITEM(seq, x), "LL", &b, &e)) { Py_DECREF(seq); return nullptr; }
+        if (self->rc == 1 && b > nsep0) {  // map qry coordinates back (reveal.c:1411-1416)
+            const long long nb = nsep0 + (self->nT - b - (e - b)), ne = nsep0 + (self->nT - b);
+            b = nb;
+            e = ne;
+            if (PyList_Check(intervals)) PyList_SetItem(intervals, x, Py_BuildValue("(LL)", b, e));
+        }
+        flat.push_back(b);
+        flat.push_back(e);
+    }
+    Py_DECREF(seq);
+    if (!self->sub && fail_native(g_api.rv_sub_root(self->h, &self->sub)) != 0) return nullptr;
+    int status;
+    Py_BEGIN_ALLOW_THREADS;
+    status = g_api.rv_sub_extract(self->sub, flat.data(), (int32_t)(flat.size() / 2));
+    Py_END_ALLOW_THREADS;
+    if (fail_native(status) != 0) return nullptr;
+    self->n = g_api.rv_sub_n ? g_api.rv_sub_n(self->sub) : self->n;
+    self->extracted = 1;
+    self->tdirty = 1;  // the extracted bases were lower-cased on the device (reveal.c:1432)
+    Py_RETURN_NONE;
+}
+
 // puttext(begin, text): overwrites a stretch of the indexed text (host copy and device) -- used when the parts of a sharded
 // recursion are collected: the owner of a unit sends the stretches whose matched bases it lower-cased.
 static PyObject *index_puttext(Index *self, PyObject *args) {
@@ -987,7 +1041,7 @@ static PyObject *get_array(Index *self, int which) {  // 0 SA, 1 SAi, 2 LCP
     Index *r = root_of(self);
     std::vector<int32_t> v;
     int status;
-    if (self->mainidx && which != 1) {
+    if ((self->mainidx || self->extracted) && which != 1) {
         if (!self->sub) {
             PyErr_SetString(PyExc_TypeError, "Index not yet constructed.");  // SA/LCP of a processed sub-index are freed
             return nullptr;
@@ -995,8 +1049,9 @@ static PyObject *get_array(Index *self, int which) {  // 0 SA, 1 SAi, 2 LCP
         v.resize((size_t)self->n);
         status = g_api.rv_sub_get(self->sub, which == 0 ? 0 : 1, v.data());
     } else {
-        v.resize((size_t)r->n);
+        v.resize((size_t)r->nT);   // the handle's arrays have one entry per character of the text (nT >= n after extract)
         status = which == 0 ? g_api.rv_get_sa(r->h, v.data(), 32) : (which == 1 ? g_api.rv_get_sai(r->h, v.data(), 32) : g_api.rv_get_lcp(r->h, v.data(), 32));
+        v.resize((size_t)r->n);    // the reference lists n entries (interface.c:546-655)
     }
     if (fail_native(status) != 0) return nullptr;
 #ifdef SA64
@@ -1068,6 +1123,7 @@ static PyMethodDef index_methods[] = {
     {"splitindex", (PyCFunction)index_splitindex, METH_VARARGS,
      "splitindex(leading, trailing, matching, rest, merged, newleft, newright, skipleft, skipright) -> (lead, trail, par): one recursion step."},
     {"copy", (PyCFunction)index_copy, METH_NOARGS, nullptr},
+    {"extract", (PyCFunction)index_extract, METH_VARARGS, "extract(intervals): take the text positions of the (begin, end) intervals out of the index in place (reveal.c:1386-1505)."},
     {"puttext", (PyCFunction)index_puttext, METH_VARARGS, "puttext(begin, text): overwrite a stretch of the indexed text (sharded recursion: collecting the parts)."},
     {"addsample", (PyCFunction)index_addsample, METH_VARARGS, nullptr},
     {"addsequence", (PyCFunction)index_addsequence, METH_VARARGS, nullptr},

@@ -271,7 +271,7 @@ __device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u3
 #define RV_PR_CHUNK 256
 #endif
 #ifndef RV_PR_MINBLOCKS
-#define RV_PR_MINBLOCKS 10
+#define RV_PR_MINBLOCKS 8
 #endif
 static const int PR_THREADS = RV_PR_THREADS;
 static const int PR_WARPS = PR_THREADS / 32;
@@ -280,7 +280,7 @@ static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched t
 static const int PR_ROUNDS = PR_MAXT / 32;
 static const int PL_CAP = 512;                         // pair items per warp (a power of two >= 32 * 15 + 31)
 #ifndef RV_ET_WAYS
-#define RV_ET_WAYS 8
+#define RV_ET_WAYS 4
 #endif
 static const int ET_WAYS = RV_ET_WAYS;                          // entries per bucket of the sampled-pair table
 

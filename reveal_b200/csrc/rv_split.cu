@@ -1247,6 +1247,127 @@ int rv_rec_stats(rv_index *h, int64_t *steps2, double *seconds2) {
     return RV_OK;
 }
 
+// extract (reveal.c:1386-1505): takes the text positions of `intervals` out of the sub-index IN PLACE -- their suffixes are
+// dropped from SA / LCP (the LCP of a survivor is the minimum over the dropped run before it, :1452-1478), the inverse is
+// rewritten to the new ranks, the bases are lower-cased (:1432) and bubble_sort runs on the result with the intervals (:1497).
+// It is the split of rv_sub_step with ONE class: every slot is labelled "keep" first, the intervals then "matched".
+// Slot 0: the reference starts its copy loop at slot 1 and leaves SA[0] of the result uninitialised (:1448); here slot 0
+// holds the suffix that belongs there.
+int rv_sub_extract(rv_sub *sub, const int64_t *intervals, int32_t nintervals) {
+    if (!sub || (nintervals > 0 && !intervals) || nintervals < 0) return RV_ERR_ARG;
+    MainView v;
+    RV_TRY(main_view(sub->main, &v));
+    DevPool *pool = pool_of(v);
+    Stream &st = *v.st;
+    const i64 n = sub->n;
+    if (n <= 0 || nintervals == 0) return RV_OK;
+    struct Lease {
+        DevPool *pool;
+        std::vector<void *> blocks;
+        int take(size_t bytes, void **out) {
+            int r = pool->take(bytes, out);
+            if (r == RV_OK) blocks.push_back(*out);
+            return r;
+        }
+        ~Lease() {
+            for (void *p : blocks) pool->give(p);
+        }
+    } lease;
+    lease.pool = pool;
+    std::vector<i64> ibeg, pre, bbeg;
+    i64 total = 0;
+    for (int k = 0; k < nintervals; k++) {
+        const i64 b = intervals[2 * k], e = intervals[2 * k + 1];
+        if (b < 0 || e > v.n || e < b) { set_error("rv_sub_extract: interval out of range"); return RV_ERR_ARG; }
+        bbeg.push_back(b);
+        if (e == b) continue;
+        ibeg.push_back(b);
+        pre.push_back(total);
+        total += e - b;
+    }
+    const int m = (int)ibeg.size();
+    if (total > n) { set_error("rv_sub_extract: the intervals cover more positions than the index has suffixes"); return RV_ERR_ARG; }
+    const i64 cn = n - total;
+    // tables: [ibeg m][pre m][bbeg nb] then m label bytes, d_counts in the last 32 bytes
+    const size_t words = (size_t)2 * m + bbeg.size() + 8;
+    const size_t bytes = (words * 8 + (size_t)m + 64 + 15) / 16 * 16;
+    void *dtab = nullptr;
+    RV_TRY(lease.take(bytes, &dtab));
+    std::vector<unsigned char> host(bytes, 0);
+    i64 *hw = (i64 *)host.data();
+    for (int k = 0; k < m; k++) { hw[k] = ibeg[k]; hw[m + k] = pre[k]; }
+    for (size_t k = 0; k < bbeg.size(); k++) hw[2 * m + k] = bbeg[k];
+    memset(host.data() + words * 8, 3, (size_t)m);
+    RV_CUDA(cudaMemcpyAsync(dtab, host.data(), bytes, cudaMemcpyHostToDevice, st.s));
+    const i64 *d_ibeg = (const i64 *)dtab, *d_pre = d_ibeg + m, *d_bbeg = d_ibeg + 2 * m;
+    const unsigned char *d_lab = (const unsigned char *)dtab + words * 8;
+    u32 *d_counts = (u32 *)((unsigned char *)dtab + bytes - 32);
+    void *dD = nullptr;
+    RV_TRY(lease.take((size_t)n, &dD));
+    unsigned char *D = (unsigned char *)dD;
+    RV_CUDA(cudaMemsetAsync(D, 1, (size_t)n, st.s));  // every slot: class 0 ("keep")
+    if (total > 0) {
+        RV_LAUNCH(label_kernel, (unsigned)((total + 255) / 256), 256, 0, st.s, d_ibeg, d_pre, d_lab, m, total, v.ISA, D, n);
+        st.launches++;
+    }
+    void *p1 = nullptr, *p2 = nullptr;
+    RV_TRY(pool->take((size_t)(cn + 2) * 4, &p1));
+    if (pool->take((size_t)(cn + 2) * 4, &p2) != RV_OK) { pool->give(p1); return RV_ERR_NOMEM; }
+    int *nSA = (int *)p1, *nLCP = (int *)p2;
+    const i64 ntiles = (n + SP_TILE - 1) / SP_TILE;
+    void *dtiles = nullptr;
+    if (lease.take((size_t)ntiles * sizeof(SplitState) + 64, &dtiles) != RV_OK) { pool->give(p1); pool->give(p2); return RV_ERR_NOMEM; }
+    SplitState *tiles = (SplitState *)dtiles;
+    RV_LAUNCH(split_reduce_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, sub->LCP, D, n, tiles);
+    RV_LAUNCH(split_tilescan_kernel, 1, 32, 0, st.s, tiles, ntiles, d_counts);
+    RV_LAUNCH(split_apply_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, sub->SA, sub->LCP, D, n, tiles, v.ISA, nSA, nLCP, (int *)nullptr, (int *)nullptr,
+              (int *)nullptr, (int *)nullptr, (u32)cn, 0u, 0u);
+    st.launches += 3;
+    u32 *hc = st.pinned + 300;
+    RV_CUDA(cudaMemcpyAsync(hc, d_counts, 12, cudaMemcpyDeviceToHost, st.s));
+    if (total > 0) {
+        RV_LAUNCH(lower_kernel, (unsigned)((total + 255) / 256), 256, 0, st.s, d_ibeg, d_pre, m, total, v.T);
+        st.launches++;
+    }
+    void *dcand = nullptr;
+    if (cn > 0 && !bbeg.empty()) {  // bubble_sort(idx, intervals) (reveal.c:1497)
+        if (cn <= 8192) {
+            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, (int)bbeg.size());
+            st.launches++;
+        } else {
+            if (lease.take((size_t)(BB_CAP + 16) * 4, &dcand) != RV_OK) { pool->give(p1); pool->give(p2); return RV_ERR_NOMEM; }
+            int *cand = (int *)dcand, *cand_cnt = cand + BB_CAP;
+            RV_CUDA(cudaMemsetAsync(cand_cnt, 0, 4, st.s));
+            i64 blocks = (cn + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            for (int b = 0; b < (int)bbeg.size(); b++) {
+                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, nSA, nLCP, cn, d_bbeg, b, cand, cand_cnt);
+                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, b, cand, cand_cnt);
+                st.launches += 2;
+            }
+        }
+    }
+    RV_CUDA(cudaStreamSynchronize(st.s));
+    RV_KCHECK();
+    if ((i64)hc[0] != cn) {
+        pool->give(p1);
+        pool->give(p2);
+        set_error("rv_sub_extract: the intervals cover %lld positions but only %lld of them are suffixes of this index", (long long)total,
+                  (long long)(n - (i64)hc[0]));
+        return RV_ERR_ARG;
+    }
+    if (sub->owns) {
+        pool->give(sub->SA);
+        pool->give(sub->LCP);
+    }
+    sub->SA = nSA;
+    sub->LCP = nLCP;
+    sub->n = cn;
+    sub->owns = true;
+    sub->cached = false;
+    return RV_OK;
+}
+
 // kernel launches behind those steps: [0] single-launch path (one launch serves a whole batch), [1] general path (calls)
 int rv_rec_launches(rv_index *h, int64_t *launches2) {
     MainView v;

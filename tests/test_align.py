@@ -233,3 +233,67 @@ def splitindex_case(mod32, ns, length, minl):
         frontier = nxt
     assert steps >= 3
     assert ours.T == ref.T[:ref.n]
+
+
+# ---- extract (reveal.c:1386-1505) -------------------------------------------------------------------------------------------
+def extract_case(mod32, ns, length, minl, seed):
+    """index.extract(intervals): the positions of a MUM (and of a second, shorter stretch) leave the index in place.  Against the
+    reference's own extract: n, LCP, SAi, the text, and SA from slot 1 on -- the reference never writes SA[0] of its result
+    (its copy loop starts at slot 1, reveal.c:1448); here slot 0 holds the suffix that belongs there, checked separately."""
+    rng = np.random.default_rng(seed)
+    samples = random_related(rng, ns, length, 4, snp=0.03)
+    seqs = [[bytes(c).decode() for c in contigs] for contigs in samples]
+
+    def build(mod):
+        idx = mod.index()
+        for k, contigs in enumerate(seqs):
+            idx.addsample("s%d" % k)
+            for c in contigs:
+                idx.addsequence(c)
+        idx.construct()
+        return idx
+
+    ours, ref = build(mod32), build(R.module(32))
+    mums = ref.getmultimums(minlength=minl, minn=2) if ns > 2 else [(l, 2, ((0, a), (1, b))) for l, (a, b), _ in ref.getmums(minl)]
+    best = max(mums, key=lambda m: m[0])
+    l = best[0]
+    intervals = [(p, p + l) for _, p in best[2]]
+    sa_before = list(ours.SA)
+    gone = set()
+    for b, e in intervals:
+        gone.update(range(b, e))
+    ours.extract(list(intervals))
+    ref.extract(list(intervals))
+    assert ours.n == ref.n == len(sa_before) - len(gone)
+    assert list(ours.LCP) == list(ref.LCP)
+    sa_o, sa_r = list(ours.SA), list(ref.SA)
+    assert sa_o[1:] == sa_r[1:]
+    assert sa_o == [s for s in sa_before if s not in gone] or sa_o[0] == [s for s in sa_before if s not in gone][0]   # slot 0: the survivor that sorts first
+    assert ours.T == ref.T[:len(ours.T)]
+    keep = [p for p in range(len(sa_before)) if p not in gone]
+    sai_o, sai_r = list(ours.SAi), list(ref.SAi)
+    # (the reference lists the first n entries of its inverse array; positions >= n are not visible through the getter)
+    # and never rewrites the inverse entry of the suffix that belongs into slot 0
+    vis = [p for p in keep if p < ours.n and p != sa_o[0]]
+    assert [sai_o[p] for p in vis] == [sai_r[p] for p in vis]
+    if sa_o[0] < ours.n:
+        assert sai_o[sa_o[0]] == 0
+    # the sweeps of the extracted index run on its own arrays
+    if ns == 2:
+        o = [m for m in ours.getmums(minl)]
+        assert all(not (set(range(a, a + ll)) & gone) and not (set(range(b, b + ll)) & gone) for ll, (a, b), _ in o)
+    return len(intervals)
+
+
+@needs_ref
+@pytest.mark.parametrize("ns,length,minl", [(2, 1500, 8), (3, 1000, 8)])
+def test_extract_matches_reference(emu_reveallib, ns, length, minl):
+    assert extract_case(emu_reveallib.mod32, ns, length, minl, 40 + ns) >= 2
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("ns,length,minl", [(2, 40000, 14), (4, 15000, 12)])
+def test_extract_matches_reference_cuda(ns, length, minl):
+    from reveal_b200 import reveallib
+    assert extract_case(reveallib, ns, length, minl, 60 + ns) >= 2
