@@ -700,6 +700,26 @@ struct Origin {
 };
 
 static bool parse_mums(PyObject *list, std::vector<Mum> &out) {
+    if (PyObject_CheckBuffer(list) && !PyList_Check(list) && !PyTuple_Check(list)) {
+        // pair MUM rows straight from the device sweep (reveallib.mumrows): int64 triples (l, a, b) = (l, 2, ((0, a), (1, b)))
+        Py_buffer view;
+        if (PyObject_GetBuffer(list, &view, PyBUF_SIMPLE) != 0) return false;
+        const int64_t *r = (const int64_t *)view.buf;
+        const Py_ssize_t n = view.len / 24;
+        out.reserve((size_t)n);
+        for (Py_ssize_t i = 0; i < n; i++) {
+            Mum m;
+            m.l = r[3 * i];
+            m.n = 2;
+            m.orig = nullptr;
+            m.spd = nullptr;
+            m.sp.emplace_back(0L, r[3 * i + 1]);
+            m.sp.emplace_back(1L, r[3 * i + 2]);
+            out.push_back(m);
+        }
+        PyBuffer_Release(&view);
+        return true;
+    }
     PyObject *seq = PySequence_Fast(list, "mums must be a sequence");
     if (!seq) return false;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);

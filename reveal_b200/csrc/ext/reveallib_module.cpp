@@ -530,8 +530,39 @@ static Index *new_child(Index *root, rv_sub *sub, int64_t n, int depth, int nsam
     return c;
 }
 
+// ---- pair MUM rows as a sequence object --------------------------------------------------------------------------------------
+// The recursion hands a MUM list to the mumpicker at every step; built as Python tuples (four objects per MUM, reveal.c:167-169)
+// that is a fifth of the host time of an alignment, and a native picker reads the numbers straight back out of them.  `mumrows`
+// keeps the (l, a, b) rows the device produced: len() and indexing give the reference's tuples (l, 2, ((0, a), (1, b))) on demand
+// -- a callback written for the list works on it by iteration and indexing -- and the buffer protocol exposes the int64 rows
+// (remcore.Graph.mumpicker* reads those).  Only handed out when align() is called with mums_as_rows=True.
+struct MumRows {
+    PyObject_HEAD
+    std::vector<int64_t> *rows;
+};
+static PyTypeObject MumRowsType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+static void mumrows_dealloc(MumRows *self) {
+    delete self->rows;
+    Py_TYPE(self)->tp_free((PyObject *)self);
+}
+static Py_ssize_t mumrows_len(MumRows *self) { return (Py_ssize_t)(self->rows->size() / 3); }
+static PyObject *mumrows_item(MumRows *self, Py_ssize_t i) {
+    const Py_ssize_t n = mumrows_len(self);
+    if (i < 0 || i >= n) {
+        PyErr_SetString(PyExc_IndexError, "mumrows index out of range");
+        return nullptr;
+    }
+    const int64_t *r = self->rows->data() + 3 * i;
+    return Py_BuildValue("(L,i,((i,L),(i,L)))", (long long)r[0], 2, 0, (long long)r[1], 1, (long long)r[2]);  // reveal.c:167-169
+}
+static int mumrows_getbuffer(MumRows *self, Py_buffer *view, int flags) {
+    return PyBuffer_FillInfo(view, (PyObject *)self, self->rows->data(), (Py_ssize_t)(self->rows->size() * 8), 1, flags);
+}
+static PySequenceMethods mumrows_as_sequence = {(lenfunc)mumrows_len, nullptr, nullptr, (ssizeargfunc)mumrows_item};
+static PyBufferProcs mumrows_as_buffer = {(getbufferproc)mumrows_getbuffer, nullptr};
+
 // MUMs of a (sub)index in the shape the reference hands to mumpicker (reveal.c:802-829)
-static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
+static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn, bool as_rows = false) {
     int64_t nr = 0, nm = 0;
     int status;
     if (root->nsamples > 2) {
@@ -549,6 +580,13 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn) {
     if (fail_native(status) != 0) return nullptr;
     std::vector<int64_t> rows((size_t)(3 * nr + 3));
     if (fail_native(g_api.rv_sub_fetch(sub, rows.data(), nr, nullptr, 0)) != 0) return nullptr;
+    if (as_rows) {
+        MumRows *mr = (MumRows *)MumRowsType.tp_alloc(&MumRowsType, 0);
+        if (!mr) return nullptr;
+        rows.resize((size_t)(3 * nr));
+        mr->rows = new std::vector<int64_t>(std::move(rows));
+        return (PyObject *)mr;
+    }
     PyObject *lst = PyList_New((Py_ssize_t)nr);
     PyObject *two = PyLong_FromLong(2), *zero = PyLong_FromLong(0), *one = PyLong_FromLong(1);
     for (int64_t i = 0; i < nr; i++) {  // (l, 2, ((0, a), (1, b))): reveal.c:167-169
@@ -604,15 +642,15 @@ static void release_index_view(Index *idx) {
 
 static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     static const char *kwlist[] = {"mumpicker", "align", "threads", "wpen", "wscore", "minl", "minn",  // interface.c:303
-                                   "shard_rank", "shard_world", "shard_grain", "mumpicker_batch", nullptr};
+                                   "shard_rank", "shard_world", "shard_grain", "mumpicker_batch", "mums_as_rows", nullptr};
     PyObject *mumpicker, *graphalign, *mumpicker_batch = nullptr;
-    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 2;
+    int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 2, mums_as_rows = 0;
     if (self->mainidx || !self->built) {
         PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
         return nullptr;
     }
-    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiiiiiiO", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn,
-                                     &shard_rank, &shard_world, &shard_grain, &mumpicker_batch))
+    if (!PyArg_ParseTupleAndKeywords(args, kwds, "OO|iiiiiiiiOp", (char **)kwlist, &mumpicker, &graphalign, &threads, &wpen, &wscore, &minl, &minn,
+                                     &shard_rank, &shard_world, &shard_grain, &mumpicker_batch, &mums_as_rows))
         return nullptr;
     // mumpicker_batch (optional): callable([(mums, idx, precomputed), ...], minlength=) -> [pick, ...] -- the mumpicker for all
     // sub-indexes of a frontier batch at once (their picks do not depend on each other), so that e.g. their chaining recurrences
@@ -685,7 +723,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             PyObject *mums;
             if (!precomputed) {
                 const double t0 = now_s();
-                mums = extract_mums(self, idx->sub, minl, minn);
+                mums = extract_mums(self, idx->sub, minl, minn, mums_as_rows != 0);  // (rows: pair MUMs only, see mumrows)
                 as.extract += now_s() - t0;
                 if (!mums) ok = false;
             } else {
@@ -1313,6 +1351,14 @@ PyMODINIT_FUNC MODINIT(void) {
     IndexType.tp_methods = index_methods;
     IndexType.tp_getset = index_getset;
     if (PyType_Ready(&IndexType) < 0) return nullptr;
+    MumRowsType.tp_name = MODNAME ".mumrows";
+    MumRowsType.tp_basicsize = sizeof(MumRows);
+    MumRowsType.tp_flags = Py_TPFLAGS_DEFAULT;
+    MumRowsType.tp_doc = "pair MUM rows (l, a, b) of a sub-index: a sequence of the reference's MUM tuples, and a buffer of int64 rows";
+    MumRowsType.tp_dealloc = (destructor)mumrows_dealloc;
+    MumRowsType.tp_as_sequence = &mumrows_as_sequence;
+    MumRowsType.tp_as_buffer = &mumrows_as_buffer;
+    if (PyType_Ready(&MumRowsType) < 0) return nullptr;
     PyObject *m = PyModule_Create(&moduledef);
     if (!m) return nullptr;
     Py_INCREF(&IndexType);

@@ -1094,6 +1094,7 @@ def align_genomes(args, index_module=None, shard=None):
         extra = {}
         if rem.batch_picker is not None and hasattr(mod, "align_stats"):   # this repository's extension: frontier batches
             extra["mumpicker_batch"] = rem.batch_picker
+            extra["mums_as_rows"] = True    # pair MUM lists stay int64 rows between the device sweep and the native picker
         if shard is not None and shard[1] > 1:
             if rem.core is None:
                 raise RuntimeError("a sharded recursion needs the compiled graph (reveal_b200.remcore)")
@@ -1134,7 +1135,7 @@ def align(aobjs, ref=None, minlength=20, minn=2, seedsize=None, threads=0, targe
     idx.construct()
     with rem.recursion_graph():
         mumpicker, graphalign = rem.callbacks(minlength)
-        extra = {"mumpicker_batch": rem.batch_picker} if rem.batch_picker is not None and hasattr(mod, "align_stats") else {}
+        extra = {"mumpicker_batch": rem.batch_picker, "mums_as_rows": True} if rem.batch_picker is not None and hasattr(mod, "align_stats") else {}
         idx.align(mumpicker, graphalign, threads=threads, wpen=wpen, wscore=wscore, minl=minlength, minn=minn, **extra)
     rem.prune_nodes(T=idx.T)
     G.remove_node(first)

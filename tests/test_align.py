@@ -297,3 +297,32 @@ def test_extract_matches_reference(emu_reveallib, ns, length, minl):
 def test_extract_matches_reference_cuda(ns, length, minl):
     from reveal_b200 import reveallib
     assert extract_case(reveallib, ns, length, minl, 60 + ns) >= 2
+
+
+@needs_ref
+def test_align_mums_as_rows_emulated(emu_reveallib):
+    """align(mums_as_rows=True): pair MUM lists arrive as `mumrows` objects -- len(), iteration and indexing give the reference's
+    tuples, so the same callbacks produce the same events; the buffer holds the int64 rows."""
+    rng = np.random.default_rng(5)
+    samples = random_related(rng, 2, 1500, 4, snp=0.03)
+    ref = run_reference(samples, 8, 2)
+    log = []
+    idx = emu_reveallib.index()
+    for k, seqs in enumerate(samples):
+        idx.addsample("s%d" % k)
+        for s in seqs:
+            idx.addsequence(bytes(s).decode("ascii"))
+    idx.construct()
+    seen = []
+    mp, ga = make_callbacks(log, minlen=8)
+
+    def picker(mums, index, precomputed=False, minlength=0):
+        seen.append(type(mums).__name__)
+        if type(mums).__name__ == "mumrows" and len(mums):
+            rows = np.frombuffer(memoryview(mums), dtype=np.int64).reshape(-1, 3)
+            assert [(int(l), 2, ((0, int(a)), (1, int(b)))) for l, a, b in rows] == [tuple(m) for m in mums] == [mums[i] for i in range(len(mums))]
+        return mp(mums, index, precomputed=precomputed, minlength=minlength)
+
+    idx.align(picker, ga, threads=1, minl=8, minn=2, mums_as_rows=True)
+    assert "mumrows" in seen
+    assert compare(ref, (log, idx.T)) > 3
