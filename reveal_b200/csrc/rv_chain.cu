@@ -36,11 +36,15 @@ __device__ __forceinline__ Cand cand_shfl_down(const Cand &c, int d) {
     return r;
 }
 
+// smem_words: 64-bit words of dynamic shared memory per block.  A list whose rows x (k + 3) words fit works entirely out of
+// shared memory (coordinates, lengths, scores, "reachable since" -- every row re-reads all earlier rows, and the recurrence is a
+// chain of dependent steps, so the latency of those reads IS the run time); longer lists read global memory.
 __global__ void __launch_bounds__(CH_THREADS)
 chain_dp_kernel(const i64 *__restrict__ start, const i64 *__restrict__ length, const i64 *__restrict__ gain, const i64 *__restrict__ row_off,
                 const i64 *__restrict__ start_off, const int *__restrict__ kk, i64 wpen, int model, i64 *__restrict__ link, i64 *__restrict__ score,
-                i64 *__restrict__ joined) {
+                i64 *__restrict__ joined, int smem_words) {
     __shared__ Cand s_best[CH_THREADS / 32];
+    RV_DYN_SMEM(i64, dyn);
     const int job = (int)blockIdx.x;
     const i64 r0 = row_off[job];
     const int rows = (int)(row_off[job + 1] - r0);
@@ -49,10 +53,26 @@ chain_dp_kernel(const i64 *__restrict__ start, const i64 *__restrict__ length, c
     const i64 *len = length + r0, *gn = gain + r0;
     i64 *lk = link + r0, *sc = score + r0, *jn = joined + r0;
     const int tid = (int)threadIdx.x;
-    for (int i = tid; i < rows; i += CH_THREADS) jn[i] = i == 0 ? 0 : -1;
-    if (tid == 0 && rows > 0) {
-        lk[0] = 0;
-        sc[0] = 0;
+    const bool in_smem = (i64)rows * (k + 3) <= (i64)smem_words;
+    if (in_smem) {
+        i64 *s_st = dyn, *s_len = dyn + (i64)rows * k, *s_sc = s_len + rows, *s_jn = s_sc + rows;
+        for (int i = tid; i < rows * k; i += CH_THREADS) s_st[i] = st[i];
+        for (int i = tid; i < rows; i += CH_THREADS) {
+            s_len[i] = len[i];
+            s_jn[i] = i == 0 ? 0 : -1;
+            s_sc[i] = 0;
+        }
+        st = s_st;
+        len = s_len;
+        sc = s_sc;
+        jn = s_jn;
+        if (tid == 0 && rows > 0) lk[0] = 0;
+    } else {
+        for (int i = tid; i < rows; i += CH_THREADS) jn[i] = i == 0 ? 0 : -1;
+        if (tid == 0 && rows > 0) {
+            lk[0] = 0;
+            sc[0] = 0;
+        }
     }
     __syncthreads();
     i64 dist[CH_MAXK];
@@ -64,6 +84,24 @@ chain_dp_kernel(const i64 *__restrict__ start, const i64 *__restrict__ length, c
         for (int i = tid; i < r; i += CH_THREADS) {
             const i64 *si = st + (i64)i * k;
             const i64 li = len[i];
+            if (k == 2) {  // two paths (pairwise alignment, the usual case): registers only
+                const i64 d0 = sr[0] - (si[0] + li), d1 = sr[1] - (si[1] + li);
+                if (d0 < 0 || d1 < 0) continue;
+                i64 j = jn[i];
+                if (j < 0) {
+                    j = r;
+                    jn[i] = r;
+                }
+                const i64 hi = d0 > d1 ? d0 : d1, lo = d0 > d1 ? d1 : d0;
+                const i64 pen = model == 0 ? hi - lo : (model == 1 ? (d0 + d1) / 2 : hi);
+                Cand c;
+                c.total = sc[i] + gn[r] - wpen * pen;
+                c.score = sc[i];
+                c.joined = j;
+                c.row = i;
+                if (cand_better(c, best)) best = c;
+                continue;
+            }
             bool ok = true;
             for (int c = 0; c < k; c++) {
                 const i64 d = sr[c] - (si[c] + li);
@@ -126,6 +164,10 @@ chain_dp_kernel(const i64 *__restrict__ start, const i64 *__restrict__ length, c
         }
         __syncthreads();
     }
+    if (in_smem) {  // the scores go back to global memory in one sweep
+        i64 *gsc = score + r0;
+        for (int i = tid; i < rows; i += CH_THREADS) gsc[i] = sc[i];
+    }
 }
 
 }  // namespace rv
@@ -171,8 +213,26 @@ extern "C" int rv_chain_batch(rv_index *h, int32_t nlists, const int64_t *row_of
     RV_CUDA(cudaMemcpyAsync(d_roff, row_off, (size_t)(nlists + 1) * 8, cudaMemcpyHostToDevice, st.s));
     RV_CUDA(cudaMemcpyAsync(d_soff, start_off, (size_t)(nlists + 1) * 8, cudaMemcpyHostToDevice, st.s));
     RV_CUDA(cudaMemcpyAsync(d_kk, kk, (size_t)nlists * 4, cudaMemcpyHostToDevice, st.s));
-    RV_LAUNCH(chain_dp_kernel, (unsigned)nlists, CH_THREADS, 0, st.s, (const i64 *)d_start, (const i64 *)d_len, (const i64 *)d_gain, (const i64 *)d_roff,
-              (const i64 *)d_soff, (const int *)d_kk, (i64)wpen, (int)model, d_link, d_score, d_joined);
+    // dynamic shared memory: enough for the longest list of the batch, at most 96 KB per block
+    i64 need_words = 0;
+    for (int i = 0; i < nlists; i++) {
+        const i64 wds = (row_off[i + 1] - row_off[i]) * (kk[i] + 3);
+        if (wds > need_words && wds * 8 <= 96 * 1024) need_words = wds;
+    }
+    const size_t smem = (size_t)need_words * 8;
+#ifndef RV_EMU
+    if (smem > 48 * 1024) {
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        RV_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            RV_CUDA(cudaFuncSetAttribute(chain_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done[dev] = true;
+        }
+    }
+#endif
+    RV_LAUNCH(chain_dp_kernel, (unsigned)nlists, CH_THREADS, smem, st.s, (const i64 *)d_start, (const i64 *)d_len, (const i64 *)d_gain, (const i64 *)d_roff,
+              (const i64 *)d_soff, (const int *)d_kk, (i64)wpen, (int)model, d_link, d_score, d_joined, (int)need_words);
     st.launches++;
     RV_CUDA(cudaMemcpyAsync(link, d_link, rows * 8, cudaMemcpyDeviceToHost, st.s));
     RV_CUDA(cudaMemcpyAsync(score, d_score, rows * 8, cudaMemcpyDeviceToHost, st.s));

@@ -139,8 +139,14 @@ __device__ __forceinline__ u32 first_barrier(const Barriers &B, u32 x, u32 len) 
     if (len == 0u) return 0u;
     u32 w = x >> 5;
     const u32 wl = (x + len - 1u) >> 5;  // last level-0 word of the range
-    // The usual answer is "none", and level 1 (n/1024 words: cache resident) can say so alone when the range lies within two
-    // of its words: level 0 is only touched when a barrier is near.
+    // The usual answer is "none".  Level 2 (one bit per 1024 characters, a few hundred words: always cached) says so alone for
+    // every text that is not littered with '$' / 'N'; else level 1 (n/1024 words) when the range lies within two of its words:
+    // level 0 is only touched when a barrier is near.
+    if ((wl >> 5) - (w >> 5) <= 1u) {
+        const u32 va = w >> 5, vb = wl >> 5;   // level-1 words = level-2 bits of the range
+        const u32 qa = B.b2[va >> 5] >> (va & 31u), qb = B.b2[vb >> 5] >> (vb & 31u);
+        if (((qa | qb) & 1u) == 0u) return len;
+    }
     if ((wl >> 5) - (w >> 5) <= 1u) {
         const u32 v = w >> 5, vl = wl >> 5;
         u32 m = B.b1[v] >> (w & 31u);                   // words w .. end of level-1 word v

@@ -159,18 +159,27 @@ __global__ void __launch_bounds__(SP_THREADS) split_reduce_kernel(const int *__r
     if (threadIdx.x == 0) tiles[blockIdx.x] = total;
 }
 
-// single thread block: exclusive scan of the tile states (sequential over tiles; tiles are few)
-__global__ void __launch_bounds__(32) split_tilescan_kernel(SplitState *__restrict__ tiles, i64 ntiles, u32 *__restrict__ counts) {
-    if (threadIdx.x != 0) return;
-    SplitState run = split_identity();
-    for (i64 t = 0; t < ntiles; t++) {
-        SplitState x = tiles[t];
+// single thread block: exclusive scan of the tile states.  Every thread folds a contiguous run of tiles, the block scans the
+// per-thread states (the combine is associative), every thread writes the exclusive prefixes of its run.
+static const int TS_THREADS = 256;
+__global__ void __launch_bounds__(TS_THREADS) split_tilescan_kernel(SplitState *__restrict__ tiles, i64 ntiles, u32 *__restrict__ counts) {
+    __shared__ SplitState s_warp[32];
+    const i64 chunk = (ntiles + TS_THREADS - 1) / TS_THREADS;
+    const i64 lo = (i64)threadIdx.x * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
+    SplitState mine = split_identity();
+    for (i64 t = lo; t < hi; t++) mine = split_combine(mine, tiles[t]);
+    SplitState total;
+    SplitState run = block_excl_scan_state(mine, s_warp, &total);
+    for (i64 t = lo; t < hi; t++) {
+        const SplitState x = tiles[t];
         tiles[t] = run;
         run = split_combine(run, x);
     }
-    counts[0] = run.cnt[0];
-    counts[1] = run.cnt[1];
-    counts[2] = run.cnt[2];
+    if (threadIdx.x == 0) {
+        counts[0] = total.cnt[0];
+        counts[1] = total.cnt[1];
+        counts[2] = total.cnt[2];
+    }
 }
 
 __global__ void __launch_bounds__(SP_THREADS)
@@ -940,7 +949,7 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
     SplitState *tiles = (SplitState *)dtiles;
     u32 *d_counts = (u32 *)((unsigned char *)dtab + bytes - 32);
     RV_LAUNCH(split_reduce_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, parent->LCP, D, n, tiles);
-    RV_LAUNCH(split_tilescan_kernel, 1, 32, 0, st.s, tiles, ntiles, d_counts);
+    RV_LAUNCH(split_tilescan_kernel, 1, TS_THREADS, 0, st.s, tiles, ntiles, d_counts);
     RV_LAUNCH(split_apply_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, parent->SA, parent->LCP, D, n, tiles, v.ISA,
               kids[0] ? kids[0]->SA : nullptr, kids[0] ? kids[0]->LCP : nullptr, kids[1] ? kids[1]->SA : nullptr,
               kids[1] ? kids[1]->LCP : nullptr, kids[2] ? kids[2]->SA : nullptr, kids[2] ? kids[2]->LCP : nullptr, (u32)cls_n[0], (u32)cls_n[1],
@@ -1319,7 +1328,7 @@ int rv_sub_extract(rv_sub *sub, const int64_t *intervals, int32_t nintervals) {
     if (lease.take((size_t)ntiles * sizeof(SplitState) + 64, &dtiles) != RV_OK) { pool->give(p1); pool->give(p2); return RV_ERR_NOMEM; }
     SplitState *tiles = (SplitState *)dtiles;
     RV_LAUNCH(split_reduce_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, sub->LCP, D, n, tiles);
-    RV_LAUNCH(split_tilescan_kernel, 1, 32, 0, st.s, tiles, ntiles, d_counts);
+    RV_LAUNCH(split_tilescan_kernel, 1, TS_THREADS, 0, st.s, tiles, ntiles, d_counts);
     RV_LAUNCH(split_apply_kernel, (unsigned)ntiles, SP_THREADS, 0, st.s, sub->SA, sub->LCP, D, n, tiles, v.ISA, nSA, nLCP, (int *)nullptr, (int *)nullptr,
               (int *)nullptr, (int *)nullptr, (u32)cn, 0u, 0u);
     st.launches += 3;
