@@ -161,6 +161,20 @@ static int fail_native(int status) {
     return -1;
 }
 
+// Result lists hold hundreds of thousands of tuples of integers.  None of them can be part of a reference cycle, so they are taken
+// out of the cyclic collector's lists as they are made (what the collector itself does with such tuples when it meets them,
+// Objects/tupleobject.c _PyTuple_MaybeUntrack), and no collection is started while a list is being filled: more than half of a
+// getmums() call was the collector traversing the young tuples over and over.
+struct GcPause {
+    int was;
+    GcPause() : was(PyGC_Disable()) {}
+    ~GcPause() { if (was) PyGC_Enable(); }
+};
+static inline PyObject *atomic_tuple(PyObject *t) {
+    if (t) PyObject_GC_UnTrack(t);
+    return t;
+}
+
 static Index *root_of(Index *self) { return self->mainidx ? self->mainidx : self; }
 
 static int ensure_handle(Index *self) {
@@ -359,19 +373,20 @@ static int need_built(Index *self, PyObject *exc, const char *msg) {
 
 // ---- sweeps ------------------------------------------------------------------------------------------------------------------
 static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vector<int64_t> &mem, int64_t nrec, int64_t nmem, bool counts_are_sizes) {
+    GcPause gc_pause;
     PyObject *lst = PyList_New((Py_ssize_t)nrec);
     if (!lst) return nullptr;
     for (int64_t k = 0; k < nrec; k++) {
         int64_t l = hdr[3 * k], cnt = hdr[3 * k + 1], first = hdr[3 * k + 2];
         int64_t end = counts_are_sizes ? first + cnt : (k + 1 < nrec ? hdr[3 * (k + 1) + 2] : nmem);
-        PyObject *members = PyTuple_New((Py_ssize_t)(end - first));
+        PyObject *members = atomic_tuple(PyTuple_New((Py_ssize_t)(end - first)));
         for (int64_t x = first; x < end; x++) {
-            PyObject *sp = PyTuple_New(2);
+            PyObject *sp = atomic_tuple(PyTuple_New(2));
             PyTuple_SET_ITEM(sp, 0, PyLong_FromLong((long)mem[2 * x]));
             PyTuple_SET_ITEM(sp, 1, PyLong_FromLongLong((long long)mem[2 * x + 1]));
             PyTuple_SET_ITEM(members, (Py_ssize_t)(x - first), sp);
         }
-        PyObject *rec = PyTuple_New(3);  // (l, n, ((sample, position), ...)): reveal.c:497 / :353
+        PyObject *rec = atomic_tuple(PyTuple_New(3));  // (l, n, ((sample, position), ...)): reveal.c:497 / :353
         PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)l));
         PyTuple_SET_ITEM(rec, 1, PyLong_FromLong((long)cnt));
         PyTuple_SET_ITEM(rec, 2, members);
@@ -406,11 +421,12 @@ static PyObject *index_getmums(Index *self, PyObject *args) {
         rows.resize((size_t)(3 * k + 3));
         if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
     }
+    GcPause gc_pause;
     PyObject *lst = PyList_New((Py_ssize_t)k);
     if (!lst) return nullptr;
     PyObject *rcobj = PyLong_FromLong(self->rc);
     for (int64_t i = 0; i < k; i++) {  // (l, (a, b), rc): reveal.c:102-106 -- built without format parsing, this list is the bulk of the call
-        PyObject *ab = PyTuple_New(2), *rec = PyTuple_New(3);
+        PyObject *ab = atomic_tuple(PyTuple_New(2)), *rec = atomic_tuple(PyTuple_New(3));
         PyTuple_SET_ITEM(ab, 0, PyLong_FromLongLong((long long)rows[3 * i + 1]));
         PyTuple_SET_ITEM(ab, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
         PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));
@@ -587,10 +603,11 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn, bool
         mr->rows = new std::vector<int64_t>(std::move(rows));
         return (PyObject *)mr;
     }
+    GcPause gc_pause;
     PyObject *lst = PyList_New((Py_ssize_t)nr);
     PyObject *two = PyLong_FromLong(2), *zero = PyLong_FromLong(0), *one = PyLong_FromLong(1);
     for (int64_t i = 0; i < nr; i++) {  // (l, 2, ((0, a), (1, b))): reveal.c:167-169
-        PyObject *sa = PyTuple_New(2), *sb = PyTuple_New(2), *mem = PyTuple_New(2), *rec = PyTuple_New(3);
+        PyObject *sa = atomic_tuple(PyTuple_New(2)), *sb = atomic_tuple(PyTuple_New(2)), *mem = atomic_tuple(PyTuple_New(2)), *rec = atomic_tuple(PyTuple_New(3));
         Py_INCREF(zero);
         PyTuple_SET_ITEM(sa, 0, zero);
         PyTuple_SET_ITEM(sa, 1, PyLong_FromLongLong((long long)rows[3 * i + 1]));
@@ -1245,11 +1262,12 @@ static PyObject *mod_chain_dp(PyObject *, PyObject *args) {
 // per pair).  A pair longer than the block path holds, or with more MUMs than a block reports, is built as a regular index.
 static rv_index *g_batch_ws = nullptr;
 static PyObject *pair_rows_to_list(const int64_t *rows, int64_t k) {
+    GcPause gc_pause;
     PyObject *lst = PyList_New((Py_ssize_t)k);
     if (!lst) return nullptr;
     PyObject *zero = PyLong_FromLong(0);
     for (int64_t i = 0; i < k; i++) {  // (l, (a, b), rc): reveal.c:102-106
-        PyObject *ab = PyTuple_New(2), *rec = PyTuple_New(3);
+        PyObject *ab = atomic_tuple(PyTuple_New(2)), *rec = atomic_tuple(PyTuple_New(3));
         PyTuple_SET_ITEM(ab, 0, PyLong_FromLongLong((long long)rows[3 * i + 1]));
         PyTuple_SET_ITEM(ab, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
         PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));

@@ -131,6 +131,30 @@ struct rv_index {
 
 extern "C" void rv_pool_destroy(void *pool);
 
+// The CUDA objects of a handle that owns its stream -- stream, 2 KB of pinned memory, phase events, profile events -- and the
+// alphabet of the last text it built outlive the handle in a small cache: a caller that creates one index object per alignment
+// (the extension does) pays no cudaStreamCreate / cudaMallocHost / cudaFreeHost per construct(), and its first build starts
+// speculatively with the previous text's code table instead of waiting for the byte histogram.
+struct Shell {
+    int device;
+    cudaStream_t s;
+    u32 *pinned;
+    cudaEvent_t ev[6];
+    std::vector<cudaEvent_t> free_events;
+    AlphaCache alpha;
+};
+static std::vector<Shell> g_shells;
+static const size_t SHELL_SLOTS = 4;
+
+static void shell_destroy(Shell &sh) {
+    for (int i = 0; i < 6; i++)
+        if (sh.ev[i]) cudaEventDestroy(sh.ev[i]);
+    for (cudaEvent_t e : sh.free_events) cudaEventDestroy(e);
+    if (sh.pinned) cudaFreeHost(sh.pinned);
+    if (sh.s) cudaStreamDestroy(sh.s);
+}
+
+
 static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
 extern "C" {
@@ -204,11 +228,14 @@ void rv_host_free(void *ptr) {
 }
 int rv_trim(void) {
     std::vector<Cached> d, h;
+    std::vector<Shell> shells;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         d.swap(g_dev_cache);
         h.swap(g_host_cache);
+        shells.swap(g_shells);
     }
+    for (Shell &sh : shells) shell_destroy(sh);
     int cur = 0;
     cudaGetDevice(&cur);
     for (Cached &c : d) {
@@ -232,6 +259,22 @@ int rv_index_create(rv_index **out, void *stream) {
     rv_index *h = new rv_index();
     memset(&h->times, 0, sizeof h->times);
     cudaGetDevice(&h->device);
+    if (!stream) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_shells.size(); i++)
+            if (g_shells[i].device == h->device) {
+                Shell &sh = g_shells[i];
+                h->st.s = sh.s;
+                h->st.pinned = sh.pinned;
+                h->st.alpha = sh.alpha;
+                h->st.free_events.swap(sh.free_events);
+                for (int k = 0; k < 6; k++) h->ev[k] = sh.ev[k];
+                h->own_stream = true;
+                g_shells.erase(g_shells.begin() + (long)i);
+                *out = h;
+                return RV_OK;
+            }
+    }
     if (stream) {
         h->st.s = (cudaStream_t)stream;
     } else {
@@ -273,12 +316,23 @@ void rv_index_free(rv_index *h) {
     h->sw.release();
     h->res.release();
     h->chain.release();
-    for (int i = 0; i < 6; i++)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     prof_collect(h->st);
-    for (cudaEvent_t e : h->st.free_events) cudaEventDestroy(e);
-    if (h->st.pinned) cudaFreeHost(h->st.pinned);
-    if (h->own_stream) cudaStreamDestroy(h->st.s);
+    Shell sh;
+    sh.device = h->device;
+    sh.s = h->own_stream ? h->st.s : (cudaStream_t)0;
+    sh.pinned = h->st.pinned;
+    for (int i = 0; i < 6; i++) sh.ev[i] = h->ev[i];
+    sh.free_events.swap(h->st.free_events);
+    sh.alpha = h->st.alpha;
+    bool kept = false;
+    if (h->own_stream && cudaGetLastError() == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_shells.size() < SHELL_SLOTS) {
+            g_shells.push_back(std::move(sh));
+            kept = true;
+        }
+    }
+    if (!kept) shell_destroy(sh);
     delete h;
 }
 

@@ -40,6 +40,7 @@ def run(files, module, label):
     try:
         from reveal_b200 import remcore
         chain = remcore.chain_stats()
+        chain["pick_phases_s"] = remcore.pick_phases()
     except Exception:
         chain = None
     return {"arm": label, "align_stats": stats, "chain_stats": chain, "seconds": t2 - t0, "align_genomes_s": t1 - t0, "aligned_bases": bases, "total_bases": total,
