@@ -213,6 +213,13 @@ typedef struct rv_step_desc {
     int32_t status;        /* out: rv_status of this step */
 } rv_step_desc;
 int rv_sub_step_batch(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn);
+/* The same batch in two halves, so that the caller's host work for the NEXT batch (the two callbacks of every waiting
+ * sub-index) overlaps the device part of this one: _begin stages the steps, enqueues the launch and returns a ticket, _end
+ * waits for it (an event), fills children / status of every step and frees the ticket.  `steps` stays valid and untouched in
+ * between; one open ticket per main index.  rv_sub_step_batch = _begin + _end. */
+typedef struct rv_step_batch rv_step_batch;
+int rv_sub_step_batch_begin(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn, rv_step_batch **ticket);
+int rv_sub_step_batch_end(rv_step_batch *ticket);
 /* steps2[0]/seconds2[0]: recursion steps taken by the single-launch path and their host wall time; [1]: general path */
 int rv_rec_stats(rv_index *idx, int64_t *steps2, double *seconds2);
 int rv_rec_launches(rv_index *idx, int64_t *launches2); /* launches behind those steps: [0] one per batch, [1] general-path calls */

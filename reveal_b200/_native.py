@@ -79,6 +79,8 @@ SIGNATURES = {
     "rv_mums_tiny_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
     "rv_chain_batch": (ctypes.c_int, [c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, c_vp, c_vp]),
     "rv_sub_step_batch": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    "rv_sub_step_batch_begin": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_vp)]),
+    "rv_sub_step_batch_end": (ctypes.c_int, [c_vp]),
     "rv_sub_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64]),
     "rv_result_pack_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64]),
     "rv_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),

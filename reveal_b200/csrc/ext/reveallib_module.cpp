@@ -38,7 +38,7 @@
     X(rv_last_error) X(rv_version) X(rv_host_alloc) X(rv_host_free) X(rv_index_create) X(rv_index_free) X(rv_build) X(rv_build_cached) X(rv_get_times)   \
     X(rv_get_sa) X(rv_get_sai) X(rv_get_lcp) X(rv_get_so) X(rv_get_text) X(rv_put_text) X(rv_mums_pair_count) X(rv_mums_pair_fetch)    \
     X(rv_mums_multi_count) X(rv_mems_multi_count) X(rv_mums_multi_fetch) X(rv_sub_root) X(rv_sub_n) X(rv_sub_free) X(rv_sub_get)    \
-    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch) X(rv_sub_extract) X(rv_mums_tiny_batch)
+    X(rv_sub_mums_pair) X(rv_sub_mums_multi) X(rv_sub_fetch) X(rv_sub_step) X(rv_sub_step_batch) X(rv_sub_step_batch_begin) X(rv_sub_step_batch_end) X(rv_sub_extract) X(rv_mums_tiny_batch)
 
 struct Api {
 #define X(name) decltype(&::name) name = nullptr;
@@ -715,9 +715,66 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
     const double t_begin = now_s();
     PyObject *kw_minl = PyLong_FromLong(minl);
     std::vector<PendingStep *> batch;
-    std::vector<rv_step_desc> descs;
+    // Device / host overlap: the device part of a batch is only ENQUEUED (rv_sub_step_batch_begin); while it runs, the callbacks
+    // of the next sub-indexes on the queue are served, and its children are collected (rv_sub_step_batch_end) right before the
+    // next batch goes out.  (Taking a frontier that fits one batch in two halves, so that there always is something to overlap,
+    // was measured and dropped: the host side of a launch costs more than the wait it hides -- RV_ALIGN_SPLIT=1 brings it back.)
+    struct InFlight {
+        std::vector<PendingStep *> batch;
+        std::vector<rv_step_desc> descs;
+        rv_step_batch *ticket = nullptr;
+        bool open = false;
+    } fly;
+    const bool overlap = batch_max > 1 && !getenv("RV_ALIGN_NO_OVERLAP");
+    const bool split_frontier = getenv("RV_ALIGN_SPLIT") != nullptr;
+    // waits for the batch in flight, creates its children (pushed on the queue) and releases its steps
+    auto finish = [&]() {
+        if (!fly.open) return;
+        fly.open = false;
+        double t0 = now_s();
+        int status;
+        Py_BEGIN_ALLOW_THREADS;
+        status = g_api.rv_sub_step_batch_end(fly.ticket);
+        Py_END_ALLOW_THREADS;
+        fly.ticket = nullptr;
+        double t1 = now_s(); as.step += t1 - t0; t0 = t1;
+        if (status != 0 || !ok) {
+            if (ok) { fail_native(status); ok = false; }
+            for (rv_step_desc &d : fly.descs)   // children of the steps that did succeed
+                for (int c = 0; c < 3; c++)
+                    if (d.children[c]) g_api.rv_sub_free(d.children[c]);
+        } else {
+            PyObject *empty = PyList_New(0);
+            for (size_t i = 0; i < fly.batch.size(); i++) {
+                PendingStep &p = *fly.batch[i];
+                rv_sub **kids = fly.descs[i].children;
+                const int depth = p.idx->depth + 1;
+                Index *i_par = kids[2] ? new_child(self, kids[2], p.parn, depth, count_samples(self, p.par_b), p.rest, p.idx->left_node, p.idx->right_node, empty) : nullptr;
+                Index *i_lead = kids[0] ? new_child(self, kids[0], p.leadn, depth, count_samples(self, p.lead_b), p.leading, p.idx->left_node, p.newright, p.skipleft) : nullptr;
+                Index *i_trail = kids[1] ? new_child(self, kids[1], p.trailn, depth, count_samples(self, p.trail_b), p.trailing, p.newleft, p.idx->right_node, p.skipright) : nullptr;
+                if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
+                if (i_lead) queue.push_back(i_lead);
+                if (i_trail) queue.push_back(i_trail);
+            }
+            Py_DECREF(empty);
+        }
+        as.child += now_s() - t0;
+        for (PendingStep *p : fly.batch) {
+            Py_XDECREF(p->pick);
+            Py_XDECREF(p->result);
+            release_index_view(p->idx);
+            delete p;
+        }
+        fly.batch.clear();
+    };
     for (;;) {
-    while (ok && !queue.empty()) {
+    while (ok && (!queue.empty() || fly.open)) {
+        if (queue.empty()) {  // nothing to overlap with: the children of the batch in flight are the work
+            finish();
+            continue;
+        }
+        size_t take = batch_max;
+        if (overlap && split_frontier && queue.size() > 2 && queue.size() < 2 * batch_max) take = (queue.size() + 1) / 2;
         // ---- the sub-indexes on top of the queue (LIFO, reveal.c:21-26) and their MUM lists ----
         std::vector<PendingStep *> cand;
         std::vector<PyObject *> cand_mums;   // owned
@@ -726,7 +783,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             PyErr_SetString(PyExc_TypeError, "**** mumpicker isn't callable");
             ok = false;
         }
-        while (ok && !queue.empty() && cand.size() < batch_max) {
+        while (ok && !queue.empty() && cand.size() < take) {
             Index *idx = queue.back();
             queue.pop_back();
             if (prefix && idx != self && idx->n <= unit_max) {  // below the cut: a unit, dealt out once the part above the cut is done
@@ -843,13 +900,15 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                 delete ps;
             }
         }
-        // ---- the device part of every staged step: one call ----
+        // ---- the batch in flight has had its overlap: collect it (its children go on the queue) ----
+        finish();
+        // ---- the device part of every staged step: one launch, left in flight ----
         if (ok && !batch.empty()) {
             double t0 = now_s();
-            descs.assign(batch.size(), rv_step_desc());
+            fly.descs.assign(batch.size(), rv_step_desc());
             for (size_t i = 0; i < batch.size(); i++) {
                 PendingStep &p = *batch[i];
-                rv_step_desc &d = descs[i];
+                rv_step_desc &d = fly.descs[i];
                 memset(&d, 0, sizeof d);
                 d.parent = p.idx->sub;
                 d.lead = p.lead.data(); d.nlead = (int32_t)p.lead_b.size();
@@ -859,35 +918,18 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                 d.matching = p.match.data(); d.nmatch = (int32_t)p.match_b.size();
                 for (int c = 0; c < 3; c++) d.sweep[c] = p.sweep[c];
             }
-            int status;
-            Py_BEGIN_ALLOW_THREADS;
-            status = g_api.rv_sub_step_batch(descs.data(), (int32_t)descs.size(), minl, minn);
-            Py_END_ALLOW_THREADS;
-            double t1 = now_s(); as.step += t1 - t0; t0 = t1;
+            int status = g_api.rv_sub_step_batch_begin(fly.descs.data(), (int32_t)fly.descs.size(), minl, minn, &fly.ticket);
+            as.step += now_s() - t0;
             as.steps += (long long)batch.size();
             as.batches++;
             self->tdirty = 1;  // matched bases were lower-cased on the device (reveal.c:1230-1234)
             if (fail_native(status) != 0) {
                 ok = false;
-                for (rv_step_desc &d : descs)   // children of the steps that did succeed
-                    for (int c = 0; c < 3; c++)
-                        if (d.children[c]) g_api.rv_sub_free(d.children[c]);
             } else {
-                PyObject *empty = PyList_New(0);
-                for (size_t i = 0; i < batch.size(); i++) {
-                    PendingStep &p = *batch[i];
-                    rv_sub **kids = descs[i].children;
-                    const int depth = p.idx->depth + 1;
-                    Index *i_par = kids[2] ? new_child(self, kids[2], p.parn, depth, count_samples(self, p.par_b), p.rest, p.idx->left_node, p.idx->right_node, empty) : nullptr;
-                    Index *i_lead = kids[0] ? new_child(self, kids[0], p.leadn, depth, count_samples(self, p.lead_b), p.leading, p.idx->left_node, p.newright, p.skipleft) : nullptr;
-                    Index *i_trail = kids[1] ? new_child(self, kids[1], p.trailn, depth, count_samples(self, p.trail_b), p.trailing, p.newleft, p.idx->right_node, p.skipright) : nullptr;
-                    if (i_par) queue.push_back(i_par);      // push order of reveal.c:1296-1324
-                    if (i_lead) queue.push_back(i_lead);
-                    if (i_trail) queue.push_back(i_trail);
-                }
-                Py_DECREF(empty);
+                fly.batch.swap(batch);
+                fly.open = true;
+                if (!overlap) finish();
             }
-            as.child += now_s() - t0;
         }
         for (PendingStep *p : batch) {
             Py_XDECREF(p->pick);
@@ -897,6 +939,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
         }
         batch.clear();
     }
+    finish();  // (an error left a batch in flight)
     if (!ok || !prefix) break;
     // ---- the part above the cut is done on every rank: deal the units out ----
     prefix = false;

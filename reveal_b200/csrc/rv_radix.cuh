@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict_
 }
 
 #ifndef RV_RS_MINBLOCKS
-#define RV_RS_MINBLOCKS 4
+#define RV_RS_MINBLOCKS 5
 #endif
 template <typename KeyT, bool HAS_VAL, bool FROM_TEXT>
 __global__ void __launch_bounds__(RS_THREADS, RV_RS_MINBLOCKS)

@@ -38,7 +38,10 @@ static const int AP_THREADS = 256;
 static const int AP_IPT = 8;
 static const int AP_TILE = AP_THREADS * AP_IPT;  // 2048 active entries per tile
 
-static const int SA_SMALL_G = 16;     // largest group finished by direct comparison
+#ifndef RV_SA_SMALL_G
+#define RV_SA_SMALL_G 16
+#endif
+static const int SA_SMALL_G = RV_SA_SMALL_G;     // largest group finished by direct comparison (<= 16: group geometry lives in 32-key windows)
 #ifndef RV_SA_CMP_CAP
 #define RV_SA_CMP_CAP 65536
 #endif

@@ -692,6 +692,7 @@ struct RecCtx {
     i64 *h_out = nullptr, *d_out = nullptr;
     i64 out_words = 0;
     SmallStepArgs *h_args = nullptr, *d_args = nullptr;  // host-mapped argument blocks of one batch (SM_BATCH steps)
+    struct rv_step_batch *open_ticket = nullptr;         // rv_sub_step_batch_begin without its _end yet
     // step statistics: [0] single-launch path, [1] general path
     long long steps[2] = {0, 0};
     long long launches[2] = {0, 0};
@@ -1142,83 +1143,182 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
 // Recursion steps of one main index, as many as the caller has ready (a frontier of independent sub-indexes, reveal.c:1296-1324
 // pushes up to three per step): the steps whose parent fits a thread block go through ONE launch and ONE synchronisation, one
 // block per step; the others take the general path one after the other.  Every step reports its own status.
-int rv_sub_step_batch(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn) {
+//
+// Two halves so that a caller can overlap the device part of one batch with the host part (callbacks) of the next one:
+//   rv_sub_step_batch_begin  checks and stages the steps, enqueues the launch and returns a ticket; when the batch needs several
+//                            launches (more than SM_BATCH block-sized steps) only the last one is left in flight
+//   rv_sub_step_batch_end    waits for that launch (an event, not the whole stream), hands children and statuses over, runs
+//                            the general-path steps, frees the ticket
+// `steps` must stay valid and untouched in between, and at most ONE ticket of a main index may be open at a time: the argument
+// blocks and the result buffer of the launch are single host-mapped arrays of the index.
+struct rv_step_batch {
+    rv_step_desc *steps = nullptr;
+    int32_t nsteps = 0, minl = 0, minn = 0;
+    MainView v;
+    RecCtx *ctx = nullptr;
+    int worst = RV_OK;
+    std::vector<int> general, which;
+    std::vector<SmallPrep> prep;
+    cudaEvent_t done = 0;
+    bool launched = false;
+    double t0 = 0;
+};
+
+static int batch_collect(rv_step_batch *b) {
+    RecCtx *ctx = b->ctx;
+    const int m = (int)b->which.size();
+    for (int k = 0; k < m; k++) {
+        int r = small_collect(b->steps[b->which[k]], ctx, b->prep[k], b->minl, b->minn);
+        if (r != RV_OK) {
+            b->steps[b->which[k]].status = r;
+            b->worst = r;
+        }
+    }
+    ctx->steps[0] += m;
+    ctx->launches[0]++;
+    ctx->host_s[0] += now_s() - b->t0;
+    b->which.clear();
+    b->prep.clear();
+    b->launched = false;
+    return RV_OK;
+}
+
+int rv_sub_step_batch_begin(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn, rv_step_batch **ticket) {
+    if (!ticket) return RV_ERR_ARG;
+    *ticket = nullptr;
     if (!steps || nsteps < 0) return RV_ERR_ARG;
-    if (nsteps == 0) return RV_OK;
     for (int i = 0; i < nsteps; i++) {
         if (!steps[i].parent || steps[i].parent->main != steps[0].parent->main) { set_error("rv_sub_step_batch: steps of different indexes"); return RV_ERR_ARG; }
         steps[i].children[0] = steps[i].children[1] = steps[i].children[2] = nullptr;
         steps[i].status = RV_OK;
     }
-    MainView v;
-    RV_TRY(main_view(steps[0].parent->main, &v));
-    RecCtx *ctx = nullptr;
-    RV_TRY(small_ctx(v, &ctx));
-    Stream &st = *v.st;
-    int worst = RV_OK;
-    std::vector<int> general;
+    rv_step_batch *b = new rv_step_batch();
+    b->steps = steps;
+    b->nsteps = nsteps;
+    b->minl = minl;
+    b->minn = minn;
+    *ticket = b;
+    if (nsteps == 0) return RV_OK;
+    int r0 = main_view(steps[0].parent->main, &b->v);
+    if (r0 == RV_OK) r0 = small_ctx(b->v, &b->ctx);
+    if (r0 == RV_OK && b->ctx->open_ticket) {
+        set_error("rv_sub_step_batch_begin: another batch of this index is still open");
+        r0 = RV_ERR_STATE;
+    }
+    if (r0 != RV_OK) {
+        delete b;
+        *ticket = nullptr;
+        return r0;
+    }
+    RecCtx *ctx = b->ctx;
+    Stream &st = *b->v.st;
     for (int base = 0; base < nsteps;) {
+        if (b->launched) {  // a batch of more than SM_BATCH block-sized steps: the argument blocks are needed again
+            cudaError_t e = cudaEventSynchronize(b->done);
+            if (e != cudaSuccess) { set_error("rv_sub_step_batch: %s", cudaGetErrorString(e)); b->worst = RV_ERR_CUDA; b->launched = false; break; }
+            batch_collect(b);
+        }
         // ---- one launch: the next run of (at most SM_BATCH) steps ----
-        const double t0 = now_s();
-        std::vector<SmallPrep> prep;
-        std::vector<int> which;
+        b->t0 = now_s();
         int i = base;
-        for (; i < nsteps && (int)which.size() < SM_BATCH; i++) {
+        for (; i < nsteps && (int)b->which.size() < SM_BATCH; i++) {
             SmallPrep pp;
             int handled = 0;
-            int r = small_prepare(steps[i], v, ctx, minl, minn, ctx->h_args[which.size()], pp, &handled);
+            int r = small_prepare(steps[i], b->v, ctx, minl, minn, ctx->h_args[b->which.size()], pp, &handled);
             if (r != RV_OK) {
                 steps[i].status = r;
-                worst = r;
+                b->worst = r;
                 continue;
             }
             if (!handled) {
-                general.push_back(i);
+                b->general.push_back(i);
                 continue;
             }
-            which.push_back(i);
-            prep.push_back(pp);
+            b->which.push_back(i);
+            b->prep.push_back(pp);
         }
         base = i;
-        const int m = (int)which.size();
+        const int m = (int)b->which.size();
         if (m > 0) {
             // every step gets an equal share of the host-mapped result buffer (a child whose MUMs do not fit is swept again later)
             const i64 share = (ctx->out_words / m) & ~(i64)7;
             for (int k = 0; k < m; k++) {
-                prep[k].out_off = share * k;
-                prep[k].out_words = share;
+                b->prep[k].out_off = share * k;
+                b->prep[k].out_words = share;
                 ctx->h_args[k].out = ctx->d_out + share * k;
                 ctx->h_args[k].out_words = share;
             }
-            RV_LAUNCH(small_step_kernel, (unsigned)m, SM_THREADS, 0, st.s, (const SmallStepArgs *)ctx->d_args);
-            st.launches++;
-            RV_CUDA(cudaStreamSynchronize(st.s));
-            RV_KCHECK();
-            for (int k = 0; k < m; k++) {
-                int r = small_collect(steps[which[k]], ctx, prep[k], minl, minn);
-                if (r != RV_OK) {
-                    steps[which[k]].status = r;
-                    worst = r;
-                }
+            cudaError_t e = cudaSuccess;
+            if (!b->done) e = cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming);
+            if (e == cudaSuccess) {
+                RV_LAUNCH(small_step_kernel, (unsigned)m, SM_THREADS, 0, st.s, (const SmallStepArgs *)ctx->d_args);
+                e = cudaGetLastError();
             }
-            ctx->steps[0] += m;
-            ctx->launches[0]++;
-            ctx->host_s[0] += now_s() - t0;
+            if (e == cudaSuccess) e = cudaEventRecord(b->done, st.s);
+            if (e != cudaSuccess) {
+                set_error("rv_sub_step_batch: launch failed: %s", cudaGetErrorString(e));
+                for (int k = 0; k < m; k++) {
+                    for (int q = 0; q < 3; q++) rv_sub_free(b->prep[k].kids[q]);
+                    steps[b->which[k]].status = RV_ERR_CUDA;
+                }
+                b->which.clear();
+                b->prep.clear();
+                b->worst = RV_ERR_CUDA;
+                break;
+            }
+            st.launches++;
+            b->launched = true;
         }
     }
-    for (int i : general) {
+    ctx->open_ticket = b;
+    return RV_OK;
+}
+
+int rv_sub_step_batch_end(rv_step_batch *b) {
+    if (!b) return RV_ERR_ARG;
+    if (b->nsteps == 0 || !b->ctx) {
+        delete b;
+        return RV_OK;
+    }
+    RecCtx *ctx = b->ctx;
+    if (b->launched) {
+        cudaError_t e = cudaEventSynchronize(b->done);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("rv_sub_step_batch: %s", cudaGetErrorString(e));
+            for (size_t k = 0; k < b->which.size(); k++) {
+                for (int q = 0; q < 3; q++) rv_sub_free(b->prep[k].kids[q]);
+                b->steps[b->which[k]].status = RV_ERR_CUDA;
+            }
+            b->worst = RV_ERR_CUDA;
+            b->launched = false;
+        } else {
+            batch_collect(b);
+        }
+    }
+    for (int i : b->general) {
         const double t0 = now_s();
-        rv_step_desc &d = steps[i];
+        rv_step_desc &d = b->steps[i];
         int r = split_general(d.parent, d.lead, d.nlead, d.trail, d.ntrail, d.par, d.npar, d.mum_sp, d.mum_n, d.mum_l, d.matching, d.nmatch, d.children);
         if (r != RV_OK) {
             d.status = r;
-            worst = r;
+            b->worst = r;
         }
         ctx->steps[1]++;
         ctx->launches[1]++;
         ctx->host_s[1] += now_s() - t0;
     }
+    const int worst = b->worst;
+    if (b->done) cudaEventDestroy(b->done);
+    ctx->open_ticket = nullptr;
+    delete b;
     return worst;
+}
+
+int rv_sub_step_batch(rv_step_desc *steps, int32_t nsteps, int32_t minl, int32_t minn) {
+    rv_step_batch *b = nullptr;
+    RV_TRY(rv_sub_step_batch_begin(steps, nsteps, minl, minn, &b));
+    return rv_sub_step_batch_end(b);
 }
 
 int rv_sub_step(rv_sub *parent, const int64_t *lead, int32_t nlead, const int64_t *trail, int32_t ntrail, const int64_t *par, int32_t npar,
