@@ -138,6 +138,8 @@ extern "C" void rv_pool_destroy(void *pool);
 struct Shell {
     int device;
     cudaStream_t s;
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     u32 *pinned;
     cudaEvent_t ev[6];
     std::vector<cudaEvent_t> free_events;
@@ -151,6 +153,9 @@ static void shell_destroy(Shell &sh) {
         if (sh.ev[i]) cudaEventDestroy(sh.ev[i]);
     for (cudaEvent_t e : sh.free_events) cudaEventDestroy(e);
     if (sh.pinned) cudaFreeHost(sh.pinned);
+    if (sh.ev_fork) cudaEventDestroy(sh.ev_fork);
+    if (sh.ev_join) cudaEventDestroy(sh.ev_join);
+    if (sh.side) cudaStreamDestroy(sh.side);
     if (sh.s) cudaStreamDestroy(sh.s);
 }
 
@@ -265,6 +270,9 @@ int rv_index_create(rv_index **out, void *stream) {
             if (g_shells[i].device == h->device) {
                 Shell &sh = g_shells[i];
                 h->st.s = sh.s;
+                h->st.side = sh.side;
+                h->st.ev_fork = sh.ev_fork;
+                h->st.ev_join = sh.ev_join;
                 h->st.pinned = sh.pinned;
                 h->st.alpha = sh.alpha;
                 h->st.free_events.swap(sh.free_events);
@@ -311,6 +319,7 @@ int rv_index_create(rv_index **out, void *stream) {
 void rv_index_free(rv_index *h) {
     if (!h) return;
     cudaStreamSynchronize(h->st.s);
+    if (h->st.side) cudaStreamSynchronize(h->st.side);
     rv_pool_destroy(h->pool);
     h->arena.release();
     h->sw.release();
@@ -320,6 +329,9 @@ void rv_index_free(rv_index *h) {
     Shell sh;
     sh.device = h->device;
     sh.s = h->own_stream ? h->st.s : (cudaStream_t)0;
+    sh.side = h->st.side;
+    sh.ev_fork = h->st.ev_fork;
+    sh.ev_join = h->st.ev_join;
     sh.pinned = h->st.pinned;
     for (int i = 0; i < 6; i++) sh.ev[i] = h->ev[i];
     sh.free_events.swap(h->st.free_events);

@@ -70,6 +70,10 @@ struct AlphaCache {
 
 struct Stream {
     cudaStream_t s = 0;
+    // Side stream of a build: work that does not depend on the radix sort (byte histogram, text pass, clearing of the comparison
+    // stage's tables) runs beside the digit passes; forked from / joined into `s` with the two events.  Created on first use.
+    cudaStream_t side = 0;
+    cudaEvent_t ev_fork = 0, ev_join = 0;
     u32 *pinned = nullptr;      // 2 KB of pinned host memory for small asynchronous read-backs
     AlphaCache alpha;
     int launches = 0;           // kernels launched by this library on the stream since the last reset
@@ -94,28 +98,46 @@ inline int prof_event(Stream &st, cudaEvent_t *e) {
     RV_CUDA(cudaEventCreate(e));
     return RV_OK;
 }
-inline int prof_begin(Stream &st) {
+// (`on`: the stream the bracketed kernels are launched on, st.s by default; begin / end pairs do not nest)
+inline int prof_begin(Stream &st, cudaStream_t on = 0) {
     if (!st.prof) return RV_OK;
     RV_TRY(prof_event(st, &st.cur0));
-    RV_CUDA(cudaEventRecord(st.cur0, st.s));
+    RV_CUDA(cudaEventRecord(st.cur0, on ? on : st.s));
     return RV_OK;
 }
-inline int prof_end(Stream &st, int slot, long long launches, long long bytes) {
+inline int prof_end(Stream &st, int slot, long long launches, long long bytes, cudaStream_t on = 0) {
     if (!st.prof) return RV_OK;
     ProfRec r;
     r.e0 = st.cur0;
     RV_TRY(prof_event(st, &r.e1));
-    RV_CUDA(cudaEventRecord(r.e1, st.s));
+    RV_CUDA(cudaEventRecord(r.e1, on ? on : st.s));
     r.slot = slot;
     r.launches = launches;
     r.bytes = bytes;
     st.pending.push_back(r);
     return RV_OK;
 }
+// fork: the side stream waits for everything enqueued on st.s so far; join: st.s waits for the side stream
+inline int side_fork(Stream &st) {
+    if (!st.ev_fork) {
+        RV_CUDA(cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking));
+        RV_CUDA(cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming));
+        RV_CUDA(cudaEventCreateWithFlags(&st.ev_join, cudaEventDisableTiming));
+    }
+    RV_CUDA(cudaEventRecord(st.ev_fork, st.s));
+    RV_CUDA(cudaStreamWaitEvent(st.side, st.ev_fork, 0));
+    return RV_OK;
+}
+inline int side_join(Stream &st) {
+    RV_CUDA(cudaEventRecord(st.ev_join, st.side));
+    RV_CUDA(cudaStreamWaitEvent(st.s, st.ev_join, 0));
+    return RV_OK;
+}
 // resolve the recorded pairs (synchronises the stream)
 inline int prof_collect(Stream &st) {
     if (st.pending.empty()) return RV_OK;
     RV_CUDA(cudaStreamSynchronize(st.s));
+    if (st.side) RV_CUDA(cudaStreamSynchronize(st.side));
     for (ProfRec &r : st.pending) {
         float ms = 0;
         RV_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));

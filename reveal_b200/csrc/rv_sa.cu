@@ -894,7 +894,7 @@ struct SaBuffers {
 template <typename KeyT>
 static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char *dT, i64 n, const CodeTable &tab, int sigma, u32 base, int k,
                             int key_bits, int *dSA, int *dISA, int *dLCP, KeyT **keys_out, u32 **sa_out, u32 **sa_free, bool *packed_out,
-                            PhaseTimes *pt) {
+                            PhaseTimes *pt, cudaStream_t aux) {
     KeyT *k0 = (KeyT *)B.k0, *k1 = (KeyT *)B.k1;
     // the (key, suffix) pairs are virtual: the histogram kernel and the first digit pass roll the k-mer keys
     // straight from the text (TextKeySrc), so no key array is written before the first scatter
@@ -908,14 +908,10 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     src.pw[0] = 1;
     for (int t = 1; t < 64; t++) src.pw[t] = t < k ? src.pw[t - 1] * (u64)base : 0;
     memcpy(src.code, st.alpha.kcls, sizeof src.code);  // key digits = classes (rare symbols merged), not the exact codes
-    bool in0;
-    RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0, &src));
-    if (pt) pt->sa_sorted_items += n;
-    KeyT *keys = in0 ? k0 : k1;
-    u32 *sa = in0 ? B.v0 : B.v1;
-    // comparison stage
-    RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, st.s));
-    RV_CUDA(cudaMemsetAsync(B.needbits, 0, (size_t)(n / 32 + 2) * 4, st.s));
+    // ---- beside the digit passes (stream `aux`, joined below): the tables of the comparison stage are cleared and the text pass
+    //      (barrier bitmaps, 4-bit packed text) runs; neither depends on the sort ----
+    RV_CUDA(cudaMemsetAsync(B.deferred, 0, (size_t)n, aux));
+    RV_CUDA(cudaMemsetAsync(B.needbits, 0, (size_t)(n / 32 + 2) * 4, aux));
     const i64 pr_per_block = (i64)PR_WARPS * PR_CHUNK;
     // text for the comparisons: 4-bit packed codes when the alphabet allows (sigma <= 15), else the raw bytes
     const bool packed = sigma <= 15 && !getenv("RV_SA_NO_PACK");  // env: test hook for the byte path
@@ -932,16 +928,22 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
             if ((st.alpha.kcls[c] & 0x100) && st.alpha.code[c] && c != '$' && c != 'N') ok = false;
         if (ok) key_digits2 = k;
     }
-    RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, st.s));
+    RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, aux));
     const int step_syms = packed ? 32 : 16;
-    RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, st.s));
-    RV_TRY(prof_begin(st));
+    RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, aux));
+    RV_TRY(prof_begin(st, aux));
     if (packed) {
-        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, TP_THREADS, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
+        RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, TP_THREADS, 0, aux, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     } else {
-        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, TP_THREADS, 0, st.s, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
+        RV_LAUNCH((sa_textprep_kernel<false>), prep_blocks, TP_THREADS, 0, aux, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     }
-    RV_TRY(prof_end(st, RV_PROF_TEXT, 1, (long long)n));
+    RV_TRY(prof_end(st, RV_PROF_TEXT, 1, (long long)n, aux));
+    bool in0;
+    RV_TRY(radix_sort_pairs<KeyT>(st, k0, k1, B.v0, B.v1, n, make_plan(0, key_bits), B.rscratch, &in0, &src));
+    if (pt) pt->sa_sorted_items += n;
+    KeyT *keys = in0 ? k0 : k1;
+    u32 *sa = in0 ? B.v0 : B.v1;
+    if (aux != st.s) RV_TRY(side_join(st));
     const u32 *W = packed ? (const u32 *)B.packed : (const u32 *)dT;
     RV_TRY(prof_begin(st));
     if (packed) {
@@ -1090,16 +1092,24 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     // 1. alphabet.  The histogram always runs, but when the handle has built a text before, the build starts at once
     //    with that text's code table and the histogram is only checked at the single synchronisation point below
     //    (a symbol the table lacks -> rebuild with the fresh table).  The first build on a handle waits for it.
+    //    Work that does not depend on the radix sort -- this histogram, the text pass and the clearing of the comparison
+    //    stage's tables -- runs on the handle's side stream, beside the digit passes (RV_SA_NO_SIDE=1: everything on one stream).
     u32 *hist = st.pinned;  // [0..255] counts, [256] stage-4 flag
-    RV_CUDA(cudaMemsetAsync(B.small, 0, 512 * 4, st.s));
+    const bool speculative = st.alpha.valid && !fresh_alphabet;
+    const bool use_side = !getenv("RV_SA_NO_SIDE");
+    cudaStream_t aux = st.s;
+    if (use_side && speculative) {
+        RV_TRY(side_fork(st));
+        aux = st.side ? st.side : st.s;
+    }
+    RV_CUDA(cudaMemsetAsync(B.small, 0, 512 * 4, aux));
     {
         i64 blocks = (n + 256 * 64 - 1) / (256 * 64);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        RV_LAUNCH(sa_bytehist_kernel, (unsigned)blocks, 256, 0, st.s, dT, n, B.small);
+        RV_LAUNCH(sa_bytehist_kernel, (unsigned)blocks, 256, 0, aux, dT, n, B.small);
         st.launches++;
     }
-    RV_CUDA(cudaMemcpyAsync(hist, B.small, 256 * 4, cudaMemcpyDeviceToHost, st.s));
-    const bool speculative = st.alpha.valid && !fresh_alphabet;
+    RV_CUDA(cudaMemcpyAsync(hist, B.small, 256 * 4, cudaMemcpyDeviceToHost, aux));
     CodeTable tab;
     if (!speculative) {
         RV_CUDA(cudaStreamSynchronize(st.s));
@@ -1136,6 +1146,10 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         }
         if (al.sigma_eff < 2) al.sigma_eff = 2;
         al.valid = true;
+        if (use_side) {
+            RV_TRY(side_fork(st));
+            aux = st.side ? st.side : st.s;
+        }
     }
     memcpy(tab.code, st.alpha.code, sizeof tab.code);
     const int sigma = st.alpha.sigma, sigma_eff = st.alpha.sigma_eff;
@@ -1186,9 +1200,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
     u32 *keys32 = nullptr;
     u64 *keys64 = nullptr;
     if (use32) {
-        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys32, &sa, &sa_free, &packed, pt));
+        RV_TRY(sort_and_compare<u32>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys32, &sa, &sa_free, &packed, pt, aux));
     } else {
-        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys64, &sa, &sa_free, &packed, pt));
+        RV_TRY(sort_and_compare<u64>(st, B, dT, n, tab, sigma, base, k, key_bits, dSA, dISA, dLCP, &keys64, &sa, &sa_free, &packed, pt, aux));
     }
     // ---- the one synchronisation point of a build: is stage 4 needed, and (speculative start) was the alphabet right ----
     RV_CUDA(cudaMemcpyAsync(hist + 256, B.small + 257, 4, cudaMemcpyDeviceToHost, st.s));

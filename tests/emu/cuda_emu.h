@@ -335,6 +335,7 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) { e->t = emu_now(); return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return 0; }
 #define cudaFuncSetAttribute(...) (0)
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 0
