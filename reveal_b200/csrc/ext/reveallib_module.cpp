@@ -93,15 +93,21 @@ struct HostText {
     ~HostText() { drop(); }
     void drop() {
         if (p) {
-            if (pinned) g_api.rv_host_free(p); else free(p);
+            if (pinned) { g_api.rv_host_free(p); last_cap() = cap; }
+            else free(p);
         }
         p = nullptr;
         n = cap = 0;
     }
+    // capacity of the pinned block released last: the library keeps released blocks for the next text, and a text of about the
+    // same size as the previous one (one index per alignment job) then starts in a block that already holds all of it -- no
+    // doubling copies while its sequences are appended
+    static size_t &last_cap() { static size_t c = 0; return c; }
     bool reserve(size_t need) {
         if (need <= cap) return true;
         size_t c = cap ? cap * 2 : (size_t)1 << 12;
         while (c < need) c *= 2;
+        if (!p && need >= ((size_t)1 << 16) && last_cap() > c && last_cap() <= 4 * c) c = last_cap();
         char *q = nullptr;
         bool pin = false;
         void *vp = nullptr;
@@ -144,6 +150,7 @@ struct Index {
     HostText *T;                 // host copy of the text (root only)
     std::vector<int64_t> *nsep;
     int nsamples, rc, depth, cache, built, tdirty, extracted;
+    int consumed;                // root: its own SA / LCP were given up at its first split inside align() (reveal.c:1279-1284)
     int64_t n, nT;
     std::string *safile, *lcpfile;
     // recursion state
@@ -191,7 +198,7 @@ static PyObject *index_new(PyTypeObject *type, PyObject *, PyObject *) {
     self->nsep = new std::vector<int64_t>();
     self->safile = new std::string();
     self->lcpfile = new std::string();
-    self->nsamples = self->rc = self->depth = self->cache = self->built = self->tdirty = self->extracted = 0;
+    self->nsamples = self->rc = self->depth = self->cache = self->built = self->tdirty = self->extracted = self->consumed = 0;
     self->n = self->nT = 0;
     self->sub = nullptr;
     self->mainidx = nullptr;
@@ -342,6 +349,7 @@ static PyObject *index_construct(Index *self, PyObject *args, PyObject *kwds) {
     self->rc = rc;
     self->nT = self->n;
     self->built = 1;
+    self->consumed = 0;
     self->tdirty = rc;  // the reference reverse-complements its T in place (interface.c:168-172)
     self->depth = 0;
     if (self->cache == 1) {  // interface.c:182-189, 273-285
@@ -369,6 +377,16 @@ static int need_built(Index *self, PyObject *exc, const char *msg) {
     if (r->built) return 0;
     PyErr_SetString(exc, msg);
     return -1;
+}
+// for what reads the root's own SA / LCP: gone once align() has split the root (reveal.c:1279-1284; the reference would follow a
+// NULL pointer there)
+static int need_arrays(Index *self) {
+    if (need_built(self, RevealError, "Index not yet constructed.") != 0) return -1;
+    if (!self->mainidx && self->consumed) {
+        PyErr_SetString(RevealError, "Index not yet constructed (its suffix array was given up by align()).");
+        return -1;
+    }
+    return 0;
 }
 
 // ---- sweeps ------------------------------------------------------------------------------------------------------------------
@@ -398,7 +416,7 @@ static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vecto
 static PyObject *index_getmums(Index *self, PyObject *args) {
     int minl = 0;
     if (!PyArg_ParseTuple(args, "i", &minl)) return nullptr;
-    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) {
+    if (self->mainidx || need_arrays(self) != 0) {
         if (self->mainidx) PyErr_SetString(RevealError, "getmums() on a child index");
         return nullptr;
     }
@@ -443,7 +461,7 @@ static PyObject *multi_common(Index *self, PyObject *args, PyObject *kwds, bool 
     static const char *kwlist[] = {"minlength", "minn", nullptr};
     int minl = 0, minn = 2;
     if (!PyArg_ParseTupleAndKeywords(args, kwds, "|ii", (char **)kwlist, &minl, &minn)) return nullptr;
-    if (need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
+    if (need_arrays(self) != 0) return nullptr;
     int64_t nr = 0, nm = 0;
     int status;
     std::vector<int64_t> hdr, mem;
@@ -662,7 +680,9 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
                                    "shard_rank", "shard_world", "shard_grain", "mumpicker_batch", "mums_as_rows", nullptr};
     PyObject *mumpicker, *graphalign, *mumpicker_batch = nullptr;
     int threads = 0, wpen = 0, wscore = 0, minl = 0, minn = 0, shard_rank = 0, shard_world = 1, shard_grain = 2, mums_as_rows = 0;
-    if (self->mainidx || !self->built) {
+    // (the reference frees the root's SA and LCP at its first split, reveal.c:1279-1284: a second align() -- which would run on an
+    // inverse array the first one rewrote -- stops here as well)
+    if (self->mainidx || !self->built || self->consumed) {
         PyErr_SetString(RevealError, "Index not yet constructed, alignment stopped.");  // interface.c:295-298
         return nullptr;
     }
@@ -923,6 +943,8 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             as.steps += (long long)batch.size();
             as.batches++;
             self->tdirty = 1;  // matched bases were lower-cased on the device (reveal.c:1230-1234)
+            for (PendingStep *p : batch)
+                if (p->idx == self) self->consumed = 1;  // the root was split: its SA / LCP are gone (reveal.c:1279-1284)
             if (fail_native(status) != 0) {
                 ok = false;
             } else {
@@ -993,10 +1015,7 @@ static PyObject *index_splitindex(Index *idx, PyObject *args) {
     PyObject *leading, *trailing, *matching, *rest, *merged, *newleft, *newright, *skipleft, *skipright;
     if (!PyArg_ParseTuple(args, "OOOOOOOOO", &leading, &trailing, &matching, &rest, &merged, &newleft, &newright, &skipleft, &skipright)) return nullptr;
     Index *root = root_of(idx);
-    if (!root->built) {
-        PyErr_SetString(RevealError, "Index not yet constructed.");
-        return nullptr;
-    }
+    if (need_arrays(idx) != 0) return nullptr;
     if (!idx->sub) {
         if (idx->mainidx) {
             PyErr_SetString(RevealError, "splitindex: the arrays of this sub-index were already released");
@@ -1046,7 +1065,7 @@ static PyObject *index_splitindex(Index *idx, PyObject *args) {
 static PyObject *index_extract(Index *self, PyObject *args) {
     PyObject *intervals;
     if (!PyArg_ParseTuple(args, "O", &intervals)) return nullptr;
-    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) {
+    if (self->mainidx || need_arrays(self) != 0) {
         if (self->mainidx) PyErr_SetString(RevealError, "extract() on a child index is not supported");
         return nullptr;
     }
@@ -1099,7 +1118,7 @@ static PyObject *index_puttext(Index *self, PyObject *args) {
 
 // ---- copy (interface.c:432-470) -----------------------------------------------------------------------------------------------
 static PyObject *index_copy(Index *self, PyObject *) {
-    if (self->mainidx || need_built(self, RevealError, "Index not yet constructed.") != 0) return nullptr;
+    if (self->mainidx || need_arrays(self) != 0) return nullptr;
     Index *c = (Index *)index_new(&IndexType, nullptr, nullptr);
     if (!c) return nullptr;
     if (self->tdirty) {
@@ -1137,6 +1156,10 @@ static PyObject *ints_to_list(const std::vector<int32_t> &v, bool as_unsigned) {
 static PyObject *get_array(Index *self, int which) {  // 0 SA, 1 SAi, 2 LCP
     if (need_built(self, PyExc_TypeError, "Index not yet constructed.") != 0) return nullptr;
     Index *r = root_of(self);
+    if (!self->mainidx && self->consumed && which != 1) {  // interface.c:548-551 / :590-593 after reveal.c:1279-1284
+        PyErr_SetString(PyExc_TypeError, "Index not yet constructed.");
+        return nullptr;
+    }
     std::vector<int32_t> v;
     int status;
     if ((self->mainidx || self->extracted) && which != 1) {

@@ -24,21 +24,57 @@ static const int SW_THREADS = 256;
 static const int SW_CHUNKS = 4;
 static const int SW_TILE = SW_THREADS * SW_CHUNKS;
 
-// count pass: per-tile number of hits + one hit bit per slot (a ballot word per 32 slots), so that the write
-// pass only touches the (sparse) hits
+// count pass: per-tile number of hits + one hit bit per slot (a word per 32 slots), so that the write pass only touches the
+// (sparse) hits.  A thread takes 4 CONSECUTIVE slots: their LCP and SA entries arrive as two 128-bit loads issued before anything
+// is tested (32 bytes in flight per thread keep HBM busy; one 4-byte load per thread and test did not), then the text gathers of
+// the slots that pass the LCP / sample tests go out together.
 __global__ void __launch_bounds__(SW_THREADS) pair_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u32 *__restrict__ hitbits) {
     __shared__ u64 scratch[33];
-    u64 mine = 0;
-    for (int c = 0; c < SW_CHUNKS; c++) {
-        i64 i = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
-        i64 l, a, b;
-        bool hit = pair_test(p, i, l, a, b);
-        unsigned m = __ballot_sync(FULL, hit);
-        if ((threadIdx.x & 31u) == 0) hitbits[i >> 5] = m;
-        mine += hit ? 1u : 0u;
+    const i64 i0 = (i64)blockIdx.x * SW_TILE + (i64)threadIdx.x * SW_CHUNKS;  // SW_CHUNKS == 4
+    u32 h = 0;  // bit j: slot i0 + j is a hit
+    const bool vec = ((((size_t)p.SA) | ((size_t)p.LCP)) & 15u) == 0;
+    if (vec && i0 + 4 <= p.n) {
+        const int4 lv = *(const int4 *)(p.LCP + i0);
+        const int4 sv = *(const int4 *)(p.SA + i0);
+        const int lprev = i0 > 0 ? p.LCP[i0 - 1] : 0;
+        const int sprev = i0 > 0 ? p.SA[i0 - 1] : 0;
+        const int lnext = i0 + 4 < p.n ? p.LCP[i0 + 4] : (int)0x80000000;  // no slot after the last one (pair_candidate)
+        const int l[6] = {lprev, lv.x, lv.y, lv.z, lv.w, lnext};
+        const int s[5] = {sprev, sv.x, sv.y, sv.z, sv.w};
+        bool cand[4];
+        i64 a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int li = l[j + 1];
+            cand[j] = i0 + j >= 1 && li >= p.minl && li > 0 && l[j] < li && l[j + 2] < li && (((i64)s[j + 1] > p.nsep0) != ((i64)s[j] > p.nsep0));
+            a[j] = s[j + 1] < s[j] ? s[j + 1] : s[j];
+            b[j] = s[j + 1] < s[j] ? s[j] : s[j + 1];
+        }
+        unsigned char ca[4], cb[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool g = cand[j] && a[j] > 0 && b[j] > 0;
+            ca[j] = g ? p.T[a[j] - 1] : (unsigned char)0;
+            cb[j] = g ? p.T[b[j] - 1] : (unsigned char)1;  // (no gather: left-maximal, as in left_maximal())
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cand[j] && (ca[j] != cb[j] || ca[j] == 'N' || ca[j] == '$' || is_lower(ca[j]))) h |= 1u << j;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            i64 l, a, b;
+            if (pair_test(p, i0 + j, l, a, b)) h |= 1u << j;
+        }
     }
+    // hit word of 32 slots = the nibbles of 8 neighbouring lanes
+    u32 word = h << (4u * (threadIdx.x & 7u));
+    word |= __shfl_xor_sync(FULL, word, 1);
+    word |= __shfl_xor_sync(FULL, word, 2);
+    word |= __shfl_xor_sync(FULL, word, 4);
+    if ((threadIdx.x & 7u) == 0) hitbits[i0 >> 5] = word;  // (the bitmap is padded to whole tiles)
     u64 total;
-    block_incl_sum<SW_THREADS, u64>(mine, scratch, &total);
+    block_incl_sum<SW_THREADS, u64>((u64)__popc(h), scratch, &total);
     if (threadIdx.x == 0) tile_rec[blockIdx.x] = total;
 }
 
@@ -183,20 +219,38 @@ mems_write_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb, 
     }
 }
 
-// single block: in-place exclusive scan of up to two u64 arrays; totals -> out[0], out[1]
+// single block: in-place exclusive scan of up to two u64 arrays; totals -> out[0], out[1].  A thread takes TS_K consecutive tiles
+// (all its loads in flight at once, a serial sum in registers), so a text of 8 million slots is one block-wide scan instead of eight.
+static const int TS_K = 8;
 __global__ void __launch_bounds__(1024) sweep_tilescan_kernel(u64 *__restrict__ a, u64 *__restrict__ b, i64 tiles, u64 *__restrict__ out) {
     __shared__ u64 s1[33], s2[33];
     u64 ca = 0, cb = 0;
-    for (i64 b0 = 0; b0 < tiles; b0 += 1024) {
-        i64 t = b0 + threadIdx.x;
-        u64 va = t < tiles ? a[t] : 0ull;
-        u64 vb = (b && t < tiles) ? b[t] : 0ull;
-        u64 ta, tb;
-        u64 ia = block_incl_sum<1024, u64>(va, s1, &ta);
-        u64 ib = block_incl_sum<1024, u64>(vb, s2, &tb);
-        if (t < tiles) {
-            a[t] = ca + ia - va;
-            if (b) b[t] = cb + ib - vb;
+    for (i64 b0 = 0; b0 < tiles; b0 += 1024 * TS_K) {
+        const i64 t0 = b0 + (i64)threadIdx.x * TS_K;
+        u64 va[TS_K], vb[TS_K];
+#pragma unroll
+        for (int j = 0; j < TS_K; j++) {
+            va[j] = t0 + j < tiles ? a[t0 + j] : 0ull;
+            vb[j] = (b && t0 + j < tiles) ? b[t0 + j] : 0ull;
+        }
+        u64 sa = 0, sb = 0;
+#pragma unroll
+        for (int j = 0; j < TS_K; j++) {
+            sa += va[j];
+            sb += vb[j];
+        }
+        u64 ta, tb = 0, ib = 0;
+        const u64 ia = block_incl_sum<1024, u64>(sa, s1, &ta);
+        if (b) ib = block_incl_sum<1024, u64>(sb, s2, &tb);  // (b is the same for every thread)
+        u64 ra = ca + ia - sa, rb = cb + ib - sb;
+#pragma unroll
+        for (int j = 0; j < TS_K; j++) {
+            if (t0 + j < tiles) {
+                a[t0 + j] = ra;
+                if (b) b[t0 + j] = rb;
+            }
+            ra += va[j];
+            rb += vb[j];
         }
         ca += ta;
         cb += tb;

@@ -15,13 +15,18 @@ __device__ __forceinline__ bool left_maximal(const unsigned char *T, i64 a, i64 
 }
 
 // ---- pair sweep ---------------------------------------------------------------
-__device__ __forceinline__ bool pair_test(const SweepArgs &p, i64 i, i64 &l, i64 &a, i64 &b) {
+// the LCP half of the test: slot i holds a value >= minl that is larger than both neighbours (unique, reveal.c:86-95)
+__device__ __forceinline__ bool pair_candidate(const SweepArgs &p, i64 i, int &li) {
     if (i < 1 || i >= p.n) return false;
-    int li = p.LCP[i];
+    li = p.LCP[i];
     if (li < p.minl) return false;
     if (p.LCP[i - 1] >= li) return false;                        // not unique (reveal.c:86-95)
     if (i + 1 < p.n && p.LCP[i + 1] >= li) return false;
     if (0 >= li) return false;                                   // la := 0 at the last slot
+    return true;
+}
+// the SA / text half: the two suffixes lie in different samples and the match cannot be extended to the left
+__device__ __forceinline__ bool pair_confirm(const SweepArgs &p, i64 i, int li, i64 &l, i64 &a, i64 &b) {
     i64 s1 = p.SA[i], s0 = p.SA[i - 1];
     if ((s1 > p.nsep0) == (s0 > p.nsep0)) return false;          // both in the same sample
     a = s1 < s0 ? s1 : s0;
@@ -30,6 +35,10 @@ __device__ __forceinline__ bool pair_test(const SweepArgs &p, i64 i, i64 &l, i64
     l = li;
     if (p.rc == 1) b = p.nsep0 + ((p.flavour ? p.n : p.nT) - b - l);  // reveal.c:98-100 / :162-164
     return true;
+}
+__device__ __forceinline__ bool pair_test(const SweepArgs &p, i64 i, i64 &l, i64 &a, i64 &b) {
+    int li;
+    return pair_candidate(p, i, li) && pair_confirm(p, i, li, l, a, b);
 }
 
 // ---- multi sweep --------------------------------------------------------------

@@ -326,3 +326,44 @@ def test_align_mums_as_rows_emulated(emu_reveallib):
     idx.align(picker, ga, threads=1, minl=8, minn=2, mums_as_rows=True)
     assert "mumrows" in seen
     assert compare(ref, (log, idx.T)) > 3
+
+
+@needs_ref
+def test_root_arrays_are_gone_after_align(emu_reveallib):
+    """The reference frees the root's SA and LCP at its first split (reveal.c:1279-1284): a second align() stops with
+    'Index not yet constructed' (interface.c:295-298) and the SA / LCP getters raise TypeError (interface.c:548-551), while
+    SAi, T and n stay readable.  Same here -- a second align() would otherwise run on the inverse array the first one rewrote."""
+    rng = np.random.default_rng(11)
+    samples = random_related(rng, 2, 1200, 4, snp=0.03)
+
+    def build(mod):
+        idx = mod.index()
+        for k, seqs in enumerate(samples):
+            idx.addsample("s%d" % k)
+            for s in seqs:
+                idx.addsequence(bytes(s).decode("ascii"))
+        idx.construct()
+        return idx
+
+    for mod, err in ((emu_reveallib, emu_reveallib.error), (R.module(32), R.module(32).error)):
+        idx = build(mod)
+        assert len(idx.SA) == idx.n
+        mp, ga = make_callbacks([], minlen=8)
+        idx.align(mp, ga, threads=0, minl=8, minn=2)
+        with pytest.raises(err, match="not yet constructed"):
+            idx.align(mp, ga, threads=0, minl=8, minn=2)
+        with pytest.raises(TypeError, match="not yet constructed"):
+            idx.SA
+        with pytest.raises(TypeError, match="not yet constructed"):
+            idx.LCP
+        assert len(idx.SAi) == idx.n and len(idx.T) >= idx.n
+    with pytest.raises(emu_reveallib.error):   # (the reference follows a NULL pointer here)
+        idx2 = build(emu_reveallib)
+        mp, ga = make_callbacks([], minlen=8)
+        idx2.align(mp, ga, minl=8, minn=2)
+        idx2.getmums(8)
+    # an index whose root was never split keeps its arrays (no MUM of that length)
+    idx3 = build(emu_reveallib)
+    mp, ga = make_callbacks([], minlen=5000)
+    idx3.align(mp, ga, minl=5000, minn=2)
+    assert len(idx3.SA) == idx3.n
