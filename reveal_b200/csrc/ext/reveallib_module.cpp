@@ -107,7 +107,8 @@ struct HostText {
         if (need <= cap) return true;
         size_t c = cap ? cap * 2 : (size_t)1 << 12;
         while (c < need) c *= 2;
-        if (!p && need >= ((size_t)1 << 16) && last_cap() > c && last_cap() <= 4 * c) c = last_cap();
+        static const bool hint = getenv("RV_TEXT_NO_HINT") == nullptr;
+        if (hint && !p && need >= ((size_t)1 << 16) && last_cap() > c && last_cap() <= 4 * c) c = last_cap();
         char *q = nullptr;
         bool pin = false;
         void *vp = nullptr;

@@ -74,17 +74,72 @@ __device__ __forceinline__ bool multi_ok(const SweepArgs &p, i64 lb, i64 ub) {
     return true;
 }
 
+// The members of the interval [lb, ub] while lb walks to the left: what ismultimum (reveal.c:227-259) asks about them, kept up to
+// date one member at a time -- every member's suffix, left character and sample are fetched ONCE per closing slot, not once
+// per nested interval and neighbour pair (five similar genomes: 15 gathers instead of 48).
+//   left-maximal  <=>  some neighbouring pair differs in its left character, or has a special one ('N', '$', lower case), or
+//                      sits at the start of the text  <=>  a member at position 0, or not all left characters equal, or the
+//                      common left character is special
+//   one suffix per sample: two samples -- the two ends lie on different sides of nsep0; up to 64 -- a bit per sample
+struct MultiMembers {
+    bool anyzero, allsame, havec, dup, side_first, side_last;
+    unsigned char c0;
+    u64 seen;
+    int count;
+    __device__ __forceinline__ void init() {
+        anyzero = havec = dup = side_first = side_last = false;
+        allsame = true;
+        c0 = 0;
+        seen = 0;
+        count = 0;
+    }
+    __device__ __forceinline__ void add(const SweepArgs &p, i64 pos) {
+        if (pos == 0) {
+            anyzero = true;
+        } else {
+            const unsigned char c = p.T[pos - 1];
+            if (!havec) {
+                c0 = c;
+                havec = true;
+            } else if (c != c0) {
+                allsame = false;
+            }
+        }
+        if (p.main_nsamples == 2 || !p.SO) {   // (no SO array: one or two samples; one sample never reports anything)
+            const bool side = pos > p.nsep0;
+            if (count == 0) side_first = side;
+            side_last = side;
+        } else {
+            const u64 bit = 1ull << p.SO[pos];
+            if (seen & bit) dup = true;
+            seen |= bit;
+        }
+        count++;
+    }
+    __device__ __forceinline__ bool ok(const SweepArgs &p) const {
+        const bool maximal = anyzero || !allsame || c0 == 'N' || c0 == '$' || is_lower(c0);
+        if (!maximal) return false;
+        return p.main_nsamples == 2 ? side_first != side_last : !dup;
+    }
+};
+
 // Visits every reportable interval that closes at slot ub, inner first.
 template <class F> __device__ __forceinline__ void multi_visit(const SweepArgs &p, i64 ub, F emit) {
     if (ub < 1 || ub >= p.n) return;
     const i64 next = ub + 1 < p.n ? (i64)p.LCP[ub + 1] : -1;  // -1: the final flush closes everything (reveal.c:538)
     i64 m = p.LCP[ub];
+    if (m <= next || m <= 0 || m < p.minl) return;            // nothing closes here, or nothing long enough (m only shrinks below)
+    const bool tracked = p.main_nsamples <= 64;
+    MultiMembers mem;
+    mem.init();
+    if (tracked) mem.add(p, p.SA[ub]);
     i64 lb = ub - 1;
     for (;;) {
-        if (m <= next || m <= 0) break;
+        if (m <= next || m <= 0 || m < p.minl) break;
+        if (tracked) mem.add(p, p.SA[lb]);
         i64 size = ub - lb + 1;
         if ((i64)p.LCP[lb] < m) {  // lb is the left boundary of an lcp-interval of value m
-            if (m >= p.minl && size >= p.minn && size <= p.main_nsamples && multi_ok(p, lb, ub)) emit(m, lb, size);
+            if (size >= p.minn && size <= p.main_nsamples && (tracked ? mem.ok(p) : multi_ok(p, lb, ub))) emit(m, lb, size);
         }
         if (lb == 0 || size >= p.main_nsamples) break;
         i64 v = p.LCP[lb];
