@@ -105,17 +105,50 @@ __global__ void __launch_bounds__(SW_THREADS) pair_write_kernel(SweepArgs p, con
 }
 
 // ---- multi sweep --------------------------------------------------------------
+// Two phases per tile of SW_TILE slots.  (1) every thread looks at 4 consecutive slots by one 128-bit LCP load and keeps the ones
+// where an interval of at least minl closes (LCP[ub] > LCP[ub+1]) -- a third of the slots of similar genomes, fewer elsewhere;
+// their tile offsets are compacted into a shared list.  (2) the threads take the listed slots one after the other, so the walks
+// with their gathers run with every lane busy instead of the 10 of 32 a slot-per-thread mapping leaves active.
 __global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem,
                                                                  u32 *__restrict__ hitbits) {
     __shared__ u64 s1[33], s2[33];
-    u64 nr = 0, nm = 0;
-    for (int c = 0; c < SW_CHUNKS; c++) {
-        i64 ub = (i64)blockIdx.x * SW_TILE + c * SW_THREADS + threadIdx.x;
-        u64 r0 = nr;
-        multi_visit(p, ub, [&](i64, i64, i64 size) { nr++; nm += (u64)size; });
-        unsigned m = __ballot_sync(FULL, nr != r0);
-        if ((threadIdx.x & 31u) == 0) hitbits[ub >> 5] = m;
+    __shared__ u32 s3[33];
+    __shared__ unsigned short s_list[SW_TILE];
+    __shared__ u32 s_hit[SW_TILE / 32];
+    const i64 tile0 = (i64)blockIdx.x * SW_TILE;
+    const i64 i0 = tile0 + (i64)threadIdx.x * SW_CHUNKS;  // SW_CHUNKS == 4
+    if (threadIdx.x < SW_TILE / 32) s_hit[threadIdx.x] = 0;
+    u32 closing = 0;  // bit j: an interval may close at slot i0 + j
+    if ((((size_t)p.LCP) & 15u) == 0 && i0 + 4 < p.n) {
+        const int4 lv = *(const int4 *)(p.LCP + i0);
+        const int l[5] = {lv.x, lv.y, lv.z, lv.w, p.LCP[i0 + 4]};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i0 + j >= 1 && l[j] > l[j + 1] && l[j] > 0 && l[j] >= p.minl) closing |= 1u << j;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const i64 ub = i0 + j;
+            if (ub < 1 || ub >= p.n) continue;
+            const i64 next = ub + 1 < p.n ? (i64)p.LCP[ub + 1] : -1;
+            const i64 m = p.LCP[ub];
+            if (m > next && m > 0 && m >= p.minl) closing |= 1u << j;
+        }
     }
+    u32 total;
+    const u32 cnt = (u32)__popc(closing);
+    u32 at = block_incl_sum<SW_THREADS, u32>(cnt, s3, &total) - cnt;
+    for (u32 bits = closing; bits; bits &= bits - 1u) s_list[at++] = (unsigned short)(threadIdx.x * SW_CHUNKS + (__ffs((int)bits) - 1));
+    __syncthreads();
+    u64 nr = 0, nm = 0;
+    for (u32 k = threadIdx.x; k < total; k += SW_THREADS) {
+        const u32 off = s_list[k];
+        const u64 r0 = nr;
+        multi_visit(p, tile0 + off, [&](i64, i64, i64 size) { nr++; nm += (u64)size; });
+        if (nr != r0) atomicOr(&s_hit[off >> 5], 1u << (off & 31u));
+    }
+    __syncthreads();
+    if (threadIdx.x < SW_TILE / 32) hitbits[(tile0 >> 5) + threadIdx.x] = s_hit[threadIdx.x];  // (the bitmap is padded to whole tiles)
     u64 tr, tm;
     block_incl_sum<SW_THREADS, u64>(nr, s1, &tr);
     block_incl_sum<SW_THREADS, u64>(nm, s2, &tm);
