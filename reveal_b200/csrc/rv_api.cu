@@ -603,6 +603,8 @@ struct MainView {
     unsigned short *SO;
     i64 n, nsep0;
     int nsamples, rc;
+    const i64 *nsep_host;  // the separators (nsamples - 1 of them), host memory of the handle
+    int nsep_count;
     void **pool_slot;
 };
 int main_view(rv_index *h, MainView *out) {
@@ -617,6 +619,8 @@ int main_view(rv_index *h, MainView *out) {
     out->nsep0 = h->nsamples > 1 ? h->nsep[0] : -1;
     out->nsamples = h->nsamples;
     out->rc = h->rc;
+    out->nsep_host = h->nsep.data();
+    out->nsep_count = (int)h->nsep.size();
     out->pool_slot = &h->pool;
     return RV_OK;
 }
@@ -650,6 +654,10 @@ static SweepArgs root_args(const rv_index *h) {
     a.minl = 0;
     a.minn = 2;
     a.main_nsamples = h->nsamples;
+    if (h->nsamples > 2 && (int)h->nsep.size() <= SW_NSEP_INLINE) {
+        a.nsep_n = (int)h->nsep.size();
+        for (int k = 0; k < a.nsep_n; k++) a.nsep_v[k] = h->nsep[(size_t)k];
+    }
     return a;
 }
 

@@ -721,6 +721,8 @@ struct MainView {
     unsigned short *SO;
     i64 n, nsep0;
     int nsamples, rc;
+    const i64 *nsep_host;  // the separators (nsamples - 1 of them), host memory of the handle
+    int nsep_count;
     void **pool_slot;  // where the handle keeps its DevPool*
 };
 int main_view(rv_index *h, MainView *out);
@@ -797,6 +799,10 @@ static SweepArgs sub_args(const rv_sub *s, const MainView &v) {
     a.minl = 0;
     a.minn = 2;
     a.main_nsamples = v.nsamples;
+    if (v.nsamples > 2 && v.nsep_count <= SW_NSEP_INLINE) {
+        a.nsep_n = v.nsep_count;
+        for (int k = 0; k < a.nsep_n; k++) a.nsep_v[k] = v.nsep_host[k];
+    }
     return a;
 }
 

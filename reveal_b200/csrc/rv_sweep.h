@@ -17,7 +17,13 @@ struct SweepArgs {
     int minl;
     int minn;
     int main_nsamples;
+    // Sample separators carried in the argument block (constant bank of the launch) when there are at most SW_NSEP_INLINE of
+    // them: the sample of a position is then a handful of compares, sample(pos) = #{k : nsep[k] < pos} = SO[pos], instead of a
+    // gather from the 2-bytes-per-character SO array that misses L2 at genome scale.  0: use SO.
+    int nsep_n = 0;
+    i64 nsep_v[15];
 };
+static const int SW_NSEP_INLINE = 15;
 
 size_t sweep_scratch_bytes(i64 n);
 int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, i64 *d_spec, i64 cap_spec);

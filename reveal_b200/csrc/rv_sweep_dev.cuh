@@ -42,7 +42,14 @@ __device__ __forceinline__ bool pair_test(const SweepArgs &p, i64 i, i64 &l, i64
 }
 
 // ---- multi sweep --------------------------------------------------------------
-__device__ __forceinline__ int sample_of(const SweepArgs &p, i64 pos) { return p.SO ? (int)p.SO[pos] : (pos > p.nsep0 ? 1 : 0); }
+__device__ __forceinline__ int sample_of(const SweepArgs &p, i64 pos) {
+    if (p.nsep_n > 0) {
+        int smp = 0;
+        for (int k = 0; k < p.nsep_n; k++) smp += p.nsep_v[k] < pos ? 1 : 0;
+        return smp;
+    }
+    return p.SO ? (int)p.SO[pos] : (pos > p.nsep0 ? 1 : 0);
+}
 
 // ismultimum (reveal.c:227-259) for the interval [lb,ub] of value l > 0
 __device__ __forceinline__ bool multi_ok(const SweepArgs &p, i64 lb, i64 ub) {
@@ -110,7 +117,13 @@ struct MultiMembers {
             if (count == 0) side_first = side;
             side_last = side;
         } else {
-            const u64 bit = 1ull << p.SO[pos];
+            int smp = 0;
+            if (p.nsep_n > 0) {
+                for (int k = 0; k < p.nsep_n; k++) smp += p.nsep_v[k] < pos ? 1 : 0;   // = SO[pos] (so_fill_kernel)
+            } else {
+                smp = (int)p.SO[pos];
+            }
+            const u64 bit = 1ull << smp;
             if (seen & bit) dup = true;
             seen |= bit;
         }
