@@ -130,6 +130,7 @@ struct rv_index {
 };
 
 extern "C" void rv_pool_destroy(void *pool);
+extern "C" void rv_pool_trim(void);
 
 // The CUDA objects of a handle that owns its stream -- stream, 2 KB of pinned memory, phase events, profile events -- and the
 // alphabet of the last text it built outlive the handle in a small cache: a caller that creates one index object per alignment
@@ -241,6 +242,7 @@ int rv_trim(void) {
         shells.swap(g_shells);
     }
     for (Shell &sh : shells) shell_destroy(sh);
+    rv_pool_trim();
     int cur = 0;
     cudaGetDevice(&cur);
     for (Cached &c : d) {

@@ -632,7 +632,8 @@ struct DevPool {
     // (which synchronises the device and costs ~1 ms) except when a new slab is needed
     std::multimap<size_t, void *> free_;
     std::map<void *, size_t> size_;
-    std::vector<void *> slabs_;
+    std::vector<std::pair<void *, size_t>> slabs_;   // every slab of the pool
+    std::vector<std::pair<void *, size_t>> spare_;   // slabs of a previous recursion, not carved yet (see recycle)
     unsigned char *cur_ = nullptr;
     size_t cur_left_ = 0;
     static size_t round_up(size_t b) {
@@ -649,22 +650,33 @@ struct DevPool {
             return RV_OK;
         }
         if (c > cur_left_) {
-            size_t slab = (size_t)64 << 20;
-            if (slab < 2 * c) slab = 2 * c;
-            void *p = nullptr;
-            cudaError_t e = cudaMalloc(&p, slab);
-            if (e != cudaSuccess && slab > c) {
-                slab = c;
-                e = cudaMalloc(&p, slab);
+            int best = -1;
+            for (int i = 0; i < (int)spare_.size(); i++)
+                if (spare_[i].second >= c && (best < 0 || spare_[i].second < spare_[best].second)) best = i;
+            if (best >= 0) {
+                cur_ = (unsigned char *)spare_[best].first;
+                cur_left_ = spare_[best].second;
+                spare_.erase(spare_.begin() + best);
+            } else {
+                size_t slab = (size_t)64 << 20;
+                if (slab < 2 * c) slab = 2 * c;
+                void *p = nullptr;
+                cudaError_t e = cudaMalloc(&p, slab);
+                if (e != cudaSuccess && slab > c) {
+                    cudaGetLastError();
+                    slab = c;
+                    e = cudaMalloc(&p, slab);
+                }
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    set_error("cudaMalloc(%zu) failed: %s", slab, cudaGetErrorString(e));
+                    return RV_ERR_NOMEM;
+                }
+                // the unused tail of the previous slab is abandoned (at most one block of the largest class seen)
+                slabs_.push_back({p, slab});
+                cur_ = (unsigned char *)p;
+                cur_left_ = slab;
             }
-            if (e != cudaSuccess) {
-                set_error("cudaMalloc(%zu) failed: %s", slab, cudaGetErrorString(e));
-                return RV_ERR_NOMEM;
-            }
-            // the unused tail of the previous slab is abandoned (at most one block of the largest class seen)
-            slabs_.push_back(p);
-            cur_ = (unsigned char *)p;
-            cur_left_ = slab;
         }
         *out = cur_;
         size_[cur_] = c;
@@ -676,9 +688,23 @@ struct DevPool {
         if (!p) return;
         free_.insert({size_[p], p});
     }
+    size_t bytes() const {
+        size_t b = 0;
+        for (auto &sl : slabs_) b += sl.second;
+        return b;
+    }
+    // every block is back (the recursion that used the pool is over, its stream synchronised): the slabs wait for the next one
+    void recycle() {
+        free_.clear();
+        size_.clear();
+        spare_ = slabs_;
+        cur_ = nullptr;
+        cur_left_ = 0;
+    }
     void destroy() {
-        for (void *p : slabs_) cudaFree(p);
+        for (auto &sl : slabs_) cudaFree(sl.first);
         slabs_.clear();
+        spare_.clear();
         free_.clear();
         size_.clear();
         cur_ = nullptr;
@@ -693,6 +719,7 @@ struct RecCtx {
     i64 out_words = 0;
     SmallStepArgs *h_args = nullptr, *d_args = nullptr;  // host-mapped argument blocks of one batch (SM_BATCH steps)
     struct rv_step_batch *open_ticket = nullptr;         // rv_sub_step_batch_begin without its _end yet
+    int device = 0;
     // step statistics: [0] single-launch path, [1] general path
     long long steps[2] = {0, 0};
     long long launches[2] = {0, 0};
@@ -730,21 +757,75 @@ int sub_sweep_pair(rv_index *h, const SweepArgs &a, int64_t *count);
 int sub_sweep_multi(rv_index *h, const SweepArgs &a, int64_t *nrec, int64_t *nmem);
 }  // namespace rv
 
+// The recursion context of an index -- device slabs of the children's arrays, 32 MB of host-mapped result buffer, the argument
+// blocks -- outlives the index in a small cache: one `rem` per index object would otherwise pay a dozen cudaMalloc / cudaFree and
+// two cudaHostAlloc per alignment (tens of milliseconds, and serialised in the driver between the ranks of a box, which all
+// reach the top of their recursion at the same moment).
+#include <mutex>
+static std::mutex g_ctx_mu;
+static std::vector<RecCtx *> g_ctx_cache;
+static const size_t CTX_SLOTS = 2;
+static const size_t CTX_MAX_BYTES = (size_t)16 << 30;
+
 static RecCtx *ctx_of(MainView &v) {
-    if (!*v.pool_slot) *v.pool_slot = new RecCtx();
+    if (!*v.pool_slot) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        RecCtx *c = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_ctx_mu);
+            for (size_t i = 0; i < g_ctx_cache.size(); i++)
+                if (g_ctx_cache[i]->device == dev) {
+                    c = g_ctx_cache[i];
+                    g_ctx_cache.erase(g_ctx_cache.begin() + (long)i);
+                    break;
+                }
+        }
+        if (!c) {
+            c = new RecCtx();
+            c->device = dev;
+        }
+        *v.pool_slot = c;
+    }
     return (RecCtx *)*v.pool_slot;
+}
+static void ctx_destroy(RecCtx *c) {
+    c->pool.destroy();
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_args) cudaFreeHost(c->h_args);
+    delete c;
 }
 static DevPool *pool_of(MainView &v) { return &ctx_of(v)->pool; }
 
 extern "C" {
 
-void rv_pool_destroy(void *pool) {  // called by rv_index_free
+void rv_pool_destroy(void *pool) {  // called by rv_index_free, after the index's stream was synchronised
     if (!pool) return;
     RecCtx *c = (RecCtx *)pool;
-    c->pool.destroy();
-    if (c->h_out) cudaFreeHost(c->h_out);
-    if (c->h_args) cudaFreeHost(c->h_args);
-    delete c;
+    if (!c->open_ticket && c->pool.bytes() <= CTX_MAX_BYTES) {
+        c->pool.recycle();
+        for (int k = 0; k < 2; k++) c->steps[k] = c->launches[k] = 0, c->host_s[k] = 0;
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (g_ctx_cache.size() < CTX_SLOTS) {
+            g_ctx_cache.push_back(c);
+            return;
+        }
+    }
+    ctx_destroy(c);
+}
+void rv_pool_trim(void) {  // rv_trim: give the cached recursion contexts back
+    std::vector<RecCtx *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        drop.swap(g_ctx_cache);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (RecCtx *c : drop) {
+        cudaSetDevice(c->device);
+        ctx_destroy(c);
+    }
+    cudaSetDevice(cur);
 }
 
 int rv_sub_root(rv_index *h, rv_sub **out) {
