@@ -7,7 +7,7 @@ import pytest
 
 import oracle.port as P
 from conftest import golden_names, load_golden
-from util import check_handle_reuse, check_pack_block, check_against_golden, check_against_oracle, random_related
+from util import check_handle_reuse, check_pack_block, check_sweep_prefetch, check_against_golden, check_against_oracle, random_related
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -77,6 +77,10 @@ def test_emu_byte_comparison_path(emu_lib, monkeypatch):
 
 def test_emu_handle_reuse_alphabet_cache(emu_lib):
     check_handle_reuse(emu_lib)
+
+
+def test_emu_sweeps_between_rebuilds(emu_lib):
+    check_sweep_prefetch(emu_lib)
 
 
 def test_emu_pack_into_peer_block(emu_lib):

@@ -9,7 +9,7 @@ import pytest
 import oracle.port as P
 from conftest import golden_names, load_golden
 from reveal_b200 import synth
-from util import check_handle_reuse, check_pack_block, NativeIndex, assert_same, check_against_golden, check_against_oracle, random_related
+from util import check_handle_reuse, check_pack_block, check_sweep_prefetch, NativeIndex, assert_same, check_against_golden, check_against_oracle, random_related
 
 pytestmark = pytest.mark.gpu
 
@@ -183,6 +183,10 @@ def test_cuda_byte_comparison_path(cuda_lib, monkeypatch):
 
 def test_cuda_handle_reuse_alphabet_cache(cuda_lib):
     check_handle_reuse(cuda_lib)
+
+
+def test_cuda_sweeps_between_rebuilds(cuda_lib):
+    check_sweep_prefetch(cuda_lib)
 
 
 def test_cuda_pack_into_peer_block(cuda_lib):

@@ -167,6 +167,51 @@ def check_handle_reuse(L):
     idx.close()
 
 
+def check_sweep_prefetch(L):
+    """Sweeps between rebuilds of one handle (result buffer, scratch and alphabet are reused; a build that enqueued the sweep
+    its handle was asked for last in front of its own synchronisation point was measured and dropped -- it saved nothing -- but
+    what such a short cut could get wrong stays tested): the answer must be the sweep of the NEW text whatever happens in
+    between: another minimum length, a text that needs the doubling rounds, a changed text (rv_put_text), a request repeated."""
+    import ctypes
+
+    import oracle.port as P
+    rng = np.random.default_rng(17)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    rep = al[rng.integers(0, 4, size=40)].tobytes()
+    base = al[rng.integers(0, 4, size=2500)].tobytes()
+    texts = [random_related(rng, 2, 3000, 4, snp=0.02),
+             random_related(rng, 2, 2600, 4, snp=0.03),
+             [[base[:1200] + rep * 30 + base[1200:]], [base[:700] + b"T" + base[701:1900] + rep * 4 + base[1900:]]],   # stage 4
+             random_related(rng, 2, 2000, 4, snp=0.02)]
+    idx = None
+    for k, samples in enumerate(texts):
+        T, nsep, _ = P.assemble(samples)
+        if idx is None:
+            idx = NativeIndex(L, T, nsep, 2)
+        else:
+            idx.rebuild(T, nsep, 2)
+        o = P.Index(T, nsep, 2)
+        if k == 1:
+            assert_same(idx.mums(9, 1), o.getmums(9, rem=True), "another minl right after a build")
+        assert_same(idx.mums(6, 1), o.getmums(6, rem=True), "getmums text %d" % k)
+        assert_same(idx.mums(6, 1), o.getmums(6, rem=True), "getmums text %d, asked again" % k)
+        assert_same(idx.mums(6, 0), o.getmums(6), "other flavour")
+        assert_same(idx.mums(6, 1), o.getmums(6, rem=True), "back to the hinted request")
+    # a change of the text between the build and the request voids the prefetched answer
+    T, nsep, _ = P.assemble(texts[0])
+    idx.rebuild(T, nsep, 2)
+    o = P.Index(T, nsep, 2)
+    want = o.getmums(6, rem=True)
+    pos = int(want[0][1]) - 1 if len(want) and want[0][1] > 0 else 5
+    T2 = T.copy()
+    T2[pos] = ord("a")   # lower case left of a match: left-maximal now whatever stood there
+    _native.check(L, L.rv_put_text(idx.h, pos, T2[pos:pos + 1].ctypes.data, 1))
+    o2 = P.Index(T, nsep, 2)
+    o2.T = T2
+    assert_same(idx.mums(6, 1), o2.getmums(6, rem=True), "after rv_put_text")
+    idx.close()
+
+
 def check_pack_block(L):
     """rv_result_pack_device into a peer block allocated by this process (rv_peer_alloc / rv_peer_read / rv_peer_free):
     header row (count, pack sequence number, 0) and the rows, with room to spare and with a capacity below the count."""
