@@ -397,13 +397,21 @@ def run_ours(args, rank, world, local_rank):
     k_cold, _ = step_api()      # the very first call of the process through the drop-in: CUDA context, module load, first allocations
     torch.cuda.synchronize()
     cold_first_call_s = time.perf_counter() - t_cold
+    # Warm-up steps with every kernel group bracketed by event pairs: they name the dominant kernel (largest share of the step).
+    # The event pairs cost a few microseconds of a step themselves (C2: 0.94 ms with all of them, 0.90 ms without), so the
+    # TIMED steps bracket only that kernel -- its launch durations for `roofline` are measured live inside the timed region, as
+    # the contract asks -- and the table of the other kernels comes from extra, untimed steps afterwards.
+    _native.check(L, L.rv_profile(h, 1))
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    profw = _native.KernelProfile()
+    _native.check(L, L.rv_get_profile(h, ctypes.byref(profw)))
+    top_slot = max(range(len(profw.SLOTS)), key=lambda k: profw.ms[k] if profw.launches[k] else -1.0)
     # ---- timed: device-resident input -----------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    _native.check(L, L.rv_profile(h, 1))
+    _native.check(L, L.rv_profile(h, 1 | (2 << top_slot)))   # mask: only the dominant kernel's slot
     prof0 = _native.KernelProfile()
     _native.check(L, L.rv_get_profile(h, ctypes.byref(prof0)))
     barrier()
@@ -452,6 +460,22 @@ def run_ours(args, rank, world, local_rank):
     _native.check(L, L.rv_get_profile(h, ctypes.byref(prof)))
     times = _native.Times()
     _native.check(L, L.rv_get_times(h, ctypes.byref(times)))
+    # the other kernels: extra steps after the timed region, every group bracketed
+    _native.check(L, L.rv_profile(h, 1))
+    extra_steps = min(args.steps, 3)
+    extra_evs = []
+    for _ in range(extra_steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_resident()
+        e1.record(stream)
+        extra_evs.append((e0, e1))
+    torch.cuda.synchronize()
+    extra_ms = sum(a.elapsed_time(b) for a, b in extra_evs)
+    prof_all = _native.KernelProfile()
+    _native.check(L, L.rv_get_profile(h, ctypes.byref(prof_all)))
     _native.check(L, L.rv_profile(h, 0))
     # ---- timed: end to end from pinned host memory through the C-ABI (secondary: e2e_cabi) -----------------------
     step_e2e()
@@ -494,15 +518,20 @@ def run_ours(args, rank, world, local_rank):
         value = total_bases * args.steps / (dev_ms_max * 1e-3)
         e2e_value = total_bases * args.steps / (e2e_ms_max * 1e-3)
         launches = int(prof.launches_total - prof0.launches_total)
-        kernels = []
-        for k, name in enumerate(prof.SLOTS):
-            if prof.launches[k] and prof.ms[k] > 0:
-                gbs = (prof.bytes[k] / 1e9) / (prof.ms[k] * 1e-3)
-                kernels.append({"kernel": name, "launches": int(prof.launches[k]), "avg_launch_ms": prof.ms[k] / prof.launches[k],
-                                "achieved": gbs, "frac": gbs / peak, "share_of_step": prof.ms[k] / dev_ms,
-                                "algorithmic_bytes_per_launch": prof.bytes[k] / prof.launches[k]})
-        kernels.sort(key=lambda d: -d["share_of_step"])
-        top = kernels[0] if kernels else {}
+        def rows_of(pr, total_ms, where):
+            out = []
+            for k, name in enumerate(pr.SLOTS):
+                if pr.launches[k] and pr.ms[k] > 0:
+                    gbs = (pr.bytes[k] / 1e9) / (pr.ms[k] * 1e-3)
+                    out.append({"kernel": name, "launches": int(pr.launches[k]), "avg_launch_ms": pr.ms[k] / pr.launches[k],
+                                "achieved": gbs, "frac": gbs / peak, "share_of_step": pr.ms[k] / total_ms,
+                                "algorithmic_bytes_per_launch": pr.bytes[k] / pr.launches[k], "measured": where})
+            out.sort(key=lambda d: -d["share_of_step"])
+            return out
+        timed = rows_of(prof, dev_ms, "inside the timed region (the only kernel bracketed there)")
+        top = timed[0] if timed else {}
+        kernels = timed + [r for r in rows_of(prof_all, extra_ms, "%d extra steps after the timed region, every kernel group bracketed" % extra_steps)
+                           if r["kernel"] != top.get("kernel")]
         traffic, traffic_src = measured_traffic(top.get("kernel"), args.workload)
         bpb = 35 if ns == 2 else 39
         line = {"metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

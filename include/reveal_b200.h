@@ -103,6 +103,8 @@ typedef struct rv_kernel_profile {
     int64_t bytes[RV_PROF_SLOTS];
     int64_t launches_total; /* every kernel this handle launched since creation */
 } rv_kernel_profile;
+/* enable: 0 off, 1 every slot, else a mask -- bit k+1 set: slot k is bracketed (the event pairs cost a few microseconds of a
+ * step themselves: a timed region brackets only the kernel it reports) */
 int rv_profile(rv_index *idx, int32_t enable);
 int rv_get_profile(rv_index *idx, rv_kernel_profile *out);
 int64_t rv_index_n(const rv_index *idx);

@@ -462,6 +462,7 @@ int rv_profile(rv_index *h, int32_t enable) {
     if (!h) return RV_ERR_ARG;
     RV_TRY(prof_collect(h->st));
     h->st.prof = enable != 0;
+    h->st.prof_mask = enable > 1 ? (unsigned)enable >> 1 : 0xffffffffu;
     for (int k = 0; k < RV_PROF_SLOTS; k++) {
         h->st.prof_ms[k] = 0;
         h->st.prof_launches[k] = 0;

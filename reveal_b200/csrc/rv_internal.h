@@ -81,6 +81,7 @@ struct Stream {
     // optional per-kernel profile: event pairs recorded around runs of one kernel, resolved lazily
     // (prof_collect) so that profiling adds no synchronisation to the measured step
     bool prof = false;
+    unsigned prof_mask = 0xffffffffu;   // bit k: slot k is bracketed (rv_profile)
     std::vector<ProfRec> pending;
     std::vector<cudaEvent_t> free_events;
     cudaEvent_t cur0 = 0;
@@ -99,14 +100,14 @@ inline int prof_event(Stream &st, cudaEvent_t *e) {
     return RV_OK;
 }
 // (`on`: the stream the bracketed kernels are launched on, st.s by default; begin / end pairs do not nest)
-inline int prof_begin(Stream &st, cudaStream_t on = 0) {
-    if (!st.prof) return RV_OK;
+inline int prof_begin(Stream &st, int slot, cudaStream_t on = 0) {
+    if (!st.prof || !((st.prof_mask >> slot) & 1u)) return RV_OK;
     RV_TRY(prof_event(st, &st.cur0));
     RV_CUDA(cudaEventRecord(st.cur0, on ? on : st.s));
     return RV_OK;
 }
 inline int prof_end(Stream &st, int slot, long long launches, long long bytes, cudaStream_t on = 0) {
-    if (!st.prof) return RV_OK;
+    if (!st.prof || !((st.prof_mask >> slot) & 1u)) return RV_OK;
     ProfRec r;
     r.e0 = st.cur0;
     RV_TRY(prof_event(st, &r.e1));

@@ -399,7 +399,7 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
         attr_done[dev] = true;
     }
     bool in0 = true;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_RADIX_PASS));
     for (int p = 0; p < plan.npass; p++) {
         if (p == 0 && text) {
             RV_LAUNCH((rs_pass_kernel<KeyT, true, true>), (unsigned)tiles, RS_THREADS, smem, st.s, (const KeyT *)nullptr, k1, (const u32 *)nullptr, v1, n,

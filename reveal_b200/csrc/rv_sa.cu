@@ -931,7 +931,7 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     RV_CUDA(cudaMemsetAsync(B.bar2, 0, (size_t)(n / 32768 + 8) * 4, aux));
     const int step_syms = packed ? 32 : 16;
     RV_CUDA(cudaMemsetAsync(B.etab, 0, (size_t)(n / step_syms + 2) * ET_WAYS * 8, aux));
-    RV_TRY(prof_begin(st, aux));
+    RV_TRY(prof_begin(st, RV_PROF_TEXT, aux));
     if (packed) {
         RV_LAUNCH((sa_textprep_kernel<true>), prep_blocks, TP_THREADS, 0, aux, dT, n, tab, B.bar, B.bar1, B.bar2, B.packed);
     } else {
@@ -945,14 +945,14 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     u32 *sa = in0 ? B.v0 : B.v1;
     if (aux != st.s) RV_TRY(side_join(st));
     const u32 *W = packed ? (const u32 *)B.packed : (const u32 *)dT;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_LEAD));
     if (packed) {
         RV_LAUNCH((sa_lead_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
     } else {
         RV_LAUNCH((sa_lead_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
     }
     RV_TRY(prof_end(st, RV_PROF_LEAD, 1, (long long)n * (long long)(sizeof(KeyT) + 4)));
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_PAIRS));
     if (packed) {
         RV_LAUNCH((sa_place_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
                   B.small + 257, B.chunk_start, B.needbits, key_digits2);
@@ -1230,7 +1230,7 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         // text positions (a handful for a stray long match, all of them for a text that is one big repeat)
         const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
         const Barriers bars = {B.bar, B.bar1, B.bar2};
-        RV_TRY(prof_begin(st));
+        RV_TRY(prof_begin(st, RV_PROF_LCP));
         if (packed) {
             RV_LAUNCH((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, bars, dSA, dISA, dLCP);
         } else {
@@ -1262,7 +1262,7 @@ int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *
     const Barriers bars = {bar, bar1, bar2};
     RV_CUDA(cudaMemsetAsync(needbits, 0xff, (size_t)(n / 32 + 2) * 4, st.s));
     const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_LCP));
     RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
     RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
     st.launches += 2;

@@ -310,7 +310,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, 
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
     u64 *tile_rec = (u64 *)scratch;
     u64 *totals = tile_rec + 2 * tiles;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     RV_LAUNCH(pair_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, (u64 *)nullptr, tiles, totals);
@@ -327,7 +327,7 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, 
 int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, i64 cap) {
     if (p.n < 2) return RV_OK;
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     const u64 *tile_rec = (const u64 *)scratch;
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
     RV_LAUNCH(pair_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_out, cap);
@@ -345,7 +345,7 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
     u64 *tile_rec = (u64 *)scratch, *tile_mem = tile_rec + tiles;
     u64 *totals = tile_rec + 2 * tiles;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     RV_LAUNCH(multi_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
     RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
@@ -365,7 +365,7 @@ int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr,
     if (p.n < 2) return RV_OK;
     i64 tiles = (p.n + SW_TILE - 1) / SW_TILE;
     const u64 *tile_rec = (const u64 *)scratch, *tile_mem = tile_rec + tiles;
-    RV_TRY(prof_begin(st));
+    RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
     RV_LAUNCH(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
               d_mem, mem_cap);

@@ -41,7 +41,8 @@ def main():
 
     for _ in range(3):
         step()
-    _native.check(L, L.rv_profile(h, 1))
+    if not os.environ.get("RV_BENCH_NO_PROFILE"):   # (per-kernel event pairs cost a few microseconds of the step themselves)
+        _native.check(L, L.rv_profile(h, 1))
     torch.cuda.synchronize()
     ms = 0.0
     for _ in range(steps):
