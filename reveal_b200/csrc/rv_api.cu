@@ -608,10 +608,12 @@ struct MainView {
     int nsamples, rc;
     const i64 *nsep_host;  // the separators (nsamples - 1 of them), host memory of the handle
     int nsep_count;
+    int device;            // the GPU the handle lives on
     void **pool_slot;
 };
 int main_view(rv_index *h, MainView *out) {
     RV_TRY(need_built(h));
+    RV_CUDA(cudaSetDevice(h->device));   // (a process may drive several GPUs: everything below works on the handle's)
     out->st = &h->st;
     out->T = h->dT;
     out->SA = h->dSA;
@@ -624,6 +626,7 @@ int main_view(rv_index *h, MainView *out) {
     out->rc = h->rc;
     out->nsep_host = h->nsep.data();
     out->nsep_count = (int)h->nsep.size();
+    out->device = h->device;
     out->pool_slot = &h->pool;
     return RV_OK;
 }

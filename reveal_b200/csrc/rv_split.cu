@@ -750,6 +750,7 @@ struct MainView {
     int nsamples, rc;
     const i64 *nsep_host;  // the separators (nsamples - 1 of them), host memory of the handle
     int nsep_count;
+    int device;            // the GPU the handle lives on
     void **pool_slot;  // where the handle keeps its DevPool*
 };
 int main_view(rv_index *h, MainView *out);
@@ -769,8 +770,7 @@ static const size_t CTX_MAX_BYTES = (size_t)16 << 30;
 
 static RecCtx *ctx_of(MainView &v) {
     if (!*v.pool_slot) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+        const int dev = v.device;
         RecCtx *c = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_ctx_mu);
