@@ -220,28 +220,16 @@ split_apply_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, cons
 static const int BB_THREADS = 1024;
 static const int BB_CAP = 4096;  // candidates per matched interval handled by the sorted fast path
 
-// the reference's loop body for slot i (reveal.c:686-722), on the child's arrays
-__device__ __forceinline__ void bubble_body(int *SA, int *LCP, int *SAi, i64 n, i64 i, i64 begin) {
-    if ((SA[i] < begin) && ((i64)SA[i] + LCP[i] > begin)) {  // the match overlaps the start position
-        i64 x = i;
-        int tmpSA = SA[i], tmpLCP = LCP[i];
-        while (((i64)LCP[x] >= begin - tmpSA) && x > 0) {
-            SAi[SA[x - 1]] = (int)x;
-            SA[x] = SA[x - 1];
-            LCP[x] = LCP[x - 1];
-            x--;
-        }
-        SAi[tmpSA] = (int)x;
-        SA[x] = tmpSA;
-        LCP[x + 1] = (int)(begin - tmpSA);
-        if (i < n - 1) {
-            if (tmpLCP < LCP[i + 1]) LCP[i + 1] = tmpLCP;
-        }
-    } else if (i < n - 1) {
-        if ((SA[i] < begin) && ((i64)SA[i] + LCP[i + 1] > begin)) {
-            if (LCP[i + 1] > LCP[i]) LCP[i + 1] = (int)(begin - SA[i]);
-        }
+// The reference's loop body for slot i (reveal.c:686-722): if the match of SA[i] with its upper neighbour runs across `begin`, the
+// entry is moved down to the first slot whose LCP is below the truncated length begin - SA[i] (entries in between shift up by
+// one), LCP[x + 1] becomes that length and LCP[i + 1] is capped by the old LCP[i]; else, if its match with the LOWER neighbour
+// runs across `begin`, LCP[i + 1] is cut to begin - SA[i] when it exceeds LCP[i].
+static inline int bubble_cap() {   // candidates per matched interval of the sorted fast path (test hook: RV_BUBBLE_CAP)
+    if (const char *e = getenv("RV_BUBBLE_CAP")) {
+        int x = atoi(e);
+        if (x >= 32 && x <= BB_CAP) return x;
     }
+    return BB_CAP;
 }
 
 // Replays the loop body for the sorted candidate slots cand[0..cnt), candidates one after the other (their
@@ -313,101 +301,16 @@ __device__ __forceinline__ void bubble_replay_block(int *SA, int *LCP, int *SAi,
     }
 }
 
-// bubble_sort of one child by one thread block (any block size that is a power of two <= 1024)
-__device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n, const i64 *begins, int nbegins, int *s_cand, int *s_cnt) {
+// ascending bitonic sort of s_cand[0..cnt) by the whole block (padded with INT_MAX to a power of two <= BB_CAP)
+__device__ __forceinline__ void bubble_sort_cands(int *s_cand, int cnt) {
     const int NT = (int)blockDim.x;
-    for (int b = 0; b < nbegins; b++) {
-        const i64 begin = begins[b];
-        if (threadIdx.x == 0) *s_cnt = 0;
-        __syncthreads();
-        // candidates: LCP values only decrease during the pass, so a slot whose original values do not
-        // reach across `begin` can never take either branch
-        for (i64 i = threadIdx.x; i < n; i += NT) {
-            i64 s = SA[i];
-            if (s < begin) {
-                bool c = s + LCP[i] > begin || (i < n - 1 && s + LCP[i + 1] > begin);
-                if (c) {
-                    int at = atomicAdd(s_cnt, 1);
-                    if (at < BB_CAP) s_cand[at] = (int)i;
-                }
-            }
-        }
-        __syncthreads();
-        const int cnt = *s_cnt;
-        if (cnt > BB_CAP) {  // rare: too many candidates for shared memory, replay the whole loop
-            if (threadIdx.x == 0)
-                for (i64 i = 0; i < n; i++) bubble_body(SA, LCP, SAi, n, i, begin);
-        } else if (cnt > 0) {
-            // bitonic sort of the candidate slots (ascending), padded with INT_MAX
-            int m = 1;
-            while (m < cnt) m <<= 1;
-            for (int i = cnt + threadIdx.x; i < m; i += NT) s_cand[i] = 0x7fffffff;
-            __syncthreads();
-            for (int k = 2; k <= m; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = threadIdx.x; i < m; i += NT) {
-                        int ixj = i ^ j;
-                        if (ixj > i) {
-                            int a = s_cand[i], c = s_cand[ixj];
-                            bool up = (i & k) == 0;
-                            if ((a > c) == up) {
-                                s_cand[i] = c;
-                                s_cand[ixj] = a;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_cnt + 1);
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int nbegins) {
-    __shared__ int s_cand[BB_CAP];
-    __shared__ int s_cnt[12];  // [0] candidate count, [1..] scratch of the replay
-    bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, s_cnt);
-}
-
-// Large children: the candidate scan runs grid-wide, the sort + replay in one block.
-__global__ void __launch_bounds__(256) bubble_detect_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, i64 n, const i64 *__restrict__ begins,
-                                                           int b, int *__restrict__ cand, int *__restrict__ cand_cnt) {
-    const i64 begin = begins[b];
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        i64 s = SA[i];
-        if (s < begin) {
-            bool c = s + LCP[i] > begin || (i < n - 1 && s + LCP[i + 1] > begin);
-            if (c) {
-                int at = atomicAdd(cand_cnt, 1);
-                if (at < BB_CAP) cand[at] = (int)i;
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(BB_THREADS) bubble_apply_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int b,
-                                                                  const int *__restrict__ cand, int *cand_cnt) {
-    __shared__ int s_cand[BB_CAP];
-    const i64 begin = begins[b];
-    const int cnt = *cand_cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) *cand_cnt = 0;  // ready for the next matched interval
-    if (cnt > BB_CAP) {  // rare: too many candidates, replay the whole loop
-        if (threadIdx.x == 0)
-            for (i64 i = 0; i < n; i++) bubble_body(SA, LCP, SAi, n, i, begin);
-        return;
-    }
-    if (cnt == 0) return;
     int m = 1;
     while (m < cnt) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += BB_THREADS) s_cand[i] = i < cnt ? cand[i] : 0x7fffffff;
+    for (int i = cnt + threadIdx.x; i < m; i += NT) s_cand[i] = 0x7fffffff;
     __syncthreads();
     for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += BB_THREADS) {
+            for (int i = threadIdx.x; i < m; i += NT) {
                 int ixj = i ^ j;
                 if (ixj > i) {
                     int a = s_cand[i], c = s_cand[ixj];
@@ -421,8 +324,103 @@ __global__ void __launch_bounds__(BB_THREADS) bubble_apply_kernel(int *SA, int *
             __syncthreads();
         }
     }
-    __shared__ int s_tmp[8];
-    bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_tmp);
+}
+
+__device__ __forceinline__ bool bubble_candidate(const int *SA, const int *LCP, i64 n, i64 i, i64 begin) {
+    const i64 s = SA[i];
+    return s < begin && (s + LCP[i] > begin || (i < n - 1 && s + LCP[i + 1] > begin));
+}
+
+// More candidates than the sorted fast path holds (a repeat of thousands of characters runs across `begin`): the child is taken
+// in windows of `cap` consecutive slots, in slot order -- a window has at most `cap` candidates, they are collected, sorted and
+// replayed like above.  Equivalent to the reference's loop over all slots: the body of slot i only moves entries among the slots
+// <= i and lowers LCP[i + 1], so the slots of a later window still hold their own entries when their window is looked at, and
+// LCP values only ever shrink, so no slot becomes a candidate after its window was collected (the replay re-checks each one).
+// (Round 1 handed this case to ONE thread replaying all n slots.)
+__device__ __forceinline__ void bubble_windows(int *SA, int *LCP, int *SAi, i64 n, i64 begin, int *s_cand, int *s_cnt /*[12]*/, int cap) {
+    const int NT = (int)blockDim.x;
+    for (i64 w0 = 0; w0 < n; w0 += cap) {
+        if (threadIdx.x == 0) *s_cnt = 0;
+        __syncthreads();
+        const i64 w1 = w0 + cap < n ? w0 + cap : n;
+        for (i64 i = w0 + threadIdx.x; i < w1; i += NT)
+            if (bubble_candidate(SA, LCP, n, i, begin)) s_cand[atomicAdd(s_cnt, 1)] = (int)i;
+        __syncthreads();
+        const int cnt = *s_cnt;
+        __syncthreads();
+        if (cnt > 0) {
+            bubble_sort_cands(s_cand, cnt);
+            bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_cnt + 1);
+        }
+        __syncthreads();
+    }
+}
+
+// bubble_sort of one child by one thread block (any block size that is a power of two <= 1024); cap <= BB_CAP: candidates the
+// sorted fast path takes at once (BB_CAP but for tests)
+__device__ __forceinline__ void bubble_block(int *SA, int *LCP, int *SAi, i64 n, const i64 *begins, int nbegins, int *s_cand, int *s_cnt, int cap) {
+    const int NT = (int)blockDim.x;
+    for (int b = 0; b < nbegins; b++) {
+        const i64 begin = begins[b];
+        if (threadIdx.x == 0) *s_cnt = 0;
+        __syncthreads();
+        // candidates: LCP values only decrease during the pass, so a slot whose original values do not
+        // reach across `begin` can never take either branch
+        for (i64 i = threadIdx.x; i < n; i += NT) {
+            if (bubble_candidate(SA, LCP, n, i, begin)) {
+                int at = atomicAdd(s_cnt, 1);
+                if (at < cap) s_cand[at] = (int)i;
+            }
+        }
+        __syncthreads();
+        const int cnt = *s_cnt;
+        __syncthreads();
+        if (cnt > cap) {
+            bubble_windows(SA, LCP, SAi, n, begin, s_cand, s_cnt, cap);
+        } else if (cnt > 0) {
+            bubble_sort_cands(s_cand, cnt);
+            bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_cnt + 1);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BB_THREADS) bubble_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int nbegins, int cap) {
+    __shared__ int s_cand[BB_CAP];
+    __shared__ int s_cnt[12];  // [0] candidate count, [1..] scratch of the replay
+    bubble_block(SA, LCP, SAi, n, begins, nbegins, s_cand, s_cnt, cap);
+}
+
+// Large children: the candidate scan runs grid-wide, the sort + replay in one block.
+__global__ void __launch_bounds__(256) bubble_detect_kernel(const int *__restrict__ SA, const int *__restrict__ LCP, i64 n, const i64 *__restrict__ begins,
+                                                           int b, int *__restrict__ cand, int *__restrict__ cand_cnt, int cap) {
+    const i64 begin = begins[b];
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (bubble_candidate(SA, LCP, n, i, begin)) {
+            int at = atomicAdd(cand_cnt, 1);
+            if (at < cap) cand[at] = (int)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BB_THREADS) bubble_apply_kernel(int *SA, int *LCP, int *SAi, i64 n, const i64 *__restrict__ begins, int b,
+                                                                  const int *__restrict__ cand, int *cand_cnt, int cap) {
+    __shared__ int s_cand[BB_CAP];
+    __shared__ int s_cnt[12];
+    const i64 begin = begins[b];
+    const int cnt = *cand_cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) *cand_cnt = 0;  // ready for the next matched interval
+    if (cnt > cap) {  // rare: more candidates than the fast path holds
+        bubble_windows(SA, LCP, SAi, n, begin, s_cand, s_cnt, cap);
+        return;
+    }
+    if (cnt == 0) return;
+    for (int i = threadIdx.x; i < cnt; i += BB_THREADS) s_cand[i] = cand[i];
+    __syncthreads();
+    bubble_sort_cands(s_cand, cnt);
+    bubble_replay_block(SA, LCP, SAi, n, begin, s_cand, cnt, s_cnt + 1);
 }
 
 // ---- one whole recursion step of a SMALL sub-index in a single launch ---------------------------
@@ -455,6 +453,7 @@ struct SmallStepArgs {
     i64 bbeg[SM_MAXMUM];
     int *cSA[3], *cLCP[3];
     int cn[3], do_sweep[3];
+    int bb_cap;     // candidates per matched interval the sorted fast path of bubble_sort takes (BB_CAP but for tests)
     i64 *out;       // host-mapped: [0..15] header, then rows / members
     i64 out_words;
 };
@@ -608,7 +607,7 @@ __global__ void __launch_bounds__(SM_THREADS) small_step_kernel(const SmallStepA
     }
     __syncthreads();
     // ---- bubble_sort of the leading child (reveal.c:1250-1252) ----
-    if (a.cn[0] > 0 && a.nb > 0) bubble_block(a.cSA[0], a.cLCP[0], a.SAi, (i64)a.cn[0], a.bbeg, a.nb, s_cand, s_cnt);
+    if (a.cn[0] > 0 && a.nb > 0) bubble_block(a.cSA[0], a.cLCP[0], a.SAi, (i64)a.cn[0], a.bbeg, a.nb, s_cand, s_cnt, a.bb_cap);
     __syncthreads();
     // ---- the children's MUM sweeps (reveal.c:802-829 of their own steps) ----
     for (int c = 0; c < 3; c++) {
@@ -1058,7 +1057,7 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
         i64 block_maxn = 8192;
         if (const char *e = getenv("RV_BUBBLE_BLOCK_MAXN")) block_maxn = atoll(e);  // test hook
         if (kids[0]->n <= block_maxn) {
-            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, (int)bbeg.size());
+            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, (int)bbeg.size(), bubble_cap());
             st.launches++;
         } else {
             RV_TRY(lease.take((size_t)(BB_CAP + 16) * 4, &dcand));
@@ -1067,8 +1066,8 @@ static int split_general(rv_sub *parent, const int64_t *lead, int32_t nlead, con
             i64 blocks = (kids[0]->n + 255) / 256;
             if (blocks > 148 * 8) blocks = 148 * 8;
             for (int b = 0; b < (int)bbeg.size(); b++) {
-                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, kids[0]->SA, kids[0]->LCP, kids[0]->n, d_bbeg, b, cand, cand_cnt);
-                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, b, cand, cand_cnt);
+                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, kids[0]->SA, kids[0]->LCP, kids[0]->n, d_bbeg, b, cand, cand_cnt, bubble_cap());
+                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, kids[0]->SA, kids[0]->LCP, v.ISA, kids[0]->n, d_bbeg, b, cand, cand_cnt, bubble_cap());
                 st.launches += 2;
             }
         }
@@ -1180,6 +1179,7 @@ static int small_prepare(const rv_step_desc &d, MainView &v, RecCtx *ctx, int32_
     a.rc = v.rc;
     a.minl = minl;
     a.minn = minn;
+    a.bb_cap = bubble_cap();
     a.pSA = parent->SA;
     a.pLCP = parent->LCP;
     a.n = (int)n;
@@ -1528,7 +1528,7 @@ int rv_sub_extract(rv_sub *sub, const int64_t *intervals, int32_t nintervals) {
     void *dcand = nullptr;
     if (cn > 0 && !bbeg.empty()) {  // bubble_sort(idx, intervals) (reveal.c:1497)
         if (cn <= 8192) {
-            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, (int)bbeg.size());
+            RV_LAUNCH(bubble_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, (int)bbeg.size(), bubble_cap());
             st.launches++;
         } else {
             if (lease.take((size_t)(BB_CAP + 16) * 4, &dcand) != RV_OK) { pool->give(p1); pool->give(p2); return RV_ERR_NOMEM; }
@@ -1537,8 +1537,8 @@ int rv_sub_extract(rv_sub *sub, const int64_t *intervals, int32_t nintervals) {
             i64 blocks = (cn + 255) / 256;
             if (blocks > 148 * 8) blocks = 148 * 8;
             for (int b = 0; b < (int)bbeg.size(); b++) {
-                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, nSA, nLCP, cn, d_bbeg, b, cand, cand_cnt);
-                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, b, cand, cand_cnt);
+                RV_LAUNCH(bubble_detect_kernel, (unsigned)blocks, 256, 0, st.s, nSA, nLCP, cn, d_bbeg, b, cand, cand_cnt, bubble_cap());
+                RV_LAUNCH(bubble_apply_kernel, 1, BB_THREADS, 0, st.s, nSA, nLCP, v.ISA, cn, d_bbeg, b, cand, cand_cnt, bubble_cap());
                 st.launches += 2;
             }
         }

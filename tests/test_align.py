@@ -85,16 +85,59 @@ def test_align_matches_reference_emulated(emu_reveallib, name, ns, length, sigma
 
 
 @needs_ref
-@pytest.mark.parametrize("small_maxn,bubble_maxn", [("0", "100000"), ("0", "0"), ("600", "0")])
-def test_align_general_step_paths_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn):
-    """RV_SMALL_MAXN / RV_BUBBLE_BLOCK_MAXN force the multi-kernel step and the grid-wide bubble detection."""
+@pytest.mark.parametrize("small_maxn,bubble_maxn,bubble_cap", [("0", "100000", None), ("0", "0", None), ("600", "0", None),
+                                                               ("16384", "100000", "32"), ("0", "100000", "32"), ("0", "0", "32")])
+def test_align_general_step_paths_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn, bubble_cap):
+    """RV_SMALL_MAXN / RV_BUBBLE_BLOCK_MAXN force the multi-kernel step and the grid-wide bubble detection; RV_BUBBLE_CAP=32
+    makes matched intervals with more than 32 candidate slots take bubble_sort's windowed path (4096 in the product) in the
+    single-block step, the one-block bubble kernel and the grid-wide detection + apply pair."""
     monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
     monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
+    if bubble_cap:
+        monkeypatch.setenv("RV_BUBBLE_CAP", bubble_cap)
     rng = np.random.default_rng(77)
     samples = random_related(rng, 3, 1100, 4, snp=0.03)
     assert compare(run_reference(samples, 8, 2), run_ours(emu_reveallib, samples, 8, 2)) > 3
     samples = random_related(rng, 2, 1500, 4, snp=0.03)
     assert compare(run_reference(samples, 8, 2), run_ours(emu_reveallib, samples, 8, 2)) > 3
+
+
+def repeat_before_match(rng, rlen=300, mlen=400, nsamples=2):
+    """Two samples whose longest MUM M starts right behind the second copy of a repeat R in sample 0, the first copy being
+    followed by the first characters of M: every suffix inside that second copy matches its twin in the first copy ACROSS the
+    start of M, i.e. bubble_sort of the leading child meets about rlen candidate slots for that matched interval."""
+    al = np.frombuffer(b"ACGT", np.uint8)
+
+    def rnd(k):
+        return al[rng.integers(0, 4, size=k)].tobytes()
+    R, M = rnd(rlen), rnd(mlen)
+    s0 = rnd(500) + R + M[:25] + rnd(400) + R + M + rnd(300)
+    return [[s0]] + [[rnd(700 - 60 * k) + M + rnd(350 + 40 * k)] for k in range(nsamples - 1)]
+
+
+@needs_ref
+@pytest.mark.parametrize("small_maxn,bubble_maxn", [("16384", "100000"), ("0", "100000"), ("0", "0")])
+def test_bubble_sort_more_candidates_than_the_fast_path_holds_emulated(emu_reveallib, monkeypatch, small_maxn, bubble_maxn):
+    """A matched interval with more candidate slots than bubble_sort's sorted fast path takes at once (RV_BUBBLE_CAP=32 here,
+    4096 in the product) goes through the windowed replay -- in the single-block step, the one-block bubble kernel and the
+    grid-wide detection + apply pair (round 1 handed this case to one thread).  The children's SA and LCP arrays are compared
+    with the reference's own splitindex."""
+    monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
+    monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
+    monkeypatch.setenv("RV_BUBBLE_CAP", "32")
+    splitindex_case(emu_reveallib.mod32, 3, 0, 10, samples=repeat_before_match(np.random.default_rng(123), nsamples=3), min_steps=1)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("small_maxn,bubble_maxn", [("16384", "100000"), ("0", "100000"), ("0", "0")])
+def test_bubble_sort_more_candidates_than_the_fast_path_holds_cuda(monkeypatch, small_maxn, bubble_maxn):
+    """The same on the CUDA library at the product's limit: a 6000-character repeat in front of the match gives about 6000
+    candidate slots, more than the 4096 the sorted fast path takes."""
+    from reveal_b200 import reveallib
+    monkeypatch.setenv("RV_SMALL_MAXN", small_maxn)
+    monkeypatch.setenv("RV_BUBBLE_BLOCK_MAXN", bubble_maxn)
+    splitindex_case(reveallib, 3, 0, 10, samples=repeat_before_match(np.random.default_rng(321), rlen=6000, mlen=700, nsamples=3), min_steps=1)
 
 
 @needs_ref
@@ -186,9 +229,10 @@ def test_splitindex_matches_reference_cuda(ns, length, minl):
     splitindex_case(reveallib, ns, length, minl)
 
 
-def splitindex_case(mod32, ns, length, minl):
+def splitindex_case(mod32, ns, length, minl, samples=None, min_steps=3):
     rng = np.random.default_rng(900 + ns)
-    samples = random_related(rng, ns, length, 4, snp=0.03)
+    if samples is None:
+        samples = random_related(rng, ns, length, 4, snp=0.03)
     seqs = [[bytes(c).decode() for c in contigs] for contigs in samples]
 
     def build(mod):
@@ -231,7 +275,7 @@ def splitindex_case(mod32, ns, length, minl):
                 if ca is not None and ca.n > 1:
                     nxt.append((ca, cb))
         frontier = nxt
-    assert steps >= 3
+    assert steps >= min_steps
     assert ours.T == ref.T[:ref.n]
 
 
