@@ -720,6 +720,27 @@ static bool parse_mums(PyObject *list, std::vector<Mum> &out) {
         PyBuffer_Release(&view);
         return true;
     }
+    if (!PyList_Check(list) && !PyTuple_Check(list) && PyObject_HasAttrString(list, "_rv_multi")) {
+        // multi-MUM rows straight from the device sweep (reveallib.multimumrows): record rows (l, n, first) + member rows
+        struct RvMultiView { const int64_t *hdr; int64_t nrec; const int64_t *mem; int64_t nmem; };   // layout of reveallib_module.cpp
+        PyObject *cap = PyObject_GetAttrString(list, "_rv_multi");
+        if (!cap) return false;
+        const RvMultiView *v = (const RvMultiView *)PyCapsule_GetPointer(cap, "reveal_b200.RvMultiView");
+        if (!v) { Py_DECREF(cap); return false; }
+        out.reserve((size_t)v->nrec);
+        for (int64_t i = 0; i < v->nrec; i++) {
+            Mum m;
+            m.l = v->hdr[3 * i];
+            m.n = (long)v->hdr[3 * i + 1];
+            m.orig = nullptr;
+            m.spd = nullptr;
+            const int64_t first = v->hdr[3 * i + 2];
+            for (int64_t x = 0; x < m.n; x++) m.sp.emplace_back((long)v->mem[2 * (first + x)], v->mem[2 * (first + x) + 1]);
+            out.push_back(std::move(m));
+        }
+        Py_DECREF(cap);
+        return true;
+    }
     PyObject *seq = PySequence_Fast(list, "mums must be a sequence");
     if (!seq) return false;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);

@@ -596,6 +596,53 @@ static int mumrows_getbuffer(MumRows *self, Py_buffer *view, int flags) {
 static PySequenceMethods mumrows_as_sequence = {(lenfunc)mumrows_len, nullptr, nullptr, (ssizeargfunc)mumrows_item};
 static PyBufferProcs mumrows_as_buffer = {(getbufferproc)mumrows_getbuffer, nullptr};
 
+// The same for multi-MUMs (more than two samples): `multimumrows` keeps the record rows (l, n, first) and the member rows
+// (sample, position) of the device sweep.  len() and indexing give the reference's tuples (l, n, ((sample, position), ...)),
+// reveal.c:497; a native picker reaches the arrays through the capsule attribute `_rv_multi` (struct RvMultiView below; the
+// capsule keeps the object alive).
+struct RvMultiView {      // shared with remcore_module.cpp by layout
+    const int64_t *hdr;   // nrec x (l, n, first member)
+    int64_t nrec;
+    const int64_t *mem;   // nmem x (sample, position)
+    int64_t nmem;
+};
+struct MultiMumRows {
+    PyObject_HEAD
+    std::vector<int64_t> *hdr, *mem;
+    RvMultiView view;
+};
+static PyTypeObject MultiMumRowsType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+static void multimumrows_dealloc(MultiMumRows *self) {
+    delete self->hdr;
+    delete self->mem;
+    Py_TYPE(self)->tp_free((PyObject *)self);
+}
+static Py_ssize_t multimumrows_len(MultiMumRows *self) { return (Py_ssize_t)self->view.nrec; }
+static PyObject *multimumrows_item(MultiMumRows *self, Py_ssize_t i) {
+    if (i < 0 || i >= (Py_ssize_t)self->view.nrec) {
+        PyErr_SetString(PyExc_IndexError, "multimumrows index out of range");
+        return nullptr;
+    }
+    const int64_t *h = self->view.hdr + 3 * i;
+    const int64_t cnt = h[1], first = h[2];
+    PyObject *members = PyTuple_New((Py_ssize_t)cnt);
+    if (!members) return nullptr;
+    for (int64_t x = 0; x < cnt; x++)
+        PyTuple_SET_ITEM(members, (Py_ssize_t)x, Py_BuildValue("(lL)", (long)self->view.mem[2 * (first + x)], (long long)self->view.mem[2 * (first + x) + 1]));
+    return Py_BuildValue("(LlN)", (long long)h[0], (long)cnt, members);
+}
+static void multiview_capsule_free(PyObject *cap) { Py_XDECREF((PyObject *)PyCapsule_GetContext(cap)); }
+static PyObject *multimumrows_view(MultiMumRows *self, void *) {
+    PyObject *cap = PyCapsule_New(&self->view, "reveal_b200.RvMultiView", multiview_capsule_free);
+    if (!cap) return nullptr;
+    Py_INCREF((PyObject *)self);
+    PyCapsule_SetContext(cap, self);
+    return cap;
+}
+static PySequenceMethods multimumrows_as_sequence = {(lenfunc)multimumrows_len, nullptr, nullptr, (ssizeargfunc)multimumrows_item};
+static PyGetSetDef multimumrows_getset[] = {{"_rv_multi", (getter)multimumrows_view, nullptr, "capsule over the record and member rows", nullptr},
+                                            {nullptr, nullptr, nullptr, nullptr, nullptr}};
+
 // MUMs of a (sub)index in the shape the reference hands to mumpicker (reveal.c:802-829)
 static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn, bool as_rows = false) {
     int64_t nr = 0, nm = 0;
@@ -607,6 +654,14 @@ static PyObject *extract_mums(Index *root, rv_sub *sub, int minl, int minn, bool
         if (fail_native(status) != 0) return nullptr;
         std::vector<int64_t> hdr((size_t)(3 * nr + 3)), mem((size_t)(2 * nm + 2));
         if (fail_native(g_api.rv_sub_fetch(sub, hdr.data(), nr, mem.data(), nm)) != 0) return nullptr;
+        if (as_rows) {
+            MultiMumRows *mr = (MultiMumRows *)MultiMumRowsType.tp_alloc(&MultiMumRowsType, 0);
+            if (!mr) return nullptr;
+            mr->hdr = new std::vector<int64_t>(std::move(hdr));
+            mr->mem = new std::vector<int64_t>(std::move(mem));
+            mr->view = RvMultiView{mr->hdr->data(), nr, mr->mem->data(), nm};
+            return (PyObject *)mr;
+        }
         return multi_to_list(hdr, mem, nr, nm, true);
     }
     Py_BEGIN_ALLOW_THREADS;
@@ -818,7 +873,7 @@ static PyObject *index_align(Index *self, PyObject *args, PyObject *kwds) {
             PyObject *mums;
             if (!precomputed) {
                 const double t0 = now_s();
-                mums = extract_mums(self, idx->sub, minl, minn, mums_as_rows != 0);  // (rows: pair MUMs only, see mumrows)
+                mums = extract_mums(self, idx->sub, minl, minn, mums_as_rows != 0);  // (mumrows / multimumrows)
                 as.extract += now_s() - t0;
                 if (!mums) ok = false;
             } else {
@@ -1444,6 +1499,14 @@ PyMODINIT_FUNC MODINIT(void) {
     MumRowsType.tp_as_sequence = &mumrows_as_sequence;
     MumRowsType.tp_as_buffer = &mumrows_as_buffer;
     if (PyType_Ready(&MumRowsType) < 0) return nullptr;
+    MultiMumRowsType.tp_name = MODNAME ".multimumrows";
+    MultiMumRowsType.tp_basicsize = sizeof(MultiMumRows);
+    MultiMumRowsType.tp_flags = Py_TPFLAGS_DEFAULT;
+    MultiMumRowsType.tp_doc = "multi-MUM rows of a sub-index: a sequence of the reference's tuples (l, n, ((sample, position), ...))";
+    MultiMumRowsType.tp_dealloc = (destructor)multimumrows_dealloc;
+    MultiMumRowsType.tp_as_sequence = &multimumrows_as_sequence;
+    MultiMumRowsType.tp_getset = multimumrows_getset;
+    if (PyType_Ready(&MultiMumRowsType) < 0) return nullptr;
     PyObject *m = PyModule_Create(&moduledef);
     if (!m) return nullptr;
     Py_INCREF(&IndexType);

@@ -344,11 +344,13 @@ def test_extract_matches_reference_cuda(ns, length, minl):
 
 
 @needs_ref
-def test_align_mums_as_rows_emulated(emu_reveallib):
-    """align(mums_as_rows=True): pair MUM lists arrive as `mumrows` objects -- len(), iteration and indexing give the reference's
-    tuples, so the same callbacks produce the same events; the buffer holds the int64 rows."""
+@pytest.mark.parametrize("ns", [2, 3])
+def test_align_mums_as_rows_emulated(emu_reveallib, ns):
+    """align(mums_as_rows=True): pair MUM lists arrive as `mumrows` objects, multi-MUM lists (more than two samples) as
+    `multimumrows` -- len(), iteration and indexing give the reference's tuples, so the same callbacks produce the same events;
+    the buffer of a `mumrows` holds the int64 rows."""
     rng = np.random.default_rng(5)
-    samples = random_related(rng, 2, 1500, 4, snp=0.03)
+    samples = random_related(rng, ns, 1500, 4, snp=0.03)
     ref = run_reference(samples, 8, 2)
     log = []
     idx = emu_reveallib.index()
@@ -368,7 +370,7 @@ def test_align_mums_as_rows_emulated(emu_reveallib):
         return mp(mums, index, precomputed=precomputed, minlength=minlength)
 
     idx.align(picker, ga, threads=1, minl=8, minn=2, mums_as_rows=True)
-    assert "mumrows" in seen
+    assert ("mumrows" if ns == 2 else "multimumrows") in seen
     assert compare(ref, (log, idx.T)) > 3
 
 
