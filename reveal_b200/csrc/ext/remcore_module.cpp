@@ -656,7 +656,7 @@ template <class T, int N> struct SmallVec {
 struct Mum {
     int64_t l;
     long n;
-    SmallVec<std::pair<long, int64_t>, 4> sp;  // (sample of the index, position), in the order of the tuple
+    SmallVec<std::pair<long, int64_t>, 8> sp;  // (sample of the index, position), in the order of the tuple
     PyObject *orig;                            // the caller's tuple while the anchor is untouched (borrowed)
     PyObject *spd;                             // the caller's position tuple while the positions are untouched (borrowed)
 };
@@ -664,7 +664,7 @@ struct Mum {
 struct Rel {
     int64_t l;
     long n;
-    SmallVec<std::pair<int32_t, int64_t>, 4> point;  // (path id, coordinate), insertion-ordered like the dict it mirrors
+    SmallVec<std::pair<int32_t, int64_t>, 8> point;  // (path id, coordinate), insertion-ordered like the dict it mirrors
     int src;                                         // index into the picked anchors
     uint64_t value_hash() const {                    // of the coordinate values in order (the reference keys a dict by that tuple)
         uint64_t h = 0x9e3779b97f4a7c15ull ^ point.size();
