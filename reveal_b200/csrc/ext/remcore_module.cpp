@@ -786,25 +786,37 @@ static void trim_overlap(std::vector<Mum> &mums) {
     const size_t ncoord = mums[0].sp.size();
     for (size_t coord = 0; coord < ncoord; coord++) {
         if (mums.size() <= 1) break;
-        // order by (position in this coordinate, longer first), stable: sorted as small (key, index) records, anchors moved once
+        // order by (position in this coordinate, longer first), stable: sorted as small (key, index) records; an anchor itself
+        // is moved ONCE per coordinate, into the trimmed list
         const size_t n = mums.size();
         struct Key { int64_t pos, l; uint32_t at; };
         std::vector<Key> keyv(n);
         for (size_t i = 0; i < n; i++) keyv[i] = Key{mums[i].sp[coord].second, mums[i].l, (uint32_t)i};
-        std::stable_sort(keyv.begin(), keyv.end(), [](const Key &a, const Key &b) { return a.pos != b.pos ? a.pos < b.pos : a.l > b.l; });
-        std::vector<int64_t> ends(n);
-        for (size_t i = 0; i < n; i++) ends[i] = keyv[i].pos + keyv[i].l;
-        std::vector<Mum> kept;
+        bool sorted = true;   // (lists come in suffix-array order or, further down, already in this order: skip the sort when they do)
+        for (size_t i = 1; i < n && sorted; i++)
+            sorted = keyv[i - 1].pos < keyv[i].pos || (keyv[i - 1].pos == keyv[i].pos && keyv[i - 1].l >= keyv[i].l);
+        if (!sorted) std::stable_sort(keyv.begin(), keyv.end(), [](const Key &a, const Key &b) { return a.pos != b.pos ? a.pos < b.pos : a.l > b.l; });
+        std::vector<uint32_t> kept;
         kept.reserve(n);
-        for (size_t i = 0; i < n; i++)  // the reference compares the FIRST anchor with its successor, or (i-1 = -1) with the last one
-            if ((i == 0 && ends[1] > ends[0]) || ends[(i + n - 1) % n] < ends[i]) kept.push_back(mums[keyv[i].at]);
-        mums.swap(kept);
-        if (mums.size() <= 1) break;
+        for (size_t i = 0; i < n; i++) {  // the reference compares the FIRST anchor with its successor, or (i-1 = -1) with the last one
+            const int64_t end_i = keyv[i].pos + keyv[i].l, end_1 = keyv[1].pos + keyv[1].l, end_0 = keyv[0].pos + keyv[0].l;
+            const Key &pk = keyv[(i + n - 1) % n];
+            if ((i == 0 && end_1 > end_0) || pk.pos + pk.l < end_i) kept.push_back(keyv[i].at);
+        }
         std::vector<Mum> trimmed;
-        trimmed.reserve(mums.size());
-        trimmed.push_back(mums[0]);
-        for (size_t i = 1; i < mums.size(); i++) {
-            Mum mum = mums[i];
+        trimmed.reserve(kept.size());
+        if (kept.size() <= 1) {
+            for (uint32_t at : kept) trimmed.push_back(std::move(mums[at]));
+            mums.swap(trimmed);
+            break;
+        }
+        trimmed.push_back(std::move(mums[kept[0]]));
+        for (size_t i = 1; i < kept.size(); i++) {
+            Mum &mum = mums[kept[i]];   // (every index occurs once: not moved from yet)
+            if (trimmed.empty()) {      // (the anchor before swallowed its predecessor and was dropped itself)
+                trimmed.push_back(std::move(mum));
+                continue;
+            }
             const Mum &prev = trimmed.back();
             const int64_t overlap = prev.sp[coord].second + prev.l - mum.sp[coord].second;
             if (overlap > 0) {
@@ -819,10 +831,10 @@ static void trim_overlap(std::vector<Mum> &mums) {
                     for (auto &p : mum.sp) p.second += overlap;
                     mum.orig = nullptr;
                     mum.spd = nullptr;
-                    trimmed.push_back(mum);
+                    trimmed.push_back(std::move(mum));
                 }
             } else {
-                trimmed.push_back(mum);
+                trimmed.push_back(std::move(mum));
             }
         }
         mums.swap(trimmed);
