@@ -632,6 +632,22 @@ template <class T, int N> struct SmallVec {
     T inl[N];
     std::vector<T> more;
     uint32_t count = 0;
+    SmallVec() {}
+    // copies and moves touch the elements in use only (two of the eight inline slots for a pair of genomes)
+    SmallVec(const SmallVec &o) : more(o.more), count(o.count) { take(o); }
+    SmallVec(SmallVec &&o) noexcept : more(std::move(o.more)), count(o.count) { take(o); }
+    SmallVec &operator=(const SmallVec &o) {
+        if (this != &o) { more = o.more; count = o.count; take(o); }
+        return *this;
+    }
+    SmallVec &operator=(SmallVec &&o) noexcept {
+        if (this != &o) { more = std::move(o.more); count = o.count; take(o); }
+        return *this;
+    }
+    void take(const SmallVec &o) {
+        const uint32_t k = count < (uint32_t)N ? count : (uint32_t)N;
+        for (uint32_t i = 0; i < k; i++) inl[i] = o.inl[i];
+    }
     size_t size() const { return count; }
     bool empty() const { return count == 0; }
     T *data() { return count <= (uint32_t)N ? inl : more.data(); }
@@ -795,7 +811,8 @@ static void trim_overlap(std::vector<Mum> &mums) {
         bool sorted = true;   // (lists come in suffix-array order or, further down, already in this order: skip the sort when they do)
         for (size_t i = 1; i < n && sorted; i++)
             sorted = keyv[i - 1].pos < keyv[i].pos || (keyv[i - 1].pos == keyv[i].pos && keyv[i - 1].l >= keyv[i].l);
-        if (!sorted) std::stable_sort(keyv.begin(), keyv.end(), [](const Key &a, const Key &b) { return a.pos != b.pos ? a.pos < b.pos : a.l > b.l; });
+        // (the index as the last key makes the order total: plain sort = stable sort)
+        if (!sorted) std::sort(keyv.begin(), keyv.end(), [](const Key &a, const Key &b) { return a.pos != b.pos ? a.pos < b.pos : (a.l != b.l ? a.l > b.l : a.at < b.at); });
         std::vector<uint32_t> kept;
         kept.reserve(n);
         for (size_t i = 0; i < n; i++) {  // the reference compares the FIRST anchor with its successor, or (i-1 = -1) with the last one
@@ -876,8 +893,15 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
     std::vector<Mum> &all = J.all, &picked = J.picked;
     if (!parse_mums(list, all)) return -1;
     PK_MARK(0)
-    for (auto &m : all)
-        if (m.n == nsamples) picked.push_back(m);
+    {
+        size_t full = 0;
+        for (auto &m : all)
+            if (m.n == nsamples) full++;
+        if (full == all.size() && full > 0) picked = std::move(all);   // every anchor spans all samples (always, for two): no copy
+        else
+            for (auto &m : all)
+                if (m.n == nsamples) picked.push_back(m);
+    }
     if (picked.empty() && nsamples > 2) {  // schemes.segment: the sample group with the largest total length x group size
         std::vector<std::vector<long>> parts;
         std::vector<std::vector<int>> members;
