@@ -127,6 +127,40 @@ template <typename KeyT> struct KeyRoller {
     }
 };
 
+// DNA fast path of the roller: four frequent symbols (2-bit digits) and 32-bit keys (k <= 16).  The TK_PER = 16 consecutive
+// suffixes of a thread need the 16 + k - 1 <= 31 symbols from its first position on: two 128-bit loads of the text, the
+// classes of the 32 symbols packed two bits each into one 64-bit word (first symbol in the top bits) and the rare / max-fill
+// flags one bit per symbol; every key is then a shift and a mask of that word -- the same value KeyRoller::key() yields.
+struct KeyBlock4 {
+    u64 P;       // class of symbol t in bits [62 - 2t, 64 - 2t)
+    u32 rm, xm;  // bit t: symbol t is rare / rare with max fill
+    // usable when the whole 32-byte window lies inside the text and is 16-byte aligned
+    static __device__ __forceinline__ bool fits(const TextKeySrc &s, i64 i0) {
+        return TK_PER == 16 && s.base == 4u && s.k <= 16 && i0 + 32 <= s.n && ((((size_t)s.T) + (size_t)i0) & 15u) == 0u;
+    }
+    __device__ __forceinline__ void load(const unsigned char *p, const unsigned short *s_code) {
+        const uint4 a = *(const uint4 *)p, b = *(const uint4 *)(p + 16);
+        const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        P = 0;
+        rm = xm = 0;
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+            const u32 c = s_code[(w[t >> 2] >> (8 * (t & 3))) & 0xffu];
+            P = (P << 2) | (u64)(c & 3u);
+            rm |= ((c >> 8) & 1u) << t;
+            xm |= ((c >> 9) & 1u) << t;
+        }
+    }
+    __device__ __forceinline__ u32 key(int j, int k) const {  // suffix at symbol j (0..15) of the window
+        const u32 raw = (u32)(P >> (2 * (32 - j - k))) & (k >= 16 ? 0xffffffffu : ((1u << (2 * k)) - 1u));
+        const u32 r = (rm >> j) & ((1u << k) - 1u);
+        if (r == 0u) return raw;
+        const int d = __ffs((int)r) - 1;                    // first rare symbol of the window: the key ends there
+        const u32 low = (1u << (2 * (k - 1 - d))) - 1u;     // the digits behind it
+        return ((xm >> (j + d)) & 1u) ? (raw | low) : (raw & ~low);
+    }
+};
+
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src, RadixPlan plan, u32 *__restrict__ ghist) {
     __shared__ u32 sh[RS_MAXPASS * RS_BINS];
@@ -136,6 +170,16 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src
     __syncthreads();
     const i64 stride = (i64)gridDim.x * RS_THREADS * TK_PER;
     for (i64 i0 = ((i64)blockIdx.x * RS_THREADS + threadIdx.x) * TK_PER; i0 < src.n; i0 += stride) {
+        if (sizeof(KeyT) == 4 && KeyBlock4::fits(src, i0)) {
+            KeyBlock4 kb;
+            kb.load(src.T + i0, s_code);
+#pragma unroll
+            for (int j = 0; j < TK_PER; j++) {
+                const u32 key = kb.key(j, src.k);
+                for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * RS_BINS + ((key >> plan.shift[p]) & plan.mask[p])], 1u);
+            }
+            continue;
+        }
         KeyRoller<KeyT> kr;
         kr.first(src, s_code, i0);
         for (int j = 0; j < TK_PER && i0 + j < src.n; j++) {
@@ -225,15 +269,28 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
         unsigned short *s_code = (unsigned short *)s_off;  // 512 B: s_off is written much later
         s_code[tid] = src.code[tid];
         __syncthreads();
+        // (one pad element per 32 keeps the blocked writes -- a thread's RS_IPT consecutive keys -- and the striped reads free of
+        //  bank conflicts; the tail of the padded array lies in the value area, which is not in use yet)
         const i64 i0 = base + (i64)tid * RS_IPT;
         if (i0 < n) {
-            KeyRoller<KeyT> kr;
-            kr.first(src, s_code, i0);
+            if (sizeof(KeyT) == 4 && RS_IPT == TK_PER && KeyBlock4::fits(src, i0)) {
+                KeyBlock4 kb;
+                kb.load(src.T + i0, s_code);
 #pragma unroll
-            for (int j = 0; j < RS_IPT; j++) {
-                if (i0 + j < n) {
-                    s_keys[tid * RS_IPT + j] = kr.key(src);
-                    kr.next(src, s_code, i0 + j);
+                for (int j = 0; j < RS_IPT; j++) {
+                    const int e = (int)tid * RS_IPT + j;
+                    s_keys[e + (e >> 5)] = (KeyT)kb.key(j, src.k);
+                }
+            } else {
+                KeyRoller<KeyT> kr;
+                kr.first(src, s_code, i0);
+#pragma unroll
+                for (int j = 0; j < RS_IPT; j++) {
+                    if (i0 + j < n) {
+                        const int e = (int)tid * RS_IPT + j;
+                        s_keys[e + (e >> 5)] = kr.key(src);
+                        kr.next(src, s_code, i0 + j);
+                    }
                 }
             }
         }
@@ -241,7 +298,7 @@ rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             int idx = wbase + k * 32 + (int)l;
-            key[k] = idx < cnt ? s_keys[idx] : (KeyT)0;
+            key[k] = idx < cnt ? s_keys[idx + (idx >> 5)] : (KeyT)0;
         }
         __syncthreads();  // s_keys is reused as the bucket-ordered staging area below
     } else if (by_tma) {

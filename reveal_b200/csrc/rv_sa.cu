@@ -147,25 +147,25 @@ __device__ __forceinline__ u32 first_barrier(const Barriers &B, u32 x, u32 len) 
     // level 0 is only touched when a barrier is near.
     if ((wl >> 5) - (w >> 5) <= 1u) {
         const u32 va = w >> 5, vb = wl >> 5;   // level-1 words = level-2 bits of the range
-        const u32 qa = B.b2[va >> 5] >> (va & 31u), qb = B.b2[vb >> 5] >> (vb & 31u);
+        const u32 qa = __ldg(B.b2 + (va >> 5)) >> (va & 31u), qb = __ldg(B.b2 + (vb >> 5)) >> (vb & 31u);
         if (((qa | qb) & 1u) == 0u) return len;
     }
     if ((wl >> 5) - (w >> 5) <= 1u) {
         const u32 v = w >> 5, vl = wl >> 5;
-        u32 m = B.b1[v] >> (w & 31u);                   // words w .. end of level-1 word v
+        u32 m = __ldg(B.b1 + v) >> (w & 31u);           // words w .. end of level-1 word v
         if (v == vl) {
             const u32 span = wl - w;
             if (span < 31u) m &= (2u << span) - 1u;
         } else {
             const u32 last = wl & 31u;                   // words 0 .. last of level-1 word vl
-            u32 m2 = B.b1[vl];
+            u32 m2 = __ldg(B.b1 + vl);
             if (last < 31u) m2 &= (2u << last) - 1u;
             m |= m2;
         }
         if (m == 0u) return len;
     }
     {
-        const u32 bits = B.b0[w] >> (x & 31u);
+        const u32 bits = __ldg(B.b0 + w) >> (x & 31u);
         if (bits) {
             const u32 at = (u32)(__ffs((int)bits) - 1);
             return at < len ? at : len;
@@ -280,13 +280,14 @@ __device__ __forceinline__ int direct_lcp(const u32 *__restrict__ W, u32 n32, u3
 #define RV_PR_CHUNK 256
 #endif
 #ifndef RV_PR_MINBLOCKS
-#define RV_PR_MINBLOCKS 8
+#define RV_PR_MINBLOCKS 9
 #endif
 static const int PR_THREADS = RV_PR_THREADS;
 static const int PR_WARPS = PR_THREADS / 32;
 static const int PR_CHUNK = RV_PR_CHUNK;               // nominal SA slots per warp
 static const int PR_MAXT = PR_CHUNK + 32;              // a chunk is stretched to whole groups (<= SA_SMALL_G more), padded to rounds
 static const int PR_ROUNDS = PR_MAXT / 32;
+static_assert(PR_ROUNDS <= 10, "pair_chunk_setup packs one 6-bit field per round into 64 bits");
 static const int PL_CAP = 512;                         // pair items per warp (a power of two >= 32 * 15 + 31)
 #ifndef RV_ET_WAYS
 #define RV_ET_WAYS 4
@@ -322,8 +323,12 @@ __device__ __forceinline__ void window_run(const KeyT *__restrict__ keys, i64 n,
     if (R > 15 || R < 0) R = 15;
 }
 
+// keyclz: for slot t = 32 r + lane, bits [6r, 6r+6) = leading zero bits of (key of slot t) ^ (key of slot t-1), capped at 32 --
+// what sa_place_kernel needs of the keys once the staging is over (PR_ROUNDS <= 10)
 template <typename KeyT>
-__device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, u32 *s_head_raw /*[PR_ROUNDS+2]*/) {
+__device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, u32 *s_head_raw /*[PR_ROUNDS+2]*/,
+                                                 u64 &keyclz) {
+    keyclz = 0ull;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     c.head = s_head_raw + 1;
     const i64 c0 = ((i64)blockIdx.x * PR_WARPS + w) * PR_CHUNK;
@@ -365,6 +370,7 @@ __device__ __forceinline__ void pair_chunk_setup(PairChunk &c, const KeyT *__res
         KeyT kp = __shfl_up_sync(FULL, kreg[r], 1);
         if (lane == 0) kp = carry;
         const bool is_head = valid && (e == 0 || kreg[r] != kp);
+        if (sizeof(KeyT) == 4) keyclz |= (u64)(u32)__clz((int)((u32)kreg[r] ^ (u32)kp)) << (6 * r);
         const unsigned hm = __ballot_sync(FULL, is_head);
         if (lane == 0) c.head[r] = hm;
         if (t < PR_MAXT) c.ssa[t] = sreg[r];
@@ -406,7 +412,8 @@ sa_lead_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n,
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     PairChunk c;
     c.ssa = s_sa[w];
-    pair_chunk_setup(c, keys, sa, n, s_head[w]);
+    u64 keyclz_unused;
+    pair_chunk_setup(c, keys, sa, n, s_head[w], keyclz_unused);
     if (c.nt == 0) return;
     unsigned short *list = s_list[w];
     // the sampled members of the run (their groups are looked at when a lane takes them)
@@ -461,18 +468,20 @@ template <int SB>
 __device__ __forceinline__ bool resolve_pair(const u32 *__restrict__ W, u32 n32, const u64 *__restrict__ etab, u32 x, u32 y, u32 &lcp, bool &x_less) {
     typedef Sym<SB> S;
     const u32 xo = x & (S::STEP - 1u);
-    const u32 cc = xo ? S::STEP - xo : 0u;  // the diagonal reaches its sampled position after cc matching symbols
+    const u32 cc = xo ? S::STEP - xo : 0u;  // the diagonal reaches its sampled position after cc matching symbols (a sampled x: at once)
     const u32 lenmin = n32 - y;
     const u32 bucket = (x + cc) >> (S::LOG_SPW + 2u);
     const u64 first = cc < lenmin ? etab[(size_t)bucket * ET_WAYS] : 0ull;  // in flight while the step below runs
-    if (xo == 0u && etab_find(etab, bucket, first, y, lcp, x_less)) return true;
-    if (fwd_compare<SB>(W, n32, x, y, 0u, S::STEP, lcp, x_less)) return true;  // one step
-    u32 l2;
-    if (xo != 0u && cc < lenmin && etab_find(etab, bucket, first, y + cc, l2, x_less)) {
-        lcp = cc + l2;
-        return true;
+    bool decided = fwd_compare<SB>(W, n32, x, y, 0u, S::STEP, lcp, x_less);  // one step
+    if (!decided && cc < lenmin) {
+        u32 l2;
+        if (etab_find(etab, bucket, first, y + cc, l2, x_less)) {
+            lcp = cc + l2;
+            decided = true;
+        }
     }
-    return fwd_compare<SB>(W, n32, x, y, S::STEP, (u32)SA_CMP_CAP, lcp, x_less);
+    if (!decided) decided = fwd_compare<SB>(W, n32, x, y, S::STEP, (u32)SA_CMP_CAP, lcp, x_less);
+    return decided;
 }
 
 // Every member of a small group meets each earlier member once; the larger suffix of a pair gains one smaller mate (-> its place
@@ -496,7 +505,8 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
     c.ssa = s_sa[w];
     u32 *ssa = c.ssa, *lcpv = s_lcp[w], *cnt = s_cnt[w], *sdef = s_def[w];
     unsigned char *sL = s_L[w];
-    pair_chunk_setup(c, keys, sa, n, s_head[w]);
+    u64 keyclz;
+    pair_chunk_setup(c, keys, sa, n, s_head[w], keyclz);
     const int nt = c.nt;
     const i64 s = c.s;
     if (lane == 0) chunk_start[(i64)blockIdx.x * PR_WARPS + w] = nt ? (int)s : -1;  // its LCP entry: sa_chunkhead_kernel
@@ -528,30 +538,43 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             const u32 inc = warp_incl_sum(cpairs);
             const u32 total = __shfl_sync(FULL, inc, 31);
             const u32 at = qn + inc - cpairs;
-            for (u32 d = 1; d <= cpairs; d++) plist[(at + d - 1u) & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | d);
+            // (groups of two to four members are the rule: their items are written without a loop)
+            if (cpairs >= 1u) plist[at & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | 1u);
+            if (cpairs >= 2u) plist[(at + 1u) & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | 2u);
+            if (cpairs >= 3u) plist[(at + 2u) & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | 3u);
+            for (u32 d = 4; d <= cpairs; d++) plist[(at + d - 1u) & (PL_CAP - 1)] = (unsigned short)(((u32)t << 4) | d);
             qn += total;
             __syncwarp();
         }
         // drain whole warps' worth (everything after the last round); a round adds at most 32 * 15 items, PL_CAP holds that plus a rest
         while (qn - next >= 32u || (r == rounds && qn != next)) {
             const u32 idx = next + lane;
-            if ((int)(qn - idx) > 0) {
+            bool have = (int)(qn - idx) > 0;
+            int tx = 0, ty = 0, t0 = 0;
+            if (have) {
                 const u32 it = plist[idx & (PL_CAP - 1)];
-                const int tx = (int)(it >> 4), ty = tx - (int)(it & 15u);
-                const int t0 = tx - (int)sL[tx];
-                if (!((sdef[t0 >> 5] >> (t0 & 31)) & 1u)) {  // else given up: stage 4 orders this group
-                    const u32 p = ssa[tx], q = ssa[ty];
-                    const u32 x = p < q ? p : q, y = p < q ? q : p;  // positions: x < y
-                    u32 lcp = 0;
-                    bool x_less = false;
-                    if (resolve_pair<SB>(W, n32, etab, x, y, lcp, x_less)) {
-                        const bool p_less = (p == x) == x_less;
-                        const int big = p_less ? ty : tx;  // the larger suffix gains a smaller mate
-                        atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
-                        atomicMax(&lcpv[big], lcp);
-                    } else {  // too long: let the doubling rounds order this group
-                        atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
-                    }
+                tx = (int)(it >> 4);
+                ty = tx - (int)(it & 15u);
+                t0 = tx - (int)sL[tx];
+                have = !((sdef[t0 >> 5] >> (t0 & 31)) & 1u);  // else given up: stage 4 orders this group
+            }
+            u32 lcp = 0;
+            bool p_less = false, ok = false;
+            if (have) {
+                const u32 p = ssa[tx], q = ssa[ty];
+                const u32 x = p < q ? p : q, y = p < q ? q : p;  // positions: x < y
+                bool x_less = false;
+                ok = resolve_pair<SB>(W, n32, etab, x, y, lcp, x_less);
+                p_less = (p == x) == x_less;
+            }
+            __syncwarp();  // the comparisons end at different times: the updates below are issued once for the whole warp
+            if (have) {
+                if (ok) {
+                    const int big = p_less ? ty : tx;  // the larger suffix gains a smaller mate
+                    atomicAdd(&cnt[big >> 2], 1u << (8 * (big & 3)));
+                    atomicMax(&lcpv[big], lcp);
+                } else {  // too long: let the doubling rounds order this group
+                    atomicOr(&sdef[t0 >> 5], 1u << (t0 & 31));
                 }
             }
             next += (qn - next) < 32u ? (qn - next) : 32u;
@@ -617,8 +640,7 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
             // leading digits of the two keys ARE the common prefix, provided no '$'/'N' (and not the end of the text) lies within
             // those symbols of either suffix -- two key loads and two looks at the cache-resident bitmap level instead of a
             // comparison on the text.
-            const u32 kc = (u32)keys[s + f], kp = (u32)keys[s + f - 1];
-            const u32 lk = (u32)(__clz((int)(kc ^ kp)) - (32 - 2 * key_digits2)) >> 1;
+            const u32 lk = (((u32)(keyclz >> (6 * (f >> 5))) & 63u) - (u32)(32 - 2 * key_digits2)) >> 1;  // f = 32 r + lane: this lane staged the slot
             if (a + lk + 1u <= n32 && b + lk + 1u <= n32 && first_barrier(bars, a, lk + 1u) == lk + 1u && first_barrier(bars, b, lk + 1u) == lk + 1u) {
                 LCP[s + f] = (int)lk;
                 continue;
