@@ -15,6 +15,7 @@
         auto rv_k_ = kern;                                                                 \
         emu::launch(#kern, dim3(grid), dim3(block), (size_t)(smem), [&]() { rv_k_(__VA_ARGS__); }); \
     } while (0)
+#define RV_LAUNCH_PDL RV_LAUNCH
 #define RV_DYN_SMEM(T, name) T *name = (T *)emu::S().dyn_smem
 #define RV_SPIN() rv_emu_spin()
 #else
@@ -24,6 +25,31 @@
         auto rv_k_ = kern;                                             \
         rv_k_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
     } while (0)
+// Programmatic dependent launch: the kernel may be made resident while its predecessor on the stream is still draining (its
+// blocks wait in grid_dep_wait(), the first statement of every kernel launched this way), which takes the launch latency and
+// the ramp of the first wave out of the gap between two kernels of a chain.  RV_PDL=0 builds plain launches.
+#ifndef RV_PDL
+#define RV_PDL 1
+#endif
+#if RV_PDL
+#define RV_LAUNCH_PDL(kern, grid_, block_, smem_, stream_, ...)                                   \
+    do {                                                                                        \
+        auto rv_k_ = kern;                                                                      \
+        cudaLaunchConfig_t rv_cfg_ = {};                                                        \
+        rv_cfg_.gridDim = dim3(grid_);                                                         \
+        rv_cfg_.blockDim = dim3(block_);                                                       \
+        rv_cfg_.dynamicSmemBytes = (size_t)(smem_);                                            \
+        rv_cfg_.stream = (stream_);                                                            \
+        cudaLaunchAttribute rv_at_[1];                                                          \
+        rv_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+        rv_at_[0].val.programmaticStreamSerializationAllowed = 1;                               \
+        rv_cfg_.attrs = rv_at_;                                                                 \
+        rv_cfg_.numAttrs = 1;                                                                   \
+        cudaLaunchKernelEx(&rv_cfg_, rv_k_, __VA_ARGS__);                                       \
+    } while (0)
+#else
+#define RV_LAUNCH_PDL RV_LAUNCH
+#endif
 #define RV_DYN_SMEM(T, name)                                    \
     extern __shared__ __align__(16) unsigned char name##_raw_[]; \
     T *name = (T *)name##_raw_
@@ -40,6 +66,15 @@ static const unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
+
+// first statement of a kernel that may be launched with RV_LAUNCH_PDL: everything the predecessor wrote is visible after it
+// (a no-op for a plain launch); then the successor, if it was launched the same way, may be made resident
+__device__ __forceinline__ void grid_dep_wait() {
+#if !defined(RV_EMU) && RV_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // volatile single-word global accesses for inter-block protocols
 __device__ __forceinline__ u32 ld_volatile(const u32 *p) { return *(const volatile u32 *)p; }

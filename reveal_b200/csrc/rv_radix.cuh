@@ -163,6 +163,7 @@ struct KeyBlock4 {
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src, RadixPlan plan, u32 *__restrict__ ghist) {
+    grid_dep_wait();
     __shared__ u32 sh[RS_MAXPASS * RS_BINS];
     __shared__ unsigned short s_code[256];
     s_code[threadIdx.x] = src.code[threadIdx.x];  // RS_THREADS == 256
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT *__restrict__ keys, i64 n, RadixPlan plan, u32 *__restrict__ ghist) {
+    grid_dep_wait();
     __shared__ u32 sh[RS_MAXPASS * RS_BINS];
     for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) sh[i] = 0;
     __syncthreads();
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT *__restr
 
 // one block per pass: exclusive scan of the 256 bucket counts
 __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const u32 *__restrict__ ghist, u32 *__restrict__ gbase) {
+    grid_dep_wait();
     __shared__ u32 scratch[33];
     u32 c = ghist[blockIdx.x * RS_BINS + threadIdx.x];
     u32 total;
@@ -231,6 +234,7 @@ template <typename KeyT, bool HAS_VAL, bool FROM_TEXT>
 __global__ void __launch_bounds__(RS_THREADS, RV_RS_MINBLOCKS)
 rs_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin, u32 *__restrict__ vout,
                i64 n, int shift, u32 mask, int dbits, const u32 *__restrict__ gbase, u32 *status, u32 *ticket, TextKeySrc src) {
+    grid_dep_wait();
     __shared__ u32 s_whist[RS_WARPS * RS_BINS];  // per-warp bucket counts -> running per-warp offsets inside the bucket
     __shared__ u32 s_start[RS_BINS];             // first tile-local slot of each bucket
     __shared__ u32 s_off[RS_BINS];               // global slot of a bucket's first item minus s_start (mod 2^32)
@@ -439,7 +443,7 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     } else {
         RV_LAUNCH((rs_hist_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st.s, k0, n, plan, ghist);
     }
-    RV_LAUNCH(rs_scan_kernel, plan.npass, RS_BINS, 0, st.s, ghist, gbase);
+    RV_LAUNCH_PDL(rs_scan_kernel, plan.npass, RS_BINS, 0, st.s, ghist, gbase);
     st.launches += 2;
     const size_t smem = (size_t)RS_TILE * (sizeof(KeyT) + 4);
     static bool attr_done[64] = {false};  // per device: a process may drive several GPUs (rv_set_device)
@@ -459,11 +463,11 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     RV_TRY(prof_begin(st, RV_PROF_RADIX_PASS));
     for (int p = 0; p < plan.npass; p++) {
         if (p == 0 && text) {
-            RV_LAUNCH((rs_pass_kernel<KeyT, true, true>), (unsigned)tiles, RS_THREADS, smem, st.s, (const KeyT *)nullptr, k1, (const u32 *)nullptr, v1, n,
+            RV_LAUNCH_PDL((rs_pass_kernel<KeyT, true, true>), (unsigned)tiles, RS_THREADS, smem, st.s, (const KeyT *)nullptr, k1, (const u32 *)nullptr, v1, n,
                       plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS, status + (size_t)p * tiles * RS_BINS, ticket + p,
                       *text);
         } else {
-            RV_LAUNCH((rs_pass_kernel<KeyT, true, false>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0, in0 ? v0 : v1,
+            RV_LAUNCH_PDL((rs_pass_kernel<KeyT, true, false>), (unsigned)tiles, RS_THREADS, smem, st.s, in0 ? k0 : k1, in0 ? k1 : k0, in0 ? v0 : v1,
                       in0 ? v1 : v0, n, plan.shift[p], plan.mask[p], mask_bits(plan.mask[p]), gbase + p * RS_BINS,
                       status + (size_t)p * tiles * RS_BINS, ticket + p, none);
         }

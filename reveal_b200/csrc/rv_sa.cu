@@ -405,6 +405,7 @@ __device__ __forceinline__ bool pair_chunk_group(const PairChunk &c, int t, int 
 template <typename KeyT, int SB>
 __global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
 sa_lead_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W, u64 *__restrict__ etab) {
+    grid_dep_wait();
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
     __shared__ u32 s_head[PR_WARPS][PR_ROUNDS + 2];
     __shared__ unsigned short s_list[PR_WARPS][PR_MAXT];
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(PR_THREADS, RV_PR_MINBLOCKS)
 sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n, const u32 *__restrict__ W, Barriers bars,
                 const u64 *__restrict__ etab, int *__restrict__ SA, int *__restrict__ rank, int *__restrict__ LCP, unsigned char *__restrict__ deferred,
                 u32 *__restrict__ flag_large, int *__restrict__ chunk_start, u32 *__restrict__ needbits, int key_digits2) {
+    grid_dep_wait();
     __shared__ u32 s_sa[PR_WARPS][PR_MAXT];
     __shared__ u32 s_lcp[PR_WARPS][PR_MAXT];
     __shared__ u32 s_cnt[PR_WARPS][PR_MAXT / 4];        // one byte per slot: smaller mates seen so far
@@ -654,6 +656,7 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
 __global__ void __launch_bounds__(256)
 sa_chunkhead_kernel(const int *__restrict__ chunk_start, i64 nchunks, i64 n, const unsigned char *__restrict__ T, Barriers bars,
                     const int *__restrict__ SA, int *__restrict__ LCP, u32 *__restrict__ needbits) {
+    grid_dep_wait();
     i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     int j = chunk_start[c];
@@ -682,6 +685,7 @@ static const int LS_WORDS = 2;
 template <int SB>
 __global__ void __launch_bounds__(128)
 lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict__ W, Barriers bars, const int *__restrict__ SA, const int *__restrict__ ISA, int *__restrict__ LCP) {
+    grid_dep_wait();
     typedef Sym<SB> S;
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 w0 = t * LS_WORDS, nwords = (n + 31) / 32;
@@ -738,6 +742,7 @@ lcp_sparse_kernel(const u32 *__restrict__ needbits, i64 n, const u32 *__restrict
 // key[e] = rank[sa[e]] : (rank[sa[e]+h]+1, or 0 when the suffix ends first)
 __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ grp, const int *__restrict__ rank,
                                                        i64 A, i64 n, i64 h, u64 *__restrict__ keys) {
+    grid_dep_wait();
     i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A) return;
     i64 p = (i64)sa[e] + h;
@@ -751,6 +756,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const u32 *__restrict__ 
 // the groups that reach stage 4 are refined by the true symbols of those positions.
 __global__ void __launch_bounds__(256) sa_exact_gather_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ grp, const unsigned char *__restrict__ T,
                                                              CodeTable tab, i64 A, i64 n, i64 off, int kx, u32 xbase, u64 *__restrict__ keys) {
+    grid_dep_wait();
     __shared__ unsigned short s_code[256];
     s_code[threadIdx.x] = tab.code[threadIdx.x];
     __syncthreads();
@@ -778,6 +784,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, i64 A, int G,
                                                                const unsigned char *__restrict__ deferred,
                                                                u32 *__restrict__ tile_max, u32 *__restrict__ tile_cnt) {
+    grid_dep_wait();
     __shared__ u32 s1[33], s2[33];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
     u32 mx = 0, cnt = 0;
@@ -802,6 +809,7 @@ __global__ void __launch_bounds__(AP_THREADS) sa_reduce_kernel(const KeyT *__res
 
 // single block: exclusive max-scan / sum-scan over the tile aggregates; total -> *out_total
 __global__ void __launch_bounds__(1024) sa_tilescan_kernel(u32 *__restrict__ tile_max, u32 *__restrict__ tile_cnt, i64 tiles, u32 *__restrict__ out_total) {
+    grid_dep_wait();
     __shared__ u32 s1[33], s2[33];
     __shared__ u32 s_im[1024];
     u32 carry_max = 0, carry_sum = 0;
@@ -836,6 +844,7 @@ sa_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, const
                 const unsigned char *__restrict__ deferred, const u32 *__restrict__ tile_max, const u32 *__restrict__ tile_cnt,
                 int *__restrict__ SA, int *__restrict__ rank, u32 *__restrict__ sa2, u32 *__restrict__ pos2, u32 *__restrict__ grp2,
                 u32 *__restrict__ needbits) {
+    grid_dep_wait();
     __shared__ u32 s1[33], s2[33];
     __shared__ u32 s_im[AP_THREADS];
     i64 base = (i64)blockIdx.x * AP_TILE + (i64)threadIdx.x * AP_IPT;
@@ -969,17 +978,17 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     const u32 *W = packed ? (const u32 *)B.packed : (const u32 *)dT;
     RV_TRY(prof_begin(st, RV_PROF_LEAD));
     if (packed) {
-        RV_LAUNCH((sa_lead_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
+        RV_LAUNCH_PDL((sa_lead_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
     } else {
-        RV_LAUNCH((sa_lead_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
+        RV_LAUNCH_PDL((sa_lead_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, B.etab);
     }
     RV_TRY(prof_end(st, RV_PROF_LEAD, 1, (long long)n * (long long)(sizeof(KeyT) + 4)));
     RV_TRY(prof_begin(st, RV_PROF_PAIRS));
     if (packed) {
-        RV_LAUNCH((sa_place_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
+        RV_LAUNCH_PDL((sa_place_kernel<KeyT, 4>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
                   B.small + 257, B.chunk_start, B.needbits, key_digits2);
     } else {
-        RV_LAUNCH((sa_place_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
+        RV_LAUNCH_PDL((sa_place_kernel<KeyT, 8>), pblocks, PR_THREADS, 0, st.s, keys, sa, n, W, bars, (const u64 *)B.etab, dSA, dISA, dLCP, B.deferred,
                   B.small + 257, B.chunk_start, B.needbits, key_digits2);
     }
     RV_TRY(prof_end(st, RV_PROF_PAIRS, 1, (long long)n * (long long)(sizeof(KeyT) + 4 + 12)));
@@ -987,7 +996,7 @@ static int sort_and_compare(Stream &st, const SaBuffers &B, const unsigned char 
     {   // the chunk-head LCP pass is enqueued before anyone knows whether stage 4 is needed: slots that stage 4 still has to
         // fill read -1 and the entry is left to lcp_sparse_kernel
         const i64 nchunks = ((n + pr_per_block - 1) / pr_per_block) * PR_WARPS;
-        RV_LAUNCH(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, bars, dSA, dLCP, B.needbits);
+        RV_LAUNCH_PDL(sa_chunkhead_kernel, (unsigned)((nchunks + 255) / 256), 256, 0, st.s, B.chunk_start, nchunks, n, dT, bars, dSA, dLCP, B.needbits);
         st.launches++;
     }
     RV_KCHECK();
@@ -1021,15 +1030,15 @@ static int doubling(Stream &st, const SaBuffers &B, const unsigned char *dT, con
     for (int round = 0;; round++) {
         const i64 tiles = (A + AP_TILE - 1) / AP_TILE;
         if (round == 0) {
-            RV_LAUNCH((sa_reduce_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, pos, A, SA_SMALL_G, B.deferred, B.tile_max, B.tile_cnt);
-            RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
-            RV_LAUNCH((sa_apply_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, sa, pos, A, SA_SMALL_G, B.deferred, B.tile_max,
+            RV_LAUNCH_PDL((sa_reduce_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, pos, A, SA_SMALL_G, B.deferred, B.tile_max, B.tile_cnt);
+            RV_LAUNCH_PDL(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
+            RV_LAUNCH_PDL((sa_apply_kernel<KeyT>), (unsigned)tiles, AP_THREADS, 0, st.s, keys0, sa, pos, A, SA_SMALL_G, B.deferred, B.tile_max,
                       B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next, B.needbits);
         } else {
-            RV_LAUNCH((sa_reduce_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
+            RV_LAUNCH_PDL((sa_reduce_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
                       B.tile_cnt);
-            RV_LAUNCH(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
-            RV_LAUNCH((sa_apply_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
+            RV_LAUNCH_PDL(sa_tilescan_kernel, 1, 1024, 0, st.s, B.tile_max, B.tile_cnt, tiles, B.small + 256);
+            RV_LAUNCH_PDL((sa_apply_kernel<u64>), (unsigned)tiles, AP_THREADS, 0, st.s, keys, sa, pos, A, 1, (const unsigned char *)nullptr, B.tile_max,
                       B.tile_cnt, dSA, dISA, sa_alt, pos_next, grp_next, (u32 *)nullptr);
         }
         st.launches += 3;
@@ -1052,12 +1061,12 @@ static int doubling(Stream &st, const SaBuffers &B, const unsigned char *dT, con
         grp_next = (grp == B.grpA) ? B.grpB : B.grpA;
         RadixPlan plan;
         if (covered < k) {  // exact refinement of the symbols [covered, covered + kx)
-            RV_LAUNCH(sa_exact_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dT, tab, A, n, covered, kx, xbase, keys);
+            RV_LAUNCH_PDL(sa_exact_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dT, tab, A, n, covered, kx, xbase, keys);
             plan = make_plan(0, xbits, 32, 32 + nbits);
             covered += kx;
             h = covered;
         } else {
-            RV_LAUNCH(sa_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dISA, A, n, h, keys);
+            RV_LAUNCH_PDL(sa_gather_kernel, (unsigned)((A + 255) / 256), 256, 0, st.s, sa, grp, dISA, A, n, h, keys);
             plan = make_plan(0, nbits, 32, 32 + nbits);
             h *= 2;
         }
@@ -1254,9 +1263,9 @@ int sa_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, int *dSA, in
         const Barriers bars = {B.bar, B.bar1, B.bar2};
         RV_TRY(prof_begin(st, RV_PROF_LCP));
         if (packed) {
-            RV_LAUNCH((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, bars, dSA, dISA, dLCP);
+            RV_LAUNCH_PDL((lcp_sparse_kernel<4>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)B.packed, bars, dSA, dISA, dLCP);
         } else {
-            RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
+            RV_LAUNCH_PDL((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, B.needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
         }
         RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)first_active * 13 + n / 8));
         st.launches++;
@@ -1285,7 +1294,7 @@ int lcp_build(Stream &st, Arena &ws, const unsigned char *dT, i64 n, const int *
     RV_CUDA(cudaMemsetAsync(needbits, 0xff, (size_t)(n / 32 + 2) * 4, st.s));
     const i64 lthreads = ((n + 31) / 32 + LS_WORDS - 1) / LS_WORDS;
     RV_TRY(prof_begin(st, RV_PROF_LCP));
-    RV_LAUNCH((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
+    RV_LAUNCH_PDL((lcp_sparse_kernel<8>), (unsigned)((lthreads + 127) / 128), 128, 0, st.s, needbits, n, (const u32 *)dT, bars, dSA, dISA, dLCP);
     RV_TRY(prof_end(st, RV_PROF_LCP, 1, (long long)n * 13));
     st.launches += 2;
     RV_KCHECK();

@@ -25,94 +25,64 @@ static const int SW_CHUNKS = 4;
 static const int SW_TILE = SW_THREADS * SW_CHUNKS;
 
 // count pass: per-tile number of hits + one hit bit per slot (a word per 32 slots), so that the write pass only touches the
-// (sparse) hits.  A block takes PC_TPB tiles; a thread takes 4 CONSECUTIVE slots of each: their LCP and SA entries arrive as
-// 128-bit loads that are ALL issued before anything is tested (2 * PC_TPB * 16 bytes in flight per thread; one tile per block --
-// 32 bytes per thread and a block-wide scan behind them -- left HBM idle half of a block's life), the entries of the slots to
-// the left and right come from the neighbouring lanes, and the text gathers of the slots that pass the LCP / sample tests go
-// out together.  The tile totals are a warp sum + one shared-memory add per warp for all PC_TPB tiles at once.
-static const int PC_TPB = 4;
-__global__ void __launch_bounds__(SW_THREADS) pair_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u32 *__restrict__ hitbits, i64 tiles) {
-    __shared__ u32 s_tot[PC_TPB];
-    if (threadIdx.x < PC_TPB) s_tot[threadIdx.x] = 0u;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
+// (sparse) hits.  A thread takes 4 CONSECUTIVE slots: their LCP and SA entries arrive as two 128-bit loads issued before anything
+// is tested (32 bytes in flight per thread keep HBM busy; one 4-byte load per thread and test did not), then the text gathers of
+// the slots that pass the LCP / sample tests go out together.
+__global__ void __launch_bounds__(SW_THREADS) pair_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u32 *__restrict__ hitbits) {
+    grid_dep_wait();
+    __shared__ u64 scratch[33];
+    const i64 i0 = (i64)blockIdx.x * SW_TILE + (i64)threadIdx.x * SW_CHUNKS;  // SW_CHUNKS == 4
+    u32 h = 0;  // bit j: slot i0 + j is a hit
     const bool vec = ((((size_t)p.SA) | ((size_t)p.LCP)) & 15u) == 0;
-    int4 lv[PC_TPB], sv[PC_TPB];
-    bool full[PC_TPB];
+    if (vec && i0 + 4 <= p.n) {
+        const int4 lv = *(const int4 *)(p.LCP + i0);
+        const int4 sv = *(const int4 *)(p.SA + i0);
+        const int lprev = i0 > 0 ? p.LCP[i0 - 1] : 0;
+        const int sprev = i0 > 0 ? p.SA[i0 - 1] : 0;
+        const int lnext = i0 + 4 < p.n ? p.LCP[i0 + 4] : (int)0x80000000;  // no slot after the last one (pair_candidate)
+        const int l[6] = {lprev, lv.x, lv.y, lv.z, lv.w, lnext};
+        const int s[5] = {sprev, sv.x, sv.y, sv.z, sv.w};
+        bool cand[4];
+        i64 a[4], b[4];
 #pragma unroll
-    for (int c = 0; c < PC_TPB; c++) {
-        const i64 i0 = ((i64)blockIdx.x * PC_TPB + c) * SW_TILE + (i64)threadIdx.x * SW_CHUNKS;  // SW_CHUNKS == 4
-        full[c] = vec && i0 + 4 <= p.n;
-        lv[c] = full[c] ? *(const int4 *)(p.LCP + i0) : make_int4(0, 0, 0, 0);
-        sv[c] = full[c] ? *(const int4 *)(p.SA + i0) : make_int4(0, 0, 0, 0);
-    }
-    u32 packed_cnt = 0;  // hits of tile c in bits [8c, 8c+8) (at most 4 per thread, 128 per warp)
-#pragma unroll
-    for (int c = 0; c < PC_TPB; c++) {
-        const i64 tile = (i64)blockIdx.x * PC_TPB + c;
-        const i64 i0 = tile * SW_TILE + (i64)threadIdx.x * SW_CHUNKS;
-        // the slot before the thread's first and the one after its last: held by the neighbouring lanes (whole warps shuffle)
-        int lprev = __shfl_up_sync(FULL, lv[c].w, 1), sprev = __shfl_up_sync(FULL, sv[c].w, 1);
-        int lnext = __shfl_down_sync(FULL, lv[c].x, 1);
-        const bool next_full = __shfl_down_sync(FULL, full[c] ? 1 : 0, 1) != 0;
-        u32 h = 0;  // bit j: slot i0 + j is a hit
-        if (full[c]) {
-            if (lane == 0) {
-                lprev = i0 > 0 ? p.LCP[i0 - 1] : 0;
-                sprev = i0 > 0 ? p.SA[i0 - 1] : 0;
-            }
-            if (lane == 31 || !next_full) lnext = i0 + 4 < p.n ? p.LCP[i0 + 4] : (int)0x80000000;  // no slot after the last one (pair_candidate)
-            const int l[6] = {lprev, lv[c].x, lv[c].y, lv[c].z, lv[c].w, lnext};
-            const int sx[5] = {sprev, sv[c].x, sv[c].y, sv[c].z, sv[c].w};
-            bool cand[4];
-            i64 a[4], b[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int li = l[j + 1];
-                cand[j] = i0 + j >= 1 && li >= p.minl && li > 0 && l[j] < li && l[j + 2] < li && (((i64)sx[j + 1] > p.nsep0) != ((i64)sx[j] > p.nsep0));
-                a[j] = sx[j + 1] < sx[j] ? sx[j + 1] : sx[j];
-                b[j] = sx[j + 1] < sx[j] ? sx[j] : sx[j + 1];
-            }
-            unsigned char ca[4], cb[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool g = cand[j] && a[j] > 0 && b[j] > 0;
-                ca[j] = g ? p.T[a[j] - 1] : (unsigned char)0;
-                cb[j] = g ? p.T[b[j] - 1] : (unsigned char)1;  // (no gather: left-maximal, as in left_maximal())
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (cand[j] && (ca[j] != cb[j] || ca[j] == 'N' || ca[j] == '$' || is_lower(ca[j]))) h |= 1u << j;
-        } else if (tile < tiles) {  // the last slots of the arrays, or arrays that are not 16-byte aligned
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                i64 l, a, b;
-                if (pair_test(p, i0 + j, l, a, b)) h |= 1u << j;
-            }
+        for (int j = 0; j < 4; j++) {
+            const int li = l[j + 1];
+            cand[j] = i0 + j >= 1 && li >= p.minl && li > 0 && l[j] < li && l[j + 2] < li && (((i64)s[j + 1] > p.nsep0) != ((i64)s[j] > p.nsep0));
+            a[j] = s[j + 1] < s[j] ? s[j + 1] : s[j];
+            b[j] = s[j + 1] < s[j] ? s[j] : s[j + 1];
         }
-        // hit word of 32 slots = the nibbles of 8 neighbouring lanes
-        u32 word = h << (4u * (threadIdx.x & 7u));
-        word |= __shfl_xor_sync(FULL, word, 1);
-        word |= __shfl_xor_sync(FULL, word, 2);
-        word |= __shfl_xor_sync(FULL, word, 4);
-        if ((threadIdx.x & 7u) == 0 && tile < tiles) hitbits[i0 >> 5] = word;  // (the bitmap is padded to whole tiles)
-        packed_cnt |= (u32)__popc(h) << (8 * c);
-    }
-    const u32 wsum = warp_incl_sum(packed_cnt);  // no field overflows: 32 lanes * 4 hits
-    if (lane == 31) {
+        unsigned char ca[4], cb[4];
 #pragma unroll
-        for (int c = 0; c < PC_TPB; c++) atomicAdd(&s_tot[c], (wsum >> (8 * c)) & 0xffu);
+        for (int j = 0; j < 4; j++) {
+            const bool g = cand[j] && a[j] > 0 && b[j] > 0;
+            ca[j] = g ? p.T[a[j] - 1] : (unsigned char)0;
+            cb[j] = g ? p.T[b[j] - 1] : (unsigned char)1;  // (no gather: left-maximal, as in left_maximal())
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cand[j] && (ca[j] != cb[j] || ca[j] == 'N' || ca[j] == '$' || is_lower(ca[j]))) h |= 1u << j;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            i64 l, a, b;
+            if (pair_test(p, i0 + j, l, a, b)) h |= 1u << j;
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < PC_TPB) {
-        const i64 tile = (i64)blockIdx.x * PC_TPB + threadIdx.x;
-        if (tile < tiles) tile_rec[tile] = (u64)s_tot[threadIdx.x];
-    }
+    // hit word of 32 slots = the nibbles of 8 neighbouring lanes
+    u32 word = h << (4u * (threadIdx.x & 7u));
+    word |= __shfl_xor_sync(FULL, word, 1);
+    word |= __shfl_xor_sync(FULL, word, 2);
+    word |= __shfl_xor_sync(FULL, word, 4);
+    if ((threadIdx.x & 7u) == 0) hitbits[i0 >> 5] = word;  // (the bitmap is padded to whole tiles)
+    u64 total;
+    block_incl_sum<SW_THREADS, u64>((u64)__popc(h), scratch, &total);
+    if (threadIdx.x == 0) tile_rec[blockIdx.x] = total;
 }
 
 // write pass: one warp per tile of SW_TILE slots (= 32 ballot words, one per lane)
 __global__ void __launch_bounds__(SW_THREADS) pair_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u32 *__restrict__ hitbits,
                                                                 i64 tiles, i64 *__restrict__ out, i64 cap) {
+    grid_dep_wait();
     const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
     if (tile >= tiles) return;  // warp-uniform
     const unsigned lane = threadIdx.x & 31u;
@@ -143,6 +113,7 @@ __global__ void __launch_bounds__(SW_THREADS) pair_write_kernel(SweepArgs p, con
 // with their gathers run with every lane busy instead of the 10 of 32 a slot-per-thread mapping leaves active.
 __global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem,
                                                                  u32 *__restrict__ hitbits) {
+    grid_dep_wait();
     __shared__ u64 s1[33], s2[33];
     __shared__ u32 s3[33];
     __shared__ unsigned short s_list[SW_TILE];
@@ -194,6 +165,7 @@ __global__ void __launch_bounds__(SW_THREADS) multi_count_kernel(SweepArgs p, u6
 __global__ void __launch_bounds__(SW_THREADS)
 multi_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u64 *__restrict__ tile_mem, const u32 *__restrict__ hitbits, i64 tiles,
                    i64 *__restrict__ hdr, i64 hdr_cap, i64 *__restrict__ members, i64 mem_cap) {
+    grid_dep_wait();
     const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
     if (tile >= tiles) return;  // warp-uniform
     const unsigned lane = threadIdx.x & 31u;
@@ -230,6 +202,7 @@ multi_write_kernel(SweepArgs p, const u64 *__restrict__ tile_rec, const u64 *__r
 // ---- multi-MEM sweep: one thread per segment start (see mem_walk) ----------------------------------------------
 __global__ void __launch_bounds__(SW_THREADS) mems_count_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb,
                                                                 u64 *__restrict__ tile_rec, u64 *__restrict__ tile_mem, u32 *__restrict__ hitbits) {
+    grid_dep_wait();
     __shared__ u64 s1[33], s2[33];
     u64 nr = 0, nm = 0;
     for (int c = 0; c < SW_CHUNKS; c++) {
@@ -251,6 +224,7 @@ __global__ void __launch_bounds__(SW_THREADS) mems_count_kernel(SweepArgs p, int
 __global__ void __launch_bounds__(SW_THREADS)
 mems_write_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb, const u64 *__restrict__ tile_rec, const u64 *__restrict__ tile_mem,
                   const u32 *__restrict__ hitbits, i64 tiles, i64 *__restrict__ hdr, i64 hdr_cap, i64 *__restrict__ members, i64 mem_cap) {
+    grid_dep_wait();
     const i64 tile = (i64)blockIdx.x * (SW_THREADS / 32) + (threadIdx.x >> 5);
     if (tile >= tiles) return;  // warp-uniform
     const unsigned lane = threadIdx.x & 31u;
@@ -288,6 +262,7 @@ mems_write_kernel(SweepArgs p, int *__restrict__ st_l, int *__restrict__ st_lb, 
 // (all its loads in flight at once, a serial sum in registers), so a text of 8 million slots is one block-wide scan instead of eight.
 static const int TS_K = 8;
 __global__ void __launch_bounds__(1024) sweep_tilescan_kernel(u64 *__restrict__ a, u64 *__restrict__ b, i64 tiles, u64 *__restrict__ out) {
+    grid_dep_wait();
     __shared__ u64 s1[33], s2[33];
     u64 ca = 0, cb = 0;
     for (i64 b0 = 0; b0 < tiles; b0 += 1024 * TS_K) {
@@ -343,9 +318,9 @@ int sweep_pair_count(Stream &st, const SweepArgs &p, void *scratch, i64 *count, 
     u64 *tile_rec = (u64 *)scratch;
     u64 *totals = tile_rec + 2 * tiles;
     RV_TRY(prof_begin(st, RV_PROF_SWEEP));
-    RV_LAUNCH(pair_count_kernel, (unsigned)((tiles + PC_TPB - 1) / PC_TPB), SW_THREADS, 0, st.s, p, tile_rec, (u32 *)(tile_rec + 2 * tiles + 8), tiles);
+    RV_LAUNCH(pair_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 9));
-    RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, (u64 *)nullptr, tiles, totals);
+    RV_LAUNCH_PDL(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, (u64 *)nullptr, tiles, totals);
     st.launches += 2;
     u64 *h = (u64 *)(st.pinned + 304);  // pinned: the read-back is asynchronous and the speculative write pass is enqueued before the host waits
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
@@ -362,7 +337,7 @@ int sweep_pair_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_out, 
     RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     const u64 *tile_rec = (const u64 *)scratch;
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
-    RV_LAUNCH(pair_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_out, cap);
+    RV_LAUNCH_PDL(pair_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_out, cap);
     // the sparse pass reads one hit bit per slot and a tile offset per 1024 slots; the rows it writes are booked by the caller
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)(p.n / 8 + tiles * 8)));
     st.launches++;
@@ -380,7 +355,7 @@ int sweep_multi_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, 
     RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     RV_LAUNCH(multi_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (u32 *)(tile_rec + 2 * tiles + 8));
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)p.n * 11));
-    RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
+    RV_LAUNCH_PDL(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
     st.launches += 2;
     u64 *h = (u64 *)(st.pinned + 304);
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
@@ -399,7 +374,7 @@ int sweep_multi_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr,
     const u64 *tile_rec = (const u64 *)scratch, *tile_mem = tile_rec + tiles;
     RV_TRY(prof_begin(st, RV_PROF_SWEEP));
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
-    RV_LAUNCH(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
+    RV_LAUNCH_PDL(multi_write_kernel, wblocks, SW_THREADS, 0, st.s, p, tile_rec, tile_mem, (const u32 *)(tile_rec + 2 * tiles + 8), tiles, d_hdr, hdr_cap,
               d_mem, mem_cap);
     RV_TRY(prof_end(st, RV_PROF_SWEEP, 1, (long long)(p.n / 8 + tiles * 16)));
     st.launches++;
@@ -434,7 +409,7 @@ int sweep_mems_count(Stream &st, const SweepArgs &p, void *scratch, i64 *nrec, i
     i64 tiles;
     mems_layout(scratch, p.n, &tile_rec, &tile_mem, &totals, &hitbits, &st_l, &st_lb, &tiles);
     RV_LAUNCH(mems_count_kernel, (unsigned)tiles, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits);
-    RV_LAUNCH(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
+    RV_LAUNCH_PDL(sweep_tilescan_kernel, 1, 1024, 0, st.s, tile_rec, tile_mem, tiles, totals);
     st.launches += 2;
     u64 *h = (u64 *)(st.pinned + 304);
     RV_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, st.s));
@@ -452,7 +427,7 @@ int sweep_mems_write(Stream &st, const SweepArgs &p, void *scratch, i64 *d_hdr, 
     i64 tiles;
     mems_layout(scratch, p.n, &tile_rec, &tile_mem, &totals, &hitbits, &st_l, &st_lb, &tiles);
     const unsigned wblocks = (unsigned)((tiles + SW_THREADS / 32 - 1) / (SW_THREADS / 32));
-    RV_LAUNCH(mems_write_kernel, wblocks, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits, tiles, d_hdr, hdr_cap, d_mem, mem_cap);
+    RV_LAUNCH_PDL(mems_write_kernel, wblocks, SW_THREADS, 0, st.s, p, st_l, st_lb, tile_rec, tile_mem, hitbits, tiles, d_hdr, hdr_cap, d_mem, mem_cap);
     st.launches++;
     RV_KCHECK();
     return RV_OK;

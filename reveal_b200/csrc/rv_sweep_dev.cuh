@@ -162,6 +162,7 @@ template <class F> __device__ __forceinline__ void multi_visit(const SweepArgs &
 }
 
 
+
 // ---- multi-MEM walk (getmultimems, reveal.c:292-434 + ismultimem :261-290) --------------------------------
 // The reference's lcp-interval stack walk reports intervals of ANY size whose members cover >= minn samples, and
 // its `continue` at reveal.c:340-342 (taken when an interval is a multi-MEM of too few samples) skips the
