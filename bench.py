@@ -527,6 +527,9 @@ def run_ours(args, rank, world, local_rank):
                     out.append({"kernel": name, "launches": int(pr.launches[k]), "avg_launch_ms": pr.ms[k] / pr.launches[k],
                                 "achieved": gbs, "frac": gbs / peak, "share_of_step": pr.ms[k] / total_ms,
                                 "algorithmic_bytes_per_launch": pr.bytes[k] / pr.launches[k], "measured": where})
+                    if name == "text passes":  # (10.7 us when ncu runs it alone: profiles/)
+                        out[-1]["note"] = "side stream, beside the digit passes of the sort: elapsed time under contention, not on the critical path"
+
             out.sort(key=lambda d: -d["share_of_step"])
             return out
         timed = rows_of(prof, dev_ms, "inside the timed region (the only kernel bracketed there)")

@@ -183,27 +183,6 @@ static inline PyObject *atomic_tuple(PyObject *t) {
     return t;
 }
 
-// Match lengths repeat all over a result list (tens of thousands of MUMs, a few hundred distinct lengths): one int object per
-// length and list instead of one per record -- a fifth of the objects of a getmums() list, and of the work of releasing it.
-struct LengthInts {
-    enum { CAP = 4096 };
-    PyObject *v[CAP];
-    bool on;  // (short lists -- one per recursion step -- are not worth clearing the table for)
-    explicit LengthInts(int64_t records) : on(records >= 1024) {
-        if (on) memset(v, 0, sizeof v);
-    }
-    ~LengthInts() {
-        if (on)
-            for (int i = 0; i < CAP; i++) Py_XDECREF(v[i]);
-    }
-    PyObject *get(long long l) {  // new reference
-        if (!on || l < 0 || l >= CAP) return PyLong_FromLongLong(l);
-        if (!v[l]) v[l] = PyLong_FromLongLong(l);
-        Py_XINCREF(v[l]);
-        return v[l];
-    }
-};
-
 static Index *root_of(Index *self) { return self->mainidx ? self->mainidx : self; }
 
 static int ensure_handle(Index *self) {
@@ -414,7 +393,6 @@ static int need_arrays(Index *self) {
 // ---- sweeps ------------------------------------------------------------------------------------------------------------------
 static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vector<int64_t> &mem, int64_t nrec, int64_t nmem, bool counts_are_sizes) {
     GcPause gc_pause;
-    LengthInts lens(nrec);
     PyObject *lst = PyList_New((Py_ssize_t)nrec);
     if (!lst) return nullptr;
     for (int64_t k = 0; k < nrec; k++) {
@@ -428,7 +406,7 @@ static PyObject *multi_to_list(const std::vector<int64_t> &hdr, const std::vecto
             PyTuple_SET_ITEM(members, (Py_ssize_t)(x - first), sp);
         }
         PyObject *rec = atomic_tuple(PyTuple_New(3));  // (l, n, ((sample, position), ...)): reveal.c:497 / :353
-        PyTuple_SET_ITEM(rec, 0, lens.get((long long)l));
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)l));
         PyTuple_SET_ITEM(rec, 1, PyLong_FromLong((long)cnt));
         PyTuple_SET_ITEM(rec, 2, members);
         PyList_SET_ITEM(lst, (Py_ssize_t)k, rec);
@@ -463,7 +441,6 @@ static PyObject *index_getmums(Index *self, PyObject *args) {
         if (fail_native(g_api.rv_mums_pair_fetch(self->h, rows.data(), k)) != 0) return nullptr;
     }
     GcPause gc_pause;
-    LengthInts lens(k);
     PyObject *lst = PyList_New((Py_ssize_t)k);
     if (!lst) return nullptr;
     PyObject *rcobj = PyLong_FromLong(self->rc);
@@ -471,7 +448,7 @@ static PyObject *index_getmums(Index *self, PyObject *args) {
         PyObject *ab = atomic_tuple(PyTuple_New(2)), *rec = atomic_tuple(PyTuple_New(3));
         PyTuple_SET_ITEM(ab, 0, PyLong_FromLongLong((long long)rows[3 * i + 1]));
         PyTuple_SET_ITEM(ab, 1, PyLong_FromLongLong((long long)rows[3 * i + 2]));
-        PyTuple_SET_ITEM(rec, 0, lens.get((long long)rows[3 * i]));
+        PyTuple_SET_ITEM(rec, 0, PyLong_FromLongLong((long long)rows[3 * i]));
         PyTuple_SET_ITEM(rec, 1, ab);
         Py_INCREF(rcobj);
         PyTuple_SET_ITEM(rec, 2, rcobj);
