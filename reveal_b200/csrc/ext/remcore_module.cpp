@@ -20,7 +20,13 @@
 #include <string>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <pthread.h>
 #include <deque>
 #include <map>
 #include <unordered_map>
@@ -168,7 +174,7 @@ static void remove_node(Graph *g, int id) {
     Py_CLEAR(n.extra);
 }
 
-static int node_at(Graph *g, int64_t pos) {
+static int node_at(const Graph *g, int64_t pos) {
     auto it = g->tracked->upper_bound(pos);
     if (it == g->tracked->begin()) return -1;
     --it;
@@ -878,21 +884,56 @@ struct PickJob {
     bool need_dp = false;   // start / length / gain hold a recurrence of m + 1 rows; link / score are to be filled
     bool dp_done = false;
     int split = -1;
+    // pick_parse -> pick_build: the bounding nodes as node ids (-1: None; -3: not found, the pending KeyError is kept in bound_err)
+    int bound_id[2] = {-1, -1};
+    PyObject *bound_err[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    // pick_build runs without the Python API (possibly on a worker thread): what it has to say waits here
+    int err = 0;            // 1 KeyError, 2 ValueError
+    int err_bound = -1;     // side whose kept KeyError is to be raised
+    std::string err_msg;
+    double pk[6] = {0, 0, 0, 0, 0, 0};
+    ~PickJob() {
+        for (auto &e : bound_err)
+            for (PyObject *o : e) Py_XDECREF(o);
+    }
 };
 
-// 1: go on (run the recurrence if need_dp, then pick_finish); 0: the answer is the empty tuple; -1: error set
 static double pk_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static double g_pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
+// The part of the preparation that reads Python objects: the anchors of the list and the node ids of the two bounds.
+static int pick_parse(Graph *g, PyObject *list, PickJob &J) {
+    const double t0 = pk_now();
+    if (!parse_mums(list, J.all)) return -1;
+    for (int side = 0; side < 2; side++) {
+        PyObject *bound = side == 0 ? J.leftnode : J.rightnode;
+        if (bound == Py_None) { J.bound_id[side] = -1; continue; }
+        const int id = find_node(g, bound);
+        if (id < 0) {  // raised only if the preparation gets as far as the bounds (like the one-piece flow did)
+            PyErr_Fetch(&J.bound_err[side][0], &J.bound_err[side][1], &J.bound_err[side][2]);
+            J.bound_id[side] = -3;
+        } else {
+            J.bound_id[side] = id;
+        }
+    }
+    J.pk[0] += pk_now() - t0;
+    return 1;
+}
+static int pick_fail(PickJob &J, int kind, const char *fmt, long long a = 0) {
+    char buf[160];
+    snprintf(buf, sizeof buf, fmt, a);
+    J.err = kind;
+    J.err_msg = buf;
+    return -1;
+}
+// The rest of it: no Python API, nothing of the graph is written -- the jobs of a frontier batch run side by side on the
+// threads of the pool.  -1: J.err / J.err_bound say what to raise (pick_raise).
+static int pick_build(const Graph *g, PickJob &J) {
     double pk_t = pk_now(), pk_u;
-#define PK_MARK(i) pk_u = pk_now(); g_pk[i] += pk_u - pk_t; pk_t = pk_u;
+#define PK_MARK(i) pk_u = pk_now(); J.pk[i] += pk_u - pk_t; pk_t = pk_u;
     const long nsamples = J.nsamples, maxmums = J.maxmums;
     const int trim = J.trim;
     const long long wscore = J.wscore;
-    PyObject *leftnode = J.leftnode, *rightnode = J.rightnode;
     std::vector<Mum> &all = J.all, &picked = J.picked;
-    if (!parse_mums(list, all)) return -1;
-    PK_MARK(0)
     {
         size_t full = 0;
         for (auto &m : all)
@@ -952,7 +993,7 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
         r.src = (int)i;
         for (auto &p : picked[i].sp) {
             int id = node_at(g, p.second);
-            if (id < 0) { PyErr_Format(PyExc_KeyError, "no node covers index position %lld", (long long)p.second); return -1; }
+            if (id < 0) return pick_fail(J, 1, "no node covers index position %lld", (long long)p.second);
             const Node &nd = (*g->nodes)[id];
             const int64_t shift = p.second - nd.begin;
             for (auto &kv : nd.offsets) {
@@ -1002,25 +1043,28 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
     std::vector<int32_t> &keys = J.keys;
     for (auto &kv : rel.back().point) keys.push_back(kv.first);
     const size_t k = J.k = keys.size();
-    if (k == 0 || k > 64) { PyErr_SetString(PyExc_ValueError, "anchor over no path or over more than 64 paths"); return -1; }
+    if (k == 0 || k > 64) return pick_fail(J, 2, "anchor over no path or over more than 64 paths");
     // bounds of the sub-index in path coordinates
     std::vector<int64_t> &left = J.left, &right = J.right;
     left.assign(k, 0);
     right.assign(k, 0);
     for (int side = 0; side < 2; side++) {
-        PyObject *bound = side == 0 ? leftnode : rightnode;
-        if (bound == Py_None) {
+        const int id = J.bound_id[side];
+        if (id == -1) {
             for (size_t c = 0; c < k; c++) {
                 if (side == 0) left[c] = -1;
                 else {
-                    if (keys[c] < 0 || (size_t)keys[c] >= g->id2end->size()) { PyErr_SetString(PyExc_KeyError, "path without a length"); return -1; }
+                    if (keys[c] < 0 || (size_t)keys[c] >= g->id2end->size()) return pick_fail(J, 1, "path without a length");
                     right[c] = (*g->id2end)[keys[c]];
                 }
             }
             continue;
         }
-        int id = find_node(g, bound);
-        if (id < 0) return -1;
+        if (id < 0) {
+            J.err = 1;
+            J.err_bound = side;
+            return -1;
+        }
         const Node &nd = (*g->nodes)[id];
         for (size_t c = 0; c < k; c++) {
             bool found = false;
@@ -1030,7 +1074,7 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
                     found = true;
                     break;
                 }
-            if (!found) { PyErr_Format(PyExc_KeyError, "path %d does not run through the bounding node", (int)keys[c]); return -1; }
+            if (!found) return pick_fail(J, 1, "path %lld does not run through the bounding node", (long long)keys[c]);
         }
     }
     auto coord_of = [](const Rel &r, int32_t key) -> int64_t {
@@ -1077,6 +1121,27 @@ static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
     }
     PK_MARK(5)
     return 1;
+}
+// the error pick_build left in the job, as a Python exception (always returns -1)
+static int pick_raise(PickJob &J) {
+    if (J.err_bound >= 0 && J.bound_err[J.err_bound][0]) {
+        PyObject **e = J.bound_err[J.err_bound];
+        PyErr_Restore(e[0], e[1], e[2]);
+        e[0] = e[1] = e[2] = nullptr;
+    } else {
+        PyErr_SetString(J.err == 2 ? PyExc_ValueError : PyExc_KeyError, J.err_msg.c_str());
+    }
+    return -1;
+}
+static void pick_account(const PickJob &J) {
+    for (int i = 0; i < 6; i++) g_pk[i] += J.pk[i];
+}
+// 1: go on (run the recurrence if need_dp, then pick_finish); 0: the answer is the empty tuple; -1: error set
+static int pick_prepare(Graph *g, PyObject *list, PickJob &J) {
+    if (pick_parse(g, list, J) < 0) return -1;
+    const int st = pick_build(g, J);
+    pick_account(J);
+    return st < 0 ? pick_raise(J) : st;
 }
 
 static PyObject *pick_finish(Graph *g, PickJob &J) {
@@ -1268,6 +1333,90 @@ static bool chain_device_ready() {
     return true;
 }
 
+// ---- worker threads for the preparation of a frontier batch ---------------------------------------------------------------------
+// The picks of a batch are independent and their preparation (trim_overlap, path coordinates, the rows of the recurrence, the
+// short recurrences themselves) is plain C++ on private data plus reads of a graph that nobody writes meanwhile: the jobs are
+// dealt out to a small pool.  The calling thread keeps the GIL and works along; the workers never touch a Python object.
+// Threads: RV_REM_THREADS, else remcore.set_threads(n), else min(8, cores / 2); 1 = no pool.  The pool is made on first use and
+// never torn down (no joins at interpreter exit); a forked child starts without one.
+struct Pool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, done_cv;
+    std::function<void(size_t)> fn;
+    size_t n = 0, generation = 0;
+    std::atomic<size_t> next{0};
+    int active = 0;
+    void run() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            fn(i);
+        }
+    }
+    void worker() {
+        size_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return generation != seen; });
+            seen = generation;
+            lk.unlock();
+            run();
+            lk.lock();
+            if (--active == 0) done_cv.notify_one();
+        }
+    }
+    explicit Pool(int workers) {
+        for (int i = 0; i < workers; i++) th.emplace_back([this] { worker(); });
+    }
+    void parallel_for(size_t count, const std::function<void(size_t)> &f) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = f;
+            n = count;
+            next.store(0);
+            active = (int)th.size();
+            generation++;
+        }
+        cv.notify_all();
+        run();
+        std::unique_lock<std::mutex> lk(mu);
+        done_cv.wait(lk, [&] { return active == 0; });
+    }
+};
+static Pool *g_pool = nullptr;
+static long long g_pooled_calls = 0, g_pooled_jobs = 0;
+static int g_threads = 0;  // 0: not decided yet
+static void pool_after_fork() { g_pool = nullptr; }  // the child has none of the parent's threads (the old object is left alone)
+static int pool_threads() {
+    if (g_threads > 0) return g_threads;
+    int t = 0;
+    if (const char *e = getenv("RV_REM_THREADS")) t = atoi(e);
+    if (t <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        t = (int)(hw / 2);
+        if (t > 8) t = 8;
+    }
+    if (t < 1) t = 1;
+    g_threads = t;
+    return t;
+}
+static void for_each_job(size_t count, const std::function<void(size_t)> &f) {
+    const int t = pool_threads();
+    if (t <= 1 || count < 4) {
+        for (size_t i = 0; i < count; i++) f(i);
+        return;
+    }
+    if (!g_pool) {
+        static bool hooked = false;
+        if (!hooked) { pthread_atfork(nullptr, nullptr, pool_after_fork); hooked = true; }
+        g_pool = new Pool(t - 1);
+    }
+    g_pooled_calls++;
+    g_pooled_jobs += (long long)count;
+    g_pool->parallel_for(count, f);
+}
+
 // runs the recurrences of the prepared jobs: the long ones together on the device when that pays, the rest on the host
 static bool run_recurrences(std::vector<PickJob *> &jobs) {
     static const size_t SMALL = 48;          // rows below which a list is not worth a thread block
@@ -1320,18 +1469,21 @@ static bool run_recurrences(std::vector<PickJob *> &jobs) {
             g_chain.launches++;
         }
     }
+    std::vector<PickJob *> rest;
     for (PickJob *J : jobs)
-        if (J->need_dp) {
-            pick_dp_host(*J);
-            J->need_dp = false;
-            J->dp_done = true;
-            g_chain.host_lists++;
-        }
+        if (J->need_dp) rest.push_back(J);
+    for_each_job(rest.size(), [&](size_t i) {
+        pick_dp_host(*rest[i]);
+        rest[i]->need_dp = false;
+        rest[i]->dp_done = true;
+    });
+    g_chain.host_lists += (long long)rest.size();
     return true;
 }
 
 // front part of the mumpicker callback: 0 -> *result is the answer; 1 -> J is prepared (recurrence, then pick_finish); -1 error
-static int mumpicker_front(Graph *g, PyObject *mums, PyObject *idx, int precomputed, PyObject **result, PickJob &J) {
+// defer_build: only the Python half of the preparation (pick_parse) is done here; the caller runs pick_build for its whole batch
+static int mumpicker_front(Graph *g, PyObject *mums, PyObject *idx, int precomputed, PyObject **result, PickJob &J, bool defer_build = false) {
     *result = nullptr;
     const Py_ssize_t n = PyObject_Length(mums);
     if (n < 0) return -1;
@@ -1367,7 +1519,7 @@ static int mumpicker_front(Graph *g, PyObject *mums, PyObject *idx, int precompu
         J.wscore = g->pk_wscore;
         J.wpen = g->pk_wpen;
         J.seedsize = g->pk_seedsize;
-        st = pick_prepare(g, mums, J);
+        st = defer_build ? pick_parse(g, mums, J) : pick_prepare(g, mums, J);
         if (st == 0) { *result = PyTuple_New(0); if (!*result) st = -1; }
     }
     Py_XDECREF(ns);
@@ -1414,9 +1566,32 @@ static PyObject *Graph_mumpicker_batch(Graph *g, PyObject *args, PyObject *kwds)
         PyObject *mums, *idx;
         int precomputed = 0;
         if (!PyArg_ParseTuple(e, "OO|p", &mums, &idx, &precomputed)) { ok = false; break; }
-        state[(size_t)i] = mumpicker_front(g, mums, idx, precomputed, &results[(size_t)i], jobs[(size_t)i]);
+        state[(size_t)i] = mumpicker_front(g, mums, idx, precomputed, &results[(size_t)i], jobs[(size_t)i], true);
         if (state[(size_t)i] < 0) ok = false;
         else if (state[(size_t)i] == 1) pending.push_back(&jobs[(size_t)i]);
+    }
+    if (ok) {  // the C++ half of every preparation, side by side
+        std::vector<int> built(pending.size(), 0);
+        for_each_job(pending.size(), [&](size_t j) { built[j] = pick_build(g, *pending[j]); });
+        std::vector<PickJob *> go;
+        size_t j = 0;
+        for (Py_ssize_t i = 0; i < n; i++) {
+            if (state[(size_t)i] != 1) continue;
+            PickJob &J = jobs[(size_t)i];
+            pick_account(J);
+            const int st = built[j++];
+            if (st < 0) {
+                if (ok) pick_raise(J);  // the first failure is the one reported
+                ok = false;
+            } else if (st == 0) {
+                state[(size_t)i] = 0;
+                results[(size_t)i] = PyTuple_New(0);
+                if (!results[(size_t)i]) ok = false;
+            } else {
+                go.push_back(&J);
+            }
+        }
+        pending.swap(go);
     }
     if (ok) ok = run_recurrences(pending);
     PyObject *out = ok ? PyList_New(n) : nullptr;
@@ -1493,9 +1668,19 @@ static PyObject *mod_pick_phases(PyObject *, PyObject *) {
     return Py_BuildValue("{s:d,s:d,s:d,s:d,s:d,s:d}", "parse", g_pk[0], "filter_trim", g_pk[1], "sort", g_pk[2], "lookup", g_pk[3], "origin", g_pk[4], "rows", g_pk[5]);
 }
 static PyObject *mod_chain_stats(PyObject *, PyObject *) {
-    return Py_BuildValue("{s:O,s:L,s:L,s:L}", "device", g_chain.ready ? Py_True : Py_False, "device_lists", g_chain.device_lists, "host_lists", g_chain.host_lists,
-                         "launches", g_chain.launches);
+    return Py_BuildValue("{s:O,s:L,s:L,s:L,s:i,s:L,s:L}", "device", g_chain.ready ? Py_True : Py_False, "device_lists", g_chain.device_lists, "host_lists",
+                         g_chain.host_lists, "launches", g_chain.launches, "threads", pool_threads(), "pooled_calls", g_pooled_calls, "pooled_jobs", g_pooled_jobs);
 }
+// set_threads(n) -> previous setting: threads that prepare the picks of a frontier batch (1: the calling thread alone; 0: decide
+// again from RV_REM_THREADS / the core count).  A pool that exists keeps its size.
+static PyObject *mod_set_threads(PyObject *, PyObject *args) {
+    int n = 0;
+    if (!PyArg_ParseTuple(args, "i", &n)) return nullptr;
+    const int before = g_threads;
+    g_threads = n < 0 ? 0 : (n > 64 ? 64 : n);
+    return PyLong_FromLong(before);
+}
+
 static PyObject *mod_set_chain_library(PyObject *, PyObject *args) {
     const char *path;
     if (!PyArg_ParseTuple(args, "s", &path)) return nullptr;
@@ -1512,6 +1697,7 @@ static PyObject *mod_set_chain_library(PyObject *, PyObject *args) {
 static PyMethodDef module_methods[] = {
     {"pick_phases", mod_pick_phases, METH_NOARGS, "seconds this process spent in the phases of the mumpicker's preparation (diagnostics)"},
     {"chain_stats", mod_chain_stats, METH_NOARGS, "where the chaining recurrences of this process ran: lists on the device / on the host, device launches"},
+    {"set_threads", mod_set_threads, METH_VARARGS, "set_threads(n) -> previous: threads preparing the picks of a frontier batch (1 = none besides the caller, 0 = default)"},
     {"_set_chain_library", mod_set_chain_library, METH_VARARGS, "test hook: the C-ABI library rv_chain_batch is taken from (the emulated kernels)"},
     {nullptr, nullptr, 0, nullptr}};
 
