@@ -1342,11 +1342,17 @@ static bool chain_device_ready() {
 struct Pool {
     std::vector<std::thread> th;
     std::mutex mu;
-    std::condition_variable cv, done_cv;
+    std::condition_variable cv;
     std::function<void(size_t)> fn;
-    size_t n = 0, generation = 0;
-    std::atomic<size_t> next{0};
-    int active = 0;
+    size_t n = 0;
+    std::atomic<size_t> generation{0}, next{0};
+    std::atomic<int> inside{0};          // workers between "may I" and "done"
+    std::atomic<bool> accepting{false};  // the job description (fn, n) is valid and there may be jobs left
+    static void relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
     void run() {
         for (;;) {
             const size_t i = next.fetch_add(1);
@@ -1354,16 +1360,29 @@ struct Pool {
             fn(i);
         }
     }
+    // The calls of a recursion come a few milliseconds apart and in pairs (preparation, then the short recurrences): a worker
+    // that has just finished keeps looking for the next call for a while (a futex wake-up costs more than the work of a small
+    // batch) and only then goes to sleep.
     void worker() {
         size_t seen = 0;
         for (;;) {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return generation != seen; });
-            seen = generation;
-            lk.unlock();
-            run();
-            lk.lock();
-            if (--active == 0) done_cv.notify_one();
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spin = 0;; spin++) {
+                if (generation.load(std::memory_order_acquire) != seen) { got = true; break; }
+                relax();
+                if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(600)) break;
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen; });
+            }
+            seen = generation.load(std::memory_order_acquire);
+            // A worker that wakes up late must not hold the caller back, nor read a job description that is being replaced:
+            // it announces itself, then asks; the caller closes the call first and waits for the announced ones only.
+            inside.fetch_add(1);
+            if (accepting.load()) run();
+            inside.fetch_sub(1);
         }
     }
     explicit Pool(int workers) {
@@ -1375,13 +1394,13 @@ struct Pool {
             fn = f;
             n = count;
             next.store(0);
-            active = (int)th.size();
-            generation++;
+            accepting.store(true);
+            generation.fetch_add(1);
         }
         cv.notify_all();
-        run();
-        std::unique_lock<std::mutex> lk(mu);
-        done_cv.wait(lk, [&] { return active == 0; });
+        run();                     // returns when every job has been claimed
+        accepting.store(false);
+        while (inside.load() != 0) relax();  // the claimed ones are being finished: short jobs, no sleeping here
     }
 };
 static Pool *g_pool = nullptr;
