@@ -1102,7 +1102,7 @@ def align_genomes(args, index_module=None, shard=None):
             extra.update(shard_rank=rem.shard[0], shard_world=rem.shard[1])
             if not os.environ.get("RV_REM_THREADS") and hasattr(_remcore, "set_threads"):
                 # the ranks of one box share its cores: the pick threads of a rank (remcore's pool) are cut accordingly
-                _remcore.set_threads(max(1, min(8, (os.cpu_count() or 2) // 2 // rem.shard[1])))
+                _remcore.set_threads(max(1, min(4, (os.cpu_count() or 2) // 2 // rem.shard[1])))
         idx.align(mumpicker, graphalign, threads=args.threads, wpen=args.wpen, wscore=args.wscore, minl=args.minlength, minn=args.minn, **extra)
     align_genomes.last_shard_stats = rem.shard_stats
     return rem.G, idx
