@@ -170,14 +170,36 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_text_kernel(TextKeySrc src
     for (int i = threadIdx.x; i < plan.npass * RS_BINS; i += RS_THREADS) sh[i] = 0;
     __syncthreads();
     const i64 stride = (i64)gridDim.x * RS_THREADS * TK_PER;
+    int byte_digits = plan.npass == 3 || plan.npass == 4 ? plan.npass : 0;  // npass if digit p is byte p of the key
+    for (int p = 0; p < plan.npass; p++)
+        if (plan.shift[p] != 8 * p || plan.mask[p] != 0xffu) byte_digits = 0;
     for (i64 i0 = ((i64)blockIdx.x * RS_THREADS + threadIdx.x) * TK_PER; i0 < src.n; i0 += stride) {
         if (sizeof(KeyT) == 4 && KeyBlock4::fits(src, i0)) {
             KeyBlock4 kb;
             kb.load(src.T + i0, s_code);
+            if (byte_digits == 3) {  // the digits are the bytes of the key (12- and 16-mers of DNA): no plan look-ups, no loop
 #pragma unroll
-            for (int j = 0; j < TK_PER; j++) {
-                const u32 key = kb.key(j, src.k);
-                for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * RS_BINS + ((key >> plan.shift[p]) & plan.mask[p])], 1u);
+                for (int j = 0; j < TK_PER; j++) {
+                    const u32 key = kb.key(j, src.k);
+                    atomicAdd(&sh[key & 0xffu], 1u);
+                    atomicAdd(&sh[RS_BINS + ((key >> 8) & 0xffu)], 1u);
+                    atomicAdd(&sh[2 * RS_BINS + ((key >> 16) & 0xffu)], 1u);
+                }
+            } else if (byte_digits == 4) {
+#pragma unroll
+                for (int j = 0; j < TK_PER; j++) {
+                    const u32 key = kb.key(j, src.k);
+                    atomicAdd(&sh[key & 0xffu], 1u);
+                    atomicAdd(&sh[RS_BINS + ((key >> 8) & 0xffu)], 1u);
+                    atomicAdd(&sh[2 * RS_BINS + ((key >> 16) & 0xffu)], 1u);
+                    atomicAdd(&sh[3 * RS_BINS + (key >> 24)], 1u);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TK_PER; j++) {
+                    const u32 key = kb.key(j, src.k);
+                    for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * RS_BINS + ((key >> plan.shift[p]) & plan.mask[p])], 1u);
+                }
             }
             continue;
         }
