@@ -457,7 +457,10 @@ int radix_sort_pairs(Stream &st, KeyT *k0, KeyT *k1, u32 *v0, u32 *v1, i64 n, co
     u32 *status = ticket + 32;
     size_t zero_bytes = (size_t)(2 * RS_MAXPASS * RS_BINS + 32) * 4 + (size_t)plan.npass * tiles * RS_BINS * 4;
     RV_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, st.s));
-    int hist_blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+#ifndef RV_HIST_BPS
+#define RV_HIST_BPS 8   // blocks per SM of the (grid-stride) histogram kernels (measured at C2: 5 = one resident wave and 10 are 0.5 % slower)
+#endif
+    int hist_blocks = (int)(tiles < 148 * RV_HIST_BPS ? tiles : 148 * RV_HIST_BPS);
     TextKeySrc none;
     memset(&none, 0, sizeof none);
     if (text) {

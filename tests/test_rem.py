@@ -505,3 +505,34 @@ def test_rem_batched_picks_with_device_chaining_emulated(emu_reveallib, tmp_path
         assert after["device"] and after["device_lists"] > before["device_lists"] and after["launches"] > before["launches"]
     finally:
         remcore._set_chain_library("")   # back to the library next to the module
+
+
+def test_rem_pick_pool_emulated(emu_reveallib, tmp_path):
+    """The C++ half of the picks of a frontier batch on remcore's thread pool (set_threads): the golden graphs with one thread
+    and with three, the pool really used, and a forked child (which has none of the parent's threads) still working."""
+    from reveal_b200 import remcore
+    prev = remcore.set_threads(1)
+    try:
+        for threads in (1, 3):
+            remcore.set_threads(threads)
+            before = remcore.chain_stats()
+            for name in ("synth2_4k", "synth3_3k"):
+                d = tmp_path / ("%s_t%d" % (name, threads))
+                d.mkdir()
+                run_case(name, d, emu_reveallib.mod32)
+            after = remcore.chain_stats()
+            assert after["threads"] == threads
+            assert (after["pooled_calls"] > before["pooled_calls"]) == (threads > 1)
+        pid = os.fork()
+        if pid == 0:   # the child: same module state, no worker threads
+            code = 1
+            try:
+                d = tmp_path / "child"
+                d.mkdir()
+                run_case("synth2_4k", d, emu_reveallib.mod32)
+                code = 0
+            finally:
+                os._exit(code)
+        assert os.waitpid(pid, 0)[1] == 0
+    finally:
+        remcore.set_threads(prev)
