@@ -19,5 +19,5 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rs_pass_kernel -s 12 -c 2 -f -o gpurun_out/prof_rs_pass_kernel \
     python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_rs_pass_kernel.log 2>&1; echo "ncu rs_pass exit $?"
 scripts/gpu_check.sh sanitize
-timeout 500 python scripts/gpu_fuzz.py 60 3 > gpurun_out/fuzz_3.json 2> gpurun_out/fuzz_3.err; echo "fuzz exit $?"; cat gpurun_out/fuzz_3.json
+timeout 500 python scripts/gpu_fuzz.py ${FUZZ_SECONDS:-60} ${FUZZ_SEED:-3} > gpurun_out/fuzz_${FUZZ_SEED:-3}.json 2> gpurun_out/fuzz_${FUZZ_SEED:-3}.err; echo "fuzz exit $?"; cat gpurun_out/fuzz_${FUZZ_SEED:-3}.json
 for w in c2 c3 real c4; do python scripts/bench_brief.py gpurun_out/bench_$w.json; done
