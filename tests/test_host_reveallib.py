@@ -198,3 +198,20 @@ def test_copy_is_independent(emu_reveallib):
     assert b.getmultimums(3, 2) == a.getmultimums(3, 2)
     del a
     assert len(b.getmultimums(3, 2)) > 0
+
+
+def test_addsequence_copies_big_sequences_in_parts(emu_reveallib):
+    """A sequence of 2 MB and more is copied into the text buffer on several threads (copy_big): the text that comes back is the
+    text that went in, whatever the lengths are relative to the part size, and the returned intervals are the reference's."""
+    rng = np.random.default_rng(9)
+    al = np.frombuffer(b"ACGTN", np.uint8)
+    idx = emu_reveallib.index()
+    want, at = [], 0
+    for k, ln in enumerate([(1 << 21) - 1, 1 << 21, (1 << 21) + 4097, 3 * (1 << 20) + 11, 5]):
+        s = al[rng.integers(0, 5, size=ln)].tobytes().decode()
+        idx.addsample("s%d" % k)
+        assert idx.addsequence(s) == (at, at + ln)
+        want.append(s)
+        at += ln + 1
+    assert idx.n == at
+    assert idx.T == "$".join(want) + "$"
