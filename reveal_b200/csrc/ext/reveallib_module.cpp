@@ -90,7 +90,10 @@ static void copy_big(char *dst, const char *src, size_t len) {
     static const size_t MIN_BIG = (size_t)1 << 21;
     static const unsigned cores = std::thread::hardware_concurrency();
     static const int forced = getenv("RV_TEXT_COPY_THREADS") ? atoi(getenv("RV_TEXT_COPY_THREADS")) : 0;  // 1..4 (measurements)
-    const size_t parts = len < MIN_BIG ? 1 : (forced >= 1 && forced <= 4 ? (size_t)forced : (cores < 4 ? 1 : (cores >= 8 ? 4 : 2)));
+    // the processes of one box (one per GPU under torchrun) share its cores: a process takes its share, at most four threads
+    static const int local_world = getenv("LOCAL_WORLD_SIZE") && atoi(getenv("LOCAL_WORLD_SIZE")) > 0 ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1;
+    static const unsigned share = cores / (2u * (unsigned)local_world);
+    const size_t parts = len < MIN_BIG ? 1 : (forced >= 1 && forced <= 4 ? (size_t)forced : (share >= 4 ? 4 : (share >= 2 ? 2 : 1)));
     if (parts == 1) {
         memcpy(dst, src, len);
         return;
