@@ -640,8 +640,8 @@ sa_place_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sa, i64 n
         if (sizeof(KeyT) == 4 && key_digits2 > 0) {
             // Neighbouring groups differ inside their keys.  With 2-bit digits and every rare symbol a barrier symbol, the equal
             // leading digits of the two keys ARE the common prefix, provided no '$'/'N' (and not the end of the text) lies within
-            // those symbols of either suffix -- two key loads and two looks at the cache-resident bitmap level instead of a
-            // comparison on the text.
+            // those symbols of either suffix -- the leading zeros of key XOR previous key, kept by this lane since the staging, and
+            // two looks at the cache-resident bitmap level instead of a comparison on the text.
             const u32 lk = (((u32)(keyclz >> (6 * (f >> 5))) & 63u) - (u32)(32 - 2 * key_digits2)) >> 1;  // f = 32 r + lane: this lane staged the slot
             if (a + lk + 1u <= n32 && b + lk + 1u <= n32 && first_barrier(bars, a, lk + 1u) == lk + 1u && first_barrier(bars, b, lk + 1u) == lk + 1u) {
                 LCP[s + f] = (int)lk;
