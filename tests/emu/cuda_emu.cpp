@@ -10,6 +10,54 @@ State &S() { return g_state; }
 
 static const size_t kStack = 256 * 1024;
 
+#if RV_EMU_ASM_SWITCH
+// emu_switch(from, to): saves the callee-saved registers of the running fiber on its stack and its stack pointer in *from,
+// then resumes the fiber whose stack pointer is in *to (System V x86-64; no signal mask, no floating-point environment).
+extern "C" void emu_switch(FiberCtx *from, FiberCtx *to);
+asm(R"(
+.text
+.globl emu_switch
+.hidden emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+static inline void switch_to(FiberCtx *from, FiberCtx *to) { emu_switch(from, to); }
+// a fresh fiber: its first resumption "returns" into entry() with the stack aligned as after a call
+static void prepare(FiberCtx &ctx, char *stack, size_t bytes, void (*entry)()) {
+    uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+    void **sp = (void **)top;
+    *--sp = nullptr;          // the return address entry() would see (it never returns)
+    *--sp = (void *)entry;    // popped by emu_switch's ret
+    for (int i = 0; i < 6; i++) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
+    ctx.sp = (void *)sp;
+}
+#else
+static inline void switch_to(FiberCtx *from, FiberCtx *to) { swapcontext(from, to); }
+static void prepare(FiberCtx &ctx, char *stack, size_t bytes, void (*entry)()) {
+    getcontext(&ctx);
+    ctx.uc_stack.ss_sp = stack;
+    ctx.uc_stack.ss_size = bytes;
+    ctx.uc_link = nullptr;
+    makecontext(&ctx, entry, 0);
+}
+#endif
+
 void die(const char *msg) {
     State &s = S();
     fprintf(stderr, "[cuda_emu] FATAL in kernel %s block %u thread %u: %s\n", s.kname, s.b_idx.x, s.t_idx.x, msg);
@@ -19,7 +67,7 @@ void die(const char *msg) {
 void yield() {
     State &s = S();
     Fiber &f = s.fibers[s.cur];
-    swapcontext(&f.ctx, &s.sched);
+    switch_to(&f.ctx, &s.sched);
 }
 
 static void fiber_entry() {
@@ -34,7 +82,8 @@ static void fiber_entry() {
         s.bar_arrived = 0;
         s.bar_gen++;
     }
-    swapcontext(&f.ctx, &s.sched);
+    switch_to(&f.ctx, &s.sched);
+    abort();  // a finished fiber is never resumed
 }
 
 void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
@@ -68,11 +117,7 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
         for (auto &w : s.warps) { w.arrived = 0; }
         for (int t = 0; t < nt; t++) {
             Fiber &f = s.fibers[t];
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack;
-            f.ctx.uc_stack.ss_size = kStack;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+            prepare(f.ctx, f.stack, kStack, fiber_entry);
             f.done = false;
             f.tid = uint3{(unsigned)t, 0, 0};
         }
@@ -84,7 +129,7 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
                 if (f.done) continue;
                 s.cur = t;
                 s.t_idx = f.tid;
-                swapcontext(&s.sched, &f.ctx);
+                switch_to(&s.sched, &f.ctx);
             }
             if (s.progress == last_progress) {
                 if (++idle_rounds > 4) {

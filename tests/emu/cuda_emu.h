@@ -55,8 +55,18 @@ struct WarpState {
     unsigned long long slot[32];
 };
 
+// Context of a fiber.  x86-64: the stack pointer of a suspended fiber (callee-saved registers on its stack, emu_switch in
+// cuda_emu.cpp) -- swapcontext makes a signal-mask system call per switch, a third of the emulator's run time; elsewhere ucontext.
+#if defined(__x86_64__)
+#define RV_EMU_ASM_SWITCH 1
+struct FiberCtx { void *sp = nullptr; };
+#else
+#define RV_EMU_ASM_SWITCH 0
+typedef ucontext_t FiberCtx;
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    FiberCtx ctx;
     char *stack = nullptr;
     bool done = true;
     uint3 tid;
@@ -65,7 +75,7 @@ struct Fiber {
 struct State {
     uint3 t_idx{0, 0, 0}, b_idx{0, 0, 0};
     dim3 b_dim, g_dim;
-    ucontext_t sched;
+    FiberCtx sched;
     std::vector<Fiber> fibers;
     std::vector<WarpState> warps;
     int cur = -1;

@@ -83,7 +83,7 @@ def test_rc_with_empty_first_sample_is_refused(emu_lib):
         NativeIndex(emu_lib, T, nsep, 2, rc=1)
 
 
-@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("seed", range(6))
 def test_fuzz_emulated_dna_with_rare_symbols(emu_lib, seed):
     """The `mid` leg of scripts/gpu_fuzz.py scaled down to emulator sizes: related DNA genomes with repeats, tandem arrays, N runs,
     stray IUPAC letters and many contigs -- the texts whose keys are 2-bit digits with rare symbols ending them (KeyBlock4 and
@@ -94,6 +94,6 @@ def test_fuzz_emulated_dna_with_rare_symbols(emu_lib, seed):
     spec = importlib.util.spec_from_file_location("gpu_fuzz", os.path.join(os.path.dirname(here), "scripts", "gpu_fuzz.py"))
     Z = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(Z)
-    Z.SCALE = 0.01
-    for trial in range(3):
+    Z.SCALE = 0.02
+    for trial in range(4):
         Z.leg_mid(emu_lib, np.random.default_rng(4200 + 10 * seed + trial))

@@ -508,30 +508,33 @@ def test_rem_batched_picks_with_device_chaining_emulated(emu_reveallib, tmp_path
 
 
 def test_rem_pick_pool_emulated(emu_reveallib, tmp_path):
-    """The C++ half of the picks of a frontier batch on remcore's thread pool (set_threads): the golden graphs with one thread
-    and with three, the pool really used, and a forked child (which has none of the parent's threads) still working."""
+    """The C++ half of the picks of a frontier batch on remcore's thread pool (set_threads): the golden graph with three threads
+    (the other emulated cases pin it with the default), the pool really used, and a forked child (which has none of the parent's
+    threads) making its own."""
     from reveal_b200 import remcore
-    prev = remcore.set_threads(1)
+    prev = remcore.set_threads(3)
     try:
-        for threads in (1, 3):
-            remcore.set_threads(threads)
-            before = remcore.chain_stats()
-            for name in (("synth2_4k",) if threads == 1 else ("synth2_4k", "synth3_3k")):
-                d = tmp_path / ("%s_t%d" % (name, threads))
-                d.mkdir()
-                run_case(name, d, emu_reveallib.mod32)
-            after = remcore.chain_stats()
-            assert after["threads"] == threads
-            assert (after["pooled_calls"] > before["pooled_calls"]) == (threads > 1)
+        before = remcore.chain_stats()
+        d = tmp_path / "t3"
+        d.mkdir()
+        run_case("synth2_4k", d, emu_reveallib.mod32)
+        after = remcore.chain_stats()
+        assert after["threads"] == 3 and after["pooled_calls"] > before["pooled_calls"]
+        remcore.set_threads(1)
+        before = remcore.chain_stats()
+        d = tmp_path / "t1"
+        d.mkdir()
+        run_case("t1_t2", d, emu_reveallib.mod32)
+        assert remcore.chain_stats()["pooled_calls"] == before["pooled_calls"]
         pid = os.fork()
         if pid == 0:   # the child: same module state, no worker threads
             code = 1
             try:
+                remcore.set_threads(2)
                 d = tmp_path / "child"
                 d.mkdir()
-                remcore.set_threads(2)
                 run_case("synth2_4k", d, emu_reveallib.mod32)
-                code = 0
+                code = 0 if remcore.chain_stats()["pooled_calls"] > after["pooled_calls"] else 2
             finally:
                 os._exit(code)
         assert os.waitpid(pid, 0)[1] == 0
