@@ -85,3 +85,19 @@ def test_emu_sweeps_between_rebuilds(emu_lib):
 
 def test_emu_pack_into_peer_block(emu_lib):
     check_pack_block(emu_lib)
+
+
+@pytest.mark.parametrize("ngenomes,length", [(2, 40000), (5, 15000)])
+def test_emu_dna_at_three_digit_passes(emu_lib, ngenomes, length):
+    """Synthetic genomes large enough for 12-mer keys (n > 65 536): three byte-wide digit passes, the DNA key block (two 128-bit text
+    loads, 2-bit packed window) in the histogram kernel and the first pass, the byte-digit histogram -- the configuration of
+    BASELINE configs[1] -- with N runs and stray IUPAC letters as rare symbols; arrays and sweeps against the oracle."""
+    from reveal_b200 import synth
+    rng = np.random.default_rng(17 + ngenomes)
+    gs = [np.array(g) for g in synth.genomes(ngenomes, length, seed=31 + ngenomes, snp=0.01, indel=0.001)]
+    for g in gs:
+        at = int(rng.integers(100, length - 200))
+        g[at:at + int(rng.integers(1, 40))] = ord("N")
+        g[rng.integers(0, len(g), size=3)] = np.frombuffer(b"RYK", np.uint8)
+    T, nsep = synth.concat([[g] for g in gs])
+    check_against_oracle(emu_lib, T, nsep, ngenomes, minl=12, minn=2)
